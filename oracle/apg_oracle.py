@@ -1,0 +1,429 @@
+"""CPU oracle for the batched differentiable rollout (policy -> dynamics x horizon -> loss -> gradient).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this file.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` use it,
+and there only as the checker / the timed CPU arm -- never as a code path of the product.
+
+It is an independent closed-form restatement, in plain PyTorch (CPU, fp32 or fp64), of the reference
+functions on the hot path.  Every function cites the reference file:line it follows
+(paths relative to the reference checkout).  Gradients come from ``torch.autograd`` on these restated ops.
+
+Pinning: ``oracle/make_golden.py`` runs the *unmodified reference code* (imported from /root/reference with
+stubbed optional deps) on the known-answer inputs KAT-1..6 of SURVEY.md section 8c plus seeded random cases
+and freezes its outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks this oracle against
+those vectors.  The reference's autoregressive / LSTM train steps cannot run ``backward()`` (in-place
+aliasing at scripts/train_drone.py:138-142), so for those two modes only the *forward* (loss, actions,
+states) is pinned against the reference; the gradient oracle there is autograd on the functional
+restatement below whose forward is pinned ("cumulative" window semantics).
+"""
+import math
+
+import torch
+
+# --------------------------------------------------------------------------------------------
+# physical constants (neural_control/dynamics/config_quad.json, config_fixed_wing.json,
+# config_cartpole.json + overrides at cartpole_dynamics.py:34-36)
+# --------------------------------------------------------------------------------------------
+QUAD_CFG = dict(
+    mass=0.723, arm_length=0.31, frame_inertia=(4.5, 4.5, 7.0), kinv_ang_vel_tau=(16.6, 16.6, 5.0),
+    gravity=(0.0, 0.0, -9.81), rotational_drag=(0.0, 0.0, 0.0), translational_drag=(0.0, 0.0, 0.0),
+)
+WING_CFG = dict(
+    mass=1.01, I_xx=0.04766, I_yy=0.05005, I_zz=0.09558, I_xz=-0.00105, rho=1.225, S=0.276, c=0.185,
+    b=1.54, g=9.81, CL0=0.39, CL_alpha=4.5321, CL_q=0.318, CL_del_e=0.527, CD0=0.0765, CD_alpha=0.3346,
+    CD_q=0.354, CD_del_e=0.004, CY0=0.0, CY_beta=-0.033, CY_p=-0.1, CY_r=0.039, CY_del_a=0.0,
+    CY_del_r=0.225, Cl0=0.0, Cl_beta=-0.081, Cl_p=-0.529, Cl_r=0.159, Cl_del_a=-0.453, Cl_del_r=0.005,
+    Cm0=0.02, Cm_alpha=-1.4037, Cm_q=-0.1324, Cm_del_e=-0.4236, Cn0=0.0, Cn_beta=0.189, Cn_p=-0.083,
+    Cn_r=-0.948, Cn_del_a=-0.041, Cn_del_r=-0.077, epsilon=0.16534698176788384,
+)
+CARTPOLE_CFG = dict(masscart=1.0, masspole=0.1, length=0.5, max_force_mag=30.0, friction=0.5)
+ALPHA_BOUND = float(10.0 / 180.0 * math.pi)  # fixed_wing_dynamics.py:10
+
+# fixed normalisation of the wing state (neural_control/dataset.py:284-300)
+WING_MEAN = (0.0, 0.0, 0.0, 11.525899887084961, -0.00016766408225521445, 0.16617104411125183,
+             0.007394296582788229, 0.018172707409, 0.020353179425001144, -0.0005361468647606671,
+             0.01662314310669899, 0.004487641621381044)
+WING_STD = (16.626325607299805, 0.8449159860610962, 0.8879243731498718, 0.6243225932121277,
+            0.28072822093963623, 0.29176747798, 0.04499124363064766, 0.10370047390460968, 0.049977313727,
+            0.06449887901544571, 0.27508440613746643, 0.05634994804859)
+
+
+def _cols(x):
+    return [x[:, i] for i in range(x.shape[1])]
+
+
+# --------------------------------------------------------------------------------------------
+# A7  quadrotor step  (dynamics/quad_dynamics_flightmare.py:128-216, quad_dynamics_base.py:59-127)
+# --------------------------------------------------------------------------------------------
+def quad_inertia(cfg=QUAD_CFG):
+    """J = m/12 * l^2 * frame_inertia  (quad_dynamics_base.py:32-35)."""
+    s = cfg["mass"] / 12.0 * cfg["arm_length"] ** 2
+    return tuple(s * f for f in cfg["frame_inertia"])
+
+
+def quad_step(state, action, dt, cfg=QUAD_CFG):
+    """state (N,12) = [pos, euler rpy, vel world, body rates]; action (N,4) in [0,1]."""
+    px, py, pz, roll, pitch, yaw, vx, vy, vz, wx, wy, wz = _cols(state)
+    a0, a1, a2, a3 = _cols(action)
+    dt_ = float(dt)
+    Jx, Jy, Jz = quad_inertia(cfg)
+    Kx, Ky, Kz = cfg["kinv_ang_vel_tau"]
+    gx, gy, gz = cfg["gravity"]
+    tdx, tdy, tdz = cfg["translational_drag"]
+    rdx, rdy, rdz = cfg["rotational_drag"]
+    m = cfg["mass"]
+
+    thrust = a0 * 15 - 7.5 + 9.81                                   # :139
+    brx, bry, brz = a1 - 0.5, a2 - 0.5, a3 - 0.5                     # :140
+    # c = w x (J w)                                                  # :146-149
+    jwx, jwy, jwz = Jx * wx, Jy * wy, Jz * wz
+    cx = wy * jwz - wz * jwy
+    cy = wz * jwx - wx * jwz
+    cz = wx * jwy - wy * jwx
+    # desired torque = J K (br - w) + c + rot_drag                   # :95-117
+    tx = Jx * (Kx * (brx - wx)) + cx + rdx
+    ty = Jy * (Ky * (bry - wy)) + cy + rdy
+    tz = Jz * (Kz * (brz - wz)) + cz + rdz
+    force = m * thrust                                               # :101
+    # acceleration = 1/m * R_body_to_world [0,0,force] + g + drag    # :74-93
+    Cy, Sy = torch.cos(yaw), torch.sin(yaw)
+    Cp, Sp = torch.cos(pitch), torch.sin(pitch)
+    Cr, Sr = torch.cos(roll), torch.sin(roll)
+    f_over_m = (1.0 / m) * force
+    ax = f_over_m * (Cy * Sp * Cr + Sr * Sy) + gx + tdx
+    ay = f_over_m * (Cr * Sy * Sp - Cy * Sr) + gy + tdy
+    az = f_over_m * (Cr * Cp) + gz + tdz
+    # position uses 0.5*dt*vel (reference quirk, :172-174)
+    npx = px + 0.5 * dt_ * dt_ * ax + 0.5 * dt_ * vx
+    npy = py + 0.5 * dt_ * dt_ * ay + 0.5 * dt_ * vy
+    npz = pz + 0.5 * dt_ * dt_ * az + 0.5 * dt_ * vz
+    nvx, nvy, nvz = vx + dt_ * ax, vy + dt_ * ay, vz + dt_ * az     # :175
+    # angular acceleration = J^-1 (tau - c)                          # :178-183
+    nwx = wx + dt_ * ((tx - cx) / Jx)
+    nwy = wy + dt_ * ((ty - cy) / Jy)
+    nwz = wz + dt_ * ((tz - cz) / Jz)
+    # attitude integrates the OLD body rates through E(att)         # :210, base :96-127
+    er = wx - Sp * wz
+    ep = Cr * wy + Cp * Sr * wz
+    ey = -Sr * wy + Cp * Cr * wz
+    nroll, npitch, nyaw = roll + dt_ * er, pitch + dt_ * ep, yaw + dt_ * ey
+    return torch.stack((npx, npy, npz, nroll, npitch, nyaw, nvx, nvy, nvz, nwx, nwy, nwz), dim=1)
+
+
+def world_to_body_rows(att):
+    """Rows of the world->body matrix (quad_dynamics_base.py:59-94)."""
+    roll, pitch, yaw = att[:, 0], att[:, 1], att[:, 2]
+    Cy, Sy = torch.cos(yaw), torch.sin(yaw)
+    Cp, Sp = torch.cos(pitch), torch.sin(pitch)
+    Cr, Sr = torch.cos(roll), torch.sin(roll)
+    r0 = (Cy * Cp, Sy * Cp, -Sp)
+    r1 = (Cy * Sp * Sr - Cr * Sy, Cr * Cy + Sr * Sy * Sp, Cp * Sr)
+    r2 = (Cy * Sp * Cr + Sr * Sy, Cr * Sy * Sp - Cy * Sr, Cr * Cp)
+    return r0, r1, r2
+
+
+# A4  per-step featurizer (neural_control/dataset.py:207-220, 146-153)
+def state_preprocessing(state):
+    """(N,12) -> (N,15): [vel(3), W00,W01,W10,W11,W20,W21, W.vel(3), body rates(3)]."""
+    vel = state[:, 6:9]
+    r0, r1, r2 = world_to_body_rows(state[:, 3:6])
+    vb = [r[0] * vel[:, 0] + r[1] * vel[:, 1] + r[2] * vel[:, 2] for r in (r0, r1, r2)]
+    feats = [vel[:, 0], vel[:, 1], vel[:, 2], r0[0], r0[1], r1[0], r1[1], r2[0], r2[1],
+             vb[0], vb[1], vb[2], state[:, 9], state[:, 10], state[:, 11]]
+    return torch.stack(feats, dim=1)
+
+
+# --------------------------------------------------------------------------------------------
+# A8  fixed-wing step (dynamics/fixed_wing_dynamics.py:98-267)
+# --------------------------------------------------------------------------------------------
+def wing_step(state, action, dt, cfg=WING_CFG):
+    """state (N,12) = [pos NED, vel body uvw, euler phi/theta/psi, body rates pqr]."""
+    x, y, z, u, v, w, phi, theta, psi, p, q, r = _cols(state)
+    a0, a1, a2, a3 = _cols(action)
+    pi = math.pi
+    T = a0 * 7                                                        # :41-46
+    del_e = pi * (a1 * 40 - 20) / 180
+    del_a = pi * (a2 * 5 - 2.5) / 180
+    del_r = pi * (a3 * 40 - 20) / 180
+    g_m = cfg["g"] * cfg["mass"]
+
+    V = torch.sqrt(u ** 2 + v ** 2 + w ** 2)                          # :129
+    alpha = torch.clamp(torch.arctan(w / u), -ALPHA_BOUND, ALPHA_BOUND)   # :130-131
+    beta = torch.clamp(torch.arctan(v / V), -ALPHA_BOUND, ALPHA_BOUND)    # :132-133
+    c2v = cfg["c"] / (2 * V)
+    b2v = cfg["b"] / (2 * V)
+    CL = cfg["CL0"] + cfg["CL_alpha"] * alpha + cfg["CL_q"] * c2v * q + cfg["CL_del_e"] * del_e
+    CD = cfg["CD0"] + cfg["CD_alpha"] * alpha + cfg["CD_q"] * c2v * q + cfg["CD_del_e"] * del_e
+    CY = (cfg["CY0"] + cfg["CY_beta"] * beta + cfg["CY_p"] * b2v * p + cfg["CY_r"] * b2v * r
+          + cfg["CY_del_a"] * del_a + cfg["CY_del_r"] * del_r)
+    Cl = (cfg["Cl0"] + cfg["Cl_beta"] * beta + cfg["Cl_p"] * b2v * p + cfg["Cl_r"] * b2v * r
+          + cfg["Cl_del_a"] * del_a + cfg["Cl_del_r"] * del_r)
+    Cm = cfg["Cm0"] + cfg["Cm_alpha"] * alpha + cfg["Cm_q"] * c2v * q + cfg["Cm_del_e"] * del_e
+    Cn = (cfg["Cn0"] + cfg["Cn_beta"] * beta + cfg["Cn_p"] * b2v * p + cfg["Cn_r"] * b2v * r
+          + cfg["Cn_del_a"] * del_a + cfg["Cn_del_r"] * del_r)
+    qS = 0.5 * cfg["rho"] * V ** 2 * cfg["S"]
+    L, D, Y = qS * CL, qS * CD, qS * CY
+    # all three moments are scaled by the chord c (reference quirk, :170-175)
+    l_m, m_m, n_m = qS * cfg["c"] * Cl, qS * cfg["c"] * Cm, qS * cfg["c"] * Cn
+
+    sa, ca, sb, cb = torch.sin(alpha), torch.cos(alpha), torch.sin(beta), torch.cos(beta)
+    sph, cph, sth, cth = torch.sin(phi), torch.cos(phi), torch.sin(theta), torch.cos(theta)
+    sps, cps = torch.sin(psi), torch.cos(psi)
+    # f = R_bw [-D, Y, -L] + R(phi,theta,0) [0,0,g m] + [T cos eps, 0, T sin eps]   (:185-204)
+    fx = ca * cb * (-D) + (-ca * sb) * Y + (-sa) * (-L) + (-sth) * g_m + T * math.cos(cfg["epsilon"])
+    fy = sb * (-D) + cb * Y + (sph * cth) * g_m
+    fz = sa * cb * (-D) + (-sa * sb) * Y + ca * (-L) + (cph * cth) * g_m + T * math.sin(cfg["epsilon"])
+    # pos_dot = R_ib(phi,theta,psi) uvw   (:213-216, 65-93)
+    xd = cth * cps * u + (-cph * sps + sph * sth * cps) * v + (sph * sps + cph * sth * cps) * w
+    yd = cth * sps * u + (cph * cps + sph * sth * sps) * v + (-sph * cps + cph * sth * sps) * w
+    zd = -sth * u + sph * cth * v + cph * cth * w
+    # uvw_dot = f/m - omega x vel   (:220-221)
+    inv_m = 1.0 / cfg["mass"]
+    ud = inv_m * fx - (q * w - r * v)
+    vd = inv_m * fy - (r * u - p * w)
+    wd = inv_m * fz - (p * v - q * u)
+    # euler-angle kinematics (:225-245)
+    tth = torch.tan(theta)
+    phid = p + sph * tth * q + cph * tth * r
+    thetad = cph * q - sph * r
+    psid = (sph / cth) * q + (cph / cth) * r
+    # omega_dot = I^-1 (M - omega x I omega), I with -I_xz off-diagonals (:33-39, 250-255)
+    Ixx, Iyy, Izz, off = cfg["I_xx"], cfg["I_yy"], cfg["I_zz"], -cfg["I_xz"]
+    Iw_x = Ixx * p + off * r
+    Iw_y = Iyy * q
+    Iw_z = off * p + Izz * r
+    rx = l_m - (q * Iw_z - r * Iw_y)
+    ry = m_m - (r * Iw_x - p * Iw_z)
+    rz = n_m - (p * Iw_y - q * Iw_x)
+    det = Ixx * Izz - off * off
+    pd = (Izz * rx - off * rz) / det
+    qd = ry / Iyy
+    rd = (-off * rx + Ixx * rz) / det
+    dt_ = float(dt)
+    dot = torch.stack((xd, yd, zd, ud, vd, wd, phid, thetad, psid, pd, qd, rd), dim=1)
+    return state + dt_ * dot                                           # :265
+
+
+# --------------------------------------------------------------------------------------------
+# A9  cartpole step (dynamics/cartpole_dynamics.py:53-119)
+# --------------------------------------------------------------------------------------------
+def cartpole_step(state, action, dt, cfg=CARTPOLE_CFG):
+    """state (N,4) = [x, xdot, theta, thetadot]; action (N,1) in [-1,1]."""
+    gravity = 9.81
+    total_mass = cfg["masspole"] + cfg["masscart"]
+    pml = cfg["masspole"] * cfg["length"]
+    fr = cfg["friction"]
+    x, xdot, th, thdot = _cols(state)
+    force = action[:, 0] * cfg["max_force_mag"] * 0.5                  # :60
+    s, c = torch.sin(th), torch.cos(th)
+    xacc = (-2 * pml * thdot ** 2 * s + 3 * cfg["masspole"] * gravity * s * c + 4 * force
+            - 4 * fr * xdot) / (4 * total_mass - 3 * cfg["masspole"] * c ** 2)          # :86-97
+    thacc = (-3 * pml * thdot ** 2 * s * c + 6 * total_mass * gravity * s
+             + 6 * (force - fr * xdot) * c) / (4 * cfg["length"] * total_mass - 3 * pml * c ** 2)  # :99-111
+    dt_ = float(dt)
+    sd, cd = torch.sin(thdot * dt_), torch.cos(thdot * dt_)           # :113-119
+    new_s = s * cd + c * sd
+    new_c = c * cd - s * sd
+    return torch.stack((x + xdot * dt_, xdot + xacc * dt_, torch.atan2(new_s, new_c),
+                        thdot + thacc * dt_), dim=1)
+
+
+STEP_FN = {"quad": quad_step, "wing": wing_step, "cartpole": cartpole_step}
+
+
+# --------------------------------------------------------------------------------------------
+# A10-A12 losses (neural_control/drone_loss.py:12-39, 72-82, 136-145); sums, not means
+# --------------------------------------------------------------------------------------------
+def quad_mpc_loss(states, ref, actions):
+    pos = ((states[:, :, 0:3] - ref[:, :, 0:3]) ** 2).sum()
+    vel = ((states[:, :, 6:9] - ref[:, :, 6:9]) ** 2).sum()
+    av = (states[:, :, 9:12] ** 2).sum()
+    thr = ((actions[:, :, 0] - 0.5) ** 2).sum()
+    rates = ((actions[:, :, 1:4] - 0.5) ** 2).sum()
+    return 10 * pos + 1 * vel + 0.1 * av + 0.1 * rates + 5 * thr
+
+
+def fixed_wing_mpc_loss(states, lin_ref, actions):
+    return 10 * ((states[:, :, 0:3] - lin_ref) ** 2).sum() + 0.1 * ((actions[:, :, 1:4] - 0.5) ** 2).sum()
+
+
+def cartpole_loss_mpc(states, ref, actions):
+    wts = torch.tensor([0.0, 3.0, 10.0, 1.0], dtype=states.dtype)
+    return (((states - ref) ** 2) * wts).sum() + 0.01 * (actions ** 2).sum()
+
+
+def cartpole_make_reference(cur, h):
+    """scripts/train_cartpole.py:103-110: ref[:,k] = cur*(1-k/(h-1)) for k<h-1, last row 0; no grad."""
+    ref = torch.zeros(cur.shape[0], h, cur.shape[1], dtype=cur.dtype)
+    for k in range(h - 1):
+        ref[:, k] = cur.detach() * (1 - 1 / (h - 1) * k)
+    return ref
+
+
+LOSS_FN = {"quad": quad_mpc_loss, "wing": fixed_wing_mpc_loss, "cartpole": cartpole_loss_mpc}
+
+
+# --------------------------------------------------------------------------------------------
+# A1-A3 policies.  ``params`` is the list of tensors in net.parameters() order, torch layouts:
+#   hutter : states_in.{w,b}, conv_ref.{w,b}, ref_in.{w,b}, fc1, fc2, fc3, fc_out      (14 tensors)
+#   lstm   : conv_ref.{w,b}, ref_in.{w,b}, fc_out.{w,b}, lstm.{w_ih,w_hh,b_ih,b_hh}    (10 tensors)
+#   simple : fc0, fc1, fc2, fc3, fc_out                                               (10 tensors)
+# --------------------------------------------------------------------------------------------
+def _conv_encoder(ref, w, b):
+    """Conv1d(ref_dim->20,k=3,valid) over the horizon axis + relu, flattened channel-major
+    (index c*(h-2)+t)  (models/hutter_model.py:36-40)."""
+    n, h, d = ref.shape
+    cols = torch.stack([ref[:, t:t + 3, :] for t in range(h - 2)], dim=1)   # (N, h-2, 3, d): [j, ch]
+    # out[n,t,c] = b[c] + sum_{ch,j} w[c,ch,j] * ref[n,t+j,ch]
+    out = torch.einsum("ntjd,cdj->ntc", cols, w) + b
+    return torch.relu(out).transpose(1, 2).reshape(n, -1)
+
+
+def hutter_forward(params, state, ref, conv=True):
+    """models/hutter_model.py:32-49 (logits; the caller applies sigmoid)."""
+    ws, bs, wc, bc, wr, br, w1, b1, w2, b2, w3, b3, wo, bo = params
+    s = torch.tanh(state @ ws.t() + bs)
+    if conv:
+        r = _conv_encoder(ref, wc, bc)
+    else:
+        r = torch.tanh(ref.reshape(ref.shape[0], -1) @ wr.t() + br)
+    x = torch.cat((s, r), dim=1)
+    x = torch.tanh(x @ w1.t() + b1)
+    x = torch.tanh(x @ w2.t() + b2)
+    x = torch.tanh(x @ w3.t() + b3)
+    return x @ wo.t() + bo
+
+
+def lstm_forward(params, state, ref, hc):
+    """models/rnn.py:34-50: conv encoder -> LSTMCell(175,8) (gate order i,f,g,o) -> Linear(8,out)."""
+    wc, bc, wr, br, wo, bo, w_ih, w_hh, b_ih, b_hh = params
+    h_prev, c_prev = hc
+    x = torch.cat((state, _conv_encoder(ref, wc, bc)), dim=1)
+    gates = x @ w_ih.t() + b_ih + h_prev @ w_hh.t() + b_hh
+    i, f, g, o = gates.chunk(4, dim=1)
+    c_new = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(g)
+    h_new = torch.sigmoid(o) * torch.tanh(c_new)
+    return h_new @ wo.t() + bo, (h_new, c_new)
+
+
+def simple_forward(params, x):
+    """models/simple_model.py:20-28: column 0 zeroed, tanh on every layer including the output."""
+    x = torch.cat((torch.zeros_like(x[:, :1]), x[:, 1:]), dim=1)
+    for i in range(0, 10, 2):
+        x = torch.tanh(x @ params[i].t() + params[i + 1])
+    return x
+
+
+# --------------------------------------------------------------------------------------------
+# A6 concurrent rollouts (scripts/train_drone.py:175-203, train_fixed_wing.py:90-116,
+#    train_cartpole.py:118-155, train_base.py:202-206)
+# --------------------------------------------------------------------------------------------
+def rollout_concurrent(system, params, in_state, cur, in_ref, ref, h, dt):
+    """Returns (loss, states (N,h,S), actions (N,h,A))."""
+    if system == "quad":
+        act = torch.sigmoid(hutter_forward(params, in_state, in_ref, conv=True)).reshape(-1, h, 4)
+    elif system == "wing":
+        act = torch.sigmoid(hutter_forward(params, in_state, in_ref, conv=False)).reshape(-1, h, 4)
+    elif system == "cartpole":
+        act = simple_forward(params, in_state).reshape(-1, h, 1)
+        ref = cartpole_make_reference(cur, h)
+    else:
+        raise ValueError(system)
+    step = STEP_FN[system]
+    states = []
+    s = cur
+    for k in range(h):
+        s = step(s, act[:, k], dt)
+        states.append(s)
+    states = torch.stack(states, dim=1)
+    return LOSS_FN[system](states, ref, act), states, act
+
+
+# --------------------------------------------------------------------------------------------
+# A5 autoregressive / LSTM rollouts (scripts/train_drone.py:113-173), functional restatement
+# --------------------------------------------------------------------------------------------
+def recurrent_window(in_ref0, k, h, pos_hist, window):
+    """Window of h reference rows seen by the policy at step k.
+
+    cumulative (the reference's actual forward semantics, caused by the in-place write into the shared
+    (N,2h,9) buffer at train_drone.py:138-142): row j = k+r holds
+        in_ref0[j,:3] - sum_{i=max(0,j-h+1)}^{k} pos_i
+    relative (documented intent): in_ref0[j,:3] - pos_k.   Columns 3:9 are never touched.
+    ``pos_hist`` = [pos_0 .. pos_k] (each (N,3)).
+    """
+    win = in_ref0[:, k:k + h]
+    if window == "relative":
+        sub = pos_hist[k][:, None, :].expand(-1, h, -1)
+    elif window == "cumulative":
+        rows = []
+        for r in range(h):
+            lo = max(0, k + r - h + 1)
+            acc = pos_hist[lo]
+            for i in range(lo + 1, k + 1):
+                acc = acc + pos_hist[i]
+            rows.append(acc)
+        sub = torch.stack(rows, dim=1)
+    else:
+        raise ValueError(window)
+    return torch.cat((win[:, :, :3] - sub, win[:, :, 3:]), dim=2)
+
+
+def rollout_recurrent(mode, params, cur, in_ref0, ref, h, dt, window="cumulative", hc0=None):
+    """Quadrotor only.  mode in {'autoregressive','lstm'}.  in_ref0, ref: (N,2h,9).
+    Returns (loss, states (N,h,12), actions (N,h,4))."""
+    s = cur
+    pos_hist, states, actions = [], [], []
+    hc = hc0
+    for k in range(h):
+        pos_hist.append(s[:, :3])
+        win = recurrent_window(in_ref0, k, h, pos_hist, window)
+        feat = state_preprocessing(s)
+        if mode == "autoregressive":
+            logits = hutter_forward(params, feat, win, conv=True)
+        elif mode == "lstm":
+            logits, hc = lstm_forward(params, feat, win, hc)
+        else:
+            raise ValueError(mode)
+        a = torch.sigmoid(logits)
+        s = quad_step(s, a, dt)
+        states.append(s)
+        actions.append(a)
+    states = torch.stack(states, dim=1)
+    actions = torch.stack(actions, dim=1)
+    return quad_mpc_loss(states, ref[:, :h], actions), states, actions
+
+
+# --------------------------------------------------------------------------------------------
+# value-and-gradient drivers
+# --------------------------------------------------------------------------------------------
+def value_and_grad(fn, params, *args, **kw):
+    """Runs ``fn(params, ...)`` -> (loss, states, actions) and back-propagates the loss.
+    Returns (loss, [grad or None per param], states, actions); unused params get None, exactly like
+    the reference leaves ``.grad`` None for ``ref_in`` (conv nets) / ``conv_ref`` (wing nets)."""
+    ps = [p.detach().clone().requires_grad_(True) for p in params]
+    loss, states, actions = fn(ps, *args, **kw)
+    grads = torch.autograd.grad(loss, ps, allow_unused=True)
+    return loss.detach(), list(grads), states.detach(), actions.detach()
+
+
+def concurrent_value_and_grad(system, params, in_state, cur, in_ref, ref, h, dt):
+    return value_and_grad(lambda ps: rollout_concurrent(system, ps, in_state, cur, in_ref, ref, h, dt), params)
+
+
+def recurrent_value_and_grad(mode, params, cur, in_ref0, ref, h, dt, window="cumulative", hc0=None):
+    return value_and_grad(
+        lambda ps: rollout_recurrent(mode, ps, cur, in_ref0, ref, h, dt, window=window, hc0=hc0), params)
+
+
+def sgd_momentum_step(params, grads, bufs, lr, momentum=0.9):
+    """A13: optim.SGD(lr, momentum=0.9) update (scripts/train_base.py:139-143); None grads are skipped."""
+    out_p, out_b = [], []
+    for p, g, b in zip(params, grads, bufs):
+        if g is None:
+            out_p.append(p)
+            out_b.append(b)
+            continue
+        nb = g.clone() if b is None else momentum * b + g
+        out_p.append(p - lr * nb)
+        out_b.append(nb)
+    return out_p, out_b

@@ -1,0 +1,388 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference code.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference checkout does not exist on the GPU box):
+
+    python oracle/make_golden.py [--ref /root/reference] [--out tests/golden]
+
+The reference is imported from its checkout with its optional third-party deps (casadi, gym, matplotlib,
+pyglet, pyquaternion, ruamel) stubbed in ``sys.modules`` (they are only touched at import / construction
+time on this path).  Everything saved here is an output of the reference's own functions/methods:
+
+  steps.npz        single dynamics steps: the ``__main__`` vectors of the three dynamics files (KAT-1/2/3,
+                   SURVEY.md 8c) + seeded random batches, with vector-Jacobian products from reference autograd
+  conc_*.npz       concurrent train steps through TrainDrone / TrainFixedWing.train_controller_model and the
+                   TrainCartpole.run_epoch body: loss, actions, states, all parameter gradients; both with the
+                   shipped trained_models (KAT-4/5/6) and with seeded default-initialised nets
+  rec_*.npz        autoregressive / LSTM forward through TrainDrone.train_recurrent_model (its backward()
+                   raises in the reference, so only loss/actions/states exist), plus state_preprocessing
+"""
+import argparse
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+
+
+def import_reference(ref_root):
+    for m in ['casadi', 'matplotlib', 'matplotlib.pyplot', 'matplotlib.animation', 'mpl_toolkits',
+              'mpl_toolkits.mplot3d', 'gym', 'gym.utils', 'gym.spaces', 'pyglet', 'pyglet.gl',
+              'pyquaternion', 'ruamel', 'ruamel.yaml']:
+        sys.modules[m] = MagicMock()
+
+    class _Env:
+        pass
+    sys.modules['gym'].Env = _Env
+    sys.path[:0] = [ref_root, os.path.join(ref_root, 'scripts')]
+
+
+def npify(d):
+    out = {}
+    for k, v in d.items():
+        if v is None:
+            continue
+        out[k] = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
+    args = ap.parse_args()
+    import_reference(args.ref)
+    os.makedirs(args.out, exist_ok=True)
+
+    import torch
+    from neural_control.drone_loss import quad_mpc_loss, fixed_wing_mpc_loss, cartpole_loss_mpc  # noqa: F401
+    torch.autograd.set_detect_anomaly(False)
+    from neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from neural_control.dynamics.fixed_wing_dynamics import FixedWingDynamics
+    from neural_control.dynamics.cartpole_dynamics import CartpoleDynamics
+    from neural_control.dataset import state_preprocessing
+    from neural_control.models.hutter_model import Net as HutterNet
+    from neural_control.models.rnn import LSTM_NEW
+    from neural_control.models.simple_model import Net as SimpleNet
+    import train_drone
+    import train_fixed_wing
+    import train_cartpole
+
+    quad, wing, cart = FlightmareDynamics(), FixedWingDynamics(), CartpoleDynamics()
+    f32 = torch.float32
+
+    # ------------------------------------------------------------------ single steps
+    steps = {}
+    kat1_state = torch.tensor([[-0.203302, -8.12219, 0.484883, -0.15613, -0.446313, 0.25728, -4.70952,
+                                0.627684, -2.506545, -0.039999, -0.200001, 0.1]], dtype=f32)
+    steps["kat1_state"] = kat1_state
+    steps["kat1_action"] = torch.tensor([[0.45, 0.46, 0.3, 0.6]], dtype=f32)
+    steps["kat1_out"] = quad(kat1_state, steps["kat1_action"], 0.05)
+    steps["kat1b_action"] = torch.tensor([[0.7, 0.9, 0.2, 0.35]], dtype=f32)
+    steps["kat1b_out"] = quad(kat1_state, steps["kat1b_action"], 0.1)
+    # fixed_wing_dynamics.py:496-504 __main__ vectors
+    kat2_state = torch.tensor([[0.6933, -0.8747, 0.9757, -0.8422, 0.5494, -1.1936, 0.0368, 0.8417,
+                                -0.9412, -1.4291, 0.4538, -0.5257]], dtype=f32)
+    kat2_action = torch.tensor([[-0.5518, -2.9553, 0.0311, -0.6691]], dtype=f32)
+    steps["kat2_state"], steps["kat2_action"] = kat2_state, kat2_action
+    steps["kat2_out"] = wing(kat2_state, kat2_action, 0.05)
+    kat2b_state = torch.zeros(1, 12, dtype=f32)
+    kat2b_state[0, 3], kat2b_state[0, 5], kat2b_state[0, 7], kat2b_state[0, 10] = 11.5, 0.3, 0.05, 0.02
+    steps["kat2b_state"] = kat2b_state
+    steps["kat2b_action"] = torch.tensor([[0.3, 0.55, 0.45, 0.6]], dtype=f32)
+    steps["kat2b_out"] = wing(kat2b_state, steps["kat2b_action"], 0.05)
+    steps["kat3_state"] = torch.tensor([[0.5, 1.3, 0.1, 0.4]], dtype=f32)
+    steps["kat3_action"] = torch.tensor([[0.4]], dtype=f32)
+    steps["kat3_out"] = cart(steps["kat3_state"], steps["kat3_action"], 0.02)
+
+    g = torch.Generator().manual_seed(20260925)
+    n = 16
+
+    def rnd(*shape, lo=-1.0, hi=1.0):
+        return torch.rand(*shape, generator=g, dtype=f32) * (hi - lo) + lo
+
+    # random quad states: moderate attitudes/velocities/rates
+    qs = torch.cat((rnd(n, 3, lo=-2, hi=2), rnd(n, 3, lo=-0.8, hi=0.8), rnd(n, 3, lo=-3, hi=3),
+                    rnd(n, 3, lo=-1, hi=1)), dim=1)
+    qa = rnd(n, 4, lo=0.02, hi=0.98)
+    ws = torch.zeros(n, 12, dtype=f32)
+    ws[:, :3] = rnd(n, 3, lo=-5, hi=5)
+    ws[:, 3] = 11.5 + rnd(n, lo=-1.5, hi=1.5)
+    ws[:, 4] = rnd(n, lo=-0.8, hi=0.8)
+    ws[:, 5] = rnd(n, lo=-1.0, hi=1.0)
+    ws[:, 6:9] = rnd(n, 3, lo=-0.3, hi=0.3)
+    ws[:, 9:12] = rnd(n, 3, lo=-0.3, hi=0.3)
+    # make a few rows exercise the alpha / beta clamps (|atan| > 10 deg)
+    ws[0, 5], ws[1, 5], ws[2, 4], ws[3, 4] = 3.5, -3.2, 3.0, -2.8
+    wa = rnd(n, 4, lo=0.02, hi=0.98)
+    cs = torch.stack((rnd(n, lo=-2.4, hi=2.4), rnd(n, lo=-1.5, hi=1.5), rnd(n, lo=-3.1, hi=3.1),
+                      rnd(n, lo=-1.5, hi=1.5)), dim=1)
+    ca = rnd(n, 1, lo=-1, hi=1)
+    for name, dyn, s0, a0, dt in (("quad", quad, qs, qa, 0.1), ("wing", wing, ws, wa, 0.05),
+                                  ("cartpole", cart, cs, ca, 0.05)):
+        s = s0.clone().requires_grad_(True)
+        a = a0.clone().requires_grad_(True)
+        out = dyn(s, a, dt)
+        cot = rnd(*out.shape)
+        gs, ga = torch.autograd.grad((out * cot).sum(), (s, a))
+        steps[f"rand_{name}_state"], steps[f"rand_{name}_action"] = s0, a0
+        steps[f"rand_{name}_dt"] = np.float64(dt)
+        steps[f"rand_{name}_out"], steps[f"rand_{name}_cot"] = out, cot
+        steps[f"rand_{name}_gstate"], steps[f"rand_{name}_gaction"] = gs, ga
+    # featurizer
+    fs = qs.clone().requires_grad_(True)
+    feat = state_preprocessing(fs)
+    fcot = rnd(*feat.shape)
+    steps["feat_state"], steps["feat_out"], steps["feat_cot"] = qs, feat, fcot
+    steps["feat_gstate"] = torch.autograd.grad((feat * fcot).sum(), fs)[0]
+    np.savez_compressed(os.path.join(args.out, "steps.npz"), **npify(steps))
+
+    # ------------------------------------------------------------------ concurrent train steps
+    class Recorder:
+        """wraps a dynamics object, recording the states it returns (detached copies)."""
+
+        def __init__(self, dyn):
+            self.dyn, self.states = dyn, []
+
+        def __call__(self, state, action, dt):
+            out = self.dyn(state, action, dt)
+            self.states.append(out.detach().clone())
+            return out
+
+    def grads_of(net):
+        return {f"grad_{i}": (p.grad.detach().clone() if p.grad is not None else None)
+                for i, (nm, p) in enumerate(net.named_parameters())}
+
+    def params_of(net):
+        d = {f"param_{i}": p.detach().clone() for i, (nm, p) in enumerate(net.named_parameters())}
+        d["param_names"] = np.array([nm for nm, _ in net.named_parameters()])
+        return d
+
+    def quad_inputs(cur, ref):
+        in_state = state_preprocessing(cur)
+        in_ref = torch.cat((ref[..., :3], ref[..., 6:9], ref[..., 6:9] - cur[:, None, 6:9]), dim=2)
+        return in_state, in_ref
+
+    def run_quad_conc(net, cur, ref, h, dt, tag):
+        in_state, in_ref = quad_inputs(cur, ref)
+        rec = Recorder(quad)
+        me = MagicMock()
+        me.horizon, me.state_size, me.action_dim, me.delta_t = h, 12, 4, dt
+        me.train_dynamics, me.net = rec, net
+        for p in net.parameters():
+            p.grad = None
+        actions = torch.sigmoid(net(in_state, in_ref))                      # train_base.py:202-206
+        action_seq = torch.reshape(actions, (-1, h, 4))
+        loss = train_drone.TrainDrone.train_controller_model(me, cur, action_seq, in_ref, ref)
+        d = dict(in_state=in_state, cur=cur, in_ref=in_ref, ref=ref, h=np.int64(h), dt=np.float64(dt),
+                 loss=loss.detach(), actions=action_seq.detach(), states=torch.stack(rec.states, dim=1))
+        d.update(params_of(net))
+        d.update(grads_of(net))
+        np.savez_compressed(os.path.join(args.out, f"conc_quad_{tag}.npz"), **npify(d))
+        print(f"conc_quad_{tag}: loss {loss.item():.6f}")
+
+    # KAT-4: shipped model
+    net = torch.load(os.path.join(args.ref, "trained_models/quad/current_model/model_quad"), weights_only=False)
+    cur = torch.cat((kat1_state, 0.5 * kat1_state), dim=0).clone()
+    cur[:, :3] = 0
+    kk = torch.arange(1, 11, dtype=f32)[None, :, None]
+    bb = torch.arange(1, 3, dtype=f32)[:, None, None]
+    ref = 0.01 * kk * bb * torch.arange(1, 10, dtype=f32)[None, None, :]
+    run_quad_conc(net, cur, ref, 10, 0.1, "kat4")
+
+    def synth_quad(nn_, L, dt, gen):
+        """polynomial references + drone states as in SURVEY.md 8d."""
+        def u(*shape, lo, hi):
+            return torch.rand(*shape, generator=gen, dtype=f32) * (hi - lo) + lo
+        c = torch.zeros(nn_, 3, 6, dtype=f32)
+        c[:, :, 1] = u(nn_, 3, lo=-1.5, hi=1.5)
+        for i in range(2, 6):
+            c[:, :, i] = u(nn_, 3, lo=-0.5, hi=0.5) / math.factorial(i)
+        t = (torch.arange(L, dtype=f32) + 1) * dt
+        pw = torch.stack([t ** i for i in range(6)], dim=0)                      # (6, L)
+        dpw = torch.stack([i * t ** max(i - 1, 0) if i > 0 else torch.zeros_like(t) for i in range(6)], dim=0)
+        pos = torch.einsum("nai,il->nla", c, pw)
+        vel = torch.einsum("nai,il->nla", c, dpw)
+        ref_ = torch.zeros(nn_, L, 9, dtype=f32)
+        ref_[:, :, 0:3], ref_[:, :, 6:9] = pos, vel
+        cur_ = torch.zeros(nn_, 12, dtype=f32)
+        cur_[:, 3:6] = u(nn_, 3, lo=-0.2, hi=0.2)
+        cur_[:, 6:9] = c[:, :, 1] + 0.3 * torch.randn(nn_, 3, generator=gen, dtype=f32)
+        return cur_, ref_
+
+    import math
+    g2 = torch.Generator().manual_seed(1234)
+    torch.manual_seed(0)
+    net = HutterNet(15, 10, 9, 40)
+    cur, ref = synth_quad(8, 10, 0.1, g2)
+    run_quad_conc(net, cur, ref, 10, 0.1, "rand")
+    torch.manual_seed(1)
+    net = HutterNet(15, 6, 9, 24)
+    cur, ref = synth_quad(5, 6, 0.1, g2)
+    cur[:, 9:12] = 0.3 * torch.randn(5, 3, generator=g2, dtype=f32)     # non-zero body rates too
+    run_quad_conc(net, cur, ref, 6, 0.1, "rand_h6")
+
+    # wing
+    from neural_control.dataset import WingDataset
+    wmean = torch.tensor([0.0, 0.0, 0.0, 11.525899887084961, -0.00016766408225521445, 0.16617104411125183,
+                          0.007394296582788229, 0.018172707409, 0.020353179425001144, -0.0005361468647606671,
+                          0.01662314310669899, 0.004487641621381044]).float()
+    wstd = torch.tensor([16.626325607299805, 0.8449159860610962, 0.8879243731498718, 0.6243225932121277,
+                         0.28072822093963623, 0.29176747798, 0.04499124363064766, 0.10370047390460968,
+                         0.049977313727, 0.06449887901544571, 0.27508440613746643, 0.05634994804859]).float()
+
+    def wing_inputs(cur, target, h, dt, mean, std):
+        """the arithmetic of WingDataset.prepare_data / _compute_target_pos, through the reference methods"""
+        ds = MagicMock()
+        ds.mean, ds.std, ds.dt, ds.horizon = mean, std, dt, h
+        ds._compute_target_pos = lambda cs_, rv: WingDataset._compute_target_pos(ds, cs_, rv)
+        return WingDataset.prepare_data(ds, cur.clone(), target.clone())
+
+    def run_wing_conc(net, cur, target, h, dt, mean, std, tag):
+        in_state, cur2, in_ref, ref_ = wing_inputs(cur, target, h, dt, mean, std)
+        rec = Recorder(wing)
+        me = MagicMock()
+        me.horizon, me.state_size, me.action_dim, me.delta_t_train = h, 12, 4, dt
+        me.train_dynamics, me.net = rec, net
+        for p in net.parameters():
+            p.grad = None
+        actions = torch.sigmoid(net(in_state, in_ref))
+        action_seq = torch.reshape(actions, (-1, h, 4))
+        loss = train_fixed_wing.TrainFixedWing.train_controller_model(me, cur2, action_seq, in_ref, ref_)
+        d = dict(in_state=in_state, cur=cur2, in_ref=in_ref, ref=ref_, h=np.int64(h), dt=np.float64(dt),
+                 loss=loss.detach(), actions=action_seq.detach(), states=torch.stack(rec.states, dim=1),
+                 target=target, mean=mean, std=std)
+        d.update(params_of(net))
+        d.update(grads_of(net))
+        np.savez_compressed(os.path.join(args.out, f"conc_wing_{tag}.npz"), **npify(d))
+        print(f"conc_wing_{tag}: loss {loss.item():.6f}")
+
+    import json
+    wcfg = json.load(open(os.path.join(args.ref, "trained_models/wing/current_model/config.json")))
+    net = torch.load(os.path.join(args.ref, "trained_models/wing/current_model/model_wing"), weights_only=False)
+    sw = kat2b_state[0]
+    cur = torch.stack((sw, sw * torch.tensor([1, 1, 1, 1.02, 1, .5, 1, -1, 1, 1, 2, 1], dtype=f32)), dim=0)
+    target = torch.tensor([[50.0, 3.0, -2.0], [50.0, -4.0, 1.0]], dtype=f32)
+    run_wing_conc(net, cur, target, 10, 0.05, torch.tensor(wcfg["mean"]).float(), torch.tensor(wcfg["std"]).float(),
+                  "kat5")
+
+    def synth_wing(nn_, gen):
+        def u(*shape, lo, hi):
+            return torch.rand(*shape, generator=gen, dtype=f32) * (hi - lo) + lo
+        cur_ = torch.zeros(nn_, 12, dtype=f32)
+        cur_[:, 3] = 11.5 + u(nn_, lo=-0.5, hi=0.5)
+        cur_[:, 5] = u(nn_, lo=-0.5, hi=0.5)
+        cur_[:, 7] = u(nn_, lo=-2, hi=2) * math.pi / 180
+        cur_[:, 10] = u(nn_, lo=-0.005, hi=0.005)
+        tgt = torch.stack((torch.full((nn_,), 50.0), u(nn_, lo=-5, hi=5), u(nn_, lo=-5, hi=5)), dim=1)
+        return cur_, tgt
+
+    torch.manual_seed(2)
+    net = HutterNet(9, 1, 3, 80, conv=False)
+    cur, target = synth_wing(8, g2)
+    run_wing_conc(net, cur, target, 20, 0.05, wmean, wstd, "rand_h20")
+
+    # cartpole: body of TrainCartpole.run_epoch (train_cartpole.py:118-165) through the real method
+    def run_cart_conc(net, states, h, dt, tag):
+        rec = Recorder(cart)
+        me = MagicMock()
+        me.horizon, me.state_size, me.action_dim, me.delta_t = h, 4, 1, dt
+        me.train_dynamics, me.net = rec, net
+        me.results_dict = {"trained": []}
+        in_state = states.clone()
+        cur_ = states.clone()
+        # two identical batches so that ``running_loss / i`` (i = last batch index) is defined
+        me.trainloader = [(in_state.clone(), cur_.clone()), (in_state.clone(), cur_.clone())]
+        me.make_reference = lambda cs_: train_cartpole.TrainCartpole.make_reference(me, cs_)
+        for p in net.parameters():
+            p.grad = None
+        grads, losses = [], []
+
+        class Opt:
+            def zero_grad(self_):
+                for p in net.parameters():
+                    p.grad = None
+
+            def step(self_):
+                grads.append([p.grad.detach().clone() for p in net.parameters()])
+        me.optimizer_controller = Opt()
+        me.loss_logging = lambda epoch_loss, train="controller": losses.append(epoch_loss)
+        epoch_loss = train_cartpole.TrainCartpole.run_epoch(me, train="controller")
+        # epoch_loss = (l0 + l1) / 1 with l0 == l1
+        loss = torch.tensor(epoch_loss / 2.0, dtype=f32)
+        act = net(states.clone()).reshape(-1, h, 1).detach()
+        d = dict(in_state=states, cur=states, h=np.int64(h), dt=np.float64(dt), loss=loss, actions=act,
+                 states=torch.stack(rec.states[:h], dim=1),
+                 ref=train_cartpole.TrainCartpole.make_reference(me, states))
+        d.update(params_of(net))
+        d.update({f"grad_{i}": gr for i, gr in enumerate(grads[0])})
+        np.savez_compressed(os.path.join(args.out, f"conc_cartpole_{tag}.npz"), **npify(d))
+        print(f"conc_cartpole_{tag}: loss {loss.item():.6f}")
+
+    net = torch.load(os.path.join(args.ref, "trained_models/cartpole/current_model/model_cartpole"),
+                     weights_only=False)
+    run_cart_conc(net, torch.tensor([[.5, 1.3, .1, .4], [-.2, .1, -.05, .3]], dtype=f32), 10, 0.05, "kat6")
+    torch.manual_seed(3)
+    net = SimpleNet(4, 5)
+    st = (torch.rand(128, 4, generator=g2, dtype=f32) * 2 - 1) * torch.tensor([2.4, 7.5, math.pi, 7.5])
+    st[:, 1] *= 0.2
+    st[:, 3] *= 0.2
+    run_cart_conc(net, st, 5, 0.05, "rand_b128_h5")
+
+    # ------------------------------------------------------------------ recurrent forward (AR / LSTM)
+    def run_rec(mode, net, cur, in_ref2, ref2, h, dt, tag):
+        rec = Recorder(quad)
+        me = MagicMock()
+        me.horizon, me.state_size, me.action_dim, me.delta_t = h, 12, 4, dt
+        me.train_dynamics, me.net, me.train_mode = rec, net, ("LSTM" if mode == "lstm" else "autoregressive")
+        hc0 = {}
+        if mode == "lstm":
+            orig_reset = net.reset_hidden_state
+
+            def reset(bs=1):
+                orig_reset(bs)
+                hc0["h0"], hc0["c0"] = net.hidden_state.clone(), net.cell_state.clone()
+            net.reset_hidden_state = reset
+        acts = []
+        orig_forward = net.forward
+
+        def fwd(a, b):
+            o = orig_forward(a, b)
+            acts.append(torch.sigmoid(o).detach().clone())
+            return o
+        net.forward = fwd
+        in_ref_buf = in_ref2.clone()           # the method mutates this buffer in place
+        orig_backward = torch.Tensor.backward
+        torch.Tensor.backward = lambda self, *a, **k: None   # reference backward() raises here
+        try:
+            with torch.no_grad():
+                loss = train_drone.TrainDrone.train_recurrent_model(me, None, cur.clone(), in_ref_buf, ref2)
+        finally:
+            torch.Tensor.backward = orig_backward
+            net.forward = orig_forward
+        d = dict(cur=cur, in_ref=in_ref2, ref=ref2, h=np.int64(h), dt=np.float64(dt), loss=loss.detach(),
+                 actions=torch.stack(acts, dim=1), states=torch.stack(rec.states, dim=1))
+        d.update(hc0)
+        d.update(params_of(net))
+        np.savez_compressed(os.path.join(args.out, f"rec_{tag}.npz"), **npify(d))
+        print(f"rec_{tag}: loss {loss.item():.6f}")
+
+    def rec_inputs(nn_, h, dt, gen):
+        cur_, ref2 = synth_quad(nn_, 2 * h, dt, gen)
+        in_ref2 = torch.cat((ref2[..., :3], ref2[..., 6:9], ref2[..., 6:9] - cur_[:, None, 6:9]), dim=2)
+        return cur_, in_ref2, ref2
+
+    torch.manual_seed(4)
+    net = HutterNet(15, 10, 9, 4)
+    cur, in_ref2, ref2 = rec_inputs(8, 10, 0.1, g2)
+    run_rec("autoregressive", net, cur, in_ref2, ref2, 10, 0.1, "ar_rand")
+    cur2 = cur.clone()
+    cur2[:, :3] = 0.2 * torch.randn(8, 3, generator=g2, dtype=f32)      # non-zero initial position
+    run_rec("autoregressive", net, cur2, in_ref2, ref2, 10, 0.1, "ar_rand_pos0")
+    torch.manual_seed(5)
+    net = LSTM_NEW(15, 10, 9, 4)
+    torch.manual_seed(6)
+    run_rec("lstm", net, cur, in_ref2, ref2, 10, 0.1, "lstm_rand")
+
+
+if __name__ == "__main__":
+    main()

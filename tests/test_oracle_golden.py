@@ -1,0 +1,141 @@
+"""The oracle (oracle/apg_oracle.py) against the golden vectors produced by the unmodified reference
+(oracle/make_golden.py -> tests/golden/*.npz).  CPU only.
+
+Tolerances (fp32 oracle vs fp32 reference; both are chains of fp32 ops in different association order):
+  single steps      : max abs error <= 2e-6 * scale
+  rollout loss      : rel <= 2e-6
+  rollout gradients : per-tensor L2 rel <= 2e-5
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import apg_oracle as O
+from tests.helpers import load_golden, golden_params, golden_grads, t, rel_err, max_rel_to_scale
+
+STEP_TOL = 2e-6
+LOSS_TOL = 2e-6
+GRAD_TOL = 2e-5
+
+
+def test_kat_single_steps():
+    g = load_golden("steps.npz")
+    for name, fn, dt in (("kat1", O.quad_step, 0.05), ("kat2", O.wing_step, 0.05), ("kat2b", O.wing_step, 0.05),
+                         ("kat3", O.cartpole_step, 0.02)):
+        out = fn(t(g[f"{name}_state"]), t(g[f"{name}_action"]), dt)
+        assert max_rel_to_scale(out, g[f"{name}_out"]) <= STEP_TOL, name
+    out = O.quad_step(t(g["kat1_state"]), t(g["kat1b_action"]), 0.1)
+    assert max_rel_to_scale(out, g["kat1b_out"]) <= STEP_TOL
+    # the literal values quoted in SURVEY.md 8c
+    np.testing.assert_allclose(g["kat1_out"][0, :3], [-0.32615805, -8.10602474, 0.42004830], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(g["kat3_out"][0], [0.52600002, 1.40573132, 0.10800000, 0.77437150], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,fn", [("quad", O.quad_step), ("wing", O.wing_step), ("cartpole", O.cartpole_step)])
+def test_random_steps_and_vjp(name, fn):
+    g = load_golden("steps.npz")
+    dt = float(g[f"rand_{name}_dt"])
+    s = t(g[f"rand_{name}_state"]).requires_grad_(True)
+    a = t(g[f"rand_{name}_action"]).requires_grad_(True)
+    out = fn(s, a, dt)
+    assert max_rel_to_scale(out, g[f"rand_{name}_out"]) <= STEP_TOL
+    gs, ga = torch.autograd.grad((out * t(g[f"rand_{name}_cot"])).sum(), (s, a))
+    assert max_rel_to_scale(gs, g[f"rand_{name}_gstate"]) <= 2e-5
+    assert max_rel_to_scale(ga, g[f"rand_{name}_gaction"]) <= 2e-5
+    # fp64 oracle agrees with the fp32 reference to fp32 precision as well
+    out64 = fn(t(g[f"rand_{name}_state"], torch.float64), t(g[f"rand_{name}_action"], torch.float64), dt)
+    assert max_rel_to_scale(out64, g[f"rand_{name}_out"]) <= 5e-6
+
+
+def test_state_preprocessing():
+    g = load_golden("steps.npz")
+    s = t(g["feat_state"]).requires_grad_(True)
+    feat = O.state_preprocessing(s)
+    assert max_rel_to_scale(feat, g["feat_out"]) <= STEP_TOL
+    gs = torch.autograd.grad((feat * t(g["feat_cot"])).sum(), s)[0]
+    assert max_rel_to_scale(gs, g["feat_gstate"]) <= 1e-5
+
+
+CONC = [("quad", "conc_quad_kat4.npz"), ("quad", "conc_quad_rand.npz"), ("quad", "conc_quad_rand_h6.npz"),
+        ("wing", "conc_wing_kat5.npz"), ("wing", "conc_wing_rand_h20.npz"),
+        ("cartpole", "conc_cartpole_kat6.npz"), ("cartpole", "conc_cartpole_rand_b128_h5.npz")]
+
+
+@pytest.mark.parametrize("system,fname", CONC)
+def test_concurrent_rollout(system, fname):
+    g = load_golden(fname)
+    params = golden_params(g)
+    h, dt = int(g["h"]), float(g["dt"])
+    in_ref = t(g["in_ref"]) if "in_ref" in g else None
+    loss, grads, states, actions = O.concurrent_value_and_grad(
+        system, params, t(g["in_state"]), t(g["cur"]), in_ref, t(g["ref"]), h, dt)
+    assert abs(float(loss) - float(g["loss"])) <= LOSS_TOL * abs(float(g["loss"])), (float(loss), float(g["loss"]))
+    assert max_rel_to_scale(actions, g["actions"]) <= 2e-6
+    assert max_rel_to_scale(states, g["states"]) <= 5e-6
+    ref_grads = golden_grads(g)
+    for i, (go, gr) in enumerate(zip(grads, ref_grads)):
+        if gr is None:
+            assert go is None, f"param {i} should have no gradient (unused by the reference forward)"
+        else:
+            assert rel_err(go, gr) <= GRAD_TOL, (i, rel_err(go, gr))
+
+
+def test_kat4_literal_values():
+    """the numbers quoted in SURVEY.md 8c for the shipped quad model"""
+    g = load_golden("conc_quad_kat4.npz")
+    assert abs(float(g["loss"]) - 1557.710938) < 2e-3
+    np.testing.assert_allclose(g["actions"][0, 0], [0.85247970, 0.26715422, 0.99926859, 0.09718276], atol=2e-6)
+    assert abs(np.linalg.norm(g["grad_6"]) - 2679.971191) < 0.05     # fc1.weight
+    assert "grad_4" not in g and "grad_5" not in g                    # ref_in.* unused -> None
+
+
+@pytest.mark.parametrize("mode,fname", [("autoregressive", "rec_ar_rand.npz"),
+                                        ("autoregressive", "rec_ar_rand_pos0.npz"), ("lstm", "rec_lstm_rand.npz")])
+def test_recurrent_forward_cumulative(mode, fname):
+    g = load_golden(fname)
+    params = golden_params(g)
+    h, dt = int(g["h"]), float(g["dt"])
+    hc0 = (t(g["h0"]), t(g["c0"])) if mode == "lstm" else None
+    loss, states, actions = O.rollout_recurrent(mode, params, t(g["cur"]), t(g["in_ref"]), t(g["ref"]), h, dt,
+                                                window="cumulative", hc0=hc0)
+    assert abs(float(loss) - float(g["loss"])) <= 5e-6 * abs(float(g["loss"]))
+    assert max_rel_to_scale(actions, g["actions"]) <= 1e-5
+    assert max_rel_to_scale(states, g["states"]) <= 1e-5
+    # the "relative" window is a different function (documented-intent variant)
+    loss_rel, _, _ = O.rollout_recurrent(mode, params, t(g["cur"]), t(g["in_ref"]), t(g["ref"]), h, dt,
+                                         window="relative", hc0=hc0)
+    assert abs(float(loss_rel) - float(g["loss"])) > 2e-5 * abs(float(g["loss"]))
+
+
+def test_recurrent_gradients_exist_and_match_fp64():
+    """No reference gradient exists for AR/LSTM (its backward raises); the gradient oracle is autograd on the
+    forward-pinned restatement.  Check fp32 vs fp64 self-consistency."""
+    g = load_golden("rec_ar_rand.npz")
+    h, dt = int(g["h"]), float(g["dt"])
+    l32, g32, _, _ = O.recurrent_value_and_grad("autoregressive", golden_params(g), t(g["cur"]), t(g["in_ref"]),
+                                                t(g["ref"]), h, dt)
+    d = torch.float64
+    l64, g64, _, _ = O.recurrent_value_and_grad("autoregressive", golden_params(g, d), t(g["cur"], d),
+                                                t(g["in_ref"], d), t(g["ref"], d), h, dt)
+    assert abs(float(l32) - float(l64)) <= 2e-6 * abs(float(l64))
+    for a, b in zip(g32, g64):
+        if b is None:
+            assert a is None
+        else:
+            assert rel_err(a, b) <= 5e-5
+
+
+def test_sgd_momentum_matches_torch():
+    torch.manual_seed(0)
+    p = [torch.randn(5, 3), torch.randn(7)]
+    mods = [torch.nn.Parameter(x.clone()) for x in p]
+    opt = torch.optim.SGD(mods, lr=1e-2, momentum=0.9)
+    bufs = [None, None]
+    for it in range(3):
+        grads = [torch.randn_like(x) for x in p]
+        for m, gr in zip(mods, grads):
+            m.grad = gr.clone()
+        opt.step()
+        p, bufs = O.sgd_momentum_step(p, grads, bufs, 1e-2)
+        for a, b in zip(p, mods):
+            assert torch.allclose(a, b.detach(), atol=1e-7)
