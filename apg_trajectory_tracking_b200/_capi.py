@@ -1,0 +1,64 @@
+"""ctypes binding of libapg_b200.so (include/apg_b200.h).  No CPU fallback: if the library is missing or there is
+no CUDA device the product path raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libapg_b200.so")
+MAX_PHYS = 48
+
+c_float_p = ctypes.c_void_p   # device / host pointers are passed as raw addresses
+
+
+class ApgConfig(ctypes.Structure):
+    _fields_ = [("system", ctypes.c_int), ("mode", ctypes.c_int), ("window", ctypes.c_int), ("net", ctypes.c_int),
+                ("n_drones", ctypes.c_int), ("horizon", ctypes.c_int), ("state_feat", ctypes.c_int),
+                ("ref_len", ctypes.c_int), ("ref_dim", ctypes.c_int), ("out_dim", ctypes.c_int),
+                ("dt", ctypes.c_float), ("phys", ctypes.c_float * MAX_PHYS)]
+
+
+EXPORTS = {
+    "apg_version": (ctypes.c_int, []),
+    "apg_sm_count": (ctypes.c_int, []),
+    "apg_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "apg_num_params": (ctypes.c_int, [ctypes.POINTER(ApgConfig)]),
+    "apg_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ApgConfig)]),
+    "apg_rollout_forward": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p] +
+                            [c_float_p] * 3 + [ctypes.c_void_p]),
+    "apg_rollout_backward": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p,
+                             ctypes.c_float, c_float_p, ctypes.c_void_p]),
+    "apg_rollout_value_and_grad_host": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 8),
+    "apg_dynamics_step": (ctypes.c_int, [ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_int,
+                                         c_float_p, ctypes.c_void_p]),
+    "apg_dynamics_step_adjoint": (ctypes.c_int, [ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_float,
+                                                 ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
+    "apg_quad_features": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "apg_quad_features_adjoint": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class ApgError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built: `python -m apg_trajectory_tracking_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ApgError(f"{LIB_PATH} is missing: build the CUDA extension with "
+                           "`python -m apg_trajectory_tracking_b200.build` (there is no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        msg = lib().apg_error_string(code)
+        raise ApgError(f"apg_b200 call failed ({code}): {msg.decode() if msg else '?'}")

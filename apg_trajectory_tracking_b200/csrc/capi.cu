@@ -1,0 +1,309 @@
+// extern "C" boundary of libapg_b200.so (declared in include/apg_b200.h).  Plain pointers and sizes only.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/apg_b200.h"
+#include "kernels.h"
+
+using namespace apg;
+
+namespace {
+
+int g_sm_count = -1;
+
+int sm_count() {
+  if (g_sm_count < 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    g_sm_count = n;
+  }
+  return g_sm_count;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t up256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int state_dim(int system) { return system == SYS_CARTPOLE ? 4 : 12; }
+int action_dim(int system) { return system == SYS_CARTPOLE ? 1 : 4; }
+
+bool is_hutter(const apg_config* c) { return c->net == NET_HUTTER_CONV || c->net == NET_HUTTER_LIN; }
+
+int check_config(const apg_config* c) {
+  if (!c) return APG_ERR_BAD_CONFIG;
+  if (c->n_drones <= 0 || c->horizon <= 0 || c->horizon > 64) return APG_ERR_BAD_CONFIG;
+  if (c->system < 0 || c->system > 2 || c->mode < 0 || c->mode > 2) return APG_ERR_BAD_CONFIG;
+  if (is_hutter(c)) {
+    if (c->mode != MODE_CONCURRENT) return APG_ERR_UNSUPPORTED;
+    if (c->out_dim != action_dim(c->system) * c->horizon) return APG_ERR_BAD_CONFIG;
+    if (c->net == NET_HUTTER_CONV) {
+      if (c->system != SYS_QUAD) return APG_ERR_UNSUPPORTED;
+      if (c->ref_len < 3 || c->ref_len > 11 || 3 * c->ref_dim > 32) return APG_ERR_BAD_CONFIG;
+    } else {
+      if (c->system != SYS_WING) return APG_ERR_UNSUPPORTED;
+      if (c->ref_len * c->ref_dim > 32) return APG_ERR_BAD_CONFIG;
+    }
+    if (c->state_feat < 1 || c->state_feat > 32) return APG_ERR_BAD_CONFIG;
+    return 0;
+  }
+  return APG_ERR_UNSUPPORTED;
+}
+
+HutterLayout hutter_layout(const apg_config* c) {
+  return make_hutter_layout(c->state_feat, c->ref_len, c->ref_dim, c->out_dim, c->net == NET_HUTTER_CONV);
+}
+
+void add_seg(PackTable& t, int which, int mode, int src, int dst, int rows, int cols, int ldd) {
+  PackSeg& s = t.seg[t.n++];
+  s.which = which; s.mode = mode; s.src = src; s.dst = dst; s.rows = rows; s.cols = cols; s.ldd = ldd;
+}
+
+PackTable hutter_pack_table(const HutterLayout& y) {
+  PackTable t;
+  t.n = 0;
+  // forward: [in][out]
+  add_seg(t, 0, PK_TRANSPOSE, y.t_ws, y.f_ws, HID, y.F0, HID);
+  add_seg(t, 0, PK_COPY_PAD, y.t_bs, y.f_bs, 1, HID, HID);
+  if (y.conv) {
+    add_seg(t, 0, PK_CONV_FWD, y.t_wc, y.f_wr, CONV_CH, y.KC, CONV_CH);
+    add_seg(t, 0, PK_COPY_PAD, y.t_bc, y.f_br, 1, CONV_CH, CONV_CH);
+  } else {
+    add_seg(t, 0, PK_TRANSPOSE, y.t_wr, y.f_wr, HID, y.LR, HID);
+    add_seg(t, 0, PK_COPY_PAD, y.t_br, y.f_br, 1, HID, HID);
+  }
+  add_seg(t, 0, PK_TRANSPOSE, y.t_w1, y.f_w1, HID, y.K1, HID);
+  add_seg(t, 0, PK_COPY_PAD, y.t_b1, y.f_b1, 1, HID, HID);
+  add_seg(t, 0, PK_TRANSPOSE, y.t_w2, y.f_w2, HID, HID, HID);
+  add_seg(t, 0, PK_COPY_PAD, y.t_b2, y.f_b2, 1, HID, HID);
+  add_seg(t, 0, PK_TRANSPOSE, y.t_w3, y.f_w3, HID, HID, HID);
+  add_seg(t, 0, PK_COPY_PAD, y.t_b3, y.f_b3, 1, HID, HID);
+  add_seg(t, 0, PK_TRANSPOSE, y.t_wo, y.f_wo, y.Mo, HID, y.Mo4);
+  add_seg(t, 0, PK_COPY_PAD, y.t_bo, y.f_bo, 1, y.Mo, y.Mo4);
+  // backward: [out][in]
+  add_seg(t, 1, PK_COPY_PAD, y.t_wo, y.b_wo, y.Mo, HID, HID);
+  add_seg(t, 1, PK_COPY_PAD, y.t_w3, y.b_w3, HID, HID, HID);
+  add_seg(t, 1, PK_COPY_PAD, y.t_w2, y.b_w2, HID, HID, HID);
+  add_seg(t, 1, PK_COPY_PAD, y.t_w1, y.b_w1, HID, y.K1, y.K1);
+  add_seg(t, 1, PK_COPY_PAD, y.t_ws, y.b_ws, HID, y.F0, y.ld_bws);
+  if (y.conv) add_seg(t, 1, PK_CONV_BWD, y.t_wc, y.b_wr, CONV_CH, y.KC, y.ld_bwr);
+  else        add_seg(t, 1, PK_COPY_PAD, y.t_wr, y.b_wr, HID, y.LR, y.ld_bwr);
+  return t;
+}
+
+struct Plan {
+  int grid, ntiles;
+  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, total;
+};
+
+Plan make_plan(const apg_config* c, const HutterLayout& y) {
+  Plan p;
+  p.ntiles = (c->n_drones + TM - 1) / TM;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  p.grid = p.ntiles < sms ? p.ntiles : sms;
+  const int S = state_dim(c->system);
+  size_t o = 0;
+  p.o_wf = o;     o += up256(sizeof(float) * y.f_total);
+  p.o_wb = o;     o += up256(sizeof(float) * y.b_total);
+  p.o_lossp = o;  o += up256(sizeof(float) * 1024);
+  p.o_gradp = o;  o += up256(sizeof(float) * (size_t)sms * y.n_params);
+  p.o_x1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.K1 * TMP);
+  p.o_h1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * HID * TMP);
+  p.o_h2 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * HID * TMP);
+  p.o_h3 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * HID * TMP);
+  p.o_act = o;    o += up256(sizeof(float) * (size_t)p.ntiles * y.Mo4 * TMP);
+  p.o_states = o; o += up256(sizeof(float) * (size_t)p.ntiles * c->horizon * S * TMP);
+  p.total = o;
+  return p;
+}
+
+RolloutArgs make_args(const apg_config* c, const Plan& p, const float* in_state, const float* cur, const float* in_ref,
+                      const float* ref, const float* h0c0, void* workspace) {
+  RolloutArgs a;
+  memset(&a, 0, sizeof(a));
+  char* w = static_cast<char*>(workspace);
+  a.in_state = in_state; a.cur = cur; a.in_ref = in_ref; a.ref = ref; a.h0c0 = h0c0;
+  a.N = c->n_drones; a.h = c->horizon; a.ref_rows = c->horizon; a.window = c->window; a.dt = c->dt;
+  memcpy(a.pc.v, c->phys, sizeof(float) * MAX_PHYS);
+  a.wf = reinterpret_cast<float*>(w + p.o_wf);
+  a.wb = reinterpret_cast<float*>(w + p.o_wb);
+  a.loss_partials = reinterpret_cast<float*>(w + p.o_lossp);
+  a.grad_partials = reinterpret_cast<float*>(w + p.o_gradp);
+  a.st_x1 = reinterpret_cast<float*>(w + p.o_x1);
+  a.st_h1 = reinterpret_cast<float*>(w + p.o_h1);
+  a.st_h2 = reinterpret_cast<float*>(w + p.o_h2);
+  a.st_h3 = reinterpret_cast<float*>(w + p.o_h3);
+  a.st_act = reinterpret_cast<float*>(w + p.o_act);
+  a.st_states = reinterpret_cast<float*>(w + p.o_states);
+  return a;
+}
+
+int check_ptrs(const apg_config* c, const float* params, const float* in_state, const float* cur, const float* in_ref,
+               const float* ref, void* workspace) {
+  if (!params || !in_state || !cur || !workspace) return APG_ERR_BAD_CONFIG;
+  if (c->system != SYS_CARTPOLE && (!in_ref || !ref)) return APG_ERR_BAD_CONFIG;
+  if (!aligned16(params) || !aligned16(in_state) || !aligned16(cur) || !aligned16(in_ref) || !aligned16(ref) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return APG_ERR_ALIGNMENT;
+  return 0;
+}
+
+// cached device buffers of the host-buffer entry point
+struct HostCache {
+  void* buf = nullptr;
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+} g_cache;
+
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) int apg_version(void) { return 1; }
+__attribute__((visibility("default"))) int apg_sm_count(void) { return sm_count(); }
+
+__attribute__((visibility("default"))) const char* apg_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case APG_ERR_BAD_CONFIG: return "apg: bad configuration or null pointer";
+    case APG_ERR_UNSUPPORTED: return "apg: unsupported system/net/mode combination";
+    case APG_ERR_ALIGNMENT: return "apg: pointer not 16-byte aligned (workspace: 256)";
+    case APG_ERR_NO_DEVICE: return "apg: no CUDA device";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "apg: unknown error";
+  }
+}
+
+__attribute__((visibility("default"))) int apg_num_params(const apg_config* cfg) {
+  const int e = check_config(cfg);
+  if (e) return e;
+  return hutter_layout(cfg).n_params;
+}
+
+__attribute__((visibility("default"))) size_t apg_workspace_bytes(const apg_config* cfg) {
+  if (check_config(cfg)) return 0;
+  const HutterLayout y = hutter_layout(cfg);
+  return make_plan(cfg, y).total;
+}
+
+__attribute__((visibility("default"))) int apg_rollout_forward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                        const float* in_ref, const float* ref, const float* h0c0, void* workspace, float* loss,
+                        float* states_out, float* actions_out, void* stream) {
+  int e = check_config(cfg);
+  if (e) return e;
+  if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, workspace))) return e;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const HutterLayout y = hutter_layout(cfg);
+  const Plan p = make_plan(cfg, y);
+  RolloutArgs a = make_args(cfg, p, in_state, cur, in_ref, ref, h0c0, workspace);
+  a.states_out = states_out;
+  a.actions_out = actions_out;
+  cudaError_t ce;
+  if ((ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
+    return (int)ce;
+  if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
+  if (loss && (ce = launch_sum_loss(a.loss_partials, p.grid, loss, st))) return (int)ce;
+  return 0;
+}
+
+__attribute__((visibility("default"))) int apg_rollout_backward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                         const float* in_ref, const float* ref, const float* h0c0, void* workspace, float grad_loss,
+                         float* grad_params, void* stream) {
+  int e = check_config(cfg);
+  if (e) return e;
+  if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, workspace))) return e;
+  if (!grad_params) return APG_ERR_BAD_CONFIG;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const HutterLayout y = hutter_layout(cfg);
+  const Plan p = make_plan(cfg, y);
+  RolloutArgs a = make_args(cfg, p, in_state, cur, in_ref, ref, h0c0, workspace);
+  cudaError_t ce;
+  if ((ce = launch_hutter_adj(cfg->system, y, a, p.grid, st))) return (int)ce;
+  if ((ce = launch_reduce_grad(a.grad_partials, p.grid, y.n_params, grad_loss, grad_params, st))) return (int)ce;
+  return 0;
+}
+
+__attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const apg_config* cfg, const float* params_host, const float* in_state_host,
+                                    const float* cur_host, const float* in_ref_host, const float* ref_host,
+                                    const float* h0c0_host, float* loss_host, float* grad_params_host) {
+  int e = check_config(cfg);
+  if (e) return e;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  const HutterLayout y = hutter_layout(cfg);
+  const int N = cfg->n_drones, h = cfg->horizon, S = state_dim(cfg->system);
+  const int refw = cfg->system == SYS_QUAD ? 9 : (cfg->system == SYS_WING ? 3 : 0);
+  const size_t b_params = up256(sizeof(float) * y.n_params);
+  const size_t b_ins = up256(sizeof(float) * (size_t)N * cfg->state_feat);
+  const size_t b_cur = up256(sizeof(float) * (size_t)N * S);
+  const size_t b_inr = up256(sizeof(float) * (size_t)N * cfg->ref_len * cfg->ref_dim);
+  const size_t b_ref = up256(sizeof(float) * (size_t)N * h * refw + 16);
+  const size_t b_ws = apg_workspace_bytes(cfg);
+  const size_t need = 2 * b_params + b_ins + b_cur + b_inr + b_ref + 256 + b_ws;
+  cudaError_t ce;
+  if (!g_cache.stream && (ce = cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking))) return (int)ce;
+  if (g_cache.cap < need) {
+    if (g_cache.buf) cudaFree(g_cache.buf);
+    g_cache.buf = nullptr;
+    g_cache.cap = 0;
+    if ((ce = cudaMalloc(&g_cache.buf, need))) return (int)ce;
+    g_cache.cap = need;
+  }
+  char* b = static_cast<char*>(g_cache.buf);
+  float* d_params = reinterpret_cast<float*>(b); b += b_params;
+  float* d_grad = reinterpret_cast<float*>(b);   b += b_params;
+  float* d_ins = reinterpret_cast<float*>(b);    b += b_ins;
+  float* d_cur = reinterpret_cast<float*>(b);    b += b_cur;
+  float* d_inr = reinterpret_cast<float*>(b);    b += b_inr;
+  float* d_ref = reinterpret_cast<float*>(b);    b += b_ref;
+  float* d_loss = reinterpret_cast<float*>(b);   b += 256;
+  void* d_ws = b;
+  cudaStream_t st = g_cache.stream;
+#define APG_H2D(dst, src, bytes) \
+  if ((src) && (bytes) && (ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st))) return (int)ce;
+  APG_H2D(d_params, params_host, sizeof(float) * y.n_params)
+  APG_H2D(d_ins, in_state_host, sizeof(float) * (size_t)N * cfg->state_feat)
+  APG_H2D(d_cur, cur_host, sizeof(float) * (size_t)N * S)
+  APG_H2D(d_inr, in_ref_host, sizeof(float) * (size_t)N * cfg->ref_len * cfg->ref_dim)
+  APG_H2D(d_ref, ref_host, sizeof(float) * (size_t)N * h * refw)
+#undef APG_H2D
+  (void)h0c0_host;
+  if ((e = apg_rollout_forward(cfg, d_params, d_ins, d_cur, d_inr, d_ref, nullptr, d_ws, d_loss, nullptr, nullptr, st)))
+    return e;
+  if ((e = apg_rollout_backward(cfg, d_params, d_ins, d_cur, d_inr, d_ref, nullptr, d_ws, 1.0f, d_grad, st))) return e;
+  if (loss_host && (ce = cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, st))) return (int)ce;
+  if (grad_params_host &&
+      (ce = cudaMemcpyAsync(grad_params_host, d_grad, sizeof(float) * y.n_params, cudaMemcpyDeviceToHost, st)))
+    return (int)ce;
+  if ((ce = cudaStreamSynchronize(st))) return (int)ce;
+  return 0;
+}
+
+__attribute__((visibility("default"))) int apg_dynamics_step(int system, const float* phys, const float* state, const float* action, float dt, int n,
+                      float* out, void* stream) {
+  if (!phys || !state || !action || !out || n < 0) return APG_ERR_BAD_CONFIG;
+  PhysConsts pc;
+  memcpy(pc.v, phys, sizeof(float) * MAX_PHYS);
+  return (int)launch_step(system, pc, state, action, dt, n, out, static_cast<cudaStream_t>(stream));
+}
+
+__attribute__((visibility("default"))) int apg_dynamics_step_adjoint(int system, const float* phys, const float* state, const float* action, float dt, int n,
+                              const float* grad_out, float* grad_state, float* grad_action, void* stream) {
+  if (!phys || !state || !action || !grad_out || !grad_state || !grad_action || n < 0) return APG_ERR_BAD_CONFIG;
+  PhysConsts pc;
+  memcpy(pc.v, phys, sizeof(float) * MAX_PHYS);
+  return (int)launch_step_adj(system, pc, state, action, dt, n, grad_out, grad_state, grad_action,
+                              static_cast<cudaStream_t>(stream));
+}
+
+__attribute__((visibility("default"))) int apg_quad_features(const float* state, int n, float* feat, void* stream) {
+  if (!state || !feat || n < 0) return APG_ERR_BAD_CONFIG;
+  return (int)launch_features(state, n, feat, static_cast<cudaStream_t>(stream));
+}
+
+__attribute__((visibility("default"))) int apg_quad_features_adjoint(const float* state, const float* grad_feat, int n, float* grad_state, void* stream) {
+  if (!state || !grad_feat || !grad_state || n < 0) return APG_ERR_BAD_CONFIG;
+  return (int)launch_features_adj(state, grad_feat, n, grad_state, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

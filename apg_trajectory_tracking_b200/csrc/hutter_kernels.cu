@@ -1,0 +1,397 @@
+// Fused rollout kernels for the "hutter" policy MLP (models/hutter_model.py) in CONCURRENT mode:
+//   quadrotor  : Net(15, 10, 9, 4h, conv=True )  (scripts/train_drone.py:82-88,  175-203)
+//   fixed wing : Net( 9,  1, 3, 4h, conv=False)  (scripts/train_fixed_wing.py:67-73, 90-116)
+//
+// hutter_fwd_kernel  one persistent CTA per SM; per tile of 64 drones: TMA-staged input tiles -> policy forward
+//                    (all weights resident in shared memory, [in][out] packing) -> sigmoid -> h dynamics steps ->
+//                    tracking loss.  Activations / actions / states are stashed tile-major for the adjoint.
+// hutter_adj_kernel  replays the horizon in reverse (hand-written adjoint of the dynamics, no autograd tape),
+//                    back-propagates through the MLP ([out][in] weights resident) and accumulates the weight
+//                    gradient of its tiles into a per-CTA partial (deterministic, reduced by apg_reduce_kernel).
+#include "dyn_phase.cuh"
+#include "layouts.h"
+#include "rollout_args.h"
+#include "tile_engine.cuh"
+
+namespace apg {
+
+__device__ __forceinline__ void load_tile_manual(float* dst, const float* __restrict__ src, int row_floats, int valid) {
+  const int nv = valid * row_floats;
+  for (int i = threadIdx.x; i < TM * row_floats; i += NT) dst[i] = i < nv ? src[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <template <typename> class SysT, bool CONV>
+__global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y, const RolloutArgs g) {
+  extern __shared__ __align__(128) float smem[];
+  using Sys = SysT<float>;
+  constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
+  float* s_w = smem;
+  float* s_ins = s_w + y.f_total;
+  float* s_inr = s_ins + pad4(TM * y.F0);
+  float* s_x1 = s_inr + pad4(TM * y.LR);
+  float* s_h = s_x1 + y.XR * TMP;
+  float* s_red = s_h + HID * TMP;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_red + 8);
+  uint64_t* bar_in = bar_w + 1;
+
+  const Lane L;
+  const int tid = threadIdx.x;
+  const int ntiles = (g.N + TM - 1) / TM;
+  const uint32_t ins_bytes = TM * y.F0 * 4, inr_bytes = TM * y.LR * 4;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_in, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_inputs = [&](int tile) {   // thread 0, full tiles only
+    mbar_expect_tx(bar_in, ins_bytes + inr_bytes);
+    bulk_g2s(s_ins, g.in_state + (size_t)tile * TM * y.F0, ins_bytes, bar_in);
+    bulk_g2s(s_inr, g.in_ref + (size_t)tile * TM * y.LR, inr_bytes, bar_in);
+  };
+  auto tile_full = [&](int tile) { return (tile + 1) * TM <= g.N; };
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, y.f_total * 4);
+    bulk_g2s_chunked(s_w, g.wf, y.f_total * 4, bar_w);
+    if ((int)blockIdx.x < ntiles && tile_full(blockIdx.x)) issue_inputs(blockIdx.x);
+  }
+  mbar_wait(bar_w, 0);
+
+  uint32_t in_phase = 0;
+  float cta_loss = 0.f;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int valid = min(TM, g.N - tile * TM);
+    if (valid == TM) {
+      mbar_wait(bar_in, in_phase);
+      in_phase ^= 1;
+    } else {
+      load_tile_manual(s_ins, g.in_state + (size_t)tile * TM * y.F0, y.F0, valid);
+      load_tile_manual(s_inr, g.in_ref + (size_t)tile * TM * y.LR, y.LR, valid);
+      __syncthreads();
+    }
+    // ---- first layer: state branch and reference branch -> X1 = [s | r]
+    dense<SrcAoS, EPI_ACT>(L, SrcAoS{s_ins, y.F0, 0}, y.F0, s_w + y.f_ws, HID, s_w + y.f_bs, HID / 4, s_x1, 0, 1,
+                           ACT_TANH);
+    if (CONV) {
+      // Conv1d(RD -> 20, k=3, valid) over the L reference rows == npos dense layers on shifted 3*RD windows;
+      // output index is channel-major c*npos + t (hutter_model.py:36-40)
+      const int ncg = CONV_CH / 4;
+      for (int vg = L.og0; vg < y.npos * ncg; vg += 16) {
+        const int t = vg / ncg, cg = vg - t * ncg;
+        float acc[4][4] = {};
+        mac_tile(acc, SrcAoS{s_inr, y.LR, y.RD * t}, y.KC, s_w + y.f_wr + 4 * cg, CONV_CH, L.dg);
+        store_tile<EPI_ACT>(acc, s_w + y.f_br, cg, s_x1, HID + t, y.npos, ACT_RELU, L.dg);
+      }
+    } else {
+      dense<SrcAoS, EPI_ACT>(L, SrcAoS{s_inr, y.LR, 0}, y.LR, s_w + y.f_wr, HID, s_w + y.f_br, HID / 4, s_x1, HID, 1,
+                             ACT_TANH);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      const int next = tile + gridDim.x;
+      if (next < ntiles && tile_full(next)) issue_inputs(next);        // input buffers are free again
+      bulk_s2g(g.st_x1 + (size_t)tile * y.K1 * TMP, s_x1, y.K1 * TMP * 4);
+      bulk_commit();
+    }
+    // ---- fc1
+    dense<SrcT, EPI_ACT>(L, SrcT{s_x1}, y.K1, s_w + y.f_w1, HID, s_w + y.f_b1, HID / 4, s_h, 0, 1, ACT_TANH);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(g.st_h1 + (size_t)tile * HID * TMP, s_h, HID * TMP * 4);
+      bulk_commit();
+      bulk_wait_read<1>();      // the X1 store has finished reading s_x1
+    }
+    __syncthreads();
+    // ---- fc2 : s_h -> s_x1 rows [0,64)
+    dense<SrcT, EPI_ACT>(L, SrcT{s_h}, HID, s_w + y.f_w2, HID, s_w + y.f_b2, HID / 4, s_x1, 0, 1, ACT_TANH);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(g.st_h2 + (size_t)tile * HID * TMP, s_x1, HID * TMP * 4);
+      bulk_commit();
+      bulk_wait_read<1>();      // the h1 store has finished reading s_h
+    }
+    __syncthreads();
+    // ---- fc3 : s_x1 rows [0,64) -> s_h
+    dense<SrcT, EPI_ACT>(L, SrcT{s_x1}, HID, s_w + y.f_w3, HID, s_w + y.f_b3, HID / 4, s_h, 0, 1, ACT_TANH);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(g.st_h3 + (size_t)tile * HID * TMP, s_h, HID * TMP * 4);
+      bulk_commit();
+    }
+    // ---- fc_out + sigmoid (train_base.py:202-203) : s_h -> s_x1 rows [64, 64+Mo4)
+    float* s_act = s_x1 + HID * TMP;
+    dense<SrcT, EPI_ACT>(L, SrcT{s_h}, HID, s_w + y.f_wo, y.Mo4, s_w + y.f_bo, y.Mo4 / 4, s_act, 0, 1, ACT_SIGMOID);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(g.st_act + (size_t)tile * y.Mo4 * TMP, s_act, y.Mo4 * TMP * 4);
+      bulk_commit();
+    }
+    // ---- horizon: one thread per drone
+    float my_loss = 0.f;
+    if (tid < valid) {
+      const size_t drone = (size_t)tile * TM + tid;
+      my_loss = dyn_forward_conc<SysT>(s_act, tid, g.cur + drone * S, g.ref + drone * g.ref_rows * R, g.h, g.dt, g.pc.v,
+                                       g.st_states + (size_t)tile * g.h * S * TMP,
+                                       g.states_out ? g.states_out + drone * g.h * S : nullptr,
+                                       g.actions_out ? g.actions_out + drone * g.h * A : nullptr);
+    }
+    const float tl = block_sum(my_loss, s_red);
+    if (tid == 0) {
+      cta_loss += tl;
+      bulk_wait_read<0>();      // every stash store has finished reading shared memory
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    g.loss_partials[blockIdx.x] = cta_loss;
+    bulk_wait_all();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// adjoint
+// ------------------------------------------------------------------------------------------------------------
+// conv_ref weight gradient: dWc[c][d][j] = sum_t sum_drone dz[c*npos+t][drone] * in_ref[drone][(t+j)*RD + d].
+// One warp per position t, lanes over the 3*RD window entries, 20 channel accumulators per lane; the 8 per-warp
+// partials are combined in a fixed order through shared-memory scratch.
+__device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, const float* __restrict__ dzr,
+                                        const float* __restrict__ s_inr, float* __restrict__ scratch,
+                                        float* __restrict__ P) {
+  float acc[CONV_CH], accb[CONV_CH];
+#pragma unroll
+  for (int c = 0; c < CONV_CH; ++c) acc[c] = accb[c] = 0.f;
+  const bool kin = L.lane < y.KC;
+  for (int t = L.warp; t < y.npos; t += NWARP) {
+    for (int d4 = 0; d4 < TM / 4; ++d4) {
+      const float* xp = s_inr + (4 * d4) * y.LR + y.RD * t + L.lane;
+      const float4 xv = kin ? make_float4(xp[0], xp[y.LR], xp[2 * y.LR], xp[3 * y.LR])
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < CONV_CH; ++c) {
+        const float4 z = *reinterpret_cast<const float4*>(dzr + (c * y.npos + t) * TMP + 4 * d4);
+        acc[c] = dot4(z, xv, acc[c]);
+        accb[c] += (z.x + z.y) + (z.z + z.w);
+      }
+    }
+  }
+  const int stride = CONV_CH * y.KC + CONV_CH;
+  float* my = scratch + L.warp * stride;
+#pragma unroll
+  for (int c = 0; c < CONV_CH; ++c) {
+    if (kin) my[c * y.KC + L.lane] = acc[c];
+    if (L.lane == 0) my[CONV_CH * y.KC + c] = accb[c];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < stride; idx += NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) s += scratch[w * stride + idx];
+    if (idx < CONV_CH * y.KC) {
+      const int c = idx / y.KC, kk = idx - c * y.KC;
+      const int j = kk / y.RD, dch = kk - j * y.RD;
+      P[y.t_wc + c * y.KC + dch * 3 + j] += s;      // torch layout [c][d][j]
+    } else {
+      P[y.t_bc + idx - CONV_CH * y.KC] += s;
+    }
+  }
+}
+
+template <int NKI>
+__device__ __forceinline__ void dw_T_dispatch(const Lane& L, const float* dz, int M, const float* x, int K, float* P,
+                                              int ldp, float* Pb) {
+  dw_T<NKI>(L, dz, M, x, K, P, ldp, Pb);
+}
+
+__device__ __forceinline__ void dw_T_any(const Lane& L, const float* dz, int M, const float* x, int K, float* P,
+                                         int ldp, float* Pb) {
+  const int nki = (K + 31) / 32;
+  switch (nki) {
+    case 1: dw_T<1>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 2: dw_T<2>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 3: dw_T<3>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 4: dw_T<4>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 5: dw_T<5>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 6: dw_T<6>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 7: dw_T<7>(L, dz, M, x, K, P, ldp, Pb); break;
+    default: dw_T<8>(L, dz, M, x, K, P, ldp, Pb); break;
+  }
+}
+
+template <template <typename> class SysT, bool CONV>
+__global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y, const RolloutArgs g) {
+  extern __shared__ __align__(128) float smem[];
+  using Sys = SysT<float>;
+  constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
+  float* s_w = smem;
+  float* bufA = s_w + y.b_total;
+  float* bufB = bufA + y.XR * TMP;
+  float* bufD = bufB + HID * TMP;
+  float* bufC = bufD + HID * TMP;
+  float* s_red = bufC + HID * TMP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8);
+  uint64_t *bar_w = bars, *bar_A = bars + 1, *bar_B = bars + 2, *bar_D = bars + 3, *bar_C = bars + 4,
+           *bar_in = bars + 5;
+  float* s_ins = bufB;                       // input tiles reuse bufB|bufD once those are dead
+  float* s_inr = bufB + pad4(TM * y.F0);
+  float* scratch = s_inr + pad4(TM * y.LR);  // .. up to the end of bufC (conv_dw)
+
+  const Lane L;
+  const int tid = threadIdx.x;
+  const int ntiles = (g.N + TM - 1) / TM;
+  float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
+  for (int i = tid; i < y.n_params; i += NT) P[i] = 0.f;
+  if (tid == 0) {
+    for (int b = 0; b < 6; ++b) mbar_init(bars + b, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t hbytes = HID * TMP * 4;
+  auto issue_stage_loads = [&](int tile) {    // thread 0
+    mbar_expect_tx(bar_A, y.K1 * TMP * 4);
+    bulk_g2s_chunked(bufA, g.st_x1 + (size_t)tile * y.K1 * TMP, y.K1 * TMP * 4, bar_A);
+    mbar_expect_tx(bar_B, hbytes);
+    bulk_g2s(bufB, g.st_h3 + (size_t)tile * HID * TMP, hbytes, bar_B);
+    mbar_expect_tx(bar_D, hbytes);
+    bulk_g2s(bufD, g.st_h2 + (size_t)tile * HID * TMP, hbytes, bar_D);
+  };
+  // tiles are visited in the reverse order of the forward kernel: the most recently written stash is still in L2
+  const int first = ntiles - 1 - (int)blockIdx.x;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, y.b_total * 4);
+    bulk_g2s_chunked(s_w, g.wb, y.b_total * 4, bar_w);
+    if (first >= 0) issue_stage_loads(first);
+  }
+  mbar_wait(bar_w, 0);
+
+  uint32_t ph = 0, ph_in = 0;
+  for (int tile = first; tile >= 0; tile -= gridDim.x) {
+    const int valid = min(TM, g.N - tile * TM);
+    // ---- reverse sweep through the dynamics -> d loss / d logits in bufC rows [0, h*A)
+    if (tid < TM) {
+      if (tid < valid) {
+        const size_t drone = (size_t)tile * TM + tid;
+        dyn_adjoint_conc<SysT>(g.st_act + (size_t)tile * y.Mo4 * TMP, g.st_states + (size_t)tile * g.h * S * TMP, tid,
+                               g.cur + drone * S, g.ref + drone * g.ref_rows * R, g.h, g.dt, g.pc.v, bufC);
+      } else {
+        for (int r = 0; r < y.Mo4; ++r) bufC[r * TMP + tid] = 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- fc_out
+    mbar_wait(bar_B, ph);
+    dw_T<2>(L, bufC, y.Mo, bufB, HID, P + y.t_wo, HID, P + y.t_bo);
+    __syncthreads();
+    dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, y.Mo, s_w + y.b_wo, HID, nullptr, HID / 4, bufB, 0, 1, 0);   // dz3 over h3
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar_C, hbytes);
+      bulk_g2s(bufC, g.st_h1 + (size_t)tile * HID * TMP, hbytes, bar_C);
+    }
+    // ---- fc3
+    mbar_wait(bar_D, ph);
+    dw_T<2>(L, bufB, HID, bufD, HID, P + y.t_w3, HID, P + y.t_b3);
+    __syncthreads();
+    dense<SrcT, EPI_DTANH>(L, SrcT{bufB}, HID, s_w + y.b_w3, HID, nullptr, HID / 4, bufD, 0, 1, 0);    // dz2 over h2
+    __syncthreads();
+    // ---- fc2
+    mbar_wait(bar_C, ph);
+    dw_T<2>(L, bufD, HID, bufC, HID, P + y.t_w2, HID, P + y.t_b2);
+    __syncthreads();
+    dense<SrcT, EPI_DTANH>(L, SrcT{bufD}, HID, s_w + y.b_w2, HID, nullptr, HID / 4, bufC, 0, 1, 0);    // dz1 over h1
+    fence_proxy_async();
+    __syncthreads();
+    // bufB | bufD are dead: fetch the input tiles into them while fc1 is processed
+    if (valid == TM) {
+      if (tid == 0) {
+        mbar_expect_tx(bar_in, TM * (y.F0 + y.LR) * 4);
+        bulk_g2s(s_ins, g.in_state + (size_t)tile * TM * y.F0, TM * y.F0 * 4, bar_in);
+        bulk_g2s(s_inr, g.in_ref + (size_t)tile * TM * y.LR, TM * y.LR * 4, bar_in);
+      }
+    } else {
+      load_tile_manual(s_ins, g.in_state + (size_t)tile * TM * y.F0, y.F0, valid);
+      load_tile_manual(s_inr, g.in_ref + (size_t)tile * TM * y.LR, y.LR, valid);
+    }
+    // ---- fc1
+    mbar_wait(bar_A, ph);
+    dw_T_any(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
+    __syncthreads();
+    dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, HID, s_w + y.b_w1, y.K1, nullptr, HID / 4, bufA, 0, 1, 0);   // ds over s
+    if (CONV)
+      dense<SrcT, EPI_DRELU>(L, SrcT{bufC}, HID, s_w + y.b_w1 + HID, y.K1, nullptr, y.NRtot / 4, bufA, HID, 1, 0);
+    else
+      dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, HID, s_w + y.b_w1 + HID, y.K1, nullptr, y.NRtot / 4, bufA, HID, 1, 0);
+    __syncthreads();
+    // ---- first layer weight gradients (no dX: the inputs need no gradient in concurrent mode)
+    if (valid == TM) {
+      mbar_wait(bar_in, ph_in);
+      ph_in ^= 1;
+    }
+    dw_AoS(L, bufA, HID, s_ins, y.F0, 0, y.F0, P + y.t_ws, y.F0, P + y.t_bs);
+    if (CONV)
+      conv_dw(L, y, bufA + HID * TMP, s_inr, scratch, P);
+    else
+      dw_AoS(L, bufA + HID * TMP, HID, s_inr, y.LR, 0, y.LR, P + y.t_wr, y.LR, P + y.t_br);
+    fence_proxy_async();
+    __syncthreads();
+    ph ^= 1;
+    const int next = tile - gridDim.x;
+    if (tid == 0 && next >= 0) issue_stage_loads(next);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------------
+size_t hutter_fwd_smem_bytes(const HutterLayout& y) {
+  return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP + 8) + 16;
+}
+size_t hutter_adj_smem_bytes(const HutterLayout& y) {
+  return sizeof(float) * (size_t)(y.b_total + y.XR * TMP + 3 * HID * TMP + 8) + 64;
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t launch_hutter_fwd(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = hutter_fwd_smem_bytes(y);
+  cudaError_t e;
+  if (system == SYS_QUAD && y.conv) {
+    if ((e = set_smem(hutter_fwd_kernel<Quad, true>, smem)) != cudaSuccess) return e;
+    hutter_fwd_kernel<Quad, true><<<grid, NT, smem, st>>>(y, a);
+  } else if (system == SYS_WING && !y.conv) {
+    if ((e = set_smem(hutter_fwd_kernel<Wing, false>, smem)) != cudaSuccess) return e;
+    hutter_fwd_kernel<Wing, false><<<grid, NT, smem, st>>>(y, a);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = hutter_adj_smem_bytes(y);
+  cudaError_t e;
+  if (system == SYS_QUAD && y.conv) {
+    if ((e = set_smem(hutter_adj_kernel<Quad, true>, smem)) != cudaSuccess) return e;
+    hutter_adj_kernel<Quad, true><<<grid, NT, smem, st>>>(y, a);
+  } else if (system == SYS_WING && !y.conv) {
+    if ((e = set_smem(hutter_adj_kernel<Wing, false>, smem)) != cudaSuccess) return e;
+    hutter_adj_kernel<Wing, false><<<grid, NT, smem, st>>>(y, a);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace apg

@@ -1,0 +1,24 @@
+// Host-side launcher declarations (definitions in the *_kernels.cu files).
+#pragma once
+#include <cuda_runtime.h>
+#include "layouts.h"
+#include "rollout_args.h"
+
+namespace apg {
+
+size_t hutter_fwd_smem_bytes(const HutterLayout& y);
+size_t hutter_adj_smem_bytes(const HutterLayout& y);
+cudaError_t launch_hutter_fwd(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
+
+cudaError_t launch_pack(const PackTable& t, const float* params, float* wf, float* wb, cudaStream_t st);
+cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st);
+cudaError_t launch_sum_loss(const float* partials, int ncta, float* loss, cudaStream_t st);
+cudaError_t launch_step(int system, const PhysConsts& pc, const float* s, const float* a, float dt, int n, float* out,
+                        cudaStream_t st);
+cudaError_t launch_step_adj(int system, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
+                            const float* g, float* gs, float* ga, cudaStream_t st);
+cudaError_t launch_features(const float* s, int n, float* f, cudaStream_t st);
+cudaError_t launch_features_adj(const float* s, const float* gf, int n, float* gs, cudaStream_t st);
+
+}  // namespace apg

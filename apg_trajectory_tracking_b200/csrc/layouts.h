@@ -1,0 +1,92 @@
+// Parameter / shared-memory layouts of the policy networks, shared by host (capi.cu) and device code.
+//
+// "torch flat" = the tensors of net.parameters() concatenated in order, each in its torch layout.  This is what the
+// C-ABI takes (params) and returns (grad_params).
+//   hutter (models/hutter_model.py:12-30): states_in.{w[64][F0],b}, conv_ref.{w[20][RD][3],b}, ref_in.{w[64][L*RD],b},
+//                                          fc1.{w[64][K1],b}, fc2, fc3, fc_out.{w[Mo][64],b}
+//   simple (models/simple_model.py:9-18) : fc0.{w[32][4],b}, fc1.{w[64][32],b}, fc2.{w[64][64],b}, fc3.{w[32][64],b},
+//                                          fc_out.{w[Mo][32],b}
+//   lstm   (models/rnn.py:7-27)          : conv_ref.{w,b}, ref_in.{w,b}, fc_out.{w[Mo][8],b},
+//                                          lstm.{weight_ih[32][F0+20*npos], weight_hh[32][8], bias_ih[32], bias_hh[32]}
+// "packed fwd" = [in][out] (transposed, output dim padded to a multiple of 4) for the forward GEMMs;
+// "packed bwd" = [out][in] (input dim padded to a multiple of 4) for the dX GEMMs.  Both are produced on the device
+// by apg_pack_kernel once per call from the torch-flat vector.
+#pragma once
+
+namespace apg {
+
+enum NetKind { NET_HUTTER_CONV = 0, NET_HUTTER_LIN = 1, NET_SIMPLE = 2, NET_LSTM = 3 };
+enum Mode { MODE_CONCURRENT = 0, MODE_AUTOREGRESSIVE = 1, MODE_LSTM = 2 };
+enum Window { WINDOW_CUMULATIVE = 0, WINDOW_RELATIVE = 1 };
+
+constexpr int TM = 64;        // drones per tile
+constexpr int TMP = 68;       // padded row length of feature-major tiles (floats)
+constexpr int NT = 256;       // threads per CTA
+constexpr int NWARP = NT / 32;
+
+inline __host__ __device__ int pad4(int x) { return (x + 3) & ~3; }
+
+constexpr int HID = 64;       // hidden width of the hutter nets
+constexpr int CONV_CH = 20;   // conv_ref output channels
+
+struct HutterLayout {
+  int F0, L, RD, Mo, conv;      // state features, reference rows seen by the net, reference width, outputs, conv?
+  int npos, KC, LR, KR, NRtot, K1, Mo4, XR;
+  // torch flat offsets
+  int t_ws, t_bs, t_wc, t_bc, t_wr, t_br, t_w1, t_b1, t_w2, t_b2, t_w3, t_b3, t_wo, t_bo, n_params;
+  // packed forward
+  int f_ws, f_bs, f_wr, f_br, f_w1, f_b1, f_w2, f_b2, f_w3, f_b3, f_wo, f_bo, f_total, ld_wr;
+  // packed backward ([out][in_padded])
+  int b_wo, b_w3, b_w2, b_w1, b_ws, b_wr, b_total, ld_bws, ld_bwr;
+};
+
+inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, int conv) {
+  HutterLayout y;
+  y.F0 = F0; y.L = L; y.RD = RD; y.Mo = Mo; y.conv = conv;
+  y.npos = conv ? L - 2 : 1;
+  y.KC = 3 * RD;
+  y.LR = L * RD;
+  y.KR = conv ? y.KC : y.LR;
+  y.NRtot = conv ? CONV_CH * y.npos : HID;
+  y.K1 = HID + y.NRtot;
+  y.Mo4 = pad4(Mo);
+  y.XR = y.K1 > HID + y.Mo4 ? y.K1 : HID + y.Mo4;
+  int o = 0;
+  y.t_ws = o; o += HID * F0;      y.t_bs = o; o += HID;
+  y.t_wc = o; o += CONV_CH * RD * 3; y.t_bc = o; o += CONV_CH;
+  y.t_wr = o; o += HID * y.LR;    y.t_br = o; o += HID;
+  y.t_w1 = o; o += HID * y.K1;    y.t_b1 = o; o += HID;
+  y.t_w2 = o; o += HID * HID;     y.t_b2 = o; o += HID;
+  y.t_w3 = o; o += HID * HID;     y.t_b3 = o; o += HID;
+  y.t_wo = o; o += Mo * HID;      y.t_bo = o; o += Mo;
+  y.n_params = o;
+  const int nr = conv ? CONV_CH : HID;
+  y.ld_wr = nr;
+  o = 0;
+  y.f_ws = o; o += pad4(F0 * HID);      y.f_bs = o; o += HID;
+  y.f_wr = o; o += pad4(y.KR * nr);     y.f_br = o; o += pad4(nr);
+  y.f_w1 = o; o += y.K1 * HID;          y.f_b1 = o; o += HID;
+  y.f_w2 = o; o += HID * HID;           y.f_b2 = o; o += HID;
+  y.f_w3 = o; o += HID * HID;           y.f_b3 = o; o += HID;
+  y.f_wo = o; o += HID * y.Mo4;         y.f_bo = o; o += y.Mo4;
+  y.f_total = o;
+  y.ld_bws = pad4(F0);
+  y.ld_bwr = pad4(y.KR);
+  o = 0;
+  y.b_wo = o; o += Mo * HID;
+  y.b_w3 = o; o += HID * HID;
+  y.b_w2 = o; o += HID * HID;
+  y.b_w1 = o; o += HID * y.K1;
+  y.b_ws = o; o += HID * y.ld_bws;
+  y.b_wr = o; o += nr * y.ld_bwr;
+  y.b_total = o;
+  return y;
+}
+
+// Segment table of the pack kernel: dst[...] = src[...] with a layout transform.
+enum PackMode { PK_COPY_PAD = 0, PK_TRANSPOSE = 1, PK_CONV_FWD = 2, PK_CONV_BWD = 3 };
+struct PackSeg { int src, dst, rows, cols, ldd, mode, which; };   // which: 0 -> fwd buffer, 1 -> bwd buffer
+constexpr int MAX_PACK_SEGS = 24;
+struct PackTable { int n; PackSeg seg[MAX_PACK_SEGS]; };
+
+}  // namespace apg

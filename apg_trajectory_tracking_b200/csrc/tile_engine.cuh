@@ -1,0 +1,289 @@
+// Tile engine: the building blocks every rollout kernel is made of.
+//
+// One CTA (256 threads, one per SM, persistent) works on a tile of TM = 64 drones.  Activations of a tile live in
+// shared memory "feature-major": row = feature, TMP = 68 floats per row (64 drones + 4 pad so that lanes that
+// walk consecutive rows hit distinct 16-byte bank groups).  Input tiles arrive in their natural drone-major
+// (AoS) layout by bulk async copies (TMA 1-D, cp.async.bulk + mbarrier) and are consumed in place.
+//
+//  dense()    Y[o][d] = epi( b[o] + sum_k A[k][d] * W[k][o] )        register tile 4 drones x 4 outputs / thread
+//             used for every layer forward (W packed [in][out]) and for dX (A = dZ, W = torch layout [out][in])
+//  dw_T()     dW[j][k] += sum_d dZ[j][d] * X[k][d]                    8 rows x NKI*32 columns per warp
+//  dw_AoS()   same with X drone-major (first layers read the input tiles directly)
+//
+// All arithmetic is fp32 FMA on the CUDA cores: the contractions here are 64-wide with fp32 parity required
+// (tolerance 1e-5 on the loss), see DESIGN.md for why the tensor-core variant is a 3xTF32 follow-up.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "layouts.h"
+
+namespace apg {
+
+
+enum Act { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+enum Epi { EPI_ACT = 0, EPI_DTANH = 1, EPI_DRELU = 2, EPI_DNONE = 3, EPI_DSIGMOID = 4 };
+
+// ------------------------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA 1-D) helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// Spin on the phase parity.  A bounded spin that traps instead of hanging the GPU if a copy never lands.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+// global -> shared, completion signalled on the mbarrier (bytes multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared -> global (bulk group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Copy `bytes` (multiple of 16) global -> shared in chunks, all signalled on one barrier. Call from ONE thread,
+// after mbar_expect_tx(bar, bytes).
+__device__ __forceinline__ void bulk_g2s_chunked(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  constexpr uint32_t CH = 32768;
+  for (uint32_t o = 0; o < bytes; o += CH) {
+    const uint32_t n = bytes - o < CH ? bytes - o : CH;
+    bulk_g2s(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, n, bar);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// thread mapping of the 4x4 register-tile GEMM: a warp spans 4 drone groups x 8 output groups
+// ------------------------------------------------------------------------------------------------------------
+struct Lane {
+  int lane, warp, dg, og0;
+  __device__ __forceinline__ Lane() {
+    lane = threadIdx.x & 31;
+    warp = threadIdx.x >> 5;
+    dg = (lane >> 3) + 4 * (warp & 3);     // 0..15 : drones 4*dg .. 4*dg+3
+    og0 = (lane & 7) + 8 * (warp >> 2);    // 0..15 : outputs 4*og .. 4*og+3
+  }
+};
+
+// A operand sources: value of feature k for the 4 drones of drone-group dg
+struct SrcT {   // feature-major smem tile [K][TMP]
+  const float* base;
+  __device__ __forceinline__ float4 ld(int k, int dg) const {
+    return *reinterpret_cast<const float4*>(base + k * TMP + 4 * dg);
+  }
+};
+struct SrcAoS {  // drone-major smem tile [TM][ld], features start at column `off`
+  const float* base;
+  int ld_, off;
+  __device__ __forceinline__ float4 ld(int k, int dg) const {
+    const float* p = base + (4 * dg) * ld_ + off + k;
+    return make_float4(p[0], p[ld_], p[2 * ld_], p[3 * ld_]);
+  }
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_TANH) return tanhf(v);
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+
+// acc[i][j] += A[k][drone i] * W[k][4*og + j]  over k in [0,K)
+template <class Src>
+__device__ __forceinline__ void mac_tile(float (&acc)[4][4], const Src& A, int K, const float* __restrict__ Wcol,
+                                         int ldw, int dg) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 a = A.ld(k, dg);
+    const float4 w = *reinterpret_cast<const float4*>(Wcol + k * ldw);
+    acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
+    acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
+    acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
+    acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
+    acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]);
+    acc[2][2] = fmaf(a.z, w.z, acc[2][2]); acc[2][3] = fmaf(a.z, w.w, acc[2][3]);
+    acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]);
+    acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
+  }
+}
+
+// Epilogue of one 4x4 tile: outputs o = 4*og + j go to row (row0 + o*row_stride) of the feature-major tile Y.
+//   EPI_ACT    : Y = act(acc + bias)
+//   EPI_D*     : Y = acc * act'(Y_old)   (in-place backward through the activation whose OUTPUT is stored in Y)
+template <int EPI>
+__device__ __forceinline__ void store_tile(const float (&acc)[4][4], const float* __restrict__ bias, int og,
+                                           float* Y, int row0, int row_stride, int act, int dg) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = 4 * og + j;
+    float* yp = Y + (row0 + o * row_stride) * TMP + 4 * dg;
+    float4 v = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+    if (EPI == EPI_ACT) {
+      const float b = bias ? bias[o] : 0.f;
+      v.x = act_apply(v.x + b, act); v.y = act_apply(v.y + b, act);
+      v.z = act_apply(v.z + b, act); v.w = act_apply(v.w + b, act);
+    } else if (EPI == EPI_DTANH) {
+      const float4 y = *reinterpret_cast<const float4*>(yp);
+      v.x *= 1.f - y.x * y.x; v.y *= 1.f - y.y * y.y; v.z *= 1.f - y.z * y.z; v.w *= 1.f - y.w * y.w;
+    } else if (EPI == EPI_DRELU) {
+      const float4 y = *reinterpret_cast<const float4*>(yp);
+      v.x = y.x > 0.f ? v.x : 0.f; v.y = y.y > 0.f ? v.y : 0.f;
+      v.z = y.z > 0.f ? v.z : 0.f; v.w = y.w > 0.f ? v.w : 0.f;
+    } else if (EPI == EPI_DSIGMOID) {
+      const float4 y = *reinterpret_cast<const float4*>(yp);
+      v.x *= y.x * (1.f - y.x); v.y *= y.y * (1.f - y.y); v.z *= y.z * (1.f - y.z); v.w *= y.w * (1.f - y.w);
+    }
+    *reinterpret_cast<float4*>(yp) = v;
+  }
+}
+
+// Generic dense layer on a tile.  W is [K][ldw] in shared memory with ldw >= 4*M4 (zero-padded columns),
+// M4 = number of 4-wide output groups.  All 256 threads call it; no internal barrier.
+template <class Src, int EPI>
+__device__ __forceinline__ void dense(const Lane& L, const Src& A, int K, const float* __restrict__ W, int ldw,
+                                      const float* __restrict__ bias, int M4, float* Y, int row0, int row_stride,
+                                      int act) {
+  for (int og = L.og0; og < M4; og += 16) {
+    float acc[4][4] = {};
+    mac_tile(acc, A, K, W + 4 * og, ldw, L.dg);
+    store_tile<EPI>(acc, bias, og, Y, row0, row_stride, act, L.dg);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight-gradient contractions.  P points at the CTA's partial-gradient matrix in global memory (torch layout
+// [M][ldp]); each (j,k) entry is owned by exactly one thread -> plain read-modify-write, deterministic.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float c) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, c))));
+}
+
+// dW[j][k] += sum_d dZ[j][d] X[k][d], X feature-major [K][TMP]; K <= 32*NKI.  Also db[j] += sum_d dZ[j][d].
+template <int NKI>
+__device__ __forceinline__ void dw_T(const Lane& L, const float* __restrict__ dz, int M, const float* __restrict__ x,
+                                     int K, float* __restrict__ P, int ldp, float* __restrict__ Pb) {
+  for (int j0 = 8 * L.warp; j0 < M; j0 += 8 * NWARP) {
+    float acc[8][NKI];
+    float accb[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      accb[jj] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NKI; ++i) acc[jj][i] = 0.f;
+    }
+#pragma unroll 2
+    for (int d4 = 0; d4 < TM / 4; ++d4) {
+      float4 xv[NKI];
+#pragma unroll
+      for (int i = 0; i < NKI; ++i) {
+        const int k = L.lane + 32 * i;
+        xv[i] = k < K ? *reinterpret_cast<const float4*>(x + k * TMP + 4 * d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float4 z = (j0 + jj < M) ? *reinterpret_cast<const float4*>(dz + (j0 + jj) * TMP + 4 * d4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        accb[jj] += (z.x + z.y) + (z.z + z.w);
+#pragma unroll
+        for (int i = 0; i < NKI; ++i) acc[jj][i] = dot4(z, xv[i], acc[jj][i]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = j0 + jj;
+      if (j < M) {
+#pragma unroll
+        for (int i = 0; i < NKI; ++i) {
+          const int k = L.lane + 32 * i;
+          if (k < K) P[j * ldp + k] += acc[jj][i];
+        }
+        if (Pb && L.lane == 0) Pb[j] += accb[jj];
+      }
+    }
+  }
+}
+
+// Same with X drone-major: X[k][d] = xa[d*ld + off + k], K <= 32.
+__device__ __forceinline__ void dw_AoS(const Lane& L, const float* __restrict__ dz, int M, const float* __restrict__ xa,
+                                       int ld, int off, int K, float* __restrict__ P, int ldp,
+                                       float* __restrict__ Pb) {
+  for (int j0 = 8 * L.warp; j0 < M; j0 += 8 * NWARP) {
+    float acc[8], accb[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) acc[jj] = accb[jj] = 0.f;
+    const bool kin = L.lane < K;
+    for (int d4 = 0; d4 < TM / 4; ++d4) {
+      const float* xp = xa + (4 * d4) * ld + off + L.lane;
+      const float4 xv = kin ? make_float4(xp[0], xp[ld], xp[2 * ld], xp[3 * ld]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float4 z = (j0 + jj < M) ? *reinterpret_cast<const float4*>(dz + (j0 + jj) * TMP + 4 * d4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        accb[jj] += (z.x + z.y) + (z.z + z.w);
+        acc[jj] = dot4(z, xv, acc[jj]);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = j0 + jj;
+      if (j < M) {
+        if (kin) P[j * ldp + L.lane] += acc[jj];
+        if (Pb && L.lane == 0) Pb[j] += accb[jj];
+      }
+    }
+  }
+}
+
+// block-wide sum of one float per thread (result valid in thread 0); `scratch` = NWARP floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) r += scratch[w];
+  }
+  __syncthreads();
+  return r;
+}
+
+}  // namespace apg

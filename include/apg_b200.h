@@ -1,0 +1,97 @@
+/* apg_b200 -- C ABI of the B200-native batched differentiable rollout (policy -> dynamics x horizon -> tracking
+ * loss -> analytic policy gradient).
+ *
+ * The reference (lis-epfl/apg_trajectory_tracking) has no FFI: its "plugin interface" for this path is the Python
+ * surface used by the trainers.  Each entry point below names the reference code it replaces:
+ *
+ *   apg_rollout_forward / apg_rollout_backward
+ *        concurrent   : scripts/train_base.py:202-207 (net forward, sigmoid, reshape) +
+ *                       scripts/train_drone.py:175-203 / scripts/train_fixed_wing.py:90-116 /
+ *                       scripts/train_cartpole.py:127-155 (h dynamics steps, *_mpc_loss, loss.backward())
+ *        recurrent    : scripts/train_drone.py:113-173 (autoregressive / LSTM loop)
+ *   apg_dynamics_step / apg_dynamics_step_adjoint
+ *        neural_control/dynamics/quad_dynamics_flightmare.py:125-216, fixed_wing_dynamics.py:95-267,
+ *        cartpole_dynamics.py:50-119 (__call__) and what autograd records for them
+ *   apg_rollout_value_and_grad_host
+ *        the same train step called with HOST buffers (host<->device copies inside), i.e. what a CPU caller
+ *        of the reference's trainer sees
+ *
+ * Conventions: all tensors fp32, row-major, contiguous, 16-byte aligned; `params` / `grad_params` are the tensors
+ * of net.parameters() concatenated in order, each in its torch layout; device pointers unless the name ends in
+ * _host; `stream` is a cudaStream_t; every function returns 0 on success, a negative apg error or a positive
+ * cudaError_t otherwise (see apg_error_string).  No function allocates device memory except the *_host one.
+ */
+#ifndef APG_B200_H
+#define APG_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { APG_SYS_QUAD = 0, APG_SYS_WING = 1, APG_SYS_CARTPOLE = 2 };
+enum { APG_MODE_CONCURRENT = 0, APG_MODE_AUTOREGRESSIVE = 1, APG_MODE_LSTM = 2 };
+enum { APG_WINDOW_CUMULATIVE = 0, APG_WINDOW_RELATIVE = 1 };
+enum { APG_NET_HUTTER_CONV = 0, APG_NET_HUTTER_LIN = 1, APG_NET_SIMPLE = 2, APG_NET_LSTM = 3 };
+enum { APG_ERR_BAD_CONFIG = -1, APG_ERR_UNSUPPORTED = -2, APG_ERR_ALIGNMENT = -3, APG_ERR_NO_DEVICE = -4 };
+
+#define APG_MAX_PHYS 48
+
+typedef struct apg_config {
+  int system;      /* APG_SYS_*                                                          */
+  int mode;        /* APG_MODE_*                                                         */
+  int window;      /* APG_WINDOW_* (recurrent modes; cumulative = the reference's forward) */
+  int net;         /* APG_NET_*                                                          */
+  int n_drones;    /* N: rows of every per-drone tensor                                  */
+  int horizon;     /* h: dynamics steps per rollout                                      */
+  int state_feat;  /* width of in_state rows (quad 15, wing 9, cartpole 4)               */
+  int ref_len;     /* reference rows the policy sees per call (quad h, wing 1)           */
+  int ref_dim;     /* width of one in_ref row (quad 9, wing 3)                           */
+  int out_dim;     /* policy outputs per call (concurrent: A*h, recurrent: A)            */
+  float dt;        /* integration step                                                   */
+  float phys[APG_MAX_PHYS]; /* physical constants, layout of csrc/apg_math.cuh enums     */
+} apg_config;
+
+/* number of fp32 parameters of the policy described by cfg (== sum of net.parameters() sizes) */
+int apg_num_params(const apg_config* cfg);
+/* bytes of device workspace (packed weights, activation stash, per-CTA partials) the rollout calls need */
+size_t apg_workspace_bytes(const apg_config* cfg);
+
+/* Forward rollout.  in_state [N][state_feat], cur [N][S], in_ref [N][ref_len*ref_dim] (concurrent) or
+ * [N][2h][ref_dim] (recurrent), ref [N][h][REFW] (concurrent; quad 9, wing 3, cartpole: NULL) or [N][2h][9],
+ * h0c0 [2][N][8] (LSTM only).  Writes the scalar loss (sum over drones, horizon, components) to *loss (device)
+ * and optionally states [N][h][S] / actions [N][h][A]. Leaves the activation stash in `workspace`. */
+int apg_rollout_forward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                        const float* in_ref, const float* ref, const float* h0c0, void* workspace, float* loss,
+                        float* states_out, float* actions_out, void* stream);
+
+/* Adjoint of the forward call that last used `workspace` (same cfg and inputs): writes
+ * grad_params = grad_loss * d loss / d params  (n_params floats; entries of tensors the forward does not use
+ * are 0, the Python wrapper leaves their .grad None like the reference). */
+int apg_rollout_backward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                         const float* in_ref, const float* ref, const float* h0c0, void* workspace,
+                         float grad_loss, float* grad_params, void* stream);
+
+/* One train-step evaluation with HOST buffers: H2D of params and inputs, forward, backward, D2H of the loss and
+ * the gradient, synchronous.  Device buffers are cached inside the library between calls. */
+int apg_rollout_value_and_grad_host(const apg_config* cfg, const float* params_host, const float* in_state_host,
+                                    const float* cur_host, const float* in_ref_host, const float* ref_host,
+                                    const float* h0c0_host, float* loss_host, float* grad_params_host);
+
+/* Single dynamics step out = f(state, action) for N rows, and its vector-Jacobian product. */
+int apg_dynamics_step(int system, const float* phys, const float* state, const float* action, float dt, int n,
+                      float* out, void* stream);
+int apg_dynamics_step_adjoint(int system, const float* phys, const float* state, const float* action, float dt,
+                              int n, const float* grad_out, float* grad_state, float* grad_action, void* stream);
+/* quadrotor featurizer (neural_control/dataset.py:207-220) and its vector-Jacobian product */
+int apg_quad_features(const float* state, int n, float* feat, void* stream);
+int apg_quad_features_adjoint(const float* state, const float* grad_feat, int n, float* grad_state, void* stream);
+
+int apg_sm_count(void);
+int apg_version(void);
+const char* apg_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APG_B200_H */
