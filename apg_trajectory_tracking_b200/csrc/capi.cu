@@ -46,8 +46,22 @@ int check_config(const apg_config* c) {
     if (c->state_feat < 1 || c->state_feat > 32) return APG_ERR_BAD_CONFIG;
     return 0;
   }
+  if (c->net == NET_SIMPLE) {
+    if (c->mode != MODE_CONCURRENT || c->system != SYS_CARTPOLE) return APG_ERR_UNSUPPORTED;
+    if (c->out_dim != c->horizon || c->state_feat != 4 || c->horizon < 2) return APG_ERR_BAD_CONFIG;
+    return 0;
+  }
   return APG_ERR_UNSUPPORTED;
 }
+
+SimpleLayout simple_layout(const apg_config* c) { return make_simple_layout(c->state_feat, c->out_dim); }
+
+PackTable simple_pack_table(const SimpleLayout& y);
+
+// per-net sizes the workspace plan needs
+struct NetInfo { int n_params, f_total, b_total, x1_rows, h_rows, act_rows; };
+
+NetInfo net_info(const apg_config* c);
 
 HutterLayout hutter_layout(const apg_config* c) {
   return make_hutter_layout(c->state_feat, c->ref_len, c->ref_dim, c->out_dim, c->net == NET_HUTTER_CONV);
@@ -95,7 +109,32 @@ struct Plan {
   size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, total;
 };
 
-Plan make_plan(const apg_config* c, const HutterLayout& y) {
+NetInfo net_info(const apg_config* c) {
+  NetInfo n;
+  if (is_hutter(c)) {
+    const HutterLayout y = hutter_layout(c);
+    n.n_params = y.n_params; n.f_total = y.f_total; n.b_total = y.b_total;
+    n.x1_rows = y.K1; n.h_rows = HID; n.act_rows = y.Mo4;
+  } else {
+    const SimpleLayout y = simple_layout(c);
+    n.n_params = y.n_params; n.f_total = y.f_total; n.b_total = y.b_total;
+    n.x1_rows = y.rows_total; n.h_rows = 0; n.act_rows = 0;
+  }
+  return n;
+}
+
+PackTable simple_pack_table(const SimpleLayout& y) {
+  PackTable t;
+  t.n = 0;
+  for (int l = 0; l < SIMPLE_NL; ++l) {
+    add_seg(t, 0, PK_TRANSPOSE, y.t_w[l], y.f_w[l], y.dout[l], y.din[l], y.ldf[l]);
+    add_seg(t, 0, PK_COPY_PAD, y.t_b[l], y.f_b[l], 1, y.dout[l], y.ldf[l]);
+    add_seg(t, 1, PK_COPY_PAD, y.t_w[l], y.b_w[l], y.dout[l], y.din[l], y.ldb[l]);
+  }
+  return t;
+}
+
+Plan make_plan(const apg_config* c, const NetInfo& y) {
   Plan p;
   p.ntiles = (c->n_drones + TM - 1) / TM;
   int sms = sm_count();
@@ -107,11 +146,11 @@ Plan make_plan(const apg_config* c, const HutterLayout& y) {
   p.o_wb = o;     o += up256(sizeof(float) * y.b_total);
   p.o_lossp = o;  o += up256(sizeof(float) * 1024);
   p.o_gradp = o;  o += up256(sizeof(float) * (size_t)sms * y.n_params);
-  p.o_x1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.K1 * TMP);
-  p.o_h1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * HID * TMP);
-  p.o_h2 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * HID * TMP);
-  p.o_h3 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * HID * TMP);
-  p.o_act = o;    o += up256(sizeof(float) * (size_t)p.ntiles * y.Mo4 * TMP);
+  p.o_x1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.x1_rows * TMP);
+  p.o_h1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.h_rows * TMP);
+  p.o_h2 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.h_rows * TMP);
+  p.o_h3 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.h_rows * TMP);
+  p.o_act = o;    o += up256(sizeof(float) * (size_t)p.ntiles * y.act_rows * TMP);
   p.o_states = o; o += up256(sizeof(float) * (size_t)p.ntiles * c->horizon * S * TMP);
   p.total = o;
   return p;
@@ -176,13 +215,12 @@ __attribute__((visibility("default"))) const char* apg_error_string(int code) {
 __attribute__((visibility("default"))) int apg_num_params(const apg_config* cfg) {
   const int e = check_config(cfg);
   if (e) return e;
-  return hutter_layout(cfg).n_params;
+  return net_info(cfg).n_params;
 }
 
 __attribute__((visibility("default"))) size_t apg_workspace_bytes(const apg_config* cfg) {
   if (check_config(cfg)) return 0;
-  const HutterLayout y = hutter_layout(cfg);
-  return make_plan(cfg, y).total;
+  return make_plan(cfg, net_info(cfg)).total;
 }
 
 __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
@@ -193,15 +231,22 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
   if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, workspace))) return e;
   if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const HutterLayout y = hutter_layout(cfg);
-  const Plan p = make_plan(cfg, y);
+  const Plan p = make_plan(cfg, net_info(cfg));
   RolloutArgs a = make_args(cfg, p, in_state, cur, in_ref, ref, h0c0, workspace);
   a.states_out = states_out;
   a.actions_out = actions_out;
   cudaError_t ce;
-  if ((ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
-    return (int)ce;
-  if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
+  if (is_hutter(cfg)) {
+    const HutterLayout y = hutter_layout(cfg);
+    if ((ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
+      return (int)ce;
+    if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
+  } else {
+    const SimpleLayout y = simple_layout(cfg);
+    if ((ce = launch_pack(simple_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
+      return (int)ce;
+    if ((ce = launch_simple_fwd(y, a, p.grid, st))) return (int)ce;
+  }
   if (loss && (ce = launch_sum_loss(a.loss_partials, p.grid, loss, st))) return (int)ce;
   return 0;
 }
@@ -215,12 +260,16 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
   if (!grad_params) return APG_ERR_BAD_CONFIG;
   if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const HutterLayout y = hutter_layout(cfg);
-  const Plan p = make_plan(cfg, y);
+  const NetInfo ni = net_info(cfg);
+  const Plan p = make_plan(cfg, ni);
   RolloutArgs a = make_args(cfg, p, in_state, cur, in_ref, ref, h0c0, workspace);
   cudaError_t ce;
-  if ((ce = launch_hutter_adj(cfg->system, y, a, p.grid, st))) return (int)ce;
-  if ((ce = launch_reduce_grad(a.grad_partials, p.grid, y.n_params, grad_loss, grad_params, st))) return (int)ce;
+  if (is_hutter(cfg)) {
+    if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
+  } else {
+    if ((ce = launch_simple_adj(simple_layout(cfg), a, p.grid, st))) return (int)ce;
+  }
+  if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;
   return 0;
 }
 
@@ -230,7 +279,7 @@ __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const
   int e = check_config(cfg);
   if (e) return e;
   if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
-  const HutterLayout y = hutter_layout(cfg);
+  const NetInfo y = net_info(cfg);
   const int N = cfg->n_drones, h = cfg->horizon, S = state_dim(cfg->system);
   const int refw = cfg->system == SYS_QUAD ? 9 : (cfg->system == SYS_WING ? 3 : 0);
   const size_t b_params = up256(sizeof(float) * y.n_params);

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
   float* bufB = bufA + y.XR * TMP;
   float* bufD = bufB + HID * TMP;
   float* bufC = bufD + HID * TMP;
-  float* s_red = bufC + HID * TMP;
+  float* s_red = bufC + y.CR * TMP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 8);
   uint64_t *bar_w = bars, *bar_A = bars + 1, *bar_B = bars + 2, *bar_D = bars + 3, *bar_C = bars + 4,
            *bar_in = bars + 5;
@@ -356,7 +356,7 @@ size_t hutter_fwd_smem_bytes(const HutterLayout& y) {
   return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP + 8) + 16;
 }
 size_t hutter_adj_smem_bytes(const HutterLayout& y) {
-  return sizeof(float) * (size_t)(y.b_total + y.XR * TMP + 3 * HID * TMP + 8) + 64;
+  return sizeof(float) * (size_t)(y.b_total + y.XR * TMP + (2 * HID + y.CR) * TMP + 8) + 64;
 }
 
 template <typename K>

@@ -11,6 +11,11 @@ size_t hutter_adj_smem_bytes(const HutterLayout& y);
 cudaError_t launch_hutter_fwd(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 
+size_t simple_fwd_smem_bytes(const SimpleLayout& y);
+size_t simple_adj_smem_bytes(const SimpleLayout& y);
+cudaError_t launch_simple_fwd(const SimpleLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_simple_adj(const SimpleLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
+
 cudaError_t launch_pack(const PackTable& t, const float* params, float* wf, float* wb, cudaStream_t st);
 cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st);
 cudaError_t launch_sum_loss(const float* partials, int ncta, float* loss, cudaStream_t st);

@@ -31,7 +31,7 @@ constexpr int CONV_CH = 20;   // conv_ref output channels
 
 struct HutterLayout {
   int F0, L, RD, Mo, conv;      // state features, reference rows seen by the net, reference width, outputs, conv?
-  int npos, KC, LR, KR, NRtot, K1, Mo4, XR;
+  int npos, KC, LR, KR, NRtot, K1, Mo4, XR, CR;   // CR: rows of the d-logit buffer of the adjoint kernel
   // torch flat offsets
   int t_ws, t_bs, t_wc, t_bc, t_wr, t_br, t_w1, t_b1, t_w2, t_b2, t_w3, t_b3, t_wo, t_bo, n_params;
   // packed forward
@@ -51,6 +51,7 @@ inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, i
   y.K1 = HID + y.NRtot;
   y.Mo4 = pad4(Mo);
   y.XR = y.K1 > HID + y.Mo4 ? y.K1 : HID + y.Mo4;
+  y.CR = y.Mo4 > HID ? y.Mo4 : HID;
   int o = 0;
   y.t_ws = o; o += HID * F0;      y.t_bs = o; o += HID;
   y.t_wc = o; o += CONV_CH * RD * 3; y.t_bc = o; o += CONV_CH;
@@ -80,6 +81,37 @@ inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, i
   y.b_ws = o; o += HID * y.ld_bws;
   y.b_wr = o; o += nr * y.ld_bwr;
   y.b_total = o;
+  return y;
+}
+
+// ---- simple (cartpole) MLP: 4 -> 32 -> 64 -> 64 -> 32 -> Mo, tanh everywhere (models/simple_model.py:9-28)
+constexpr int SIMPLE_NL = 5;
+struct SimpleLayout {
+  int F0, Mo, Mo4;
+  int din[SIMPLE_NL], dout[SIMPLE_NL];          // real layer dims
+  int t_w[SIMPLE_NL], t_b[SIMPLE_NL], n_params;  // torch flat offsets
+  int f_w[SIMPLE_NL], f_b[SIMPLE_NL], ldf[SIMPLE_NL], f_total;   // packed fwd [in][out4]
+  int b_w[SIMPLE_NL], ldb[SIMPLE_NL], b_total;                   // packed bwd [out][in4]
+  int row[SIMPLE_NL], rows_total;               // activation arena: row offset of each layer's output
+};
+
+inline __host__ SimpleLayout make_simple_layout(int F0, int Mo) {
+  SimpleLayout y;
+  y.F0 = F0; y.Mo = Mo; y.Mo4 = pad4(Mo);
+  const int dims[SIMPLE_NL + 1] = {F0, 32, 64, 64, 32, Mo};
+  int ot = 0, of = 0, ob = 0, r = 0;
+  for (int l = 0; l < SIMPLE_NL; ++l) {
+    y.din[l] = dims[l]; y.dout[l] = dims[l + 1];
+    y.t_w[l] = ot; ot += dims[l + 1] * dims[l];
+    y.t_b[l] = ot; ot += dims[l + 1];
+    y.ldf[l] = pad4(dims[l + 1]);
+    y.f_w[l] = of; of += dims[l] * y.ldf[l];
+    y.f_b[l] = of; of += y.ldf[l];
+    y.ldb[l] = pad4(dims[l]);
+    y.b_w[l] = ob; ob += dims[l + 1] * y.ldb[l];
+    y.row[l] = r; r += y.ldf[l];
+  }
+  y.n_params = ot; y.f_total = of; y.b_total = ob; y.rows_total = r;
   return y;
 }
 

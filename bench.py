@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the batched differentiable rollout train step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+metric   drone-steps/sec (fwd+bwd) = N_total * h / time of one train iteration
+         iteration = policy forward -> sigmoid -> h dynamics steps -> tracking loss -> full backward to the weight
+         gradient [-> NCCL sum-allreduce of the flat gradient when G > 1] -> SGD(momentum) step
+workload BASELINE configs[1]: quadrotor, concurrent MLP Net(15,10,9,40), horizon 10, N = 65536 drones PER GPU
+         (weak scaling), synthetic polynomial reference trajectories, default-initialised policy.
+One "step" = one train iteration over the whole (per-GPU) batch.  Device-timed with CUDA events around every
+step on the launching stream; the L2 is flushed (256 MiB write) between timed steps, outside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (system, mode, h, dt, N per GPU, algorithmic bytes per drone-step (fwd+bwd), flops per drone-step)
+    "quad_concurrent": dict(system="quad", mode="concurrent", h=10, dt=0.1, n=65536, bytes_per_step=165.6,
+                            flops_per_step=17.7e3, label="quad concurrent MLP Net(15,10,9,40) h=10 N=65536/GPU"),
+    "wing_concurrent": dict(system="wing", mode="concurrent", h=20, dt=0.05, n=131072, bytes_per_step=33.6,
+                            flops_per_step=8.1e3, label="fixed-wing MLP Net(9,1,3,80) h=20 N=131072/GPU"),
+    "cartpole_concurrent": dict(system="cartpole", mode="concurrent", h=5, dt=0.05, n=128, bytes_per_step=12.8,
+                                flops_per_step=10e3, label="cartpole MLP Net(4,5) h=5 B=128"),
+}
+LR = {"quad": 1e-5, "wing": 1e-4, "cartpole": 1e-5}
+
+
+def hutter_shapes(system, h):
+    if system == "quad":
+        return [(64, 15), (64,), (20, 9, 3), (20,), (64, 9 * h), (64,), (64, 64 + 20 * (h - 2)), (64,), (64, 64), (64,),
+                (64, 64), (64,), (4 * h, 64), (4 * h,)]
+    if system == "wing":
+        return [(64, 9), (64,), (20, 3, 3), (20,), (64, 3), (64,), (64, 128), (64,), (64, 64), (64,), (64, 64), (64,),
+                (4 * h, 64), (4 * h,)]
+    return [(32, 4), (32,), (64, 32), (64,), (64, 64), (64,), (32, 64), (32,), (h, 32), (h,)]
+
+
+def default_init(system, h, seed=0):
+    """PyTorch default (kaiming-uniform, a=sqrt(5)) initialisation == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for both
+    weights and biases of Linear / Conv1d; drawn tensor by tensor from a seeded generator."""
+    g = torch.Generator().manual_seed(seed)
+    out, fan_in = [], 1
+    for s in hutter_shapes(system, h):
+        if len(s) > 1:
+            fan_in = 1
+            for d in s[1:]:
+                fan_in *= d
+        out.append((torch.rand(*s, generator=g) * 2 - 1) / fan_in ** 0.5)
+    return out
+
+
+def make_case(w, n, seed, device):
+    from apg_trajectory_tracking_b200 import synthetic as SY
+    if w["system"] == "quad":
+        return SY.quad_case(n, w["h"], w["dt"], seed=seed, device=device)
+    if w["system"] == "wing":
+        return SY.wing_case(n, w["h"], w["dt"], seed=seed, device=device)
+    c = SY.cartpole_case(n, seed=seed, device=device)
+    c["in_ref"], c["ref"] = None, None
+    return c
+
+
+def make_spec(w):
+    from apg_trajectory_tracking_b200 import rollout as R
+    if w["system"] == "quad":
+        return R.RolloutSpec.quad_concurrent(w["h"], w["dt"])
+    if w["system"] == "wing":
+        return R.RolloutSpec.wing_concurrent(w["h"], w["dt"])
+    return R.RolloutSpec.cartpole_concurrent(w["h"], w["dt"])
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower() == "active":
+                    reasons.add(nm)
+        sm.sort()
+        # median of the upper half: samples taken between steps (L2 flush, host gaps) would bias a plain median
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+def cpu_reference_step(w, n, params, case, threads):
+    """One train iteration of the reference algorithm on the CPU (oracle port: same op chain as the reference's
+    PyTorch code, autograd tape and all) -- returns a closure running one step."""
+    from oracle import apg_oracle as O
+    torch.set_num_threads(threads)
+    ps = [p.clone() for p in params]
+    bufs = [None] * len(ps)
+    lr = LR[w["system"]]
+
+    def step():
+        nonlocal ps, bufs
+        loss, grads, _, _ = O.concurrent_value_and_grad(w["system"], ps, case["in_state"], case["cur"], case["in_ref"],
+                                                        case["ref"], w["h"], w["dt"])
+        ps, bufs = O.sgd_momentum_step(ps, grads, bufs, lr)
+        return float(loss)
+    return step
+
+
+def physical_cores():
+    try:
+        import psutil
+        c = psutil.cpu_count(logical=False)
+        if c:
+            return int(c)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def run_reference(args, w, rank):
+    """--impl reference: the reference's CPU algorithm for the path (oracle port; the Python reference itself cannot
+    travel to the GPU box), all host cores, rank 0 only."""
+    if rank != 0:
+        return
+    threads = physical_cores()
+    n = w["n"]
+    case = make_case(w, n, 1234, "cpu")
+    params = default_init(w["system"], w["h"])
+    step = cpu_reference_step(w, n, params, case, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt_s = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = n * w["h"] / dt_s
+    line = {
+        "impl": "reference", "metric": "drone-steps/sec (fwd+bwd)", "value": value, "unit": "drone-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["label"].replace("/GPU", " (one host)"), "horizon": w["h"], "n_drones": n,
+                   "note": "CPU arm: oracle port of the reference's PyTorch op chain (autograd tape) + SGD step"},
+        "cpu_baseline": {"value": value, "unit": "drone-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"full workload N={n}, {args.steps} iterations"},
+        "e2e": {"value": value, "unit": "drone-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="quad_concurrent", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override drones per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.n:
+        w["n"] = args.n
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    if args.warmup < 3:
+        args.warmup = 3
+    import torch.distributed as dist
+    from apg_trajectory_tracking_b200 import train as T
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, h = w["n"], w["h"]
+    case = make_case(w, n, 1234 + rank, dev)
+    params = default_init(w["system"], h)
+    stepper = T.FusedTrainStep(params, make_spec(w), n, lr=LR[w["system"]], device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    args_step = (case["in_state"], case["cur"], case.get("in_ref"), case.get("ref"))
+
+    for _ in range(args.warmup):
+        stepper.step(*args_step)
+    barrier()
+
+    # ---- device-timed region: K steps, an event pair (+ one in the middle) around each
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        if flush_buf is not None:
+            flush_buf.zero_()
+        e = ev[i]
+        e[0].record()
+        loss, _, _ = stepper.runner.forward(stepper.flat, *args_step)
+        e[1].record()
+        stepper.runner.backward(1.0, out=stepper.grad)
+        e[2].record()
+        if world > 1:
+            dist.all_reduce(stepper.grad)
+        stepper.buf.mul_(stepper.momentum).add_(stepper.grad)
+        stepper.flat.add_(stepper.buf, alpha=-stepper.lr)
+        e[3].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    t_step = [e[0].elapsed_time(e[3]) for e in ev]
+    t_fwd = [e[0].elapsed_time(e[1]) for e in ev]
+    t_adj = [e[1].elapsed_time(e[2]) for e in ev]
+    ms = sum(t_step) / len(t_step)
+    ms_t = torch.tensor([ms, sum(t_fwd) / len(t_fwd), sum(t_adj) / len(t_adj)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms, ms_fwd, ms_adj = [float(x) for x in ms_t.tolist()]
+    value = world * n * h / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- end-to-end: the same train step through the public API with HOST (pinned) inputs every step:
+    #      H2D of in_state/cur/in_ref/ref + forward + adjoint (+ allreduce) + SGD + D2H of the loss
+    host = {k: (v.cpu().pin_memory() if v is not None else None) for k, v in case.items()}
+    h2d = sum(v.numel() * 4 for v in host.values() if v is not None)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        float(stepper.step(host["in_state"], host["cur"], host.get("in_ref"), host.get("ref")).item())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        float(stepper.step(host["in_state"], host["cur"], host.get("in_ref"), host.get("ref")).item())
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * h / float(e2e_t.item())
+
+    # ---- CPU baseline next to it (rank 0, single GPU runs only): the oracle port on all host cores
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = physical_cores()
+        ncpu = min(n, 65536)
+        ccase = make_case(w, ncpu, 1234, "cpu")
+        cstep = cpu_reference_step(w, ncpu, params, ccase, threads)
+        cstep()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 40):
+            cstep()
+            reps += 1
+        cs = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": ncpu * h / cs, "unit": "drone-steps/s", "cores": threads, "kind": "port",
+                        "sample": f"N={ncpu} drones x h={h}, {reps} iterations ({cs * 1e3:.1f} ms each), "
+                                  "oracle port of the reference's PyTorch op chain incl. SGD step"}
+
+    if rank == 0:
+        peak, peak_src, _ = measured_peaks()
+        # dominant kernel = the adjoint kernel (+ its tiny gradient-reduce epilogue launch): it re-reads every
+        # per-drone input once -> algorithmic bytes per launch = half of the fwd+bwd per-step figure
+        adj_bytes = 0.5 * w["bytes_per_step"] * n * h
+        achieved = adj_bytes / (ms_adj * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload, {}).get("adjoint_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        sm_max = clocks.get("sm_max_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        line = {
+            "metric": "drone-steps/sec (fwd+bwd)", "value": value, "unit": "drone-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "horizon": h, "n_drones_per_gpu": n, "n_drones_total": n * world,
+                       "policy_init": "torch default init, seed 0", "optimizer": "SGD lr %g momentum 0.9" % LR[w["system"]],
+                       "l2": "flushed between timed steps (256 MiB write, untimed)" if flush_buf is not None else "not flushed",
+                       "parallelism": f"dp{world} (drone-axis shards, one NCCL sum-allreduce of the flat gradient)"},
+            "ms_forward_kernel": ms_fwd, "ms_adjoint_kernel": ms_adj, "wall_s_timed_region": t_wall,
+            "final_loss": final_loss,
+            "roofline": {"bound": "hbm", "kernel": "adjoint (hutter_adj_kernel + reduce)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src,
+                         "note": "algorithmic bytes = per-drone inputs read once by the adjoint pass; the path is "
+                                 "fp32-FMA bound (arithmetic intensity ~100 flop/B), see roofline_compute"},
+            "roofline_compute": {"bound": "fp32_fma", "achieved": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9,
+                                 "peak": fp32_peak, "unit": "TFLOP/s",
+                                 "frac": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9 / fp32_peak,
+                                 "peak_source": "148 SM x 128 FMA/clk x 2 x clocks.max.sm (nominal)"},
+            "e2e": {"value": e2e_value, "unit": "drone-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps, "api": "apg_trajectory_tracking_b200.train.FusedTrainStep.step(host tensors)"},
+            "gpu_launches": stepper.kernel_launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,7 +81,8 @@ def test_single_step_kernels(name):
 
 
 CONC = [("quad", "conc_quad_kat4.npz"), ("quad", "conc_quad_rand.npz"), ("quad", "conc_quad_rand_h6.npz"),
-        ("wing", "conc_wing_kat5.npz"), ("wing", "conc_wing_rand_h20.npz")]
+        ("wing", "conc_wing_kat5.npz"), ("wing", "conc_wing_rand_h20.npz"),
+        ("cartpole", "conc_cartpole_kat6.npz"), ("cartpole", "conc_cartpole_rand_b128_h5.npz")]
 
 
 @pytest.mark.parametrize("system,fname", CONC)
@@ -92,7 +93,8 @@ def test_concurrent_vs_reference_golden(system, fname):
     h, dt = int(g["h"]), float(g["dt"])
     spec = _spec_for(R, system, h, dt)
     loss, states, actions, grads, _ = _run_gpu(R, spec, params, t(g["in_state"]), t(g["cur"]),
-                                               t(g["in_ref"]) if "in_ref" in g else None, t(g["ref"]))
+                                               t(g["in_ref"]) if "in_ref" in g else None,
+                                               t(g["ref"]) if system != "cartpole" else None)
     assert abs(loss - float(g["loss"])) <= LOSS_TOL * abs(float(g["loss"])), (loss, float(g["loss"]))
     assert max_rel_to_scale(actions, g["actions"]) <= ACT_TOL
     assert max_rel_to_scale(states, g["states"]) <= ACT_TOL
@@ -131,6 +133,24 @@ def test_concurrent_vs_oracle_random(system, h, n):
     assert abs(loss - float(ol)) <= LOSS_TOL * abs(float(ol)), (loss, float(ol))
     assert max_rel_to_scale(actions, oact) <= ACT_TOL
     assert max_rel_to_scale(states, ost) <= ACT_TOL
+    _check_grads(grads, og)
+
+
+@pytest.mark.parametrize("h,n", [(5, 128), (10, 1000), (7, 65)])
+def test_cartpole_vs_oracle_random(h, n):
+    R, SY, P, _capi, O = _imports()
+    dt = 0.05
+    case = SY.cartpole_case(n, seed=n)
+    torch.manual_seed(n)
+    shapes = [(32, 4), (32,), (64, 32), (64,), (64, 64), (64,), (32, 64), (32,), (h, 32), (h,)]
+    params = [(torch.rand(*s) * 2 - 1) / (s[-1] if len(s) > 1 else 32) ** 0.5 for s in shapes]
+    spec = R.RolloutSpec.cartpole_concurrent(h, dt)
+    loss, states, actions, grads, _ = _run_gpu(R, spec, params, case["in_state"], case["cur"], None, None)
+    ol, og, ost, oact = O.concurrent_value_and_grad("cartpole", params, case["in_state"], case["cur"], None, None, h,
+                                                    dt)
+    assert abs(loss - float(ol)) <= LOSS_TOL * abs(float(ol)), (loss, float(ol))
+    assert max_rel_to_scale(actions, oact) <= ACT_TOL
+    assert max_rel_to_scale(states, ost) <= 2e-5      # theta wraps through atan2: abs error relative to pi
     _check_grads(grads, og)
 
 
