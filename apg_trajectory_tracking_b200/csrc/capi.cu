@@ -33,6 +33,14 @@ int check_config(const apg_config* c) {
   if (!c) return APG_ERR_BAD_CONFIG;
   if (c->n_drones <= 0 || c->horizon <= 0 || c->horizon > 64) return APG_ERR_BAD_CONFIG;
   if (c->system < 0 || c->system > 2 || c->mode < 0 || c->mode > 2) return APG_ERR_BAD_CONFIG;
+  if (is_hutter(c) && c->mode == MODE_AUTOREGRESSIVE) {
+    // Net(15, h, 9, 4) evaluated every step on features(state) and the next-h reference rows
+    if (c->net != NET_HUTTER_CONV || c->system != SYS_QUAD) return APG_ERR_UNSUPPORTED;
+    if (c->out_dim != 4 || c->state_feat != 15 || c->ref_dim != 9 || c->ref_len != c->horizon) return APG_ERR_BAD_CONFIG;
+    if (c->horizon < 3 || c->horizon > 10) return APG_ERR_BAD_CONFIG;
+    if (c->window != WINDOW_CUMULATIVE && c->window != WINDOW_RELATIVE) return APG_ERR_BAD_CONFIG;
+    return 0;
+  }
   if (is_hutter(c)) {
     if (c->mode != MODE_CONCURRENT) return APG_ERR_UNSUPPORTED;
     if (c->out_dim != action_dim(c->system) * c->horizon) return APG_ERR_BAD_CONFIG;
@@ -59,7 +67,8 @@ SimpleLayout simple_layout(const apg_config* c) { return make_simple_layout(c->s
 PackTable simple_pack_table(const SimpleLayout& y);
 
 // per-net sizes the workspace plan needs
-struct NetInfo { int n_params, f_total, b_total, x1_rows, h_rows, act_rows; };
+struct NetInfo { int n_params, f_total, b_total, x1_rows, h_rows, act_rows, steps; };
+bool is_recurrent(const apg_config* c) { return c->mode != MODE_CONCURRENT; }
 
 NetInfo net_info(const apg_config* c);
 
@@ -115,10 +124,11 @@ NetInfo net_info(const apg_config* c) {
     const HutterLayout y = hutter_layout(c);
     n.n_params = y.n_params; n.f_total = y.f_total; n.b_total = y.b_total;
     n.x1_rows = y.K1; n.h_rows = HID; n.act_rows = y.Mo4;
+    n.steps = is_recurrent(c) ? c->horizon : 1;
   } else {
     const SimpleLayout y = simple_layout(c);
     n.n_params = y.n_params; n.f_total = y.f_total; n.b_total = y.b_total;
-    n.x1_rows = y.rows_total; n.h_rows = 0; n.act_rows = 0;
+    n.x1_rows = y.rows_total; n.h_rows = 0; n.act_rows = 0; n.steps = 1;
   }
   return n;
 }
@@ -146,11 +156,12 @@ Plan make_plan(const apg_config* c, const NetInfo& y) {
   p.o_wb = o;     o += up256(sizeof(float) * y.b_total);
   p.o_lossp = o;  o += up256(sizeof(float) * 1024);
   p.o_gradp = o;  o += up256(sizeof(float) * (size_t)sms * y.n_params);
-  p.o_x1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.x1_rows * TMP);
-  p.o_h1 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.h_rows * TMP);
-  p.o_h2 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.h_rows * TMP);
-  p.o_h3 = o;     o += up256(sizeof(float) * (size_t)p.ntiles * y.h_rows * TMP);
-  p.o_act = o;    o += up256(sizeof(float) * (size_t)p.ntiles * y.act_rows * TMP);
+  const size_t nst = (size_t)p.ntiles * y.steps;
+  p.o_x1 = o;     o += up256(sizeof(float) * nst * y.x1_rows * TMP);
+  p.o_h1 = o;     o += up256(sizeof(float) * nst * y.h_rows * TMP);
+  p.o_h2 = o;     o += up256(sizeof(float) * nst * y.h_rows * TMP);
+  p.o_h3 = o;     o += up256(sizeof(float) * nst * y.h_rows * TMP);
+  p.o_act = o;    o += up256(sizeof(float) * nst * y.act_rows * TMP);
   p.o_states = o; o += up256(sizeof(float) * (size_t)p.ntiles * c->horizon * S * TMP);
   p.total = o;
   return p;
@@ -162,7 +173,8 @@ RolloutArgs make_args(const apg_config* c, const Plan& p, const float* in_state,
   memset(&a, 0, sizeof(a));
   char* w = static_cast<char*>(workspace);
   a.in_state = in_state; a.cur = cur; a.in_ref = in_ref; a.ref = ref; a.h0c0 = h0c0;
-  a.N = c->n_drones; a.h = c->horizon; a.ref_rows = c->horizon; a.window = c->window; a.dt = c->dt;
+  a.N = c->n_drones; a.h = c->horizon; a.ref_rows = is_recurrent(c) ? 2 * c->horizon : c->horizon;
+  a.window = c->window; a.dt = c->dt;
   memcpy(a.pc.v, c->phys, sizeof(float) * MAX_PHYS);
   a.wf = reinterpret_cast<float*>(w + p.o_wf);
   a.wb = reinterpret_cast<float*>(w + p.o_wb);
@@ -179,7 +191,8 @@ RolloutArgs make_args(const apg_config* c, const Plan& p, const float* in_state,
 
 int check_ptrs(const apg_config* c, const float* params, const float* in_state, const float* cur, const float* in_ref,
                const float* ref, void* workspace) {
-  if (!params || !in_state || !cur || !workspace) return APG_ERR_BAD_CONFIG;
+  if (!params || !cur || !workspace) return APG_ERR_BAD_CONFIG;
+  if (!in_state && !is_recurrent(c)) return APG_ERR_BAD_CONFIG;   // recurrent modes featurise `cur` in-kernel
   if (c->system != SYS_CARTPOLE && (!in_ref || !ref)) return APG_ERR_BAD_CONFIG;
   if (!aligned16(params) || !aligned16(in_state) || !aligned16(cur) || !aligned16(in_ref) || !aligned16(ref) ||
       (reinterpret_cast<uintptr_t>(workspace) & 255u))
@@ -240,7 +253,8 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
     const HutterLayout y = hutter_layout(cfg);
     if ((ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
       return (int)ce;
-    if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
+    if (is_recurrent(cfg)) { if ((ce = launch_rec_fwd(y, a, p.grid, st))) return (int)ce; }
+    else if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
   } else {
     const SimpleLayout y = simple_layout(cfg);
     if ((ce = launch_pack(simple_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
@@ -265,7 +279,8 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
   RolloutArgs a = make_args(cfg, p, in_state, cur, in_ref, ref, h0c0, workspace);
   cudaError_t ce;
   if (is_hutter(cfg)) {
-    if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
+    if (is_recurrent(cfg)) { if ((ce = launch_rec_adj(hutter_layout(cfg), a, p.grid, st))) return (int)ce; }
+    else if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
   } else {
     if ((ce = launch_simple_adj(simple_layout(cfg), a, p.grid, st))) return (int)ce;
   }
@@ -285,8 +300,10 @@ __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const
   const size_t b_params = up256(sizeof(float) * y.n_params);
   const size_t b_ins = up256(sizeof(float) * (size_t)N * cfg->state_feat);
   const size_t b_cur = up256(sizeof(float) * (size_t)N * S);
-  const size_t b_inr = up256(sizeof(float) * (size_t)N * cfg->ref_len * cfg->ref_dim);
-  const size_t b_ref = up256(sizeof(float) * (size_t)N * h * refw + 16);
+  const int rec = is_recurrent(cfg) ? 2 : 1;        // recurrent modes carry 2h reference rows
+  const size_t n_inr = (size_t)N * cfg->ref_len * cfg->ref_dim * rec, n_ref = (size_t)N * h * refw * rec;
+  const size_t b_inr = up256(sizeof(float) * n_inr + 16);
+  const size_t b_ref = up256(sizeof(float) * n_ref + 16);
   const size_t b_ws = apg_workspace_bytes(cfg);
   const size_t need = 2 * b_params + b_ins + b_cur + b_inr + b_ref + 256 + b_ws;
   cudaError_t ce;
@@ -313,13 +330,16 @@ __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const
   APG_H2D(d_params, params_host, sizeof(float) * y.n_params)
   APG_H2D(d_ins, in_state_host, sizeof(float) * (size_t)N * cfg->state_feat)
   APG_H2D(d_cur, cur_host, sizeof(float) * (size_t)N * S)
-  APG_H2D(d_inr, in_ref_host, sizeof(float) * (size_t)N * cfg->ref_len * cfg->ref_dim)
-  APG_H2D(d_ref, ref_host, sizeof(float) * (size_t)N * h * refw)
+  APG_H2D(d_inr, in_ref_host, sizeof(float) * n_inr)
+  APG_H2D(d_ref, ref_host, sizeof(float) * n_ref)
 #undef APG_H2D
   (void)h0c0_host;
-  if ((e = apg_rollout_forward(cfg, d_params, d_ins, d_cur, d_inr, d_ref, nullptr, d_ws, d_loss, nullptr, nullptr, st)))
+  const float* p_ins = in_state_host ? d_ins : nullptr;
+  const float* p_inr = in_ref_host ? d_inr : nullptr;
+  const float* p_ref = ref_host ? d_ref : nullptr;
+  if ((e = apg_rollout_forward(cfg, d_params, p_ins, d_cur, p_inr, p_ref, nullptr, d_ws, d_loss, nullptr, nullptr, st)))
     return e;
-  if ((e = apg_rollout_backward(cfg, d_params, d_ins, d_cur, d_inr, d_ref, nullptr, d_ws, 1.0f, d_grad, st))) return e;
+  if ((e = apg_rollout_backward(cfg, d_params, p_ins, d_cur, p_inr, p_ref, nullptr, d_ws, 1.0f, d_grad, st))) return e;
   if (loss_host && (ce = cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, st))) return (int)ce;
   if (grad_params_host &&
       (ce = cudaMemcpyAsync(grad_params_host, d_grad, sizeof(float) * y.n_params, cudaMemcpyDeviceToHost, st)))

@@ -12,13 +12,9 @@
 #include "layouts.h"
 #include "rollout_args.h"
 #include "tile_engine.cuh"
+#include "hutter_policy.cuh"
 
 namespace apg {
-
-__device__ __forceinline__ void load_tile_manual(float* dst, const float* __restrict__ src, int row_floats, int valid) {
-  const int nv = valid * row_floats;
-  for (int i = threadIdx.x; i < TM * row_floats; i += NT) dst[i] = i < nv ? src[i] : 0.f;
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // forward
@@ -74,22 +70,7 @@ __global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y,
       __syncthreads();
     }
     // ---- first layer: state branch and reference branch -> X1 = [s | r]
-    dense<SrcAoS, EPI_ACT>(L, SrcAoS{s_ins, y.F0, 0}, y.F0, s_w + y.f_ws, HID, s_w + y.f_bs, HID / 4, s_x1, 0, 1,
-                           ACT_TANH);
-    if (CONV) {
-      // Conv1d(RD -> 20, k=3, valid) over the L reference rows == npos dense layers on shifted 3*RD windows;
-      // output index is channel-major c*npos + t (hutter_model.py:36-40)
-      const int ncg = CONV_CH / 4;
-      for (int vg = L.og0; vg < y.npos * ncg; vg += 16) {
-        const int t = vg / ncg, cg = vg - t * ncg;
-        float acc[4][4] = {};
-        mac_tile(acc, SrcAoS{s_inr, y.LR, y.RD * t}, y.KC, s_w + y.f_wr + 4 * cg, CONV_CH, L.dg);
-        store_tile<EPI_ACT>(acc, s_w + y.f_br, cg, s_x1, HID + t, y.npos, ACT_RELU, L.dg);
-      }
-    } else {
-      dense<SrcAoS, EPI_ACT>(L, SrcAoS{s_inr, y.LR, 0}, y.LR, s_w + y.f_wr, HID, s_w + y.f_br, HID / 4, s_x1, HID, 1,
-                             ACT_TANH);
-    }
+    hutter_first_layer<CONV>(L, y, s_w, s_ins, s_inr, s_x1);
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -98,43 +79,10 @@ __global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y,
       bulk_s2g(g.st_x1 + (size_t)tile * y.K1 * TMP, s_x1, y.K1 * TMP * 4);
       bulk_commit();
     }
-    // ---- fc1
-    dense<SrcT, EPI_ACT>(L, SrcT{s_x1}, y.K1, s_w + y.f_w1, HID, s_w + y.f_b1, HID / 4, s_h, 0, 1, ACT_TANH);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      bulk_s2g(g.st_h1 + (size_t)tile * HID * TMP, s_h, HID * TMP * 4);
-      bulk_commit();
-      bulk_wait_read<1>();      // the X1 store has finished reading s_x1
-    }
-    __syncthreads();
-    // ---- fc2 : s_h -> s_x1 rows [0,64)
-    dense<SrcT, EPI_ACT>(L, SrcT{s_h}, HID, s_w + y.f_w2, HID, s_w + y.f_b2, HID / 4, s_x1, 0, 1, ACT_TANH);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      bulk_s2g(g.st_h2 + (size_t)tile * HID * TMP, s_x1, HID * TMP * 4);
-      bulk_commit();
-      bulk_wait_read<1>();      // the h1 store has finished reading s_h
-    }
-    __syncthreads();
-    // ---- fc3 : s_x1 rows [0,64) -> s_h
-    dense<SrcT, EPI_ACT>(L, SrcT{s_x1}, HID, s_w + y.f_w3, HID, s_w + y.f_b3, HID / 4, s_h, 0, 1, ACT_TANH);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      bulk_s2g(g.st_h3 + (size_t)tile * HID * TMP, s_h, HID * TMP * 4);
-      bulk_commit();
-    }
-    // ---- fc_out + sigmoid (train_base.py:202-203) : s_h -> s_x1 rows [64, 64+Mo4)
+    // ---- fc1, fc2, fc3, fc_out + sigmoid (train_base.py:202-203); every activation is stashed for the adjoint
     float* s_act = s_x1 + HID * TMP;
-    dense<SrcT, EPI_ACT>(L, SrcT{s_h}, HID, s_w + y.f_wo, y.Mo4, s_w + y.f_bo, y.Mo4 / 4, s_act, 0, 1, ACT_SIGMOID);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      bulk_s2g(g.st_act + (size_t)tile * y.Mo4 * TMP, s_act, y.Mo4 * TMP * 4);
-      bulk_commit();
-    }
+    hutter_trunk(L, y, s_w, s_x1, s_h, g.st_h1 + (size_t)tile * HID * TMP, g.st_h2 + (size_t)tile * HID * TMP,
+                 g.st_h3 + (size_t)tile * HID * TMP, g.st_act + (size_t)tile * y.Mo4 * TMP);
     // ---- horizon: one thread per drone
     float my_loss = 0.f;
     if (tid < valid) {
@@ -160,72 +108,6 @@ __global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y,
 // ------------------------------------------------------------------------------------------------------------
 // adjoint
 // ------------------------------------------------------------------------------------------------------------
-// conv_ref weight gradient: dWc[c][d][j] = sum_t sum_drone dz[c*npos+t][drone] * in_ref[drone][(t+j)*RD + d].
-// One warp per position t, lanes over the 3*RD window entries, 20 channel accumulators per lane; the 8 per-warp
-// partials are combined in a fixed order through shared-memory scratch.
-__device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, const float* __restrict__ dzr,
-                                        const float* __restrict__ s_inr, float* __restrict__ scratch,
-                                        float* __restrict__ P) {
-  float acc[CONV_CH], accb[CONV_CH];
-#pragma unroll
-  for (int c = 0; c < CONV_CH; ++c) acc[c] = accb[c] = 0.f;
-  const bool kin = L.lane < y.KC;
-  for (int t = L.warp; t < y.npos; t += NWARP) {
-    for (int d4 = 0; d4 < TM / 4; ++d4) {
-      const float* xp = s_inr + (4 * d4) * y.LR + y.RD * t + L.lane;
-      const float4 xv = kin ? make_float4(xp[0], xp[y.LR], xp[2 * y.LR], xp[3 * y.LR])
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < CONV_CH; ++c) {
-        const float4 z = *reinterpret_cast<const float4*>(dzr + (c * y.npos + t) * TMP + 4 * d4);
-        acc[c] = dot4(z, xv, acc[c]);
-        accb[c] += (z.x + z.y) + (z.z + z.w);
-      }
-    }
-  }
-  const int stride = CONV_CH * y.KC + CONV_CH;
-  float* my = scratch + L.warp * stride;
-#pragma unroll
-  for (int c = 0; c < CONV_CH; ++c) {
-    if (kin) my[c * y.KC + L.lane] = acc[c];
-    if (L.lane == 0) my[CONV_CH * y.KC + c] = accb[c];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < stride; idx += NT) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) s += scratch[w * stride + idx];
-    if (idx < CONV_CH * y.KC) {
-      const int c = idx / y.KC, kk = idx - c * y.KC;
-      const int j = kk / y.RD, dch = kk - j * y.RD;
-      P[y.t_wc + c * y.KC + dch * 3 + j] += s;      // torch layout [c][d][j]
-    } else {
-      P[y.t_bc + idx - CONV_CH * y.KC] += s;
-    }
-  }
-}
-
-template <int NKI>
-__device__ __forceinline__ void dw_T_dispatch(const Lane& L, const float* dz, int M, const float* x, int K, float* P,
-                                              int ldp, float* Pb) {
-  dw_T<NKI>(L, dz, M, x, K, P, ldp, Pb);
-}
-
-__device__ __forceinline__ void dw_T_any(const Lane& L, const float* dz, int M, const float* x, int K, float* P,
-                                         int ldp, float* Pb) {
-  const int nki = (K + 31) / 32;
-  switch (nki) {
-    case 1: dw_T<1>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 2: dw_T<2>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 3: dw_T<3>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 4: dw_T<4>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 5: dw_T<5>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 6: dw_T<6>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 7: dw_T<7>(L, dz, M, x, K, P, ldp, Pb); break;
-    default: dw_T<8>(L, dz, M, x, K, P, ldp, Pb); break;
-  }
-}
-
 template <template <typename> class SysT, bool CONV>
 __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y, const RolloutArgs g) {
   extern __shared__ __align__(128) float smem[];

@@ -154,6 +154,57 @@ def test_cartpole_vs_oracle_random(h, n):
     _check_grads(grads, og)
 
 
+def _random_ar_params(h, seed):
+    torch.manual_seed(seed)
+    shapes = [(64, 15), (64,), (20, 9, 3), (20,), (64, 9 * h), (64,), (64, 64 + 20 * (h - 2)), (64,), (64, 64), (64,),
+              (64, 64), (64,), (4, 64), (4,)]
+    out = []
+    for s_ in shapes:
+        fan_in = s_[1] * (s_[2] if len(s_) == 3 else 1) if len(s_) > 1 else 64
+        out.append((torch.rand(*s_) * 2 - 1) / fan_in ** 0.5)
+    return out
+
+
+@pytest.mark.parametrize("fname", ["rec_ar_rand.npz", "rec_ar_rand_pos0.npz"])
+def test_autoregressive_forward_vs_reference_golden(fname):
+    """the reference's AR train step only has a forward (its backward() raises): loss / actions / states"""
+    R, SY, P, _capi, O = _imports()
+    g = load_golden(fname)
+    params = golden_params(g)
+    h, dt = int(g["h"]), float(g["dt"])
+    spec = R.RolloutSpec.quad_recurrent("autoregressive", h, dt, "cumulative")
+    loss, states, actions, grads, _ = _run_gpu(R, spec, params, None, t(g["cur"]), t(g["in_ref"]), t(g["ref"]))
+    assert abs(loss - float(g["loss"])) <= LOSS_TOL * abs(float(g["loss"])), (loss, float(g["loss"]))
+    assert max_rel_to_scale(actions, g["actions"]) <= 2e-5
+    assert max_rel_to_scale(states, g["states"]) <= 2e-5
+    # gradient oracle: autograd on the forward-pinned functional restatement
+    ol, og, _, _ = O.recurrent_value_and_grad("autoregressive", params, t(g["cur"]), t(g["in_ref"]), t(g["ref"]), h, dt,
+                                              window="cumulative")
+    _check_grads(grads, og, tol=2e-4)
+
+
+@pytest.mark.parametrize("window,h,n,pos0", [("cumulative", 10, 70, False), ("relative", 10, 70, False),
+                                             ("cumulative", 10, 333, True), ("relative", 6, 64, True),
+                                             ("cumulative", 5, 1, False)])
+def test_autoregressive_vs_oracle_random(window, h, n, pos0):
+    R, SY, P, _capi, O = _imports()
+    dt = 0.1
+    case = SY.quad_case(n, 2 * h, dt, seed=100 + n)
+    cur = case["cur"].clone()
+    if pos0:
+        cur[:, :3] = 0.3 * torch.randn(n, 3, generator=torch.Generator().manual_seed(n))
+        cur[:, 9:12] = 0.2 * torch.randn(n, 3, generator=torch.Generator().manual_seed(n + 1))
+    params = _random_ar_params(h, seed=n)
+    spec = R.RolloutSpec.quad_recurrent("autoregressive", h, dt, window)
+    loss, states, actions, grads, _ = _run_gpu(R, spec, params, None, cur, case["in_ref"], case["ref"])
+    ol, og, ost, oact = O.recurrent_value_and_grad("autoregressive", params, cur, case["in_ref"], case["ref"], h, dt,
+                                                   window=window)
+    assert abs(loss - float(ol)) <= LOSS_TOL * abs(float(ol)), (loss, float(ol))
+    assert max_rel_to_scale(actions, oact) <= 2e-5
+    assert max_rel_to_scale(states, ost) <= 2e-5
+    _check_grads(grads, og, tol=2e-4)
+
+
 def test_host_buffer_entry_point_matches_device_path():
     R, SY, P, _capi, O = _imports()
     n, h, dt = 300, 10, 0.1
