@@ -54,6 +54,13 @@ int check_config(const apg_config* c) {
     if (c->state_feat < 1 || c->state_feat > 32) return APG_ERR_BAD_CONFIG;
     return 0;
   }
+  if (c->net == NET_LSTM) {
+    if (c->mode != MODE_LSTM || c->system != SYS_QUAD) return APG_ERR_UNSUPPORTED;
+    if (c->out_dim != 4 || c->state_feat != 15 || c->ref_dim != 9 || c->ref_len != c->horizon) return APG_ERR_BAD_CONFIG;
+    if (c->horizon < 3 || c->horizon > 10) return APG_ERR_BAD_CONFIG;
+    if (c->window != WINDOW_CUMULATIVE && c->window != WINDOW_RELATIVE) return APG_ERR_BAD_CONFIG;
+    return 0;
+  }
   if (c->net == NET_SIMPLE) {
     if (c->mode != MODE_CONCURRENT || c->system != SYS_CARTPOLE) return APG_ERR_UNSUPPORTED;
     if (c->out_dim != c->horizon || c->state_feat != 4 || c->horizon < 2) return APG_ERR_BAD_CONFIG;
@@ -63,6 +70,8 @@ int check_config(const apg_config* c) {
 }
 
 SimpleLayout simple_layout(const apg_config* c) { return make_simple_layout(c->state_feat, c->out_dim); }
+LstmLayout lstm_layout(const apg_config* c) { return make_lstm_layout(c->state_feat, c->ref_len, c->ref_dim, c->out_dim); }
+PackTable lstm_pack_table(const LstmLayout& y);
 
 PackTable simple_pack_table(const SimpleLayout& y);
 
@@ -76,9 +85,17 @@ HutterLayout hutter_layout(const apg_config* c) {
   return make_hutter_layout(c->state_feat, c->ref_len, c->ref_dim, c->out_dim, c->net == NET_HUTTER_CONV);
 }
 
+// contiguous source [rows][cols]; destination row stride ldd, zero-filled up to ldd
 void add_seg(PackTable& t, int which, int mode, int src, int dst, int rows, int cols, int ldd) {
   PackSeg& s = t.seg[t.n++];
-  s.which = which; s.mode = mode; s.src = src; s.dst = dst; s.rows = rows; s.cols = cols; s.ldd = ldd;
+  s.which = which; s.mode = mode; s.src = src; s.sld = cols; s.dst = dst; s.rows = rows; s.cols = cols;
+  s.wcols = ldd; s.ldd = ldd;
+}
+// general form: strided source, destination window of wcols columns inside rows of stride ldd
+void add_seg_ex(PackTable& t, int which, int mode, int src, int sld, int dst, int rows, int cols, int wcols, int ldd) {
+  PackSeg& s = t.seg[t.n++];
+  s.which = which; s.mode = mode; s.src = src; s.sld = sld; s.dst = dst; s.rows = rows; s.cols = cols;
+  s.wcols = wcols; s.ldd = ldd;
 }
 
 PackTable hutter_pack_table(const HutterLayout& y) {
@@ -125,12 +142,38 @@ NetInfo net_info(const apg_config* c) {
     n.n_params = y.n_params; n.f_total = y.f_total; n.b_total = y.b_total;
     n.x1_rows = y.K1; n.h_rows = HID; n.act_rows = y.Mo4;
     n.steps = is_recurrent(c) ? c->horizon : 1;
+  } else if (c->net == NET_LSTM) {
+    const LstmLayout y = lstm_layout(c);
+    n.n_params = y.n_params; n.f_total = y.f_total; n.b_total = y.b_total;
+    n.x1_rows = y.ROWS; n.h_rows = 0; n.act_rows = 0; n.steps = c->horizon;
   } else {
     const SimpleLayout y = simple_layout(c);
     n.n_params = y.n_params; n.f_total = y.f_total; n.b_total = y.b_total;
     n.x1_rows = y.rows_total; n.h_rows = 0; n.act_rows = 0; n.steps = 1;
   }
   return n;
+}
+
+PackTable lstm_pack_table(const LstmLayout& y) {
+  PackTable t;
+  t.n = 0;
+  const int G = 4 * LSTM_HS, f0p = pad4(y.F0), nc = CONV_CH * y.npos, mo4 = pad4(y.Mo);
+  add_seg(t, 0, PK_CONV_FWD, y.t_wc, y.f_wc, CONV_CH, y.KC, CONV_CH);
+  add_seg(t, 0, PK_COPY_PAD, y.t_bc, y.f_bc, 1, CONV_CH, CONV_CH);
+  add_seg_ex(t, 0, PK_TRANSPOSE, y.t_wih, y.IH, y.f_wg, G, y.F0, G, G);
+  if (f0p > y.F0) add_seg_ex(t, 0, PK_COPY_PAD, y.t_wih, 1, y.f_wg + y.F0 * G, f0p - y.F0, 0, G, G);
+  add_seg_ex(t, 0, PK_TRANSPOSE, y.t_wih + y.F0, y.IH, y.f_wg + f0p * G, G, nc, G, G);
+  add_seg_ex(t, 0, PK_TRANSPOSE, y.t_whh, LSTM_HS, y.f_wg + y.KX * G, G, LSTM_HS, G, G);
+  add_seg(t, 0, PK_COPY_PAD, y.t_bih, y.f_bih, 1, G, G);
+  add_seg(t, 0, PK_COPY_PAD, y.t_bhh, y.f_bhh, 1, G, G);
+  add_seg(t, 0, PK_TRANSPOSE, y.t_wo, y.f_wo, y.Mo, LSTM_HS, mo4);
+  add_seg(t, 0, PK_COPY_PAD, y.t_bo, y.f_bo, 1, y.Mo, mo4);
+  add_seg_ex(t, 1, PK_COPY_PAD, y.t_wih, y.IH, y.b_wg, G, y.F0, f0p, y.KG);
+  add_seg_ex(t, 1, PK_COPY_PAD, y.t_wih + y.F0, y.IH, y.b_wg + f0p, G, nc, nc, y.KG);
+  add_seg_ex(t, 1, PK_COPY_PAD, y.t_whh, LSTM_HS, y.b_wg + y.KX, G, LSTM_HS, LSTM_HS, y.KG);
+  add_seg(t, 1, PK_COPY_PAD, y.t_wo, y.b_wo, y.Mo, LSTM_HS, LSTM_HS);
+  add_seg(t, 1, PK_CONV_BWD, y.t_wc, y.b_wc, CONV_CH, y.KC, y.ld_bwr);
+  return t;
 }
 
 PackTable simple_pack_table(const SimpleLayout& y) {
@@ -255,6 +298,12 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
       return (int)ce;
     if (is_recurrent(cfg)) { if ((ce = launch_rec_fwd(y, a, p.grid, st))) return (int)ce; }
     else if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
+  } else if (cfg->net == NET_LSTM) {
+    if (!h0c0) return APG_ERR_BAD_CONFIG;
+    const LstmLayout y = lstm_layout(cfg);
+    if ((ce = launch_pack(lstm_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
+      return (int)ce;
+    if ((ce = launch_lstm_fwd(y, a, p.grid, st))) return (int)ce;
   } else {
     const SimpleLayout y = simple_layout(cfg);
     if ((ce = launch_pack(simple_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
@@ -281,6 +330,8 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
   if (is_hutter(cfg)) {
     if (is_recurrent(cfg)) { if ((ce = launch_rec_adj(hutter_layout(cfg), a, p.grid, st))) return (int)ce; }
     else if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
+  } else if (cfg->net == NET_LSTM) {
+    if ((ce = launch_lstm_adj(lstm_layout(cfg), a, p.grid, st))) return (int)ce;
   } else {
     if ((ce = launch_simple_adj(simple_layout(cfg), a, p.grid, st))) return (int)ce;
   }
@@ -304,8 +355,10 @@ __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const
   const size_t n_inr = (size_t)N * cfg->ref_len * cfg->ref_dim * rec, n_ref = (size_t)N * h * refw * rec;
   const size_t b_inr = up256(sizeof(float) * n_inr + 16);
   const size_t b_ref = up256(sizeof(float) * n_ref + 16);
+  const size_t n_hc = cfg->net == NET_LSTM ? (size_t)2 * N * LSTM_HS : 0;
+  const size_t b_hc = up256(sizeof(float) * n_hc + 16);
   const size_t b_ws = apg_workspace_bytes(cfg);
-  const size_t need = 2 * b_params + b_ins + b_cur + b_inr + b_ref + 256 + b_ws;
+  const size_t need = 2 * b_params + b_ins + b_cur + b_inr + b_ref + b_hc + 256 + b_ws;
   cudaError_t ce;
   if (!g_cache.stream && (ce = cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking))) return (int)ce;
   if (g_cache.cap < need) {
@@ -322,6 +375,7 @@ __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const
   float* d_cur = reinterpret_cast<float*>(b);    b += b_cur;
   float* d_inr = reinterpret_cast<float*>(b);    b += b_inr;
   float* d_ref = reinterpret_cast<float*>(b);    b += b_ref;
+  float* d_hc = reinterpret_cast<float*>(b);     b += b_hc;
   float* d_loss = reinterpret_cast<float*>(b);   b += 256;
   void* d_ws = b;
   cudaStream_t st = g_cache.stream;
@@ -332,14 +386,15 @@ __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const
   APG_H2D(d_cur, cur_host, sizeof(float) * (size_t)N * S)
   APG_H2D(d_inr, in_ref_host, sizeof(float) * n_inr)
   APG_H2D(d_ref, ref_host, sizeof(float) * n_ref)
+  APG_H2D(d_hc, h0c0_host, sizeof(float) * n_hc)
 #undef APG_H2D
-  (void)h0c0_host;
+  const float* p_hc = (h0c0_host && n_hc) ? d_hc : nullptr;
   const float* p_ins = in_state_host ? d_ins : nullptr;
   const float* p_inr = in_ref_host ? d_inr : nullptr;
   const float* p_ref = ref_host ? d_ref : nullptr;
-  if ((e = apg_rollout_forward(cfg, d_params, p_ins, d_cur, p_inr, p_ref, nullptr, d_ws, d_loss, nullptr, nullptr, st)))
+  if ((e = apg_rollout_forward(cfg, d_params, p_ins, d_cur, p_inr, p_ref, p_hc, d_ws, d_loss, nullptr, nullptr, st)))
     return e;
-  if ((e = apg_rollout_backward(cfg, d_params, p_ins, d_cur, p_inr, p_ref, nullptr, d_ws, 1.0f, d_grad, st))) return e;
+  if ((e = apg_rollout_backward(cfg, d_params, p_ins, d_cur, p_inr, p_ref, p_hc, d_ws, 1.0f, d_grad, st))) return e;
   if (loss_host && (ce = cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, st))) return (int)ce;
   if (grad_params_host &&
       (ce = cudaMemcpyAsync(grad_params_host, d_grad, sizeof(float) * y.n_params, cudaMemcpyDeviceToHost, st)))

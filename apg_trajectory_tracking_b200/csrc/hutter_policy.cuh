@@ -17,19 +17,25 @@ __device__ __forceinline__ void load_tile_manual(float* dst, const float* __rest
 //          relu, output index channel-major c*npos + t (hutter_model.py:36-40)
 //   !CONV: tanh(ref_in(ref))
 // s_ins / s_inr are the drone-major input tiles [TM][F0] / [TM][L*RD].
+// Conv1d(RD -> 20, k=3, valid) + relu on the drone-major reference tile s_inr [TM][LR]; output rows row0 + c*npos + t
+__device__ __forceinline__ void conv_layer_fwd(const Lane& L, int npos, int RD, int LR, int KC, const float* Wc,
+                                               const float* bc, const float* s_inr, float* Y, int row0) {
+  const int ncg = CONV_CH / 4;
+  for (int vg = L.og0; vg < npos * ncg; vg += 16) {
+    const int t = vg / ncg, cg = vg - t * ncg;
+    float acc[4][4] = {};
+    mac_tile(acc, SrcAoS{s_inr, LR, RD * t}, KC, Wc + 4 * cg, CONV_CH, L.dg);
+    store_tile<EPI_ACT>(acc, bc, cg, Y, row0 + t, npos, ACT_RELU, L.dg);
+  }
+}
+
 template <bool CONV>
 __device__ __forceinline__ void hutter_first_layer(const Lane& L, const HutterLayout& y, const float* s_w,
                                                    const float* s_ins, const float* s_inr, float* s_x1) {
   dense<SrcAoS, EPI_ACT>(L, SrcAoS{s_ins, y.F0, 0}, y.F0, s_w + y.f_ws, HID, s_w + y.f_bs, HID / 4, s_x1, 0, 1,
                          ACT_TANH);
   if (CONV) {
-    const int ncg = CONV_CH / 4;
-    for (int vg = L.og0; vg < y.npos * ncg; vg += 16) {
-      const int t = vg / ncg, cg = vg - t * ncg;
-      float acc[4][4] = {};
-      mac_tile(acc, SrcAoS{s_inr, y.LR, y.RD * t}, y.KC, s_w + y.f_wr + 4 * cg, CONV_CH, L.dg);
-      store_tile<EPI_ACT>(acc, s_w + y.f_br, cg, s_x1, HID + t, y.npos, ACT_RELU, L.dg);
-    }
+    conv_layer_fwd(L, y.npos, y.RD, y.LR, y.KC, s_w + y.f_wr, s_w + y.f_br, s_inr, s_x1, HID);
   } else {
     dense<SrcAoS, EPI_ACT>(L, SrcAoS{s_inr, y.LR, 0}, y.LR, s_w + y.f_wr, HID, s_w + y.f_br, HID / 4, s_x1, HID, 1,
                            ACT_TANH);

@@ -13,6 +13,8 @@ cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutAr
 
 cudaError_t launch_rec_fwd(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_rec_adj(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_lstm_fwd(const LstmLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_lstm_adj(const LstmLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 size_t simple_fwd_smem_bytes(const SimpleLayout& y);
 size_t simple_adj_smem_bytes(const SimpleLayout& y);
 cudaError_t launch_simple_fwd(const SimpleLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);

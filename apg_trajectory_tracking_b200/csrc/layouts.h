@@ -115,9 +115,60 @@ inline __host__ SimpleLayout make_simple_layout(int F0, int Mo) {
   return y;
 }
 
+// ---- LSTM policy (models/rnn.py): conv encoder -> LSTMCell(15 + 20*npos, 8) -> Linear(8, 4)
+// Per-step activation arena of a tile (feature-major rows of TMP floats), stashed whole for the adjoint:
+//   [0,15) features, 15 zero pad, [16,KX) conv (c*npos+t), [KX,KX+8) h_prev, then c_prev(8), gates i|f|g|o (32),
+//   c'(8), h'(8), actions(4)
+constexpr int LSTM_HS = 8;
+struct LstmLayout {
+  int F0, L, RD, Mo, npos, KC, LR, IH, KX, KG, ROWS;
+  int R_HP, R_CP, R_G, R_C, R_H, R_A;
+  int t_wc, t_bc, t_wr, t_br, t_wo, t_bo, t_wih, t_whh, t_bih, t_bhh, n_params;
+  int f_wc, f_bc, f_wg, f_bih, f_bhh, f_wo, f_bo, f_total;
+  int b_wg, b_wo, b_wc, ld_bwr, b_total;
+  HutterLayout cv;     // the conv-encoder fields the shared conv helpers read (npos, KC, LR, RD, L, t_wc, t_bc, ld_bwr)
+};
+
+inline __host__ LstmLayout make_lstm_layout(int F0, int L, int RD, int Mo) {
+  LstmLayout y;
+  y.F0 = F0; y.L = L; y.RD = RD; y.Mo = Mo;
+  y.npos = L - 2; y.KC = 3 * RD; y.LR = L * RD;
+  y.IH = F0 + CONV_CH * y.npos;
+  y.KX = pad4(F0) + CONV_CH * y.npos;
+  y.KG = y.KX + LSTM_HS;
+  y.R_HP = y.KX; y.R_CP = y.KX + 8; y.R_G = y.KX + 16; y.R_C = y.KX + 48; y.R_H = y.KX + 56; y.R_A = y.KX + 64;
+  y.ROWS = y.KX + 68;
+  int o = 0;
+  y.t_wc = o; o += CONV_CH * RD * 3;  y.t_bc = o; o += CONV_CH;
+  y.t_wr = o; o += HID * y.LR;        y.t_br = o; o += HID;
+  y.t_wo = o; o += Mo * LSTM_HS;      y.t_bo = o; o += Mo;
+  y.t_wih = o; o += 4 * LSTM_HS * y.IH;
+  y.t_whh = o; o += 4 * LSTM_HS * LSTM_HS;
+  y.t_bih = o; o += 4 * LSTM_HS;
+  y.t_bhh = o; o += 4 * LSTM_HS;
+  y.n_params = o;
+  o = 0;
+  y.f_wc = o; o += pad4(y.KC * CONV_CH);  y.f_bc = o; o += CONV_CH;
+  y.f_wg = o; o += y.KG * 4 * LSTM_HS;
+  y.f_bih = o; o += 4 * LSTM_HS;          y.f_bhh = o; o += 4 * LSTM_HS;
+  y.f_wo = o; o += LSTM_HS * pad4(Mo);    y.f_bo = o; o += pad4(Mo);
+  y.f_total = o;
+  y.ld_bwr = pad4(y.KC);
+  o = 0;
+  y.b_wg = o; o += 4 * LSTM_HS * y.KG;
+  y.b_wo = o; o += pad4(Mo * LSTM_HS);
+  y.b_wc = o; o += CONV_CH * y.ld_bwr;
+  y.b_total = o;
+  y.cv = make_hutter_layout(F0, L, RD, Mo, 1);
+  y.cv.t_wc = y.t_wc; y.cv.t_bc = y.t_bc; y.cv.ld_bwr = y.ld_bwr;
+  return y;
+}
+
 // Segment table of the pack kernel: dst[...] = src[...] with a layout transform.
 enum PackMode { PK_COPY_PAD = 0, PK_TRANSPOSE = 1, PK_CONV_FWD = 2, PK_CONV_BWD = 3 };
-struct PackSeg { int src, dst, rows, cols, ldd, mode, which; };   // which: 0 -> fwd buffer, 1 -> bwd buffer
+// src is [rows][cols] with row stride sld; the destination window is `wcols` wide (zero-filled beyond the data)
+// with row stride ldd.  which: 0 -> fwd buffer, 1 -> bwd buffer
+struct PackSeg { int src, sld, dst, rows, cols, wcols, ldd, mode, which; };
 constexpr int MAX_PACK_SEGS = 24;
 struct PackTable { int n; PackSeg seg[MAX_PACK_SEGS]; };
 

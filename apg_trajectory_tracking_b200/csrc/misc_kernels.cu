@@ -12,16 +12,21 @@ __global__ void apg_pack_kernel(const PackTable t, const float* __restrict__ par
     const float* src = params + g.src;
     float* dst = (g.which ? wb : wf) + g.dst;
     int total;
-    if (g.mode == PK_COPY_PAD || g.mode == PK_CONV_BWD) total = g.rows * g.ldd;
+    if (g.mode == PK_COPY_PAD) total = g.rows * g.wcols;
+    else if (g.mode == PK_CONV_BWD) total = g.rows * g.ldd;
+    else if (g.mode == PK_TRANSPOSE) total = g.cols * g.wcols;
     else total = g.cols * g.ldd;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
       float v = 0.f;
-      if (g.mode == PK_COPY_PAD) {                 // dst[r][c], c < ldd
-        const int r = i / g.ldd, c = i - r * g.ldd;
-        if (c < g.cols) v = src[r * g.cols + c];
-      } else if (g.mode == PK_TRANSPOSE) {         // dst[c][r], r < ldd  (src [rows][cols])
-        const int c = i / g.ldd, r = i - c * g.ldd;
-        if (r < g.rows) v = src[r * g.cols + c];
+      int di = i;
+      if (g.mode == PK_COPY_PAD) {                 // dst[r][c], c < wcols
+        const int r = i / g.wcols, c = i - r * g.wcols;
+        if (c < g.cols) v = src[r * g.sld + c];
+        di = r * g.ldd + c;
+      } else if (g.mode == PK_TRANSPOSE) {         // dst[c][r], r < wcols  (src [rows][cols])
+        const int c = i / g.wcols, r = i - c * g.wcols;
+        if (r < g.rows) v = src[r * g.sld + c];
+        di = c * g.ldd + r;
       } else if (g.mode == PK_CONV_FWD) {          // src [C=rows][RD][3] -> dst[kk = j*RD + d][c], cols = 3*RD
         const int kk = i / g.ldd, c = i - kk * g.ldd;
         const int rd = g.cols / 3, j = kk / rd, d = kk - j * rd;
@@ -31,7 +36,7 @@ __global__ void apg_pack_kernel(const PackTable t, const float* __restrict__ par
         const int rd = g.cols / 3;
         if (kk < g.cols) { const int j = kk / rd, d = kk - j * rd; v = src[c * g.cols + d * 3 + j]; }
       }
-      dst[i] = v;
+      dst[di] = v;
     }
   }
 }

@@ -32,13 +32,13 @@ def _spec_for(R, system, h, dt):
     return R.RolloutSpec.cartpole_concurrent(h, dt)
 
 
-def _run_gpu(R, spec, params, in_state, cur, in_ref, ref):
+def _run_gpu(R, spec, params, in_state, cur, in_ref, ref, h0c0=None):
     dev = "cuda:0"
     n = cur.shape[0]
     runner = R.Rollout(spec, n, dev)
     flat = R.flatten_params(params).to(dev)
     cu = lambda x: None if x is None else x.to(dev).contiguous()
-    loss, states, actions = runner.forward(flat, cu(in_state), cu(cur), cu(in_ref), cu(ref), None, True, True)
+    loss, states, actions = runner.forward(flat, cu(in_state), cu(cur), cu(in_ref), cu(ref), cu(h0c0), True, True)
     grad = runner.backward(1.0)
     torch.cuda.synchronize()
     return float(loss.item()), states.cpu(), actions.cpu(), R.split_flat(grad.cpu(), params), runner
@@ -199,6 +199,52 @@ def test_autoregressive_vs_oracle_random(window, h, n, pos0):
     loss, states, actions, grads, _ = _run_gpu(R, spec, params, None, cur, case["in_ref"], case["ref"])
     ol, og, ost, oact = O.recurrent_value_and_grad("autoregressive", params, cur, case["in_ref"], case["ref"], h, dt,
                                                    window=window)
+    assert abs(loss - float(ol)) <= LOSS_TOL * abs(float(ol)), (loss, float(ol))
+    assert max_rel_to_scale(actions, oact) <= 2e-5
+    assert max_rel_to_scale(states, ost) <= 2e-5
+    _check_grads(grads, og, tol=2e-4)
+
+
+def _random_lstm_params(h, seed):
+    torch.manual_seed(seed)
+    ih = 15 + 20 * (h - 2)
+    shapes = [(20, 9, 3), (20,), (64, 9 * h), (64,), (4, 8), (4,), (32, ih), (32, 8), (32,), (32,)]
+    fans = [27, 27, 9 * h, 9 * h, 8, 8, 8, 8, 8, 8]
+    return [(torch.rand(*s_) * 2 - 1) / f ** 0.5 for s_, f in zip(shapes, fans)]
+
+
+def test_lstm_forward_vs_reference_golden():
+    R, SY, P, _capi, O = _imports()
+    g = load_golden("rec_lstm_rand.npz")
+    params = golden_params(g)
+    h, dt = int(g["h"]), float(g["dt"])
+    h0c0 = torch.stack((t(g["h0"]), t(g["c0"])), 0)
+    spec = R.RolloutSpec.quad_recurrent("lstm", h, dt, "cumulative")
+    loss, states, actions, grads, _ = _run_gpu(R, spec, params, None, t(g["cur"]), t(g["in_ref"]), t(g["ref"]), h0c0)
+    assert abs(loss - float(g["loss"])) <= LOSS_TOL * abs(float(g["loss"])), (loss, float(g["loss"]))
+    assert max_rel_to_scale(actions, g["actions"]) <= 2e-5
+    assert max_rel_to_scale(states, g["states"]) <= 2e-5
+    ol, og, _, _ = O.recurrent_value_and_grad("lstm", params, t(g["cur"]), t(g["in_ref"]), t(g["ref"]), h, dt,
+                                              window="cumulative", hc0=(t(g["h0"]), t(g["c0"])))
+    _check_grads(grads, og, tol=2e-4)
+
+
+@pytest.mark.parametrize("window,h,n", [("cumulative", 10, 70), ("relative", 10, 130), ("cumulative", 6, 64),
+                                        ("cumulative", 10, 1000)])
+def test_lstm_vs_oracle_random(window, h, n):
+    R, SY, P, _capi, O = _imports()
+    dt = 0.1
+    case = SY.quad_case(n, 2 * h, dt, seed=200 + n)
+    cur = case["cur"].clone()
+    cur[:, :3] = 0.2 * torch.randn(n, 3, generator=torch.Generator().manual_seed(n))
+    gen = torch.Generator().manual_seed(n + 5)
+    h0, c0 = torch.randn(n, 8, generator=gen), torch.randn(n, 8, generator=gen)
+    params = _random_lstm_params(h, seed=n)
+    spec = R.RolloutSpec.quad_recurrent("lstm", h, dt, window)
+    loss, states, actions, grads, _ = _run_gpu(R, spec, params, None, cur, case["in_ref"], case["ref"],
+                                               torch.stack((h0, c0), 0))
+    ol, og, ost, oact = O.recurrent_value_and_grad("lstm", params, cur, case["in_ref"], case["ref"], h, dt,
+                                                   window=window, hc0=(h0, c0))
     assert abs(loss - float(ol)) <= LOSS_TOL * abs(float(ol)), (loss, float(ol))
     assert max_rel_to_scale(actions, oact) <= 2e-5
     assert max_rel_to_scale(states, ost) <= 2e-5
