@@ -1,0 +1,90 @@
+"""Trainer base of the rollout hot path (reference: ``scripts/train_base.py`` ``TrainBase``).
+
+Kept: the constructor keywords that select the hot-path variant, ``init_optimizer`` (DataLoader + SGD momentum 0.9,
+:130-143), ``run_epoch`` (:188-218), the abstract ``train_controller_model``.  The mini-batch body of ``run_epoch``
+is ONE fused rollout (forward + adjoint kernel) followed by the torch optimizer step.  Out of scope here
+(SURVEY.md section 2): evaluation, self-play data, curriculum, model saving, TensorBoard."""
+from collections import defaultdict
+
+import torch
+import torch.optim as optim
+
+from .. import train as T
+
+
+class _NullWriter:
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
+class TrainBase:
+    def __init__(self, train_dynamics, eval_dynamics, sample_in="train_env", delta_t=0.05, delta_t_train=0.05,
+                 epoch_size=500, batch_size=8, state_size=12, horizon=10, ref_dim=3, action_dim=4,
+                 learning_rate_controller=0.0001, learning_rate_dynamics=0.001, train_mode="concurrent",
+                 system="quad", window="cumulative", device=None, **kwargs):
+        self.sample_in = sample_in
+        self.delta_t, self.delta_t_train = delta_t, delta_t_train
+        self.epoch_size, self.batch_size = epoch_size, batch_size
+        self.state_size, self.horizon, self.ref_dim, self.action_dim = state_size, horizon, ref_dim, action_dim
+        self.learning_rate_controller = learning_rate_controller
+        self.learning_rate_dynamics = learning_rate_dynamics
+        self.train_mode, self.system, self.window = train_mode, system, window
+        self.device = device
+        self.config = dict(kwargs)
+        self.results_dict = defaultdict(list)
+        self.results_dict["loss"].append(0)
+        self.train_dynamics, self.eval_dynamics = train_dynamics, eval_dynamics
+        self.state_data, self.net, self.fused = None, None, None
+        self.writer = _NullWriter()
+        if self.train_mode in ("autoregressive", "LSTM"):
+            self.actions_out_dim, self.ref_length = self.action_dim, self.horizon * 2
+        elif self.train_mode == "concurrent":
+            self.actions_out_dim, self.ref_length = self.action_dim * self.horizon, self.horizon
+        else:
+            raise ValueError("Train mode must be one of concurrent, autoregressive, or LSTM")
+
+    # dt the rollout integrates with (the wing trainer uses delta_t_train, train_fixed_wing.py:101-103)
+    def rollout_dt(self):
+        return self.delta_t
+
+    def modified_params(self):
+        cfg = getattr(self.train_dynamics, "cfg", None)
+        return self.config.get("modified_params", {}) if cfg is None else self.config.get("modified_params", {})
+
+    def init_optimizer(self):
+        if self.state_data is not None:
+            self.trainloader = torch.utils.data.DataLoader(self.state_data, batch_size=self.batch_size, shuffle=True,
+                                                           num_workers=0)
+        spec = T.spec_for_net(self.net, self.system, self.horizon, self.rollout_dt(), self.train_mode, self.window,
+                              self.modified_params())
+        self.fused = T.ModuleRollout(self.net, spec, self.device)
+        self.optimizer_controller = optim.SGD(self.net.parameters(), lr=self.learning_rate_controller, momentum=0.9)
+
+    def train_controller_model(self, current_state, action_seq, in_ref_state, ref_states):
+        """implemented in the sub classes (un-fused path: the caller already evaluated the policy)"""
+        raise NotImplementedError
+
+    def fused_train_step(self, in_state, current_state, in_ref_state, ref_states):
+        """zero_grad -> rollout loss + analytic gradient (two launches) -> optimizer step"""
+        self.optimizer_controller.zero_grad()
+        h0c0 = None
+        if self.train_mode == "LSTM":
+            self.net.reset_hidden_state(current_state.size()[0])
+            h0c0 = torch.stack((self.net.hidden_state, self.net.cell_state), 0)
+        loss = self.fused.loss_and_grad(None if self.train_mode != "concurrent" else in_state, current_state,
+                                        in_ref_state, ref_states, h0c0)
+        self.writer.add_scalar("loss/training", loss)
+        self.optimizer_controller.step()
+        return loss
+
+    def run_epoch(self, train="controller", epoch=0):
+        running_loss, i = 0.0, 0
+        for i, data in enumerate(self.trainloader, 0):
+            in_state, current_state, in_ref_state, ref_states = data
+            loss = self.fused_train_step(in_state, current_state, in_ref_state, ref_states)
+            running_loss += loss.item()
+        epoch_loss = running_loss / max(i, 1)      # the reference divides by the last batch index (:213)
+        self.results_dict["loss"].append(epoch_loss)
+        self.results_dict["trained"].append(train)
+        self.writer.add_scalar("Loss/train", epoch_loss, epoch)
+        return epoch_loss

@@ -1,0 +1,123 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/apg_b200.h declares,
+its host-only entry points (layout arithmetic) answer correctly, and the Python mirror refuses CPU tensors
+(no CPU fallback).  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from apg_trajectory_tracking_b200 import build as B, _capi
+    B.build()
+    return _capi
+
+
+def test_library_exports_every_declared_symbol(capi):
+    hdr = open(os.path.join(ROOT, "include", "apg_b200.h")).read()
+    declared = set(re.findall(r"\b(apg_[a-z_0-9]+)\s*\(", hdr))
+    assert declared >= {"apg_rollout_forward", "apg_rollout_backward", "apg_rollout_value_and_grad_host",
+                        "apg_dynamics_step", "apg_dynamics_step_adjoint", "apg_num_params", "apg_workspace_bytes"}
+    raw = ctypes.CDLL(capi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/apg_b200.h but not exported"
+    assert set(capi.EXPORTS) == declared
+    assert capi.lib().apg_version() >= 1
+    assert b"success" in capi.lib().apg_error_string(0)
+
+
+@pytest.mark.parametrize("fname,spec_args,expected", [
+    ("conc_quad_rand.npz", ("quad", "concurrent", 10), 32728),
+    ("conc_wing_rand_h20.npz", ("wing", "concurrent", 20), 22872),
+    ("conc_cartpole_kat6.npz", ("cartpole", "concurrent", 10), 8842),
+    ("rec_ar_rand.npz", ("quad", "autoregressive", 10), 30388),
+    ("rec_lstm_rand.npz", ("quad", "lstm", 10), 12340),
+])
+def test_param_counts_match_reference_models(capi, fname, spec_args, expected):
+    """apg_num_params == sum of net.parameters() sizes of the reference nets"""
+    from apg_trajectory_tracking_b200 import rollout as R
+    g = load_golden(fname)
+    n_ref = sum(g[f"param_{i}"].size for i in range(len(g["param_names"])))
+    system, mode, h = spec_args
+    if mode == "concurrent":
+        spec = {"quad": R.RolloutSpec.quad_concurrent, "wing": R.RolloutSpec.wing_concurrent,
+                "cartpole": R.RolloutSpec.cartpole_concurrent}[system](h)
+    else:
+        spec = R.RolloutSpec.quad_recurrent(mode, h)
+    cfg = spec.config(128)
+    n = capi.lib().apg_num_params(ctypes.byref(cfg))
+    assert n == n_ref == expected
+    assert capi.lib().apg_workspace_bytes(ctypes.byref(cfg)) > 0
+
+
+def test_bad_configs_are_rejected(capi):
+    from apg_trajectory_tracking_b200 import rollout as R
+    lib = capi.lib()
+    cfg = R.RolloutSpec.quad_concurrent(10).config(16)
+    cfg.out_dim = 39
+    assert lib.apg_num_params(ctypes.byref(cfg)) == -1          # APG_ERR_BAD_CONFIG
+    cfg = R.RolloutSpec.wing_concurrent(10).config(16)
+    cfg.mode = 1
+    assert lib.apg_num_params(ctypes.byref(cfg)) == -2          # APG_ERR_UNSUPPORTED
+    cfg = R.RolloutSpec.quad_concurrent(10).config(0)
+    assert lib.apg_num_params(ctypes.byref(cfg)) == -1
+    with pytest.raises(capi.ApgError):
+        capi.check(-2)
+
+
+def test_module_mirror_has_reference_parameter_names_and_shapes():
+    import neural_control  # noqa: F401  (top-level alias of the mirror package)
+    from neural_control.models.hutter_model import Net
+    from neural_control.models.rnn import LSTM_NEW
+    from neural_control.models.simple_model import Net as SimpleNet
+    for fname, net in (("conc_quad_rand.npz", Net(15, 10, 9, 40)), ("conc_wing_rand_h20.npz", Net(9, 1, 3, 80, conv=False)),
+                       ("conc_cartpole_kat6.npz", SimpleNet(4, 10)), ("rec_ar_rand.npz", Net(15, 10, 9, 4)),
+                       ("rec_lstm_rand.npz", LSTM_NEW(15, 10, 9, 4))):
+        g = load_golden(fname)
+        names = [str(x) for x in g["param_names"]]
+        mine = list(net.named_parameters())
+        assert [n for n, _ in mine] == names
+        assert [tuple(p.shape) for _, p in mine] == [g[f"param_{i}"].shape for i in range(len(names))]
+
+
+def test_no_cpu_fallback():
+    from apg_trajectory_tracking_b200 import _capi
+    from neural_control.models.hutter_model import Net
+    from neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from neural_control.dynamics.cartpole_dynamics import CartpoleDynamics
+    from neural_control.drone_loss import quad_mpc_loss
+    from neural_control.dataset import state_preprocessing
+    with pytest.raises(_capi.ApgError):
+        Net(15, 10, 9, 40)(torch.zeros(2, 15), torch.zeros(2, 10, 9))
+    with pytest.raises(_capi.ApgError):
+        FlightmareDynamics()(torch.zeros(2, 12), torch.zeros(2, 4), 0.1)
+    with pytest.raises(_capi.ApgError):
+        CartpoleDynamics()(torch.zeros(2, 4), torch.zeros(2, 1), 0.05)
+    with pytest.raises(_capi.ApgError):
+        state_preprocessing(torch.zeros(2, 12))
+    with pytest.raises(_capi.ApgError):
+        quad_mpc_loss(torch.zeros(2, 10, 12), torch.zeros(2, 10, 9), torch.zeros(2, 10, 4))
+    if not torch.cuda.is_available():
+        from apg_trajectory_tracking_b200 import rollout as R
+        with pytest.raises(_capi.ApgError):
+            R.Rollout(R.RolloutSpec.quad_concurrent(10), 8)
+
+
+def test_physical_constants_match_reference_config():
+    from apg_trajectory_tracking_b200 import params as P
+    q = P.quad_phys()
+    assert abs(q[0] - 0.723) < 1e-7 and abs(q[1] - 0.723 / 12 * 0.31 ** 2 * 4.5) < 1e-8 and q[9] == np.float32(-9.81)
+    q2 = P.quad_phys({"mass": 1.0})
+    assert q2[0] == 1.0 and q2[1] != q[1]
+    w = P.wing_phys()
+    assert abs(w[4] + 0.00105) < 1e-9 and abs(w[40] - 0.16534698176788384) < 1e-7
+    c = P.cartpole_phys()
+    assert list(c[:5]) == [1.0, np.float32(0.1), 0.5, 30.0, 0.5]
