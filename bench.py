@@ -34,11 +34,20 @@ WORKLOADS = {
                             flops_per_step=8.1e3, label="fixed-wing MLP Net(9,1,3,80) h=20 N=131072/GPU"),
     "cartpole_concurrent": dict(system="cartpole", mode="concurrent", h=5, dt=0.05, n=128, bytes_per_step=12.8,
                                 flops_per_step=10e3, label="cartpole MLP Net(4,5) h=5 B=128"),
+    "quad_autoregressive": dict(system="quad", mode="autoregressive", h=10, dt=0.1, n=65536, bytes_per_step=225.6,
+                                flops_per_step=169e3, label="quad autoregressive Net(15,10,9,4) h=10 N=65536/GPU"),
+    "quad_lstm": dict(system="quad", mode="lstm", h=10, dt=0.1, n=32768, bytes_per_step=238.4, flops_per_step=62e3,
+                      label="quad LSTM_NEW(15,10,9,4) h=10 N=32768/GPU"),
 }
 LR = {"quad": 1e-5, "wing": 1e-4, "cartpole": 1e-5}
 
 
-def hutter_shapes(system, h):
+def hutter_shapes(system, h, mode="concurrent"):
+    if mode == "autoregressive":
+        return [(64, 15), (64,), (20, 9, 3), (20,), (64, 9 * h), (64,), (64, 64 + 20 * (h - 2)), (64,), (64, 64), (64,),
+                (64, 64), (64,), (4, 64), (4,)]
+    if mode == "lstm":
+        return [(20, 9, 3), (20,), (64, 9 * h), (64,), (4, 8), (4,), (32, 15 + 20 * (h - 2)), (32, 8), (32,), (32,)]
     if system == "quad":
         return [(64, 15), (64,), (20, 9, 3), (20,), (64, 9 * h), (64,), (64, 64 + 20 * (h - 2)), (64,), (64, 64), (64,),
                 (64, 64), (64,), (4 * h, 64), (4 * h,)]
@@ -48,22 +57,31 @@ def hutter_shapes(system, h):
     return [(32, 4), (32,), (64, 32), (64,), (64, 64), (64,), (32, 64), (32,), (h, 32), (h,)]
 
 
-def default_init(system, h, seed=0):
+def default_init(system, h, seed=0, mode="concurrent"):
     """PyTorch default (kaiming-uniform, a=sqrt(5)) initialisation == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for both
     weights and biases of Linear / Conv1d; drawn tensor by tensor from a seeded generator."""
     g = torch.Generator().manual_seed(seed)
     out, fan_in = [], 1
-    for s in hutter_shapes(system, h):
+    for s in hutter_shapes(system, h, mode):
         if len(s) > 1:
             fan_in = 1
             for d in s[1:]:
                 fan_in *= d
+        if mode == "lstm" and s[0] == 32:
+            fan_in = 8                       # nn.LSTMCell initialises everything with U(-1/sqrt(hidden), ..)
         out.append((torch.rand(*s, generator=g) * 2 - 1) / fan_in ** 0.5)
     return out
 
 
 def make_case(w, n, seed, device):
     from apg_trajectory_tracking_b200 import synthetic as SY
+    if w.get("mode", "concurrent") != "concurrent":
+        c = SY.quad_case(n, 2 * w["h"], w["dt"], seed=seed, device=device)
+        c["in_state"] = None
+        if w["mode"] == "lstm":
+            g = torch.Generator().manual_seed(seed + 77)
+            c["h0c0"] = torch.stack((torch.randn(n, 8, generator=g), torch.randn(n, 8, generator=g)), 0).to(device)
+        return c
     if w["system"] == "quad":
         return SY.quad_case(n, w["h"], w["dt"], seed=seed, device=device)
     if w["system"] == "wing":
@@ -75,6 +93,8 @@ def make_case(w, n, seed, device):
 
 def make_spec(w):
     from apg_trajectory_tracking_b200 import rollout as R
+    if w.get("mode", "concurrent") != "concurrent":
+        return R.RolloutSpec.quad_recurrent(w["mode"], w["h"], w["dt"])
     if w["system"] == "quad":
         return R.RolloutSpec.quad_concurrent(w["h"], w["dt"])
     if w["system"] == "wing":
@@ -150,8 +170,13 @@ def cpu_reference_step(w, n, params, case, threads):
 
     def step():
         nonlocal ps, bufs
-        loss, grads, _, _ = O.concurrent_value_and_grad(w["system"], ps, case["in_state"], case["cur"], case["in_ref"],
-                                                        case["ref"], w["h"], w["dt"])
+        if w.get("mode", "concurrent") == "concurrent":
+            loss, grads, _, _ = O.concurrent_value_and_grad(w["system"], ps, case["in_state"], case["cur"],
+                                                            case["in_ref"], case["ref"], w["h"], w["dt"])
+        else:
+            hc = (case["h0c0"][0], case["h0c0"][1]) if w["mode"] == "lstm" else None
+            loss, grads, _, _ = O.recurrent_value_and_grad(w["mode"], ps, case["cur"], case["in_ref"], case["ref"],
+                                                           w["h"], w["dt"], hc0=hc)
         ps, bufs = O.sgd_momentum_step(ps, grads, bufs, lr)
         return float(loss)
     return step
@@ -174,9 +199,9 @@ def run_reference(args, w, rank):
     if rank != 0:
         return
     threads = physical_cores()
-    n = w["n"]
+    n = w["n"] if w.get("mode", "concurrent") == "concurrent" else min(w["n"], 8192)   # bounded sample per step
     case = make_case(w, n, 1234, "cpu")
-    params = default_init(w["system"], w["h"])
+    params = default_init(w["system"], w["h"], mode=w.get("mode", "concurrent"))
     step = cpu_reference_step(w, n, params, case, threads)
     for _ in range(args.warmup):
         step()
@@ -192,7 +217,7 @@ def run_reference(args, w, rank):
         "config": {"workload": w["label"].replace("/GPU", " (one host)"), "horizon": w["h"], "n_drones": n,
                    "note": "CPU arm: oracle port of the reference's PyTorch op chain (autograd tape) + SGD step"},
         "cpu_baseline": {"value": value, "unit": "drone-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"full workload N={n}, {args.steps} iterations"},
+                         "sample": f"N={n} drones x h={w['h']} per step, {args.steps} iterations"},
         "e2e": {"value": value, "unit": "drone-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,7 +227,7 @@ def run_reference(args, w, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="quad_concurrent", choices=sorted(WORKLOADS))
@@ -234,7 +259,7 @@ def main():
 
     n, h = w["n"], w["h"]
     case = make_case(w, n, 1234 + rank, dev)
-    params = default_init(w["system"], h)
+    params = default_init(w["system"], h, mode=w.get("mode", "concurrent"))
     stepper = T.FusedTrainStep(params, make_spec(w), n, lr=LR[w["system"]], device=dev)
 
     def barrier():
@@ -243,15 +268,18 @@ def main():
         torch.cuda.synchronize()
 
     flush_buf = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    args_step = (case["in_state"], case["cur"], case.get("in_ref"), case.get("ref"))
+    args_step = (case["in_state"], case["cur"], case.get("in_ref"), case.get("ref"), case.get("h0c0"))
 
+    # clocks are sampled from the warm-up to the end of the timed region (and, if that is shorter than ~1.5 s,
+    # over extra identical untimed steps appended after it) so that a 200 ms sampler sees the loaded clocks
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_sampler0 = time.perf_counter()
     for _ in range(args.warmup):
         stepper.step(*args_step)
     barrier()
 
     # ---- device-timed region: K steps, an event pair (+ one in the middle) around each
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -271,7 +299,15 @@ def main():
         e[3].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    extra_steps = 0
+    while time.perf_counter() - t_sampler0 < 1.5 and extra_steps < 5000:
+        stepper.step(*args_step)
+        extra_steps += 1
+        if extra_steps % 20 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
+    clocks["note"] = f"sampled over warm-up + timed region + {extra_steps} identical untimed steps"
     t_step = [e[0].elapsed_time(e[3]) for e in ev]
     t_fwd = [e[0].elapsed_time(e[1]) for e in ev]
     t_adj = [e[1].elapsed_time(e[2]) for e in ev]
@@ -288,12 +324,13 @@ def main():
     host = {k: (v.cpu().pin_memory() if v is not None else None) for k, v in case.items()}
     h2d = sum(v.numel() * 4 for v in host.values() if v is not None)
     e2e_steps = max(3, min(args.steps, 10))
+    hargs = (host["in_state"], host["cur"], host.get("in_ref"), host.get("ref"), host.get("h0c0"))
     for _ in range(2):
-        float(stepper.step(host["in_state"], host["cur"], host.get("in_ref"), host.get("ref")).item())
+        float(stepper.step(*hargs).item())
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        float(stepper.step(host["in_state"], host["cur"], host.get("in_ref"), host.get("ref")).item())
+        float(stepper.step(*hargs).item())
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -305,7 +342,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = physical_cores()
-        ncpu = min(n, 65536)
+        ncpu = min(n, 65536) if w.get("mode", "concurrent") == "concurrent" else min(n, 8192)
         ccase = make_case(w, ncpu, 1234, "cpu")
         cstep = cpu_reference_step(w, ncpu, params, ccase, threads)
         cstep()
@@ -323,6 +360,8 @@ def main():
         # dominant kernel = the adjoint kernel (+ its tiny gradient-reduce epilogue launch): it re-reads every
         # per-drone input once -> algorithmic bytes per launch = half of the fwd+bwd per-step figure
         adj_bytes = 0.5 * w["bytes_per_step"] * n * h
+        kname = {"concurrent": "hutter_adj_kernel", "autoregressive": "rec_adj_kernel", "lstm": "lstm_adj_kernel"}[
+            w.get("mode", "concurrent")] if w["system"] != "cartpole" else "simple_adj_kernel"
         achieved = adj_bytes / (ms_adj * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -343,7 +382,7 @@ def main():
                        "parallelism": f"dp{world} (drone-axis shards, one NCCL sum-allreduce of the flat gradient)"},
             "ms_forward_kernel": ms_fwd, "ms_adjoint_kernel": ms_adj, "wall_s_timed_region": t_wall,
             "final_loss": final_loss,
-            "roofline": {"bound": "hbm", "kernel": "adjoint (hutter_adj_kernel + reduce)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": f"adjoint ({kname} + apg_reduce_kernel)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = per-drone inputs read once by the adjoint pass; the path is "
