@@ -115,6 +115,12 @@ def test_loss_curve_matches_oracle_training(system):
     ps, bufs = [p.clone() for p in params], [None] * len(params)
     for it in range(iters):
         case = bench.make_case(w, n, 50 + it, "cpu")
+        if system == "cartpole":
+            # pole near upright like the reference's training data (thresh_div <= 0.21, cartpole_env.py:178-236):
+            # a falling pole crosses the atan2 branch cut at +-pi inside the horizon, where a 1-ulp difference flips
+            # the wrapped angle by 2 pi (true of the reference as well) -- no fp32 tolerance can absorb that
+            case["cur"][:, 2] *= 0.07
+            case["in_state"] = case["cur"].clone()
         gl = stepper.step(*[None if case.get(k) is None else case[k].to(DEV) for k in ("in_state", "cur", "in_ref", "ref")])
         ol, og, _, _ = O.concurrent_value_and_grad(system, ps, case["in_state"], case["cur"], case.get("in_ref"),
                                                    case.get("ref"), h, dt)
