@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libapg_b200.so")
+LIB_PATH = os.environ.get("APG_B200_LIB", os.path.join(HERE, "libapg_b200.so"))
 MAX_PHYS = 48
 
 c_float_p = ctypes.c_void_p   # device / host pointers are passed as raw addresses

@@ -14,6 +14,13 @@
 #include "tile_engine.cuh"
 #include "hutter_policy.cuh"
 
+#ifdef APG_PROFILE
+__device__ long long g_apg_prof[2][148][APG_NPROF];
+extern "C" __attribute__((visibility("default"))) int apg_debug_profile(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_apg_prof, sizeof(long long) * 2 * 148 * APG_NPROF);
+}
+#endif
+
 namespace apg {
 
 // ------------------------------------------------------------------------------------------------------------
@@ -59,11 +66,14 @@ __global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y,
 
   uint32_t in_phase = 0;
   float cta_loss = 0.f;
+  PROF_DECL
+  PROF(0);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int valid = min(TM, g.N - tile * TM);
     if (valid == TM) {
       mbar_wait(bar_in, in_phase);
       in_phase ^= 1;
+      PROF(1);
     } else {
       load_tile_manual(s_ins, g.in_state + (size_t)tile * TM * y.F0, y.F0, valid);
       load_tile_manual(s_inr, g.in_ref + (size_t)tile * TM * y.LR, y.LR, valid);
@@ -73,6 +83,7 @@ __global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y,
     hutter_first_layer<CONV>(L, y, s_w, s_ins, s_inr, s_x1);
     fence_proxy_async();
     __syncthreads();
+    PROF(2);
     if (tid == 0) {
       const int next = tile + gridDim.x;
       if (next < ntiles && tile_full(next)) issue_inputs(next);        // input buffers are free again
@@ -83,6 +94,7 @@ __global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y,
     float* s_act = s_x1 + HID * TMP;
     hutter_trunk(L, y, s_w, s_x1, s_h, g.st_h1 + (size_t)tile * HID * TMP, g.st_h2 + (size_t)tile * HID * TMP,
                  g.st_h3 + (size_t)tile * HID * TMP, g.st_act + (size_t)tile * y.Mo4 * TMP);
+    PROF(3);
     // ---- horizon: one thread per drone
     float my_loss = 0.f;
     if (tid < valid) {
@@ -93,16 +105,20 @@ __global__ void __launch_bounds__(NT, 1) hutter_fwd_kernel(const HutterLayout y,
                                        g.actions_out ? g.actions_out + drone * g.h * A : nullptr);
     }
     const float tl = block_sum(my_loss, s_red);
+    PROF(4);
     if (tid == 0) {
       cta_loss += tl;
       bulk_wait_read<0>();      // every stash store has finished reading shared memory
     }
     __syncthreads();
+    PROF(5);
   }
   if (tid == 0) {
     g.loss_partials[blockIdx.x] = cta_loss;
     bulk_wait_all();
   }
+  PROF(6);
+  PROF_FLUSH(0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -155,6 +171,8 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
   mbar_wait(bar_w, 0);
 
   uint32_t ph = 0, ph_in = 0;
+  PROF_DECL
+  PROF(0);
   for (int tile = first; tile >= 0; tile -= gridDim.x) {
     const int valid = min(TM, g.N - tile * TM);
     // ---- reverse sweep through the dynamics -> d loss / d logits in bufC rows [0, h*A)
@@ -168,30 +186,40 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
       }
     }
     __syncthreads();
+    PROF(1);
     // ---- fc_out
     mbar_wait(bar_B, ph);
+    PROF(2);
     dw_T<2>(L, bufC, y.Mo, bufB, HID, P + y.t_wo, HID, P + y.t_bo);
     __syncthreads();
+    PROF(3);
     dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, y.Mo, s_w + y.b_wo, HID, nullptr, HID / 4, bufB, 0, 1, 0);   // dz3 over h3
     fence_proxy_async();
     __syncthreads();
+    PROF(4);
     if (tid == 0) {
       mbar_expect_tx(bar_C, hbytes);
       bulk_g2s(bufC, g.st_h1 + (size_t)tile * HID * TMP, hbytes, bar_C);
     }
     // ---- fc3
     mbar_wait(bar_D, ph);
+    PROF(5);
     dw_T<2>(L, bufB, HID, bufD, HID, P + y.t_w3, HID, P + y.t_b3);
     __syncthreads();
+    PROF(6);
     dense<SrcT, EPI_DTANH>(L, SrcT{bufB}, HID, s_w + y.b_w3, HID, nullptr, HID / 4, bufD, 0, 1, 0);    // dz2 over h2
     __syncthreads();
+    PROF(7);
     // ---- fc2
     mbar_wait(bar_C, ph);
+    PROF(8);
     dw_T<2>(L, bufD, HID, bufC, HID, P + y.t_w2, HID, P + y.t_b2);
     __syncthreads();
+    PROF(9);
     dense<SrcT, EPI_DTANH>(L, SrcT{bufD}, HID, s_w + y.b_w2, HID, nullptr, HID / 4, bufC, 0, 1, 0);    // dz1 over h1
     fence_proxy_async();
     __syncthreads();
+    PROF(10);
     // bufB | bufD are dead: fetch the input tiles into them while fc1 is processed
     if (valid == TM) {
       if (tid == 0) {
@@ -205,19 +233,23 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
     }
     // ---- fc1
     mbar_wait(bar_A, ph);
+    PROF(11);
     dw_T_any(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
     __syncthreads();
+    PROF(12);
     dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, HID, s_w + y.b_w1, y.K1, nullptr, HID / 4, bufA, 0, 1, 0);   // ds over s
     if (CONV)
       dense<SrcT, EPI_DRELU>(L, SrcT{bufC}, HID, s_w + y.b_w1 + HID, y.K1, nullptr, y.NRtot / 4, bufA, HID, 1, 0);
     else
       dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, HID, s_w + y.b_w1 + HID, y.K1, nullptr, y.NRtot / 4, bufA, HID, 1, 0);
     __syncthreads();
+    PROF(13);
     // ---- first layer weight gradients (no dX: the inputs need no gradient in concurrent mode)
     if (valid == TM) {
       mbar_wait(bar_in, ph_in);
       ph_in ^= 1;
     }
+    PROF(14);
     dw_AoS(L, bufA, HID, s_ins, y.F0, 0, y.F0, P + y.t_ws, y.F0, P + y.t_bs);
     if (CONV)
       conv_dw(L, y, bufA + HID * TMP, s_inr, scratch, P);
@@ -225,10 +257,12 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
       dw_AoS(L, bufA + HID * TMP, HID, s_inr, y.LR, 0, y.LR, P + y.t_wr, y.LR, P + y.t_br);
     fence_proxy_async();
     __syncthreads();
+    PROF(15);
     ph ^= 1;
     const int next = tile - gridDim.x;
     if (tid == 0 && next >= 0) issue_stage_loads(next);
   }
+  PROF_FLUSH(1);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -17,6 +17,19 @@
 #include <stdint.h>
 #include "layouts.h"
 
+// ---- optional per-phase cycle accounting (build with -DAPG_PROFILE; tools/phase_profile.py) ----------------
+#ifdef APG_PROFILE
+#define APG_NPROF 24
+#define PROF_DECL long long prof_t0_ = clock64(); long long prof_acc_[APG_NPROF]; \
+  for (int i_ = 0; i_ < APG_NPROF; ++i_) prof_acc_[i_] = 0;
+#define PROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); prof_acc_[i] += t_ - prof_t0_; prof_t0_ = t_; } } while (0)
+#define PROF_FLUSH(k) do { if (threadIdx.x == 0 && blockIdx.x < 148) for (int i_ = 0; i_ < APG_NPROF; ++i_) g_apg_prof[k][blockIdx.x][i_] = prof_acc_[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i) do { } while (0)
+#define PROF_FLUSH(k) do { } while (0)
+#endif
+
 namespace apg {
 
 
