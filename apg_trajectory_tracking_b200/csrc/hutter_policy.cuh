@@ -124,9 +124,9 @@ __device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, co
     if (idx < CONV_CH * y.KC) {
       const int c = idx / y.KC, kk = idx - c * y.KC;
       const int j = kk / y.RD, dch = kk - j * y.RD;
-      P[y.t_wc + c * y.KC + dch * 3 + j] += s;      // torch layout [c][d][j]
+      red_add(P + y.t_wc + c * y.KC + dch * 3 + j, s);      // torch layout [c][d][j]
     } else {
-      P[y.t_bc + idx - CONV_CH * y.KC] += s;
+      red_add(P + y.t_bc + idx - CONV_CH * y.KC, s);
     }
   }
 }

@@ -193,13 +193,13 @@ __device__ __forceinline__ void lstm_dw_gates(const Lane& L, const LstmLayout& y
 #pragma unroll
       for (int i = 0; i < NKI; ++i) {
         const int k = L.lane + 32 * i;
-        if (k < y.F0) P[y.t_wih + j * y.IH + k] += acc[jj][i];
-        else if (k >= f0p && k < y.KX) P[y.t_wih + j * y.IH + k - (f0p - y.F0)] += acc[jj][i];
-        else if (k >= y.KX && k < K) P[y.t_whh + j * LSTM_HS + (k - y.KX)] += acc[jj][i];
+        if (k < y.F0) red_add(P + y.t_wih + j * y.IH + k, acc[jj][i]);
+        else if (k >= f0p && k < y.KX) red_add(P + y.t_wih + j * y.IH + k - (f0p - y.F0), acc[jj][i]);
+        else if (k >= y.KX && k < K) red_add(P + y.t_whh + j * LSTM_HS + (k - y.KX), acc[jj][i]);
       }
       if (L.lane == 0) {
-        P[y.t_bih + j] += accb[jj];
-        P[y.t_bhh + j] += accb[jj];
+        red_add(P + y.t_bih + j, accb[jj]);
+        red_add(P + y.t_bhh + j, accb[jj]);
       }
     }
   }

@@ -204,6 +204,13 @@ __device__ __forceinline__ void dense(const Lane& L, const Src& A, int K, const 
 // weight-gradient contractions.  P points at the CTA's partial-gradient matrix in global memory (torch layout
 // [M][ldp]); each (j,k) entry is owned by exactly one thread -> plain read-modify-write, deterministic.
 // ------------------------------------------------------------------------------------------------------------
+// Accumulate into the CTA's gradient partial without waiting for the old value: red.global.add.f32.  Every address is
+// owned by exactly one thread of one CTA for the whole launch (same-address reductions of one thread retire in
+// program order), so the result is deterministic although the instruction is an atomic.
+__device__ __forceinline__ void red_add(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float c) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, c))));
 }
@@ -245,9 +252,9 @@ __device__ __forceinline__ void dw_T(const Lane& L, const float* __restrict__ dz
 #pragma unroll
         for (int i = 0; i < NKI; ++i) {
           const int k = L.lane + 32 * i;
-          if (k < K) P[j * ldp + k] += acc[jj][i];
+          if (k < K) red_add(P + j * ldp + k, acc[jj][i]);
         }
-        if (Pb && L.lane == 0) Pb[j] += accb[jj];
+        if (Pb && L.lane == 0) red_add(Pb + j, accb[jj]);
       }
     }
   }
@@ -277,8 +284,8 @@ __device__ __forceinline__ void dw_AoS(const Lane& L, const float* __restrict__ 
     for (int jj = 0; jj < 8; ++jj) {
       const int j = j0 + jj;
       if (j < M) {
-        if (kin) P[j * ldp + L.lane] += acc[jj];
-        if (Pb && L.lane == 0) Pb[j] += accb[jj];
+        if (kin) red_add(P + j * ldp + L.lane, acc[jj]);
+        if (Pb && L.lane == 0) red_add(Pb + j, accb[jj]);
       }
     }
   }
