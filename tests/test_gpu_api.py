@@ -105,7 +105,7 @@ def test_loss_curve_matches_oracle_training(system):
     from oracle import apg_oracle as O
     import bench
     n, iters = 256, 20
-    h = {"quad": 10, "wing": 10, "cartpole": 10}[system]
+    h = {"quad": 10, "wing": 10, "cartpole": 5}[system]
     dt = {"quad": 0.1, "wing": 0.05, "cartpole": 0.05}[system]
     lr = {"quad": 1e-5, "wing": 1e-4, "cartpole": 1e-5}[system]
     w = dict(system=system, h=h, dt=dt)
@@ -116,10 +116,12 @@ def test_loss_curve_matches_oracle_training(system):
     for it in range(iters):
         case = bench.make_case(w, n, 50 + it, "cpu")
         if system == "cartpole":
-            # pole near upright like the reference's training data (thresh_div <= 0.21, cartpole_env.py:178-236):
-            # a falling pole crosses the atan2 branch cut at +-pi inside the horizon, where a 1-ulp difference flips
-            # the wrapped angle by 2 pi (true of the reference as well) -- no fp32 tolerance can absorb that
-            case["cur"][:, 2] *= 0.07
+            # pole near upright and slow like the reference's training data (thresh_div <= 0.21,
+            # cartpole_env.py:178-236), horizon 5 (BASELINE config 0): the open-loop pole diverges with e^(5.6 t)
+            # and a falling pole crosses the atan2 branch cut at +-pi, where a 1-ulp difference flips the wrapped
+            # angle by 2 pi (true of the reference as well) -- no fp32 tolerance can absorb that
+            case["cur"][:, 2] *= 0.02
+            case["cur"][:, 3] *= 0.2
             case["in_state"] = case["cur"].clone()
         gl = stepper.step(*[None if case.get(k) is None else case[k].to(DEV) for k in ("in_state", "cur", "in_ref", "ref")])
         ol, og, _, _ = O.concurrent_value_and_grad(system, ps, case["in_state"], case["cur"], case.get("in_ref"),
