@@ -190,10 +190,10 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
     // ---- fc_out
     mbar_wait(bar_B, ph);
     PROF(2);
-    dw_T<2>(L, bufC, y.Mo, bufB, HID, P + y.t_wo, HID, P + y.t_bo);
+    dw_auto(L, bufC, y.Mo, bufB, HID, P + y.t_wo, HID, P + y.t_bo);
     __syncthreads();
     PROF(3);
-    dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, y.Mo, s_w + y.b_wo, HID, nullptr, HID / 4, bufB, 0, 1, 0);   // dz3 over h3
+    dense_auto<EPI_DTANH>(L, bufC, y.Mo, s_w + y.b_wo, HID, mma_sw(HID), nullptr, HID, bufB, 0, 0);   // dz3 over h3
     fence_proxy_async();
     __syncthreads();
     PROF(4);
@@ -204,19 +204,19 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
     // ---- fc3
     mbar_wait(bar_D, ph);
     PROF(5);
-    dw_T<2>(L, bufB, HID, bufD, HID, P + y.t_w3, HID, P + y.t_b3);
+    dw_auto(L, bufB, HID, bufD, HID, P + y.t_w3, HID, P + y.t_b3);
     __syncthreads();
     PROF(6);
-    dense<SrcT, EPI_DTANH>(L, SrcT{bufB}, HID, s_w + y.b_w3, HID, nullptr, HID / 4, bufD, 0, 1, 0);    // dz2 over h2
+    dense_auto<EPI_DTANH>(L, bufB, HID, s_w + y.b_w3, HID, mma_sw(HID), nullptr, HID, bufD, 0, 0);    // dz2 over h2
     __syncthreads();
     PROF(7);
     // ---- fc2
     mbar_wait(bar_C, ph);
     PROF(8);
-    dw_T<2>(L, bufD, HID, bufC, HID, P + y.t_w2, HID, P + y.t_b2);
+    dw_auto(L, bufD, HID, bufC, HID, P + y.t_w2, HID, P + y.t_b2);
     __syncthreads();
     PROF(9);
-    dense<SrcT, EPI_DTANH>(L, SrcT{bufD}, HID, s_w + y.b_w2, HID, nullptr, HID / 4, bufC, 0, 1, 0);    // dz1 over h1
+    dense_auto<EPI_DTANH>(L, bufD, HID, s_w + y.b_w2, HID, mma_sw(HID), nullptr, HID, bufC, 0, 0);    // dz1 over h1
     fence_proxy_async();
     __syncthreads();
     PROF(10);
@@ -234,14 +234,14 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
     // ---- fc1
     mbar_wait(bar_A, ph);
     PROF(11);
-    dw_T_any(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
+    dw_auto(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
     __syncthreads();
     PROF(12);
-    dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, HID, s_w + y.b_w1, y.K1, nullptr, HID / 4, bufA, 0, 1, 0);   // ds over s
+    dense_auto<EPI_DTANH>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, HID, bufA, 0, 0);   // ds over s
     if (CONV)
-      dense<SrcT, EPI_DRELU>(L, SrcT{bufC}, HID, s_w + y.b_w1 + HID, y.K1, nullptr, y.NRtot / 4, bufA, HID, 1, 0);
+      dense_auto<EPI_DRELU>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, y.NRtot, bufA, HID, 0, HID);
     else
-      dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, HID, s_w + y.b_w1 + HID, y.K1, nullptr, y.NRtot / 4, bufA, HID, 1, 0);
+      dense_auto<EPI_DTANH>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, y.NRtot, bufA, HID, 0, HID);
     __syncthreads();
     PROF(13);
     // ---- first layer weight gradients (no dX: the inputs need no gradient in concurrent mode)

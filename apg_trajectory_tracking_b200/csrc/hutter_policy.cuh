@@ -48,7 +48,7 @@ __device__ __forceinline__ void hutter_first_layer(const Lane& L, const HutterLa
 __device__ __forceinline__ void hutter_trunk(const Lane& L, const HutterLayout& y, const float* s_w, float* s_x1,
                                              float* s_h, float* st_h1, float* st_h2, float* st_h3, float* st_act) {
   const int tid = threadIdx.x;
-  dense<SrcT, EPI_ACT>(L, SrcT{s_x1}, y.K1, s_w + y.f_w1, HID, s_w + y.f_b1, HID / 4, s_h, 0, 1, ACT_TANH);
+  dense_auto<EPI_ACT>(L, s_x1, y.K1, s_w + y.f_w1, HID, mma_sw(HID), s_w + y.f_b1, HID, s_h, 0, ACT_TANH);
   fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void hutter_trunk(const Lane& L, const HutterLayout& 
   }
   __syncthreads();
   // fc2 : s_h -> s_x1 rows [0,64)
-  dense<SrcT, EPI_ACT>(L, SrcT{s_h}, HID, s_w + y.f_w2, HID, s_w + y.f_b2, HID / 4, s_x1, 0, 1, ACT_TANH);
+  dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_w2, HID, mma_sw(HID), s_w + y.f_b2, HID, s_x1, 0, ACT_TANH);
   fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
@@ -68,7 +68,7 @@ __device__ __forceinline__ void hutter_trunk(const Lane& L, const HutterLayout& 
   }
   __syncthreads();
   // fc3 : s_x1 rows [0,64) -> s_h
-  dense<SrcT, EPI_ACT>(L, SrcT{s_x1}, HID, s_w + y.f_w3, HID, s_w + y.f_b3, HID / 4, s_h, 0, 1, ACT_TANH);
+  dense_auto<EPI_ACT>(L, s_x1, HID, s_w + y.f_w3, HID, mma_sw(HID), s_w + y.f_b3, HID, s_h, 0, ACT_TANH);
   fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
@@ -77,7 +77,8 @@ __device__ __forceinline__ void hutter_trunk(const Lane& L, const HutterLayout& 
   }
   // fc_out + sigmoid : s_h -> s_x1 rows [64, 64+Mo4)
   float* s_act = s_x1 + HID * TMP;
-  dense<SrcT, EPI_ACT>(L, SrcT{s_h}, HID, s_w + y.f_wo, y.Mo4, s_w + y.f_bo, y.Mo4 / 4, s_act, 0, 1, ACT_SIGMOID);
+  dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_wo, y.ld_fwo, mma_sw(y.ld_fwo), s_w + y.f_bo, y.Mo4, s_act, 0,
+                      ACT_SIGMOID);
   fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
@@ -130,21 +131,5 @@ __device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, co
     }
   }
 }
-
-__device__ __forceinline__ void dw_T_any(const Lane& L, const float* dz, int M, const float* x, int K, float* P,
-                                         int ldp, float* Pb) {
-  const int nki = (K + 31) / 32;
-  switch (nki) {
-    case 1: dw_T<1>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 2: dw_T<2>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 3: dw_T<3>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 4: dw_T<4>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 5: dw_T<5>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 6: dw_T<6>(L, dz, M, x, K, P, ldp, Pb); break;
-    case 7: dw_T<7>(L, dz, M, x, K, P, ldp, Pb); break;
-    default: dw_T<8>(L, dz, M, x, K, P, ldp, Pb); break;
-  }
-}
-
 
 }  // namespace apg

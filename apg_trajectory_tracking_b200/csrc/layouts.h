@@ -26,6 +26,16 @@ constexpr int NWARP = NT / 32;
 
 inline __host__ __device__ int pad4(int x) { return (x + 3) & ~3; }
 
+// Leading dimension of a weight matrix whose rows are read as mma.sync B fragments (lane (g,t) reads row k0+t,
+// column n0+g): rows must land in distinct 8-bank groups.  ld % 32 == 8 or 24 does that by itself; ld % 32 == 0
+// needs the XOR swizzle col ^ ((row & 3) << 3)  (mma_sw); ld % 32 == 16 is padded by 8.
+inline __host__ __device__ int mma_ld(int n) {
+  int l = (n + 7) & ~7;
+  if ((l & 31) == 16) l += 8;
+  return l;
+}
+inline __host__ __device__ int mma_sw(int ld) { return (ld & 31) == 0; }
+
 constexpr int HID = 64;       // hidden width of the hutter nets
 constexpr int CONV_CH = 20;   // conv_ref output channels
 
@@ -36,8 +46,10 @@ struct HutterLayout {
   int t_ws, t_bs, t_wc, t_bc, t_wr, t_br, t_w1, t_b1, t_w2, t_b2, t_w3, t_b3, t_wo, t_bo, n_params;
   // packed forward
   int f_ws, f_bs, f_wr, f_br, f_w1, f_b1, f_w2, f_b2, f_w3, f_b3, f_wo, f_bo, f_total, ld_wr;
+  int ld_fwo;                   // row stride of the packed fc_out forward weights (mma_ld(Mo))
   // packed backward ([out][in_padded])
   int b_wo, b_w3, b_w2, b_w1, b_ws, b_wr, b_total, ld_bws, ld_bwr;
+  int ld_bw1;                   // row stride of the packed fc1 backward weights (mma_ld(K1))
 };
 
 inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, int conv) {
@@ -69,7 +81,8 @@ inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, i
   y.f_w1 = o; o += y.K1 * HID;          y.f_b1 = o; o += HID;
   y.f_w2 = o; o += HID * HID;           y.f_b2 = o; o += HID;
   y.f_w3 = o; o += HID * HID;           y.f_b3 = o; o += HID;
-  y.f_wo = o; o += HID * y.Mo4;         y.f_bo = o; o += y.Mo4;
+  y.ld_fwo = mma_ld(y.Mo4);
+  y.f_wo = o; o += HID * y.ld_fwo;      y.f_bo = o; o += y.Mo4;
   y.f_total = o;
   y.ld_bws = pad4(F0);
   y.ld_bwr = pad4(y.KR);
@@ -77,7 +90,8 @@ inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, i
   y.b_wo = o; o += Mo * HID;
   y.b_w3 = o; o += HID * HID;
   y.b_w2 = o; o += HID * HID;
-  y.b_w1 = o; o += HID * y.K1;
+  y.ld_bw1 = mma_ld(y.K1);
+  y.b_w1 = o; o += HID * y.ld_bw1;
   y.b_ws = o; o += HID * y.ld_bws;
   y.b_wr = o; o += nr * y.ld_bwr;
   y.b_total = o;
@@ -168,7 +182,7 @@ inline __host__ LstmLayout make_lstm_layout(int F0, int L, int RD, int Mo) {
 enum PackMode { PK_COPY_PAD = 0, PK_TRANSPOSE = 1, PK_CONV_FWD = 2, PK_CONV_BWD = 3 };
 // src is [rows][cols] with row stride sld; the destination window is `wcols` wide (zero-filled beyond the data)
 // with row stride ldd.  which: 0 -> fwd buffer, 1 -> bwd buffer
-struct PackSeg { int src, sld, dst, rows, cols, wcols, ldd, mode, which; };
+struct PackSeg { int src, sld, dst, rows, cols, wcols, ldd, mode, which, sw; };   // sw: XOR-swizzle the dst columns
 constexpr int MAX_PACK_SEGS = 24;
 struct PackTable { int n; PackSeg seg[MAX_PACK_SEGS]; };
 

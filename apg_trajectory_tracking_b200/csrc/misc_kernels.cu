@@ -22,11 +22,11 @@ __global__ void apg_pack_kernel(const PackTable t, const float* __restrict__ par
       if (g.mode == PK_COPY_PAD) {                 // dst[r][c], c < wcols
         const int r = i / g.wcols, c = i - r * g.wcols;
         if (c < g.cols) v = src[r * g.sld + c];
-        di = r * g.ldd + c;
+        di = r * g.ldd + (g.sw ? (c ^ ((r & 3) << 3)) : c);
       } else if (g.mode == PK_TRANSPOSE) {         // dst[c][r], r < wcols  (src [rows][cols])
         const int c = i / g.wcols, r = i - c * g.wcols;
         if (r < g.rows) v = src[r * g.sld + c];
-        di = c * g.ldd + r;
+        di = c * g.ldd + (g.sw ? (r ^ ((c & 3) << 3)) : r);
       } else if (g.mode == PK_CONV_FWD) {          // src [C=rows][RD][3] -> dst[kk = j*RD + d][c], cols = 3*RD
         const int kk = i / g.ldd, c = i - kk * g.ldd;
         const int rd = g.cols / 3, j = kk / rd, d = kk - j * rd;

@@ -231,21 +231,21 @@ __global__ void __launch_bounds__(NT, 1) rec_adj_kernel(const HutterLayout y, co
       __syncthreads();
       // ---- fc_out
       mbar_wait(bar_B, ph);
-      dw_T<2>(L, s_dlog, y.Mo, bufB, HID, P + y.t_wo, HID, P + y.t_bo);
+      dw_auto(L, s_dlog, y.Mo, bufB, HID, P + y.t_wo, HID, P + y.t_bo);
       __syncthreads();
-      dense<SrcT, EPI_DTANH>(L, SrcT{s_dlog}, y.Mo, s_w + y.b_wo, HID, nullptr, HID / 4, bufB, 0, 1, 0);
+      dense_auto<EPI_DTANH>(L, s_dlog, y.Mo, s_w + y.b_wo, HID, mma_sw(HID), nullptr, HID, bufB, 0, 0);
       __syncthreads();
       // ---- fc3
       mbar_wait(bar_D, ph);
-      dw_T<2>(L, bufB, HID, bufD, HID, P + y.t_w3, HID, P + y.t_b3);
+      dw_auto(L, bufB, HID, bufD, HID, P + y.t_w3, HID, P + y.t_b3);
       __syncthreads();
-      dense<SrcT, EPI_DTANH>(L, SrcT{bufB}, HID, s_w + y.b_w3, HID, nullptr, HID / 4, bufD, 0, 1, 0);
+      dense_auto<EPI_DTANH>(L, bufB, HID, s_w + y.b_w3, HID, mma_sw(HID), nullptr, HID, bufD, 0, 0);
       __syncthreads();
       // ---- fc2
       mbar_wait(bar_C, ph);
-      dw_T<2>(L, bufD, HID, bufC, HID, P + y.t_w2, HID, P + y.t_b2);
+      dw_auto(L, bufD, HID, bufC, HID, P + y.t_w2, HID, P + y.t_b2);
       __syncthreads();
-      dense<SrcT, EPI_DTANH>(L, SrcT{bufD}, HID, s_w + y.b_w2, HID, nullptr, HID / 4, bufC, 0, 1, 0);
+      dense_auto<EPI_DTANH>(L, bufD, HID, s_w + y.b_w2, HID, mma_sw(HID), nullptr, HID, bufC, 0, 0);
       __syncthreads();
       // ---- rebuild the policy inputs of step k in bufB|bufD (dead now): features(S_k) and the window
       if (tid < TM) {
@@ -258,10 +258,10 @@ __global__ void __launch_bounds__(NT, 1) rec_adj_kernel(const HutterLayout y, co
       __syncthreads();
       // ---- fc1
       mbar_wait(bar_A, ph);
-      dw_T_any(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
+      dw_auto(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
       __syncthreads();
-      dense<SrcT, EPI_DTANH>(L, SrcT{bufC}, HID, s_w + y.b_w1, y.K1, nullptr, HID / 4, bufA, 0, 1, 0);
-      dense<SrcT, EPI_DRELU>(L, SrcT{bufC}, HID, s_w + y.b_w1 + HID, y.K1, nullptr, y.NRtot / 4, bufA, HID, 1, 0);
+      dense_auto<EPI_DTANH>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, HID, bufA, 0, 0);
+      dense_auto<EPI_DRELU>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, y.NRtot, bufA, HID, 0, HID);
       __syncthreads();
       // ---- first layer: weight gradients, then the input gradients (they feed the state cotangent)
       dw_AoS(L, bufA, HID, s_ins, y.F0, 0, y.F0, P + y.t_ws, y.F0, P + y.t_bs);

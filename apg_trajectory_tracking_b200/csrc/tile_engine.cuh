@@ -102,6 +102,13 @@ __device__ __forceinline__ void bulk_g2s_chunked(void* dst, const void* src, uin
   }
 }
 
+// Accumulate into the CTA's gradient partial without waiting for the old value: red.global.add.f32.  Every address is
+// owned by exactly one thread of one CTA for the whole launch (same-address reductions of one thread retire in
+// program order), so the result is deterministic although the instruction is an atomic.
+__device__ __forceinline__ void red_add(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // thread mapping of the 4x4 register-tile GEMM: a warp spans 4 drone groups x 8 output groups
 // ------------------------------------------------------------------------------------------------------------
@@ -139,13 +146,16 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 }
 
 // acc[i][j] += A[k][drone i] * W[k][4*og + j]  over k in [0,K)
+// `Wcol` points at column 4*og of row 0; with sw != 0 the matrix is stored XOR-swizzled (col ^ ((row&3)<<3)), which
+// keeps every aligned group of 4 columns contiguous.
 template <class Src>
 __device__ __forceinline__ void mac_tile(float (&acc)[4][4], const Src& A, int K, const float* __restrict__ Wcol,
-                                         int ldw, int dg) {
+                                         int ldw, int dg, int sw = 0, int col0 = 0) {
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
     const float4 a = A.ld(k, dg);
-    const float4 w = *reinterpret_cast<const float4*>(Wcol + k * ldw);
+    const int cs = sw ? ((col0 ^ ((k & 3) << 3)) - col0) : 0;
+    const float4 w = *reinterpret_cast<const float4*>(Wcol + k * ldw + cs);
     acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
     acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
     acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
@@ -192,11 +202,163 @@ __device__ __forceinline__ void store_tile(const float (&acc)[4][4], const float
 template <class Src, int EPI>
 __device__ __forceinline__ void dense(const Lane& L, const Src& A, int K, const float* __restrict__ W, int ldw,
                                       const float* __restrict__ bias, int M4, float* Y, int row0, int row_stride,
-                                      int act) {
+                                      int act, int sw = 0, int wcol0 = 0) {
   for (int og = L.og0; og < M4; og += 16) {
     float acc[4][4] = {};
-    mac_tile(acc, A, K, W + 4 * og, ldw, L.dg);
+    mac_tile(acc, A, K, W + wcol0 + 4 * og, ldw, L.dg, sw, wcol0 + 4 * og);
     store_tile<EPI>(acc, bias, og, Y, row0, row_stride, act, L.dg);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tensor-core variants: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, hi = top 19 bits;
+// a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate) -> fp32-level accuracy (~2^-21 relative) at three
+// tensor instructions per tile, and a quarter of the shared-memory operand traffic of the FFMA tiles.
+// Fragment coordinates (g = lane>>2, t = lane&3): A(16x8): a0 (g,t) a1 (g+8,t) a2 (g,t+4) a3 (g+8,t+4);
+// B(8x8): b0 (k=t,n=g) b1 (k=t+4,n=g); C(16x8): c0 (g,2t) c1 (g,2t+1) c2 (g+8,2t) c3 (g+8,2t+1).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0f,
+                                           float b1f) {
+  uint32_t bh0, bl0, bh1, bl1;
+  split_tf32(b0f, bh0, bl0);
+  split_tf32(b1f, bh1, bl1);
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+
+// Y[row0 + n][d] = epi(bias[n] + sum_k A[k][d] * W[k][n]) for the 64 drones of the tile; A feature-major [K][TMP],
+// W [K][ldw] (swizzled when sw), K % 8 == 0, N % 8 == 0.  Warp w: drones 16*(w&3) .., groups of 4 n-tiles
+// alternate between the two warp halves.
+template <int EPI>
+__device__ __forceinline__ void dense_mma(const Lane& L, const float* __restrict__ A, int K,
+                                          const float* __restrict__ W, int ldw, int sw, const float* __restrict__ bias,
+                                          int N, float* Y, int row0, int act, int wcol0 = 0) {
+  const int g = L.lane >> 2, t = L.lane & 3;
+  const int m0 = (L.warp & 3) * 16;
+  const int nt8 = N >> 3;
+  const int xs = sw ? (t << 3) : 0;
+  for (int nc = (L.warp >> 2); nc * 4 < nt8; nc += 2) {
+    const int nt0 = nc * 4;
+    const int ntc = nt8 - nt0 < 4 ? nt8 - nt0 : 4;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    const float* ap = A + t * TMP + m0 + g;
+    const float* wp = W + t * ldw;
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t ah[4], al[4];
+      split_tf32(ap[k0 * TMP], ah[0], al[0]);
+      split_tf32(ap[k0 * TMP + 8], ah[1], al[1]);
+      split_tf32(ap[(k0 + 4) * TMP], ah[2], al[2]);
+      split_tf32(ap[(k0 + 4) * TMP + 8], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < ntc) {
+          const int n = (wcol0 + (nt0 + j) * 8 + g) ^ xs;
+          mma_3xtf32(acc[j], ah, al, wp[k0 * ldw + n], wp[(k0 + 4) * ldw + n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < ntc) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = (nt0 + j) * 8 + 2 * t + (e & 1);
+          const int d = m0 + g + ((e >> 1) << 3);
+          float* yp = Y + (row0 + n) * TMP + d;
+          float v = acc[j][e];
+          if (EPI == EPI_ACT) {
+            v = act_apply(v + (bias ? bias[n] : 0.f), act);
+          } else if (EPI == EPI_DTANH) {
+            const float y = *yp;
+            v *= 1.f - y * y;
+          } else if (EPI == EPI_DRELU) {
+            v = *yp > 0.f ? v : 0.f;
+          } else if (EPI == EPI_DSIGMOID) {
+            const float y = *yp;
+            v *= y * (1.f - y);
+          }
+          *yp = v;
+        }
+      }
+    }
+  }
+}
+
+// db[j] += sum_d dZ[j][d]  (thread j < M)
+__device__ __forceinline__ void bias_grad(const float* __restrict__ dz, int M, float* __restrict__ Pb) {
+  for (int j = threadIdx.x; j < M; j += NT) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < TM / 4; ++d4) {
+      const float4 z = *reinterpret_cast<const float4*>(dz + j * TMP + 4 * d4);
+      s0 += z.x + z.y;
+      s1 += z.z + z.w;
+    }
+    red_add(Pb + j, s0 + s1);
+  }
+}
+
+// dW[j][k] += sum_d dZ[j][d] X[k][d]  (both feature-major, reduction over the 64 drones), M rows, K % 8 == 0 columns.
+// Warp w: 16-row tile (w & 3) (+4, ...), the 8-column tiles split between the two warp halves; NT n-tiles per pass.
+template <int NTP>
+__device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ dz, int M, const float* __restrict__ x,
+                                       int K, float* __restrict__ P, int ldp) {
+  const int g = L.lane >> 2, t = L.lane & 3;
+  const int nt8 = K >> 3;
+  const int per_half = (nt8 + 1) >> 1;
+  for (int mt = (L.warp & 3); mt * 16 < M; mt += 4) {
+    const int j0 = mt * 16;
+    const int nb = (L.warp >> 2) * per_half;
+    const int ne = nb + per_half < nt8 ? nb + per_half : nt8;
+    for (int n0 = nb; n0 < ne; n0 += NTP) {
+      float acc[NTP][4];
+#pragma unroll
+      for (int j = 0; j < NTP; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      const float* zp = dz + (j0 + g) * TMP + t;
+#pragma unroll 2
+      for (int d0 = 0; d0 < TM; d0 += 8) {
+        uint32_t ah[4], al[4];
+        split_tf32(zp[d0], ah[0], al[0]);
+        split_tf32(zp[8 * TMP + d0], ah[1], al[1]);
+        split_tf32(zp[d0 + 4], ah[2], al[2]);
+        split_tf32(zp[8 * TMP + d0 + 4], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < NTP; ++j) {
+          if (n0 + j < ne) {
+            const float* xp = x + ((n0 + j) * 8 + g) * TMP + d0 + t;
+            mma_3xtf32(acc[j], ah, al, xp[0], xp[4]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NTP; ++j) {
+        if (n0 + j < ne) {
+          const int k = (n0 + j) * 8 + 2 * t;
+          if (j0 + g < M) {
+            red_add(P + (j0 + g) * ldp + k, acc[j][0]);
+            red_add(P + (j0 + g) * ldp + k + 1, acc[j][1]);
+          }
+          if (j0 + g + 8 < M) {
+            red_add(P + (j0 + g + 8) * ldp + k, acc[j][2]);
+            red_add(P + (j0 + g + 8) * ldp + k + 1, acc[j][3]);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -204,13 +366,6 @@ __device__ __forceinline__ void dense(const Lane& L, const Src& A, int K, const 
 // weight-gradient contractions.  P points at the CTA's partial-gradient matrix in global memory (torch layout
 // [M][ldp]); each (j,k) entry is owned by exactly one thread -> plain read-modify-write, deterministic.
 // ------------------------------------------------------------------------------------------------------------
-// Accumulate into the CTA's gradient partial without waiting for the old value: red.global.add.f32.  Every address is
-// owned by exactly one thread of one CTA for the whole launch (same-address reductions of one thread retire in
-// program order), so the result is deterministic although the instruction is an atomic.
-__device__ __forceinline__ void red_add(float* addr, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
-}
-
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float c) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, c))));
 }
@@ -288,6 +443,42 @@ __device__ __forceinline__ void dw_AoS(const Lane& L, const float* __restrict__ 
         if (Pb && L.lane == 0) red_add(Pb + j, accb[jj]);
       }
     }
+  }
+}
+
+// Dispatchers: tensor-core path when the contraction is 8-aligned, FFMA tiles otherwise (small / odd layers).
+template <int EPI>
+__device__ __forceinline__ void dense_auto(const Lane& L, const float* __restrict__ A, int K,
+                                           const float* __restrict__ W, int ldw, int sw, const float* __restrict__ bias,
+                                           int N, float* Y, int row0, int act, int wcol0 = 0) {
+  if ((((K | N) & 7) == 0))
+    dense_mma<EPI>(L, A, K, W, ldw, sw, bias, N, Y, row0, act, wcol0);
+  else
+    dense<SrcT, EPI>(L, SrcT{A}, K, W, ldw, bias, N / 4, Y, row0, 1, act, sw, wcol0);
+}
+
+template <int NKI>
+__device__ __forceinline__ void dw_T(const Lane& L, const float* __restrict__ dz, int M, const float* __restrict__ x,
+                                     int K, float* __restrict__ P, int ldp, float* __restrict__ Pb);
+
+__device__ __forceinline__ void dw_auto(const Lane& L, const float* __restrict__ dz, int M, const float* __restrict__ x,
+                                        int K, float* __restrict__ P, int ldp, float* __restrict__ Pb) {
+  if ((K & 7) == 0 && M >= 16) {
+    bias_grad(dz, M, Pb);
+    if (K <= 64) dw_mma<4>(L, dz, M, x, K, P, ldp);
+    else dw_mma<7>(L, dz, M, x, K, P, ldp);
+    return;
+  }
+  const int nki = (K + 31) / 32;
+  switch (nki) {
+    case 1: dw_T<1>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 2: dw_T<2>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 3: dw_T<3>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 4: dw_T<4>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 5: dw_T<5>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 6: dw_T<6>(L, dz, M, x, K, P, ldp, Pb); break;
+    case 7: dw_T<7>(L, dz, M, x, K, P, ldp, Pb); break;
+    default: dw_T<8>(L, dz, M, x, K, P, ldp, Pb); break;
   }
 }
 
