@@ -107,13 +107,17 @@ PackTable hutter_pack_table(const HutterLayout& y) {
   PackTable t;
   t.n = 0;
   // forward: [in][out]
-  add_seg(t, 0, PK_TRANSPOSE, y.t_ws, y.f_ws, HID, y.F0, HID);
+  const int f0p8 = (y.F0 + 7) & ~7, krp8 = (y.KR + 7) & ~7;
+  add_seg_mma(t, 0, PK_TRANSPOSE, y.t_ws, y.f_ws, HID, y.F0, HID);
+  if (f0p8 > y.F0) add_seg_ex(t, 0, PK_COPY_PAD, y.t_ws, 1, y.f_ws + y.F0 * HID, f0p8 - y.F0, 0, HID, HID);   // zero rows
   add_seg(t, 0, PK_COPY_PAD, y.t_bs, y.f_bs, 1, HID, HID);
   if (y.conv) {
-    add_seg(t, 0, PK_CONV_FWD, y.t_wc, y.f_wr, CONV_CH, y.KC, CONV_CH);
+    add_seg(t, 0, PK_CONV_FWD, y.t_wc, y.f_wr, CONV_CH, y.KC, 24);
+    if (krp8 > y.KR) add_seg_ex(t, 0, PK_COPY_PAD, y.t_wc, 1, y.f_wr + y.KR * 24, krp8 - y.KR, 0, 24, 24);
     add_seg(t, 0, PK_COPY_PAD, y.t_bc, y.f_br, 1, CONV_CH, CONV_CH);
   } else {
-    add_seg(t, 0, PK_TRANSPOSE, y.t_wr, y.f_wr, HID, y.LR, HID);
+    add_seg_mma(t, 0, PK_TRANSPOSE, y.t_wr, y.f_wr, HID, y.LR, HID);
+    if (krp8 > y.KR) add_seg_ex(t, 0, PK_COPY_PAD, y.t_wr, 1, y.f_wr + y.KR * HID, krp8 - y.KR, 0, HID, HID);
     add_seg(t, 0, PK_COPY_PAD, y.t_br, y.f_br, 1, HID, HID);
   }
   add_seg_mma(t, 0, PK_TRANSPOSE, y.t_w1, y.f_w1, HID, y.K1, HID);
@@ -163,7 +167,9 @@ PackTable lstm_pack_table(const LstmLayout& y) {
   PackTable t;
   t.n = 0;
   const int G = 4 * LSTM_HS, f0p = pad4(y.F0), nc = CONV_CH * y.npos, mo4 = pad4(y.Mo);
-  add_seg(t, 0, PK_CONV_FWD, y.t_wc, y.f_wc, CONV_CH, y.KC, CONV_CH);
+  add_seg(t, 0, PK_CONV_FWD, y.t_wc, y.f_wc, CONV_CH, y.KC, 24);
+  if (((y.KC + 7) & ~7) > y.KC)
+    add_seg_ex(t, 0, PK_COPY_PAD, y.t_wc, 1, y.f_wc + y.KC * 24, ((y.KC + 7) & ~7) - y.KC, 0, 24, 24);
   add_seg(t, 0, PK_COPY_PAD, y.t_bc, y.f_bc, 1, CONV_CH, CONV_CH);
   add_seg_ex(t, 0, PK_TRANSPOSE, y.t_wih, y.IH, y.f_wg, G, y.F0, G, G);
   if (f0p > y.F0) add_seg_ex(t, 0, PK_COPY_PAD, y.t_wih, 1, y.f_wg + y.F0 * G, f0p - y.F0, 0, G, G);

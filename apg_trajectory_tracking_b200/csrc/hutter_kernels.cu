@@ -250,11 +250,11 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
       ph_in ^= 1;
     }
     PROF(14);
-    dw_AoS(L, bufA, HID, s_ins, y.F0, 0, y.F0, P + y.t_ws, y.F0, P + y.t_bs);
+    aos_linear64_dw(L, bufA, s_ins, y.F0, y.F0, P + y.t_ws, P + y.t_bs);
     if (CONV)
       conv_dw(L, y, bufA + HID * TMP, s_inr, scratch, P);
     else
-      dw_AoS(L, bufA + HID * TMP, HID, s_inr, y.LR, 0, y.LR, P + y.t_wr, y.LR, P + y.t_br);
+      aos_linear64_dw(L, bufA + HID * TMP, s_inr, y.LR, y.LR, P + y.t_wr, P + y.t_br);
     fence_proxy_async();
     __syncthreads();
     PROF(15);

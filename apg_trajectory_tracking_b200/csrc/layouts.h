@@ -74,10 +74,12 @@ inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, i
   y.t_wo = o; o += Mo * HID;      y.t_bo = o; o += Mo;
   y.n_params = o;
   const int nr = conv ? CONV_CH : HID;
-  y.ld_wr = nr;
   o = 0;
-  y.f_ws = o; o += pad4(F0 * HID);      y.f_bs = o; o += HID;
-  y.f_wr = o; o += pad4(y.KR * nr);     y.f_br = o; o += pad4(nr);
+  // first-layer weights feed mma B fragments: K rows padded to 8 (zero rows), conv columns padded to 24
+  const int ldr = conv ? 24 : HID;
+  y.ld_wr = ldr;
+  y.f_ws = o; o += ((F0 + 7) & ~7) * HID;       y.f_bs = o; o += HID;
+  y.f_wr = o; o += ((y.KR + 7) & ~7) * ldr;     y.f_br = o; o += pad4(nr);
   y.f_w1 = o; o += y.K1 * HID;          y.f_b1 = o; o += HID;
   y.f_w2 = o; o += HID * HID;           y.f_b2 = o; o += HID;
   y.f_w3 = o; o += HID * HID;           y.f_b3 = o; o += HID;
@@ -162,7 +164,7 @@ inline __host__ LstmLayout make_lstm_layout(int F0, int L, int RD, int Mo) {
   y.t_bhh = o; o += 4 * LSTM_HS;
   y.n_params = o;
   o = 0;
-  y.f_wc = o; o += pad4(y.KC * CONV_CH);  y.f_bc = o; o += CONV_CH;
+  y.f_wc = o; o += ((y.KC + 7) & ~7) * 24;  y.f_bc = o; o += CONV_CH;
   y.f_wg = o; o += y.KG * 4 * LSTM_HS;
   y.f_bih = o; o += 4 * LSTM_HS;          y.f_bhh = o; o += 4 * LSTM_HS;
   y.f_wo = o; o += LSTM_HS * pad4(Mo);    y.f_bo = o; o += pad4(Mo);

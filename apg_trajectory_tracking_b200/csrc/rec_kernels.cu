@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(NT, 1) rec_adj_kernel(const HutterLayout y, co
       dense_auto<EPI_DRELU>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, y.NRtot, bufA, HID, 0, HID);
       __syncthreads();
       // ---- first layer: weight gradients, then the input gradients (they feed the state cotangent)
-      dw_AoS(L, bufA, HID, s_ins, y.F0, 0, y.F0, P + y.t_ws, y.F0, P + y.t_bs);
+      aos_linear64_dw(L, bufA, s_ins, y.F0, y.F0, P + y.t_ws, P + y.t_bs);
       conv_dw(L, y, bufA + HID * TMP, s_win, scratch, P);
       __syncthreads();
       dense<SrcT, EPI_DNONE>(L, SrcT{bufA}, HID, s_w + y.b_ws, y.ld_bws, nullptr, y.ld_bws / 4, s_din, 0, 1, 0);

@@ -222,8 +222,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -263,13 +262,22 @@ __device__ __forceinline__ void dense_mma(const Lane& L, const float* __restrict
       split_tf32(ap[k0 * TMP + 8], ah[1], al[1]);
       split_tf32(ap[(k0 + 4) * TMP], ah[2], al[2]);
       split_tf32(ap[(k0 + 4) * TMP + 8], ah[3], al[3]);
+      uint32_t bh[4][2], bl[4][2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j < ntc) {
           const int n = (wcol0 + (nt0 + j) * 8 + g) ^ xs;
-          mma_3xtf32(acc[j], ah, al, wp[k0 * ldw + n], wp[(k0 + 4) * ldw + n]);
+          split_tf32(wp[k0 * ldw + n], bh[j][0], bl[j][0]);
+          split_tf32(wp[(k0 + 4) * ldw + n], bh[j][1], bl[j][1]);
         }
       }
+      // term-major order: consecutive tensor instructions hit different accumulators
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < ntc) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < ntc) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (j < ntc) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -336,13 +344,21 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
         split_tf32(zp[8 * TMP + d0], ah[1], al[1]);
         split_tf32(zp[d0 + 4], ah[2], al[2]);
         split_tf32(zp[8 * TMP + d0 + 4], ah[3], al[3]);
+        uint32_t bh[NTP][2], bl[NTP][2];
 #pragma unroll
         for (int j = 0; j < NTP; ++j) {
           if (n0 + j < ne) {
             const float* xp = x + ((n0 + j) * 8 + g) * TMP + d0 + t;
-            mma_3xtf32(acc[j], ah, al, xp[0], xp[4]);
+            split_tf32(xp[0], bh[j][0], bl[j][0]);
+            split_tf32(xp[4], bh[j][1], bl[j][1]);
           }
         }
+#pragma unroll
+        for (int j = 0; j < NTP; ++j) if (n0 + j < ne) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < NTP; ++j) if (n0 + j < ne) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+#pragma unroll
+        for (int j = 0; j < NTP; ++j) if (n0 + j < ne) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
       }
 #pragma unroll
       for (int j = 0; j < NTP; ++j) {
@@ -466,7 +482,7 @@ __device__ __forceinline__ void dw_auto(const Lane& L, const float* __restrict__
   if ((K & 7) == 0 && M >= 16) {
     bias_grad(dz, M, Pb);
     if (K <= 64) dw_mma<4>(L, dz, M, x, K, P, ldp);
-    else dw_mma<7>(L, dz, M, x, K, P, ldp);
+    else dw_mma<5>(L, dz, M, x, K, P, ldp);
     return;
   }
   const int nki = (K + 31) / 32;
