@@ -89,7 +89,7 @@ HutterLayout hutter_layout(const apg_config* c) {
 void add_seg(PackTable& t, int which, int mode, int src, int dst, int rows, int cols, int ldd) {
   PackSeg& s = t.seg[t.n++];
   s.which = which; s.mode = mode; s.src = src; s.sld = cols; s.dst = dst; s.rows = rows; s.cols = cols;
-  s.wcols = ldd; s.ldd = ldd; s.sw = 0;
+  s.wcols = ldd; s.ldd = ldd; s.sw = 0; s.perm = 0;
 }
 // weight matrix read as mma B fragments: swizzled when its row stride is a multiple of 32 floats
 void add_seg_mma(PackTable& t, int which, int mode, int src, int dst, int rows, int cols, int ldd) {
@@ -100,7 +100,7 @@ void add_seg_mma(PackTable& t, int which, int mode, int src, int dst, int rows, 
 void add_seg_ex(PackTable& t, int which, int mode, int src, int sld, int dst, int rows, int cols, int wcols, int ldd) {
   PackSeg& s = t.seg[t.n++];
   s.which = which; s.mode = mode; s.src = src; s.sld = sld; s.dst = dst; s.rows = rows; s.cols = cols;
-  s.wcols = wcols; s.ldd = ldd; s.sw = 0;
+  s.wcols = wcols; s.ldd = ldd; s.sw = 0; s.perm = 0;
 }
 
 PackTable hutter_pack_table(const HutterLayout& y) {
@@ -121,6 +121,7 @@ PackTable hutter_pack_table(const HutterLayout& y) {
     add_seg(t, 0, PK_COPY_PAD, y.t_br, y.f_br, 1, HID, HID);
   }
   add_seg_mma(t, 0, PK_TRANSPOSE, y.t_w1, y.f_w1, HID, y.K1, HID);
+  t.seg[t.n - 1].perm = y.perm_npos;
   add_seg(t, 0, PK_COPY_PAD, y.t_b1, y.f_b1, 1, HID, HID);
   add_seg_mma(t, 0, PK_TRANSPOSE, y.t_w2, y.f_w2, HID, HID, HID);
   add_seg(t, 0, PK_COPY_PAD, y.t_b2, y.f_b2, 1, HID, HID);
@@ -133,6 +134,7 @@ PackTable hutter_pack_table(const HutterLayout& y) {
   add_seg_mma(t, 1, PK_COPY_PAD, y.t_w3, y.b_w3, HID, HID, HID);
   add_seg_mma(t, 1, PK_COPY_PAD, y.t_w2, y.b_w2, HID, HID, HID);
   add_seg_mma(t, 1, PK_COPY_PAD, y.t_w1, y.b_w1, HID, y.K1, y.ld_bw1);
+  t.seg[t.n - 1].perm = y.perm_npos;
   add_seg(t, 1, PK_COPY_PAD, y.t_ws, y.b_ws, HID, y.F0, y.ld_bws);
   if (y.conv) add_seg(t, 1, PK_CONV_BWD, y.t_wc, y.b_wr, CONV_CH, y.KC, y.ld_bwr);
   else        add_seg(t, 1, PK_COPY_PAD, y.t_wr, y.b_wr, HID, y.LR, y.ld_bwr);

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) hutter_adj_kernel(const HutterLayout y,
     // ---- fc1
     mbar_wait(bar_A, ph);
     PROF(11);
-    dw_auto(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
+    dw_auto(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1, y.perm_npos);
     __syncthreads();
     PROF(12);
     dense_auto<EPI_DTANH>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, HID, bufA, 0, 0);   // ds over s

@@ -75,10 +75,11 @@ __device__ __forceinline__ void aos_mma_block(const Lane& L, const float* __rest
 // Wc packed [pad8(KC)][24] (rows >= KC and columns >= 20 zero).
 constexpr int CONV_LD = 24;
 __device__ __forceinline__ void conv_layer_fwd(const Lane& L, int npos, int RD, int LR, int KC, const float* Wc,
-                                               const float* bc, const float* s_inr, float* Y, int row0) {
+                                               const float* bc, const float* s_inr, float* Y, int row0, int cs,
+                                               int ts) {
   const int m0 = (L.warp & 3) * 16;
   for (int t = (L.warp >> 2); t < npos; t += 2)
-    aos_mma_block<3>(L, s_inr, LR, RD * t, KC, Wc, CONV_LD, 0, bc, CONV_CH, m0, 0, Y, row0 + t, npos, ACT_RELU);
+    aos_mma_block<3>(L, s_inr, LR, RD * t, KC, Wc, CONV_LD, 0, bc, CONV_CH, m0, 0, Y, row0 + t * ts, cs, ACT_RELU);
 }
 
 // tanh(Linear(K -> 64)) of a drone-major input tile -> rows [row0, row0+64)
@@ -97,7 +98,7 @@ __device__ __forceinline__ void hutter_first_layer(const Lane& L, const HutterLa
                                                    const float* s_ins, const float* s_inr, float* s_x1) {
   aos_linear64_fwd(L, s_ins, y.F0, y.F0, s_w + y.f_ws, s_w + y.f_bs, s_x1, 0);
   if (CONV)
-    conv_layer_fwd(L, y.npos, y.RD, y.LR, y.KC, s_w + y.f_wr, s_w + y.f_br, s_inr, s_x1, HID);
+    conv_layer_fwd(L, y.npos, y.RD, y.LR, y.KC, s_w + y.f_wr, s_w + y.f_br, s_inr, s_x1, HID, y.conv_cs, y.conv_ts);
   else
     aos_linear64_fwd(L, s_inr, y.LR, y.LR, s_w + y.f_wr, s_w + y.f_br, s_x1, HID);
 }
@@ -163,7 +164,8 @@ __device__ __forceinline__ void aos_linear64_dw(const Lane& L, const float* __re
   bias_grad(dz, HID, Pb);
   const int j0 = (L.warp & 3) * 16;
   for (int nt = (L.warp >> 2); nt * 8 < K; nt += 2) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // three independent accumulator chains (lo*hi, hi*lo, hi*hi), summed at the end
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
     const float* zp = dz + (j0 + g) * TMP + t;
     const int n = nt * 8 + g;
 #pragma unroll 2
@@ -174,10 +176,12 @@ __device__ __forceinline__ void aos_linear64_dw(const Lane& L, const float* __re
       split_tf32(zp[d0 + 4], ah[2], al[2]);
       split_tf32(zp[8 * TMP + d0 + 4], ah[3], al[3]);
       load_b_aos(s_in, lda, 0, d0, t, n, n < K, bh, bl);
-      mma_tf32(acc, al, bh[0], bh[1]);
-      mma_tf32(acc, ah, bl[0], bl[1]);
+      mma_tf32(acc1, al, bh[0], bh[1]);
+      mma_tf32(acc2, ah, bl[0], bl[1]);
       mma_tf32(acc, ah, bh[0], bh[1]);
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += acc1[e] + acc2[e];
     const int k = nt * 8 + 2 * t;
     if (k < K) { red_add(P + (j0 + g) * K + k, acc[0]); red_add(P + (j0 + g + 8) * K + k, acc[2]); }
     if (k + 1 < K) { red_add(P + (j0 + g) * K + k + 1, acc[1]); red_add(P + (j0 + g + 8) * K + k + 1, acc[3]); }
@@ -194,7 +198,7 @@ __device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, co
   if (threadIdx.x < CONV_CH) {
     float s = 0.f;
     for (int tt = 0; tt < y.npos; ++tt) {
-      const float* zr = dzr + (threadIdx.x * y.npos + tt) * TMP;
+      const float* zr = dzr + (threadIdx.x * y.conv_cs + tt * y.conv_ts) * TMP;
 #pragma unroll
       for (int d4 = 0; d4 < TM / 4; ++d4) {
         const float4 z = *reinterpret_cast<const float4*>(zr + 4 * d4);
@@ -206,11 +210,11 @@ __device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, co
   const int c0 = (L.warp & 1) * 16;
   const int ca = min(c0 + g, CONV_CH - 1), cb = min(c0 + g + 8, CONV_CH - 1);      // clamped rows (discarded)
   for (int nt = (L.warp >> 1); nt * 8 < y.KC; nt += 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
     const int n = nt * 8 + g;
     for (int tt = 0; tt < y.npos; ++tt) {
-      const float* za = dzr + (ca * y.npos + tt) * TMP + t;
-      const float* zb = dzr + (cb * y.npos + tt) * TMP + t;
+      const float* za = dzr + (ca * y.conv_cs + tt * y.conv_ts) * TMP + t;
+      const float* zb = dzr + (cb * y.conv_cs + tt * y.conv_ts) * TMP + t;
 #pragma unroll 2
       for (int d0 = 0; d0 < TM; d0 += 8) {
         uint32_t ah[4], al[4], bh[2], bl[2];
@@ -219,11 +223,13 @@ __device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, co
         split_tf32(za[d0 + 4], ah[2], al[2]);
         split_tf32(zb[d0 + 4], ah[3], al[3]);
         load_b_aos(s_inr, y.LR, y.RD * tt, d0, t, n, n < y.KC, bh, bl);
-        mma_tf32(acc, al, bh[0], bh[1]);
-        mma_tf32(acc, ah, bl[0], bl[1]);
+        mma_tf32(acc1, al, bh[0], bh[1]);
+        mma_tf32(acc2, ah, bl[0], bl[1]);
         mma_tf32(acc, ah, bh[0], bh[1]);
       }
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += acc1[e] + acc2[e];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int c = c0 + g + ((e >> 1) << 3), kk = nt * 8 + 2 * t + (e & 1);

@@ -50,6 +50,11 @@ struct HutterLayout {
   // packed backward ([out][in_padded])
   int b_wo, b_w3, b_w2, b_w1, b_ws, b_wr, b_total, ld_bws, ld_bwr;
   int ld_bw1;                   // row stride of the packed fc1 backward weights (mma_ld(K1))
+  // row of conv output (channel c, position t) inside the activation arena, relative to the first conv row:
+  // c*conv_cs + t*conv_ts.  The reference flattens channel-major (cs = npos, ts = 1); the hutter kernels keep the
+  // tile position-major (cs = 1, ts = 20: consecutive channels in consecutive rows -> conflict-free mma fragments)
+  // and permute the fc1 weight columns at pack time (perm_npos).
+  int conv_cs, conv_ts, perm_npos;
 };
 
 inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, int conv) {
@@ -62,6 +67,7 @@ inline __host__ HutterLayout make_hutter_layout(int F0, int L, int RD, int Mo, i
   y.NRtot = conv ? CONV_CH * y.npos : HID;
   y.K1 = HID + y.NRtot;
   y.Mo4 = pad4(Mo);
+  y.conv_cs = 1; y.conv_ts = CONV_CH; y.perm_npos = conv ? y.npos : 0;
   y.XR = y.K1 > HID + y.Mo4 ? y.K1 : HID + y.Mo4;
   y.CR = y.Mo4 > HID ? y.Mo4 : HID;
   int o = 0;
@@ -177,6 +183,7 @@ inline __host__ LstmLayout make_lstm_layout(int F0, int L, int RD, int Mo) {
   y.b_total = o;
   y.cv = make_hutter_layout(F0, L, RD, Mo, 1);
   y.cv.t_wc = y.t_wc; y.cv.t_bc = y.t_bc; y.cv.ld_bwr = y.ld_bwr;
+  y.cv.conv_cs = y.npos; y.cv.conv_ts = 1; y.cv.perm_npos = 0;      // the LSTM arena stays channel-major
   return y;
 }
 
@@ -184,7 +191,8 @@ inline __host__ LstmLayout make_lstm_layout(int F0, int L, int RD, int Mo) {
 enum PackMode { PK_COPY_PAD = 0, PK_TRANSPOSE = 1, PK_CONV_FWD = 2, PK_CONV_BWD = 3 };
 // src is [rows][cols] with row stride sld; the destination window is `wcols` wide (zero-filled beyond the data)
 // with row stride ldd.  which: 0 -> fwd buffer, 1 -> bwd buffer
-struct PackSeg { int src, sld, dst, rows, cols, wcols, ldd, mode, which, sw; };   // sw: XOR-swizzle the dst columns
+// sw: XOR-swizzle the dst columns; perm: fc1 input index (position-major, see HutterLayout) -> torch column
+struct PackSeg { int src, sld, dst, rows, cols, wcols, ldd, mode, which, sw, perm; };
 constexpr int MAX_PACK_SEGS = 24;
 struct PackTable { int n; PackSeg seg[MAX_PACK_SEGS]; };
 

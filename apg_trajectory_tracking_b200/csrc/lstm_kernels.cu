@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmLayout y, con
       __syncthreads();
       build_window(s_win, g.in_ref + (size_t)tile * TM * 2 * y.LR, s_P, s_pos, k, h, y.RD, valid, g.window);
       __syncthreads();
-      conv_layer_fwd(L, y.npos, y.RD, y.LR, y.KC, s_w + y.f_wc, s_w + y.f_bc, s_win, ar, pad4(y.F0));
+      conv_layer_fwd(L, y.npos, y.RD, y.LR, y.KC, s_w + y.f_wc, s_w + y.f_bc, s_win, ar, pad4(y.F0), y.npos, 1);
       __syncthreads();
       // gate pre-activations: [x | h_prev] (KG rows) x Wg -> rows R_G .. R_G+32 (biases added in the cell pass)
       dense<SrcT, EPI_ACT>(L, SrcT{ar}, y.KG, s_w + y.f_wg, 4 * HS, nullptr, HS, ar, y.R_G, 1, ACT_NONE);

@@ -4,6 +4,12 @@
 
 namespace apg {
 
+__device__ __forceinline__ int pack_perm(int k, int npos) {     // position-major fc1 input index -> torch column
+  if (npos <= 0 || k < 64) return k;
+  const int tt = (k - 64) / 20, c = (k - 64) - tt * 20;
+  return 64 + c * npos + tt;
+}
+
 // dst = layout transform of src (see PackMode); zero-fills padding.  One block per segment chunk.
 __global__ void apg_pack_kernel(const PackTable t, const float* __restrict__ params, float* __restrict__ wf,
                                 float* __restrict__ wb) {
@@ -21,11 +27,11 @@ __global__ void apg_pack_kernel(const PackTable t, const float* __restrict__ par
       int di = i;
       if (g.mode == PK_COPY_PAD) {                 // dst[r][c], c < wcols
         const int r = i / g.wcols, c = i - r * g.wcols;
-        if (c < g.cols) v = src[r * g.sld + c];
+        if (c < g.cols) v = src[r * g.sld + pack_perm(c, g.perm)];
         di = r * g.ldd + (g.sw ? (c ^ ((r & 3) << 3)) : c);
       } else if (g.mode == PK_TRANSPOSE) {         // dst[c][r], r < wcols  (src [rows][cols])
         const int c = i / g.wcols, r = i - c * g.wcols;
-        if (r < g.rows) v = src[r * g.sld + c];
+        if (r < g.rows) v = src[r * g.sld + pack_perm(c, g.perm)];
         di = c * g.ldd + (g.sw ? (r ^ ((c & 3) << 3)) : r);
       } else if (g.mode == PK_CONV_FWD) {          // src [C=rows][RD][3] -> dst[kk = j*RD + d][c], cols = 3*RD
         const int kk = i / g.ldd, c = i - kk * g.ldd;

@@ -47,7 +47,7 @@ __device__ __forceinline__ void conv_dx_pos(const HutterLayout& y, const float* 
       const int t = r - j;
       if (t >= 0 && t < y.npos) {
         for (int ch = 0; ch < CONV_CH; ++ch) {
-          const float z = dzr[(ch * y.npos + t) * TMP + d];
+          const float z = dzr[(ch * y.conv_cs + t * y.conv_ts) * TMP + d];
           const float* w = wb + ch * y.ld_bwr + j * y.RD;
           a0 = fmaf(z, w[0], a0); a1 = fmaf(z, w[1], a1); a2 = fmaf(z, w[2], a2);
         }

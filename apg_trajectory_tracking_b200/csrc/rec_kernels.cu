@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NT, 1) rec_adj_kernel(const HutterLayout y, co
       __syncthreads();
       // ---- fc1
       mbar_wait(bar_A, ph);
-      dw_auto(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1);
+      dw_auto(L, bufC, HID, bufA, y.K1, P + y.t_w1, y.K1, P + y.t_b1, y.perm_npos);
       __syncthreads();
       dense_auto<EPI_DTANH>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, HID, bufA, 0, 0);
       dense_auto<EPI_DRELU>(L, bufC, HID, s_w + y.b_w1, y.ld_bw1, mma_sw(y.ld_bw1), nullptr, y.NRtot, bufA, HID, 0, HID);
