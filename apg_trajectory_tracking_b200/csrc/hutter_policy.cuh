@@ -104,44 +104,48 @@ __device__ __forceinline__ void hutter_first_layer(const Lane& L, const HutterLa
 }
 
 // fc1 .. fc_out on a tile whose X1 is complete in s_x1 AND whose X1 stash store has been committed as the most
-// recent bulk group by thread 0.  Leaves sigmoid(logits) in s_x1 rows [64, 64+Mo4) and every hidden activation in
-// the global stash.  Ends with a __syncthreads (actions visible to all threads).
+// recent bulk group by thread 0.  Leaves sigmoid(logits) in s_act (rows [0, Mo4)) and every hidden activation in the
+// global stash.  Ends with a group barrier (actions visible to the GEMM group).  WS: warp-specialised caller (the
+// GEMM group is threads 0..255 and syncs on named barrier 1); act_wait: optional mbarrier to wait on (parity
+// act_parity) before s_act is overwritten (the dynamics warps have finished with the previous tile's actions).
+template <bool WS>
 __device__ __forceinline__ void hutter_trunk(const Lane& L, const HutterLayout& y, const float* s_w, float* s_x1,
-                                             float* s_h, float* st_h1, float* st_h2, float* st_h3, float* st_act) {
+                                             float* s_h, float* s_act, float* st_h1, float* st_h2, float* st_h3,
+                                             float* st_act, uint64_t* act_wait = nullptr, uint32_t act_parity = 0) {
   const int tid = threadIdx.x;
   dense_auto<EPI_ACT>(L, s_x1, y.K1, s_w + y.f_w1, HID, mma_sw(HID), s_w + y.f_b1, HID, s_h, 0, ACT_TANH);
   fence_proxy_async();
-  __syncthreads();
+  gsync<WS>();
   if (tid == 0) {
     bulk_s2g(st_h1, s_h, HID * TMP * 4);
     bulk_commit();
     bulk_wait_read<1>();      // the X1 store has finished reading s_x1
   }
-  __syncthreads();
+  gsync<WS>();
   // fc2 : s_h -> s_x1 rows [0,64)
   dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_w2, HID, mma_sw(HID), s_w + y.f_b2, HID, s_x1, 0, ACT_TANH);
   fence_proxy_async();
-  __syncthreads();
+  gsync<WS>();
   if (tid == 0) {
     bulk_s2g(st_h2, s_x1, HID * TMP * 4);
     bulk_commit();
     bulk_wait_read<1>();      // the h1 store has finished reading s_h
   }
-  __syncthreads();
+  gsync<WS>();
   // fc3 : s_x1 rows [0,64) -> s_h
   dense_auto<EPI_ACT>(L, s_x1, HID, s_w + y.f_w3, HID, mma_sw(HID), s_w + y.f_b3, HID, s_h, 0, ACT_TANH);
   fence_proxy_async();
-  __syncthreads();
+  gsync<WS>();
   if (tid == 0) {
     bulk_s2g(st_h3, s_h, HID * TMP * 4);
     bulk_commit();
   }
-  // fc_out + sigmoid : s_h -> s_x1 rows [64, 64+Mo4)
-  float* s_act = s_x1 + HID * TMP;
+  // fc_out + sigmoid : s_h -> s_act
+  if (act_wait) mbar_wait(act_wait, act_parity);
   dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_wo, y.ld_fwo, mma_sw(y.ld_fwo), s_w + y.f_bo, y.Mo4, s_act, 0,
                       ACT_SIGMOID);
   fence_proxy_async();
-  __syncthreads();
+  gsync<WS>();
   if (tid == 0) {
     bulk_s2g(st_act, s_act, y.Mo4 * TMP * 4);
     bulk_commit();

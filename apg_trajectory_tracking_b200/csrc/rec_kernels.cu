@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(NT, 1) rec_fwd_kernel(const HutterLayout y, co
         bulk_s2g(g.st_x1 + sk * y.K1 * TMP, s_x1, y.K1 * TMP * 4);
         bulk_commit();
       }
-      hutter_trunk(L, y, s_w, s_x1, s_h, g.st_h1 + sk * HID * TMP, g.st_h2 + sk * HID * TMP, g.st_h3 + sk * HID * TMP,
-                   g.st_act + sk * y.Mo4 * TMP);
+      hutter_trunk<false>(L, y, s_w, s_x1, s_h, s_act, g.st_h1 + sk * HID * TMP, g.st_h2 + sk * HID * TMP,
+                          g.st_h3 + sk * HID * TMP, g.st_act + sk * y.Mo4 * TMP);
       if (tid < valid) {
         float a[A], rf[R], sn[S];
 #pragma unroll

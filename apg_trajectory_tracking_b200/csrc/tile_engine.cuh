@@ -51,6 +51,15 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier of the GEMM warp group (threads 0..255) in the warp-specialised kernels; plain __syncthreads otherwise
+template <bool WS>
+__device__ __forceinline__ void gsync() {
+  if (WS) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else __syncthreads();
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
@@ -263,24 +272,22 @@ __device__ __forceinline__ void dense_mma(const Lane& L, const float* __restrict
     for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
     const float* ap = A + t * TMP + m0 + g;
     const float* wp = W + t * ldw;
-    int ncol[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ncol[j] = (wcol0 + (nt0 + (j < ntc ? j : 0)) * 8 + g) ^ xs;
-    // raw fragments of the next k-step are fetched while the tensor instructions of the current one issue
-    float ra[4], rb[4][2];
-    auto fetch = [&](int k0) {
-      ra[0] = ap[k0 * TMP]; ra[1] = ap[k0 * TMP + 8]; ra[2] = ap[(k0 + 4) * TMP]; ra[3] = ap[(k0 + 4) * TMP + 8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { rb[j][0] = wp[k0 * ldw + ncol[j]]; rb[j][1] = wp[(k0 + 4) * ldw + ncol[j]]; }
-    };
-    fetch(0);
+#pragma unroll 2
     for (int k0 = 0; k0 < K; k0 += 8) {
-      uint32_t ah[4], al[4], bh[4][2], bl[4][2];
+      uint32_t ah[4], al[4];
+      split_tf32(ap[k0 * TMP], ah[0], al[0]);
+      split_tf32(ap[k0 * TMP + 8], ah[1], al[1]);
+      split_tf32(ap[(k0 + 4) * TMP], ah[2], al[2]);
+      split_tf32(ap[(k0 + 4) * TMP + 8], ah[3], al[3]);
+      uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) split_tf32(ra[i], ah[i], al[i]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { split_tf32(rb[j][0], bh[j][0], bl[j][0]); split_tf32(rb[j][1], bh[j][1], bl[j][1]); }
-      if (k0 + 8 < K) fetch(k0 + 8);
+      for (int j = 0; j < 4; ++j) {
+        if (j < ntc) {
+          const int n = (wcol0 + (nt0 + j) * 8 + g) ^ xs;
+          split_tf32(wp[k0 * ldw + n], bh[j][0], bl[j][0]);
+          split_tf32(wp[(k0 + 4) * ldw + n], bh[j][1], bl[j][1]);
+        }
+      }
       // term-major order: consecutive tensor instructions hit different accumulators
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (j < ntc) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
@@ -347,23 +354,22 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < NTP; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
       const float* zp = dz + (j0 + g) * TMP + t;
-      const float* xp[NTP];
-#pragma unroll
-      for (int j = 0; j < NTP; ++j) xp[j] = x + ((n0 + j < ne ? n0 + j : n0) * 8 + g) * TMP + t;
-      float ra[4], rb[NTP][2];
-      auto fetch = [&](int d0) {
-        ra[0] = zp[d0]; ra[1] = zp[8 * TMP + d0]; ra[2] = zp[d0 + 4]; ra[3] = zp[8 * TMP + d0 + 4];
-#pragma unroll
-        for (int j = 0; j < NTP; ++j) { rb[j][0] = xp[j][d0]; rb[j][1] = xp[j][d0 + 4]; }
-      };
-      fetch(0);
+#pragma unroll 2
       for (int d0 = 0; d0 < TM; d0 += 8) {
-        uint32_t ah[4], al[4], bh[NTP][2], bl[NTP][2];
+        uint32_t ah[4], al[4];
+        split_tf32(zp[d0], ah[0], al[0]);
+        split_tf32(zp[8 * TMP + d0], ah[1], al[1]);
+        split_tf32(zp[d0 + 4], ah[2], al[2]);
+        split_tf32(zp[8 * TMP + d0 + 4], ah[3], al[3]);
+        uint32_t bh[NTP][2], bl[NTP][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(ra[i], ah[i], al[i]);
-#pragma unroll
-        for (int j = 0; j < NTP; ++j) { split_tf32(rb[j][0], bh[j][0], bl[j][0]); split_tf32(rb[j][1], bh[j][1], bl[j][1]); }
-        if (d0 + 8 < TM) fetch(d0 + 8);
+        for (int j = 0; j < NTP; ++j) {
+          if (n0 + j < ne) {
+            const float* xp = x + ((n0 + j) * 8 + g) * TMP + d0 + t;
+            split_tf32(xp[0], bh[j][0], bl[j][0]);
+            split_tf32(xp[4], bh[j][1], bl[j][1]);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < NTP; ++j) if (n0 + j < ne) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
 #pragma unroll
@@ -401,7 +407,8 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float c)
 // dW[j][k] += sum_d dZ[j][d] X[k][d], X feature-major [K][TMP]; K <= 32*NKI.  Also db[j] += sum_d dZ[j][d].
 template <int NKI>
 __device__ __forceinline__ void dw_T(const Lane& L, const float* __restrict__ dz, int M, const float* __restrict__ x,
-                                     int K, float* __restrict__ P, int ldp, float* __restrict__ Pb, int perm_npos = 0) {
+                                     int K, float* __restrict__ P, int ldp, float* __restrict__ Pb, int perm_npos = 0,
+                                     int col0 = 0) {
   for (int j0 = 8 * L.warp; j0 < M; j0 += 8 * NWARP) {
     float acc[8][NKI];
     float accb[8];
@@ -435,7 +442,7 @@ __device__ __forceinline__ void dw_T(const Lane& L, const float* __restrict__ dz
 #pragma unroll
         for (int i = 0; i < NKI; ++i) {
           const int k = L.lane + 32 * i;
-          if (k < K) red_add(P + j * ldp + perm_col(k, perm_npos), acc[jj][i]);
+          if (k < K) red_add(P + j * ldp + perm_col(col0 + k, perm_npos), acc[jj][i]);
         }
         if (Pb && L.lane == 0) red_add(Pb + j, accb[jj]);
       }
@@ -495,16 +502,11 @@ __device__ __forceinline__ void dw_auto(const Lane& L, const float* __restrict__
     else dw_mma<5>(L, dz, M, x, K, P, ldp, perm_npos);
     return;
   }
-  const int nki = (K + 31) / 32;
-  switch (nki) {
-    case 1: dw_T<1>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
-    case 2: dw_T<2>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
-    case 3: dw_T<3>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
-    case 4: dw_T<4>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
-    case 5: dw_T<5>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
-    case 6: dw_T<6>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
-    case 7: dw_T<7>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
-    default: dw_T<8>(L, dz, M, x, K, P, ldp, Pb, perm_npos); break;
+  // FFMA fallback in column blocks of 64 (keeps the register footprint of the unaligned path small)
+  for (int c0 = 0; c0 < K; c0 += 64) {
+    const int kc = K - c0 < 64 ? K - c0 : 64;
+    if (kc <= 32) dw_T<1>(L, dz, M, x + c0 * TMP, kc, P, ldp, c0 == 0 ? Pb : nullptr, perm_npos, c0);
+    else dw_T<2>(L, dz, M, x + c0 * TMP, kc, P, ldp, c0 == 0 ? Pb : nullptr, perm_npos, c0);
   }
 }
 

@@ -7,8 +7,8 @@ import torch
 from apg_trajectory_tracking_b200 import rollout as R, synthetic as SY, _capi
 import bench
 
-FWD = ["setup", "wait inputs", "first layer", "trunk fc1..out", "dynamics+loss", "store drain", "tail"]
-ADJ = ["setup", "dyn adjoint", "wait h3", "dW out", "dX out", "wait h2", "dW fc3", "dX fc3", "wait h1", "dW fc2", "dX fc2",
+FWD = ["setup", "wait inputs", "first layer", "trunk fc1..out (+wait act_empty)", "handoff + store drain"]
+ADJ = ["setup", "wait dlog (dyn warps)", "wait h3", "dW out", "dX out", "wait h2", "dW fc3", "dX fc3", "wait h1", "dW fc2", "dX fc2",
        "wait X1", "dW fc1", "dX fc1", "wait inputs", "first-layer dW"]
 
 def main():
