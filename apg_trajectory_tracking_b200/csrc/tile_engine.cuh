@@ -353,14 +353,16 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
       float acc[NTP][4];
 #pragma unroll
       for (int j = 0; j < NTP; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      const float* zp = dz + (j0 + g) * TMP + t;
+      // rows beyond M (last 16-row tile of e.g. M = 40) are clamped: their results are discarded below
+      const float* zp = dz + (j0 + g < M ? j0 + g : M - 1) * TMP + t;
+      const float* zq = dz + (j0 + g + 8 < M ? j0 + g + 8 : M - 1) * TMP + t;
 #pragma unroll 2
       for (int d0 = 0; d0 < TM; d0 += 8) {
         uint32_t ah[4], al[4];
         split_tf32(zp[d0], ah[0], al[0]);
-        split_tf32(zp[8 * TMP + d0], ah[1], al[1]);
+        split_tf32(zq[d0], ah[1], al[1]);
         split_tf32(zp[d0 + 4], ah[2], al[2]);
-        split_tf32(zp[8 * TMP + d0 + 4], ah[3], al[3]);
+        split_tf32(zq[d0 + 4], ah[3], al[3]);
         uint32_t bh[NTP][2], bl[NTP][2];
 #pragma unroll
         for (int j = 0; j < NTP; ++j) {
