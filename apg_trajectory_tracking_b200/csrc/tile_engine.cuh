@@ -272,6 +272,11 @@ __device__ __forceinline__ void dense_mma(const Lane& L, const float* __restrict
     for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
     const float* ap = A + t * TMP + m0 + g;
     const float* wp = W + t * ldw;
+    // column of B fragment j; tiles beyond ntc are clamped onto a valid tile (computed, then discarded): predicated
+    // mma.sync would cost a WARPSYNC + NOP per instruction
+    int ncol[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ncol[j] = (wcol0 + (nt0 + (j < ntc ? j : 0)) * 8 + g) ^ xs;
 #pragma unroll 2
     for (int k0 = 0; k0 < K; k0 += 8) {
       uint32_t ah[4], al[4];
@@ -282,19 +287,16 @@ __device__ __forceinline__ void dense_mma(const Lane& L, const float* __restrict
       uint32_t bh[4][2], bl[4][2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j < ntc) {
-          const int n = (wcol0 + (nt0 + j) * 8 + g) ^ xs;
-          split_tf32(wp[k0 * ldw + n], bh[j][0], bl[j][0]);
-          split_tf32(wp[(k0 + 4) * ldw + n], bh[j][1], bl[j][1]);
-        }
+        split_tf32(wp[k0 * ldw + ncol[j]], bh[j][0], bl[j][0]);
+        split_tf32(wp[(k0 + 4) * ldw + ncol[j]], bh[j][1], bl[j][1]);
       }
       // term-major order: consecutive tensor instructions hit different accumulators
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (j < ntc) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+      for (int j = 0; j < 4; ++j) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (j < ntc) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+      for (int j = 0; j < 4; ++j) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (j < ntc) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
+      for (int j = 0; j < 4; ++j) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -353,9 +355,13 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
       float acc[NTP][4];
 #pragma unroll
       for (int j = 0; j < NTP; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      // rows beyond M (last 16-row tile of e.g. M = 40) are clamped: their results are discarded below
+      // rows beyond M (last 16-row tile of e.g. M = 40) and column tiles beyond `ne` are clamped onto valid data and
+      // their results discarded below: every mma.sync stays unconditional
       const float* zp = dz + (j0 + g < M ? j0 + g : M - 1) * TMP + t;
       const float* zq = dz + (j0 + g + 8 < M ? j0 + g + 8 : M - 1) * TMP + t;
+      const float* xp[NTP];
+#pragma unroll
+      for (int j = 0; j < NTP; ++j) xp[j] = x + ((n0 + j < ne ? n0 + j : n0) * 8 + g) * TMP + t;
 #pragma unroll 2
       for (int d0 = 0; d0 < TM; d0 += 8) {
         uint32_t ah[4], al[4];
@@ -366,18 +372,15 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
         uint32_t bh[NTP][2], bl[NTP][2];
 #pragma unroll
         for (int j = 0; j < NTP; ++j) {
-          if (n0 + j < ne) {
-            const float* xp = x + ((n0 + j) * 8 + g) * TMP + d0 + t;
-            split_tf32(xp[0], bh[j][0], bl[j][0]);
-            split_tf32(xp[4], bh[j][1], bl[j][1]);
-          }
+          split_tf32(xp[j][d0], bh[j][0], bl[j][0]);
+          split_tf32(xp[j][d0 + 4], bh[j][1], bl[j][1]);
         }
 #pragma unroll
-        for (int j = 0; j < NTP; ++j) if (n0 + j < ne) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+        for (int j = 0; j < NTP; ++j) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
 #pragma unroll
-        for (int j = 0; j < NTP; ++j) if (n0 + j < ne) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+        for (int j = 0; j < NTP; ++j) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
 #pragma unroll
-        for (int j = 0; j < NTP; ++j) if (n0 + j < ne) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
+        for (int j = 0; j < NTP; ++j) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
       }
 #pragma unroll
       for (int j = 0; j < NTP; ++j) {
@@ -501,7 +504,7 @@ __device__ __forceinline__ void dw_auto(const Lane& L, const float* __restrict__
   if ((K & 7) == 0 && M >= 16) {
     bias_grad(dz, M, Pb);
     if (K <= 64) dw_mma<4>(L, dz, M, x, K, P, ldp, perm_npos);
-    else dw_mma<5>(L, dz, M, x, K, P, ldp, perm_npos);
+    else dw_mma<7>(L, dz, M, x, K, P, ldp, perm_npos);
     return;
   }
   // FFMA fallback in column blocks of 64 (keeps the register footprint of the unaligned path small)
