@@ -39,9 +39,11 @@ __device__ __forceinline__ void aos_mma_block(const Lane& L, const float* __rest
                                               int row0, int row_stride, int act) {
   const int g = L.lane >> 2, t = L.lane & 3;
   const int xs = sw ? (t << 3) : 0;
-  float acc[NTC][4];
+  float acc[NTC][4], acc1[NTC][4], acc2[NTC][4];
 #pragma unroll
-  for (int j = 0; j < NTC; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int j = 0; j < NTC; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = acc1[j][e] = acc2[j][e] = 0.f;
   const float* wp = W + t * ldw;
   for (int k0 = 0; k0 < K; k0 += 8) {
     uint32_t ah[4], al[4];
@@ -54,12 +56,16 @@ __device__ __forceinline__ void aos_mma_block(const Lane& L, const float* __rest
       split_tf32(wp[(k0 + 4) * ldw + n], bh[j][1], bl[j][1]);
     }
 #pragma unroll
-    for (int j = 0; j < NTC; ++j) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+    for (int j = 0; j < NTC; ++j) mma_tf32(acc1[j], al, bh[j][0], bh[j][1]);
 #pragma unroll
-    for (int j = 0; j < NTC; ++j) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+    for (int j = 0; j < NTC; ++j) mma_tf32(acc2[j], ah, bl[j][0], bl[j][1]);
 #pragma unroll
     for (int j = 0; j < NTC; ++j) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
   }
+#pragma unroll
+  for (int j = 0; j < NTC; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] += acc1[j][e] + acc2[j][e];
 #pragma unroll
   for (int j = 0; j < NTC; ++j) {
 #pragma unroll

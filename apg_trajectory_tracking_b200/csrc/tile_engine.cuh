@@ -267,9 +267,12 @@ __device__ __forceinline__ void dense_mma(const Lane& L, const float* __restrict
   for (int nc = (L.warp >> 2); nc * 4 < nt8; nc += 2) {
     const int nt0 = nc * 4;
     const int ntc = nt8 - nt0 < 4 ? nt8 - nt0 : 4;
-    float acc[4][4];
+    // one accumulator chain per 3xTF32 term (lo*hi, hi*lo, hi*hi): a dependent tensor instruction only every 12th
+    float acc[4][4], acc1[4][4], acc2[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = acc1[j][e] = acc2[j][e] = 0.f;
     const float* ap = A + t * TMP + m0 + g;
     const float* wp = W + t * ldw;
     // column of B fragment j; tiles beyond ntc are clamped onto a valid tile (computed, then discarded): predicated
@@ -290,14 +293,17 @@ __device__ __forceinline__ void dense_mma(const Lane& L, const float* __restrict
         split_tf32(wp[k0 * ldw + ncol[j]], bh[j][0], bl[j][0]);
         split_tf32(wp[(k0 + 4) * ldw + ncol[j]], bh[j][1], bl[j][1]);
       }
-      // term-major order: consecutive tensor instructions hit different accumulators
 #pragma unroll
-      for (int j = 0; j < 4; ++j) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+      for (int j = 0; j < 4; ++j) mma_tf32(acc1[j], al, bh[j][0], bh[j][1]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+      for (int j = 0; j < 4; ++j) mma_tf32(acc2[j], ah, bl[j][0], bl[j][1]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] += acc1[j][e] + acc2[j][e];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < ntc) {
@@ -352,9 +358,11 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
     const int nb = (L.warp >> 2) * per_half;
     const int ne = nb + per_half < nt8 ? nb + per_half : nt8;
     for (int n0 = nb; n0 < ne; n0 += NTP) {
-      float acc[NTP][4];
+      float acc[NTP][4], acc1[NTP][4], acc2[NTP][4];
 #pragma unroll
-      for (int j = 0; j < NTP; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      for (int j = 0; j < NTP; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = acc1[j][e] = acc2[j][e] = 0.f;
       // rows beyond M (last 16-row tile of e.g. M = 40) and column tiles beyond `ne` are clamped onto valid data and
       // their results discarded below: every mma.sync stays unconditional
       const float* zp = dz + (j0 + g < M ? j0 + g : M - 1) * TMP + t;
@@ -376,12 +384,16 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
           split_tf32(xp[j][d0 + 4], bh[j][1], bl[j][1]);
         }
 #pragma unroll
-        for (int j = 0; j < NTP; ++j) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+        for (int j = 0; j < NTP; ++j) mma_tf32(acc1[j], al, bh[j][0], bh[j][1]);
 #pragma unroll
-        for (int j = 0; j < NTP; ++j) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+        for (int j = 0; j < NTP; ++j) mma_tf32(acc2[j], ah, bl[j][0], bl[j][1]);
 #pragma unroll
         for (int j = 0; j < NTP; ++j) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
       }
+#pragma unroll
+      for (int j = 0; j < NTP; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] += acc1[j][e] + acc2[j][e];
 #pragma unroll
       for (int j = 0; j < NTP; ++j) {
         if (n0 + j < ne) {
@@ -503,8 +515,7 @@ __device__ __forceinline__ void dw_auto(const Lane& L, const float* __restrict__
                                         int perm_npos = 0) {
   if ((K & 7) == 0 && M >= 16) {
     bias_grad(dz, M, Pb);
-    if (K <= 64) dw_mma<4>(L, dz, M, x, K, P, ldp, perm_npos);
-    else dw_mma<7>(L, dz, M, x, K, P, ldp, perm_npos);
+    dw_mma<4>(L, dz, M, x, K, P, ldp, perm_npos);
     return;
   }
   // FFMA fallback in column blocks of 64 (keeps the register footprint of the unaligned path small)
