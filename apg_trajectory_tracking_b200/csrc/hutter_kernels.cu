@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NTH, 1) hutter_adj_kernel(const HutterLayout y
     // ===================================================== GEMM group
     const Lane L;
     float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
-    for (int i = tid; i < y.n_params; i += NT) P[i] = 0.f;
+    for (int i = tid; i < y.n_params; i += NT) __stcg(P + i, 0.f);
     const uint32_t hbytes = HID * TMP * 4;
     auto issue_stage_loads = [&](int tile) {    // thread 0
       mbar_expect_tx(bar_A, y.K1 * TMP * 4);

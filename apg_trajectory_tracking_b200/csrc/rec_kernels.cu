@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT, 1) rec_adj_kernel(const HutterLayout y, co
   const int tid = threadIdx.x;
   const int ntiles = (g.N + TM - 1) / TM;
   float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
-  for (int i = tid; i < y.n_params; i += NT) P[i] = 0.f;
+  for (int i = tid; i < y.n_params; i += NT) __stcg(P + i, 0.f);
   if (tid == 0) {
     for (int b = 0; b < 5; ++b) mbar_init(bars + b, 1);
     fence_mbar_init();

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(NT, 1) simple_adj_kernel(const SimpleLayout y,
   const int tid = threadIdx.x;
   const int ntiles = (g.N + TM - 1) / TM;
   float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
-  for (int i = tid; i < y.n_params; i += NT) P[i] = 0.f;
+  for (int i = tid; i < y.n_params; i += NT) __stcg(P + i, 0.f);
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_a, 1);
