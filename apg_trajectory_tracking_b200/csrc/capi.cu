@@ -348,7 +348,13 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
   } else {
     if ((ce = launch_simple_adj(simple_layout(cfg), a, p.grid, st))) return (int)ce;
   }
-  if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;
+  int pm_off = 0, pm_k1 = 0, pm_npos = 0;
+  if (is_hutter(cfg)) {
+    const HutterLayout y = hutter_layout(cfg);
+    pm_off = y.t_w1; pm_k1 = y.K1; pm_npos = y.perm_npos;
+  }
+  if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st, pm_off, pm_k1, pm_npos)))
+    return (int)ce;
   return 0;
 }
 

@@ -193,13 +193,8 @@ __device__ __forceinline__ void aos_linear64_dw(const Lane& L, const float* __re
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[e] += acc1[e] + acc2[e];
     const int k = nt * 8 + 2 * t;
-    float* pa[4] = {k < K ? P + (j0 + g) * K + k : nullptr, k + 1 < K ? P + (j0 + g) * K + k + 1 : nullptr,
-                    k < K ? P + (j0 + g + 8) * K + k : nullptr, k + 1 < K ? P + (j0 + g + 8) * K + k + 1 : nullptr};
-    float old[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) old[e] = pa[e] ? ldp(pa[e]) : 0.f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) if (pa[e]) stp(pa[e], old[e] + acc[e]);
+    if (k < K) { red_add(P + (j0 + g) * K + k, acc[0]); red_add(P + (j0 + g + 8) * K + k, acc[2]); }
+    if (k + 1 < K) { red_add(P + (j0 + g) * K + k + 1, acc[1]); red_add(P + (j0 + g + 8) * K + k + 1, acc[3]); }
   }
 }
 
@@ -220,7 +215,7 @@ __device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, co
         s += (z.x + z.y) + (z.z + z.w);
       }
     }
-    stp(P + y.t_bc + threadIdx.x, ldp(P + y.t_bc + threadIdx.x) + s);
+    red_add(P + y.t_bc + threadIdx.x, s);
   }
   const int c0 = (L.warp & 1) * 16;
   const int ca = min(c0 + g, CONV_CH - 1), cb = min(c0 + g + 8, CONV_CH - 1);      // clamped rows (discarded)
@@ -245,17 +240,14 @@ __device__ __forceinline__ void conv_dw(const Lane& L, const HutterLayout& y, co
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[e] += acc1[e] + acc2[e];
-    float* pa[4];
-    float old[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int c = c0 + g + ((e >> 1) << 3), kk = nt * 8 + 2 * t + (e & 1);
-      const int j = kk / y.RD, dch = kk - j * y.RD;
-      pa[e] = (c < CONV_CH && kk < y.KC) ? P + y.t_wc + c * y.KC + dch * 3 + j : nullptr;   // torch layout [c][d][j]
-      old[e] = pa[e] ? ldp(pa[e]) : 0.f;
+      if (c < CONV_CH && kk < y.KC) {
+        const int j = kk / y.RD, dch = kk - j * y.RD;
+        red_add(P + y.t_wc + c * y.KC + dch * 3 + j, acc[e]);      // torch layout [c][d][j]
+      }
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) if (pa[e]) stp(pa[e], old[e] + acc[e]);
   }
 }
 

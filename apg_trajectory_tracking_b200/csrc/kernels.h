@@ -21,7 +21,8 @@ cudaError_t launch_simple_fwd(const SimpleLayout& y, const RolloutArgs& a, int g
 cudaError_t launch_simple_adj(const SimpleLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 
 cudaError_t launch_pack(const PackTable& t, const float* params, float* wf, float* wb, cudaStream_t st);
-cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st);
+cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st,
+                               int pm_off = 0, int pm_k1 = 0, int pm_npos = 0);
 cudaError_t launch_sum_loss(const float* partials, int ncta, float* loss, cudaStream_t st);
 cudaError_t launch_step(int system, const PhysConsts& pc, const float* s, const float* a, float dt, int n, float* out,
                         cudaStream_t st);

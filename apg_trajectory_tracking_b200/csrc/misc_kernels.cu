@@ -54,24 +54,36 @@ cudaError_t launch_pack(const PackTable& t, const float* params, float* wf, floa
 }
 
 // grad[p] = scale * sum_c partials[c][p], fixed summation order -> bitwise reproducible
+// The kernels keep the fc1 weight-gradient block [64][K1] of the hutter conv nets in their position-major column
+// order (64 + t*20 + c); pm_* describe that block so that the torch (channel-major, 64 + c*npos + t) entry p reads
+// the right partial column.  pm_npos == 0: no permutation.
 __global__ void apg_reduce_kernel(const float* __restrict__ partials, int ncta, int n, float scale,
-                                  float* __restrict__ grad) {
+                                  float* __restrict__ grad, int pm_off, int pm_k1, int pm_npos) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
+  int q = p;
+  if (pm_npos > 0 && p >= pm_off && p < pm_off + 64 * pm_k1) {
+    const int j = (p - pm_off) / pm_k1, k = (p - pm_off) - j * pm_k1;
+    if (k >= 64) {
+      const int c = (k - 64) / pm_npos, tt = (k - 64) - c * pm_npos;
+      q = pm_off + j * pm_k1 + 64 + tt * 20 + c;
+    }
+  }
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int c = 0;
   for (; c + 3 < ncta; c += 4) {
-    s0 += partials[(size_t)(c + 0) * n + p];
-    s1 += partials[(size_t)(c + 1) * n + p];
-    s2 += partials[(size_t)(c + 2) * n + p];
-    s3 += partials[(size_t)(c + 3) * n + p];
+    s0 += partials[(size_t)(c + 0) * n + q];
+    s1 += partials[(size_t)(c + 1) * n + q];
+    s2 += partials[(size_t)(c + 2) * n + q];
+    s3 += partials[(size_t)(c + 3) * n + q];
   }
-  for (; c < ncta; ++c) s0 += partials[(size_t)c * n + p];
+  for (; c < ncta; ++c) s0 += partials[(size_t)c * n + q];
   grad[p] = scale * ((s0 + s1) + (s2 + s3));
 }
 
-cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st) {
-  apg_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(partials, ncta, n, scale, grad);
+cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st,
+                               int pm_off, int pm_k1, int pm_npos) {
+  apg_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(partials, ncta, n, scale, grad, pm_off, pm_k1, pm_npos);
   return cudaGetLastError();
 }
 

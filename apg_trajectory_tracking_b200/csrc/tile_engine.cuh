@@ -120,12 +120,10 @@ __device__ __forceinline__ void red_add(float* addr, float v) {
 
 // Destination column of gradient column k.  Conv activations are kept position-major (64 + t*20 + c) in shared
 // memory / the stash while the reference's fc1 weight is channel-major (64 + c*npos + t): perm_npos > 0 maps back.
-// The per-CTA gradient partial lives in L2: every entry has exactly one owner thread (same CTA, same thread for all
-// tiles), so it is accumulated with plain loads / stores that bypass L1.  Global reductions (red.global.add) retire at
-// only ~1.3 cycles per lane per SM (measured: the dW phases cost 1.3 cycles per weight per tile), so the hot paths
-// prefetch the old values before their MMA loop and store old + acc afterwards; red_add remains for cold paths.
-__device__ __forceinline__ float ldp(const float* addr) { return __ldcg(addr); }
-__device__ __forceinline__ void stp(float* addr, float v) { __stcg(addr, v); }
+// two adjacent floats (8-byte aligned) in one reduction: the (col 2t, 2t+1) pair of an mma C fragment
+__device__ __forceinline__ void red_add2(float* addr, float a, float b) {
+  asm volatile("red.global.v2.f32.add [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 
 __device__ __forceinline__ int perm_col(int k, int perm_npos) {
   if (perm_npos <= 0 || k < 64) return k;
@@ -348,7 +346,7 @@ __device__ __forceinline__ void bias_grad(const float* __restrict__ dz, int M, f
       s0 += z.x + z.y;
       s1 += z.z + z.w;
     }
-    stp(Pb + j, ldp(Pb + j) + (s0 + s1));
+    red_add(Pb + j, s0 + s1);
   }
 }
 
@@ -369,21 +367,7 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
 #pragma unroll
       for (int j = 0; j < NTP; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc1[j][e] = acc2[j][e] = 0.f;
-      // prefetch the owner's running sums (L2) into the hi*hi accumulators: the load latency hides behind the MMAs
-      float* pa[NTP][4];
-#pragma unroll
-      for (int j = 0; j < NTP; ++j) {
-        const int k = (n0 + j) * 8 + 2 * t;
-        const int k0c = perm_col(k, perm_npos), k1c = perm_col(k + 1, perm_npos);
-        const bool tv = n0 + j < ne, r0 = j0 + g < M, r1 = j0 + g + 8 < M;
-        pa[j][0] = (tv && r0) ? P + (j0 + g) * ldp_ + k0c : nullptr;
-        pa[j][1] = (tv && r0) ? P + (j0 + g) * ldp_ + k1c : nullptr;
-        pa[j][2] = (tv && r1) ? P + (j0 + g + 8) * ldp_ + k0c : nullptr;
-        pa[j][3] = (tv && r1) ? P + (j0 + g + 8) * ldp_ + k1c : nullptr;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[j][e] = pa[j][e] ? ldp(pa[j][e]) : 0.f;
-      }
+        for (int e = 0; e < 4; ++e) acc[j][e] = acc1[j][e] = acc2[j][e] = 0.f;
       // rows beyond M (last 16-row tile of e.g. M = 40) and column tiles beyond `ne` are clamped onto valid data and
       // their results discarded below: every mma.sync stays unconditional
       const float* zp = dz + (j0 + g < M ? j0 + g : M - 1) * TMP + t;
@@ -411,11 +395,25 @@ __device__ __forceinline__ void dw_mma(const Lane& L, const float* __restrict__ 
 #pragma unroll
         for (int j = 0; j < NTP; ++j) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
       }
+      // The CTA's partial keeps the KERNEL's column order (fragment pairs adjacent -> one 8-byte vector reduction, a
+      // warp instruction touches 8 sectors instead of 32); apg_reduce_kernel maps to the torch order.
+      const bool vec = (ldp_ & 1) == 0;
 #pragma unroll
-      for (int j = 0; j < NTP; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (pa[j][e]) stp(pa[j][e], acc[j][e] + (acc1[j][e] + acc2[j][e]));
+      for (int j = 0; j < NTP; ++j) {
+        if (n0 + j < ne) {
+          const int k = (n0 + j) * 8 + 2 * t;
+          const float c0 = acc[j][0] + (acc1[j][0] + acc2[j][0]), c1 = acc[j][1] + (acc1[j][1] + acc2[j][1]);
+          const float c2 = acc[j][2] + (acc1[j][2] + acc2[j][2]), c3 = acc[j][3] + (acc1[j][3] + acc2[j][3]);
+          if (j0 + g < M) {
+            float* a0 = P + (j0 + g) * ldp_ + k;
+            if (vec) red_add2(a0, c0, c1); else { red_add(a0, c0); red_add(a0 + 1, c1); }
+          }
+          if (j0 + g + 8 < M) {
+            float* a1 = P + (j0 + g + 8) * ldp_ + k;
+            if (vec) red_add2(a1, c2, c3); else { red_add(a1, c2); red_add(a1 + 1, c3); }
+          }
+        }
+      }
     }
   }
 }
@@ -466,7 +464,7 @@ __device__ __forceinline__ void dw_T(const Lane& L, const float* __restrict__ dz
 #pragma unroll
         for (int i = 0; i < NKI; ++i) {
           const int k = L.lane + 32 * i;
-          if (k < K) red_add(P + j * ldp + perm_col(col0 + k, perm_npos), acc[jj][i]);
+          if (k < K) red_add(P + j * ldp + col0 + k, acc[jj][i]);
         }
         if (Pb && L.lane == 0) red_add(Pb + j, accb[jj]);
       }
