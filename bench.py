@@ -372,6 +372,9 @@ def main():
                 traffic = None
         sm_max = clocks.get("sm_max_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        # legacy-path tensor rate measured on this pool (tools/micro/rates.cu): mma.sync m16n8k8 tf32 = 476 MAC/clk/SM;
+        # the kernels spend 3 tensor instructions per product (3xTF32) -> fp32-equivalent peak = a third of that
+        mma_tf32_peak = 148 * 476 * 2 * sm_max * 1e6 / 1e12
         line = {
             "metric": "drone-steps/sec (fwd+bwd)", "value": value, "unit": "drone-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -385,12 +388,16 @@ def main():
             "roofline": {"bound": "hbm", "kernel": f"adjoint ({kname} + apg_reduce_kernel)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src,
-                         "note": "algorithmic bytes = per-drone inputs read once by the adjoint pass; the path is "
-                                 "fp32-FMA bound (arithmetic intensity ~100 flop/B), see roofline_compute"},
-            "roofline_compute": {"bound": "fp32_fma", "achieved": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9,
-                                 "peak": fp32_peak, "unit": "TFLOP/s",
-                                 "frac": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9 / fp32_peak,
-                                 "peak_source": "148 SM x 128 FMA/clk x 2 x clocks.max.sm (nominal)"},
+                         "note": "algorithmic bytes = per-drone inputs read once by the adjoint pass; traffic = ncu dram "
+                                 "bytes of one adjoint launch (it reads the 2.3 KB/drone activation stash); the path "
+                                 "is compute bound (arithmetic intensity ~100 flop/B), see roofline_compute"},
+            "roofline_compute": {"bound": "tensor (mma.sync tf32, 3xTF32 split = 3 instructions per product)",
+                                 "achieved": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9,
+                                 "peak": mma_tf32_peak / 3.0, "unit": "TFLOP/s (fp32-equivalent algorithmic flops)",
+                                 "frac": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9 / (mma_tf32_peak / 3.0),
+                                 "peak_source": "measured mma.sync m16n8k8 tf32 rate 476 MAC/clk/SM x 148 SM x "
+                                                "clocks.max.sm / 3 (tools/micro/rates.cu); fp32 FFMA peak for "
+                                                "reference: %.1f TFLOP/s" % fp32_peak},
             "e2e": {"value": e2e_value, "unit": "drone-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "api": "apg_trajectory_tracking_b200.train.FusedTrainStep.step(host tensors)"},
             "gpu_launches": stepper.kernel_launches_per_step * args.steps,
