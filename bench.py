@@ -182,6 +182,18 @@ def cpu_reference_step(w, n, params, case, threads):
     return step
 
 
+def agree_extra_steps(need_s, t_step_s, device, distributed):
+    """Number of extra untimed steps to run after the timed region, IDENTICAL on every rank: each rank proposes
+    ceil(need / step time) and the MAX over ranks is taken with one all-reduce.  (Every step contains a gradient
+    all-reduce; a per-rank time-based loop would issue mismatched collectives and deadlock.)"""
+    n = min(int(need_s / max(t_step_s, 1e-5)) + 1, 20000) if need_s > 0 else 0
+    t = torch.tensor([n], device=device, dtype=torch.int64)
+    if distributed:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def physical_cores():
     try:
         import psutil
@@ -299,13 +311,16 @@ def main():
         e[3].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    extra_steps = 0
-    while time.perf_counter() - t_sampler0 < 1.5 and extra_steps < 5000:
+    # Extra identical untimed steps so that the 200 ms clock sampler sees >= ~1.5 s of load.  The count MUST be the
+    # same on every rank (each step contains an all-reduce): it is derived from the measured step time and agreed
+    # with one MAX all-reduce -- a time-based loop per rank would issue mismatched collectives and deadlock.
+    extra_steps = agree_extra_steps(max(0.0, 1.5 - (time.perf_counter() - t_sampler0)),
+                                    t_wall / max(args.steps, 1), dev, world > 1)
+    for i in range(extra_steps):
         stepper.step(*args_step)
-        extra_steps += 1
-        if extra_steps % 20 == 0:
+        if i % 50 == 49:
             torch.cuda.synchronize()
-    torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop()
     clocks["note"] = f"sampled over warm-up + timed region + {extra_steps} identical untimed steps"
     t_step = [e[0].elapsed_time(e[3]) for e in ev]

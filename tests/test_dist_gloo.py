@@ -86,3 +86,23 @@ def test_shard_bounds_cover_the_batch():
         b = [D.shard_bounds(n, r, w) for r in range(w)]
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def _agree_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo")
+    import bench
+    # the ranks see different elapsed times / step times: they must still agree on ONE count
+    n = bench.agree_extra_steps(1.0 if rank == 0 else 0.2, 1e-3 if rank == 0 else 3e-3, "cpu", True)
+    m = bench.agree_extra_steps(0.0, 1e-3, "cpu", True)
+    torch.save((n, m), f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_bench_extra_steps_are_rank_consistent(tmp_path):
+    """regression test: the clock-sampling extension of bench.py must run the same number of (all-reducing) steps
+    on every rank"""
+    out = str(tmp_path / "agree")
+    mp.spawn(_agree_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    assert r0 == r1 and r0[0] == 1001 and r0[1] == 0
