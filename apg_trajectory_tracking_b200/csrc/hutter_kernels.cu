@@ -2,12 +2,14 @@
 //   quadrotor  : Net(15, 10, 9, 4h, conv=True )  (scripts/train_drone.py:82-88,  175-203)
 //   fixed wing : Net( 9,  1, 3, 4h, conv=False)  (scripts/train_fixed_wing.py:67-73, 90-116)
 //
-// hutter_fwd_kernel  one persistent CTA per SM; per tile of 64 drones: TMA-staged input tiles -> policy forward
-//                    (all weights resident in shared memory, [in][out] packing) -> sigmoid -> h dynamics steps ->
-//                    tracking loss.  Activations / actions / states are stashed tile-major for the adjoint.
+// hutter_fwd_kernel  one persistent CTA per SM (8 GEMM warps + 2 dynamics warps); per tile of 64 drones: TMA-staged
+//                    input tiles -> policy forward on the tensor path (all weights resident in shared memory,
+//                    [in][out] packing) -> sigmoid -> h dynamics steps -> tracking loss.  Activations / actions /
+//                    states are stashed tile-major for the adjoint.
 // hutter_adj_kernel  replays the horizon in reverse (hand-written adjoint of the dynamics, no autograd tape),
 //                    back-propagates through the MLP ([out][in] weights resident) and accumulates the weight
-//                    gradient of its tiles into a per-CTA partial (deterministic, reduced by apg_reduce_kernel).
+//                    gradient of its tiles into a per-CTA partial (one owner thread per entry -> deterministic;
+//                    reduced over CTAs in a fixed order by apg_reduce_kernel).
 #include "dyn_phase.cuh"
 #include "layouts.h"
 #include "rollout_args.h"

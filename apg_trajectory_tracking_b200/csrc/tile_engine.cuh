@@ -5,13 +5,15 @@
 // walk consecutive rows hit distinct 16-byte bank groups).  Input tiles arrive in their natural drone-major
 // (AoS) layout by bulk async copies (TMA 1-D, cp.async.bulk + mbarrier) and are consumed in place.
 //
-//  dense()    Y[o][d] = epi( b[o] + sum_k A[k][d] * W[k][o] )        register tile 4 drones x 4 outputs / thread
-//             used for every layer forward (W packed [in][out]) and for dX (A = dZ, W = torch layout [out][in])
-//  dw_T()     dW[j][k] += sum_d dZ[j][d] * X[k][d]                    8 rows x NKI*32 columns per warp
-//  dw_AoS()   same with X drone-major (first layers read the input tiles directly)
-//
-// All arithmetic is fp32 FMA on the CUDA cores: the contractions here are 64-wide with fp32 parity required
-// (tolerance 1e-5 on the loss), see DESIGN.md for why the tensor-core variant is a 3xTF32 follow-up.
+//  tensor path (contractions with K and N multiples of 8 -- all the large layers):
+//    dense_mma()  Y[n][d] = epi( b[n] + sum_k A[k][d] * W[k][n] )      mma.sync m16n8k8 TF32, 3xTF32 split (fp32-level
+//    dw_mma()     dW[j][k] += sum_d dZ[j][d] * X[k][d]                 accuracy), warp tile 16 drones x 32 outputs
+//  FFMA path (odd-sized layers: cartpole net, LSTM cell, AR fc_out):
+//    dense()      same contraction, register tile 4 drones x 4 outputs per thread
+//    dw_T() / dw_AoS()  same dW, 8 rows x NKI*32 columns per warp (X feature-major / drone-major)
+//  dense_auto() / dw_auto() pick the path.  Forward layers read W packed [in][out]; dX reads the [out][in] copy with
+//  A = dZ and multiplies by the stored activation's derivative in place.  fp32 parity (1e-5 on the loss) is required,
+//  hence 3xTF32 and not plain TF32; see DESIGN.md section 3.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -248,16 +250,6 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0f,
-                                           float b1f) {
-  uint32_t bh0, bl0, bh1, bl1;
-  split_tf32(b0f, bh0, bl0);
-  split_tf32(b1f, bh1, bl1);
-  mma_tf32(c, al, bh0, bh1);
-  mma_tf32(c, ah, bl0, bl1);
-  mma_tf32(c, ah, bh0, bh1);
-}
-
 // Y[row0 + n][d] = epi(bias[n] + sum_k A[k][d] * W[k][n]) for the 64 drones of the tile; A feature-major [K][TMP],
 // W [K][ldw] (swizzled when sw), K % 8 == 0, N % 8 == 0.  Warp w: drones 16*(w&3) .., groups of 4 n-tiles
 // alternate between the two warp halves.
