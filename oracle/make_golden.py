@@ -49,6 +49,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
+    ap.add_argument("--only-prep", action="store_true", help="only (re)generate prep_data.npz")
     args = ap.parse_args()
     import_reference(args.ref)
     os.makedirs(args.out, exist_ok=True)
@@ -69,6 +70,40 @@ def main():
 
     quad, wing, cart = FlightmareDynamics(), FixedWingDynamics(), CartpoleDynamics()
     f32 = torch.float32
+
+    # ------------------------------------------------------------------ dataset layouts (prepare_data)
+    # QuadDataset.prepare_data / WingDataset.prepare_data of the reference on raw numpy (states, ref_states)
+    from neural_control.dataset import QuadDataset, WingDataset
+    gp = np.random.RandomState(77)
+    n_p, h_p = 6, 10
+    raw_states = np.concatenate((gp.uniform(-2, 2, (n_p, 3)), gp.uniform(-0.5, 0.5, (n_p, 3)),
+                                 gp.uniform(-2, 2, (n_p, 3)), gp.uniform(-0.5, 0.5, (n_p, 3))), axis=1)
+    raw_refs = gp.uniform(-3, 3, (n_p, h_p, 9))
+    qd = MagicMock()
+    qd.to_torch = lambda a: torch.from_numpy(np.array(a)).float()
+    qd.rot_world_to_body = QuadDataset.rot_world_to_body
+    q_in_state, q_states, q_in_ref, q_ref = QuadDataset.prepare_data(qd, raw_states.copy(), raw_refs.copy())
+    wmean_p = torch.tensor([0.0, 0.0, 0.0, 11.5, 0.0, 0.17, 0.007, 0.018, 0.02, 0.0, 0.017, 0.004]).float()
+    wstd_p = torch.tensor([16.6, 0.84, 0.89, 0.62, 0.28, 0.29, 0.045, 0.104, 0.05, 0.064, 0.275, 0.056]).float()
+    wd = MagicMock()
+    wd.mean, wd.std, wd.dt, wd.horizon = wmean_p, wstd_p, 0.05, h_p
+    wd.to_torch = qd.to_torch
+    wd._compute_target_pos = lambda cs_, rv: WingDataset._compute_target_pos(wd, cs_, rv)
+    w_raw_states = np.zeros((n_p, 12))
+    w_raw_states[:, :3] = gp.uniform(-1, 1, (n_p, 3))
+    w_raw_states[:, 3] = 11.5 + gp.uniform(-1, 1, n_p)
+    w_raw_states[:, 4:] = gp.uniform(-0.3, 0.3, (n_p, 8))
+    w_targets = np.stack((np.full(n_p, 50.0), gp.uniform(-5, 5, n_p), gp.uniform(-5, 5, n_p)), axis=1)
+    w_in_state, w_states, w_in_ref, w_ref = WingDataset.prepare_data(wd, w_raw_states.copy(), w_targets.copy())
+    np.savez_compressed(os.path.join(args.out, "prep_data.npz"), **npify(dict(
+        quad_raw_states=raw_states, quad_raw_refs=raw_refs, quad_in_state=q_in_state, quad_states=q_states,
+        quad_in_ref=q_in_ref, quad_ref=q_ref, wing_raw_states=w_raw_states, wing_targets=w_targets, wing_mean=wmean_p,
+        wing_std=wstd_p, wing_dt=np.float64(0.05), wing_h=np.int64(h_p), wing_in_state=w_in_state,
+        wing_states=w_states, wing_in_ref=w_in_ref, wing_ref=w_ref)))
+    print("prep_data: quad", tuple(q_in_state.shape), tuple(q_in_ref.shape), "wing", tuple(w_in_state.shape),
+          tuple(w_ref.shape))
+    if args.only_prep:
+        return
 
     # ------------------------------------------------------------------ single steps
     steps = {}

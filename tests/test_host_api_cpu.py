@@ -121,3 +121,27 @@ def test_physical_constants_match_reference_config():
     assert abs(w[4] + 0.00105) < 1e-9 and abs(w[40] - 0.16534698176788384) < 1e-7
     c = P.cartpole_phys()
     assert list(c[:5]) == [1.0, np.float32(0.1), 0.5, 30.0, 0.5]
+
+
+def test_dataset_layouts_match_reference_prepare_data():
+    """QuadDataset / WingDataset.prepare_data mirrors against the reference's own prepare_data output
+    (tests/golden/prep_data.npz, produced by oracle/make_golden.py from the unmodified reference)"""
+    from neural_control.dataset import QuadDataset, WingDataset, CartpoleDataset
+    g = load_golden("prep_data.npz")
+    q = QuadDataset(g["quad_raw_states"], g["quad_raw_refs"])
+    for mine, key in ((q.normed_states, "quad_in_state"), (q.states, "quad_states"), (q.in_ref_states, "quad_in_ref"),
+                      (q.ref_states, "quad_ref")):
+        np.testing.assert_allclose(mine.numpy(), g[key], rtol=0, atol=2e-6)
+    a, b, c, d = q[2]
+    assert a.shape == (15,) and b.shape == (12,) and c.shape == (10, 9) and d.shape == (10, 9) and len(q) == 6
+    w = WingDataset(g["wing_raw_states"], g["wing_targets"], mean=g["wing_mean"], std=g["wing_std"],
+                    delta_t=float(g["wing_dt"]), horizon=int(g["wing_h"]))
+    for mine, key in ((w.normed_states, "wing_in_state"), (w.states, "wing_states"), (w.in_ref_states, "wing_in_ref"),
+                      (w.ref_states, "wing_ref")):
+        np.testing.assert_allclose(mine.numpy(), g[key], rtol=0, atol=3e-6)
+    # single-sample path + self-play replacement keep the layouts
+    one = q.get_and_add_eval_data(g["quad_raw_states"][0], g["quad_raw_refs"][0])
+    np.testing.assert_allclose(one[0].numpy(), g["quad_in_state"][:1], atol=2e-6)
+    c = CartpoleDataset(np.random.RandomState(0).randn(5, 4))
+    s, l = c[1]
+    assert torch.equal(s, l) and len(c) == 5
