@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# Runs every variant of tcgen05_gemm in its own process (a rejected descriptor poisons the CUDA context)
+# and writes one JSON line per run to gpurun_out/tcgen05_gemm.jsonl. Usage on the GPU box:
+#   gpurun --timeout 300 -- 'bash tools/micro/run_tcgen05.sh'
+set -u
+cd "$(dirname "$0")"
+bin=./tcgen05_gemm
+if [ ! -x "$bin" ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tcgen05_gemm tcgen05_gemm.cu || exit 1
+fi
+out=../../gpurun_out/tcgen05_gemm.jsonl
+mkdir -p ../../gpurun_out
+: > "$out"
+run() { timeout 60 "$bin" "$@" | tee -a "$out"; echo "# exit=$? args=$*" | tee -a "$out"; }
+for v in 0 1 2 3 4; do
+  run $v 128 64 64 64 0
+done
+# encoding fall-backs: LBO/SBO swapped
+for v in 1 2 3; do run $v 128 64 64 64 1; done
+# shapes the policy layers need: wider N (two layers' worth), K = 32, the M = 64 accumulator lane mapping
+run 1 128 128 64 64 0
+run 1 128 256 64 64 0
+run 1 128 64 32 64 0
+run 1 128 64 128 64 0
+run 1 64 64 64 64 0
+run 3 64 64 128 64 0
+run 4 128 256 64 64 0
