@@ -25,3 +25,10 @@ run 1 128 64 128 64 0
 run 1 64 64 64 64 0
 run 3 64 64 128 64 0
 run 4 128 256 64 64 0
+# layer chain through TMEM (TS form): one and two tiles in flight
+if [ ! -x ./tcgen05_mlp ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tcgen05_mlp tcgen05_mlp.cu || exit 1
+fi
+for args in "64 1 4" "64 2 4" "64 2 3" "7 2 4"; do
+  timeout 60 ./tcgen05_mlp $args | tee -a "$out"; echo "# exit=$? mlp args=$args" | tee -a "$out"
+done
