@@ -13,6 +13,8 @@ One "step" = one train iteration over the whole (per-GPU) batch.  Device-timed w
 step on the launching stream; the L2 is flushed (256 MiB write) between timed steps, outside the timed region.
 """
 import argparse
+import datetime
+import faulthandler
 import json
 import os
 import subprocess
@@ -215,6 +217,19 @@ def run_reference(args, w, rank):
     case = make_case(w, n, 1234, "cpu")
     params = default_init(w["system"], w["h"], mode=w.get("mode", "concurrent"))
     step = cpu_reference_step(w, n, params, case, threads)
+    step()
+    # bounded sample: shrink the per-step batch until warm-up + K steps fit the budget (throughput is per drone-step,
+    # so a smaller sample measures the same metric)
+    budget_s = float(os.environ.get("APG_BENCH_REFERENCE_BUDGET_S", "240"))
+    while n > 1024:
+        t0 = time.perf_counter()
+        step()
+        if (time.perf_counter() - t0) * (args.steps + args.warmup) <= budget_s:
+            break
+        n //= 2
+        case = make_case(w, n, 1234, "cpu")
+        step = cpu_reference_step(w, n, params, case, threads)
+        step()
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -247,6 +262,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
+    # hard wall-clock bound for the whole process: dump the Python stacks and exit instead of hanging a GPU box
+    faulthandler.dump_traceback_later(int(os.environ.get("APG_BENCH_WATCHDOG_S", "1500")), exit=True)
     w = dict(WORKLOADS[args.workload])
     if args.n:
         w["n"] = args.n
@@ -267,7 +284,8 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # a mismatched or stuck collective must end the run (NCCL watchdog abort), not hang the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     n, h = w["n"], w["h"]
     case = make_case(w, n, 1234 + rank, dev)
