@@ -12,7 +12,7 @@ out=../../gpurun_out/tcgen05_gemm.jsonl
 mkdir -p ../../gpurun_out
 : > "$out"
 run() { timeout 60 "$bin" "$@" | tee -a "$out"; echo "# exit=$? args=$*" | tee -a "$out"; }
-for v in 0 1 2 3 4; do
+for v in 0 1 2 3 4 5 6; do
   run $v 128 64 64 64 0
 done
 # encoding fall-backs: LBO/SBO swapped

@@ -18,6 +18,11 @@
 //   variant 2: SS, A/B K-major, 128B swizzle, 3xTF32      (what a TMA box load of row-major fp32 produces)
 //   variant 3: SS, A/B MN-major, 128B swizzle, 3xTF32     (the dW = dY^T X shape: K runs over the drones)
 //   variant 4: TS, A in TMEM (tcgen05.st), B K-major no swizzle, 3xTF32
+//   variant 5: SS, K-major no swizzle, 1xTF32 on RAW fp32 images (low 13 bits not cleared): does the tensor core
+//              truncate or round fp32 -> tf32?  (compare the two "err_vs_*_inputs" fields)
+//   variant 6: SS, K-major no swizzle, "2.5-term" split with a 16-bit correction: tf32(A_raw, B_raw) + tf32(A_lo, B_raw)
+//              + bf16(A_bf16, B_lo_bf16), all three accumulating into the same fp32 TMEM tile (mixed kinds);
+//              the B side then costs 4 + 2 bytes per weight instead of 4 + 4
 // Each variant runs in its own process (a bad descriptor kills the context); tools/micro/run_tcgen05.sh loops.
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +43,8 @@ struct Params {
   int a_in_tmem;   // TS form
   int reps;        // timing repetitions of the whole K loop
   int swap;        // swap the LBO and SBO fields (debug aid)
+  int raw;         // hi images hold the unmasked fp32 value
+  int mixed;       // variant 6
 };
 
 // byte offset of element (r, k) of an R x K operand inside its shared-memory image
@@ -90,6 +97,27 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(M >> 4) << 24;
   return d;
+}
+
+// kind::f16 with bf16 operands, fp32 accumulate; K = 16 per instruction
+__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 16-bit K-major no-swizzle image: core matrix 8 rows x 16 B (8 elements)
+__host__ __device__ inline uint32_t lay_off16(int r, int k, int K) {
+  return (uint32_t)((r >> 3) * ((K >> 3) * 128) + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+__device__ inline void mma_ss_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ inline uint16_t f2bf(float x) {  // round to nearest even
+  uint32_t u = __float_as_uint(x);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
 }
 
 __device__ inline void mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
@@ -152,6 +180,8 @@ __global__ void __launch_bounds__(128, 1)
   unsigned char* sAlo = sAhi + a_bytes;
   unsigned char* sBhi = sAlo + a_bytes;
   unsigned char* sBlo = sBhi + b_bytes;
+  unsigned char* sA16 = sBlo + b_bytes;            // variant 6: bf16(A), 128 x K
+  unsigned char* sB16 = sA16 + 128 * p.K * 2;      // variant 6: bf16(B - trunc(B)), RB x K
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_tmem;
 
@@ -159,23 +189,26 @@ __global__ void __launch_bounds__(128, 1)
   const uint32_t bar = smem_u32(&s_bar);
 
   // zero then fill the operand images (generic proxy), hi/lo split on the fly
-  for (int i = tid; i < (2 * a_bytes + 2 * b_bytes) / 4; i += blockDim.x) ((uint32_t*)base)[i] = 0u;
+  const int img_bytes = 2 * a_bytes + 2 * b_bytes + (p.mixed ? (128 + (p.N + 31) / 32 * 32) * p.K * 2 : 0);
+  for (int i = tid; i < img_bytes / 4; i += blockDim.x) ((uint32_t*)base)[i] = 0u;
   __syncthreads();
   for (int i = tid; i < p.M * p.K; i += blockDim.x) {
     const int r = i / p.K, k = i % p.K;
     const float x = A[i];
     const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
     const uint32_t o = lay_off(p.layA, r, k, 128, p.K);
-    *(float*)(sAhi + o) = hi;
+    *(float*)(sAhi + o) = p.raw ? x : hi;
     *(float*)(sAlo + o) = x - hi;
+    if (p.mixed) *(uint16_t*)(sA16 + lay_off16(r, k, p.K)) = f2bf(x);
   }
   for (int i = tid; i < p.N * p.K; i += blockDim.x) {
     const int r = i / p.K, k = i % p.K;
     const float x = B[i];
     const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
     const uint32_t o = lay_off(p.layB, r, k, (p.N + 31) / 32 * 32, p.K);
-    *(float*)(sBhi + o) = hi;
+    *(float*)(sBhi + o) = p.raw ? x : hi;
     *(float*)(sBlo + o) = x - hi;
+    if (p.mixed) *(uint16_t*)(sB16 + lay_off16(r, k, p.K)) = f2bf(x - hi);
   }
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -224,6 +257,21 @@ __global__ void __launch_bounds__(128, 1)
   long long t_loop = 0, t_one = 0, t_ld = 0, timeouts = 0;
 
   auto issue_kloop = [&](bool first_clears) {
+    if (p.mixed) {
+      const uint32_t idesc16 = make_idesc_bf16(p.M, p.N);
+      for (int ks = 0; ks < p.K / 16; ++ks) {  // 16-bit correction term first (smallest magnitude)
+        const uint32_t sbo16 = (p.K >> 3) * 128;
+        mma_ss_f16(tmem_d, make_desc(smem_u32(sA16) + ks * 256, 128, sbo16, 0, p.swap),
+                   make_desc(smem_u32(sB16) + ks * 256, 128, sbo16, 0, p.swap), idesc16,
+                   (ks > 0 || !first_clears) ? 1u : 0u);
+      }
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t bh = operand_desc(p.layB, smem_u32(sBhi), ks, RB, p.K, p.swap);
+        mma_ss(tmem_d, operand_desc(p.layA, smem_u32(sAlo), ks, 128, p.K, p.swap), bh, idesc, 1u);
+        mma_ss(tmem_d, operand_desc(p.layA, smem_u32(sAhi), ks, 128, p.K, p.swap), bh, idesc, 1u);
+      }
+      return;
+    }
     for (int ks = 0; ks < ksteps; ++ks) {
       const uint64_t bh = operand_desc(p.layB, smem_u32(sBhi), ks, RB, p.K, p.swap);
       const uint64_t bl = operand_desc(p.layB, smem_u32(sBlo), ks, RB, p.K, p.swap);
@@ -321,7 +369,9 @@ int main(int argc, char** argv) {
   p.K = argc > 4 ? atoi(argv[4]) : 64;
   p.reps = argc > 5 ? atoi(argv[5]) : 64;
   p.swap = argc > 6 ? atoi(argv[6]) : 0;
-  p.split = p.variant == 0 ? 1 : 3;
+  p.split = (p.variant == 0 || p.variant == 5) ? 1 : 3;
+  p.raw = (p.variant == 5 || p.variant == 6);
+  p.mixed = p.variant == 6;
   p.a_in_tmem = p.variant == 4;
   p.layA = p.layB = LAY_K_NONE;
   if (p.variant == 2) p.layA = p.layB = LAY_K_SW128;
@@ -331,7 +381,7 @@ int main(int argc, char** argv) {
     return 1;
   }
   const int RB = (p.N + 31) / 32 * 32;
-  const size_t smem = 1024 + 2 * (size_t)128 * p.K * 4 + 2 * (size_t)RB * p.K * 4;
+  const size_t smem = 1024 + 2 * (size_t)128 * p.K * 4 + 2 * (size_t)RB * p.K * 4 + (size_t)(128 + RB) * p.K * 2;
   if (smem > 227 * 1024) { printf("operands do not fit in shared memory (%zu B)\n", smem); return 1; }
 
   std::vector<float> hA((size_t)p.M * p.K), hB((size_t)p.N * p.K), hD((size_t)128 * p.N, 0.f);
@@ -355,47 +405,54 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(hT, dT, sizeof(hT), cudaMemcpyDeviceToHost));
 
   // CPU references: exact fp64 product, and the product of the tf32-truncated operands
-  std::vector<double> ref((size_t)p.M * p.N), ref_t((size_t)p.M * p.N);
+  std::vector<double> ref((size_t)p.M * p.N), ref_t((size_t)p.M * p.N), ref_r((size_t)p.M * p.N);
+  auto rne = [](float x) {
+    uint32_t u; memcpy(&u, &x, 4); u += 0xfffu + ((u >> 13) & 1u); u &= 0xffffe000u; float y; memcpy(&y, &u, 4); return y;
+  };
   auto trunc = [](float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; float y; memcpy(&y, &u, 4); return y; };
   for (int m = 0; m < p.M; ++m)
     for (int n = 0; n < p.N; ++n) {
-      double a = 0, b = 0;
+      double a = 0, b = 0, c = 0;
       for (int k = 0; k < p.K; ++k) {
         a += (double)hA[m * p.K + k] * (double)hB[n * p.K + k];
         b += (double)trunc(hA[m * p.K + k]) * (double)trunc(hB[n * p.K + k]);
+        c += (double)rne(hA[m * p.K + k]) * (double)rne(hB[n * p.K + k]);
       }
       ref[(size_t)m * p.N + n] = a;
       ref_t[(size_t)m * p.N + n] = b;
+      ref_r[(size_t)m * p.N + n] = c;
     }
   // candidate accumulator lane mappings (row m -> TMEM lane)
   struct Map { const char* name; int (*f)(int); };
   const Map maps[] = {{"lane=m", [](int m) { return m; }},
                       {"lane=(m/16)*32+m%16", [](int m) { return (m / 16) * 32 + m % 16; }},
                       {"lane=(m/32)*64+m%32", [](int m) { return (m / 32) * 64 + m % 32; }}};
-  double best = 1e30; const char* best_name = "?"; double best_t = 0;
+  double best = 1e30; const char* best_name = "?"; double best_t = 0, best_r = 0;
   for (const Map& mp : maps) {
     if (p.M == 128 && mp.f(127) != 127) continue;
-    double e = 0, et = 0;
+    double e = 0, et = 0, er = 0;
     for (int m = 0; m < p.M; ++m)
       for (int n = 0; n < p.N; ++n) {
         const double d = hD[(size_t)mp.f(m) * p.N + n];
         e = std::max(e, std::fabs(d - ref[(size_t)m * p.N + n]));
         et = std::max(et, std::fabs(d - ref_t[(size_t)m * p.N + n]));
+        er = std::max(er, std::fabs(d - ref_r[(size_t)m * p.N + n]));
       }
     if (!(e >= 0)) e = 1e30;  // NaN
-    if (e < best) { best = e; best_name = mp.name; best_t = et; }
+    if (e < best) { best = e; best_name = mp.name; best_t = et; best_r = er; }
   }
-  const int mmas = (p.K / 8) * p.split;
+  const int mmas = p.mixed ? (p.K / 8) * 2 + p.K / 16 : (p.K / 8) * p.split;
   const double cyc_per_mma = (double)hT[0] / ((double)mmas * p.reps);
   const double mac_per_clk = (double)p.M * p.N * 8 / cyc_per_mma;
   // expectation: |err| ~ K * 2^-11 for 1xTF32, ~ K * 2^-21 for 3xTF32 (inputs in [-1,1))
   const double tol = (p.split == 3 ? 4e-6 : 4e-3) * p.K / 64.0 * 4;
   const bool ok = best < tol && hT[3] == 0;
   printf("{\"variant\": %d, \"M\": %d, \"N\": %d, \"K\": %d, \"split\": %d, \"a_in_tmem\": %d, \"swap\": %d, "
-         "\"max_abs_err_vs_fp64\": %.3e, \"max_abs_err_vs_truncated_inputs\": %.3e, \"lane_map\": \"%s\", "
+         "\"max_abs_err_vs_fp64\": %.3e, \"max_abs_err_vs_truncated_inputs\": %.3e, "
+         "\"max_abs_err_vs_rne_inputs\": %.3e, \"lane_map\": \"%s\", "
          "\"cycles_per_mma\": %.1f, \"mac_per_clk_sm\": %.0f, \"single_mma_roundtrip_cycles\": %lld, "
          "\"tile_tmem_ld_cycles\": %lld, \"mbarrier_timeouts\": %lld, \"ok\": %s}\n",
-         p.variant, p.M, p.N, p.K, p.split, p.a_in_tmem, p.swap, best, best_t, best_name, cyc_per_mma, mac_per_clk,
+         p.variant, p.M, p.N, p.K, p.split, p.a_in_tmem, p.swap, best, best_t, best_r, best_name, cyc_per_mma, mac_per_clk,
          hT[1], hT[2], hT[3], ok ? "true" : "false");
   return ok ? 0 : 3;
 }
