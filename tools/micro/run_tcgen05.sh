@@ -32,3 +32,10 @@ fi
 for args in "64 1 4" "64 2 4" "64 2 3" "7 2 4"; do
   timeout 60 ./tcgen05_mlp $args | tee -a "$out"; echo "# exit=$? mlp args=$args" | tee -a "$out"
 done
+# CTA-pair (cta_group::2) GEMM: each CTA holds half of B
+if [ ! -x ./tcgen05_gemm2sm ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tcgen05_gemm2sm tcgen05_gemm2sm.cu || exit 1
+fi
+for args in "64 64 64" "128 64 64" "256 64 64" "64 32 64"; do
+  timeout 60 ./tcgen05_gemm2sm $args | tee -a "$out"; echo "# exit=$? gemm2sm args=$args" | tee -a "$out"
+done
