@@ -39,3 +39,10 @@ fi
 for args in "64 64 64" "128 64 64" "256 64 64" "64 32 64"; do
   timeout 60 ./tcgen05_gemm2sm $args | tee -a "$out"; echo "# exit=$? gemm2sm args=$args" | tee -a "$out"
 done
+# full policy forward (quad concurrent net) on tcgen05: small ragged case first, then the bench size
+if [ ! -x ./tcgen05_policy ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tcgen05_policy tcgen05_policy.cu || exit 1
+fi
+for args in "1000 3 2" "65536 20 0"; do
+  timeout 120 ./tcgen05_policy $args | tee -a "$out"; echo "# exit=$? policy args=$args" | tee -a "$out"
+done
