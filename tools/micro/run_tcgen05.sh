@@ -46,3 +46,10 @@ fi
 for args in "1000 3 2" "65536 20 0"; do
   timeout 120 ./tcgen05_policy $args | tee -a "$out"; echo "# exit=$? policy args=$args" | tee -a "$out"
 done
+# policy backward (dX chain through TMEM with TMA-streamed W^T, dW = dZ^T X from MN-major smem images)
+if [ ! -x ./tcgen05_policy_bwd ]; then
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tcgen05_policy_bwd tcgen05_policy_bwd.cu || exit 1
+fi
+for args in "300 1 2" "8192 5 0" "65536 5 0"; do
+  timeout 180 ./tcgen05_policy_bwd $args | tee -a "$out"; echo "# exit=$? policy_bwd args=$args" | tee -a "$out"
+done
