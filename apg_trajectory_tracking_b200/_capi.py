@@ -34,6 +34,13 @@ EXPORTS = {
                                                  ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "apg_quad_features": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "apg_quad_features_adjoint": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "apg_prepare_quad": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int] + [c_float_p] * 4 +
+                         [ctypes.c_void_p]),
+    "apg_prepare_wing": (ctypes.c_int, [c_float_p] * 4 + [ctypes.c_float, ctypes.c_int, ctypes.c_int] +
+                         [c_float_p] * 4 + [ctypes.c_void_p]),
+    "apg_sample_windows": (ctypes.c_int, [c_float_p] + [ctypes.c_int] * 5 + [c_float_p, c_float_p, ctypes.c_void_p]),
+    "apg_poly_reference": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                          c_float_p, ctypes.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,48 @@
+// extern "C" entry points of the data-format kernels (include/apg_b200.h, "input side" section).
+#include <stdint.h>
+
+#include "../../include/apg_b200.h"
+#include "kernels.h"
+
+using namespace apg;
+
+namespace {
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+}  // namespace
+
+#define APG_API extern "C" __attribute__((visibility("default")))
+
+APG_API int apg_prepare_quad(const float* states, const float* ref_states, int n, int ref_rows, float* in_state,
+                             float* cur_out, float* in_ref, float* ref_out, void* stream) {
+  if (!states || n < 0 || ref_rows < 0) return APG_ERR_BAD_CONFIG;
+  if ((in_ref || ref_out) && !ref_states) return APG_ERR_BAD_CONFIG;
+  if (!al16(states) || !al16(ref_states) || !al16(in_state) || !al16(cur_out) || !al16(in_ref) || !al16(ref_out))
+    return APG_ERR_ALIGNMENT;
+  return (int)launch_prepare_quad(states, ref_states, n, ref_rows, in_state, cur_out, in_ref, ref_out,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+APG_API int apg_prepare_wing(const float* states, const float* targets, const float* mean_host, const float* std_host,
+                             float dt, int horizon, int n, float* in_state, float* cur_out, float* in_ref,
+                             float* ref_out, void* stream) {
+  if (!states || !targets || !mean_host || !std_host || n < 0 || horizon <= 0) return APG_ERR_BAD_CONFIG;
+  if (!al16(states) || !al16(in_state) || !al16(cur_out) || !al16(ref_out)) return APG_ERR_ALIGNMENT;
+  return (int)launch_prepare_wing(states, targets, mean_host, std_host, dt, horizon, n, in_state, cur_out, in_ref,
+                                  ref_out, static_cast<cudaStream_t>(stream));
+}
+
+APG_API int apg_poly_reference(const float* coef, int n, int rows, float t_first, float dt, float* ref_out,
+                               void* stream) {
+  if (!coef || !ref_out || n < 0 || rows < 0) return APG_ERR_BAD_CONFIG;
+  return (int)launch_poly_reference(coef, n, rows, t_first, dt, ref_out, static_cast<cudaStream_t>(stream));
+}
+
+APG_API int apg_sample_windows(const float* traj, int traj_rows, int traj_cols, int ref_rows, int stride, int n,
+                               float* states, float* ref_states, void* stream) {
+  if (!traj || !states || !ref_states || n < 0 || ref_rows < 0 || stride <= 0 || traj_cols < 9)
+    return APG_ERR_BAD_CONFIG;
+  // the last sample reads rows (n-1)*stride .. (n-1)*stride + ref_rows
+  if (n > 0 && (long long)(n - 1) * stride + ref_rows > (long long)traj_rows - 1) return APG_ERR_BAD_CONFIG;
+  return (int)launch_sample_windows(traj, traj_cols, ref_rows, stride, n, states, ref_states,
+                                    static_cast<cudaStream_t>(stream));
+}

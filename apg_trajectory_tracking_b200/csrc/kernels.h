@@ -31,4 +31,15 @@ cudaError_t launch_step_adj(int system, const PhysConsts& pc, const float* s, co
 cudaError_t launch_features(const float* s, int n, float* f, cudaStream_t st);
 cudaError_t launch_features_adj(const float* s, const float* gf, int n, float* gs, cudaStream_t st);
 
+// data formats on the input side (prep_kernels.cu)
+cudaError_t launch_prepare_quad(const float* states, const float* ref, int n, int L, float* in_state, float* cur_out,
+                                float* in_ref, float* ref_out, cudaStream_t st);
+cudaError_t launch_prepare_wing(const float* states, const float* targets, const float* mean_host,
+                                const float* std_host, float dt, int h, int n, float* in_state, float* cur_out,
+                                float* in_ref, float* ref_out, cudaStream_t st);
+cudaError_t launch_poly_reference(const float* coef, int n, int L, float t_first, float dt, float* out,
+                                  cudaStream_t st);
+cudaError_t launch_sample_windows(const float* traj, int W, int L, int stride, int n, float* states, float* refs,
+                                  cudaStream_t st);
+
 }  // namespace apg

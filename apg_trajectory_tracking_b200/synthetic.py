@@ -62,7 +62,7 @@ def quad_case(n, ref_rows, dt=0.1, seed=1234, device="cpu"):
 
 
 def wing_case(n, horizon, dt=0.05, seed=1234, device="cpu"):
-    """returns dict(cur (n,12), ref (n,h,3), in_ref (n,3), in_state (n,9))."""
+    """returns dict(cur (n,12), ref (n,h,3), in_ref (n,3), in_state (n,9), target (n,3) = the raw reference sample)."""
     g = torch.Generator().manual_seed(seed)
     cur = torch.zeros(n, 12)
     cur[:, 3] = 11.5 + _u(g, n, lo=-0.5, hi=0.5)
@@ -76,7 +76,7 @@ def wing_case(n, horizon, dt=0.05, seed=1234, device="cpu"):
     ref = cur[:, None, :3] + unit[:, None, :] * (12 * dt) * steps
     in_ref = ref[:, -1] - cur[:, :3]
     in_state = ((cur - WING_MEAN) / WING_STD)[:, 3:]
-    out = dict(cur=cur, ref=ref, in_ref=in_ref, in_state=in_state)
+    out = dict(cur=cur, ref=ref, in_ref=in_ref, in_state=in_state, target=target)
     return {k: v.contiguous().to(device) for k, v in out.items()}
 
 

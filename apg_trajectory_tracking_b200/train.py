@@ -12,7 +12,19 @@ drone_loss.py:22-33, so the summed gradient equals the single-device large-batch
 """
 import torch
 
-from . import rollout as R
+from . import _capi, prepare as PR, rollout as R, synthetic as _syn
+
+
+def chunk_bounds(n, chunk, align=64):
+    """[(a, b)] contiguous drone ranges of at most `chunk` rows covering [0, n); every start is a multiple of `align`
+    (the 64-drone tile, which also keeps every per-chunk pointer 16-byte aligned)."""
+    n, chunk = int(n), int(chunk)
+    if n <= 0:
+        return []
+    if chunk <= 0 or chunk >= n:
+        return [(0, n)]
+    chunk = max(align, (chunk // align) * align)
+    return [(a, min(a + chunk, n)) for a in range(0, n, chunk)]
 
 
 class FusedTrainStep:
@@ -59,6 +71,121 @@ class FusedTrainStep:
         self.buf.mul_(self.momentum).add_(grad)
         self.flat.add_(self.buf, alpha=-self.lr)
         return loss
+
+    # -----------------------------------------------------------------------------------------------------------
+    # host batches: raw samples in (pinned) host memory -> chunked H2D on a copy stream, overlapped with the
+    # kernels of the previous chunk; the policy inputs are derived on the device (prepare.py)
+    # -----------------------------------------------------------------------------------------------------------
+    def default_chunk(self):
+        """drones per chunk of step_host: two waves of 64-drone tiles over the SMs (each persistent CTA gets two
+        tiles, so its GEMM / dynamics warps overlap)"""
+        return 2 * 64 * max(1, _capi.lib().apg_sm_count())
+
+    def _host_state(self, n):
+        st = getattr(self, "_hs", None)
+        if st is not None and st["n"] == n:
+            return st
+        spec, dev = self.runner.spec, self.device
+        rows = spec.horizon if spec.mode == "concurrent" else 2 * spec.horizon
+        st = {"n": n, "copy_stream": torch.cuda.Stream(device=dev), "done": None, "runners": {},
+              "cur": torch.empty(n, spec.state_dim, device=dev), "grad_tmp": torch.zeros_like(self.grad),
+              "loss": torch.zeros(1, device=dev)}
+        if spec.system == "quad":
+            st["ref"] = torch.empty(n, rows, 9, device=dev)
+            st["in_ref"] = torch.empty(n, rows, 9, device=dev)
+            st["in_state"] = torch.empty(n, 15, device=dev) if spec.mode == "concurrent" else None
+            st["h0c0"] = torch.empty(2, n, 8, device=dev) if spec.mode.lower() == "lstm" else None
+        elif spec.system == "wing":
+            st["target"] = torch.empty(n, 3, device=dev)
+            st["ref"] = torch.empty(n, spec.horizon, 3, device=dev)
+            st["in_ref"] = torch.empty(n, 3, device=dev)
+            st["in_state"] = torch.empty(n, 9, device=dev)
+        self._hs = st
+        return st
+
+    def _chunk_runner(self, st, size):
+        if size == self.runner.n:
+            return self.runner
+        if size not in st["runners"]:
+            st["runners"][size] = R.Rollout(self.runner.spec, size, self.device)
+        return st["runners"][size]
+
+    def step_host(self, cur, ref=None, h0c0=None, target=None, norm=None, chunk=None):
+        """One full train iteration from RAW host samples: ``value_and_grad_host`` + the SGD(momentum) update.
+        Returns the (local-shard) loss as a 1-element device tensor."""
+        loss, grad = self.value_and_grad_host(cur, ref, h0c0, target, norm, chunk)
+        self.buf.mul_(self.momentum).add_(grad)
+        self.flat.add_(self.buf, alpha=-self.lr)
+        return loss
+
+    def value_and_grad_host(self, cur, ref=None, h0c0=None, target=None, norm=None, chunk=None, allreduce=True):
+        """Loss and flat gradient from RAW host samples (pinned memory for asynchronous copies).
+
+        quad: ``cur`` (N,12), ``ref`` (N,L,9) raw reference rows (L = h concurrent, 2h recurrent) [+ ``h0c0`` (2,N,8)];
+        wing: ``cur`` (N,12), ``target`` (N,3), ``norm`` = (mean, std) of WingDataset (default: its fixed statistics);
+        cartpole: ``cur`` (N,4).  The batch is cut into chunks of ``chunk`` drones (default ``default_chunk()``); the
+        H2D copy of chunk c+1 runs on a copy stream while chunk c goes through prepare -> forward -> adjoint on the
+        current stream; loss and gradient are summed over the chunks (the loss is a sum over drones), then the
+        gradient is all-reduced as in ``value_and_grad``.  Returns (loss 1-element device tensor, flat gradient)."""
+        spec = self.runner.spec
+        n = int(cur.shape[0])
+        st = self._host_state(n)
+        compute = torch.cuda.current_stream(self.device)
+        copy = st["copy_stream"]
+        if st["done"] is not None:
+            copy.wait_event(st["done"])          # the previous step's kernels still read the staging buffers
+        bounds = chunk_bounds(n, chunk if chunk is not None else self.default_chunk())
+        if spec.system == "wing":
+            mean, std = norm if norm is not None else (_syn.WING_MEAN, _syn.WING_STD)
+        first = True
+        for a, b in bounds:
+            with torch.cuda.stream(copy):
+                st["cur"][a:b].copy_(cur[a:b], non_blocking=True)
+                if spec.system == "quad":
+                    st["ref"][a:b].copy_(ref[a:b], non_blocking=True)
+                    if st["h0c0"] is not None:
+                        st["h0c0"][:, a:b].copy_(h0c0[:, a:b], non_blocking=True)
+                elif spec.system == "wing":
+                    st["target"][a:b].copy_(target[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            compute.wait_event(ev)
+            c_cur = st["cur"][a:b]
+            hc = None
+            if spec.system == "quad":
+                want = ("in_state", "cur", "in_ref", "ref") if st["in_state"] is not None else ("cur", "in_ref", "ref")
+                outs = {"cur": c_cur, "ref": st["ref"][a:b], "in_ref": st["in_ref"][a:b]}
+                if st["in_state"] is not None:
+                    outs["in_state"] = st["in_state"][a:b]
+                PR.prepare_quad(c_cur, st["ref"][a:b], want=want, out=outs)
+                c_ins, c_inr, c_ref = outs.get("in_state"), outs["in_ref"], outs["ref"]
+                if st["h0c0"] is not None:
+                    hc = st["h0c0"][:, a:b].contiguous() if len(bounds) > 1 else st["h0c0"]
+            elif spec.system == "wing":
+                outs = {"cur": c_cur, "ref": st["ref"][a:b], "in_ref": st["in_ref"][a:b],
+                        "in_state": st["in_state"][a:b]}
+                PR.prepare_wing(c_cur, st["target"][a:b], mean, std, spec.dt, spec.horizon, out=outs)
+                c_ins, c_inr, c_ref = outs["in_state"], outs["in_ref"], outs["ref"]
+            else:
+                c_ins, c_inr, c_ref = c_cur, None, None
+            runner = self._chunk_runner(st, b - a)
+            loss, _, _ = runner.forward(self.flat, c_ins, c_cur, c_inr, c_ref, hc)
+            if first:
+                runner.backward(1.0, out=self.grad)
+                st["loss"].copy_(loss)
+                first = False
+            else:
+                runner.backward(1.0, out=st["grad_tmp"])
+                self.grad.add_(st["grad_tmp"])
+                st["loss"].add_(loss)
+        if self.distributed and allreduce:
+            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        st["done"] = torch.cuda.Event()
+        st["done"].record(compute)
+        # launches of this package's kernels: per chunk the rollout's 5 + the prepare kernels (quad / wing: 2)
+        self.host_launches_per_step = len(bounds) * (self.kernel_launches_per_step +
+                                                     (0 if spec.system == "cartpole" else 2))
+        return st["loss"], self.grad
 
     def parameters(self):
         """current parameters as views shaped like the originals"""
@@ -119,10 +246,16 @@ class ModuleRollout:
         return None if x is None else x.to(self.device, non_blocking=True)
 
     def loss_and_grad(self, in_state, cur, in_ref=None, ref=None, h0c0=None):
+        """``in_ref=None`` for a quadrotor batch: the policy inputs are derived from the raw ``(cur, ref)`` samples on
+        the device (QuadDataset.prepare_data as a kernel, prepare.py) -- only those two tensors cross PCIe."""
         cur = self._dev(cur)
         runner = self.runner(cur.shape[0])
-        loss, _ = runner.value_and_grad(self.flat, self._dev(in_state), cur, self._dev(in_ref), self._dev(ref),
-                                        self._dev(h0c0), out=self.flat_grad)
+        in_state, in_ref, ref = self._dev(in_state), self._dev(in_ref), self._dev(ref)
+        if self.spec.system == "quad" and in_ref is None and ref is not None:
+            want = ("in_state", "cur", "in_ref", "ref") if self.spec.mode == "concurrent" else ("cur", "in_ref", "ref")
+            d = PR.prepare_quad(cur, ref, want=want)
+            in_state, cur, in_ref, ref = d.get("in_state"), d["cur"], d["in_ref"], d["ref"]
+        loss, _ = runner.value_and_grad(self.flat, in_state, cur, in_ref, ref, self._dev(h0c0), out=self.flat_grad)
         if torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size(self.pg) > 1:
             torch.distributed.all_reduce(self.flat_grad, group=self.pg)

@@ -87,6 +87,29 @@ int apg_dynamics_step_adjoint(int system, const float* phys, const float* state,
 int apg_quad_features(const float* state, int n, float* feat, void* stream);
 int apg_quad_features_adjoint(const float* state, const float* grad_feat, int n, float* grad_state, void* stream);
 
+/* ---- input side of the path: the reference's dataset layouts produced on the device, so
+ * that a train step only has to be handed the RAW samples.  Output pointers may be NULL (that tensor is skipped).
+ *
+ * apg_prepare_quad   neural_control/dataset.py:155-204 (QuadDataset.prepare_data): states [n][12], ref_states
+ *                    [n][ref_rows][9] (pos, euler, vel) ->  in_state [n][15], cur_out [n][12] (position zeroed),
+ *                    in_ref [n][ref_rows][9] (rel. pos, vel, vel - drone vel), ref_out [n][ref_rows][9] (rel. pos).
+ *                    cur_out may alias states, ref_out may alias ref_states (the reference works in place too).
+ * apg_prepare_wing   neural_control/dataset.py:309-350 (WingDataset.prepare_data): states [n][12], targets [n][3],
+ *                    mean/std 12 HOST floats -> in_state [n][9], cur_out [n][12], in_ref [n][3], ref_out [n][h][3].
+ * apg_sample_windows neural_control/environments/drone_env.py:232-269 (full_state_training_data): window gather
+ *                    from one trajectory table [traj_rows][traj_cols >= 9]: states[i] = [traj[i*stride][0:9],0,0,0],
+ *                    ref_states[i][k] = traj[i*stride + k + 1][0:9].
+ * apg_poly_reference synthetic polynomial references: coef [n][3][6] (c0..c5 per axis) ->
+ *                    ref_out [n][rows][9] = [p(t), 0 0 0, p'(t)], t = t_first + k*dt. */
+int apg_prepare_quad(const float* states, const float* ref_states, int n, int ref_rows, float* in_state,
+                     float* cur_out, float* in_ref, float* ref_out, void* stream);
+int apg_prepare_wing(const float* states, const float* targets, const float* mean_host, const float* std_host,
+                     float dt, int horizon, int n, float* in_state, float* cur_out, float* in_ref, float* ref_out,
+                     void* stream);
+int apg_sample_windows(const float* traj, int traj_rows, int traj_cols, int ref_rows, int stride, int n,
+                       float* states, float* ref_states, void* stream);
+int apg_poly_reference(const float* coef, int n, int rows, float t_first, float dt, float* ref_out, void* stream);
+
 int apg_sm_count(void);
 int apg_version(void);
 const char* apg_error_string(int code);

@@ -145,3 +145,30 @@ def test_dataset_layouts_match_reference_prepare_data():
     c = CartpoleDataset(np.random.RandomState(0).randn(5, 4))
     s, l = c[1]
     assert torch.equal(s, l) and len(c) == 5
+
+
+def test_chunk_bounds_cover_the_batch_on_tile_boundaries():
+    """host-side logic of FusedTrainStep.step_host: chunks cover [0, n) without overlap, start on 64-drone tiles"""
+    from apg_trajectory_tracking_b200.train import chunk_bounds
+    for n, chunk in [(65536, 18944), (65536, 9472), (1000, 192), (130, 64), (64, 64), (63, 64), (10, 3), (777, 0),
+                     (5, 100000), (200, 100)]:
+        b = chunk_bounds(n, chunk)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(a % 64 == 0 and a < e for a, e in b)
+        if 0 < chunk < n:
+            assert max(e - a for a, e in b) <= max(64, chunk)
+    assert chunk_bounds(0, 64) == []
+
+
+def test_input_side_ops_refuse_cpu_tensors():
+    from apg_trajectory_tracking_b200 import prepare as PR
+    from apg_trajectory_tracking_b200._capi import ApgError
+    with pytest.raises(ApgError):
+        PR.prepare_quad(torch.zeros(4, 12), torch.zeros(4, 10, 9))
+    with pytest.raises(ApgError):
+        PR.prepare_wing(torch.zeros(4, 12), torch.zeros(4, 3), torch.zeros(12), torch.ones(12), 0.05, 10)
+    with pytest.raises(ApgError):
+        PR.sample_windows(torch.zeros(100, 9), 3, 10, 20)
+    with pytest.raises(ApgError):
+        PR.poly_reference(torch.zeros(4, 3, 6), 10, 0.1)

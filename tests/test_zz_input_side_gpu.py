@@ -1,0 +1,175 @@
+"""GPU tests of the input side of the path: the dataset layouts produced on the device and the
+chunked host-batch train step.  The file name sorts last on purpose: these kernels were written after the round's
+GPU budget was spent, so under `pytest -x` they run after every previously verified parity test.
+
+Tolerances (fp32): subtraction-only outputs bit-exact; outputs that go through sin/cos/sqrt/div 2e-6 of scale;
+train steps from raw host samples vs the same steps from prepared device tensors: loss 1e-5 relative, gradient L2
+1e-4 relative (chunk-wise summation order + last-ulp feature differences)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from apg_trajectory_tracking_b200 import prepare as PR, rollout as R, synthetic as SY, train as T
+    from apg_trajectory_tracking_b200.neural_control import dataset as DS
+    return PR, R, SY, T, DS
+
+
+def _close(a, b, tol):
+    a, b = a.detach().cpu().double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max()) <= tol * max(float(b.abs().max()), 1e-30)
+
+
+def test_prepare_quad_golden_and_in_place():
+    PR, *_ = _mods()
+    g = load_golden("prep_data.npz")
+    s = torch.tensor(g["quad_raw_states"], dtype=torch.float32).cuda()
+    r = torch.tensor(g["quad_raw_refs"], dtype=torch.float32).cuda()
+    out = PR.prepare_quad(s, r)
+    assert torch.equal(out["cur"].cpu(), torch.tensor(g["quad_states"]))
+    assert torch.equal(out["ref"].cpu(), torch.tensor(g["quad_ref"]))
+    assert torch.equal(out["in_ref"].cpu(), torch.tensor(g["quad_in_ref"]))
+    assert _close(out["in_state"], g["quad_in_state"], 2e-6)
+    s2, r2 = s.clone(), r.clone()
+    out2 = PR.prepare_quad(s2, r2, in_place=True)
+    assert out2["cur"].data_ptr() == s2.data_ptr() and out2["ref"].data_ptr() == r2.data_ptr()
+    assert torch.equal(s2, out["cur"]) and torch.equal(r2, out["ref"]) and torch.equal(out2["in_ref"], out["in_ref"])
+
+
+@pytest.mark.parametrize("n,L", [(1, 10), (63, 10), (257, 20), (4099, 7)])
+def test_prepare_quad_random_vs_host_dataset(n, L):
+    PR, R, SY, T, DS = _mods()
+    g = torch.Generator().manual_seed(n + L)
+    s = torch.randn(n, 12, generator=g)
+    s[:, 3:6] *= 0.3
+    r = torch.randn(n, L, 9, generator=g) * 2
+    want = DS.QuadDataset.prepare_data(None, s.clone(), r.clone())
+    out = PR.prepare_quad(s.cuda(), r.cuda())
+    assert torch.equal(out["cur"].cpu(), want[1]) and torch.equal(out["ref"].cpu(), want[3])
+    assert torch.equal(out["in_ref"].cpu(), want[2])
+    assert _close(out["in_state"], want[0], 2e-6)
+    only = PR.prepare_quad(s.cuda(), r.cuda(), want=("in_ref",))
+    assert set(only) == {"in_ref"} and torch.equal(only["in_ref"], out["in_ref"])
+
+
+def test_prepare_wing_golden_and_random():
+    PR, R, SY, T, DS = _mods()
+    g = load_golden("prep_data.npz")
+    s = torch.tensor(g["wing_raw_states"], dtype=torch.float32).cuda()
+    tg = torch.tensor(g["wing_targets"], dtype=torch.float32).cuda()
+    out = PR.prepare_wing(s, tg, g["wing_mean"], g["wing_std"], float(g["wing_dt"]), int(g["wing_h"]))
+    assert torch.equal(out["cur"].cpu(), torch.tensor(g["wing_states"]))
+    for k, name in (("in_state", "wing_in_state"), ("in_ref", "wing_in_ref"), ("ref", "wing_ref")):
+        assert _close(out[k], g[name], 2e-6), k
+    c = SY.wing_case(1031, 20, 0.05, seed=3)
+    out = PR.prepare_wing(c["cur"].cuda(), c["target"].cuda(), SY.WING_MEAN, SY.WING_STD, 0.05, 20)
+    for k in ("in_state", "in_ref", "ref"):
+        assert _close(out[k], c[k], 2e-6), k
+
+
+def test_sample_windows_and_poly_reference():
+    PR, R, SY, T, DS = _mods()
+    rng = np.random.default_rng(0)
+    Tn, W, L = 1001, 12, 10
+    traj = torch.tensor(rng.standard_normal((Tn, W)), dtype=torch.float32)
+    stride = 2 * L
+    n = len(traj[:-(L + 1)][::stride])
+    states, refs = PR.sample_windows(traj.cuda(), n, L, stride)
+    idx = torch.arange(n) * stride
+    assert torch.equal(states.cpu()[:, :9], traj[idx, :9]) and float(states[:, 9:].abs().max()) == 0.0
+    for k in range(L):
+        assert torch.equal(refs.cpu()[:, k], traj[idx + k + 1, :9])
+    with pytest.raises(RuntimeError):
+        PR.sample_windows(traj.cuda(), n + 1, L, stride * 2)        # would read past the table
+    # polynomial rows against the bench's host generator (same coefficients)
+    nq, rows, dt = 300, 20, 0.1
+    gen = torch.Generator().manual_seed(9)
+    c = torch.zeros(nq, 3, 6)
+    c[:, :, 1] = torch.rand(nq, 3, generator=gen) * 3 - 1.5
+    for i in range(2, 6):
+        c[:, :, i] = (torch.rand(nq, 3, generator=gen) - 0.5) / math.factorial(i)
+    t = (torch.arange(rows, dtype=torch.float64) + 1) * dt
+    pw = torch.stack([t ** i for i in range(6)])
+    dpw = torch.stack([torch.zeros_like(t) if i == 0 else i * t ** (i - 1) for i in range(6)])
+    want = torch.zeros(nq, rows, 9, dtype=torch.float64)
+    want[:, :, 0:3] = torch.einsum("nai,il->nla", c.double(), pw)
+    want[:, :, 6:9] = torch.einsum("nai,il->nla", c.double(), dpw)
+    got = PR.poly_reference(c.cuda(), rows, dt)
+    assert _close(got, want, 2e-6)
+
+
+def _params(shapes, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.rand(*s, generator=g) * 2 - 1) / (s[-1] if len(s) > 1 else 64) ** 0.5 for s in shapes]
+
+
+CASES = {
+    "quad": dict(h=10, dt=0.1, n=1000, chunk=192),
+    "wing": dict(h=20, dt=0.05, n=777, chunk=256),
+    "cartpole": dict(h=5, dt=0.05, n=300, chunk=128),
+    "autoregressive": dict(h=10, dt=0.1, n=200, chunk=64),
+    "lstm": dict(h=10, dt=0.1, n=200, chunk=128),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_step_host_from_raw_samples_equals_step_from_prepared_tensors(name):
+    """3 SGD iterations: FusedTrainStep.step(prepared CUDA tensors) vs step_host(raw pinned host samples, several
+    ragged chunks) -- same losses, same parameters afterwards"""
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    c = CASES[name]
+    h, dt, n = c["h"], c["dt"], c["n"]
+    system = "quad" if name in ("quad", "autoregressive", "lstm") else name
+    mode = name if name in ("autoregressive", "lstm") else "concurrent"
+    w = dict(system=system, mode=mode, h=h, dt=dt)
+    params = B.default_init(system, h, seed=4, mode=mode)
+    spec = B.make_spec(w)
+    case = B.make_case(w, n, 21, "cpu")
+    lr = 1e-4
+    a = T.FusedTrainStep(params, spec, n, lr=lr, device="cuda:0", distributed=False)
+    b = T.FusedTrainStep(params, spec, n, lr=lr, device="cuda:0", distributed=False)
+    dev = {k: (v.cuda() if v is not None else None) for k, v in case.items()}
+    pin = {k: (v.clone().pin_memory() if v is not None else None) for k, v in case.items()}
+    for it in range(3):
+        la = a.step(dev.get("in_state"), dev["cur"], dev.get("in_ref"), dev.get("ref"), dev.get("h0c0"))
+        lb = b.step_host(pin["cur"], ref=pin.get("ref"), h0c0=pin.get("h0c0"), target=pin.get("target"),
+                         chunk=c["chunk"])
+        la, lb = float(la.item()), float(lb.item())
+        assert abs(la - lb) <= 1e-5 * abs(la), (name, it, la, lb)
+        assert rel_err(b.grad, a.grad) <= 1e-4, (name, it)
+    assert rel_err(b.flat, a.flat) <= 1e-6
+    # the whole batch as one chunk goes through the same code path
+    l1, g1 = b.value_and_grad_host(pin["cur"], ref=pin.get("ref"), h0c0=pin.get("h0c0"), target=pin.get("target"),
+                                   chunk=0)
+    l1, g1 = float(l1.item()), g1.clone()
+    l2, g2 = b.value_and_grad_host(pin["cur"], ref=pin.get("ref"), h0c0=pin.get("h0c0"), target=pin.get("target"),
+                                   chunk=64)
+    assert abs(l1 - float(l2.item())) <= 1e-5 * abs(l1) and rel_err(g2, g1) <= 1e-4
+
+
+def test_step_host_accepts_absolute_positions():
+    """truly raw quad samples (drone not at the origin): the device prepare makes them relative like the dataset"""
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    n, h, dt = 500, 10, 0.1
+    w = dict(system="quad", mode="concurrent", h=h, dt=dt)
+    case = B.make_case(w, n, 5, "cpu")
+    params = B.default_init("quad", h, seed=1)
+    st = T.FusedTrainStep(params, B.make_spec(w), n, lr=0.0, device="cuda:0", distributed=False)
+    l0, g0 = st.value_and_grad_host(case["cur"].pin_memory(), ref=case["ref"].pin_memory(), chunk=128)
+    l0, g0 = float(l0.item()), g0.clone()
+    off = torch.randn(n, 3) * 5
+    cur, ref = case["cur"].clone(), case["ref"].clone()
+    cur[:, :3] += off
+    ref[:, :, :3] += off[:, None, :]
+    l1, g1 = st.value_and_grad_host(cur.pin_memory(), ref=ref.pin_memory(), chunk=128)
+    assert abs(float(l1.item()) - l0) <= 2e-5 * abs(l0)      # (ref + off) - (cur + off) rounds differently
+    assert rel_err(g1, g0) <= 2e-4
