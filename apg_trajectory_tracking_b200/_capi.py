@@ -34,6 +34,10 @@ EXPORTS = {
                                                  ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "apg_quad_features": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "apg_quad_features_adjoint": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "apg_eval_rollout": (ctypes.c_int, [ctypes.POINTER(ApgConfig), c_float_p, c_float_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p, c_float_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "apg_prepare_quad": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_int, ctypes.c_int] + [c_float_p] * 4 +
                          [ctypes.c_void_p]),
     "apg_prepare_wing": (ctypes.c_int, [c_float_p] * 4 + [ctypes.c_float, ctypes.c_int, ctypes.c_int] +

@@ -449,4 +449,37 @@ __attribute__((visibility("default"))) int apg_quad_features_adjoint(const float
   return (int)launch_features_adj(state, grad_feat, n, grad_state, static_cast<cudaStream_t>(stream));
 }
 
+// Closed-loop evaluation on table references (eval_kernels.cu).
+__attribute__((visibility("default"))) int apg_eval_rollout(const apg_config* cfg, const float* params, const float* tables, const int* table_index,
+                     int n_tables, int table_rows, const float* init_states, int steps, float thresh_div,
+                     float thresh_stable, int test_time, void* workspace, float* states_out, float* div_out,
+                     float* actions_out, int* n_steps_out, void* stream) {
+  int e = check_config(cfg);
+  if (e) return e;
+  if (!is_hutter(cfg) || cfg->net != NET_HUTTER_CONV || cfg->system != SYS_QUAD) return APG_ERR_UNSUPPORTED;
+  if (cfg->state_feat != 15 || cfg->ref_dim != 9 || cfg->ref_len != cfg->horizon) return APG_ERR_BAD_CONFIG;
+  if (!params || !tables || !init_states || !workspace) return APG_ERR_BAD_CONFIG;
+  if (n_tables < 1 || table_rows < 1 || steps < 1) return APG_ERR_BAD_CONFIG;
+  if (!table_index && n_tables < cfg->n_drones) return APG_ERR_BAD_CONFIG;
+  if (!aligned16(params) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APG_ERR_ALIGNMENT;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Plan p = make_plan(cfg, net_info(cfg));
+  char* w = static_cast<char*>(workspace);
+  float* wf = reinterpret_cast<float*>(w + p.o_wf);
+  float* wb = reinterpret_cast<float*>(w + p.o_wb);
+  const HutterLayout y = hutter_layout(cfg);
+  cudaError_t ce;
+  if ((ce = launch_pack(hutter_pack_table(y), params, wf, wb, st))) return (int)ce;
+  PhysConsts pc;
+  memcpy(pc.v, cfg->phys, sizeof(float) * MAX_PHYS);
+  EvalParams ev;
+  ev.steps = steps; ev.table_rows = table_rows; ev.test_time = test_time ? 1 : 0;
+  ev.thresh_div = thresh_div; ev.thresh_stable = thresh_stable;
+  if ((ce = launch_eval_rollout(y, wf, tables, table_index, init_states, cfg->n_drones, cfg->dt, pc, ev, states_out,
+                                div_out, actions_out, n_steps_out, p.grid, st)))
+    return (int)ce;
+  return 0;
+}
+
 }  // extern "C"

@@ -1,0 +1,167 @@
+// Closed-loop evaluation rollout on table references: the batched, no-grad counterpart of
+// QuadEvaluator.follow_trajectory("rand") (scripts/evaluate_drone.py:81-194).  Every drone walks its own reference
+// table: window -> QuadDataset.prepare_data -> hutter policy (first predicted action) -> dynamics step ->
+// divergence / stability -> stop or reset, for up to `steps` steps in ONE launch.  Same tile engine as the training
+// kernels (64-drone tiles, weights resident in shared memory, 3xTF32 tensor path), no stash, no loss.
+#include "eval_math.cuh"
+#include "hutter_policy.cuh"
+#include "layouts.h"
+#include "tile_engine.cuh"
+#include "kernels.h"
+
+namespace apg {
+
+struct EvalArgs {
+  const float* wf;            // packed forward weights (apg_pack_kernel)
+  const float* tables;        // [n_tables][RL][9]
+  const int* table_index;     // [N] table of each drone (nullptr: drone i uses table i)
+  const float* init_states;   // [N][12]
+  int N, h;
+  float dt;
+  PhysConsts pc;
+  EvalParams ev;
+  float* states_out;          // optional [N][steps+1][12]
+  float* div_out;             // optional [N][steps]
+  float* actions_out;         // optional [N][steps][4]
+  int* n_steps_out;           // optional [N]
+};
+
+__global__ void __launch_bounds__(NT, 1) eval_rollout_kernel(const HutterLayout y, const EvalArgs g) {
+  extern __shared__ __align__(128) float smem[];
+  using Sys = Quad<float>;
+  constexpr int S = Sys::S, A = Sys::A;
+  const int h = g.h, RL = g.ev.table_rows, steps = g.ev.steps;
+  float* s_w = smem;
+  float* s_ins = s_w + y.f_total;
+  float* s_win = s_ins + pad4(TM * y.F0);
+  float* s_x1 = s_win + pad4(TM * y.LR);
+  float* s_h = s_x1 + y.XR * TMP;
+  float* s_mf = s_h + HID * TMP;                          // [6][TM] drone position / velocity
+  int* s_mi = reinterpret_cast<int*>(s_mf + 6 * TM);      // [2][TM] window start / real rows
+  const float** s_tab = reinterpret_cast<const float**>(s_mi + 2 * TM);   // [TM] table of each drone
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_tab + TM);
+  float* s_act = s_x1 + HID * TMP;
+  const Lane L;
+  const int tid = threadIdx.x;
+  const int ntiles = (g.N + TM - 1) / TM;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, y.f_total * 4);
+    bulk_g2s_chunked(s_w, g.wf, y.f_total * 4, bar_w);
+  }
+  mbar_wait(bar_w, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int valid = min(TM, g.N - tile * TM);
+    const size_t drone = (size_t)tile * TM + tid;
+    const bool mine = tid < valid;                        // this thread owns a drone
+    float s[S];
+    int ci = 0, alive = mine ? 1 : 0, nsteps = 0;
+    const float* tab = nullptr;
+    if (mine) {
+      tab = g.tables + (size_t)(g.table_index ? g.table_index[drone] : (int)drone) * RL * 9;
+#pragma unroll
+      for (int i = 0; i < S; ++i) s[i] = g.init_states[drone * S + i];
+      if (g.states_out) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) g.states_out[drone * (steps + 1) * S + i] = s[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < S; ++i) s[i] = 0.f;
+    }
+    if (tid < TM) s_tab[tid] = tab;
+    for (int i = 0; i < steps; ++i) {
+      if (tid < TM) {
+        int start = 0, nreal = 0, ci_next = ci;
+        if (alive) eval_window_plan(ci, RL, h, &start, &nreal, &ci_next);
+        ci = ci_next;
+        float c0[S], f[15];
+        c0[0] = c0[1] = c0[2] = 0.f;
+#pragma unroll
+        for (int j = 3; j < S; ++j) c0[j] = s[j];
+        Sys::features(c0, f);
+#pragma unroll
+        for (int j = 0; j < 15; ++j) s_ins[tid * y.F0 + j] = f[j];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { s_mf[c * TM + tid] = s[c]; s_mf[(3 + c) * TM + tid] = s[6 + c]; }
+        s_mi[tid] = start;
+        s_mi[TM + tid] = alive ? nreal : -1;              // -1: no live drone in this slot -> zero window
+      }
+      __syncthreads();
+      for (int idx = tid; idx < TM * y.LR; idx += NT) {
+        const int d = idx / y.LR, e = idx - d * y.LR;
+        const int r = e / 9, c = e - r * 9;
+        float v = 0.f;
+        const int nreal = s_mi[TM + d];
+        if (nreal >= 0) {
+          const float pos_c = c < 3 ? s_mf[c * TM + d] : 0.f;
+          const float vel_c = c >= 6 ? s_mf[(c - 3) * TM + d] : 0.f;      // rows 3..5 of s_mf hold the velocity
+          v = eval_in_ref_elem(s_tab[d], RL, s_mi[d], nreal, r, c, pos_c, vel_c);
+        }
+        s_win[idx] = v;
+      }
+      __syncthreads();
+      hutter_first_layer<true>(L, y, s_w, s_ins, s_win, s_x1);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_x1, y.K1, s_w + y.f_w1, HID, mma_sw(HID), s_w + y.f_b1, HID, s_h, 0, ACT_TANH);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_w2, HID, mma_sw(HID), s_w + y.f_b2, HID, s_x1, 0, ACT_TANH);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_x1, HID, s_w + y.f_w3, HID, mma_sw(HID), s_w + y.f_b3, HID, s_h, 0, ACT_TANH);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_wo, y.ld_fwo, mma_sw(y.ld_fwo), s_w + y.f_bo, y.Mo4, s_act, 0,
+                          ACT_SIGMOID);
+      __syncthreads();
+      if (alive) {
+        float a[A], sn[S];
+#pragma unroll
+        for (int c = 0; c < A; ++c) a[c] = fminf(fmaxf(s_act[c * TMP + tid], 0.f), 1.f);   // first predicted action
+        Sys::step(s, a, g.dt, g.pc.v, sn);
+        if (g.states_out) {
+#pragma unroll
+          for (int j = 0; j < S; ++j) g.states_out[(drone * (steps + 1) + i + 1) * S + j] = sn[j];
+        }
+        if (g.actions_out) {
+#pragma unroll
+          for (int c = 0; c < A; ++c) g.actions_out[(drone * steps + i) * A + c] = a[c];
+        }
+        const float div = eval_post_step(sn, tab, ci, g.ev, &alive);
+        if (g.div_out) g.div_out[drone * steps + i] = div;
+#pragma unroll
+        for (int j = 0; j < S; ++j) s[j] = sn[j];
+        ++nsteps;
+        if (i >= RL) alive = 0;                           // evaluate_drone.py:187-188
+      }
+      // barrier before the next step overwrites s_ins / s_act; also the tile-wide early exit
+      if (!__syncthreads_or(alive)) break;
+    }
+    if (mine && g.n_steps_out) g.n_steps_out[drone] = nsteps;
+    __syncthreads();
+  }
+}
+
+size_t eval_smem_bytes(const HutterLayout& y) {
+  return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP + 6 * TM) +
+         sizeof(int) * 2 * TM + sizeof(void*) * TM + 16;
+}
+
+cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const float* tables, const int* table_index,
+                                const float* init_states, int n, float dt, const PhysConsts& pc, const EvalParams& ev,
+                                float* states_out, float* div_out, float* actions_out, int* n_steps_out, int grid,
+                                cudaStream_t st) {
+  EvalArgs a;
+  a.wf = wf; a.tables = tables; a.table_index = table_index; a.init_states = init_states;
+  a.N = n; a.h = y.L; a.dt = dt; a.pc = pc; a.ev = ev;
+  a.states_out = states_out; a.div_out = div_out; a.actions_out = actions_out; a.n_steps_out = n_steps_out;
+  const size_t smem = eval_smem_bytes(y);
+  cudaError_t e = cudaFuncSetAttribute(eval_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  eval_rollout_kernel<<<grid, NT, smem, st>>>(y, a);
+  return cudaGetLastError();
+}
+
+}  // namespace apg

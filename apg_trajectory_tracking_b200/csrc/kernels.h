@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "layouts.h"
 #include "rollout_args.h"
+#include "eval_math.cuh"
 
 namespace apg {
 
@@ -30,6 +31,12 @@ cudaError_t launch_step_adj(int system, const PhysConsts& pc, const float* s, co
                             const float* g, float* gs, float* ga, cudaStream_t st);
 cudaError_t launch_features(const float* s, int n, float* f, cudaStream_t st);
 cudaError_t launch_features_adj(const float* s, const float* gf, int n, float* gs, cudaStream_t st);
+
+// closed-loop evaluation on table references (eval_kernels.cu)
+cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const float* tables, const int* table_index,
+                                const float* init_states, int n, float dt, const PhysConsts& pc, const EvalParams& ev,
+                                float* states_out, float* div_out, float* actions_out, int* n_steps_out, int grid,
+                                cudaStream_t st);
 
 // data formats on the input side (prep_kernels.cu)
 cudaError_t launch_prepare_quad(const float* states, const float* ref, int n, int L, float* in_state, float* cur_out,

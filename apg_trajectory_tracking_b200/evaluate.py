@@ -1,0 +1,85 @@
+"""Batched closed-loop evaluation on table references.
+
+Reference: ``QuadEvaluator.follow_trajectory("rand")`` / ``run_eval`` (scripts/evaluate_drone.py:81-194, 236-298), the
+per-epoch evaluation of the quadrotor trainer (scripts/train_drone.py:205-216): a batch-1 CPU loop of up to 251 policy
+calls per run.  Here N drones walk their reference tables in ONE kernel launch (csrc/eval_kernels.cu): window ->
+QuadDataset.prepare_data -> policy -> dynamics step -> divergence / stability -> stop or reset.  CUDA only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi, rollout as R
+from .ops import _p, _require_cuda, _stream
+
+
+class TableEvaluator:
+    """Owns the workspace for (spec, N); ``follow`` runs one closed-loop evaluation of N drones."""
+
+    def __init__(self, spec: R.RolloutSpec, n_drones: int, device=None):
+        if not torch.cuda.is_available():
+            raise _capi.ApgError("no CUDA device: the evaluation rollout only runs on the GPU")
+        if spec.system != "quad" or spec.net != "hutter_conv":
+            raise _capi.ApgError("table evaluation is implemented for the quadrotor hutter conv nets")
+        self.spec, self.n = spec, int(n_drones)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lib = _capi.lib()
+        with torch.cuda.device(self.device):
+            self.cfg = spec.config(self.n)
+            ws = self.lib.apg_workspace_bytes(ctypes.byref(self.cfg))
+            if ws == 0:
+                raise _capi.ApgError("bad rollout spec for the evaluation rollout")
+            self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 256
+            self._ws_ptr = ctypes.c_void_p(self.workspace.data_ptr() + off)
+
+    def follow(self, params_flat, tables, init_states=None, table_index=None, steps=251, thresh_div=1.0,
+               thresh_stable=1.0, test_time=0, want=("states", "div", "actions")):
+        """tables (T,RL,9) rows [pos, euler, vel]; table_index (N,) int32 or None (drone i walks table i);
+        init_states (N,12) or None (at rest on the first table point, like ``zero_reset(*initial_pos)``).
+        Returns dict(states (N,steps+1,12), div (N,steps), actions (N,steps,4), n_steps (N,) int32); entries after a
+        drone stopped are zero."""
+        _require_cuda(params_flat, tables, init_states, table_index)
+        tables = tables if (tables.dtype == torch.float32 and tables.is_contiguous()) else tables.contiguous().float()
+        n, dev = self.n, self.device
+        if table_index is not None:
+            table_index = table_index.to(torch.int32).contiguous()
+            if table_index.numel() != n:
+                raise ValueError("table_index must have one entry per drone")
+        elif tables.shape[0] < n:
+            raise ValueError("without table_index there must be one table per drone")
+        if init_states is None:
+            first = tables[:, 0, :3] if table_index is None else tables[table_index.long(), 0, :3]
+            init_states = torch.zeros(n, 12, device=dev)
+            init_states[:, :3] = first[:n]
+        init_states = init_states.contiguous().float()
+        out = {"n_steps": torch.zeros(n, dtype=torch.int32, device=dev)}
+        if "states" in want:
+            out["states"] = torch.zeros(n, steps + 1, 12, device=dev)
+        if "div" in want:
+            out["div"] = torch.zeros(n, steps, device=dev)
+        if "actions" in want:
+            out["actions"] = torch.zeros(n, steps, 4, device=dev)
+        opt = lambda k: None if k not in out else _p(out[k])          # noqa: E731
+        with torch.cuda.device(dev):
+            _capi.check(self.lib.apg_eval_rollout(
+                ctypes.byref(self.cfg), _p(params_flat), _p(tables), None if table_index is None else _p(table_index),
+                int(tables.shape[0]), int(tables.shape[1]), _p(init_states), int(steps), ctypes.c_float(thresh_div),
+                ctypes.c_float(thresh_stable), int(test_time), self._ws_ptr, opt("states"), opt("div"), opt("actions"),
+                _p(out["n_steps"]), _stream(tables)))
+        return out
+
+
+def eval_statistics(div, n_steps, thresh_div):
+    """``QuadEvaluator.run_eval`` statistics (evaluate_drone.py:266-298) over the N runs of one ``follow`` call:
+    (mean, std of the steps below the divergence threshold, mean, std of the tracking error of the runs that stayed
+    below it for their whole length, mean, std of the tracking error of all runs)."""
+    d = div.detach().cpu().double().numpy()
+    ns = n_steps.detach().cpu().numpy()
+    per_run = np.array([d[i, :ns[i]].mean() if ns[i] else 0.0 for i in range(len(ns))])
+    stable = np.array([(d[i, :ns[i]] < thresh_div).sum() for i in range(len(ns))])
+    full = per_run[stable == ns[-1]]             # max_steps_stable = len(reference_traj) of the LAST run (:276)
+    nan = float("nan")
+    return (stable.mean(), stable.std(), full.mean() if len(full) else nan, full.std() if len(full) else nan,
+            per_run.mean(), per_run.std())

@@ -110,6 +110,22 @@ int apg_sample_windows(const float* traj, int traj_rows, int traj_cols, int ref_
                        float* states, float* ref_states, void* stream);
 int apg_poly_reference(const float* coef, int n, int rows, float t_first, float dt, float* ref_out, void* stream);
 
+/* ---- closed-loop evaluation on table references: QuadEvaluator.follow_trajectory("rand")
+ * (scripts/evaluate_drone.py:81-194) with Random.get_ref_traj / project_on_ref / get_current_full_state
+ * (neural_control/trajectory/random_traj.py:62-92), NetworkWrapper.predict_actions
+ * (neural_control/controllers/network_wrapper.py:41-71) and QuadRotorEnvBase.step / get_is_stable
+ * (neural_control/environments/drone_env.py:66-115), for cfg->n_drones independent drones in one launch, no gradient.
+ * cfg: quadrotor hutter conv net, concurrent (out_dim 4h: the first predicted action is applied) or autoregressive
+ * (out_dim 4); cfg->dt / cfg->phys are those of the EVALUATION dynamics.  tables [n_tables][table_rows][9] =
+ * [pos, euler, vel] rows; table_index [N] (device, may be NULL: drone i walks table i); init_states [N][12].
+ * Outputs (device, optional, caller zero-initialised: entries after a drone stopped are not written):
+ * states_out [N][steps+1][12], div_out [N][steps], actions_out [N][steps][4], n_steps_out [N] (int).
+ * workspace: apg_workspace_bytes(cfg). */
+int apg_eval_rollout(const apg_config* cfg, const float* params, const float* tables, const int* table_index,
+                     int n_tables, int table_rows, const float* init_states, int steps, float thresh_div,
+                     float thresh_stable, int test_time, void* workspace, float* states_out, float* div_out,
+                     float* actions_out, int* n_steps_out, void* stream);
+
 int apg_sm_count(void);
 int apg_version(void);
 const char* apg_error_string(int code);

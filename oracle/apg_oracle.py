@@ -427,3 +427,92 @@ def sgd_momentum_step(params, grads, bufs, lr, momentum=0.9):
         out_p.append(p - lr * nb)
         out_b.append(nb)
     return out_p, out_b
+
+
+# --------------------------------------------------------------------------------------------
+# N2  closed-loop evaluation on table references: QuadEvaluator.follow_trajectory("rand")
+#     (scripts/evaluate_drone.py:81-194) with trajectory/random_traj.py:62-96 (Random.get_ref_traj /
+#     project_on_ref / get_current_full_state), NetworkWrapper.predict_actions (controllers/network_wrapper.py:41-71),
+#     QuadRotorEnvBase.step / get_is_stable (environments/drone_env.py:66-115) and the run_eval statistics
+#     (evaluate_drone.py:236-298), restated for N independent drones at once.
+# --------------------------------------------------------------------------------------------
+def eval_window(tables, ci, h):
+    """Random.get_ref_traj for every drone: tables (N,RL,9), ci (N,) current index -> (rows (N,h,9), new ci).
+    Regular case: rows ci+1 .. ci+h and the index advances; at the end of the table (ci >= RL-h) the remaining rows
+    from ci on, padded with [last position, 0...], and the index stays (random_traj.py:67-81)."""
+    n, rl, w = tables.shape
+    end = ci >= rl - h
+    start = torch.where(end, ci, ci + 1)
+    nreal = torch.where(end, rl - ci, torch.full_like(ci, h))
+    r = torch.arange(h)[None, :]
+    idx = (start[:, None] + r).clamp(max=rl - 1)
+    rows = torch.gather(tables, 1, idx[:, :, None].expand(n, h, w))
+    pad = torch.zeros(n, h, w, dtype=tables.dtype)
+    pad[:, :, :3] = tables[:, -1:, :3]
+    rows = torch.where((r < nreal[:, None])[:, :, None], rows, pad)
+    return rows, torch.where(end, ci, ci + 1)
+
+
+def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0, thresh_stable=1.0, test_time=0,
+                       cfg=QUAD_CFG):
+    """Batched restatement of QuadEvaluator.follow_trajectory("rand").
+
+    params: hutter Net(15,h,9,4h) (concurrent: the first of the h predicted actions is applied,
+    evaluate_drone.py:154-155) or Net(15,h,9,4); tables (N,RL,9) reference rows [pos, euler, vel] as
+    Random.__init__ leaves them; init_states (N,12).  Per step: window -> QuadDataset.prepare_data -> net ->
+    sigmoid -> clip -> dynamics (evaluated in float64 on the float64 env state and rounded to float32,
+    drone_env.py:94-102) -> divergence to tables[ci,:3] -> if diverged / unstable: stop (test_time) or reset the
+    drone to the reference state.  Returns dict(states (N,steps+1,12), div (N,steps), actions (N,steps,4),
+    n_steps (N,) = steps taken before the break; entries after a break are zero)."""
+    n, rl, _ = tables.shape
+    tables = tables.float()
+    s = init_states.float().clone()
+    ci = torch.zeros(n, dtype=torch.long)
+    alive = torch.ones(n, dtype=torch.bool)
+    states = torch.zeros(n, steps + 1, 12)
+    states[:, 0] = s
+    divs, actions = torch.zeros(n, steps), torch.zeros(n, steps, 4)
+    n_steps = torch.zeros(n, dtype=torch.long)
+    out_dim = params[-1].shape[0]
+    for i in range(steps):
+        if not bool(alive.any()):
+            break
+        rows, ci_new = eval_window(tables, ci, h)
+        ci = torch.where(alive, ci_new, ci)
+        cur = s.clone()
+        rel = rows.clone()
+        rel[:, :, :3] = rel[:, :, :3] - cur[:, None, :3]                 # dataset.py:170-173
+        cur[:, :3] = 0
+        in_ref = torch.cat((rel[:, :, :3], rel[:, :, 6:9], rel[:, :, 6:9] - cur[:, None, 6:9]), dim=2)
+        with torch.no_grad():
+            act = torch.sigmoid(hutter_forward(params, state_preprocessing(cur), in_ref))
+        a0 = (act.reshape(n, h, 4)[:, 0] if out_dim == 4 * h else act).clamp(0.0, 1.0)
+        nxt = quad_step(s.double(), a0.double(), dt, cfg).float()
+        stable = (nxt[:, 3:5].abs() < thresh_stable).all(dim=1)           # drone_env.py:66-74
+        on_line = tables[torch.arange(n), ci, :3]                         # random_traj.py:83-87
+        div = (on_line.double() - nxt[:, :3].double()).norm(dim=1).float()
+        states[alive, i + 1] = nxt[alive]
+        divs[alive, i] = div[alive]
+        actions[alive, i] = a0[alive]
+        n_steps[alive] += 1
+        bad = (div > thresh_div) | ~stable
+        reset_state = torch.cat((tables[torch.arange(n), ci], torch.zeros(n, 3)), dim=1)   # random_traj.py:89-92
+        if test_time:
+            s = torch.where(alive[:, None], nxt, s)
+            alive = alive & ~bad
+        else:
+            s = torch.where((alive & bad)[:, None], reset_state, torch.where(alive[:, None], nxt, s))
+        alive = alive & (i < rl)                                          # evaluate_drone.py:187-188
+    return dict(states=states, div=divs, actions=actions, n_steps=n_steps)
+
+
+def eval_statistics(div, n_steps, thresh_div):
+    """QuadEvaluator.run_eval (evaluate_drone.py:266-298) over the N runs: per run mean divergence and the number
+    of steps below the threshold; returns the 6-tuple of run_eval."""
+    import numpy as np
+    div, n_steps = div.numpy(), n_steps.numpy()
+    d = np.array([div[i, :n_steps[i]].mean() for i in range(len(n_steps))])
+    stable = np.array([(div[i, :n_steps[i]] < thresh_div).sum() for i in range(len(n_steps))])
+    full = d[stable == n_steps[-1]]              # max_steps_stable = len(reference_traj) of the LAST run
+    return stable.mean(), stable.std(), full.mean() if len(full) else float("nan"), \
+        full.std() if len(full) else float("nan"), d.mean(), d.std()

@@ -45,14 +45,85 @@ def npify(d):
     return out
 
 
+def eval_table(seed, rows, dt, speed):
+    """synthetic stand-in for one file of data/traj_data_1 as load_prepare_trajectory returns it:
+    [pos, euler (0), vel] of a degree-5 polynomial per axis, sampled every dt"""
+    import math
+    rng = np.random.default_rng(seed)
+    c = np.zeros((3, 6))
+    c[:, 1] = rng.uniform(-speed, speed, 3)
+    for i in range(2, 6):
+        c[:, i] = rng.uniform(-0.3 * speed, 0.3 * speed, 3) / math.factorial(i)
+    t = np.arange(rows) * dt
+    pos = np.stack([sum(c[a, i] * t ** i for i in range(6)) for a in range(3)], 1)
+    vel = np.stack([sum(i * c[a, i] * t ** (i - 1) for i in range(1, 6)) for a in range(3)], 1)
+    return np.hstack((pos, np.zeros((rows, 3)), vel))
+
+
+def make_eval_golden(args):
+    """eval_rand.npz: QuadEvaluator.follow_trajectory("rand") of the unmodified reference (scripts/evaluate_drone.py)
+    with the shipped model_quad.  The only substitution is the trajectory FILE: data/traj_data_1 is not part of the
+    checkout, so load_prepare_trajectory (the file reader) is replaced by a function returning the synthetic tables
+    saved next to the outputs; Random.__init__ / get_ref_traj / project_on_ref, NetworkWrapper, QuadDataset,
+    QuadRotorEnvBase.step and FlightmareDynamics run as they are."""
+    import torch
+    cwd = os.getcwd()
+    os.chdir(args.ref)
+    _np_random = lambda seed=None: (np.random.RandomState(0), 0)      # gym is stubbed: give the env a real RNG
+    sys.modules['gym.utils'].seeding.np_random = _np_random
+    sys.modules['gym'].utils.seeding.np_random = _np_random
+    import neural_control.trajectory.random_traj as RT
+    import evaluate_drone as ED
+    from neural_control.environments.drone_env import QuadRotorEnvBase
+    from neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from neural_control.controllers.network_wrapper import NetworkWrapper
+    from neural_control.dataset import QuadDataset
+    net = torch.load('trained_models/quad/current_model/model_quad', weights_only=False)
+    net.eval()
+    h, dt = 10, 0.1
+    ds = QuadDataset.__new__(QuadDataset)            # no sampling (needs the absent data files); prepare_data only
+    ds.get_and_add_eval_data = lambda st, rf, add_to_dataset=False: QuadDataset.prepare_data(ds, st, rf)
+    out = {}
+    # (name, table seed, rows, speed, steps, test_time, thresh_div, thresh_stable)
+    runs = [("gentle", 1, 120, 0.25, 80, 0, 1.0, 1.0), ("fast_reset", 2, 120, 1.0, 80, 0, 1.0, 1.0),
+            ("fast_stop", 2, 120, 1.0, 80, 1, 1.0, 1.0), ("short_table", 3, 30, 0.3, 45, 0, 1.0, 1.0),
+            ("tight", 4, 100, 0.6, 60, 0, 0.3, 0.05)]
+    for name, seed, rows, speed, steps, test_time, tdiv, tstab in runs:
+        table = eval_table(seed, rows, dt, speed)
+        RT.load_prepare_trajectory = lambda base_dir, dt_, speed_factor, test=False, _t=table: _t.copy()
+        env = QuadRotorEnvBase(FlightmareDynamics(), dt)
+        ctrl = NetworkWrapper(net, ds, horizon=h, dt=dt)
+        ev = ED.QuadEvaluator(ctrl, env, ref_length=h, dt=dt, test_time=test_time, speed_factor=0.4,
+                              train_mode="concurrent")
+        ref_traj, drone_traj, div, acts = ev.follow_trajectory("rand", max_nr_steps=steps, thresh_stable=tstab,
+                                                               thresh_div=tdiv)
+        tab = table.copy()
+        tab[:, 2] += 3                                # Random.__init__ (random_traj.py:35)
+        out[f"{name}_table"] = tab
+        out[f"{name}_cfg"] = np.array([steps, test_time, tdiv, tstab, h, dt], dtype=np.float64)
+        out[f"{name}_ref_traj"] = np.asarray(ref_traj)
+        out[f"{name}_states"] = np.asarray(drone_traj)
+        out[f"{name}_div"] = np.asarray(div)
+        out[f"{name}_actions"] = np.asarray(acts)[:, 0]          # the applied action (evaluate_drone.py:154-155)
+        print("eval", name, "steps taken", len(div), "mean div %.4f" % np.mean(div), "resets/stops",
+              int(np.sum(np.asarray(div) > tdiv)))
+    out["run_names"] = np.array([r[0] for r in runs])
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(args.out, "eval_rand.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
     ap.add_argument("--only-prep", action="store_true", help="only (re)generate prep_data.npz")
+    ap.add_argument("--only-eval", action="store_true", help="only (re)generate eval_rand.npz")
     args = ap.parse_args()
     import_reference(args.ref)
     os.makedirs(args.out, exist_ok=True)
+    if args.only_eval:
+        make_eval_golden(args)
+        return
 
     import torch
     from neural_control.drone_loss import quad_mpc_loss, fixed_wing_mpc_loss, cartpole_loss_mpc  # noqa: F401

@@ -1,0 +1,86 @@
+"""Per-drone logic of the closed-loop evaluation kernel (csrc/eval_math.cuh: reference window, divergence, stability,
+stop / reset) compiled with g++ and driven like the kernel's per-thread code, against the golden runs of the
+reference's own QuadEvaluator.follow_trajectory("rand") (tests/golden/eval_rand.npz) and against the CPU oracle."""
+import ctypes
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import apg_oracle as O
+from tests.helpers import golden_params, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("apg_params", os.path.join(ROOT, "apg_trajectory_tracking_b200",
+                                                                             "params.py"))
+P = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(P)
+
+
+@pytest.fixture(scope="module")
+def he(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostcheck_eval") / "libhostcheck_eval.so"
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck_eval.cpp")
+    inc = os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", "-std=c++17", "-ffp-contract=off", "-I", inc,
+                           src, "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _run(he, params, tables, index, init, steps, h, dt, tdiv, tstab, test_time):
+    flat = np.ascontiguousarray(torch.cat([p.reshape(-1) for p in params]).numpy(), dtype=np.float32)
+    tables = np.ascontiguousarray(tables, dtype=np.float32)
+    init = np.ascontiguousarray(init, dtype=np.float32)
+    n, rl = init.shape[0], tables.shape[1]
+    idx = None if index is None else np.ascontiguousarray(index, dtype=np.int32)
+    states = np.zeros((n, steps + 1, 12), np.float32)
+    div, act = np.zeros((n, steps), np.float32), np.zeros((n, steps, 4), np.float32)
+    nst = np.zeros(n, np.int32)
+    pc = P.PHYS["quad"]()
+    he.hc_eval_rollout(_p(flat), h, params[-1].shape[0], _p(tables), _p(idx), rl, _p(init), n, steps,
+                       ctypes.c_float(dt), _p(pc), ctypes.c_float(tdiv), ctypes.c_float(tstab), int(test_time),
+                       _p(states), _p(div), _p(act), _p(nst))
+    return states, div, act, nst
+
+
+@pytest.mark.parametrize("name", ["gentle", "fast_reset", "fast_stop", "short_table", "tight"])
+def test_kernel_logic_matches_reference_evaluator(he, name):
+    g = load_golden("eval_rand.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
+    steps, test_time, h = int(steps), int(test_time), int(h)
+    ref_states = g[f"{name}_states"]
+    states, div, act, nst = _run(he, params, g[f"{name}_table"][None], None, ref_states[:1], steps, h, dt, tdiv, tstab,
+                                 test_time)
+    taken = len(g[f"{name}_div"])
+    assert int(nst[0]) == taken
+    assert np.abs(states[0, :taken + 1] - ref_states).max() <= 2e-5
+    assert np.abs(div[0, :taken] - g[f"{name}_div"]).max() <= 2e-5
+    assert np.abs(act[0, :taken] - g[f"{name}_actions"]).max() <= 2e-5
+    assert np.abs(states[0, taken + 1:]).sum() == 0
+
+
+def test_kernel_logic_matches_oracle_batched_with_table_index(he):
+    """several drones sharing tables through the index array, different start offsets, stop mode"""
+    g = load_golden("eval_rand.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    tabs = np.stack([g["gentle_table"][:100], g["tight_table"][:100]]).astype(np.float32)
+    index = np.array([0, 1, 1, 0, 1], dtype=np.int32)
+    rng = np.random.default_rng(0)
+    init = np.zeros((5, 12), np.float32)
+    init[:, :3] = tabs[index, 0, :3] + rng.normal(0, 0.05, (5, 3))
+    init[:, 6:9] = rng.normal(0, 0.1, (5, 3))
+    states, div, act, nst = _run(he, params, tabs, index, init, 50, 10, 0.1, 0.6, 0.5, 1)
+    out = O.eval_follow_tables(params, torch.tensor(tabs)[torch.tensor(index, dtype=torch.long)], torch.tensor(init),
+                               50, 10, 0.1, 0.6, 0.5, 1)
+    assert np.array_equal(nst, out["n_steps"].numpy())
+    assert len(set(nst.tolist())) > 1                     # the drones stop at different steps
+    assert np.abs(states - out["states"].numpy()).max() <= 2e-5
+    assert np.abs(div - out["div"].numpy()).max() <= 2e-5

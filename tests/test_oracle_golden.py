@@ -139,3 +139,47 @@ def test_sgd_momentum_matches_torch():
         p, bufs = O.sgd_momentum_step(p, grads, bufs, 1e-2)
         for a, b in zip(p, mods):
             assert torch.allclose(a, b.detach(), atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N2: closed-loop evaluation on table references, pinned on QuadEvaluator.follow_trajectory("rand") of the reference
+# ---------------------------------------------------------------------------------------------------------------
+def _eval_runs():
+    g = load_golden("eval_rand.npz")
+    return g, [str(x) for x in g["run_names"]]
+
+
+@pytest.mark.parametrize("name", ["gentle", "fast_reset", "fast_stop", "short_table", "tight"])
+def test_eval_follow_tables_matches_reference_evaluator(name):
+    g, names = _eval_runs()
+    assert name in names
+    params = golden_params(load_golden("conc_quad_kat4.npz"))            # the shipped model_quad
+    steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
+    steps, test_time, h = int(steps), int(test_time), int(h)
+    table = torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None]
+    ref_states = g[f"{name}_states"]
+    init = torch.tensor(ref_states[0], dtype=torch.float32)[None]
+    out = O.eval_follow_tables(params, table, init, steps, h, dt, tdiv, tstab, test_time)
+    taken = len(g[f"{name}_div"])
+    assert int(out["n_steps"][0]) == taken
+    # closed loop, fp32 policy on both sides: measured 4e-6 at most over these horizons
+    assert np.abs(out["states"][0, :taken + 1].numpy() - ref_states).max() <= 2e-5
+    assert np.abs(out["div"][0, :taken].numpy() - g[f"{name}_div"]).max() <= 2e-5
+    assert np.abs(out["actions"][0, :taken].numpy() - g[f"{name}_actions"]).max() <= 2e-5
+    # the projected reference points are the table rows at the walking index
+    assert float(out["states"][0, taken + 1:].abs().sum()) == 0.0
+
+
+def test_eval_follow_tables_is_batched_consistently():
+    """N drones at once == the same drones one by one (different tables, thresholds hit at different steps)"""
+    g, names = _eval_runs()
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    tabs = [torch.tensor(g[f"{n}_table"], dtype=torch.float32)[:100] for n in ("gentle", "fast_reset", "tight")]
+    tables = torch.stack(tabs)
+    init = torch.zeros(3, 12)
+    init[:, :3] = tables[:, 0, :3]
+    both = O.eval_follow_tables(params, tables, init, 40, 10, 0.1, 0.8, 1.0, 1)
+    for i in range(3):
+        one = O.eval_follow_tables(params, tables[i:i + 1], init[i:i + 1], 40, 10, 0.1, 0.8, 1.0, 1)
+        assert int(one["n_steps"][0]) == int(both["n_steps"][i])
+        assert torch.allclose(one["states"][0], both["states"][i], atol=1e-5)

@@ -173,3 +173,67 @@ def test_step_host_accepts_absolute_positions():
     l1, g1 = st.value_and_grad_host(cur.pin_memory(), ref=ref.pin_memory(), chunk=128)
     assert abs(float(l1.item()) - l0) <= 2e-5 * abs(l0)      # (ref + off) - (cur + off) rounds differently
     assert rel_err(g1, g0) <= 2e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N2: closed-loop evaluation rollout (csrc/eval_kernels.cu) vs the reference evaluator's golden runs and the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _eval_mods():
+    from apg_trajectory_tracking_b200 import evaluate as EV, rollout as R
+    from oracle import apg_oracle as O
+    from tests.helpers import golden_params
+    return EV, R, O, golden_params
+
+
+@pytest.mark.parametrize("name", ["gentle", "fast_reset", "fast_stop", "short_table", "tight"])
+def test_eval_rollout_matches_reference_evaluator(name):
+    EV, R, O, golden_params = _eval_mods()
+    g = load_golden("eval_rand.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))            # shipped model_quad, Net(15,10,9,40)
+    steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
+    steps, test_time, h = int(steps), int(test_time), int(h)
+    ev = EV.TableEvaluator(R.RolloutSpec.quad_concurrent(h, dt), 1, "cuda:0")
+    ref_states = g[f"{name}_states"]
+    out = ev.follow(R.flatten_params(params).cuda(), torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None].cuda(),
+                    init_states=torch.tensor(ref_states[:1], dtype=torch.float32).cuda(), steps=steps,
+                    thresh_div=tdiv, thresh_stable=tstab, test_time=test_time)
+    taken = len(g[f"{name}_div"])
+    assert int(out["n_steps"][0]) == taken
+    # closed loop over up to 80 steps with resets: fp32 (3xTF32 policy) vs the reference's fp32 policy / fp64 dynamics
+    assert np.abs(out["states"][0, :taken + 1].cpu().numpy() - ref_states).max() <= 1e-4
+    assert np.abs(out["div"][0, :taken].cpu().numpy() - g[f"{name}_div"]).max() <= 1e-4
+    assert np.abs(out["actions"][0, :taken].cpu().numpy() - g[f"{name}_actions"]).max() <= 1e-4
+    assert float(out["states"][0, taken + 1:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("mode,n", [("concurrent", 333), ("autoregressive", 130)])
+def test_eval_rollout_batched_vs_oracle(mode, n):
+    """many drones (partial tiles, several tiles per CTA), shared tables through the index, random policy"""
+    import bench as B
+    EV, R, O, golden_params = _eval_mods()
+    g = load_golden("eval_rand.npz")
+    h, dt, steps = 10, 0.1, 40
+    params = B.default_init("quad", h, seed=3, mode=mode)
+    spec = R.RolloutSpec.quad_concurrent(h, dt) if mode == "concurrent" else R.RolloutSpec.quad_recurrent(mode, h, dt)
+    tabs = torch.tensor(np.stack([g["gentle_table"][:100], g["tight_table"][:100], g["fast_reset_table"][:100]]),
+                        dtype=torch.float32)
+    gen = torch.Generator().manual_seed(n)
+    index = torch.randint(0, 3, (n,), generator=gen, dtype=torch.int32)
+    init = torch.zeros(n, 12)
+    init[:, :3] = tabs[index.long(), 0, :3] + 0.05 * torch.randn(n, 3, generator=gen)
+    init[:, 6:9] = 0.1 * torch.randn(n, 3, generator=gen)
+    for test_time in (0, 1):
+        want = O.eval_follow_tables(params, tabs[index.long()], init, steps, h, dt, 0.5, 0.4, test_time)
+        ev = EV.TableEvaluator(spec, n, "cuda:0")
+        out = ev.follow(R.flatten_params(params).cuda(), tabs.cuda(), init_states=init.cuda(),
+                        table_index=index.cuda(), steps=steps, thresh_div=0.5, thresh_stable=0.4, test_time=test_time)
+        # a threshold crossing can flip for a drone that sits within rounding of it: compare the drones whose
+        # decisions agree (all but at most a handful) and require the step counts to agree for >= 98 %
+        same = (out["n_steps"].cpu() == want["n_steps"].to(torch.int32))
+        assert float(same.float().mean()) >= 0.98
+        d = (out["states"].cpu() - want["states"]).abs().amax(dim=(1, 2))
+        assert float((d[same] <= 2e-3).float().mean()) >= 0.98
+        k = int(want["n_steps"].min().clamp(max=5))
+        assert float((out["states"].cpu()[:, :k + 1] - want["states"][:, :k + 1]).abs().max()) <= 1e-4
+        stats = EV.eval_statistics(out["div"], out["n_steps"], 0.5)
+        assert len(stats) == 6 and np.isfinite(stats[4])
