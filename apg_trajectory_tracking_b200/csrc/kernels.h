@@ -38,6 +38,15 @@ cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const fl
                                 float* states_out, float* div_out, float* actions_out, int* n_steps_out, int grid,
                                 cudaStream_t st);
 
+// learnt residual quadrotor dynamics (learnt_kernels.cu)
+int learnt_grid(int n, int sms);
+size_t learnt_partials_floats(int n, int sms);
+cudaError_t launch_learnt_fwd(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
+                              float* out, int sms, cudaStream_t st);
+cudaError_t launch_learnt_adj(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
+                              const float* g, float* gs, float* ga, float* grad_params, float* partials, int sms,
+                              cudaStream_t st);
+
 // data formats on the input side (prep_kernels.cu)
 cudaError_t launch_prepare_quad(const float* states, const float* ref, int n, int L, float* in_state, float* cur_out,
                                 float* in_ref, float* ref_out, cudaStream_t st);

@@ -60,6 +60,31 @@ class TrainBase:
         self.fused = T.ModuleRollout(self.net, spec, self.device)
         self.optimizer_controller = optim.SGD(self.net.parameters(), lr=self.learning_rate_controller, momentum=0.9)
 
+    def init_dynamics_optimizer(self, l2_lambda=0.0):
+        """the SGD over the learnt dynamics' parameters of the reference (train_base.py:144-150)"""
+        self.l2_lambda = l2_lambda
+        self.optimizer_dynamics = optim.SGD(self.train_dynamics.parameters(), lr=self.learning_rate_dynamics,
+                                            momentum=0.9)
+
+    def train_dynamics_model(self, current_state, action_seq):
+        """One dynamics-fitting step (train_base.py:160-186): squared difference between the learnt step (one fused
+        CUDA kernel forward, one adjoint kernel backward) and the evaluation dynamics' step on the first action,
+        + l2_lambda * (norms of the residual MLP's tensors)."""
+        self.optimizer_dynamics.zero_grad()
+        next_d1 = self.train_dynamics(current_state, action_seq[:, 0], dt=self.delta_t)
+        with torch.no_grad():
+            next_d2 = self.eval_dynamics(current_state, action_seq[:, 0], dt=self.delta_t)
+        l2_loss = 0
+        if getattr(self, "l2_lambda", 0) > 0:
+            d = self.train_dynamics
+            l2_loss = (torch.norm(d.linear_state_2.weight) + torch.norm(d.linear_state_2.bias) +
+                       torch.norm(d.linear_state_1.weight) + torch.norm(d.linear_state_1.bias))
+        loss = torch.sum((next_d1 - next_d2) ** 2) + getattr(self, "l2_lambda", 0) * l2_loss
+        loss.backward()
+        self.optimizer_dynamics.step()
+        self.results_dict["loss_dyn_per_step"].append(loss.item())
+        return loss
+
     def train_controller_model(self, current_state, action_seq, in_ref_state, ref_states):
         """implemented in the sub classes (un-fused path: the caller already evaluated the policy)"""
         raise NotImplementedError

@@ -126,6 +126,23 @@ int apg_eval_rollout(const apg_config* cfg, const float* params, const float* ta
                      float thresh_stable, int test_time, void* workspace, float* states_out, float* div_out,
                      float* actions_out, int* n_steps_out, void* stream);
 
+/* ---- learnt residual quadrotor dynamics: LearntDynamics.forward
+ * (neural_control/dynamics/quad_dynamics_trained.py:10-69) = simulate_quadrotor(linear_at @ action, state, dt) +
+ * linear_state_2(relu(linear_state_1([state, linear_at @ action]))), and what autograd records for it: the
+ * vector-Jacobian products w.r.t. state, action and the flat parameter vector (named_parameters() order:
+ * linear_at 16 | mass 1 | torch_inertia_vector 3 | torch_kinv_vector 3 | linear_state_1.weight 1024 | .bias 64 |
+ * linear_state_2.weight 768 | .bias 12 = apg_learnt_num_params() = 1891).  `phys`: the simulator constants of the
+ * construction-time parameters (the reference never refreshes its derived kinv / inertia matrices, :47-48).
+ * n rows; grad_state / grad_action / grad_params may be NULL; workspace: apg_learnt_workspace_bytes(n) bytes,
+ * 16-byte aligned (per-block partial gradients, reduced in fixed order). */
+int apg_learnt_num_params(void);
+size_t apg_learnt_workspace_bytes(int n);
+int apg_learnt_step(const float* params, const float* phys, const float* state, const float* action, float dt, int n,
+                    float* out, void* stream);
+int apg_learnt_step_adjoint(const float* params, const float* phys, const float* state, const float* action, float dt,
+                            int n, const float* grad_out, float* grad_state, float* grad_action, float* grad_params,
+                            void* workspace, void* stream);
+
 int apg_sm_count(void);
 int apg_version(void);
 const char* apg_error_string(int code);

@@ -66,7 +66,7 @@ def quad_step(state, action, dt, cfg=QUAD_CFG):
     px, py, pz, roll, pitch, yaw, vx, vy, vz, wx, wy, wz = _cols(state)
     a0, a1, a2, a3 = _cols(action)
     dt_ = float(dt)
-    Jx, Jy, Jz = quad_inertia(cfg)
+    Jx, Jy, Jz = cfg["inertia_vector"] if "inertia_vector" in cfg else quad_inertia(cfg)
     Kx, Ky, Kz = cfg["kinv_ang_vel_tau"]
     gx, gy, gz = cfg["gravity"]
     tdx, tdy, tdz = cfg["translational_drag"]
@@ -516,3 +516,34 @@ def eval_statistics(div, n_steps, thresh_div):
     full = d[stable == n_steps[-1]]              # max_steps_stable = len(reference_traj) of the LAST run
     return stable.mean(), stable.std(), full.mean() if len(full) else float("nan"), \
         full.std() if len(full) else float("nan"), d.mean(), d.std()
+
+
+# --------------------------------------------------------------------------------------------
+# N3  learnt residual dynamics of the quadrotor (neural_control/dynamics/quad_dynamics_trained.py:10-69):
+#     next = simulate_quadrotor(linear_at @ action, state, dt) + linear_state_2(relu(linear_state_1([state, at])))
+#     with mass / inertia vector / kinv vector as (differentiable) parameters of the simulator.
+#     lparams in named_parameters() order: linear_at (4,4), mass (1,), torch_inertia_vector (3,),
+#     torch_kinv_vector (3,), linear_state_1.weight (64,16), .bias (64,), linear_state_2.weight (12,64), .bias (12,)
+# --------------------------------------------------------------------------------------------
+def learnt_quad_step(lparams, state, action, dt, cfg=QUAD_CFG):
+    lin_at, mass, jvec, kvec, w1, b1, w2, b2 = lparams
+    at = action @ lin_at.t()                                              # :59-61
+    c = dict(cfg)
+    c["mass"] = mass[0]
+    c["inertia_vector"] = (jvec[0], jvec[1], jvec[2])
+    c["kinv_ang_vel_tau"] = (kvec[0], kvec[1], kvec[2])
+    new_state = quad_step(state, at, dt, c)                               # :63
+    x = torch.cat((state, at), dim=1)                                     # :51-56
+    added = torch.relu(x @ w1.t() + b1) @ w2.t() + b2
+    return new_state + added                                              # :65-66
+
+
+def learnt_dynamics_loss(lparams, state, action, target_next, dt, l2_lambda=0.0, cfg=QUAD_CFG):
+    """TrainBase.train_dynamics_model (scripts/train_base.py:160-186): sum of squared differences between the learnt
+    step and the target dynamics' step on the first action, + l2_lambda * (norms of the residual MLP tensors)."""
+    nxt = learnt_quad_step(lparams, state, action, dt, cfg)
+    loss = torch.sum((nxt - target_next) ** 2)
+    if l2_lambda > 0:
+        w1, b1, w2, b2 = lparams[4:]
+        loss = loss + l2_lambda * (torch.norm(w2) + torch.norm(b2) + torch.norm(w1) + torch.norm(b1))
+    return loss

@@ -112,17 +112,73 @@ def make_eval_golden(args):
     np.savez_compressed(os.path.join(args.out, "eval_rand.npz"), **out)
 
 
+def make_learnt_golden(args):
+    """learnt_dyn.npz: LearntDynamics.forward (neural_control/dynamics/quad_dynamics_trained.py) of the unmodified
+    reference with seeded NON-zero parameters (the reference initialises the residual MLP with zeros, which leaves it
+    without gradient forever), its vector-Jacobian products w.r.t. state, action and every parameter, and one
+    TrainBase.train_dynamics_model loss / gradient against a FlightmareDynamics with modified parameters."""
+    import torch
+    from neural_control.dynamics.quad_dynamics_trained import LearntDynamics
+    from neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    torch.manual_seed(7)
+    out = {}
+    for tag, drag in (("a", [0.0, 0.0, 0.0]), ("b", [0.02, -0.01, 0.03])):
+        d1 = LearntDynamics({"rotational_drag": drag} if tag == "b" else {})
+        with torch.no_grad():
+            d1.linear_at.add_(0.1 * torch.randn(4, 4))
+            d1.linear_state_1.weight.copy_(0.3 * torch.randn(64, 16))
+            d1.linear_state_1.bias.copy_(0.1 * torch.randn(64))
+            d1.linear_state_2.weight.copy_(0.1 * torch.randn(12, 64))
+            d1.linear_state_2.bias.copy_(0.05 * torch.randn(12))
+        n, dt = 37, 0.1 if tag == "a" else 0.05
+        s = (0.4 * torch.randn(n, 12)).requires_grad_(True)
+        a = torch.rand(n, 4).requires_grad_(True)
+        cot = torch.randn(n, 12)
+        o = d1(s, a, dt)
+        names = [k for k, _ in d1.named_parameters()]
+        grads = torch.autograd.grad(o, [s, a] + [p for _, p in d1.named_parameters()], cot, allow_unused=True)
+        out.update({f"{tag}_state": s, f"{tag}_action": a, f"{tag}_cot": cot, f"{tag}_out": o, f"{tag}_dt": dt,
+                    f"{tag}_gstate": grads[0], f"{tag}_gaction": grads[1],
+                    f"{tag}_rot_drag": np.array(drag, dtype=np.float64)})
+        for i, (k, p) in enumerate(d1.named_parameters()):
+            out[f"{tag}_param_{i}"] = p
+            out[f"{tag}_gparam_{i}"] = grads[2 + i] if grads[2 + i] is not None else torch.zeros_like(p)
+        # train_dynamics_model (train_base.py:160-186) body: loss + gradient, l2_lambda = 0.01
+        d2 = FlightmareDynamics(modified_params={"translational_drag": [0.3, 0.3, 0.3]})
+        for p in d1.parameters():
+            p.grad = None
+        n1 = d1(s.detach(), a.detach(), dt=dt)
+        n2 = d2(s.detach(), a.detach(), dt=dt)
+        l2 = (torch.norm(d1.linear_state_2.weight) + torch.norm(d1.linear_state_2.bias) +
+              torch.norm(d1.linear_state_1.weight) + torch.norm(d1.linear_state_1.bias))
+        loss = torch.sum((n1 - n2) ** 2) + 0.01 * l2
+        loss.backward()
+        out[f"{tag}_dyn_target"] = n2
+        out[f"{tag}_dyn_loss"] = loss
+        for i, (k, p) in enumerate(d1.named_parameters()):
+            out[f"{tag}_dyn_gparam_{i}"] = p.grad if p.grad is not None else torch.zeros_like(p)
+        print("learnt", tag, "loss %.6f" % float(loss), "max |g kinv| %.4g" % float(out[f"{tag}_gparam_3"].abs().max()),
+              "max |g mass| %.3g" % float(out[f"{tag}_gparam_1"].abs().max()),
+              "max |g J| %.3g" % float(out[f"{tag}_gparam_2"].abs().max()))
+    out["param_names"] = np.array(names)
+    np.savez_compressed(os.path.join(args.out, "learnt_dyn.npz"), **npify(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
     ap.add_argument("--only-prep", action="store_true", help="only (re)generate prep_data.npz")
     ap.add_argument("--only-eval", action="store_true", help="only (re)generate eval_rand.npz")
+    ap.add_argument("--only-learnt", action="store_true", help="only (re)generate learnt_dyn.npz")
     args = ap.parse_args()
     import_reference(args.ref)
     os.makedirs(args.out, exist_ok=True)
     if args.only_eval:
         make_eval_golden(args)
+        return
+    if args.only_learnt:
+        make_learnt_golden(args)
         return
 
     import torch

@@ -1,0 +1,57 @@
+// Test-only harness: the per-drone learnt-dynamics math (csrc/learnt_math.cuh) on the CPU, with the parameter
+// gradient assembled from the per-drone factors exactly like the adjoint kernel does.  Not part of the product.
+#include <vector>
+#include "learnt_math.cuh"
+
+using namespace apg;
+using Y = LearntLayout;
+
+template <typename T>
+static void run_fwd(const T* P, const float* pc, const T* s, const T* a, T dt, int n, T* out) {
+  std::vector<T> h(Y::HD);
+  for (int d = 0; d < n; ++d) {
+    T at[4];
+    LearntQuad<T>::forward(P, pc, s + d * 12, a + d * 4, dt, out + d * 12, at, h.data(), 1);
+  }
+}
+
+template <typename T>
+static void run_adj(const T* P, const float* pc, const T* s, const T* a, T dt, int n, const T* g, T* gs, T* ga,
+                    T* gP) {
+  std::vector<T> h(Y::HD), dh(Y::HD);
+  for (int i = 0; i < Y::NP; ++i) gP[i] = 0;
+  for (int d = 0; d < n; ++d) {
+    T at[4], out[12], gat[4], dk[3], dj[3];
+    const T* sd = s + d * 12;
+    const T* ad = a + d * 4;
+    const T* gd = g + d * 12;
+    LearntQuad<T>::forward(P, pc, sd, ad, dt, out, at, h.data(), 1);
+    LearntQuad<T>::adjoint(P, pc, sd, ad, at, h.data(), 1, dt, gd, gs + d * 12, ga + d * 4, dh.data(), gat, dk, dj);
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) gP[Y::O_LAT + r * 4 + c] += gat[r] * ad[c];
+    for (int i = 0; i < 3; ++i) { gP[Y::O_K + i] += dk[i]; gP[Y::O_J + i] += dj[i]; }
+    for (int j = 0; j < Y::HD; ++j) {
+      for (int k = 0; k < 12; ++k) gP[Y::O_W1 + j * Y::XD + k] += dh[j] * sd[k];
+      for (int k = 0; k < 4; ++k) gP[Y::O_W1 + j * Y::XD + 12 + k] += dh[j] * at[k];
+      gP[Y::O_B1 + j] += dh[j];
+    }
+    for (int i = 0; i < 12; ++i) {
+      for (int j = 0; j < Y::HD; ++j) gP[Y::O_W2 + i * Y::HD + j] += gd[i] * h[j];
+      gP[Y::O_B2 + i] += gd[i];
+    }
+  }
+}
+
+extern "C" int hc_learnt_num_params() { return Y::NP; }
+extern "C" void hc_learnt_fwd_f64(const double* P, const float* pc, const double* s, const double* a, double dt, int n,
+                                  double* out) { run_fwd<double>(P, pc, s, a, dt, n, out); }
+extern "C" void hc_learnt_fwd_f32(const float* P, const float* pc, const float* s, const float* a, float dt, int n,
+                                  float* out) { run_fwd<float>(P, pc, s, a, dt, n, out); }
+extern "C" void hc_learnt_adj_f64(const double* P, const float* pc, const double* s, const double* a, double dt, int n,
+                                  const double* g, double* gs, double* ga, double* gP) {
+  run_adj<double>(P, pc, s, a, dt, n, g, gs, ga, gP);
+}
+extern "C" void hc_learnt_adj_f32(const float* P, const float* pc, const float* s, const float* a, float dt, int n,
+                                  const float* g, float* gs, float* ga, float* gP) {
+  run_adj<float>(P, pc, s, a, dt, n, g, gs, ga, gP);
+}

@@ -172,3 +172,18 @@ def test_input_side_ops_refuse_cpu_tensors():
         PR.sample_windows(torch.zeros(100, 9), 3, 10, 20)
     with pytest.raises(ApgError):
         PR.poly_reference(torch.zeros(4, 3, 6), 10, 0.1)
+
+
+def test_learnt_dynamics_mirror_has_reference_parameters_and_refuses_cpu(capi):
+    from neural_control.dynamics.quad_dynamics_trained import LearntDynamics
+    from apg_trajectory_tracking_b200._capi import ApgError
+    g = load_golden("learnt_dyn.npz")
+    d = LearntDynamics()
+    names = [n for n, _ in d.named_parameters()]
+    assert names == [str(x) for x in g["param_names"]]
+    for i, (_, p) in enumerate(d.named_parameters()):
+        assert tuple(p.shape) == g[f"a_param_{i}"].shape
+    assert sum(p.numel() for p in d.parameters()) == capi.lib().apg_learnt_num_params() == 1891
+    assert torch.equal(d.linear_at.detach(), torch.eye(4)) and float(d.linear_state_2.weight.abs().max()) == 0.0
+    with pytest.raises(ApgError):
+        d(torch.zeros(2, 12), torch.zeros(2, 4), 0.1)

@@ -1,0 +1,93 @@
+"""Per-drone math of the learnt residual quadrotor dynamics (csrc/learnt_math.cuh) compiled with g++: forward against
+the golden outputs of the reference's LearntDynamics, hand-written adjoint (state, action, every parameter) against
+the reference's autograd (tests/golden/learnt_dyn.npz) and against fp64 autograd of the oracle."""
+import ctypes
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import apg_oracle as O
+from tests.helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("apg_params", os.path.join(ROOT, "apg_trajectory_tracking_b200",
+                                                                             "params.py"))
+P = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(P)
+
+
+@pytest.fixture(scope="module")
+def hl(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostcheck_learnt") / "libhostcheck_learnt.so"
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck_learnt.cpp")
+    inc = os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", "-std=c++17", "-ffp-contract=off", "-I", inc,
+                           src, "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _case(tag, dtype):
+    g = load_golden("learnt_dyn.npz")
+    flat = np.concatenate([np.asarray(g[f"{tag}_param_{i}"]).reshape(-1) for i in range(8)]).astype(dtype)
+    pc = P.PHYS["quad"]({"rotational_drag": [float(x) for x in g[f"{tag}_rot_drag"]]})
+    arr = lambda k: np.ascontiguousarray(g[f"{tag}_{k}"], dtype=dtype)          # noqa: E731
+    return g, flat, pc, arr("state"), arr("action"), arr("cot"), float(g[f"{tag}_dt"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_forward_and_adjoint_match_reference_fp32(hl, tag):
+    g, flat, pc, s, a, cot, dt = _case(tag, np.float32)
+    assert hl.hc_learnt_num_params() == flat.size == 1891
+    n = s.shape[0]
+    out = np.zeros_like(s)
+    hl.hc_learnt_fwd_f32(_p(flat), _p(pc), _p(s), _p(a), ctypes.c_float(dt), n, _p(out))
+    assert np.abs(out - g[f"{tag}_out"]).max() <= 5e-6 * np.abs(g[f"{tag}_out"]).max()
+    gs, ga, gp = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    hl.hc_learnt_adj_f32(_p(flat), _p(pc), _p(s), _p(a), ctypes.c_float(dt), n, _p(cot), _p(gs), _p(ga), _p(gp))
+    assert np.abs(gs - g[f"{tag}_gstate"]).max() <= 2e-5 * np.abs(g[f"{tag}_gstate"]).max()
+    assert np.abs(ga - g[f"{tag}_gaction"]).max() <= 2e-5 * np.abs(g[f"{tag}_gaction"]).max()
+    want = np.concatenate([np.asarray(g[f"{tag}_gparam_{i}"]).reshape(-1) for i in range(8)])
+    off = np.cumsum([0] + [np.asarray(g[f"{tag}_param_{i}"]).size for i in range(8)])
+    scale = np.abs(want).max()
+    for i in range(8):
+        got_i, want_i = gp[off[i]:off[i + 1]], want[off[i]:off[i + 1]]
+        if i == 1 or (i == 2 and np.abs(g[f"{tag}_rot_drag"]).max() == 0):
+            assert np.abs(got_i).max() == 0.0 and np.abs(want_i).max() <= 1e-4       # analytic zero vs rounding noise
+        else:
+            assert np.abs(got_i - want_i).max() <= 5e-5 * max(np.abs(want_i).max(), 1e-3 * scale), i
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_adjoint_matches_oracle_autograd_fp64(hl, tag):
+    g, flat, pc, s, a, cot, dt = _case(tag, np.float64)
+    n = s.shape[0]
+    gs, ga, gp = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    hl.hc_learnt_adj_f64(_p(flat), _p(pc), _p(s), _p(a), ctypes.c_double(dt), n, _p(cot), _p(gs), _p(ga), _p(gp))
+    lparams = [torch.tensor(np.asarray(g[f"{tag}_param_{i}"]), dtype=torch.float64, requires_grad=True)
+               for i in range(8)]
+    # the harness reads the simulator constants as fp32 (like the kernels): give the oracle the same rounded values
+    cfg = dict(O.QUAD_CFG, rotational_drag=tuple(float(np.float32(x)) for x in g[f"{tag}_rot_drag"]))
+    with torch.no_grad():
+        lparams[2].copy_(torch.tensor([float(pc[P_J]) for P_J in (1, 2, 3)], dtype=torch.float64))
+        lparams[3].copy_(torch.tensor([float(pc[k]) for k in (4, 5, 6)], dtype=torch.float64))
+    ts, ta = torch.tensor(s, requires_grad=True), torch.tensor(a, requires_grad=True)
+    out = O.learnt_quad_step(lparams, ts, ta, dt, cfg)
+    grads = torch.autograd.grad(out, [ts, ta] + lparams, torch.tensor(cot), allow_unused=True)
+    assert np.abs(gs - grads[0].numpy()).max() <= 1e-9 * np.abs(gs).max()
+    assert np.abs(ga - grads[1].numpy()).max() <= 1e-9 * np.abs(ga).max()
+    off = np.cumsum([0] + [p.numel() for p in lparams])
+    scale = max(float(x.abs().max()) for x in grads[2:] if x is not None)
+    for i in range(8):
+        want = grads[2 + i].numpy().reshape(-1)
+        tol = 1e-9 * max(np.abs(want).max(), 1e-3 * scale)
+        if i in (1, 2):
+            tol = 1e-6 * scale      # mass / inertia: autograd's cancelling terms leave fp64 rounding noise
+        assert np.abs(gp[off[i]:off[i + 1]] - want).max() <= tol, i

@@ -183,3 +183,47 @@ def test_eval_follow_tables_is_batched_consistently():
         one = O.eval_follow_tables(params, tables[i:i + 1], init[i:i + 1], 40, 10, 0.1, 0.8, 1.0, 1)
         assert int(one["n_steps"][0]) == int(both["n_steps"][i])
         assert torch.allclose(one["states"][0], both["states"][i], atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N3: learnt residual quadrotor dynamics, pinned on the reference's LearntDynamics (forward + autograd)
+# ---------------------------------------------------------------------------------------------------------------
+def _learnt_case(tag):
+    g = load_golden("learnt_dyn.npz")
+    lparams = [torch.tensor(g[f"{tag}_param_{i}"], requires_grad=True) for i in range(8)]
+    cfg = dict(O.QUAD_CFG, rotational_drag=tuple(float(x) for x in g[f"{tag}_rot_drag"]))
+    return g, lparams, cfg
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_learnt_dynamics_forward_and_vjp_match_reference(tag):
+    g, lparams, cfg = _learnt_case(tag)
+    s, a = t(g[f"{tag}_state"]).requires_grad_(True), t(g[f"{tag}_action"]).requires_grad_(True)
+    out = O.learnt_quad_step(lparams, s, a, float(g[f"{tag}_dt"]), cfg)
+    assert max_rel_to_scale(out, g[f"{tag}_out"]) <= 2e-6
+    grads = torch.autograd.grad(out, [s, a] + lparams, t(g[f"{tag}_cot"]), allow_unused=True)
+    assert max_rel_to_scale(grads[0], g[f"{tag}_gstate"]) <= 1e-5
+    assert max_rel_to_scale(grads[1], g[f"{tag}_gaction"]) <= 1e-5
+    scale = max(float(np.abs(g[f"{tag}_gparam_{i}"]).max()) for i in range(8))
+    for i in range(8):
+        want = g[f"{tag}_gparam_{i}"]
+        got = grads[2 + i] if grads[2 + i] is not None else torch.zeros_like(lparams[i])
+        if i in (1, 2) and float(np.abs(g[f"{tag}_rot_drag"]).max()) == 0.0:
+            # mass / inertia cancel analytically; the reference's autograd leaves rounding noise (<= 3e-5 here)
+            assert float(got.abs().max()) <= 1e-4 and float(np.abs(want).max()) <= 1e-4
+        elif i == 1:
+            assert float(got.abs().max()) <= 1e-4 and float(np.abs(want).max()) <= 1e-4
+        else:
+            assert float((got - t(want)).abs().max()) <= 2e-5 * max(float(np.abs(want).max()), 1e-3 * scale), i
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_learnt_dynamics_training_loss_matches_reference(tag):
+    g, lparams, cfg = _learnt_case(tag)
+    loss = O.learnt_dynamics_loss(lparams, t(g[f"{tag}_state"]), t(g[f"{tag}_action"]), t(g[f"{tag}_dyn_target"]),
+                                  float(g[f"{tag}_dt"]), 0.01, cfg)
+    assert abs(float(loss) - float(g[f"{tag}_dyn_loss"])) <= 1e-5 * abs(float(g[f"{tag}_dyn_loss"]))
+    grads = torch.autograd.grad(loss, lparams, allow_unused=True)
+    for i in (0, 3, 4, 5, 6, 7):
+        want = g[f"{tag}_dyn_gparam_{i}"]
+        assert float((grads[i] - t(want)).abs().max()) <= 2e-5 * max(float(np.abs(want).max()), 1e-3), i

@@ -237,3 +237,81 @@ def test_eval_rollout_batched_vs_oracle(mode, n):
         assert float((out["states"].cpu()[:, :k + 1] - want["states"][:, :k + 1]).abs().max()) <= 1e-4
         stats = EV.eval_statistics(out["div"], out["n_steps"], 0.5)
         assert len(stats) == 6 and np.isfinite(stats[4])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N3: learnt residual quadrotor dynamics (csrc/learnt_kernels.cu) vs the reference's LearntDynamics and the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _learnt_module(g, tag):
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_trained import LearntDynamics
+    d = LearntDynamics({"rotational_drag": [float(x) for x in g[f"{tag}_rot_drag"]]})
+    with torch.no_grad():
+        for i, (_, p) in enumerate(d.named_parameters()):
+            if i not in (1, 2, 3):                 # mass / inertia / kinv keep their construction-time values
+                p.copy_(torch.tensor(g[f"{tag}_param_{i}"]))
+    return d.cuda()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_learnt_dynamics_matches_reference(tag):
+    g = load_golden("learnt_dyn.npz")
+    d = _learnt_module(g, tag)
+    s = torch.tensor(g[f"{tag}_state"]).cuda().requires_grad_(True)
+    a = torch.tensor(g[f"{tag}_action"]).cuda().requires_grad_(True)
+    out = d(s, a, float(g[f"{tag}_dt"]))
+    assert _close(out, g[f"{tag}_out"], 5e-6)
+    (out * torch.tensor(g[f"{tag}_cot"]).cuda()).sum().backward()
+    assert _close(s.grad, g[f"{tag}_gstate"], 2e-5) and _close(a.grad, g[f"{tag}_gaction"], 2e-5)
+    scale = max(float(np.abs(g[f"{tag}_gparam_{i}"]).max()) for i in range(8))
+    for i, (name, p) in enumerate(d.named_parameters()):
+        want = torch.tensor(g[f"{tag}_gparam_{i}"])
+        if i == 1 or (i == 2 and float(np.abs(g[f"{tag}_rot_drag"]).max()) == 0.0):
+            assert float(p.grad.abs().max()) == 0.0                     # analytic zero (reference: rounding noise)
+        else:
+            err = float((p.grad.cpu() - want).abs().max())
+            assert err <= 5e-5 * max(float(want.abs().max()), 1e-3 * scale), (name, err)
+
+
+def test_learnt_dynamics_many_tiles_vs_oracle_and_training_step():
+    """N = 5000 (several 128-drone tiles per block, ragged tail) against fp32 autograd of the oracle; then three
+    train_dynamics_model steps of the trainer against the same steps on the oracle"""
+    from oracle import apg_oracle as O
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.scripts.train_base import TrainBase
+    g = load_golden("learnt_dyn.npz")
+    d = _learnt_module(g, "b")
+    gen = torch.Generator().manual_seed(0)
+    n, dt = 5000, 0.05
+    s, a, cot = 0.4 * torch.randn(n, 12, generator=gen), torch.rand(n, 4, generator=gen), torch.randn(n, 12, generator=gen)
+    lparams = [p.detach().cpu().clone().requires_grad_(True) for _, p in d.named_parameters()]
+    cfg = dict(O.QUAD_CFG, rotational_drag=tuple(float(x) for x in g["b_rot_drag"]))
+    so, ao = s.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    want = O.learnt_quad_step(lparams, so, ao, dt, cfg)
+    wg = torch.autograd.grad(want, [so, ao] + lparams, cot, allow_unused=True)
+    sc, ac = s.cuda().requires_grad_(True), a.cuda().requires_grad_(True)
+    out = d(sc, ac, dt)
+    assert _close(out, want.detach(), 5e-6)
+    (out * cot.cuda()).sum().backward()
+    assert _close(sc.grad, wg[0], 2e-5) and _close(ac.grad, wg[1], 2e-5)
+    for i, (name, p) in enumerate(d.named_parameters()):
+        if i in (1, 2):
+            continue
+        assert rel_err(p.grad, wg[2 + i]) <= 1e-4, name
+    # trainer step
+    tr = TrainBase(d, FlightmareDynamics({"translational_drag": [0.3, 0.3, 0.3]}), delta_t=dt,
+                   learning_rate_dynamics=1e-3)
+    tr.init_dynamics_optimizer(l2_lambda=0.01)
+    d.zero_grad()
+    tgt = O.quad_step(s, a, dt, dict(O.QUAD_CFG, translational_drag=(0.3, 0.3, 0.3)))
+    bufs = [None] * 8
+    for it in range(3):
+        loss = tr.train_dynamics_model(s.cuda(), a.cuda()[:, None, :])
+        ol = O.learnt_dynamics_loss(lparams, s, a, tgt, dt, 0.01, cfg)
+        og = torch.autograd.grad(ol, lparams, allow_unused=True)
+        assert abs(float(loss) - float(ol)) <= 2e-5 * abs(float(ol)), (it, float(loss), float(ol))
+        with torch.no_grad():
+            for i, p in enumerate(lparams):
+                gi = og[i] if (og[i] is not None and i not in (1, 2)) else torch.zeros_like(p)
+                bufs[i] = gi.clone() if bufs[i] is None else bufs[i] * 0.9 + gi
+                if i not in (1, 2, 3):             # the simulator ignores updates of these (construction-time values)
+                    p -= 1e-3 * bufs[i]
