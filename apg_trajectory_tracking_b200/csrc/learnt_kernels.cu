@@ -19,22 +19,8 @@ namespace {
 using Y = LearntLayout;
 constexpr int LT = 128;            // threads per block = drones per tile
 constexpr int LP = LT + 1;         // padded factor-row length
-// factor rows of the adjoint kernel
-constexpr int R_G = 0, R_H = R_G + 12, R_DH = R_H + 64, R_X = R_DH + 64, R_GAT = R_X + 16, R_A = R_GAT + 4,
-              R_DK = R_A + 4, R_DJ = R_DK + 3, R_ONE = R_DJ + 3, R_TOTAL = R_ONE + 1;     // 171 rows
 constexpr int EPT = (Y::NP + LT - 1) / LT;                                                  // entries per thread: 15
-
-// entry e of the flat parameter gradient = dot(row ra, row rb) over the drones of the tile
-__device__ __forceinline__ void entry_rows(int e, int* ra, int* rb) {
-  if (e < Y::O_MASS) { *ra = R_GAT + e / 4; *rb = R_A + (e & 3); }                                  // linear_at[r][c]
-  else if (e < Y::O_J) { *ra = -1; *rb = -1; }                                                      // mass: 0
-  else if (e < Y::O_K) { *ra = R_DJ + (e - Y::O_J); *rb = R_ONE; }
-  else if (e < Y::O_W1) { *ra = R_DK + (e - Y::O_K); *rb = R_ONE; }
-  else if (e < Y::O_B1) { const int q = e - Y::O_W1; *ra = R_DH + q / Y::XD; *rb = R_X + q % Y::XD; }
-  else if (e < Y::O_W2) { *ra = R_DH + (e - Y::O_B1); *rb = R_ONE; }
-  else if (e < Y::O_B2) { const int q = e - Y::O_W2; *ra = R_G + q / Y::HD; *rb = R_H + q % Y::HD; }
-  else { *ra = R_G + (e - Y::O_B2); *rb = R_ONE; }
-}
+using namespace learnt_rows;
 }  // namespace
 
 __global__ void __launch_bounds__(LT) learnt_fwd_kernel(const float* __restrict__ params, const PhysConsts pc,
@@ -111,7 +97,7 @@ __global__ void __launch_bounds__(LT) learnt_adj_kernel(const float* __restrict_
       const int e = t + q * LT;
       if (e < Y::NP) {
         int ra, rb;
-        entry_rows(e, &ra, &rb);
+        learnt_entry_rows(e, &ra, &rb);
         if (ra >= 0) {
           const float* pa = sF + ra * LP;
           const float* pb = sF + rb * LP;

@@ -21,6 +21,26 @@ struct LearntLayout {
                        O_W2 = O_B1 + HD, O_B2 = O_W2 + SD * HD, NP = O_B2 + SD;      // 1891
 };
 
+// Factor rows the adjoint kernel leaves per drone (one shared-memory row per factor component) and the mapping from
+// a flat parameter-gradient entry to the two rows whose dot product over the drones it is.
+namespace learnt_rows {
+constexpr int R_G = 0, R_H = R_G + 12, R_DH = R_H + 64, R_X = R_DH + 64, R_GAT = R_X + 16, R_A = R_GAT + 4,
+              R_DK = R_A + 4, R_DJ = R_DK + 3, R_ONE = R_DJ + 3, R_TOTAL = R_ONE + 1;     // 171 rows
+}
+// entry e of the flat parameter gradient = dot(row ra, row rb) over the drones; ra < 0: identically zero (mass)
+APG_HD void learnt_entry_rows(int e, int* ra, int* rb) {
+  using Y = LearntLayout;
+  using namespace learnt_rows;
+  if (e < Y::O_MASS) { *ra = R_GAT + e / 4; *rb = R_A + (e & 3); }                                  // linear_at[r][c]
+  else if (e < Y::O_J) { *ra = -1; *rb = -1; }
+  else if (e < Y::O_K) { *ra = R_DJ + (e - Y::O_J); *rb = R_ONE; }
+  else if (e < Y::O_W1) { *ra = R_DK + (e - Y::O_K); *rb = R_ONE; }
+  else if (e < Y::O_B1) { const int q = e - Y::O_W1; *ra = R_DH + q / Y::XD; *rb = R_X + q % Y::XD; }
+  else if (e < Y::O_W2) { *ra = R_DH + (e - Y::O_B1); *rb = R_ONE; }
+  else if (e < Y::O_B2) { const int q = e - Y::O_W2; *ra = R_G + q / Y::HD; *rb = R_H + q % Y::HD; }
+  else { *ra = R_G + (e - Y::O_B2); *rb = R_ONE; }
+}
+
 template <typename T>
 struct LearntQuad {
   using Y = LearntLayout;

@@ -55,3 +55,37 @@ extern "C" void hc_learnt_adj_f32(const float* P, const float* pc, const float* 
                                   const float* g, float* gs, float* ga, float* gP) {
   run_adj<float>(P, pc, s, a, dt, n, g, gs, ga, gP);
 }
+
+// The adjoint KERNEL's data flow on the host: tiles of LT drones, per-drone factors written to rows of LP floats,
+// every parameter-gradient entry a dot product of two rows over the tile (learnt_entry_rows), summed over the tiles.
+extern "C" void hc_learnt_adj_tiled_f32(const float* P, const float* pc, const float* s, const float* a, float dt,
+                                        int n, const float* g, float* gs, float* ga, float* gP, int LT) {
+  using namespace learnt_rows;
+  const int LP = LT + 1;
+  std::vector<float> F((size_t)R_TOTAL * LP);
+  for (int i = 0; i < Y::NP; ++i) gP[i] = 0;
+  for (int base = 0; base < n; base += LT) {
+    const int valid = n - base < LT ? n - base : LT;
+    for (int t = 0; t < valid; ++t) {
+      const int d = base + t;
+      float at[4], o[12], gat[4], dk[3], dj[3];
+      LearntQuad<float>::forward(P, pc, s + d * 12, a + d * 4, dt, o, at, F.data() + R_H * LP + t, LP);
+      LearntQuad<float>::adjoint(P, pc, s + d * 12, a + d * 4, at, F.data() + R_H * LP + t, LP, dt, g + d * 12,
+                                 gs + d * 12, ga + d * 4, F.data() + R_DH * LP + t, gat, dk, dj);
+      for (int j = 0; j < 12; ++j) { F[(R_G + j) * LP + t] = g[d * 12 + j]; F[(R_X + j) * LP + t] = s[d * 12 + j]; }
+      for (int j = 0; j < 4; ++j) {
+        F[(R_X + 12 + j) * LP + t] = at[j]; F[(R_GAT + j) * LP + t] = gat[j]; F[(R_A + j) * LP + t] = a[d * 4 + j];
+      }
+      for (int j = 0; j < 3; ++j) { F[(R_DK + j) * LP + t] = dk[j]; F[(R_DJ + j) * LP + t] = dj[j]; }
+      F[R_ONE * LP + t] = 1.f;
+    }
+    for (int e = 0; e < Y::NP; ++e) {
+      int ra, rb;
+      learnt_entry_rows(e, &ra, &rb);
+      if (ra < 0) continue;
+      float v = 0.f;
+      for (int k = 0; k < valid; ++k) v = fmaf(F[ra * LP + k], F[rb * LP + k], v);
+      gP[e] += v;
+    }
+  }
+}

@@ -91,3 +91,21 @@ def test_adjoint_matches_oracle_autograd_fp64(hl, tag):
         if i in (1, 2):
             tol = 1e-6 * scale      # mass / inertia: autograd's cancelling terms leave fp64 rounding noise
         assert np.abs(gp[off[i]:off[i + 1]] - want).max() <= tol, i
+
+
+def test_tiled_factor_rows_reproduce_the_parameter_gradient(hl):
+    """the adjoint kernel's tile / factor-row / entry mapping (learnt_entry_rows) against the direct outer products"""
+    rng = np.random.default_rng(1)
+    g, flat, pc, _, _, _, dt = _case("b", np.float32)
+    n = 300                                               # 3 tiles of 128 with a ragged tail
+    s = (0.4 * rng.standard_normal((n, 12))).astype(np.float32)
+    a = rng.random((n, 4)).astype(np.float32)
+    cot = rng.standard_normal((n, 12)).astype(np.float32)
+    gs1, ga1, gp1 = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    gs2, ga2, gp2 = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    hl.hc_learnt_adj_f32(_p(flat), _p(pc), _p(s), _p(a), ctypes.c_float(dt), n, _p(cot), _p(gs1), _p(ga1), _p(gp1))
+    hl.hc_learnt_adj_tiled_f32(_p(flat), _p(pc), _p(s), _p(a), ctypes.c_float(dt), n, _p(cot), _p(gs2), _p(ga2),
+                               _p(gp2), 128)
+    assert np.array_equal(gs1, gs2) and np.array_equal(ga1, ga2)
+    assert np.abs(gp1 - gp2).max() <= 2e-5 * np.abs(gp1).max()
+    assert np.abs(gp2[16:17]).max() == 0.0 and np.abs(gp2).min() >= 0 and np.count_nonzero(gp2) > 1800

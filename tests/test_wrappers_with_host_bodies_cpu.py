@@ -1,0 +1,211 @@
+"""Argument marshalling of the Python wrappers of the newer C entry points (prepare.py, evaluate.py,
+quad_dynamics_trained.py) exercised WITHOUT a GPU: `_capi.lib()` is replaced by a stand-in whose entry points take
+the same ctypes arguments and run the SAME kernel bodies compiled for the host (tests/hostcheck/*.cpp) on the CPU
+tensors' memory.  A test double for the host-side plumbing only -- the kernels themselves are checked on the GPU by
+tests/test_zz_input_side_gpu.py."""
+import contextlib
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from apg_trajectory_tracking_b200 import _capi, evaluate as EV, ops, prepare as PR, rollout as R, synthetic as SY
+from apg_trajectory_tracking_b200.neural_control import dataset as DS
+from apg_trajectory_tracking_b200.neural_control.dynamics import quad_dynamics_trained as QT
+from oracle import apg_oracle as O
+from tests.helpers import golden_params, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp, name):
+    out = tmp / f"lib{name}.so"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", "-std=c++17", "-ffp-contract=off", "-I",
+                           os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "hostcheck", f"{name}.cpp"), "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+def _addr(x):
+    """ctypes argument (c_void_p / int / None) -> integer address or None"""
+    if x is None:
+        return None
+    return x.value if isinstance(x, ctypes.c_void_p) else int(x)
+
+
+def _f(x):
+    return x.value if isinstance(x, ctypes.c_float) else float(x)
+
+
+class _HostLib:
+    """same entry-point names and argument lists as libapg_b200.so for the input-side / evaluation / learnt calls"""
+
+    def __init__(self, tmp):
+        self.real = _capi.lib()
+        self.prep, self.ev, self.ln = _build(tmp, "hostcheck_prep"), _build(tmp, "hostcheck_eval"), \
+            _build(tmp, "hostcheck_learnt")
+        self.keep = []
+
+    def __getattr__(self, name):          # host-only queries go to the real library
+        return getattr(self.real, name)
+
+    @staticmethod
+    def _vp(a):
+        return ctypes.c_void_p(a)
+
+    def apg_prepare_quad(self, states, ref, n, rows, in_state, cur, in_ref, ref_out, stream):
+        self.prep.hc_prepare_quad(*[self._vp(_addr(x)) for x in (states, ref)], n, rows,
+                                  *[self._vp(_addr(x)) for x in (in_state, cur, in_ref, ref_out)])
+        return 0
+
+    def apg_prepare_wing(self, states, targets, mean, std, dt, h, n, in_state, cur, in_ref, ref_out, stream):
+        self.prep.hc_prepare_wing(*[self._vp(_addr(x)) for x in (states, targets, mean, std)], ctypes.c_float(_f(dt)),
+                                  h, n, *[self._vp(_addr(x)) for x in (in_state, cur, in_ref, ref_out)])
+        return 0
+
+    def apg_sample_windows(self, traj, rows, cols, L, stride, n, states, refs, stream):
+        if n > 0 and (n - 1) * stride + L > rows - 1:
+            return -1
+        self.prep.hc_sample_windows(self._vp(_addr(traj)), cols, L, stride, n, self._vp(_addr(states)),
+                                    self._vp(_addr(refs)))
+        return 0
+
+    def apg_poly_reference(self, coef, n, rows, t_first, dt, out, stream):
+        self.prep.hc_poly_reference(self._vp(_addr(coef)), n, rows, ctypes.c_float(_f(t_first)),
+                                    ctypes.c_float(_f(dt)), self._vp(_addr(out)))
+        return 0
+
+    def apg_eval_rollout(self, cfg, params, tables, index, n_tables, rows, init, steps, tdiv, tstab, test_time, ws,
+                         states, div, actions, n_steps, stream):
+        c = cfg._obj
+        n = c.n_drones
+        tmp = {k: np.zeros(s, np.float32) for k, s in (("states", (n, steps + 1, 12)), ("div", (n, steps)),
+                                                        ("actions", (n, steps, 4)))}
+        self.keep.append(tmp)
+        ptr = lambda given, k: self._vp(_addr(given) if given is not None else tmp[k].ctypes.data)   # noqa: E731
+        phys = (ctypes.c_float * 48)(*c.phys)
+        self.ev.hc_eval_rollout(self._vp(_addr(params)), c.horizon, c.out_dim, self._vp(_addr(tables)),
+                                self._vp(_addr(index)), rows, self._vp(_addr(init)), n, steps, ctypes.c_float(c.dt),
+                                phys, ctypes.c_float(_f(tdiv)), ctypes.c_float(_f(tstab)), int(test_time),
+                                ptr(states, "states"), ptr(div, "div"), ptr(actions, "actions"),
+                                self._vp(_addr(n_steps)))
+        return 0
+
+    def apg_learnt_step(self, params, phys, state, action, dt, n, out, stream):
+        self.ln.hc_learnt_fwd_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
+                                  ctypes.c_float(_f(dt)), n, self._vp(_addr(out)))
+        return 0
+
+    def apg_learnt_step_adjoint(self, params, phys, state, action, dt, n, g, gs, ga, gp, ws, stream):
+        self.ln.hc_learnt_adj_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
+                                  ctypes.c_float(_f(dt)), n, *[self._vp(_addr(x)) for x in (g, gs, ga, gp)])
+        return 0
+
+
+@pytest.fixture
+def hostlib(monkeypatch, tmp_path_factory):
+    lib = _HostLib(tmp_path_factory.mktemp("hostlibs"))
+    monkeypatch.setattr(_capi, "lib", lambda: lib)
+    for mod in (ops, PR, EV, QT):
+        monkeypatch.setattr(mod, "_require_cuda", lambda *a, **k: None, raising=False)
+        monkeypatch.setattr(mod, "_stream", lambda t: None, raising=False)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    return lib
+
+
+def test_prepare_wrappers(hostlib):
+    g = load_golden("prep_data.npz")
+    s, r = torch.tensor(g["quad_raw_states"]).float(), torch.tensor(g["quad_raw_refs"]).float()
+    out = PR.prepare_quad(s.clone(), r.clone())
+    assert torch.equal(out["cur"], torch.tensor(g["quad_states"])) and torch.equal(out["ref"], torch.tensor(g["quad_ref"]))
+    assert torch.equal(out["in_ref"], torch.tensor(g["quad_in_ref"]))
+    assert torch.allclose(out["in_state"], torch.tensor(g["quad_in_state"]), atol=1e-6)
+    s2, r2 = s.clone(), r.clone()
+    o2 = PR.prepare_quad(s2, r2, in_place=True)
+    assert o2["cur"] is s2 and o2["ref"] is r2 and torch.equal(s2, out["cur"]) and torch.equal(r2, out["ref"])
+    only = PR.prepare_quad(s.clone(), r.clone(), want=("in_ref",))
+    assert set(only) == {"in_ref"} and torch.equal(only["in_ref"], out["in_ref"])
+    # slices of larger buffers as outputs (what step_host passes)
+    big = {"cur": torch.zeros(20, 12), "ref": torch.zeros(20, 10, 9), "in_ref": torch.zeros(20, 10, 9),
+           "in_state": torch.zeros(20, 15)}
+    big["cur"][8:14], big["ref"][8:14] = s, r
+    sl = {k: v[8:14] for k, v in big.items()}
+    PR.prepare_quad(sl["cur"], sl["ref"], out=sl)
+    assert torch.equal(big["in_ref"][8:14], out["in_ref"]) and torch.equal(big["cur"][8:14], out["cur"])
+    assert float(big["in_ref"][:8].abs().sum() + big["in_ref"][14:].abs().sum()) == 0.0
+    w = PR.prepare_wing(torch.tensor(g["wing_raw_states"]).float(), torch.tensor(g["wing_targets"]).float(),
+                        g["wing_mean"], g["wing_std"], float(g["wing_dt"]), int(g["wing_h"]))
+    for k, name in (("in_state", "wing_in_state"), ("in_ref", "wing_in_ref"), ("ref", "wing_ref"), ("cur", "wing_states")):
+        assert torch.allclose(w[k], torch.tensor(g[name]), atol=2e-6 * float(np.abs(g[name]).max())), k
+    traj = torch.randn(101, 10)
+    st, rf = PR.sample_windows(traj, 4, 10, 20)
+    assert torch.equal(st[:, :9], traj[[0, 20, 40, 60], :9]) and torch.equal(rf[2, 3], traj[44, :9])
+    with pytest.raises(_capi.ApgError):
+        PR.sample_windows(traj, 10, 10, 20)
+    c = SY.quad_case(5, 10, 0.1, seed=1)
+    coef = torch.zeros(5, 3, 6)
+    coef[:, :, 1] = 1.0
+    rows = PR.poly_reference(coef, 10, 0.1)
+    assert torch.allclose(rows[:, :, 0], (torch.arange(10) + 1)[None] * 0.1) and float(rows[:, :, 6].min()) == 1.0
+    assert c["ref"].shape == rows.shape
+
+
+def test_table_evaluator_wrapper(hostlib):
+    g = load_golden("eval_rand.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    name = "fast_stop"
+    steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
+    ev = EV.TableEvaluator(R.RolloutSpec.quad_concurrent(int(h), dt), 1, "cpu")
+    out = ev.follow(R.flatten_params(params), torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None],
+                    steps=int(steps), thresh_div=tdiv, thresh_stable=tstab, test_time=int(test_time))
+    taken = len(g[f"{name}_div"])
+    assert int(out["n_steps"][0]) == taken                 # default init state: at rest on the first table point
+    assert np.abs(out["states"][0, :taken + 1].numpy() - g[f"{name}_states"]).max() <= 2e-5
+    assert np.abs(out["div"][0, :taken].numpy() - g[f"{name}_div"]).max() <= 2e-5
+    # table index + explicit initial states + a subset of outputs
+    tabs = torch.tensor(np.stack([g["gentle_table"][:100], g["tight_table"][:100]]), dtype=torch.float32)
+    index = torch.tensor([1, 0, 1], dtype=torch.int32)
+    init = torch.zeros(3, 12)
+    init[:, :3] = tabs[index.long(), 0, :3] + 0.02
+    ev3 = EV.TableEvaluator(R.RolloutSpec.quad_concurrent(10, 0.1), 3, "cpu")
+    out = ev3.follow(R.flatten_params(params), tabs, init_states=init, table_index=index, steps=30, thresh_div=0.6,
+                     thresh_stable=0.5, test_time=1, want=("div",))
+    want = O.eval_follow_tables(params, tabs[index.long()], init, 30, 10, 0.1, 0.6, 0.5, 1)
+    assert set(out) == {"div", "n_steps"} and torch.equal(out["n_steps"].long(), want["n_steps"])
+    assert float((out["div"] - want["div"]).abs().max()) <= 2e-5
+    stats = EV.eval_statistics(out["div"], out["n_steps"], 0.6)
+    ostats = O.eval_statistics(want["div"], want["n_steps"], 0.6)
+    assert np.allclose(np.array(stats), np.array(ostats), rtol=1e-4, equal_nan=True)
+
+
+def test_learnt_dynamics_wrapper_and_trainer_step(hostlib):
+    from apg_trajectory_tracking_b200.scripts.train_base import TrainBase
+    g = load_golden("learnt_dyn.npz")
+    d = QT.LearntDynamics({"rotational_drag": [float(x) for x in g["b_rot_drag"]]})
+    with torch.no_grad():
+        for i, (_, p) in enumerate(d.named_parameters()):
+            if i not in (1, 2, 3):
+                p.copy_(torch.tensor(g[f"b_param_{i}"]))
+    s = torch.tensor(g["b_state"]).requires_grad_(True)
+    a = torch.tensor(g["b_action"]).requires_grad_(True)
+    out = d(s, a, float(g["b_dt"]))
+    assert float((out.detach() - torch.tensor(g["b_out"])).abs().max()) <= 5e-6 * float(np.abs(g["b_out"]).max())
+    (out * torch.tensor(g["b_cot"])).sum().backward()
+    assert torch.allclose(s.grad, torch.tensor(g["b_gstate"]), atol=2e-5 * float(np.abs(g["b_gstate"]).max()))
+    for i, (name, p) in enumerate(d.named_parameters()):
+        want = torch.tensor(g[f"b_gparam_{i}"])
+        if i != 1:
+            assert float((p.grad - want).abs().max()) <= 5e-5 * max(float(want.abs().max()), 0.1), name
+
+    class _Target:                         # stands in for the CUDA FlightmareDynamics op on this CPU double
+        def __call__(self, state, action, dt):
+            return torch.tensor(g["b_dyn_target"])
+    tr = TrainBase(d, _Target(), delta_t=float(g["b_dt"]), learning_rate_dynamics=1e-3)
+    tr.init_dynamics_optimizer(l2_lambda=0.01)
+    loss = tr.train_dynamics_model(torch.tensor(g["b_state"]), torch.tensor(g["b_action"])[:, None, :])
+    assert abs(float(loss) - float(g["b_dyn_loss"])) <= 1e-5 * abs(float(g["b_dyn_loss"]))
