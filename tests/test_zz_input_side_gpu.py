@@ -315,3 +315,44 @@ def test_learnt_dynamics_many_tiles_vs_oracle_and_training_step():
                 bufs[i] = gi.clone() if bufs[i] is None else bufs[i] * 0.9 + gi
                 if i not in (1, 2, 3):             # the simulator ignores updates of these (construction-time values)
                     p -= 1e-3 * bufs[i]
+
+
+def test_device_dataset_epoch_equals_host_dataset_epoch():
+    """an epoch over the device-resident raw samples == the same epoch through the host QuadDataset + DataLoader path
+    (same batches, no shuffling): losses and parameters agree"""
+    from apg_trajectory_tracking_b200 import device_data as DD, train as T
+    from apg_trajectory_tracking_b200.neural_control.models.hutter_model import Net
+    PR, R, SY, _, DS = _mods()
+    n, h, dt, bs = 1000, 10, 0.1, 256
+    raw = SY.quad_case(n, h, dt, seed=2)
+    off = torch.randn(n, 3)
+    states, refs = raw["cur"].clone(), raw["ref"].clone()
+    states[:, :3] += off
+    refs[:, :, :3] += off[:, None]
+    nets = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        nets.append(Net(15, h, 9, 4 * h, conv=1))
+    spec = R.RolloutSpec.quad_concurrent(h, dt)
+    ma, mb = T.ModuleRollout(nets[0], spec, "cuda:0"), T.ModuleRollout(nets[1], spec, "cuda:0")
+    oa = torch.optim.SGD(nets[0].parameters(), lr=1e-5, momentum=0.9)
+    ob = torch.optim.SGD(nets[1].parameters(), lr=1e-5, momentum=0.9)
+    host = DS.QuadDataset(states.numpy(), refs.numpy())
+    dev = DD.DeviceQuadDataset(states, refs, "cuda:0")
+    tot, i = 0.0, 0
+    for i, lo in enumerate(range(0, n, bs)):
+        b = [t[lo:lo + bs] for t in (host.normed_states, host.states, host.in_ref_states, host.ref_states)]
+        oa.zero_grad()
+        tot += float(ma.loss_and_grad(*b))
+        oa.step()
+    la = tot / max(i, 1)
+    lb = DD.run_epoch_device(mb, ob, dev, bs, shuffle=False)
+    assert abs(la - lb) <= 2e-5 * abs(la), (la, lb)
+    assert rel_err(mb.flat, ma.flat) <= 1e-6
+    # the device constructors produce the layouts of the host generator / window cutter
+    d2 = DD.DeviceQuadDataset.from_polynomials(512, h, dt, seed=1, device="cuda:0")
+    assert d2.ref_states.shape == (512, h, 9) and float(d2.ref_states[:, :, 3:6].abs().max()) == 0.0
+    traj = torch.randn(1001, 9)
+    d3 = DD.DeviceQuadDataset.from_trajectory(traj, h, device="cuda:0")
+    assert len(d3) == len(range(0, 1001 - (h + 1), 2 * h)) and torch.equal(d3.ref_states[3, 0].cpu(), traj[61])
+    assert sum(s.shape[0] for s, _ in d3.batches(16)) == len(d3)
