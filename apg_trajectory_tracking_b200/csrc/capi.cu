@@ -482,4 +482,40 @@ __attribute__((visibility("default"))) int apg_eval_rollout(const apg_config* cf
   return 0;
 }
 
+// Closed-loop evaluation of the fixed wing towards target points (eval_kernels.cu).
+__attribute__((visibility("default"))) int apg_eval_fly_to_points(const apg_config* cfg, const float* params, const float* targets, int n_targets,
+                           const float* init_states, const float* mean_host, const float* std_host, float dt_data,
+                           int steps, float thresh_div, float thresh_stable, int test_time, void* workspace,
+                           float* states_out, float* div_linear_out, float* actions_out, int* n_steps_out,
+                           float* div_target_sum_out, float* div_target_cnt_out, void* stream) {
+  int e = check_config(cfg);
+  if (e) return e;
+  if (!is_hutter(cfg) || cfg->net != NET_HUTTER_LIN || cfg->system != SYS_WING || cfg->mode != MODE_CONCURRENT)
+    return APG_ERR_UNSUPPORTED;
+  if (cfg->state_feat != 9 || cfg->ref_dim != 3 || cfg->ref_len != 1) return APG_ERR_BAD_CONFIG;
+  if (!params || !targets || !init_states || !mean_host || !std_host || !workspace) return APG_ERR_BAD_CONFIG;
+  if (n_targets < 1 || steps < 1) return APG_ERR_BAD_CONFIG;
+  if (!aligned16(params) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APG_ERR_ALIGNMENT;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Plan p = make_plan(cfg, net_info(cfg));
+  char* w = static_cast<char*>(workspace);
+  float* wf = reinterpret_cast<float*>(w + p.o_wf);
+  float* wb = reinterpret_cast<float*>(w + p.o_wb);
+  const HutterLayout y = hutter_layout(cfg);
+  cudaError_t ce;
+  if ((ce = launch_pack(hutter_pack_table(y), params, wf, wb, st))) return (int)ce;
+  PhysConsts pc;
+  memcpy(pc.v, cfg->phys, sizeof(float) * MAX_PHYS);
+  WingEvalParams ev;
+  ev.steps = steps; ev.n_targets = n_targets; ev.test_time = test_time ? 1 : 0; ev.h = cfg->horizon;
+  ev.thresh_div = thresh_div; ev.thresh_stable = thresh_stable;
+  ev.vlen = (float)(12.0 * (double)dt_data); ev.des_speed = 11.5f;
+  if ((ce = launch_eval_wing(y, wf, targets, init_states, cfg->n_drones, cfg->dt, pc, mean_host, std_host, ev,
+                             states_out, div_linear_out, actions_out, n_steps_out, div_target_sum_out,
+                             div_target_cnt_out, p.grid, st)))
+    return (int)ce;
+  return 0;
+}
+
 }  // extern "C"

@@ -144,6 +144,150 @@ __global__ void __launch_bounds__(NT, 1) eval_rollout_kernel(const HutterLayout 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// fixed wing: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py:46-130).  Per step: WingDataset.
+// prepare_data on (observed state, current target) -> hutter "linear ref" policy -> wing dynamics step -> divergence
+// to the line towards the target, target switching, stop or reset (per-drone logic in eval_math.cuh).
+// ------------------------------------------------------------------------------------------------------------
+struct WingEvalArgs {
+  const float* wf;
+  const float* targets;       // [N][K][3]
+  const float* init_states;   // [N][12]
+  int N;
+  float dt;                   // environment step
+  PhysConsts pc;
+  NormConsts nc;              // dataset mean / std
+  WingEvalParams ev;
+  float* states_out;          // optional [N][steps+1][12]
+  float* div_out;             // optional [N][steps]
+  float* actions_out;         // optional [N][steps][4]
+  int* n_steps_out;           // optional [N]
+  float* dt_sum_out;          // optional [N]  sum of the div_target list
+  float* dt_cnt_out;          // optional [N]  its length
+};
+
+__global__ void __launch_bounds__(NT, 1) eval_wing_kernel(const HutterLayout y, const WingEvalArgs g) {
+  extern __shared__ __align__(128) float smem[];
+  using Sys = Wing<float>;
+  constexpr int S = Sys::S, A = Sys::A;
+  const int steps = g.ev.steps, K = g.ev.n_targets;
+  float* s_w = smem;
+  float* s_ins = s_w + y.f_total;
+  float* s_inr = s_ins + pad4(TM * y.F0);
+  float* s_x1 = s_inr + pad4(TM * y.LR);
+  float* s_h = s_x1 + y.XR * TMP;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_h + HID * TMP);
+  float* s_act = s_x1 + HID * TMP;
+  const Lane L;
+  const int tid = threadIdx.x;
+  const int ntiles = (g.N + TM - 1) / TM;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, y.f_total * 4);
+    bulk_g2s_chunked(s_w, g.wf, y.f_total * 4, bar_w);
+  }
+  mbar_wait(bar_w, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int valid = min(TM, g.N - tile * TM);
+    const size_t drone = (size_t)tile * TM + tid;
+    const bool mine = tid < valid;
+    WingEvalDrone D;
+    const float* tg = nullptr;
+    {
+      float init[S];
+#pragma unroll
+      for (int j = 0; j < S; ++j) init[j] = mine ? g.init_states[drone * S + j] : 0.f;
+      wing_eval_init(D, init, mine ? 1 : 0);
+    }
+    if (mine) {
+      tg = g.targets + drone * K * 3;
+      if (g.states_out) {
+#pragma unroll
+        for (int j = 0; j < S; ++j) g.states_out[drone * (steps + 1) * S + j] = D.env[j];
+      }
+    }
+    for (int i = 0; i < steps; ++i) {
+      if (tid < TM) {
+        float f[9], r3[3];
+        if (D.alive) {
+          float t3[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) t3[j] = tg[D.ti * 3 + j];
+          WingPrep<float>::drone(D.obs, t3, g.nc.mean, g.nc.std_, g.ev.vlen, g.ev.h, f, r3);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) f[j] = 0.f;
+          r3[0] = r3[1] = r3[2] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) s_ins[tid * y.F0 + j] = f[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s_inr[tid * y.LR + j] = r3[j];
+      }
+      __syncthreads();
+      hutter_first_layer<false>(L, y, s_w, s_ins, s_inr, s_x1);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_x1, y.K1, s_w + y.f_w1, HID, mma_sw(HID), s_w + y.f_b1, HID, s_h, 0, ACT_TANH);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_w2, HID, mma_sw(HID), s_w + y.f_b2, HID, s_x1, 0, ACT_TANH);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_x1, HID, s_w + y.f_w3, HID, mma_sw(HID), s_w + y.f_b3, HID, s_h, 0, ACT_TANH);
+      __syncthreads();
+      dense_auto<EPI_ACT>(L, s_h, HID, s_w + y.f_wo, y.ld_fwo, mma_sw(y.ld_fwo), s_w + y.f_bo, y.Mo4, s_act, 0,
+                          ACT_SIGMOID);
+      __syncthreads();
+      if (D.alive) {
+        float a[A], nxt[S];
+#pragma unroll
+        for (int c = 0; c < A; ++c) a[c] = s_act[c * TMP + tid];            // first of the h predicted actions
+        Sys::step(D.env, a, g.dt, g.pc.v, nxt);
+        if (g.states_out) {
+#pragma unroll
+          for (int j = 0; j < S; ++j) g.states_out[(drone * (steps + 1) + i + 1) * S + j] = nxt[j];
+        }
+        if (g.actions_out) {
+#pragma unroll
+          for (int c = 0; c < A; ++c) g.actions_out[(drone * steps + i) * A + c] = a[c];
+        }
+        const float div = wing_eval_post_step(D, nxt, tg, g.ev);
+        if (g.div_out) g.div_out[drone * steps + i] = div;
+      }
+      if (!__syncthreads_or(D.alive)) break;
+    }
+    if (mine) {
+      wing_eval_finish(D, g.ev);
+      if (g.n_steps_out) g.n_steps_out[drone] = D.nsteps;
+      if (g.dt_sum_out) g.dt_sum_out[drone] = D.dt_sum;
+      if (g.dt_cnt_out) g.dt_cnt_out[drone] = D.dt_cnt;
+    }
+    __syncthreads();
+  }
+}
+
+size_t eval_wing_smem_bytes(const HutterLayout& y) {
+  return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP) + 16;
+}
+
+cudaError_t launch_eval_wing(const HutterLayout& y, const float* wf, const float* targets, const float* init_states,
+                             int n, float dt_env, const PhysConsts& pc, const float* mean_host, const float* std_host,
+                             const WingEvalParams& ev, float* states_out, float* div_out, float* actions_out,
+                             int* n_steps_out, float* dt_sum_out, float* dt_cnt_out, int grid, cudaStream_t st) {
+  WingEvalArgs a;
+  a.wf = wf; a.targets = targets; a.init_states = init_states; a.N = n; a.dt = dt_env; a.pc = pc; a.ev = ev;
+  for (int j = 0; j < 12; ++j) { a.nc.mean[j] = mean_host[j]; a.nc.std_[j] = std_host[j]; }
+  a.states_out = states_out; a.div_out = div_out; a.actions_out = actions_out; a.n_steps_out = n_steps_out;
+  a.dt_sum_out = dt_sum_out; a.dt_cnt_out = dt_cnt_out;
+  const size_t smem = eval_wing_smem_bytes(y);
+  cudaError_t e = cudaFuncSetAttribute(eval_wing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  eval_wing_kernel<<<grid, NT, smem, st>>>(y, a);
+  return cudaGetLastError();
+}
+
 size_t eval_smem_bytes(const HutterLayout& y) {
   return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP + 6 * TM) +
          sizeof(int) * 2 * TM + sizeof(void*) * TM + 16;

@@ -9,6 +9,7 @@
 //   stability   neural_control/environments/drone_env.py:66-74   (get_is_stable: |roll|, |pitch| < thresh)
 #pragma once
 #include "apg_math.cuh"
+#include "prep_math.cuh"
 
 namespace apg {
 
@@ -55,6 +56,94 @@ APG_HD float eval_post_step(float* s, const float* tab, int ci, const EvalParams
     }
   }
   return div;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fixed wing: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py:46-130), project_to_line
+// (neural_control/trajectory/q_funcs.py:6-18), SimpleWingEnv.step (environments/wing_env.py:44-58).
+// ---------------------------------------------------------------------------------------------------------
+struct WingEvalParams {
+  int steps;            // max_steps
+  int n_targets;        // K target points per drone
+  int test_time;        // 1: stop at divergence / instability; 0: reset onto the line and go on
+  int h;                // horizon of the dataset's straight-line reference
+  float thresh_div, thresh_stable;
+  float vlen;           // 12 * dataset dt (length of one reference step)
+  float des_speed;      // 11.5: speed a reset drone is given towards the target
+};
+
+// projection of p onto the line through a and b; a itself when a == b
+APG_HD void project_to_line3(const float* a, const float* b, const float* p, float* out) {
+  const float abx = b[0] - a[0], aby = b[1] - a[1], abz = b[2] - a[2];
+  if (abx == 0.f && aby == 0.f && abz == 0.f) { out[0] = a[0]; out[1] = a[1]; out[2] = a[2]; return; }
+  const float nrm = abx * abx + aby * aby + abz * abz;
+  const float t = (p[0] - a[0]) * abx + (p[1] - a[1]) * aby + (p[2] - a[2]) * abz;
+  out[0] = a[0] + abx * t / nrm; out[1] = a[1] + aby * t / nrm; out[2] = a[2] + abz * t / nrm;
+}
+
+// Per-drone bookkeeping of one flight.  env: the environment's state; obs: the state the policy is shown (the
+// evaluator's local `state`, which is NOT refreshed by a reset, :118-129); prev_pos: position after the previous step.
+struct WingEvalDrone {
+  float env[12], obs[12], prev_pos[3], line_start[3];
+  int ti, alive, nsteps;
+  float dt_sum, dt_cnt;      // sum / count of the evaluator's div_target list
+};
+
+APG_HD void wing_eval_init(WingEvalDrone& D, const float* init_state, int alive) {
+  for (int j = 0; j < 12; ++j) { D.env[j] = init_state[j]; D.obs[j] = init_state[j]; }
+  for (int j = 0; j < 3; ++j) { D.prev_pos[j] = init_state[j]; D.line_start[j] = init_state[j]; }
+  D.ti = 0; D.alive = alive; D.nsteps = 0; D.dt_sum = 0.f; D.dt_cnt = 0.f;
+}
+
+// After env.step returned nxt: divergence to the current line, target switching, stop / reset (:82-129).
+// targets: [K][3] of this drone.  Returns the divergence to the line (div_to_linear entry of this step).
+APG_HD float wing_eval_post_step(WingEvalDrone& D, const float* nxt, const float* targets, const WingEvalParams& e) {
+  const float* tgt = targets + D.ti * 3;
+  const bool stable = (nxt[6] < 0.f ? -nxt[6] : nxt[6]) < e.thresh_stable &&
+                      (nxt[7] < 0.f ? -nxt[7] : nxt[7]) < e.thresh_stable;
+  float on_line[3];
+  project_to_line3(D.line_start, tgt, nxt, on_line);
+  const float dx = on_line[0] - nxt[0], dy = on_line[1] - nxt[1], dz = on_line[2] - nxt[2];
+  const float div = sqrt_(dx * dx + dy * dy + dz * dz);
+  ++D.nsteps;
+  bool finished = false;
+  if (nxt[0] > tgt[0]) {                                        // passed the target (:93-110)
+    float t_on[3];
+    project_to_line3(D.prev_pos, nxt, tgt, t_on);
+    const float ex = t_on[0] - tgt[0], ey = t_on[1] - tgt[1], ez = t_on[2] - tgt[2];
+    D.dt_sum += sqrt_(ex * ex + ey * ey + ez * ez);
+    D.dt_cnt += 1.f;
+    if (D.ti < e.n_targets - 1) {
+      ++D.ti;
+      for (int j = 0; j < 3; ++j) D.line_start[j] = nxt[j];
+    } else {
+      finished = true;
+    }
+  }
+  for (int j = 0; j < 12; ++j) { D.obs[j] = nxt[j]; D.env[j] = nxt[j]; }
+  for (int j = 0; j < 3; ++j) D.prev_pos[j] = nxt[j];
+  if (finished) { D.alive = 0; return div; }
+  if (!stable || div > e.thresh_div) {                          // judged against the target of THIS step (:112-129)
+    D.dt_cnt += 1.f;
+    if (e.test_time) {
+      const float ex = nxt[0] - tgt[0], ey = nxt[1] - tgt[1], ez = nxt[2] - tgt[2];
+      D.dt_sum += sqrt_(ex * ex + ey * ey + ez * ez);
+      D.alive = 0;
+    } else {
+      D.dt_sum += e.thresh_div;
+      const float vx = tgt[0] - on_line[0], vy = tgt[1] - on_line[1], vz = tgt[2] - on_line[2];
+      const float vn = sqrt_(vx * vx + vy * vy + vz * vz);
+      for (int j = 0; j < 12; ++j) D.env[j] = 0.f;
+      D.env[0] = on_line[0]; D.env[1] = on_line[1]; D.env[2] = on_line[2];
+      D.env[3] = vx / vn * e.des_speed; D.env[4] = vy / vn * e.des_speed; D.env[5] = vz / vn * e.des_speed;
+    }
+  }
+  return div;
+}
+
+// end of the flight: a drone that used all its steps gets one more div_target entry (:130-132)
+APG_HD void wing_eval_finish(WingEvalDrone& D, const WingEvalParams& e) {
+  if (D.alive && D.nsteps == e.steps) { D.dt_sum += e.thresh_div; D.dt_cnt += 1.f; }
 }
 
 }  // namespace apg

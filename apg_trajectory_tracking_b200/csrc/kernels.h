@@ -38,6 +38,11 @@ cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const fl
                                 float* states_out, float* div_out, float* actions_out, int* n_steps_out, int grid,
                                 cudaStream_t st);
 
+cudaError_t launch_eval_wing(const HutterLayout& y, const float* wf, const float* targets, const float* init_states,
+                             int n, float dt_env, const PhysConsts& pc, const float* mean_host, const float* std_host,
+                             const WingEvalParams& ev, float* states_out, float* div_out, float* actions_out,
+                             int* n_steps_out, float* dt_sum_out, float* dt_cnt_out, int grid, cudaStream_t st);
+
 // learnt residual quadrotor dynamics (learnt_kernels.cu)
 int learnt_grid(int n, int sms);
 size_t learnt_partials_floats(int n, int sms);

@@ -71,6 +71,73 @@ class TableEvaluator:
         return out
 
 
+class WingTargetEvaluator:
+    """Fixed wing: ``FixedWingEvaluator.fly_to_point`` / ``run_eval`` (scripts/evaluate_fixed_wing.py:46-178) for N
+    flights at once.  ``spec``: ``RolloutSpec.wing_concurrent(h, dt_env, modified_params)`` of the EVALUATION
+    environment; ``mean`` / ``std`` / ``dt_data``: the dataset's normalisation and delta_t (WingDataset)."""
+
+    def __init__(self, spec: R.RolloutSpec, n_drones: int, mean, std, dt_data=None, device=None):
+        if not torch.cuda.is_available():
+            raise _capi.ApgError("no CUDA device: the evaluation rollout only runs on the GPU")
+        if spec.system != "wing" or spec.net != "hutter_lin":
+            raise _capi.ApgError("target evaluation is implemented for the fixed-wing hutter net")
+        self.spec, self.n = spec, int(n_drones)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lib = _capi.lib()
+        self.mean = np.ascontiguousarray(torch.as_tensor(mean).detach().cpu().numpy(), dtype=np.float32)
+        self.std = np.ascontiguousarray(torch.as_tensor(std).detach().cpu().numpy(), dtype=np.float32)
+        if self.mean.shape != (12,) or self.std.shape != (12,):
+            raise ValueError("mean / std must have 12 entries")
+        self.dt_data = float(spec.dt if dt_data is None else dt_data)
+        with torch.cuda.device(self.device):
+            self.cfg = spec.config(self.n)
+            ws = self.lib.apg_workspace_bytes(ctypes.byref(self.cfg))
+            if ws == 0:
+                raise _capi.ApgError("bad rollout spec for the evaluation rollout")
+            self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 256
+            self._ws_ptr = ctypes.c_void_p(self.workspace.data_ptr() + off)
+
+    def fly(self, params_flat, targets, init_states=None, steps=1000, thresh_div=10.0, thresh_stable=0.8,
+            test_time=0, want=("states", "div_linear", "actions")):
+        """targets (N,K,3); init_states (N,12) or None (``zero_reset``: zeros with u = 11.5 m/s).  Returns
+        dict(states (N,steps+1,12), div_linear (N,steps), actions (N,steps,4), n_steps (N,) int32,
+        div_target_sum (N,), div_target_cnt (N,)): mean target error of flight i = sum / cnt (run_eval, :157)."""
+        _require_cuda(params_flat, targets, init_states)
+        n, dev = self.n, self.device
+        targets = targets.contiguous().float()
+        if targets.dim() != 3 or targets.shape[0] != n or targets.shape[2] != 3:
+            raise ValueError(f"targets must be (N,K,3) with N = {n}")
+        if init_states is None:
+            init_states = torch.zeros(n, 12, device=dev)
+            init_states[:, 3] = 11.5
+        init_states = init_states.contiguous().float()
+        out = {"n_steps": torch.zeros(n, dtype=torch.int32, device=dev),
+               "div_target_sum": torch.zeros(n, device=dev), "div_target_cnt": torch.zeros(n, device=dev)}
+        if "states" in want:
+            out["states"] = torch.zeros(n, steps + 1, 12, device=dev)
+        if "div_linear" in want:
+            out["div_linear"] = torch.zeros(n, steps, device=dev)
+        if "actions" in want:
+            out["actions"] = torch.zeros(n, steps, 4, device=dev)
+        opt = lambda k: None if k not in out else _p(out[k])          # noqa: E731
+        with torch.cuda.device(dev):
+            _capi.check(self.lib.apg_eval_fly_to_points(
+                ctypes.byref(self.cfg), _p(params_flat), _p(targets), int(targets.shape[1]), _p(init_states),
+                ctypes.c_void_p(self.mean.ctypes.data), ctypes.c_void_p(self.std.ctypes.data),
+                ctypes.c_float(self.dt_data), int(steps), ctypes.c_float(thresh_div), ctypes.c_float(thresh_stable),
+                int(test_time), self._ws_ptr, opt("states"), opt("div_linear"), opt("actions"), _p(out["n_steps"]),
+                _p(out["div_target_sum"]), _p(out["div_target_cnt"]), _stream(targets)))
+        return out
+
+
+def wing_eval_statistics(div_target_sum, div_target_cnt):
+    """``FixedWingEvaluator.run_eval`` (evaluate_fixed_wing.py:157-178): mean and std over the flights of each
+    flight's mean target error"""
+    m = (div_target_sum / div_target_cnt.clamp(min=1)).detach().cpu().double().numpy()
+    return float(m.mean()), float(m.std())
+
+
 def eval_statistics(div, n_steps, thresh_div):
     """``QuadEvaluator.run_eval`` statistics (evaluate_drone.py:266-298) over the N runs of one ``follow`` call:
     (mean, std of the steps below the divergence threshold, mean, std of the tracking error of the runs that stayed

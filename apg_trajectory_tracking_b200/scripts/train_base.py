@@ -53,8 +53,9 @@ class TrainBase:
 
     def init_optimizer(self):
         if self.state_data is not None:
+            # pinned batches: the H2D copies of the train step are asynchronous DMA transfers
             self.trainloader = torch.utils.data.DataLoader(self.state_data, batch_size=self.batch_size, shuffle=True,
-                                                           num_workers=0)
+                                                           num_workers=0, pin_memory=torch.cuda.is_available())
         spec = T.spec_for_net(self.net, self.system, self.horizon, self.rollout_dt(), self.train_mode, self.window,
                               self.modified_params())
         self.fused = T.ModuleRollout(self.net, spec, self.device)

@@ -126,6 +126,21 @@ int apg_eval_rollout(const apg_config* cfg, const float* params, const float* ta
                      float thresh_stable, int test_time, void* workspace, float* states_out, float* div_out,
                      float* actions_out, int* n_steps_out, void* stream);
 
+/* Fixed wing: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py:46-130) with
+ * FixedWingNetWrapper.predict_actions (controllers/network_wrapper.py:81-98), WingDataset.prepare_data,
+ * SimpleWingEnv.step (environments/wing_env.py:44-58) and project_to_line (trajectory/q_funcs.py:6-18) for
+ * cfg->n_drones drones in one launch.  cfg: wing, hutter linear-ref net, concurrent (out_dim 4h, the first predicted
+ * action is applied); cfg->dt / cfg->phys: the evaluation environment; dt_data: the dataset's delta_t (reference line
+ * spacing 12*dt_data); mean / std: 12 HOST floats of the dataset.  targets [N][n_targets][3], init_states [N][12].
+ * Outputs (device, optional, caller zero-initialised): states_out [N][steps+1][12] (as returned by env.step),
+ * div_linear_out [N][steps], actions_out [N][steps][4], n_steps_out [N] (int), div_target_sum_out / _cnt_out [N]
+ * (sum and length of the evaluator's div_target list).  workspace: apg_workspace_bytes(cfg). */
+int apg_eval_fly_to_points(const apg_config* cfg, const float* params, const float* targets, int n_targets,
+                           const float* init_states, const float* mean_host, const float* std_host, float dt_data,
+                           int steps, float thresh_div, float thresh_stable, int test_time, void* workspace,
+                           float* states_out, float* div_linear_out, float* actions_out, int* n_steps_out,
+                           float* div_target_sum_out, float* div_target_cnt_out, void* stream);
+
 /* ---- learnt residual quadrotor dynamics: LearntDynamics.forward
  * (neural_control/dynamics/quad_dynamics_trained.py:10-69) = simulate_quadrotor(linear_at @ action, state, dt) +
  * linear_state_2(relu(linear_state_1([state, linear_at @ action]))), and what autograd records for it: the

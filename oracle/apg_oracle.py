@@ -547,3 +547,96 @@ def learnt_dynamics_loss(lparams, state, action, target_next, dt, l2_lambda=0.0,
         w1, b1, w2, b2 = lparams[4:]
         loss = loss + l2_lambda * (torch.norm(w2) + torch.norm(b2) + torch.norm(w1) + torch.norm(b1))
     return loss
+
+
+# --------------------------------------------------------------------------------------------
+# N2 (fixed wing)  closed-loop evaluation: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py:46-130)
+#     with FixedWingNetWrapper.predict_actions (controllers/network_wrapper.py:81-98), WingDataset.prepare_data,
+#     SimpleWingEnv.step (environments/wing_env.py:44-58) and project_to_line (trajectory/q_funcs.py:6-18),
+#     restated for N independent drones at once.
+# --------------------------------------------------------------------------------------------
+def project_to_line(a, b, p):
+    """rows of a, b, p (N,3): projection of p onto the line through a and b; a where a == b (q_funcs.py:11-12)"""
+    ab = b - a
+    nrm = (ab * ab).sum(dim=1, keepdim=True)
+    same = (a == b).all(dim=1, keepdim=True)
+    t = ((p - a) * ab).sum(dim=1, keepdim=True)
+    return torch.where(same, a, a + ab * t / torch.where(same, torch.ones_like(nrm), nrm))
+
+
+def eval_fly_to_points(params, targets, init_states, mean, std, steps, h, dt_data, dt_env, thresh_div=10.0,
+                       thresh_stable=0.8, test_time=0, des_speed=11.5, cfg=WING_CFG):
+    """Batched restatement of FixedWingEvaluator.fly_to_point.  params: hutter Net(9,1,3,4h, conv=False);
+    targets (N,K,3); init_states (N,12) (zero_reset: zeros with u = 11.5).  Kept quirk: after a reset the policy
+    still sees the PRE-reset state for one step (the evaluator's local `state` is not refreshed, :118-129) while the
+    environment continues from the reset state.
+    Returns dict(states (N,steps+1,12) as returned by env.step, div_linear (N,steps), actions (N,steps,4),
+    n_steps (N,), div_target_sum (N,), div_target_cnt (N,))."""
+    n, K, _ = targets.shape
+    mean, std = torch.as_tensor(mean).float(), torch.as_tensor(std).float()
+    env = init_states.float().clone()               # the environment's state
+    obs = env.clone()                               # what the policy is shown
+    prev_pos = env[:, :3].clone()
+    line_start = env[:, :3].clone()
+    ti = torch.zeros(n, dtype=torch.long)
+    alive = torch.ones(n, dtype=torch.bool)
+    states = torch.zeros(n, steps + 1, 12)
+    states[:, 0] = env
+    div_lin, actions = torch.zeros(n, steps), torch.zeros(n, steps, 4)
+    n_steps = torch.zeros(n, dtype=torch.long)
+    dts, dtc = torch.zeros(n), torch.zeros(n)
+    vlen = torch.tensor(12 * dt_data, dtype=torch.float32)
+    ar = torch.arange(n)
+    for i in range(steps):
+        if not bool(alive.any()):
+            break
+        tgt = targets[ar, ti].float()
+        normed = ((obs - mean) / std)[:, 3:]                                      # dataset.py:336
+        rel = tgt - obs[:, :3]
+        unit = rel / torch.sqrt((rel ** 2).sum(dim=1, keepdim=True))
+        last = obs[:, :3] + unit * vlen * h                                        # :311-321, row h-1
+        in_ref = last - obs[:, :3]                                                 # :346
+        with torch.no_grad():
+            act = torch.sigmoid(hutter_forward(params, normed, in_ref[:, None, :], conv=False))
+        a0 = act.reshape(n, h, 4)[:, 0]
+        nxt = wing_step(env, a0, dt_env, cfg).float()
+        stable = (nxt[:, 6:8].abs() < thresh_stable).all(dim=1)                    # wing_env.py:54
+        pos = nxt[:, :3]
+        on_line = project_to_line(line_start, tgt, pos)
+        div = (on_line - pos).norm(dim=1)
+        states[alive, i + 1] = nxt[alive]
+        div_lin[alive, i] = div[alive]
+        actions[alive, i] = a0[alive]
+        n_steps[alive] += 1
+        passed = alive & (pos[:, 0] > tgt[:, 0])                                   # :93-110
+        t_on = project_to_line(prev_pos, pos, tgt)
+        dts = dts + torch.where(passed, (t_on - tgt).norm(dim=1), torch.zeros(n))
+        dtc = dtc + passed.float()
+        more = passed & (ti < K - 1)
+        finished = passed & ~more
+        line_start = torch.where(more[:, None], pos, line_start)
+        ti = torch.where(more, ti + 1, ti)
+        bad = alive & ~finished & (~stable | (div > thresh_div))                   # :112-129 (old target)
+        if test_time:
+            dts = dts + torch.where(bad, (pos - tgt).norm(dim=1), torch.zeros(n))
+        else:
+            dts = dts + torch.where(bad, torch.full((n,), float(thresh_div)), torch.zeros(n))
+        dtc = dtc + bad.float()
+        vec = tgt - on_line
+        reset = torch.zeros(n, 12)
+        reset[:, :3] = on_line
+        reset[:, 3:6] = vec / vec.norm(dim=1, keepdim=True) * des_speed
+        keep = alive[:, None]
+        prev_pos = torch.where(keep, pos, prev_pos)
+        obs = torch.where(keep, nxt, obs)
+        if test_time:
+            env = torch.where(keep, nxt, env)
+            alive = alive & ~finished & ~bad
+        else:
+            env = torch.where((bad)[:, None], reset, torch.where(keep, nxt, env))
+            alive = alive & ~finished
+    maxed = alive & (n_steps == steps)                                             # :130-132
+    dts = dts + torch.where(maxed, torch.full((n,), float(thresh_div)), torch.zeros(n))
+    dtc = dtc + maxed.float()
+    return dict(states=states, div_linear=div_lin, actions=actions, n_steps=n_steps, div_target_sum=dts,
+                div_target_cnt=dtc)

@@ -112,6 +112,57 @@ def make_eval_golden(args):
     np.savez_compressed(os.path.join(args.out, "eval_rand.npz"), **out)
 
 
+def make_wing_eval_golden(args):
+    """eval_wing.npz: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py) of the unmodified reference with
+    the shipped model_wing and its config (mean / std / horizon / dt): trajectories, divergences and the target
+    errors for a few target lists and thresholds (resets, stop at divergence, several targets, step limit)."""
+    import json
+    import torch
+    cwd = os.getcwd()
+    os.chdir(args.ref)
+    import evaluate_fixed_wing as EF
+    from neural_control.environments.wing_env import SimpleWingEnv
+    from neural_control.dynamics.fixed_wing_dynamics import FixedWingDynamics
+    from neural_control.controllers.network_wrapper import FixedWingNetWrapper
+    from neural_control.dataset import WingDataset
+    net = torch.load('trained_models/wing/current_model/model_wing', weights_only=False)
+    net.eval()
+    cfg = json.load(open('trained_models/wing/current_model/config.json'))
+    ds = WingDataset.__new__(WingDataset)              # no sampling; prepare_data only
+    ds.dt, ds.horizon = cfg["delta_t"], cfg["horizon"]
+    ds.mean, ds.std = torch.tensor(cfg["mean"]).float(), torch.tensor(cfg["std"]).float()
+    ds.get_and_add_eval_data = lambda st, rf, add_to_dataset=False: WingDataset.prepare_data(ds, st, rf)
+    out = {"mean": np.array(cfg["mean"]), "std": np.array(cfg["std"]),
+           "cfg": np.array([cfg["horizon"], cfg["delta_t"], cfg["dt"]], dtype=np.float64)}
+    for i, p in enumerate(net.parameters()):
+        out[f"param_{i}"] = p.detach()
+    # (name, targets, max_steps, thresh_div, thresh_stable, test_time)
+    runs = [("one_target", [[50., -3., 3.]], 300, 4.0, 0.4, 0),
+            ("two_targets", [[30., 2., -2.], [60., -4., 1.]], 300, 4.0, 0.4, 0),
+            ("tight_reset", [[50., 8., -8.]], 200, 0.25, 0.4, 0),
+            ("tight_stop", [[50., 8., -8.]], 200, 0.25, 0.4, 1),
+            ("unstable", [[40., 12., 10.]], 150, 10.0, 0.12, 0),
+            ("step_limit", [[50., 1., 1.]], 40, 4.0, 0.4, 0)]
+    for name, targets, steps, tdiv, tstab, test_time in runs:
+        ctrl = FixedWingNetWrapper(net, ds, horizon=cfg["horizon"])
+        env = SimpleWingEnv(FixedWingDynamics(), cfg["dt"])
+        ev = EF.FixedWingEvaluator(ctrl, env, dt=cfg["dt"], horizon=cfg["horizon"], thresh_div=tdiv,
+                                   thresh_stable=tstab, test_time=test_time)
+        tg = np.array(targets)
+        traj = ev.fly_to_point(tg, max_steps=steps, return_traj=True)
+        div_target, div_linear = ev.fly_to_point(tg, max_steps=steps)
+        out[f"{name}_targets"] = tg
+        out[f"{name}_cfg"] = np.array([steps, test_time, tdiv, tstab], dtype=np.float64)
+        out[f"{name}_traj"] = traj                      # rows [state (12), applied action (4)]
+        out[f"{name}_div_target"] = np.asarray(div_target, dtype=np.float64)
+        out[f"{name}_div_linear"] = np.asarray(div_linear, dtype=np.float64)
+        print("wing eval", name, "steps", len(div_linear), "div_target", np.round(div_target, 4),
+              "max div_linear %.3f" % np.max(div_linear))
+    out["run_names"] = np.array([r[0] for r in runs])
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(args.out, "eval_wing.npz"), **npify(out))
+
+
 def make_learnt_golden(args):
     """learnt_dyn.npz: LearntDynamics.forward (neural_control/dynamics/quad_dynamics_trained.py) of the unmodified
     reference with seeded NON-zero parameters (the reference initialises the residual MLP with zeros, which leaves it
@@ -170,6 +221,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
     ap.add_argument("--only-prep", action="store_true", help="only (re)generate prep_data.npz")
     ap.add_argument("--only-eval", action="store_true", help="only (re)generate eval_rand.npz")
+    ap.add_argument("--only-wing-eval", action="store_true", help="only (re)generate eval_wing.npz")
     ap.add_argument("--only-learnt", action="store_true", help="only (re)generate learnt_dyn.npz")
     args = ap.parse_args()
     import_reference(args.ref)
@@ -179,6 +231,9 @@ def main():
         return
     if args.only_learnt:
         make_learnt_golden(args)
+        return
+    if args.only_wing_eval:
+        make_wing_eval_golden(args)
         return
 
     import torch

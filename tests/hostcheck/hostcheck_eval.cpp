@@ -88,3 +88,68 @@ extern "C" void hc_eval_rollout(const float* params, int h, int Mo, const float*
     n_steps_out[d] = nsteps;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// fixed wing: mirrors the per-thread code of eval_wing_kernel (policy: scalar hutter "linear ref" net)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+void wing_policy_first_action(const float* p, int h, const float* f /*9*/, const float* r3, float* a4) {
+  const int Mo = 4 * h;
+  const float* ws = p;  p += 64 * 9;
+  const float* bs = p;  p += 64;
+  p += 20 * 3 * 3 + 20;                 // conv_ref (unused by the linear-ref net)
+  const float* wr = p;  p += 64 * 3;
+  const float* br = p;  p += 64;
+  const float* w1 = p;  p += 64 * 128;
+  const float* b1 = p;  p += 64;
+  const float* w2 = p;  p += 64 * 64;
+  const float* b2 = p;  p += 64;
+  const float* w3 = p;  p += 64 * 64;
+  const float* b3 = p;  p += 64;
+  const float* wo = p;  p += Mo * 64;
+  const float* bo = p;
+  float x[128], h1[64], h2[64], h3[64];
+  for (int j = 0; j < 64; ++j) {
+    float s = bs[j];
+    for (int k = 0; k < 9; ++k) s += ws[j * 9 + k] * f[k];
+    x[j] = tanhf(s);
+    float q = br[j];
+    for (int k = 0; k < 3; ++k) q += wr[j * 3 + k] * r3[k];
+    x[64 + j] = tanhf(q);
+  }
+  for (int j = 0; j < 64; ++j) { float s = b1[j]; for (int k = 0; k < 128; ++k) s += w1[j * 128 + k] * x[k]; h1[j] = tanhf(s); }
+  for (int j = 0; j < 64; ++j) { float s = b2[j]; for (int k = 0; k < 64; ++k) s += w2[j * 64 + k] * h1[k]; h2[j] = tanhf(s); }
+  for (int j = 0; j < 64; ++j) { float s = b3[j]; for (int k = 0; k < 64; ++k) s += w3[j * 64 + k] * h2[k]; h3[j] = tanhf(s); }
+  for (int j = 0; j < 4; ++j) {
+    float s = bo[j];
+    for (int k = 0; k < 64; ++k) s += wo[j * 64 + k] * h3[k];
+    a4[j] = 1.f / (1.f + expf(-s));
+  }
+}
+}  // namespace
+
+extern "C" void hc_eval_wing(const float* params, int h, const float* targets, int K, const float* init_states, int n,
+                             const float* mean, const float* std_, float dt_data, float dt_env, const float* pc,
+                             int steps, float thresh_div, float thresh_stable, int test_time, float* states_out,
+                             float* div_out, float* actions_out, int* n_steps_out, float* dts_out, float* dtc_out) {
+  WingEvalParams e;
+  e.steps = steps; e.n_targets = K; e.test_time = test_time; e.h = h; e.thresh_div = thresh_div;
+  e.thresh_stable = thresh_stable; e.vlen = (float)(12.0 * (double)dt_data); e.des_speed = 11.5f;
+  for (int d = 0; d < n; ++d) {
+    WingEvalDrone D;
+    wing_eval_init(D, init_states + d * 12, 1);
+    const float* tg = targets + (size_t)d * K * 3;
+    for (int j = 0; j < 12; ++j) states_out[(size_t)d * (steps + 1) * 12 + j] = D.env[j];
+    for (int i = 0; i < steps && D.alive; ++i) {
+      float f[9], r3[3], a[4], nxt[12];
+      WingPrep<float>::drone(D.obs, tg + D.ti * 3, mean, std_, e.vlen, h, f, r3);
+      wing_policy_first_action(params, h, f, r3, a);
+      Wing<float>::step(D.env, a, dt_env, pc, nxt);
+      for (int j = 0; j < 12; ++j) states_out[((size_t)d * (steps + 1) + i + 1) * 12 + j] = nxt[j];
+      for (int c = 0; c < 4; ++c) actions_out[((size_t)d * steps + i) * 4 + c] = a[c];
+      div_out[(size_t)d * steps + i] = wing_eval_post_step(D, nxt, tg, e);
+    }
+    wing_eval_finish(D, e);
+    n_steps_out[d] = D.nsteps; dts_out[d] = D.dt_sum; dtc_out[d] = D.dt_cnt;
+  }
+}

@@ -84,3 +84,39 @@ def test_kernel_logic_matches_oracle_batched_with_table_index(he):
     assert len(set(nst.tolist())) > 1                     # the drones stop at different steps
     assert np.abs(states - out["states"].numpy()).max() <= 2e-5
     assert np.abs(div - out["div"].numpy()).max() <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fixed wing: FixedWingEvaluator.fly_to_point
+# ---------------------------------------------------------------------------------------------------------------
+def _run_wing(he, g, params, targets, init, steps, h, dt_data, dt_env, tdiv, tstab, test_time):
+    flat = np.ascontiguousarray(torch.cat([p.reshape(-1) for p in params]).numpy(), dtype=np.float32)
+    targets = np.ascontiguousarray(targets, dtype=np.float32)
+    init = np.ascontiguousarray(init, dtype=np.float32)
+    n, K = targets.shape[0], targets.shape[1]
+    mean, std = np.ascontiguousarray(g["mean"], np.float32), np.ascontiguousarray(g["std"], np.float32)
+    states = np.zeros((n, steps + 1, 12), np.float32)
+    div, act = np.zeros((n, steps), np.float32), np.zeros((n, steps, 4), np.float32)
+    nst, dts, dtc = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    pc = P.PHYS["wing"]()
+    he.hc_eval_wing(_p(flat), h, _p(targets), K, _p(init), n, _p(mean), _p(std), ctypes.c_float(dt_data),
+                    ctypes.c_float(dt_env), _p(pc), steps, ctypes.c_float(tdiv), ctypes.c_float(tstab), int(test_time),
+                    _p(states), _p(div), _p(act), _p(nst), _p(dts), _p(dtc))
+    return states, div, act, nst, dts, dtc
+
+
+@pytest.mark.parametrize("name", ["one_target", "two_targets", "tight_reset", "tight_stop", "unstable", "step_limit"])
+def test_wing_kernel_logic_matches_reference_evaluator(he, name):
+    from tests.test_oracle_golden import wing_eval_case
+    g = load_golden("eval_wing.npz")
+    params, targets, init, h, dt_data, dt_env, steps, test_time, tdiv, tstab = wing_eval_case(g, name)
+    states, div, act, nst, dts, dtc = _run_wing(he, g, params, targets.numpy(), init.numpy(), steps, h, dt_data, dt_env,
+                                                tdiv, tstab, test_time)
+    traj, dl, dtg = g[f"{name}_traj"], g[f"{name}_div_linear"], g[f"{name}_div_target"]
+    taken = len(dl)
+    assert int(nst[0]) == taken
+    scale = np.abs(traj[:, :12]).max()
+    assert np.abs(states[0, 1:taken + 1] - traj[:, :12]).max() <= 5e-5 * scale
+    assert np.abs(act[0, :taken] - traj[:, 12:]).max() <= 5e-5
+    assert np.abs(div[0, :taken] - dl).max() <= 5e-5 * max(dl.max(), 1.0)
+    assert int(dtc[0]) == len(dtg) and abs(float(dts[0]) - dtg.sum()) <= 2e-4 * max(dtg.sum(), 1.0)

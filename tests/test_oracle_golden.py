@@ -227,3 +227,36 @@ def test_learnt_dynamics_training_loss_matches_reference(tag):
     for i in (0, 3, 4, 5, 6, 7):
         want = g[f"{tag}_dyn_gparam_{i}"]
         assert float((grads[i] - t(want)).abs().max()) <= 2e-5 * max(float(np.abs(want).max()), 1e-3), i
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N2 (fixed wing): closed-loop evaluation, pinned on FixedWingEvaluator.fly_to_point of the reference
+# ---------------------------------------------------------------------------------------------------------------
+WING_EVAL_RUNS = ["one_target", "two_targets", "tight_reset", "tight_stop", "unstable", "step_limit"]
+
+
+def wing_eval_case(g, name):
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(14)]
+    h, dt_data, dt_env = int(g["cfg"][0]), float(g["cfg"][1]), float(g["cfg"][2])
+    steps, test_time, tdiv, tstab = [float(x) for x in g[f"{name}_cfg"]]
+    init = torch.zeros(1, 12)
+    init[0, 3] = 11.5                                                    # SimpleWingEnv.zero_reset
+    targets = torch.tensor(g[f"{name}_targets"], dtype=torch.float32)[None]
+    return params, targets, init, h, dt_data, dt_env, int(steps), int(test_time), tdiv, tstab
+
+
+@pytest.mark.parametrize("name", WING_EVAL_RUNS)
+def test_eval_fly_to_points_matches_reference_evaluator(name):
+    g = load_golden("eval_wing.npz")
+    params, targets, init, h, dt_data, dt_env, steps, test_time, tdiv, tstab = wing_eval_case(g, name)
+    out = O.eval_fly_to_points(params, targets, init, g["mean"], g["std"], steps, h, dt_data, dt_env, tdiv, tstab,
+                               test_time)
+    traj, dl, dtg = g[f"{name}_traj"], g[f"{name}_div_linear"], g[f"{name}_div_target"]
+    taken = len(dl)
+    assert int(out["n_steps"][0]) == taken
+    scale = np.abs(traj[:, :12]).max()
+    assert np.abs(out["states"][0, 1:taken + 1].numpy() - traj[:, :12]).max() <= 2e-5 * scale
+    assert np.abs(out["actions"][0, :taken].numpy() - traj[:, 12:]).max() <= 2e-5
+    assert np.abs(out["div_linear"][0, :taken].numpy() - dl).max() <= 2e-5 * max(dl.max(), 1.0)
+    assert int(out["div_target_cnt"][0]) == len(dtg)
+    assert abs(float(out["div_target_sum"][0]) - dtg.sum()) <= 1e-4 * max(dtg.sum(), 1.0)

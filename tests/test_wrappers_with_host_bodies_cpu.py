@@ -94,6 +94,22 @@ class _HostLib:
                                 self._vp(_addr(n_steps)))
         return 0
 
+    def apg_eval_fly_to_points(self, cfg, params, targets, K, init, mean, std, dt_data, steps, tdiv, tstab, test_time,
+                               ws, states, div, actions, n_steps, dts, dtc, stream):
+        c = cfg._obj
+        n = c.n_drones
+        tmp = {k: np.zeros(s, np.float32) for k, s in (("states", (n, steps + 1, 12)), ("div", (n, steps)),
+                                                        ("actions", (n, steps, 4)))}
+        self.keep.append(tmp)
+        ptr = lambda given, k: self._vp(_addr(given) if given is not None else tmp[k].ctypes.data)   # noqa: E731
+        phys = (ctypes.c_float * 48)(*c.phys)
+        self.ev.hc_eval_wing(self._vp(_addr(params)), c.horizon, self._vp(_addr(targets)), K, self._vp(_addr(init)), n,
+                             self._vp(_addr(mean)), self._vp(_addr(std)), ctypes.c_float(_f(dt_data)),
+                             ctypes.c_float(c.dt), phys, steps, ctypes.c_float(_f(tdiv)), ctypes.c_float(_f(tstab)),
+                             int(test_time), ptr(states, "states"), ptr(div, "div"), ptr(actions, "actions"),
+                             self._vp(_addr(n_steps)), self._vp(_addr(dts)), self._vp(_addr(dtc)))
+        return 0
+
     def apg_learnt_step(self, params, phys, state, action, dt, n, out, stream):
         self.ln.hc_learnt_fwd_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
                                   ctypes.c_float(_f(dt)), n, self._vp(_addr(out)))
@@ -209,3 +225,22 @@ def test_learnt_dynamics_wrapper_and_trainer_step(hostlib):
     tr.init_dynamics_optimizer(l2_lambda=0.01)
     loss = tr.train_dynamics_model(torch.tensor(g["b_state"]), torch.tensor(g["b_action"])[:, None, :])
     assert abs(float(loss) - float(g["b_dyn_loss"])) <= 1e-5 * abs(float(g["b_dyn_loss"]))
+
+
+def test_wing_target_evaluator_wrapper(hostlib):
+    from tests.test_oracle_golden import wing_eval_case
+    g = load_golden("eval_wing.npz")
+    for name in ("two_targets", "tight_reset"):
+        params, targets, init, h, dt_data, dt_env, steps, test_time, tdiv, tstab = wing_eval_case(g, name)
+        ev = EV.WingTargetEvaluator(R.RolloutSpec.wing_concurrent(h, dt_env), 1, g["mean"], g["std"], dt_data, "cpu")
+        out = ev.fly(R.flatten_params(params), targets, steps=steps, thresh_div=tdiv, thresh_stable=tstab,
+                     test_time=test_time)
+        traj, dl, dtg = g[f"{name}_traj"], g[f"{name}_div_linear"], g[f"{name}_div_target"]
+        taken = len(dl)
+        assert int(out["n_steps"][0]) == taken and int(out["div_target_cnt"][0]) == len(dtg)
+        assert np.abs(out["states"][0, 1:taken + 1].numpy() - traj[:, :12]).max() <= 5e-5 * np.abs(traj[:, :12]).max()
+        assert abs(float(out["div_target_sum"][0]) - dtg.sum()) <= 2e-4 * max(dtg.sum(), 1.0)
+        m, sd = EV.wing_eval_statistics(out["div_target_sum"], out["div_target_cnt"])
+        assert abs(m - dtg.mean()) <= 2e-4 * max(dtg.mean(), 1.0) and sd == 0.0
+    slim = ev.fly(R.flatten_params(params), targets, steps=20, want=())
+    assert set(slim) == {"n_steps", "div_target_sum", "div_target_cnt"} and int(slim["n_steps"][0]) == 20

@@ -356,3 +356,54 @@ def test_device_dataset_epoch_equals_host_dataset_epoch():
     d3 = DD.DeviceQuadDataset.from_trajectory(traj, h, device="cuda:0")
     assert len(d3) == len(range(0, 1001 - (h + 1), 2 * h)) and torch.equal(d3.ref_states[3, 0].cpu(), traj[61])
     assert sum(s.shape[0] for s, _ in d3.batches(16)) == len(d3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N2 (fixed wing): eval_wing_kernel vs the reference's FixedWingEvaluator.fly_to_point and the oracle
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["one_target", "two_targets", "tight_reset", "tight_stop", "unstable", "step_limit"])
+def test_wing_fly_to_points_matches_reference_evaluator(name):
+    from tests.test_oracle_golden import wing_eval_case
+    EV, R, O, _ = _eval_mods()
+    g = load_golden("eval_wing.npz")
+    params, targets, init, h, dt_data, dt_env, steps, test_time, tdiv, tstab = wing_eval_case(g, name)
+    ev = EV.WingTargetEvaluator(R.RolloutSpec.wing_concurrent(h, dt_env), 1, g["mean"], g["std"], dt_data, "cuda:0")
+    out = ev.fly(R.flatten_params(params).cuda(), targets.cuda(), steps=steps, thresh_div=tdiv, thresh_stable=tstab,
+                 test_time=test_time)
+    traj, dl, dtg = g[f"{name}_traj"], g[f"{name}_div_linear"], g[f"{name}_div_target"]
+    taken = len(dl)
+    assert int(out["n_steps"][0]) == taken
+    # closed loop with resets over up to ~100 steps, 3xTF32 policy vs the reference's fp32 CPU policy
+    scale = np.abs(traj[:, :12]).max()
+    assert np.abs(out["states"][0, 1:taken + 1].cpu().numpy() - traj[:, :12]).max() <= 5e-4 * scale
+    assert np.abs(out["actions"][0, :taken].cpu().numpy() - traj[:, 12:]).max() <= 5e-4
+    assert np.abs(out["div_linear"][0, :taken].cpu().numpy() - dl).max() <= 5e-4 * max(dl.max(), 1.0)
+    assert int(out["div_target_cnt"][0]) == len(dtg)
+    assert abs(float(out["div_target_sum"][0]) - dtg.sum()) <= 2e-3 * max(dtg.sum(), 1.0)
+
+
+def test_wing_fly_to_points_batched_vs_oracle():
+    EV, R, O, _ = _eval_mods()
+    g = load_golden("eval_wing.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(14)]
+    h, dt_data, dt_env = int(g["cfg"][0]), float(g["cfg"][1]), float(g["cfg"][2])
+    n, K, steps = 200, 2, 120
+    gen = torch.Generator().manual_seed(3)
+    targets = torch.zeros(n, K, 3)
+    targets[:, 0] = torch.tensor([25.0, 0, 0]) + (torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([6.0, 8, 8])
+    targets[:, 1] = torch.tensor([50.0, 0, 0]) + (torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([6.0, 10, 10])
+    init = torch.zeros(n, 12)
+    init[:, 3] = 11.5 + 0.3 * torch.randn(n, generator=gen)
+    init[:, 7] = 0.02 * torch.randn(n, generator=gen)
+    want = O.eval_fly_to_points(params, targets, init, g["mean"], g["std"], steps, h, dt_data, dt_env, 2.0, 0.4, 0)
+    ev = EV.WingTargetEvaluator(R.RolloutSpec.wing_concurrent(h, dt_env), n, g["mean"], g["std"], dt_data, "cuda:0")
+    out = ev.fly(R.flatten_params(params).cuda(), targets.cuda(), init_states=init.cuda(), steps=steps, thresh_div=2.0,
+                 thresh_stable=0.4, test_time=0)
+    same = out["n_steps"].cpu() == want["n_steps"].to(torch.int32)
+    assert float(same.float().mean()) >= 0.97          # a threshold within rounding can flip a decision
+    ok = same & (out["div_target_cnt"].cpu() == want["div_target_cnt"])
+    d = (out["states"].cpu() - want["states"]).abs().amax(dim=(1, 2))
+    assert float((d[ok] <= 5e-3).float().mean()) >= 0.97
+    assert float((out["states"].cpu()[:, :6] - want["states"][:, :6]).abs().max()) <= 2e-4
+    m, sd = EV.wing_eval_statistics(out["div_target_sum"], out["div_target_cnt"])
+    assert np.isfinite(m) and np.isfinite(sd)
