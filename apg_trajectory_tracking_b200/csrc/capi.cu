@@ -1,5 +1,6 @@
 // extern "C" boundary of libapg_b200.so (declared in include/apg_b200.h).  Plain pointers and sizes only.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/apg_b200.h"
@@ -143,7 +144,7 @@ PackTable hutter_pack_table(const HutterLayout& y) {
 
 struct Plan {
   int grid, ntiles;
-  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, total;
+  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_tc, total;
 };
 
 NetInfo net_info(const apg_config* c) {
@@ -219,6 +220,8 @@ Plan make_plan(const apg_config* c, const NetInfo& y) {
   p.o_h3 = o;     o += up256(sizeof(float) * nst * y.h_rows * TMP);
   p.o_act = o;    o += up256(sizeof(float) * nst * y.act_rows * TMP);
   p.o_states = o; o += up256(sizeof(float) * (size_t)p.ntiles * c->horizon * S * TMP);
+  // weight images of the optional tcgen05 forward (appended: the offsets above do not move)
+  p.o_tc = o;     o += up256(tc_blob_bytes());
   p.total = o;
   return p;
 }
@@ -254,6 +257,14 @@ int check_ptrs(const apg_config* c, const float* params, const float* in_state, 
       (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return APG_ERR_ALIGNMENT;
   return 0;
+}
+
+// APG_TC_FWD=1 selects the tcgen05 forward for the configuration it is written for (quadrotor concurrent,
+// Net(15,10,9,40,conv), h = 10); everything else, and the default, runs hutter_fwd_kernel.
+bool use_tc_forward(const apg_config* c, const HutterLayout& y) {
+  const char* e = getenv("APG_TC_FWD");
+  if (!e || e[0] != '1') return false;
+  return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && tc_fwd_supported(y, c->horizon);
 }
 
 // cached device buffers of the host-buffer entry point
@@ -310,6 +321,11 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
     if ((ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
       return (int)ce;
     if (is_recurrent(cfg)) { if ((ce = launch_rec_fwd(y, a, p.grid, st))) return (int)ce; }
+    else if (use_tc_forward(cfg, y)) {
+      // optional tcgen05 / TMEM forward (APG_TC_FWD=1): same stash, consumed by the same adjoint kernel
+      unsigned char* blob = static_cast<unsigned char*>(workspace) + p.o_tc;
+      if ((ce = launch_hutter_fwd_tc(y, params, blob, a, p.grid, st))) return (int)ce;
+    }
     else if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
   } else if (cfg->net == NET_LSTM) {
     if (!h0c0) return APG_ERR_BAD_CONFIG;

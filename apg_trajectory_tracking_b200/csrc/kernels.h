@@ -12,6 +12,12 @@ size_t hutter_adj_smem_bytes(const HutterLayout& y);
 cudaError_t launch_hutter_fwd(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 
+// optional tcgen05 / TMEM forward of the quadrotor concurrent rollout (hutter_tc_kernels.cu)
+size_t tc_blob_bytes();
+bool tc_fwd_supported(const HutterLayout& y, int h);
+cudaError_t launch_hutter_fwd_tc(const HutterLayout& y, const float* params, unsigned char* blob,
+                                 const RolloutArgs& a, int grid, cudaStream_t st);
+
 cudaError_t launch_rec_fwd(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_rec_adj(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_lstm_fwd(const LstmLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);

@@ -1,0 +1,94 @@
+"""Host-checkable parts of the optional tcgen05 forward (csrc/tc_layout.cuh): the pack-kernel body (torch-flat
+parameters -> (hi, lo) K-major weight images: padding, Toeplitz block of the conv, fc1 column permutation), the op
+list and the stash addressing, emulated on the CPU from the PACKED images and compared with the oracle's policy
+forward in the layout the (GPU-verified) adjoint kernel reads.  The tcgen05 instructions themselves can only be
+checked on the GPU (tests/test_zz_input_side_gpu.py::test_tc_forward_*)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import bench as B
+from apg_trajectory_tracking_b200 import synthetic as SY
+from oracle import apg_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TM, TMP = 64, 68
+
+
+@pytest.fixture(scope="module")
+def ht(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostcheck_tc") / "libhostcheck_tc.so"
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck_tc.cpp")
+    inc = os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", "-std=c++17", "-ffp-contract=off", "-I", inc,
+                           src, "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _unstash(st, rows, n):
+    """[ntiles64][rows][TMP] -> (n, rows)"""
+    nt = (n + TM - 1) // TM
+    a = st.reshape(nt, rows, TMP)[:, :, :TM].transpose(0, 2, 1).reshape(nt * TM, rows)
+    return a[:n]
+
+
+@pytest.mark.parametrize("n", [1, 64, 65, 130, 300])
+def test_packed_images_and_op_list_reproduce_the_policy_in_stash_layout(ht, n):
+    h = 10
+    params = B.default_init("quad", h, seed=n)
+    case = SY.quad_case(n, h, 0.1, seed=n)
+    flat = np.ascontiguousarray(torch.cat([p.reshape(-1) for p in params]).numpy(), dtype=np.float32)
+    blob = np.zeros(ht.hc_tc_blob_bytes(), np.uint8)
+    ht.hc_tc_pack(_p(flat), _p(blob))
+    nt64 = (n + TM - 1) // TM
+    nan = lambda rows: np.full(nt64 * rows * TMP, np.nan, np.float32)          # noqa: E731
+    x1, h1, h2, h3, act = nan(224), nan(64), nan(64), nan(64), nan(40)
+    ins = np.ascontiguousarray(case["in_state"].numpy(), np.float32)
+    inr = np.ascontiguousarray(case["in_ref"].numpy(), np.float32)
+    ht.hc_tc_emulate(_p(blob), _p(ins), _p(inr), n, _p(x1), _p(h1), _p(h2), _p(h3), _p(act))
+    # oracle activations (fp64), conv outputs reordered channel-major (c*8 + t) -> position-major (t*20 + c)
+    ps = [p.double() for p in params]
+    ws, bs, wc, bc, wr, br, w1, b1, w2, b2, w3, b3, wo, bo = ps
+    s = torch.tanh(case["in_state"].double() @ ws.t() + bs)
+    conv = O._conv_encoder(case["in_ref"].double(), wc, bc)                     # (n, 160) channel-major
+    conv_pm = conv.reshape(n, 20, 8).transpose(1, 2).reshape(n, 160)
+    a1 = torch.tanh(torch.cat((s, conv), 1) @ w1.t() + b1)
+    a2 = torch.tanh(a1 @ w2.t() + b2)
+    a3 = torch.tanh(a2 @ w3.t() + b3)
+    out = torch.sigmoid(a3 @ wo.t() + bo)
+    for got, rows, want in ((x1, 224, torch.cat((s, conv_pm), 1)), (h1, 64, a1), (h2, 64, a2), (h3, 64, a3),
+                            (act, 40, out)):
+        g = _unstash(got, rows, n)
+        assert np.isfinite(g).all()
+        assert np.abs(g - want.numpy()).max() <= 3e-6, rows
+    # every column of every existing 64-drone tile is written (the adjoint multiplies dead columns by zero: they
+    # must be finite), the TMP - 64 padding floats are never touched
+    full = x1.reshape(nt64, 224, TMP)
+    assert np.isfinite(full[:, :, :TM]).all() and np.isnan(full[:, :, TM:]).all()
+
+
+def test_packed_images_are_hi_lo_splits_with_zero_padding(ht):
+    params = B.default_init("quad", 10, seed=5)
+    flat = np.ascontiguousarray(torch.cat([p.reshape(-1) for p in params]).numpy(), dtype=np.float32)
+    blob = np.full(ht.hc_tc_blob_bytes(), 0xAB, np.uint8)
+    ht.hc_tc_pack(_p(flat), _p(blob))
+    words = blob.view(np.uint32)
+    assert not np.any(words == 0xABABABAB)                   # every word of the blob is written
+    img = blob[:228352].view(np.float32)
+    assert np.isfinite(img).all()
+    # hi images keep 19 significant bits: low 13 mantissa bits clear in the first (hi) half of the first image
+    ws_hi = blob[:64 * 16 * 4].view(np.uint32)
+    assert np.all((ws_hi & 0x1FFF) == 0)
+    # hi + lo reproduces the weight exactly: states_in.weight[3][7] sits at kmajor_off(3, 7, 16)
+    off = (3 >> 3) * ((16 >> 2) * 128) + (7 >> 2) * 128 + (3 & 7) * 16 + (7 & 3) * 4
+    hi = blob[off:off + 4].view(np.float32)[0]
+    lo = blob[64 * 16 * 4 + off:64 * 16 * 4 + off + 4].view(np.float32)[0]
+    assert np.float32(hi) + np.float32(lo) == params[0][3, 7].numpy()

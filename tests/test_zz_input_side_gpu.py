@@ -407,3 +407,39 @@ def test_wing_fly_to_points_batched_vs_oracle():
     assert float((out["states"].cpu()[:, :6] - want["states"][:, :6]).abs().max()) <= 2e-4
     m, sd = EV.wing_eval_statistics(out["div_target_sum"], out["div_target_cnt"])
     assert np.isfinite(m) and np.isfinite(sd)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optional tcgen05 / TMEM forward (csrc/hutter_tc_kernels.cu, APG_TC_FWD=1) vs the default forward kernel:
+# same loss / actions / states, and the same gradient when the unchanged adjoint kernel consumes its stash
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [128, 1, 63, 300, 1000, 9600, 148 * 128 * 3 + 77])
+def test_tc_forward_matches_default_forward(n):
+    import os
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    h, dt = 10, 0.1
+    params = B.default_init("quad", h, seed=n % 97)
+    case = {k: v.cuda() for k, v in SY.quad_case(n, h, dt, seed=n % 89).items()}
+    flat = R.flatten_params(params).cuda()
+    spec = R.RolloutSpec.quad_concurrent(h, dt)
+
+    def run():
+        r = R.Rollout(spec, n, "cuda:0")
+        loss, states, actions = r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"],
+                                          want_states=True, want_actions=True)
+        grad = r.backward(1.0)
+        torch.cuda.synchronize()
+        return float(loss.item()), states.cpu(), actions.cpu(), grad.cpu()
+    os.environ.pop("APG_TC_FWD", None)
+    l0, s0, a0, g0 = run()
+    os.environ["APG_TC_FWD"] = "1"
+    try:
+        l1, s1, a1, g1 = run()
+    finally:
+        os.environ.pop("APG_TC_FWD", None)
+    assert np.isfinite(l1), "tcgen05 forward reported a protocol timeout (NaN loss)"
+    assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
+    assert float((a1 - a0).abs().max()) <= 1e-5
+    assert float((s1 - s0).abs().max()) <= 1e-5 * max(float(s0.abs().max()), 1.0)
+    assert rel_err(g1, g0) <= 1e-4

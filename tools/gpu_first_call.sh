@@ -21,6 +21,9 @@ for w in wing_concurrent quad_autoregressive quad_lstm cartpole_concurrent; do
   timeout 300 python bench.py --workload $w --steps 20 --no-cpu-baseline > "$out/bench_$w.json" 2> "$out/bench_$w.err"
 done
 
+# 2b. the optional tcgen05 forward in the product bench (only meaningful if its parity test passed above)
+timeout 300 python bench.py --tc-forward --steps 30 --no-cpu-baseline --no-raw-e2e > "$out/bench_tc_forward.json" 2> "$out/bench_tc_forward.err"
+
 # 3. launch list of a short bench run (shares of the step, not absolute times)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches.csv" \
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-raw-e2e > "$out/bench_under_ncu.log" 2>&1
