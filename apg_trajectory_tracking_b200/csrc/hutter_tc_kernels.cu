@@ -75,6 +75,16 @@ __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity, vola
     }
   }
 }
+// non-blocking phase test
+__device__ __forceinline__ bool tc_mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
@@ -163,28 +173,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (warp == 8) {
     if (lane == 0) {
+      // The two slots advance independently: whichever slot has its next A operand ready gets its next op issued
+      // (non-blocking mbarrier test), so one group's dynamics phase does not hold back the other group's GEMMs.
       uint32_t par[2] = {0, 0};
-      for (int j0 = 0; j0 < my_tiles; j0 += 2)
-        for (int i = 0; i < NOPS; ++i) {
-          const Op op = op_of(i);
+      int op_i[2] = {0, 0}, tile_j[2] = {0, 1};
+      int remaining = my_tiles * NOPS;
+      long long t_idle = clock64();
+      while (remaining > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (tile_j[s] >= my_tiles) continue;
+          if (!tc_mbar_test(smem_u32(&s_bars.a_ready[s]), par[s])) continue;
+          par[s] ^= 1;
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const Op op = op_of(op_i[s]);
           const uint32_t idesc = idesc_tf32(TMT, op.N);
           const uint32_t whi = smem_u32(base + op.img_off), wlo = whi + img_bytes(op.rows, op.K);
-          for (int s = 0; s < 2; ++s) {
-            if (j0 + s >= my_tiles) continue;
-            tc_mbar_wait(smem_u32(&s_bars.a_ready[s]), par[s], abort_flag);
-            par[s] ^= 1;
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t slot = tmem + s * SLOT_COLS;
-            const uint32_t d = slot + op.d_col, ahi = slot + C_AHI, alo = slot + C_ALO;
-            for (int ks = 0; ks < op.K / 8; ++ks) {
-              const uint64_t bh = kmajor_desc(whi, ks, op.K), bl = kmajor_desc(wlo, ks, op.K);
-              mma_ts(d, alo + ks * 8, bh, idesc, (ks > 0 || !op.clear) ? 1u : 0u);
-              mma_ts(d, ahi + ks * 8, bl, idesc, 1u);
-              mma_ts(d, ahi + ks * 8, bh, idesc, 1u);
-            }
-            mma_commit(smem_u32(&s_bars.d_ready[s]));
+          const uint32_t slot = tmem + s * SLOT_COLS;
+          const uint32_t d = slot + op.d_col, ahi = slot + C_AHI, alo = slot + C_ALO;
+          for (int ks = 0; ks < op.K / 8; ++ks) {
+            const uint64_t bh = kmajor_desc(whi, ks, op.K), bl = kmajor_desc(wlo, ks, op.K);
+            mma_ts(d, alo + ks * 8, bh, idesc, (ks > 0 || !op.clear) ? 1u : 0u);
+            mma_ts(d, ahi + ks * 8, bl, idesc, 1u);
+            mma_ts(d, ahi + ks * 8, bh, idesc, 1u);
           }
+          mma_commit(smem_u32(&s_bars.d_ready[s]));
+          if (++op_i[s] == NOPS) { op_i[s] = 0; tile_j[s] += 2; }
+          --remaining;
+          progressed = true;
         }
+        if (progressed) {
+          t_idle = clock64();
+        } else if (*abort_flag || clock64() - t_idle > 2000000000LL) {
+          *abort_flag = 1;                                    // protocol error: give up, the CTA reports NaN
+          break;
+        }
+      }
     }
   } else {
     const int s = warp >> 2;
