@@ -15,6 +15,10 @@ run() { timeout 60 "$bin" "$@" | tee -a "$out"; echo "# exit=$? args=$*" | tee -
 for v in 0 1 2 3 4 5 6; do
   run $v 128 64 64 64 0
 done
+# B operand MN-major without swizzle = the K-major image of the transposed matrix (dX from the forward weight images)
+for v in 7 8; do run $v 128 64 64 64 0; run $v 128 64 64 64 1; done
+run 7 128 224 64 64 0
+run 8 128 48 64 64 0
 # encoding fall-backs: LBO/SBO swapped
 for v in 1 2 3; do run $v 128 64 64 64 1; done
 # shapes the policy layers need: wider N (two layers' worth), K = 32, the M = 64 accumulator lane mapping

@@ -20,6 +20,9 @@
 //   variant 4: TS, A in TMEM (tcgen05.st), B K-major no swizzle, 3xTF32
 //   variant 5: SS, K-major no swizzle, 1xTF32 on RAW fp32 images (low 13 bits not cleared): does the tensor core
 //              truncate or round fp32 -> tf32?  (compare the two "err_vs_*_inputs" fields)
+//   variant 7: SS, A K-major no swizzle, B MN-major NO swizzle, 3xTF32: B's image is the K-major image of B^T, i.e. a
+//              forward weight image W[out][in] serves dX = dZ W without a transposed copy (needs b_major = MN)
+//   variant 8: the same with A in TMEM (the dX chain of the adjoint: dZ written by tcgen05.st)
 //   variant 6: SS, K-major no swizzle, "2.5-term" split with a 16-bit correction: tf32(A_raw, B_raw) + tf32(A_lo, B_raw)
 //              + bf16(A_bf16, B_lo_bf16), all three accumulating into the same fp32 TMEM tile (mixed kinds);
 //              the B side then costs 4 + 2 bytes per weight instead of 4 + 4
@@ -33,7 +36,7 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 
-enum { LAY_K_NONE = 0, LAY_K_SW128 = 1, LAY_MN_SW128 = 2 };
+enum { LAY_K_NONE = 0, LAY_K_SW128 = 1, LAY_MN_SW128 = 2, LAY_MN_NONE = 3 };
 
 struct Params {
   int M, N, K;
@@ -60,6 +63,13 @@ __host__ __device__ inline uint32_t lay_off(int lay, int r, int k, int R, int K)
     uint32_t o = (uint32_t)((k >> 5) * (R * 128) + (r >> 3) * 1024 + (r & 7) * 128 + (k & 31) * 4);
     return o ^ (((o >> 7) & 7u) << 4);
   }
+  if (lay == LAY_MN_NONE) {
+    // MN-major, no swizzle (cute: ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16-byte units): core matrix = 8 k-rows x 16 B
+    // (4 mn elements); mn-adjacent core matrices 128 B apart (SBO), 8-k groups (R/4)*128 B apart (LBO).  This is
+    // byte for byte the K-major unswizzled image of the TRANSPOSED operand ([k][mn] with mn contiguous), i.e. a
+    // forward weight image W[out][in] read as the B operand of dX = dZ W (n = in, k = out) without a second copy.
+    return (uint32_t)((k >> 3) * ((R >> 2) * 128) + (r >> 2) * 128 + (k & 7) * 16 + (r & 3) * 4);
+  }
   // LAY_MN_SW128: panels of 32 mn-elements; inside a panel the k rows are 128 B apart, 8-k groups 1024 B apart (SBO),
   // panels K*128 B apart (LBO); 16-byte chunk index ^= k % 8
   uint32_t o = (uint32_t)((r >> 5) * (K * 128) + (k >> 3) * 1024 + (k & 7) * 128 + (r & 31) * 4);
@@ -83,6 +93,7 @@ __device__ inline uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t
 __device__ inline uint64_t operand_desc(int lay, uint32_t base, int ks, int R, int K, int swap) {
   if (lay == LAY_K_NONE) return make_desc(base + ks * 256, 128, (K >> 2) * 128, 0, swap);
   if (lay == LAY_K_SW128) return make_desc(base + (ks >> 2) * (R * 128) + (ks & 3) * 32, 16, 1024, 2, swap);
+  if (lay == LAY_MN_NONE) return make_desc(base + ks * ((R >> 2) * 128), (R >> 2) * 128, 128, 0, swap);
   return make_desc(base + ks * 1024, K * 128, 1024, 2, swap);
 }
 
@@ -250,7 +261,8 @@ __global__ void __launch_bounds__(128, 1)
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   }
 
-  const uint32_t idesc = make_idesc(p.M, p.N, p.layA == LAY_MN_SW128, p.layB == LAY_MN_SW128);
+  const uint32_t idesc = make_idesc(p.M, p.N, p.layA == LAY_MN_SW128 || p.layA == LAY_MN_NONE,
+                                    p.layB == LAY_MN_SW128 || p.layB == LAY_MN_NONE);
   const int ksteps = p.K / 8;
   const int RB = (p.N + 31) / 32 * 32;
   uint32_t parity = 0;
@@ -376,6 +388,8 @@ int main(int argc, char** argv) {
   p.layA = p.layB = LAY_K_NONE;
   if (p.variant == 2) p.layA = p.layB = LAY_K_SW128;
   if (p.variant == 3) p.layA = p.layB = LAY_MN_SW128;
+  if (p.variant == 7 || p.variant == 8) p.layB = LAY_MN_NONE;      // A K-major (smem / TMEM), B MN-major unswizzled
+  if (p.variant == 8) p.a_in_tmem = 1;
   if (!(p.M == 64 || p.M == 128) || p.N % 16 || p.N < 16 || p.N > 256 || p.K % 32 || p.K < 32 || p.K > 128) {
     printf("unsupported shape: M in {64,128}, N %% 16 == 0 <= 256, K %% 32 == 0 <= 128\n");
     return 1;
