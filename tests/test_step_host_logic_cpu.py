@@ -2,7 +2,7 @@
 per-system input derivation) exercised WITHOUT a GPU: the CUDA stream / event objects are replaced by no-ops, the
 rollout runner by a stand-in that evaluates the CPU oracle, and the device prepare ops by the host dataset mirror.
 Nothing of the product computes on the CPU -- this is a test double for host-side logic only; the real kernels
-behind the same code are checked by tests/test_zz_input_side_gpu.py on the GPU."""
+behind the same code are checked by tests/test_zz_new_paths_gpu.py on the GPU."""
 import contextlib
 import ctypes
 

@@ -2,7 +2,7 @@
 parameters -> (hi, lo) K-major weight images: padding, Toeplitz block of the conv, fc1 column permutation), the op
 list and the stash addressing, emulated on the CPU from the PACKED images and compared with the oracle's policy
 forward in the layout the (GPU-verified) adjoint kernel reads.  The tcgen05 instructions themselves can only be
-checked on the GPU (tests/test_zz_input_side_gpu.py::test_tc_forward_*)."""
+checked on the GPU (tests/test_zz_new_paths_gpu.py::test_tc_forward_*)."""
 import ctypes
 import os
 import subprocess

@@ -2,7 +2,7 @@
 quad_dynamics_trained.py) exercised WITHOUT a GPU: `_capi.lib()` is replaced by a stand-in whose entry points take
 the same ctypes arguments and run the SAME kernel bodies compiled for the host (tests/hostcheck/*.cpp) on the CPU
 tensors' memory.  A test double for the host-side plumbing only -- the kernels themselves are checked on the GPU by
-tests/test_zz_input_side_gpu.py."""
+tests/test_zz_new_paths_gpu.py."""
 import contextlib
 import ctypes
 import os

@@ -1,6 +1,7 @@
-"""GPU tests of the input side of the path: the dataset layouts produced on the device and the
-chunked host-batch train step.  The file name sorts last on purpose: these kernels were written after the round's
-GPU budget was spent, so under `pytest -x` they run after every previously verified parity test.
+"""GPU tests of everything built after the round-1 GPU budget was spent: the input side of the path (SURVEY.md 8f N1 /
+N4: dataset layouts on the device, chunked host-batch train step, device-resident dataset), the closed-loop evaluation
+rollouts (N2, quadrotor + fixed wing), the learnt residual dynamics (N3) and the optional tcgen05 forward kernel.
+The file name sorts last on purpose: under `pytest -x` these run after every previously verified parity test.
 
 Tolerances (fp32): subtraction-only outputs bit-exact; outputs that go through sin/cos/sqrt/div 2e-6 of scale;
 train steps from raw host samples vs the same steps from prepared device tensors: loss 1e-5 relative, gradient L2
