@@ -144,7 +144,7 @@ PackTable hutter_pack_table(const HutterLayout& y) {
 
 struct Plan {
   int grid, ntiles;
-  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_tc, total;
+  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_tc, o_dzo, o_dz3, o_dz2, o_dz1, o_dzx, total;
 };
 
 NetInfo net_info(const apg_config* c) {
@@ -222,6 +222,13 @@ Plan make_plan(const apg_config* c, const NetInfo& y) {
   p.o_states = o; o += up256(sizeof(float) * (size_t)p.ntiles * c->horizon * S * TMP);
   // weight images of the optional tcgen05 forward (appended: the offsets above do not move)
   p.o_tc = o;     o += up256(tc_blob_bytes());
+  // dZ stash of the optional split adjoint (concurrent hutter nets only; appended as well)
+  const size_t dzt = (is_hutter(c) && !is_recurrent(c)) ? (size_t)p.ntiles : 0;
+  p.o_dzo = o;    o += up256(sizeof(float) * dzt * y.act_rows * TMP);
+  p.o_dz3 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
+  p.o_dz2 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
+  p.o_dz1 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
+  p.o_dzx = o;    o += up256(sizeof(float) * dzt * y.x1_rows * TMP);
   p.total = o;
   return p;
 }
@@ -265,6 +272,13 @@ bool use_tc_forward(const apg_config* c, const HutterLayout& y) {
   const char* e = getenv("APG_TC_FWD");
   if (!e || e[0] != '1') return false;
   return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && tc_fwd_supported(y, c->horizon);
+}
+
+// APG_TC_DW=1 selects the split adjoint (mma.sync dX chain + tcgen05 streaming dW GEMM) for the same configuration
+bool use_tc_dw(const apg_config* c, const HutterLayout& y) {
+  const char* e = getenv("APG_TC_DW");
+  if (!e || e[0] != '1') return false;
+  return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && adj_dw_tc_supported(y, c->horizon);
 }
 
 // cached device buffers of the host-buffer entry point
@@ -358,6 +372,19 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
   cudaError_t ce;
   if (is_hutter(cfg)) {
     if (is_recurrent(cfg)) { if ((ce = launch_rec_adj(hutter_layout(cfg), a, p.grid, st))) return (int)ce; }
+    else if (use_tc_dw(cfg, hutter_layout(cfg))) {
+      // optional split adjoint (APG_TC_DW=1): dX chain + dZ stash, then the streaming tcgen05 weight-gradient GEMM
+      const HutterLayout y = hutter_layout(cfg);
+      char* w = static_cast<char*>(workspace);
+      DzStash z;
+      z.o = reinterpret_cast<float*>(w + p.o_dzo);  z.z3 = reinterpret_cast<float*>(w + p.o_dz3);
+      z.z2 = reinterpret_cast<float*>(w + p.o_dz2); z.z1 = reinterpret_cast<float*>(w + p.o_dz1);
+      z.x = reinterpret_cast<float*>(w + p.o_dzx);
+      if ((ce = launch_hutter_adj_dx(cfg->system, y, a, z, p.grid, st))) return (int)ce;
+      if ((ce = launch_adj_dw_tc(y, a, z, p.grid, st))) return (int)ce;
+      if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;
+      return 0;                                   // the partials are already in torch column order
+    }
     else if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
   } else if (cfg->net == NET_LSTM) {
     if ((ce = launch_lstm_adj(lstm_layout(cfg), a, p.grid, st))) return (int)ce;

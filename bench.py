@@ -335,6 +335,8 @@ def main():
     ap.add_argument("--no-raw-e2e", action="store_true", help="skip the raw-sample (step_host) end-to-end arm")
     ap.add_argument("--tc-forward", action="store_true",
                     help="use the optional tcgen05/TMEM forward kernel (APG_TC_FWD=1; quad_concurrent only)")
+    ap.add_argument("--tc-dw", action="store_true",
+                    help="use the optional split adjoint: mma.sync dX chain + tcgen05 streaming dW GEMM (APG_TC_DW=1)")
     args = ap.parse_args()
     # hard wall-clock bound for the whole process: dump the Python stacks and exit instead of hanging a GPU box
     faulthandler.dump_traceback_later(int(os.environ.get("APG_BENCH_WATCHDOG_S", "1500")), exit=True)
@@ -350,6 +352,8 @@ def main():
         return
     if args.tc_forward:
         os.environ["APG_TC_FWD"] = "1"
+    if args.tc_dw:
+        os.environ["APG_TC_DW"] = "1"
 
     if args.warmup < 3:
         args.warmup = 3
@@ -500,6 +504,8 @@ def main():
             "config": {"workload": w["label"], "horizon": h, "n_drones_per_gpu": n, "n_drones_total": n * world,
                        "forward_kernel": "hutter_fwd_tc_kernel (tcgen05/TMEM)" if os.environ.get("APG_TC_FWD") == "1"
                        and args.workload == "quad_concurrent" else "default (mma.sync)",
+                       "adjoint_kernel": "hutter_adj_dx_kernel + adj_dw_tc_kernel (tcgen05/TMEM)"
+                       if os.environ.get("APG_TC_DW") == "1" and args.workload == "quad_concurrent" else "default (mma.sync)",
                        "policy_init": "torch default init, seed 0", "optimizer": "SGD lr %g momentum 0.9" % LR[w["system"]],
                        "l2": "flushed between timed steps (256 MiB write, untimed)" if flush_buf is not None else "not flushed",
                        "parallelism": f"dp{world} (drone-axis shards, one NCCL sum-allreduce of the flat gradient)"},

@@ -77,3 +77,89 @@ extern "C" void hc_tc_emulate(const unsigned char* blob, const float* in_state, 
         st_act[stash_index(tile, row, MO, o)] = (float)(1.0 / (1.0 + exp(-(Dm[o] + bias[B_O + o]))));
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// streaming weight-gradient GEMM (csrc/adj_dw_layout.cuh): the loaders' image fill and the issuer's 3xTF32 products
+// emulated from the images (fp64 accumulation), then the accumulator -> gradient map of the kernel's epilogue
+// ---------------------------------------------------------------------------------------------------------------
+#include "adj_dw_layout.cuh"
+
+extern "C" int hc_dw_num_params() { return make_hutter_layout(F0, H, RD, MO, 1).n_params; }
+
+extern "C" void hc_dw_emulate(const float* st_x1, const float* st_h1, const float* st_h2, const float* st_h3,
+                              const float* in_state, const float* in_ref, const float* dzo, const float* dz3,
+                              const float* dz2, const float* dz1, const float* dzx, int n, float* P) {
+  using dw::AM; using dw::KD; using dw::C_TOTAL; using dw::STAGE_BYTES; using dw::A_IMG_BYTES;
+  using dw::B_IMG_BYTES; using dw::B_ROWS; using dw::chunk_off; using dw::chunk_of_item; using dw::a_chunk;
+  using dw::b_chunk; using dw::grad_index; using dw::conv_weight_from_block; using dw::conv_bias_from_block;
+  using dw::C_WO; using dw::C_W3; using dw::C_W2; using dw::C_W1A; using dw::C_W1B; using dw::C_WS; using dw::C_WT;
+  const HutterLayout y = make_hutter_layout(F0, H, RD, MO, 1);
+  dw::Sources S;
+  S.h3 = st_h3; S.h2 = st_h2; S.h1 = st_h1; S.x1 = st_x1; S.in_state = in_state; S.in_ref = in_ref;
+  S.dzo = dzo; S.dz3 = dz3; S.dz2 = dz2; S.dz1 = dz1; S.dzx = dzx;
+  std::vector<double> D((size_t)AM * C_TOTAL, 0.0);                       // [lane = A row][column]
+  std::vector<unsigned char> stage(STAGE_BYTES);
+  unsigned char *a_hi = stage.data(), *a_lo = a_hi + A_IMG_BYTES, *b_hi = a_lo + A_IMG_BYTES, *b_lo = b_hi + B_IMG_BYTES;
+  auto put = [&](unsigned char* hi, unsigned char* lo, uint32_t off, const float* x) {
+    for (int c = 0; c < 4; ++c) {
+      float h, l;
+      split_hi_lo(x[c], &h, &l);
+      memcpy(hi + off + 4 * c, &h, 4);
+      memcpy(lo + off + 4 * c, &l, 4);
+    }
+  };
+  auto at = [&](const unsigned char* img, int r, int k) {
+    float v;
+    memcpy(&v, img + chunk_off(r, k >> 2) + (k & 3) * 4, 4);
+    return (double)v;
+  };
+  const int ntiles = (n + TM - 1) / TM;
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int valid = n - tile * TM < TM ? n - tile * TM : TM;
+    for (int i = 0; i < dw::NOPS; ++i) {
+      const dw::Op op = dw::op_of(i);
+      for (int q = 0; q < AM * (KD / 4); ++q) {
+        int r, d4; float x[4];
+        chunk_of_item(q, &r, &d4);
+        a_chunk(op, S, tile, valid, r, d4, x);
+        put(a_hi, a_lo, chunk_off(r, d4), x);
+      }
+      for (int q = 0; q < B_ROWS * (KD / 4); ++q) {
+        int r, d4; float x[4];
+        chunk_of_item(q, &r, &d4);
+        b_chunk(op, S, tile, r, d4, x);
+        put(b_hi, b_lo, chunk_off(r, d4), x);
+      }
+      const bool clear = tile == 0 && op.first;
+      for (int r = 0; r < AM; ++r)
+        for (int c = 0; c < op.N; ++c) {
+          double acc = clear ? 0.0 : D[(size_t)r * C_TOTAL + op.d_col + c];
+          for (int k = 0; k < KD; ++k)
+            acc += at(a_lo, r, k) * at(b_hi, c, k) + at(a_hi, r, k) * at(b_lo, c, k) + at(a_hi, r, k) * at(b_hi, c, k);
+          D[(size_t)r * C_TOTAL + op.d_col + c] = acc;
+        }
+    }
+  }
+  for (int i = 0; i < y.n_params; ++i) P[i] = 0.f;
+  const int col0[6] = {C_WO, C_W3, C_W2, C_W1A, C_W1B, C_WS}, ncol[6] = {48, 64, 64, 64, 64, 64};
+  std::vector<int> written(y.n_params, 0);
+  for (int reg = 0; reg < 6; ++reg)
+    for (int r = 0; r < AM; ++r)
+      for (int c = 0; c < ncol[reg]; ++c) {
+        const int idx = grad_index(y, reg, r, c);
+        if (idx >= 0) { P[idx] = (float)D[(size_t)r * C_TOTAL + col0[reg] + c]; ++written[idx]; }
+      }
+  std::vector<float> T(37 * 48);
+  for (int r = 0; r <= 4 * RD; ++r)
+    for (int c = 0; c < 48; ++c) T[r * 48 + c] = (float)D[(size_t)r * C_TOTAL + C_WT + c];
+  for (int i = 0; i < NC * RD * 3 + NC; ++i) {
+    if (i < NC * RD * 3) P[y.t_wc + i] = conv_weight_from_block(T.data(), 48, i / (RD * 3), (i / 3) % RD, i % 3);
+    else P[y.t_wc + i] = conv_bias_from_block(T.data(), 48, i - NC * RD * 3);
+    ++written[y.t_wc + i];
+  }
+  // every entry outside ref_in.* must have been written exactly once (the kernel relies on it: no zero-fill there)
+  for (int i = 0; i < y.n_params; ++i) {
+    const bool ref_in = i >= y.t_wr && i < y.t_br + HID;
+    if (written[i] != (ref_in ? 0 : 1)) P[i] = NAN;
+  }
+}

@@ -92,3 +92,63 @@ def test_packed_images_are_hi_lo_splits_with_zero_padding(ht):
     hi = blob[off:off + 4].view(np.float32)[0]
     lo = blob[64 * 16 * 4 + off:64 * 16 * 4 + off + 4].view(np.float32)[0]
     assert np.float32(hi) + np.float32(lo) == params[0][3, 7].numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# streaming weight-gradient GEMM of the optional split adjoint (csrc/adj_dw_layout.cuh)
+# ---------------------------------------------------------------------------------------------------------------
+def _stash(a, rows):
+    """(n, rows) -> [ntiles64][rows][TMP] float32 with finite garbage in dead columns and NaN in the padding"""
+    n = a.shape[0]
+    nt = (n + TM - 1) // TM
+    st = np.full((nt, rows, TMP), np.nan, np.float32)
+    full = np.zeros((nt * TM, rows), np.float32)
+    full[:n] = a
+    st[:, :, :TM] = full.reshape(nt, TM, rows).transpose(0, 2, 1)
+    return st
+
+
+@pytest.mark.parametrize("n", [64, 65, 200])
+def test_streaming_dw_gemm_reproduces_the_weight_gradient(ht, n):
+    h = 10
+    params = [p.double() for p in B.default_init("quad", h, seed=100 + n)]
+    ws, bs, wc, bc, wr, br, w1, b1, w2, b2, w3, b3, wo, bo = params
+    case = SY.quad_case(n, h, 0.1, seed=n)
+    ins, inr = case["in_state"].double(), case["in_ref"].double()
+    s = torch.tanh(ins @ ws.t() + bs)
+    conv = O._conv_encoder(inr, wc, bc)                                     # channel-major (c*8 + t)
+    x = torch.cat((s, conv), 1)
+    a1 = torch.tanh(x @ w1.t() + b1)
+    a2 = torch.tanh(a1 @ w2.t() + b2)
+    a3 = torch.tanh(a2 @ w3.t() + b3)
+    g = torch.Generator().manual_seed(n)
+    dzo = torch.randn(n, 40, generator=g, dtype=torch.float64)
+    dz3 = (dzo @ wo) * (1 - a3 ** 2)
+    dz2 = (dz3 @ w3) * (1 - a2 ** 2)
+    dz1 = (dz2 @ w2) * (1 - a1 ** 2)
+    dx = dz1 @ w1
+    ds = dx[:, :64] * (1 - s ** 2)
+    dconv = dx[:, 64:] * (conv > 0)
+    pm = lambda t: t.reshape(n, 20, 8).transpose(1, 2).reshape(n, 160)      # noqa: E731  channel- -> position-major
+    f32 = lambda t: t.float().numpy()                                        # noqa: E731
+    st_x1, st_h1, st_h2, st_h3 = _stash(f32(torch.cat((s, pm(conv)), 1)), 224), _stash(f32(a1), 64), \
+        _stash(f32(a2), 64), _stash(f32(a3), 64)
+    z_o, z_3, z_2, z_1 = _stash(f32(dzo), 40), _stash(f32(dz3), 64), _stash(f32(dz2), 64), _stash(f32(dz1), 64)
+    z_x = _stash(f32(torch.cat((ds, pm(dconv)), 1)), 224)
+    ins32 = np.ascontiguousarray(case["in_state"].numpy(), np.float32)
+    inr32 = np.ascontiguousarray(case["in_ref"].numpy(), np.float32)
+    P = np.zeros(ht.hc_dw_num_params(), np.float32)
+    ht.hc_dw_emulate(_p(st_x1), _p(st_h1), _p(st_h2), _p(st_h3), _p(ins32), _p(inr32), _p(z_o), _p(z_3), _p(z_2),
+                     _p(z_1), _p(z_x), n, _p(P))
+    assert np.isfinite(P).all(), "an entry was written twice / not at all, or padding leaked into a product"
+    gwc = torch.einsum("nct,ntjd->cdj", dconv.reshape(n, 20, 8),
+                       torch.stack([inr[:, t:t + 3, :] for t in range(8)], 1))          # [c][ci][j]
+    want = [ds.t() @ ins, ds.sum(0), gwc, dconv.reshape(n, 20, 8).sum((0, 2)), torch.zeros(64, 90), torch.zeros(64),
+            dz1.t() @ x, dz1.sum(0), dz2.t() @ a1, dz2.sum(0), dz3.t() @ a2, dz3.sum(0), dzo.t() @ a3, dzo.sum(0)]
+    o = 0
+    for i, w in enumerate(want):
+        got = P[o:o + w.numel()].reshape(w.shape)
+        o += w.numel()
+        scale = max(float(w.abs().max()), 1e-6)
+        assert np.abs(got - w.numpy()).max() <= 2e-5 * scale + (0 if i not in (4, 5) else 0), i
+    assert o == P.size

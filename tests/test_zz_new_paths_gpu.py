@@ -444,3 +444,49 @@ def test_tc_forward_matches_default_forward(n):
     assert float((a1 - a0).abs().max()) <= 1e-5
     assert float((s1 - s0).abs().max()) <= 1e-5 * max(float(s0.abs().max()), 1.0)
     assert rel_err(g1, g0) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optional split adjoint (APG_TC_DW=1): mma.sync dX chain + dZ stash (hutter_adj_dx_kernel), then the weight gradient
+# as a streaming tcgen05 GEMM over the drone axis (adj_dw_tc_kernel) -- same gradient as the default adjoint
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [64, 1, 65, 300, 1000, 9600, 148 * 64 * 3 + 5])
+@pytest.mark.parametrize("tc_fwd", [0, 1])
+def test_split_adjoint_matches_default_adjoint(n, tc_fwd):
+    import os
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    h, dt = 10, 0.1
+    params = B.default_init("quad", h, seed=n % 97)
+    case = {k: v.cuda() for k, v in SY.quad_case(n, h, dt, seed=n % 89).items()}
+    flat = R.flatten_params(params).cuda()
+    spec = R.RolloutSpec.quad_concurrent(h, dt)
+
+    def run():
+        r = R.Rollout(spec, n, "cuda:0")
+        loss, _, _ = r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
+        grad = r.backward(1.0)
+        grad2 = r.backward(0.5)                      # the adjoint can be repeated and scales with grad_loss
+        torch.cuda.synchronize()
+        return float(loss.item()), grad.cpu(), grad2.cpu()
+    for k in ("APG_TC_FWD", "APG_TC_DW"):
+        os.environ.pop(k, None)
+    l0, g0, _ = run()
+    os.environ["APG_TC_DW"] = "1"
+    if tc_fwd:
+        os.environ["APG_TC_FWD"] = "1"
+    try:
+        l1, g1, g1h = run()
+    finally:
+        for k in ("APG_TC_FWD", "APG_TC_DW"):
+            os.environ.pop(k, None)
+    assert np.isfinite(l1) and bool(torch.isfinite(g1).all()), "tcgen05 kernel reported a protocol timeout (NaN)"
+    assert abs(l1 - l0) <= 1e-5 * abs(l0)
+    assert rel_err(g1, g0) <= 1e-4
+    assert rel_err(2.0 * g1h, g1) <= 1e-6
+    like = [torch.empty_like(p) for p in params]
+    for a, b, name in zip(R.split_flat(g1, like), R.split_flat(g0, like), range(14)):
+        if float(b.norm()) > 0:
+            assert rel_err(a, b) <= 2e-4, name
+        else:
+            assert float(a.abs().max()) == 0.0, name          # ref_in.*: unused by the conv net -> exactly zero

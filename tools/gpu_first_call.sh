@@ -24,6 +24,9 @@ done
 # 2b. the optional tcgen05 forward in the product bench (only meaningful if its parity test passed above)
 timeout 300 python bench.py --tc-forward --steps 30 --no-cpu-baseline --no-raw-e2e > "$out/bench_tc_forward.json" 2> "$out/bench_tc_forward.err"
 
+timeout 300 python bench.py --tc-dw --steps 30 --no-cpu-baseline --no-raw-e2e > "$out/bench_tc_dw.json" 2> "$out/bench_tc_dw.err"
+timeout 300 python bench.py --tc-forward --tc-dw --steps 30 --no-cpu-baseline --no-raw-e2e > "$out/bench_tc_both.json" 2> "$out/bench_tc_both.err"
+
 # 3. launch list of a short bench run (shares of the step, not absolute times)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches.csv" \
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-raw-e2e > "$out/bench_under_ncu.log" 2>&1
