@@ -380,7 +380,12 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
       z.o = reinterpret_cast<float*>(w + p.o_dzo);  z.z3 = reinterpret_cast<float*>(w + p.o_dz3);
       z.z2 = reinterpret_cast<float*>(w + p.o_dz2); z.z1 = reinterpret_cast<float*>(w + p.o_dz1);
       z.x = reinterpret_cast<float*>(w + p.o_dzx);
-      if ((ce = launch_hutter_adj_dx(cfg->system, y, a, z, p.grid, st))) return (int)ce;
+      const char* dx = getenv("APG_TC_DX");
+      if (dx && dx[0] == '1') {
+        // dX chain on tcgen05 as well (forward weight images read MN-major); repacks the images (parameters only)
+        unsigned char* blob = static_cast<unsigned char*>(workspace) + p.o_tc;
+        if ((ce = launch_hutter_adj_dx_tc(y, params, blob, a, z, p.grid, st))) return (int)ce;
+      } else if ((ce = launch_hutter_adj_dx(cfg->system, y, a, z, p.grid, st))) return (int)ce;
       if ((ce = launch_adj_dw_tc(y, a, z, p.grid, st))) return (int)ce;
       if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;
       return 0;                                   // the partials are already in torch column order

@@ -361,6 +361,253 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
+// =========================================================================================================
+// tcgen05 dX chain of the split adjoint (OPTIONAL PATH, APG_TC_DX=1 on top of APG_TC_DW=1): the tcgen05 counterpart
+// of hutter_adj_dx_kernel.  Same roles and hand-off protocol as hutter_fwd_tc_kernel; the A operands are the dZ_l
+// written to TMEM by the owning threads, the B operands are the SAME forward weight images read MN-major: the
+// unswizzled K-major image of W[out][in] is byte for byte the unswizzled MN-major image of W^T (CUTLASS canonical
+// forms, cute/atom/mma_traits_sm100.hpp; microbenchmark tools/micro/tcgen05_gemm.cu variants 7 / 8), so
+//     dX[drone][in] = sum_out dZ[drone][out] W[out][in]
+// needs b_major = MN, LBO = (K_f / 4) * 128 (8-row groups of the image = k groups), SBO = 128 (adjacent 16-byte
+// chunks = adjacent groups of four `in` features) and start address + ks * LBO.  Reads the activation stash, writes
+// the dZ stash adj_dw_tc_kernel consumes.
+// =========================================================================================================
+namespace {
+
+// one GEMM of the reverse op list: D[d_col, +N) = A[0, K) * W  with W's forward image (rows, Kf) read MN-major
+struct ROp { int img_off, rows, Kf, K, N, d_col; };
+constexpr int NROPS = 8;
+__device__ __forceinline__ ROp rop_of(int i) {
+  if (i == 0) return {I_WO.off, 48, 64, 40, 64, C_DMAIN};                         // dH3 = dZo Wo
+  if (i == 1) return {I_W3.off, 64, 64, 64, 64, C_DMAIN};                         // dH2 = dZ3 W3
+  if (i == 2) return {I_W2.off, 64, 64, 64, 64, C_DMAIN};                         // dH1 = dZ2 W2
+  if (i == 3) return {I_W1S.off, 64, 64, 64, 64, C_DMAIN};                        // ds  = dZ1 W1[:, :64]
+  return {I_W1G.off + (i - 4) * 2 * img_bytes(64, 40), 64, 40, 64, 48, C_DCONV};  // dconv of position pair i - 4
+}
+__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t base, int ks, int Kf) {
+  const uint32_t lbo = (Kf >> 2) * 128, sbo = 128, addr = base + ks * lbo;
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_tf32_bmn(int M, int N) { return idesc_tf32(M, N) | (1u << 16); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    hutter_adj_dx_tc_kernel(const unsigned char* __restrict__ blob, const HutterLayout y, const RolloutArgs g,
+                            const DzStash z) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) TcBars s_bars;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_abort;
+  using Sys = Quad<float>;
+  constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < BLOB_BYTES / 16; i += blockDim.x) ((uint4*)base)[i] = ((const uint4*)blob)[i];
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      tc_mbar_init(smem_u32(&s_bars.a_ready[s]), 128);
+      tc_mbar_init(smem_u32(&s_bars.d_ready[s]), 1);
+    }
+    s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  const int n = g.N;
+  const int ntiles = (n + TMT - 1) / TMT;
+  const int ntiles64 = (n + TM - 1) / TM;
+  const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  volatile int* abort_flag = &s_abort;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t par[2] = {0, 0};
+      int op_i[2] = {0, 0}, tile_j[2] = {0, 1};
+      int remaining = my_tiles * NROPS;
+      long long t_idle = clock64();
+      while (remaining > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (tile_j[s] >= my_tiles) continue;
+          if (!tc_mbar_test(smem_u32(&s_bars.a_ready[s]), par[s])) continue;
+          par[s] ^= 1;
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const ROp op = rop_of(op_i[s]);
+          const uint32_t idesc = idesc_tf32_bmn(TMT, op.N);
+          const uint32_t whi = smem_u32(base + op.img_off), wlo = whi + img_bytes(op.rows, op.Kf);
+          const uint32_t slot = tmem + s * SLOT_COLS;
+          const uint32_t d = slot + op.d_col, ahi = slot + C_AHI, alo = slot + C_ALO;
+          for (int ks = 0; ks < op.K / 8; ++ks) {
+            const uint64_t bh = mnmajor_desc(whi, ks, op.Kf), bl = mnmajor_desc(wlo, ks, op.Kf);
+            mma_ts(d, alo + ks * 8, bh, idesc, ks > 0 ? 1u : 0u);
+            mma_ts(d, ahi + ks * 8, bl, idesc, 1u);
+            mma_ts(d, ahi + ks * 8, bh, idesc, 1u);
+          }
+          mma_commit(smem_u32(&s_bars.d_ready[s]));
+          if (++op_i[s] == NROPS) { op_i[s] = 0; tile_j[s] += 2; }
+          --remaining;
+          progressed = true;
+        }
+        if (progressed) {
+          t_idle = clock64();
+        } else if (*abort_flag || clock64() - t_idle > 2000000000LL) {
+          *abort_flag = 1;
+          break;
+        }
+      }
+    }
+  } else {
+    const int s = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t slot = tmem + s * SLOT_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t d_main = slot + C_DMAIN, d_conv = slot + C_DCONV, ahi = slot + C_AHI, alo = slot + C_ALO;
+    const uint32_t bar_a = smem_u32(&s_bars.a_ready[s]), bar_d = smem_u32(&s_bars.d_ready[s]);
+    const float poison = __int_as_float(0x7fc00000);
+    uint32_t par = 0;
+    auto wait_d = [&]() {
+      tc_mbar_wait(bar_d, par, abort_flag);
+      par ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    };
+    for (int j = s; j < my_tiles; j += 2) {
+      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+      const size_t drone = (size_t)tile * TMT + row;
+      const bool live = drone < (size_t)n;
+      const bool stash = tile * 2 + (row >> 6) < ntiles64;
+      // ---- reverse dynamics sweep of this drone (dyn_phase.cuh dyn_adjoint_conc, on the stash layout): dlog[40]
+      float dlog[MO];
+#pragma unroll
+      for (int q = 0; q < MO; ++q) dlog[q] = 0.f;
+      if (live) {
+        float s0[S], sk[S], sn[S], a[A], rf[R], gq[S], gs[S], ga[A], ga2[A];
+        const float* cur_g = g.cur + drone * S;
+        const float* ref_g = g.ref + drone * g.ref_rows * R;
+#pragma unroll
+        for (int q = 0; q < S; ++q) { s0[q] = cur_g[q]; gq[q] = 0.f; }
+#pragma unroll
+        for (int q = 0; q < S; ++q) sn[q] = g.st_states[stash_index(tile, row, H * S, (H - 1) * S + q)];
+#pragma unroll
+        for (int k = H - 1; k >= 0; --k) {
+#pragma unroll
+          for (int c = 0; c < A; ++c) { a[c] = g.st_act[stash_index(tile, row, MO, k * A + c)]; ga[c] = 0.f; }
+#pragma unroll
+          for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
+          if (k > 0) {
+#pragma unroll
+            for (int q = 0; q < S; ++q) sk[q] = g.st_states[stash_index(tile, row, H * S, (k - 1) * S + q)];
+          } else {
+#pragma unroll
+            for (int q = 0; q < S; ++q) sk[q] = s0[q];
+          }
+          Sys::loss_grad(sn, rf, a, s0, k, H, gq, ga);
+          Sys::step_adj(sk, a, g.dt, g.pc.v, gq, gs, ga2);
+#pragma unroll
+          for (int c = 0; c < A; ++c) dlog[k * A + c] = (ga[c] + ga2[c]) * a[c] * (1.f - a[c]);      // sigmoid'
+#pragma unroll
+          for (int q = 0; q < S; ++q) { gq[q] = gs[q]; sn[q] = sk[q]; }
+        }
+      }
+      if (stash) {
+#pragma unroll
+        for (int q = 0; q < MO; ++q) z.o[stash_index(tile, row, MO, q)] = dlog[q];
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < MO; c0 += 8) tmem_st8_split(ahi + c0, alo + c0, dlog + c0);
+      a_operand_ready(bar_a);
+      // ---- dZ_l = (dZ_{l+1} W_{l+1}) (.) (1 - X_l^2) for h3, h2, h1: D_main -> A operand + dZ stash
+      const float* xs[3] = {g.st_h3, g.st_h2, g.st_h1};
+      float* zs[3] = {z.z3, z.z2, z.z1};
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        wait_d();
+#pragma unroll
+        for (int c0 = 0; c0 < HID; c0 += 8) {
+          float v[8];
+          tmem_ld8(d_main + c0, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float yv = stash ? xs[l][stash_index(tile, row, HID, c0 + q)] : 0.f;
+            v[q] *= 1.f - yv * yv;
+            if (stash) zs[l][stash_index(tile, row, HID, c0 + q)] = *abort_flag ? poison : v[q];
+          }
+          tmem_st8_split(ahi + c0, alo + c0, v);
+        }
+        a_operand_ready(bar_a);
+      }
+      // ---- first layer: ds = (dZ1 W1[:, :64]) (.) (1 - s^2); the A operand (dZ1) stays for the conv pieces
+      wait_d();
+#pragma unroll
+      for (int c0 = 0; c0 < HID; c0 += 8) {
+        float v[8];
+        tmem_ld8(d_main + c0, v);
+        if (stash) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float yv = g.st_x1[stash_index(tile, row, K1, c0 + q)];
+            z.x[stash_index(tile, row, K1, c0 + q)] = *abort_flag ? poison : v[q] * (1.f - yv * yv);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      tc_mbar_arrive(bar_a);                                   // D_main has been read: go on with the conv pieces
+#pragma unroll
+      for (int gp = 0; gp < 4; ++gp) {
+        wait_d();
+#pragma unroll
+        for (int c0 = 0; c0 < 40; c0 += 8) {
+          float v[8];
+          tmem_ld8(d_conv + c0, v);
+          if (stash) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int xr = x1_row_of_conv(gp, c0 + q);
+              const float yv = g.st_x1[stash_index(tile, row, K1, xr)];
+              z.x[stash_index(tile, row, K1, xr)] = *abort_flag ? poison : (yv > 0.f ? v[q] : 0.f);      // relu'
+            }
+          }
+        }
+        if (gp < 3) {
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          tc_mbar_arrive(bar_a);                               // D_conv is free for the next position pair
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, unsigned char* blob,
+                                    const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st) {
+  apg_pack_tc_kernel<<<(PAIRS_TOTAL + B_TOTAL + 255) / 256, 256, 0, st>>>(params, y, blob);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(hutter_adj_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  hutter_adj_dx_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(blob, y, a, z);
+  return cudaGetLastError();
+}
+
 size_t tc_blob_bytes() { return (size_t)BLOB_BYTES; }
 
 bool tc_fwd_supported(const HutterLayout& y, int h) {

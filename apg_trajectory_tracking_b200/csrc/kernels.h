@@ -23,6 +23,8 @@ cudaError_t launch_hutter_fwd_tc(const HutterLayout& y, const float* params, uns
 struct DzStash { float *o, *z3, *z2, *z1, *x; };      // [tile][Mo4 | 64 | 64 | 64 | K1][TMP]
 cudaError_t launch_hutter_adj_dx(int system, const HutterLayout& y, const RolloutArgs& a, const DzStash& z, int grid,
                                  cudaStream_t st);
+cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, unsigned char* blob,
+                                    const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st);
 cudaError_t launch_adj_dw_tc(const HutterLayout& y, const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st);
 bool adj_dw_tc_supported(const HutterLayout& y, int h);
 

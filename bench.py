@@ -337,6 +337,8 @@ def main():
                     help="use the optional tcgen05/TMEM forward kernel (APG_TC_FWD=1; quad_concurrent only)")
     ap.add_argument("--tc-dw", action="store_true",
                     help="use the optional split adjoint: mma.sync dX chain + tcgen05 streaming dW GEMM (APG_TC_DW=1)")
+    ap.add_argument("--tc-dx", action="store_true",
+                    help="split adjoint with the dX chain on tcgen05 as well (APG_TC_DW=1 APG_TC_DX=1)")
     args = ap.parse_args()
     # hard wall-clock bound for the whole process: dump the Python stacks and exit instead of hanging a GPU box
     faulthandler.dump_traceback_later(int(os.environ.get("APG_BENCH_WATCHDOG_S", "1500")), exit=True)
@@ -354,6 +356,9 @@ def main():
         os.environ["APG_TC_FWD"] = "1"
     if args.tc_dw:
         os.environ["APG_TC_DW"] = "1"
+    if args.tc_dx:
+        os.environ["APG_TC_DW"] = "1"
+        os.environ["APG_TC_DX"] = "1"
 
     if args.warmup < 3:
         args.warmup = 3
@@ -504,7 +509,8 @@ def main():
             "config": {"workload": w["label"], "horizon": h, "n_drones_per_gpu": n, "n_drones_total": n * world,
                        "forward_kernel": "hutter_fwd_tc_kernel (tcgen05/TMEM)" if os.environ.get("APG_TC_FWD") == "1"
                        and args.workload == "quad_concurrent" else "default (mma.sync)",
-                       "adjoint_kernel": "hutter_adj_dx_kernel + adj_dw_tc_kernel (tcgen05/TMEM)"
+                       "adjoint_kernel": ("hutter_adj_dx_tc_kernel" if os.environ.get("APG_TC_DX") == "1" else
+                                          "hutter_adj_dx_kernel") + " + adj_dw_tc_kernel (tcgen05/TMEM)"
                        if os.environ.get("APG_TC_DW") == "1" and args.workload == "quad_concurrent" else "default (mma.sync)",
                        "policy_init": "torch default init, seed 0", "optimizer": "SGD lr %g momentum 0.9" % LR[w["system"]],
                        "l2": "flushed between timed steps (256 MiB write, untimed)" if flush_buf is not None else "not flushed",

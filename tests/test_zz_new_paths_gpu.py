@@ -451,8 +451,11 @@ def test_tc_forward_matches_default_forward(n):
 # as a streaming tcgen05 GEMM over the drone axis (adj_dw_tc_kernel) -- same gradient as the default adjoint
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [64, 1, 65, 300, 1000, 9600, 148 * 64 * 3 + 5])
-@pytest.mark.parametrize("tc_fwd", [0, 1])
-def test_split_adjoint_matches_default_adjoint(n, tc_fwd):
+@pytest.mark.parametrize("flags", [("APG_TC_DW",), ("APG_TC_DW", "APG_TC_FWD"), ("APG_TC_DW", "APG_TC_DX"),
+                                   ("APG_TC_DW", "APG_TC_DX", "APG_TC_FWD")])
+def test_split_adjoint_matches_default_adjoint(n, flags):
+    """APG_TC_DW: mma.sync dX chain + tcgen05 dW GEMM; + APG_TC_DX: the dX chain on tcgen05 too (forward weight images
+    read MN-major); + APG_TC_FWD: the tcgen05 forward writes the stash"""
     import os
     import bench as B
     PR, R, SY, T, DS = _mods()
@@ -469,16 +472,16 @@ def test_split_adjoint_matches_default_adjoint(n, tc_fwd):
         grad2 = r.backward(0.5)                      # the adjoint can be repeated and scales with grad_loss
         torch.cuda.synchronize()
         return float(loss.item()), grad.cpu(), grad2.cpu()
-    for k in ("APG_TC_FWD", "APG_TC_DW"):
+    all_flags = ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX")
+    for k in all_flags:
         os.environ.pop(k, None)
     l0, g0, _ = run()
-    os.environ["APG_TC_DW"] = "1"
-    if tc_fwd:
-        os.environ["APG_TC_FWD"] = "1"
+    for k in flags:
+        os.environ[k] = "1"
     try:
         l1, g1, g1h = run()
     finally:
-        for k in ("APG_TC_FWD", "APG_TC_DW"):
+        for k in all_flags:
             os.environ.pop(k, None)
     assert np.isfinite(l1) and bool(torch.isfinite(g1).all()), "tcgen05 kernel reported a protocol timeout (NaN)"
     assert abs(l1 - l0) <= 1e-5 * abs(l0)

@@ -26,6 +26,7 @@ timeout 300 python bench.py --tc-forward --steps 30 --no-cpu-baseline --no-raw-e
 
 timeout 300 python bench.py --tc-dw --steps 30 --no-cpu-baseline --no-raw-e2e > "$out/bench_tc_dw.json" 2> "$out/bench_tc_dw.err"
 timeout 300 python bench.py --tc-forward --tc-dw --steps 30 --no-cpu-baseline --no-raw-e2e > "$out/bench_tc_both.json" 2> "$out/bench_tc_both.err"
+timeout 300 python bench.py --tc-forward --tc-dx --steps 30 --no-cpu-baseline --no-raw-e2e > "$out/bench_tc_all.json" 2> "$out/bench_tc_all.err"
 
 # 3. launch list of a short bench run (shares of the step, not absolute times)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches.csv" \
