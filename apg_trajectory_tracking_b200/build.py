@@ -31,17 +31,37 @@ def needs_build():
 
 
 def build(force=False, verbose=False, profile=False):
-    """profile=True builds libapg_b200_prof.so with per-phase cycle counters (tools/phase_profile.py)"""
+    """profile=True builds libapg_b200_prof.so with per-phase cycle counters (tools/phase_profile.py).
+    The translation units are compiled in parallel (one nvcc per .cu) and linked into one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
     out = LIB.replace(".so", "_prof.so") if profile else LIB
     if not force and not profile and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DAPG_PROFILE"] if profile else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libapg_b200.so")
+    objdir = os.path.join(HERE, "build", "prof" if profile else "obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else []) + \
+            (["-DAPG_PROFILE"] if profile else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run([_nvcc()] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True,
+                             text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = [r for r in results if r[2].returncode != 0]
+    for src, _, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+    if failed:
+        raise RuntimeError("nvcc failed on " + ", ".join(r[0] for r in failed))
+    link = subprocess.run([_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a"] +
+                          [r[1] for r in results] + ["-o", out], capture_output=True, text=True)
+    if verbose or link.returncode != 0:
+        sys.stderr.write(link.stdout + link.stderr)
+    if link.returncode != 0:
+        raise RuntimeError("nvcc failed linking libapg_b200.so")
     return out
 
 
