@@ -13,8 +13,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# order of the tests of tests/test_zz_new_paths_gpu.py (everything written after the round-1 GPU budget was spent):
+# from the simplest kernels to the tcgen05 paths, so that under `pytest -x` a failure hides as little as possible
+_NEW_PATH_ORDER = ["test_prepare", "test_sample_windows", "test_learnt", "test_eval_rollout", "test_wing_fly",
+                   "test_step_host", "test_device_dataset", "test_tc1", "test_tc2", "test_tc3"]
+
+
+def _new_path_rank(item):
+    name = item.name
+    for i, prefix in enumerate(_NEW_PATH_ORDER):
+        if name.startswith(prefix):
+            return i
+    return len(_NEW_PATH_ORDER)
+
+
 def pytest_collection_modifyitems(config, items):
     """GPU tests are selected with ``-m gpu``; without a device they are skipped, not failed."""
+    new = [it for it in items if "test_zz_new_paths_gpu" in it.nodeid]
+    if new:
+        rest = [it for it in items if "test_zz_new_paths_gpu" not in it.nodeid]
+        new.sort(key=_new_path_rank)                       # stable: keeps the file order inside a group
+        items[:] = rest + new
     try:
         import torch
         has_gpu = torch.cuda.is_available()
