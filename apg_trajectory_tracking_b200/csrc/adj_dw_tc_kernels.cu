@@ -24,19 +24,6 @@ constexpr int DW_LOADERS = 256;
 constexpr int DW_THREADS = DW_LOADERS + 32;
 constexpr int DW_SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES;
 
-__device__ __forceinline__ uint64_t dw_kmajor_desc(uint32_t base, int ks) {
-  // K-major unswizzled image with K = 64: K-adjacent core matrices 128 B apart (LBO), 8-row groups 2048 B (SBO)
-  const uint32_t addr = base + ks * 256, lbo = 128, sbo = 2048;
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fffu);
-  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ uint32_t dw_idesc(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 __device__ __forceinline__ void dw_mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -148,13 +135,13 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
           unsigned char* st = base + s * STAGE_BYTES;
           const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG_BYTES, b_hi = a_lo + A_IMG_BYTES,
                          b_lo = b_hi + B_IMG_BYTES;
-          const uint32_t idesc = dw_idesc(AM, op.N);
+          const uint32_t idesc = tc::idesc_tf32(AM, op.N);
           const uint32_t d = tmem + op.d_col;
           const bool clear = (j == 0) && op.first;
 #pragma unroll
           for (int ks = 0; ks < KD / 8; ++ks) {
-            const uint64_t ah = dw_kmajor_desc(a_hi, ks), al = dw_kmajor_desc(a_lo, ks);
-            const uint64_t bh = dw_kmajor_desc(b_hi, ks), bl = dw_kmajor_desc(b_lo, ks);
+            const uint64_t ah = tc::kmajor_desc(a_hi, ks, KD), al = tc::kmajor_desc(a_lo, ks, KD);
+            const uint64_t bh = tc::kmajor_desc(b_hi, ks, KD), bl = tc::kmajor_desc(b_lo, ks, KD);
             dw_mma_ss(d, al, bh, idesc, (ks > 0 || !clear) ? 1u : 0u);
             dw_mma_ss(d, ah, bl, idesc, 1u);
             dw_mma_ss(d, ah, bh, idesc, 1u);

@@ -25,21 +25,6 @@ constexpr int TC_THREADS = 288;
 constexpr int TC_SMEM_BYTES = 1024 + BLOB_BYTES;
 static_assert(TC_SMEM_BYTES <= 232448 - 512, "weight images do not fit in shared memory");
 
-__device__ __forceinline__ uint64_t kmajor_desc(uint32_t base, int ks, int K) {
-  // shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address, leading byte
-  // offset (K-adjacent core matrices, 128 B), stride byte offset (8-row groups), version 1, no swizzle
-  const uint32_t addr = base + ks * 256, lbo = 128, sbo = (K >> 2) * 128;
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fffu);
-  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
-  // InstrDescriptor: c_format F32 (bit 4), a/b format TF32 (bits 7, 10), K-major A and B, N >> 3 (bit 17), M >> 4 (24)
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -372,31 +357,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 // chunks = adjacent groups of four `in` features) and start address + ks * LBO.  Reads the activation stash, writes
 // the dZ stash adj_dw_tc_kernel consumes.
 // =========================================================================================================
-namespace {
-
-// one GEMM of the reverse op list: D[d_col, +N) = A[0, K) * W  with W's forward image (rows, Kf) read MN-major
-struct ROp { int img_off, rows, Kf, K, N, d_col; };
-constexpr int NROPS = 8;
-__device__ __forceinline__ ROp rop_of(int i) {
-  if (i == 0) return {I_WO.off, 48, 64, 40, 64, C_DMAIN};                         // dH3 = dZo Wo
-  if (i == 1) return {I_W3.off, 64, 64, 64, 64, C_DMAIN};                         // dH2 = dZ3 W3
-  if (i == 2) return {I_W2.off, 64, 64, 64, 64, C_DMAIN};                         // dH1 = dZ2 W2
-  if (i == 3) return {I_W1S.off, 64, 64, 64, 64, C_DMAIN};                        // ds  = dZ1 W1[:, :64]
-  return {I_W1G.off + (i - 4) * 2 * img_bytes(64, 40), 64, 40, 64, 48, C_DCONV};  // dconv of position pair i - 4
-}
-__device__ __forceinline__ uint64_t mnmajor_desc(uint32_t base, int ks, int Kf) {
-  const uint32_t lbo = (Kf >> 2) * 128, sbo = 128, addr = base + ks * lbo;
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fffu);
-  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ uint32_t idesc_tf32_bmn(int M, int N) { return idesc_tf32(M, N) | (1u << 16); }
-
-}  // namespace
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
     hutter_adj_dx_tc_kernel(const unsigned char* __restrict__ blob, const HutterLayout y, const RolloutArgs g,
                             const DzStash z) {
@@ -450,7 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           par[s] ^= 1;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const ROp op = rop_of(op_i[s]);
-          const uint32_t idesc = idesc_tf32_bmn(TMT, op.N);
+          const uint32_t idesc = idesc_tf32(TMT, op.N, 1);
           const uint32_t whi = smem_u32(base + op.img_off), wlo = whi + img_bytes(op.rows, op.Kf);
           const uint32_t slot = tmem + s * SLOT_COLS;
           const uint32_t d = slot + op.d_col, ahi = slot + C_AHI, alo = slot + C_ALO;

@@ -120,6 +120,35 @@ APG_HD void pack_body(int e, const float* P, const HutterLayout& y, unsigned cha
   }
 }
 
+// ---- tcgen05 descriptors (cute/arch/mma_sm100_desc.hpp).  Pure integer functions of a 32-bit shared-memory address so
+//      that the CPU check can decode them again (tests/hostcheck/hostcheck_tc.cpp emulates the MMAs from the
+//      descriptors, following the canonical unswizzled forms of cute/atom/mma_traits_sm100.hpp).
+// shared-memory matrix descriptor: start address [0,14), leading byte offset [16,30), stride byte offset [32,46)
+// (all >> 4), version 1 at bit 46, layout type 0 (no swizzle)
+APG_HD uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// K-major unswizzled image with K columns, k-step ks (8 tf32 = two 16-byte chunks): K-adjacent core matrices 128 B
+// apart (LBO), 8-row groups (K/4)*128 B apart (SBO)
+APG_HD uint64_t kmajor_desc(uint32_t base, int ks, int K) { return smem_desc(base + ks * 256, 128, (K >> 2) * 128); }
+// the same image read MN-major (operand = the transposed matrix): k-step ks = image rows 8*ks .. 8*ks+7; 8-row
+// groups (Kf/4)*128 B apart (LBO), adjacent 16-byte chunks = adjacent groups of four mn elements (SBO = 128)
+APG_HD uint64_t mnmajor_desc(uint32_t base, int ks, int Kf) {
+  const uint32_t lbo = (Kf >> 2) * 128;
+  return smem_desc(base + ks * lbo, lbo, 128);
+}
+// instruction descriptor, kind::tf32: c_format F32 (bit 4), a/b format TF32 (bits 7, 10), b_major at bit 16,
+// N >> 3 at bit 17, M >> 4 at bit 24
+APG_HD uint32_t idesc_tf32(int M, int N, int b_mn_major = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(b_mn_major & 1) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
 // one GEMM of the op list: D[d_col, +N) (=|+=) A[0, K) * W^T
 struct Op { int img_off, rows, K, d_col, N, clear; };
 constexpr int NOPS = 13;
@@ -134,6 +163,17 @@ APG_HD Op op_of(int i) {
   if (i == 10) return {I_W2.off, 64, 64, C_DMAIN, 64, 1};
   if (i == 11) return {I_W3.off, 64, 64, C_DMAIN, 64, 1};
   return {I_WO.off, 48, 64, C_DMAIN, 48, 1};
+}
+
+// reverse op list of the tcgen05 dX chain: D[d_col, +N) = A[0, K) * W  with W's forward image (rows, Kf) read MN-major
+struct ROp { int img_off, rows, Kf, K, N, d_col; };
+constexpr int NROPS = 8;
+APG_HD ROp rop_of(int i) {
+  if (i == 0) return {I_WO.off, 48, 64, 40, 64, C_DMAIN};                         // dH3 = dZo Wo
+  if (i == 1) return {I_W3.off, 64, 64, 64, 64, C_DMAIN};                         // dH2 = dZ3 W3
+  if (i == 2) return {I_W2.off, 64, 64, 64, 64, C_DMAIN};                         // dH1 = dZ2 W2
+  if (i == 3) return {I_W1S.off, 64, 64, 64, 64, C_DMAIN};                        // ds  = dZ1 W1[:, :64]
+  return {I_W1G.off + (i - 4) * 2 * img_bytes(64, 40), 64, 40, 64, 48, C_DCONV};  // dconv of position pair i - 4
 }
 
 // Stash addressing: the adjoint kernel (hutter_adj_kernel) reads tile-major blocks of 64 drones,

@@ -163,3 +163,179 @@ extern "C" void hc_dw_emulate(const float* st_x1, const float* st_h1, const floa
     if (written[i] != (ref_in ? 0 : 1)) P[i] = NAN;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Descriptor-level emulation: a software model of tcgen05.mma.kind::tf32 that DECODES the shared-memory and
+// instruction descriptors the kernels build (tc_layout.cuh: kmajor_desc / mnmajor_desc / idesc_tf32) and gathers the
+// operands from a byte image of shared memory by the canonical unswizzled forms of cute/atom/mma_traits_sm100.hpp
+//   Major-K  : ((8,n),2):((1,SBO),LBO)         [16-byte units]  element (i, k): (i%8)*16 + (i/8)*SBO + (k/4)*LBO + (k%4)*4
+//   Major-MN : ((1,n),(8,k)):((X,SBO),(1,LBO))                  element (i, k): (i/4)*SBO + (k%8)*16 + (k/8)*LBO + (i%4)*4
+// Operands are truncated to TF32 (top 19 bits) like the tensor core input path.  This checks the descriptor arithmetic
+// (image offsets, k-step advance, LBO / SBO, M / N fields, MN-major reuse of the forward images) against the
+// documented layouts; the hardware itself is checked by the GPU tests.
+// ---------------------------------------------------------------------------------------------------------------
+namespace emu {
+struct Tmem { std::vector<float> v; Tmem() : v(128 * 512, 0.f) {} float& at(int lane, int col) { return v[lane * 512 + col]; } };
+struct Desc { uint32_t start, lbo, sbo; bool ok; };
+static Desc decode(uint64_t d) {
+  Desc r;
+  r.start = (uint32_t)(d & 0x3fff) << 4; r.lbo = (uint32_t)((d >> 16) & 0x3fff) << 4; r.sbo = (uint32_t)((d >> 32) & 0x3fff) << 4;
+  r.ok = ((d >> 46) & 3) == 1 && (d >> 61) == 0;
+  return r;
+}
+static float tf32(float x) { union { float f; uint32_t u; } v; v.f = x; v.u &= 0xffffe000u; return v.f; }
+static float smem_f(const std::vector<unsigned char>& sm, uint32_t addr) {
+  float v; if (addr + 4 > sm.size()) return NAN; memcpy(&v, sm.data() + addr, 4); return v;
+}
+static float elem(const std::vector<unsigned char>& sm, const Desc& d, bool mn_major, int i, int k) {
+  const uint32_t off = mn_major ? (uint32_t)((i / 4) * d.sbo + (k % 8) * 16 + (k / 8) * d.lbo + (i % 4) * 4)
+                                : (uint32_t)((i % 8) * 16 + (i / 8) * d.sbo + (k / 4) * d.lbo + (k % 4) * 4);
+  return smem_f(sm, d.start + off);
+}
+// D[lane][d_col + n] (+)= sum_k A[lane][k] B[n][k], K = 8.  A from TMEM columns (a_col >= 0) or from a K-major descriptor
+static bool mma(Tmem& T, const std::vector<unsigned char>& sm, int d_col, int a_col, uint64_t a_desc, uint64_t b_desc,
+                uint32_t idesc, bool acc) {
+  const int M = (int)((idesc >> 24) & 31) * 16, N = (int)((idesc >> 17) & 63) * 8;
+  const bool bmn = (idesc >> 16) & 1, amn = (idesc >> 15) & 1;
+  if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 2 || ((idesc >> 10) & 7) != 2 || amn || M != 128 || N % 16) return false;
+  const Desc bd = decode(b_desc), ad = decode(a_desc);
+  if (!bd.ok || (a_col < 0 && !ad.ok)) return false;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double s = acc ? (double)T.at(m, d_col + n) : 0.0;
+      for (int k = 0; k < 8; ++k) {
+        const float a = a_col >= 0 ? T.at(m, a_col + k) : elem(sm, ad, false, m, k);
+        s += (double)tf32(a) * (double)tf32(elem(sm, bd, bmn, n, k));
+      }
+      T.at(m, d_col + n) = (float)s;
+    }
+  return true;
+}
+static void st_split(Tmem& T, int lane, int ahi, int alo, int col, float x) {
+  float h, l; split_hi_lo(x, &h, &l); T.at(lane, ahi + col) = h; T.at(lane, alo + col) = l;
+}
+}  // namespace emu
+
+// forward of ONE 128-drone tile through the issuer's descriptor arithmetic (slot 0); actions [128][40]
+extern "C" int hc_tc_forward_desc(const unsigned char* blob, const float* in_state, const float* in_ref, int n,
+                                  float* actions) {
+  const uint32_t base = 2048;                                   // some 1024-aligned shared-memory address
+  std::vector<unsigned char> sm(base + BLOB_BYTES);
+  memcpy(sm.data() + base, blob, BLOB_BYTES);
+  const float* bias = (const float*)(blob + IMG_TOTAL);
+  emu::Tmem T;
+  auto issue = [&](int i) {                                     // == the issuer loop of hutter_fwd_tc_kernel
+    const Op op = op_of(i);
+    const uint32_t idesc = idesc_tf32(TMT, op.N);
+    const uint32_t whi = base + op.img_off, wlo = whi + img_bytes(op.rows, op.K);
+    bool ok = true;
+    for (int ks = 0; ks < op.K / 8; ++ks) {
+      const uint64_t bh = kmajor_desc(whi, ks, op.K), bl = kmajor_desc(wlo, ks, op.K);
+      ok &= emu::mma(T, sm, op.d_col, C_ALO + ks * 8, 0, bh, idesc, ks > 0 || !op.clear);
+      ok &= emu::mma(T, sm, op.d_col, C_AHI + ks * 8, 0, bl, idesc, true);
+      ok &= emu::mma(T, sm, op.d_col, C_AHI + ks * 8, 0, bh, idesc, true);
+    }
+    return ok;
+  };
+  bool ok = true;
+  for (int r = 0; r < TMT; ++r)
+    for (int k = 0; k < 16; ++k) emu::st_split(T, r, C_AHI, C_ALO, k, (r < n && k < F0) ? in_state[r * F0 + k] : 0.f);
+  ok &= issue(0);
+  for (int r = 0; r < TMT; ++r)
+    for (int c = 0; c < 64; ++c) emu::st_split(T, r, C_AHI, C_ALO, c, tanhf(T.at(r, C_DMAIN + c) + bias[B_S + c]));
+  ok &= issue(1);
+  for (int g = 0; g < 4; ++g) {
+    for (int r = 0; r < TMT; ++r)
+      for (int k = 0; k < 40; ++k) emu::st_split(T, r, C_AHI, C_ALO, k, (r < n && k < 36) ? in_ref[r * REFW + 18 * g + k] : 0.f);
+    ok &= issue(2 + 2 * g);
+    for (int r = 0; r < TMT; ++r)
+      for (int c = 0; c < 40; ++c) emu::st_split(T, r, C_AHI, C_ALO, c, fmaxf(T.at(r, C_DCONV + c) + bias[B_C + c], 0.f));
+    ok &= issue(3 + 2 * g);
+  }
+  const int bo[3] = {B_1, B_2, B_3};
+  for (int l = 0; l < 3; ++l) {
+    for (int r = 0; r < TMT; ++r)
+      for (int c = 0; c < 64; ++c) emu::st_split(T, r, C_AHI, C_ALO, c, tanhf(T.at(r, C_DMAIN + c) + bias[bo[l] + c]));
+    ok &= issue(10 + l);
+  }
+  for (int r = 0; r < TMT; ++r)
+    for (int o = 0; o < MO; ++o) actions[r * MO + o] = 1.f / (1.f + expf(-(T.at(r, C_DMAIN + o) + bias[B_O + o])));
+  return ok ? 1 : 0;
+}
+
+// dX chain of ONE tile through the MN-major descriptors of hutter_adj_dx_tc_kernel.  Inputs row-major [128][..]:
+// dlog (40), h3, h2, h1 (64), x1 (224, position-major).  Outputs dz3, dz2, dz1 [128][64], dzx [128][224].
+extern "C" int hc_tc_dx_desc(const unsigned char* blob, const float* dlog, const float* h3, const float* h2,
+                             const float* h1, const float* x1, float* dz3, float* dz2, float* dz1, float* dzx) {
+  const uint32_t base = 3072;
+  std::vector<unsigned char> sm(base + BLOB_BYTES);
+  memcpy(sm.data() + base, blob, BLOB_BYTES);
+  emu::Tmem T;
+  auto issue = [&](int i) {                                     // == the issuer loop of hutter_adj_dx_tc_kernel
+    const ROp op = rop_of(i);
+    const uint32_t idesc = idesc_tf32(TMT, op.N, 1);
+    const uint32_t whi = base + op.img_off, wlo = whi + img_bytes(op.rows, op.Kf);
+    bool ok = true;
+    for (int ks = 0; ks < op.K / 8; ++ks) {
+      const uint64_t bh = mnmajor_desc(whi, ks, op.Kf), bl = mnmajor_desc(wlo, ks, op.Kf);
+      ok &= emu::mma(T, sm, op.d_col, C_ALO + ks * 8, 0, bh, idesc, ks > 0);
+      ok &= emu::mma(T, sm, op.d_col, C_AHI + ks * 8, 0, bl, idesc, true);
+      ok &= emu::mma(T, sm, op.d_col, C_AHI + ks * 8, 0, bh, idesc, true);
+    }
+    return ok;
+  };
+  bool ok = true;
+  for (int r = 0; r < TMT; ++r)
+    for (int c = 0; c < MO; ++c) emu::st_split(T, r, C_AHI, C_ALO, c, dlog[r * MO + c]);
+  const float* xs[3] = {h3, h2, h1};
+  float* zs[3] = {dz3, dz2, dz1};
+  for (int l = 0; l < 3; ++l) {
+    ok &= issue(l);
+    for (int r = 0; r < TMT; ++r)
+      for (int c = 0; c < 64; ++c) {
+        const float yv = xs[l][r * 64 + c], v = T.at(r, C_DMAIN + c) * (1.f - yv * yv);
+        zs[l][r * 64 + c] = v;
+        emu::st_split(T, r, C_AHI, C_ALO, c, v);
+      }
+  }
+  ok &= issue(3);
+  for (int r = 0; r < TMT; ++r)
+    for (int c = 0; c < 64; ++c) { const float yv = x1[r * K1 + c]; dzx[r * K1 + c] = T.at(r, C_DMAIN + c) * (1.f - yv * yv); }
+  for (int g = 0; g < 4; ++g) {
+    ok &= issue(4 + g);
+    for (int r = 0; r < TMT; ++r)
+      for (int c = 0; c < 40; ++c) {
+        const int xr = x1_row_of_conv(g, c);
+        dzx[r * K1 + xr] = x1[r * K1 + xr] > 0.f ? T.at(r, C_DCONV + c) : 0.f;
+      }
+  }
+  return ok ? 1 : 0;
+}
+
+// one (tile, op) of the streaming dW GEMM through the SS descriptors of adj_dw_tc_kernel: returns D[128][N]
+extern "C" int hc_dw_op_desc(const float* a_img_src /*[128][64] A rows x drones*/, const float* b_img_src /*[64][64]*/,
+                             int N, float* D) {
+  using dw::KD; using dw::AM; using dw::A_IMG_BYTES; using dw::B_IMG_BYTES; using dw::STAGE_BYTES; using dw::chunk_off;
+  const uint32_t base = 1024 + STAGE_BYTES;                      // stage 1
+  std::vector<unsigned char> sm(base + STAGE_BYTES, 0);
+  unsigned char *a_hi = sm.data() + base, *a_lo = a_hi + A_IMG_BYTES, *b_hi = a_lo + A_IMG_BYTES, *b_lo = b_hi + B_IMG_BYTES;
+  auto put = [&](unsigned char* hi, unsigned char* lo, int r, int d, float x) {
+    float h, l; split_hi_lo(x, &h, &l);
+    memcpy(hi + chunk_off(r, d >> 2) + (d & 3) * 4, &h, 4); memcpy(lo + chunk_off(r, d >> 2) + (d & 3) * 4, &l, 4);
+  };
+  for (int r = 0; r < AM; ++r) for (int d = 0; d < KD; ++d) put(a_hi, a_lo, r, d, a_img_src[r * KD + d]);
+  for (int r = 0; r < 64; ++r) for (int d = 0; d < KD; ++d) put(b_hi, b_lo, r, d, b_img_src[r * KD + d]);
+  emu::Tmem T;
+  const uint32_t A_hi = base, A_lo = A_hi + A_IMG_BYTES, B_hi = A_lo + A_IMG_BYTES, B_lo = B_hi + B_IMG_BYTES;
+  const uint32_t idesc = idesc_tf32(AM, N);
+  bool ok = true;
+  for (int ks = 0; ks < KD / 8; ++ks) {                          // == the issuer loop of adj_dw_tc_kernel
+    const uint64_t ah = kmajor_desc(A_hi, ks, KD), al = kmajor_desc(A_lo, ks, KD);
+    const uint64_t bh = kmajor_desc(B_hi, ks, KD), bl = kmajor_desc(B_lo, ks, KD);
+    ok &= emu::mma(T, sm, 16, -1, al, bh, idesc, ks > 0);
+    ok &= emu::mma(T, sm, 16, -1, ah, bl, idesc, true);
+    ok &= emu::mma(T, sm, 16, -1, ah, bh, idesc, true);
+  }
+  for (int r = 0; r < AM; ++r) for (int c = 0; c < N; ++c) D[r * N + c] = T.at(r, 16 + c);
+  return ok ? 1 : 0;
+}

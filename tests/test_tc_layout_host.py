@@ -152,3 +152,71 @@ def test_streaming_dw_gemm_reproduces_the_weight_gradient(ht, n):
         scale = max(float(w.abs().max()), 1e-6)
         assert np.abs(got - w.numpy()).max() <= 2e-5 * scale + (0 if i not in (4, 5) else 0), i
     assert o == P.size
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# descriptor-level emulation: the MMAs are executed by a software model that decodes the shared-memory / instruction
+# descriptors the kernels build (canonical unswizzled layouts of cute/atom/mma_traits_sm100.hpp, TF32 truncation)
+# ---------------------------------------------------------------------------------------------------------------
+def _net_and_case(n, seed):
+    params = B.default_init("quad", 10, seed=seed)
+    case = SY.quad_case(n, 10, 0.1, seed=seed)
+    flat = np.ascontiguousarray(torch.cat([p.reshape(-1) for p in params]).numpy(), dtype=np.float32)
+    return params, case, flat
+
+
+@pytest.mark.parametrize("n", [128, 77])
+def test_forward_issuer_descriptors_reproduce_the_policy(ht, n):
+    params, case, flat = _net_and_case(n, 11)
+    blob = np.zeros(ht.hc_tc_blob_bytes(), np.uint8)
+    ht.hc_tc_pack(_p(flat), _p(blob))
+    act = np.zeros((128, 40), np.float32)
+    ins = np.ascontiguousarray(case["in_state"].numpy(), np.float32)
+    inr = np.ascontiguousarray(case["in_ref"].numpy(), np.float32)
+    assert ht.hc_tc_forward_desc(_p(blob), _p(ins), _p(inr), n, _p(act)) == 1, "a descriptor failed to decode"
+    want = torch.sigmoid(O.hutter_forward([p.double() for p in params], case["in_state"].double(),
+                                          case["in_ref"].double())).numpy()
+    assert np.abs(act[:n] - want).max() <= 3e-6            # 3xTF32 with truncating inputs: fp32-level accuracy
+
+
+def test_dx_issuer_mn_major_descriptors_reproduce_the_dx_chain(ht):
+    n = 128
+    params, case, flat = _net_and_case(n, 12)
+    blob = np.zeros(ht.hc_tc_blob_bytes(), np.uint8)
+    ht.hc_tc_pack(_p(flat), _p(blob))
+    ps = [p.double() for p in params]
+    ws, bs, wc, bc, wr, br, w1, b1, w2, b2, w3, b3, wo, bo = ps
+    s = torch.tanh(case["in_state"].double() @ ws.t() + bs)
+    conv = O._conv_encoder(case["in_ref"].double(), wc, bc)
+    x = torch.cat((s, conv), 1)
+    a1 = torch.tanh(x @ w1.t() + b1)
+    a2 = torch.tanh(a1 @ w2.t() + b2)
+    a3 = torch.tanh(a2 @ w3.t() + b3)
+    g = torch.Generator().manual_seed(3)
+    dlog = torch.randn(n, 40, generator=g, dtype=torch.float64)
+    dz3 = (dlog @ wo) * (1 - a3 ** 2)
+    dz2 = (dz3 @ w3) * (1 - a2 ** 2)
+    dz1 = (dz2 @ w2) * (1 - a1 ** 2)
+    dx = dz1 @ w1
+    pm = lambda t: t.reshape(n, 20, 8).transpose(1, 2).reshape(n, 160)      # noqa: E731
+    want_x = torch.cat((dx[:, :64] * (1 - s ** 2), pm(dx[:, 64:] * (conv > 0))), 1)
+    f32 = lambda t: np.ascontiguousarray(t.float().numpy())                  # noqa: E731
+    o3, o2, o1, ox = (np.zeros((n, 64), np.float32) for _ in range(3)), None, None, np.zeros((n, 224), np.float32)
+    o3, o2, o1 = list(o3)
+    ok = ht.hc_tc_dx_desc(_p(blob), _p(f32(dlog)), _p(f32(a3)), _p(f32(a2)), _p(f32(a1)),
+                          _p(f32(torch.cat((s, pm(conv)), 1))), _p(o3), _p(o2), _p(o1), _p(ox))
+    assert ok == 1, "a descriptor failed to decode"
+    for got, want in ((o3, dz3), (o2, dz2), (o1, dz1), (ox, want_x)):
+        assert np.abs(got - want.numpy()).max() <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("N", [48, 64])
+def test_dw_issuer_descriptors_reproduce_one_gemm(ht, N):
+    rng = np.random.default_rng(N)
+    a = rng.standard_normal((128, 64)).astype(np.float32)
+    b = np.zeros((64, 64), np.float32)
+    b[:N] = rng.standard_normal((N, 64)).astype(np.float32)
+    d = np.zeros((128, N), np.float32)
+    assert ht.hc_dw_op_desc(_p(a), _p(b), N, _p(d)) == 1, "a descriptor failed to decode"
+    want = a.astype(np.float64) @ b[:N].astype(np.float64).T
+    assert np.abs(d - want).max() <= 2e-5 * np.abs(want).max()
