@@ -266,6 +266,11 @@ int check_ptrs(const apg_config* c, const float* params, const float* in_state, 
   return 0;
 }
 
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+
 // APG_TC_FWD=1 selects the tcgen05 forward for the configuration it is written for (quadrotor concurrent,
 // Net(15,10,9,40,conv), h = 10); everything else, and the default, runs hutter_fwd_kernel.
 bool use_tc_forward(const apg_config* c, const HutterLayout& y) {
@@ -332,7 +337,10 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
   cudaError_t ce;
   if (is_hutter(cfg)) {
     const HutterLayout y = hutter_layout(cfg);
-    if ((ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
+    // the mma.sync kernels' packed weights; not needed when forward AND both adjoint halves run on the tcgen05 images
+    const bool all_tc = use_tc_forward(cfg, y) && use_tc_dw(cfg, y) && env_flag("APG_TC_DX");
+    if (!all_tc &&
+        (ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
       return (int)ce;
     if (is_recurrent(cfg)) { if ((ce = launch_rec_fwd(y, a, p.grid, st))) return (int)ce; }
     else if (use_tc_forward(cfg, y)) {
@@ -380,11 +388,12 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
       z.o = reinterpret_cast<float*>(w + p.o_dzo);  z.z3 = reinterpret_cast<float*>(w + p.o_dz3);
       z.z2 = reinterpret_cast<float*>(w + p.o_dz2); z.z1 = reinterpret_cast<float*>(w + p.o_dz1);
       z.x = reinterpret_cast<float*>(w + p.o_dzx);
-      const char* dx = getenv("APG_TC_DX");
-      if (dx && dx[0] == '1') {
-        // dX chain on tcgen05 as well (forward weight images read MN-major); repacks the images (parameters only)
+      if (env_flag("APG_TC_DX")) {
+        // dX chain on tcgen05 as well (forward weight images read MN-major).  The images of the forward call are
+        // reused when that ran on tcgen05 (same parameters by the API contract), otherwise they are packed here.
         unsigned char* blob = static_cast<unsigned char*>(workspace) + p.o_tc;
-        if ((ce = launch_hutter_adj_dx_tc(y, params, blob, a, z, p.grid, st))) return (int)ce;
+        if ((ce = launch_hutter_adj_dx_tc(y, use_tc_forward(cfg, y) ? nullptr : params, blob, a, z, p.grid, st)))
+          return (int)ce;
       } else if ((ce = launch_hutter_adj_dx(cfg->system, y, a, z, p.grid, st))) return (int)ce;
       if ((ce = launch_adj_dw_tc(y, a, z, p.grid, st))) return (int)ce;
       if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;

@@ -559,9 +559,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
 cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, unsigned char* blob,
                                     const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st) {
-  apg_pack_tc_kernel<<<(PAIRS_TOTAL + B_TOTAL + 255) / 256, 256, 0, st>>>(params, y, blob);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
+  if (params) {                                  // nullptr: the images of the tcgen05 forward call are still valid
+    apg_pack_tc_kernel<<<(PAIRS_TOTAL + B_TOTAL + 255) / 256, 256, 0, st>>>(params, y, blob);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   e = cudaFuncSetAttribute(hutter_adj_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   hutter_adj_dx_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(blob, y, a, z);
