@@ -122,5 +122,27 @@ APG_HD float conv_weight_from_block(const float* T, int ldt, int c, int ci, int 
 }
 APG_HD float conv_bias_from_block(const float* T, int ldt, int c) { return T[4 * RD * ldt + c] + T[4 * RD * ldt + NC + c]; }
 
+// ---- reduction of the per-CTA partials (torch order, no permutation) with four CTA slices per parameter: thread
+//      (slice, p) sums partials[c][p] for the CTAs of its slice in fixed order; the slice sums are added in fixed
+//      order -> bitwise reproducible, 4x the memory-level parallelism of apg_reduce_kernel's one thread per parameter.
+constexpr int RED_SLICES = 4;
+APG_HD void reduce_slice_bounds(int ncta, int slice, int* c0, int* c1) {
+  const int per = (ncta + RED_SLICES - 1) / RED_SLICES;
+  *c0 = slice * per < ncta ? slice * per : ncta;
+  *c1 = (slice + 1) * per < ncta ? (slice + 1) * per : ncta;
+}
+APG_HD float reduce_slice_sum(const float* partials, int n, int p, int c0, int c1) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = c0;
+  for (; c + 3 < c1; c += 4) {
+    s0 += partials[(size_t)(c + 0) * n + p];
+    s1 += partials[(size_t)(c + 1) * n + p];
+    s2 += partials[(size_t)(c + 2) * n + p];
+    s3 += partials[(size_t)(c + 3) * n + p];
+  }
+  for (; c < c1; ++c) s0 += partials[(size_t)c * n + p];
+  return (s0 + s1) + (s2 + s3);
+}
+
 }  // namespace dw
 }  // namespace apg

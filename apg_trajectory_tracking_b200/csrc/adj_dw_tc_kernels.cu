@@ -249,6 +249,24 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   }
 }
 
+// grad[p] = scale * sum over CTAs of partials[c][p]: 32 parameters x 4 CTA slices per block of 128 threads
+__global__ void __launch_bounds__(128) apg_reduce4_kernel(const float* __restrict__ partials, int ncta, int n,
+                                                          float scale, float* __restrict__ grad) {
+  __shared__ float s_part[RED_SLICES][32];
+  const int pl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + pl;
+  int c0, c1;
+  reduce_slice_bounds(ncta, slice, &c0, &c1);
+  s_part[slice][pl] = p < n ? reduce_slice_sum(partials, n, p, c0, c1) : 0.f;
+  __syncthreads();
+  if (slice == 0 && p < n) grad[p] = scale * ((s_part[0][pl] + s_part[1][pl]) + (s_part[2][pl] + s_part[3][pl]));
+}
+
+cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st) {
+  apg_reduce4_kernel<<<(n + 31) / 32, 128, 0, st>>>(partials, ncta, n, scale, grad);
+  return cudaGetLastError();
+}
+
 bool adj_dw_tc_supported(const HutterLayout& y, int h) {
   return y.conv && y.F0 == F0 && y.L == H && y.RD == RD && y.Mo == MO && h == H;
 }

@@ -396,8 +396,9 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
           return (int)ce;
       } else if ((ce = launch_hutter_adj_dx(cfg->system, y, a, z, p.grid, st))) return (int)ce;
       if ((ce = launch_adj_dw_tc(y, a, z, p.grid, st))) return (int)ce;
-      if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;
-      return 0;                                   // the partials are already in torch column order
+      // the partials are already in torch column order: plain sliced reduction
+      if ((ce = launch_reduce_grad4(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;
+      return 0;
     }
     else if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
   } else if (cfg->net == NET_LSTM) {

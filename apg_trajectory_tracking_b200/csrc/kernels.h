@@ -27,6 +27,7 @@ cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, 
                                     const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st);
 cudaError_t launch_adj_dw_tc(const HutterLayout& y, const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st);
 bool adj_dw_tc_supported(const HutterLayout& y, int h);
+cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st);
 
 cudaError_t launch_rec_fwd(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_rec_adj(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);

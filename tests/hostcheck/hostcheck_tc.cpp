@@ -339,3 +339,16 @@ extern "C" int hc_dw_op_desc(const float* a_img_src /*[128][64] A rows x drones*
   for (int r = 0; r < AM; ++r) for (int c = 0; c < N; ++c) D[r * N + c] = T.at(r, 16 + c);
   return ok ? 1 : 0;
 }
+
+// the sliced reduction of the per-CTA partials exactly as apg_reduce4_kernel computes it
+extern "C" void hc_reduce4(const float* partials, int ncta, int n, float scale, float* grad) {
+  for (int p = 0; p < n; ++p) {
+    float part[dw::RED_SLICES];
+    for (int s = 0; s < dw::RED_SLICES; ++s) {
+      int c0, c1;
+      dw::reduce_slice_bounds(ncta, s, &c0, &c1);
+      part[s] = dw::reduce_slice_sum(partials, n, p, c0, c1);
+    }
+    grad[p] = scale * ((part[0] + part[1]) + (part[2] + part[3]));
+  }
+}

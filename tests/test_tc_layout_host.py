@@ -220,3 +220,14 @@ def test_dw_issuer_descriptors_reproduce_one_gemm(ht, N):
     assert ht.hc_dw_op_desc(_p(a), _p(b), N, _p(d)) == 1, "a descriptor failed to decode"
     want = a.astype(np.float64) @ b[:N].astype(np.float64).T
     assert np.abs(d - want).max() <= 2e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("ncta", [1, 3, 4, 7, 148])
+def test_sliced_partial_reduction_covers_every_cta_once(ht, ncta):
+    rng = np.random.default_rng(ncta)
+    n = 1891
+    partials = rng.standard_normal((ncta, n)).astype(np.float32)
+    grad = np.zeros(n, np.float32)
+    ht.hc_reduce4(_p(partials), ncta, n, ctypes.c_float(0.5), _p(grad))
+    want = 0.5 * partials.astype(np.float64).sum(0)
+    assert np.abs(grad - want).max() <= 1e-5 * np.abs(want).max()
