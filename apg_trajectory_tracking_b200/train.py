@@ -132,8 +132,9 @@ class FusedTrainStep:
         st = self._host_state(n)
         compute = torch.cuda.current_stream(self.device)
         copy = st["copy_stream"]
-        if st["done"] is not None:
-            copy.wait_event(st["done"])          # the previous step's kernels still read the staging buffers
+        # order the copies after everything already enqueued on the compute stream: the previous step's kernels still
+        # read the staging buffers, and freshly allocated staging memory may be a recycled block with work in flight
+        copy.wait_stream(compute)
         bounds = chunk_bounds(n, chunk if chunk is not None else self.default_chunk())
         if spec.system == "wing":
             mean, std = norm if norm is not None else (_syn.WING_MEAN, _syn.WING_STD)

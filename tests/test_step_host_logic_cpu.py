@@ -23,6 +23,9 @@ class _Stream:
     def wait_event(self, ev):
         assert ev.recorded, "waiting on an event that was never recorded"
 
+    def wait_stream(self, other):
+        pass
+
 
 class _Event:
     def __init__(self):
