@@ -187,3 +187,40 @@ def test_learnt_dynamics_mirror_has_reference_parameters_and_refuses_cpu(capi):
     assert torch.equal(d.linear_at.detach(), torch.eye(4)) and float(d.linear_state_2.weight.abs().max()) == 0.0
     with pytest.raises(ApgError):
         d(torch.zeros(2, 12), torch.zeros(2, 4), 0.1)
+
+
+def test_new_entry_points_validate_their_arguments_before_touching_the_device(capi):
+    """error codes, not crashes: null pointers / bad shapes are rejected on the host; with valid arguments the calls
+    stop at 'no CUDA device' here (nothing is computed on the CPU)"""
+    import ctypes as C
+    from apg_trajectory_tracking_b200 import rollout as R
+    lib = capi.lib()
+    buf = (C.c_float * 4096)()
+    pb = C.c_void_p(C.addressof(buf))
+    BAD, UNSUP, NODEV = -1, -2, -4
+    assert lib.apg_prepare_quad(None, pb, 4, 10, pb, pb, pb, pb, None) == BAD
+    assert lib.apg_prepare_quad(pb, None, 4, 10, None, None, pb, None, None) == BAD
+    assert lib.apg_prepare_wing(pb, pb, None, pb, C.c_float(0.05), 10, 4, pb, pb, pb, pb, None) == BAD
+    assert lib.apg_prepare_wing(pb, pb, pb, pb, C.c_float(0.05), 0, 4, pb, pb, pb, pb, None) == BAD
+    assert lib.apg_sample_windows(pb, 100, 8, 10, 20, 3, pb, pb, None) == BAD          # fewer than 9 columns
+    assert lib.apg_sample_windows(pb, 100, 9, 10, 20, 6, pb, pb, None) == BAD          # would read past the table
+    assert lib.apg_poly_reference(None, 4, 10, C.c_float(0.1), C.c_float(0.1), pb, None) == BAD
+    assert lib.apg_learnt_step(None, pb, pb, pb, C.c_float(0.1), 4, pb, None) == BAD
+    assert lib.apg_learnt_step_adjoint(pb, pb, pb, pb, C.c_float(0.1), 4, pb, pb, pb, pb, None, None) == BAD
+    assert lib.apg_learnt_workspace_bytes(1000) >= 1891 * 4
+    ws = C.c_void_p((C.addressof(buf) + 255) & ~255)
+    quad = R.RolloutSpec.quad_concurrent(10, 0.1).config(8)
+    wing = R.RolloutSpec.wing_concurrent(10, 0.05).config(8)
+    cart = R.RolloutSpec.cartpole_concurrent(5, 0.05).config(8)
+    ev = lambda cfg, steps=10, rows=20: lib.apg_eval_rollout(C.byref(cfg), pb, pb, None, 8, rows, pb, steps,   # noqa: E731
+                                                             C.c_float(1), C.c_float(1), 0, ws, None, None, None,
+                                                             None, None)
+    assert ev(cart) == UNSUP and ev(wing) == UNSUP
+    assert ev(quad, steps=0) == BAD and ev(quad, rows=0) == BAD
+    assert ev(quad) == NODEV
+    fly = lambda cfg, k=1: lib.apg_eval_fly_to_points(C.byref(cfg), pb, pb, k, pb, pb, pb, C.c_float(0.05), 10,   # noqa: E731
+                                                      C.c_float(4), C.c_float(0.4), 0, ws, None, None, None, None,
+                                                      None, None, None)
+    assert fly(quad) == UNSUP and fly(wing, k=0) == BAD and fly(wing) == NODEV
+    for code in (BAD, UNSUP, -3, NODEV):
+        assert lib.apg_error_string(code).startswith(b"apg:")
