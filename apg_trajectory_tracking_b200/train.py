@@ -27,6 +27,17 @@ def chunk_bounds(n, chunk, align=64):
     return [(a, min(a + chunk, n)) for a in range(0, n, chunk)]
 
 
+class HostLoss:
+    """loss of one ``step_host_async`` call on its way to the host"""
+
+    def __init__(self, pinned, event):
+        self._pinned, self._event = pinned, event
+
+    def item(self):
+        self._event.synchronize()
+        return float(self._pinned[0])
+
+
 class FusedTrainStep:
     def __init__(self, params, spec: R.RolloutSpec, n_drones: int, lr: float, momentum: float = 0.9, device=None,
                  process_group=None, distributed=None):
@@ -81,25 +92,34 @@ class FusedTrainStep:
         tiles, so its GEMM / dynamics warps overlap)"""
         return 2 * 64 * max(1, _capi.lib().apg_sm_count())
 
+    def _staging(self, n):
+        """device staging of one step's raw samples and derived policy inputs"""
+        spec, dev = self.runner.spec, self.device
+        rows = spec.horizon if spec.mode == "concurrent" else 2 * spec.horizon
+        sg = {"cur": torch.empty(n, spec.state_dim, device=dev), "done": None}
+        if spec.system == "quad":
+            sg["ref"] = torch.empty(n, rows, 9, device=dev)
+            sg["in_ref"] = torch.empty(n, rows, 9, device=dev)
+            sg["in_state"] = torch.empty(n, 15, device=dev) if spec.mode == "concurrent" else None
+            sg["h0c0"] = torch.empty(2, n, 8, device=dev) if spec.mode.lower() == "lstm" else None
+        elif spec.system == "wing":
+            sg["target"] = torch.empty(n, 3, device=dev)
+            sg["ref"] = torch.empty(n, spec.horizon, 3, device=dev)
+            sg["in_ref"] = torch.empty(n, 3, device=dev)
+            sg["in_state"] = torch.empty(n, 9, device=dev)
+        return sg
+
     def _host_state(self, n):
         st = getattr(self, "_hs", None)
         if st is not None and st["n"] == n:
             return st
-        spec, dev = self.runner.spec, self.device
-        rows = spec.horizon if spec.mode == "concurrent" else 2 * spec.horizon
-        st = {"n": n, "copy_stream": torch.cuda.Stream(device=dev), "done": None, "runners": {},
-              "cur": torch.empty(n, spec.state_dim, device=dev), "grad_tmp": torch.zeros_like(self.grad),
-              "loss": torch.zeros(1, device=dev)}
-        if spec.system == "quad":
-            st["ref"] = torch.empty(n, rows, 9, device=dev)
-            st["in_ref"] = torch.empty(n, rows, 9, device=dev)
-            st["in_state"] = torch.empty(n, 15, device=dev) if spec.mode == "concurrent" else None
-            st["h0c0"] = torch.empty(2, n, 8, device=dev) if spec.mode.lower() == "lstm" else None
-        elif spec.system == "wing":
-            st["target"] = torch.empty(n, 3, device=dev)
-            st["ref"] = torch.empty(n, spec.horizon, 3, device=dev)
-            st["in_ref"] = torch.empty(n, 3, device=dev)
-            st["in_state"] = torch.empty(n, 9, device=dev)
+        dev = self.device
+        # two staging sets used alternately: the copies of step i+1 may start while the kernels of step i still read
+        # theirs (step_host_async); the loss of a step is copied into one of two pinned scalars
+        st = {"n": n, "copy_stream": torch.cuda.Stream(device=dev), "runners": {}, "sets": [self._staging(n),
+              self._staging(n)], "turn": 0, "grad_tmp": torch.zeros_like(self.grad),
+              "loss": torch.zeros(1, device=dev),
+              "loss_host": [torch.empty(1, pin_memory=torch.cuda.is_available()) for _ in range(2)]}
         self._hs = st
         return st
 
@@ -118,6 +138,20 @@ class FusedTrainStep:
         self.flat.add_(self.buf, alpha=-self.lr)
         return loss
 
+    def step_host_async(self, cur, ref=None, h0c0=None, target=None, norm=None, chunk=None):
+        """``step_host`` without the host synchronisation: returns a ``HostLoss`` whose ``item()`` waits for the
+        device->host copy of this step's loss.  Calling it for step i+1 BEFORE reading the loss of step i lets the
+        H2D copies of step i+1 overlap the last kernels of step i (two staging sets).  Read a handle before the step
+        after next is issued (two pinned scalars are used alternately)."""
+        st = self._host_state(int(cur.shape[0]))
+        turn = st["turn"]
+        loss = self.step_host(cur, ref, h0c0, target, norm, chunk)
+        host = st["loss_host"][turn]
+        host.copy_(loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return HostLoss(host, ev)
+
     def value_and_grad_host(self, cur, ref=None, h0c0=None, target=None, norm=None, chunk=None, allreduce=True):
         """Loss and flat gradient from RAW host samples (pinned memory for asynchronous copies).
 
@@ -130,42 +164,46 @@ class FusedTrainStep:
         spec = self.runner.spec
         n = int(cur.shape[0])
         st = self._host_state(n)
+        sg = st["sets"][st["turn"]]
+        st["turn"] ^= 1
         compute = torch.cuda.current_stream(self.device)
         copy = st["copy_stream"]
-        # order the copies after everything already enqueued on the compute stream: the previous step's kernels still
-        # read the staging buffers, and freshly allocated staging memory may be a recycled block with work in flight
-        copy.wait_stream(compute)
+        if sg["done"] is None:
+            # first use: freshly allocated staging memory may be a recycled block with compute-stream work in flight
+            copy.wait_stream(compute)
+        else:
+            copy.wait_event(sg["done"])          # the step that last used this set (two calls ago) has finished
         bounds = chunk_bounds(n, chunk if chunk is not None else self.default_chunk())
         if spec.system == "wing":
             mean, std = norm if norm is not None else (_syn.WING_MEAN, _syn.WING_STD)
         first = True
         for a, b in bounds:
             with torch.cuda.stream(copy):
-                st["cur"][a:b].copy_(cur[a:b], non_blocking=True)
+                sg["cur"][a:b].copy_(cur[a:b], non_blocking=True)
                 if spec.system == "quad":
-                    st["ref"][a:b].copy_(ref[a:b], non_blocking=True)
-                    if st["h0c0"] is not None:
-                        st["h0c0"][:, a:b].copy_(h0c0[:, a:b], non_blocking=True)
+                    sg["ref"][a:b].copy_(ref[a:b], non_blocking=True)
+                    if sg["h0c0"] is not None:
+                        sg["h0c0"][:, a:b].copy_(h0c0[:, a:b], non_blocking=True)
                 elif spec.system == "wing":
-                    st["target"][a:b].copy_(target[a:b], non_blocking=True)
+                    sg["target"][a:b].copy_(target[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
             compute.wait_event(ev)
-            c_cur = st["cur"][a:b]
+            c_cur = sg["cur"][a:b]
             hc = None
             if spec.system == "quad":
-                want = ("in_state", "cur", "in_ref", "ref") if st["in_state"] is not None else ("cur", "in_ref", "ref")
-                outs = {"cur": c_cur, "ref": st["ref"][a:b], "in_ref": st["in_ref"][a:b]}
-                if st["in_state"] is not None:
-                    outs["in_state"] = st["in_state"][a:b]
-                PR.prepare_quad(c_cur, st["ref"][a:b], want=want, out=outs)
+                want = ("in_state", "cur", "in_ref", "ref") if sg["in_state"] is not None else ("cur", "in_ref", "ref")
+                outs = {"cur": c_cur, "ref": sg["ref"][a:b], "in_ref": sg["in_ref"][a:b]}
+                if sg["in_state"] is not None:
+                    outs["in_state"] = sg["in_state"][a:b]
+                PR.prepare_quad(c_cur, sg["ref"][a:b], want=want, out=outs)
                 c_ins, c_inr, c_ref = outs.get("in_state"), outs["in_ref"], outs["ref"]
-                if st["h0c0"] is not None:
-                    hc = st["h0c0"][:, a:b].contiguous() if len(bounds) > 1 else st["h0c0"]
+                if sg["h0c0"] is not None:
+                    hc = sg["h0c0"][:, a:b].contiguous() if len(bounds) > 1 else sg["h0c0"]
             elif spec.system == "wing":
-                outs = {"cur": c_cur, "ref": st["ref"][a:b], "in_ref": st["in_ref"][a:b],
-                        "in_state": st["in_state"][a:b]}
-                PR.prepare_wing(c_cur, st["target"][a:b], mean, std, spec.dt, spec.horizon, out=outs)
+                outs = {"cur": c_cur, "ref": sg["ref"][a:b], "in_ref": sg["in_ref"][a:b],
+                        "in_state": sg["in_state"][a:b]}
+                PR.prepare_wing(c_cur, sg["target"][a:b], mean, std, spec.dt, spec.horizon, out=outs)
                 c_ins, c_inr, c_ref = outs["in_state"], outs["in_ref"], outs["ref"]
             else:
                 c_ins, c_inr, c_ref = c_cur, None, None
@@ -181,8 +219,8 @@ class FusedTrainStep:
                 st["loss"].add_(loss)
         if self.distributed and allreduce:
             torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-        st["done"] = torch.cuda.Event()
-        st["done"].record(compute)
+        sg["done"] = torch.cuda.Event()
+        sg["done"].record(compute)
         # launches of this package's kernels: per chunk the rollout's 5 + the prepare kernels (quad / wing: 2)
         self.host_launches_per_step = len(bounds) * (self.kernel_launches_per_step +
                                                      (0 if spec.system == "cartpole" else 2))

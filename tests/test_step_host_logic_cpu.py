@@ -34,6 +34,9 @@ class _Event:
     def record(self, stream=None):
         self.recorded = True
 
+    def synchronize(self):
+        assert self.recorded
+
 
 class _OracleRunner:
     """stands in for rollout.Rollout: same attributes / calls, oracle math on CPU tensors"""
@@ -163,3 +166,23 @@ def test_bench_raw_e2e_arm_runs_its_check_and_reports(cpu_doubles):
     bad["ref"] = case["ref"] + 1.0
     out = B.measure_e2e_raw(stepper, w, bad, case, 3, 1, torch.device("cpu"), lambda: None)
     assert out["ok"] is False and "loss_raw" in out["check"]
+
+
+def test_step_host_async_equals_step_host(cpu_doubles):
+    """the overlapped variant (loss read one step late, alternating staging sets) trains exactly like step_host"""
+    n, h = 200, 10
+    w = dict(B.WORKLOADS["quad_concurrent"], n=n)
+    case = B.make_case(w, n, 7, "cpu")
+    params = B.default_init("quad", h, seed=2)
+    a = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cpu", distributed=False)
+    b = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cpu", distributed=False)
+    la = [float(a.step_host(case["cur"], ref=case["ref"], chunk=64)) for _ in range(4)]
+    lb, prev = [], None
+    for _ in range(4):
+        hnd = b.step_host_async(case["cur"], ref=case["ref"], chunk=64)
+        if prev is not None:
+            lb.append(prev.item())
+        prev = hnd
+    lb.append(prev.item())
+    assert la == lb and torch.equal(a.flat, b.flat)
+    assert b._hs["sets"][0]["done"].recorded and b._hs["sets"][1]["done"].recorded

@@ -156,6 +156,28 @@ def test_step_host_from_raw_samples_equals_step_from_prepared_tensors(name):
     assert abs(l1 - float(l2.item())) <= 1e-5 * abs(l1) and rel_err(g2, g1) <= 1e-4
 
 
+def test_step_host_async_overlapped_steps_equal_step_host():
+    """loss read one step late, alternating staging sets: same losses and parameters as the synchronous loop"""
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    n, h, dt = 1000, 10, 0.1
+    w = dict(system="quad", mode="concurrent", h=h, dt=dt)
+    params = B.default_init("quad", h, seed=3)
+    a = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cuda:0", distributed=False)
+    b = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cuda:0", distributed=False)
+    batches = [{k: v.pin_memory() for k, v in B.make_case(w, n, 40 + i, "cpu").items()} for i in range(5)]
+    la = [float(a.step_host(c["cur"], ref=c["ref"], chunk=256).item()) for c in batches]
+    lb, prev = [], None
+    for c in batches:
+        hnd = b.step_host_async(c["cur"], ref=c["ref"], chunk=256)
+        if prev is not None:
+            lb.append(prev.item())
+        prev = hnd
+    lb.append(prev.item())
+    assert la == lb, (la, lb)                        # same kernels, same order: bitwise equal
+    assert torch.equal(a.flat, b.flat)
+
+
 def test_step_host_accepts_absolute_positions():
     """truly raw quad samples (drone not at the origin): the device prepare makes them relative like the dataset"""
     import bench as B
