@@ -84,6 +84,32 @@ class FusedTrainStep:
         return loss
 
     # -----------------------------------------------------------------------------------------------------------
+    # CUDA graph of one train iteration (launch-bound small batches: the reference's own cartpole case is 128 drones)
+    # -----------------------------------------------------------------------------------------------------------
+    def capture(self, in_state, cur, in_ref=None, ref=None, h0c0=None, warmup=3):
+        """Capture ``step`` on the given (static, device) tensors into a CUDA graph: pack, forward, loss sum, adjoint,
+        gradient reduction and the SGD update become ONE launch.  ``replay()`` reruns it on whatever the static tensors
+        hold then (copy a new batch into them first); returns the static 1-element loss tensor."""
+        if self.distributed:
+            raise _capi.ApgError("capture() is single-process (the gradient all-reduce is not captured)")
+        args = tuple(None if x is None else self._dev(x) for x in (in_state, cur, in_ref, ref, h0c0))
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # kernels get their attributes set / modules loaded here
+                self.step(*args)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_loss = self.step(*args)
+        self._graph_args = args
+        return self._graph_loss
+
+    def replay(self):
+        self._graph.replay()
+        return self._graph_loss
+
+    # -----------------------------------------------------------------------------------------------------------
     # host batches: raw samples in (pinned) host memory -> chunked H2D on a copy stream, overlapped with the
     # kernels of the previous chunk; the policy inputs are derived on the device (prepare.py, SURVEY 8f N1)
     # -----------------------------------------------------------------------------------------------------------

@@ -340,6 +340,27 @@ def test_learnt_dynamics_many_tiles_vs_oracle_and_training_step():
                     p -= 1e-3 * bufs[i]
 
 
+@pytest.mark.parametrize("workload", ["cartpole_concurrent", "quad_concurrent"])
+def test_device_captured_step_graph_equals_eager_steps(workload):
+    """FusedTrainStep.capture / replay: the whole train iteration as one CUDA graph launch == the eager steps"""
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    w = dict(B.WORKLOADS[workload], n=300)
+    n, h = w["n"], w["h"]
+    case = B.make_case(w, n, 3, "cuda:0")
+    params = B.default_init(w["system"], h, seed=1)
+    a = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cuda:0", distributed=False)
+    b = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cuda:0", distributed=False)
+    args = (case["in_state"], case["cur"], case.get("in_ref"), case.get("ref"))
+    b.capture(*args, warmup=2)                       # 2 warm-up steps + the captured one do not run: replay does
+    for _ in range(2):
+        a.step(*args)                                # bring `a` to the state `b` is in after its warm-up
+    la = [float(a.step(*args).item()) for _ in range(4)]
+    lb = [float(b.replay().item()) for _ in range(4)]
+    assert la == lb, (la, lb)
+    assert torch.equal(a.flat, b.flat)
+
+
 def test_device_dataset_epoch_equals_host_dataset_epoch():
     """an epoch over the device-resident raw samples == the same epoch through the host QuadDataset + DataLoader path
     (same batches, no shuffling): losses and parameters agree"""
