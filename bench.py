@@ -553,6 +553,17 @@ def main():
             "gpu_launches": stepper.kernel_launches_per_step * args.steps,
             "clocks": clocks,
         }
+        tc_on = [k for k in ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX") if os.environ.get(k) == "1"]
+        if tc_on and args.workload == "quad_concurrent":
+            # optional tcgen05 kernels in use: quote the compute roofline against the tcgen05 TF32 rate instead
+            # (half of the measured dense bf16 rate; three tensor instructions per fp32-level product)
+            _, _, pk = measured_peaks()
+            tf32_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1650.0))) / 2.0
+            rc = line["roofline_compute"]
+            rc.update({"bound": "tensor (tcgen05 kind::tf32, 3xTF32 split; kernels: %s)" % ",".join(tc_on),
+                       "peak": tf32_peak / 3.0, "frac": rc["achieved"] / (tf32_peak / 3.0),
+                       "peak_source": "MEASURED_PEAKS.json dense bf16 rate / 2 (tf32) / 3 (3xTF32)"})
+            line["gpu_launches"] = (stepper.kernel_launches_per_step + len(tc_on)) * args.steps
         if e2e_raw is not None:
             # the raw-sample path is the headline e2e when it ran, matched the prepared-input path and is faster;
             # the prepared-input measurement is kept next to it
