@@ -47,33 +47,39 @@ APG_API int apg_sample_windows(const float* traj, int traj_rows, int traj_cols, 
                                     static_cast<cudaStream_t>(stream));
 }
 
-// ---- learnt residual quadrotor dynamics (learnt_kernels.cu)
+// ---- learnt residual dynamics (learnt_kernels.cu): system = APG_SYS_QUAD / APG_SYS_WING
 #include <string.h>
-#include "learnt_math.cuh"
 
-APG_API int apg_learnt_num_params(void) { return LearntLayout::NP; }
-
-APG_API size_t apg_learnt_workspace_bytes(int n) {
-  if (n <= 0) return 256;
-  return sizeof(float) * learnt_partials_floats(n, apg_sm_count()) + 256;
+APG_API int apg_learnt_num_params(int system) {
+  if (system != APG_SYS_QUAD && system != APG_SYS_WING) return APG_ERR_UNSUPPORTED;
+  return learnt_num_params(system);
 }
 
-APG_API int apg_learnt_step(const float* params, const float* phys, const float* state, const float* action, float dt,
-                            int n, float* out, void* stream) {
+APG_API size_t apg_learnt_workspace_bytes(int system, int n) {
+  if (system != APG_SYS_QUAD && system != APG_SYS_WING) return 0;
+  if (n <= 0) return 256;
+  return sizeof(float) * learnt_partials_floats(system, n, apg_sm_count()) + 256;
+}
+
+APG_API int apg_learnt_step(int system, const float* params, const float* phys, const float* state,
+                            const float* action, float dt, int n, float* out, void* stream) {
+  if (system != APG_SYS_QUAD && system != APG_SYS_WING) return APG_ERR_UNSUPPORTED;
   if (!params || !phys || !state || !action || !out || n < 0) return APG_ERR_BAD_CONFIG;
   PhysConsts pc;
   memcpy(pc.v, phys, sizeof(float) * MAX_PHYS);
-  return (int)launch_learnt_fwd(params, pc, state, action, dt, n, out, apg_sm_count(),
+  return (int)launch_learnt_fwd(system, params, pc, state, action, dt, n, out, apg_sm_count(),
                                 static_cast<cudaStream_t>(stream));
 }
 
-APG_API int apg_learnt_step_adjoint(const float* params, const float* phys, const float* state, const float* action,
-                                    float dt, int n, const float* grad_out, float* grad_state, float* grad_action,
-                                    float* grad_params, void* workspace, void* stream) {
+APG_API int apg_learnt_step_adjoint(int system, const float* params, const float* phys, const float* state,
+                                    const float* action, float dt, int n, const float* grad_out, float* grad_state,
+                                    float* grad_action, float* grad_params, void* workspace, void* stream) {
+  if (system != APG_SYS_QUAD && system != APG_SYS_WING) return APG_ERR_UNSUPPORTED;
   if (!params || !phys || !state || !action || !grad_out || n < 0) return APG_ERR_BAD_CONFIG;
   if (grad_params && !workspace) return APG_ERR_BAD_CONFIG;
   PhysConsts pc;
   memcpy(pc.v, phys, sizeof(float) * MAX_PHYS);
-  return (int)launch_learnt_adj(params, pc, state, action, dt, n, grad_out, grad_state, grad_action, grad_params,
-                                static_cast<float*>(workspace), apg_sm_count(), static_cast<cudaStream_t>(stream));
+  return (int)launch_learnt_adj(system, params, pc, state, action, dt, n, grad_out, grad_state, grad_action,
+                                grad_params, static_cast<float*>(workspace), apg_sm_count(),
+                                static_cast<cudaStream_t>(stream));
 }

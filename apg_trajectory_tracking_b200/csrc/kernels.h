@@ -60,14 +60,15 @@ cudaError_t launch_eval_wing(const HutterLayout& y, const float* wf, const float
                              const WingEvalParams& ev, float* states_out, float* div_out, float* actions_out,
                              int* n_steps_out, float* dt_sum_out, float* dt_cnt_out, int grid, cudaStream_t st);
 
-// learnt residual quadrotor dynamics (learnt_kernels.cu)
+// learnt residual dynamics, quadrotor / fixed wing (learnt_kernels.cu)
+int learnt_num_params(int system);
 int learnt_grid(int n, int sms);
-size_t learnt_partials_floats(int n, int sms);
-cudaError_t launch_learnt_fwd(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
-                              float* out, int sms, cudaStream_t st);
-cudaError_t launch_learnt_adj(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
-                              const float* g, float* gs, float* ga, float* grad_params, float* partials, int sms,
-                              cudaStream_t st);
+size_t learnt_partials_floats(int system, int n, int sms);
+cudaError_t launch_learnt_fwd(int system, const float* params, const PhysConsts& pc, const float* s, const float* a,
+                              float dt, int n, float* out, int sms, cudaStream_t st);
+cudaError_t launch_learnt_adj(int system, const float* params, const PhysConsts& pc, const float* s, const float* a,
+                              float dt, int n, const float* g, float* gs, float* ga, float* grad_params,
+                              float* partials, int sms, cudaStream_t st);
 
 // data formats on the input side (prep_kernels.cu)
 cudaError_t launch_prepare_quad(const float* states, const float* ref, int n, int L, float* in_state, float* cur_out,

@@ -1,61 +1,66 @@
-// Learnt residual quadrotor dynamics (reference quad_dynamics_trained.py:10-69): one step for N rows
-// and its adjoint w.r.t. state, action and all 1891 parameters.
+// Learnt residual dynamics: one step for N rows and its adjoint w.r.t. state, action and all
+// parameters, for the quadrotor (reference quad_dynamics_trained.py:10-69, 1891 parameters) and the fixed wing
+// (fixed_wing_dynamics.py:270-326, 1914 parameters).  One kernel template, two per-drone models (learnt_math.cuh,
+// learnt_wing_math.cuh).
 //
 //   forward  one thread per drone, parameters in shared memory, hidden activations in a shared-memory column of
 //            the thread (stride LP -> conflict-free), 1.8 kMAC per drone.
 //   adjoint  persistent blocks of 128 threads walk tiles of 128 drones: (1) each thread recomputes the forward of its
-//            drone and back-propagates it, leaving the per-drone factors (g, h, dh, x, gat, a, dk, dj) in shared-
-//            memory rows of LP = 129 floats; (2) the 1891 parameter-gradient entries are spread over the threads,
-//            each entry a dot product of two factor rows over the tile's drones (rows padded to 129 so that both the
-//            per-drone column accesses of phase 1 and the per-entry row walks of phase 2 are bank-conflict free),
-//            accumulated in registers over all tiles of the block; (3) one partial vector per block, summed in fixed
-//            order by apg_reduce_kernel -> bitwise reproducible.
+//            drone and back-propagates it, leaving the per-drone factors (g, h, dh, x, the cotangents of the physical
+//            parameters, 1) in shared-memory rows of LP = 129 floats; (2) the parameter-gradient entries are spread
+//            over the threads, each entry a dot product of two factor rows over the tile's drones (rows padded to 129
+//            so that both the per-drone column accesses of phase 1 and the per-entry row walks of phase 2 are
+//            bank-conflict free), accumulated in registers over all tiles of the block; (3) one partial vector per
+//            block, summed in fixed order by apg_reduce_kernel -> bitwise reproducible.
 #include "learnt_math.cuh"
+#include "learnt_wing_math.cuh"
 #include "kernels.h"
 
 namespace apg {
 
 namespace {
-using Y = LearntLayout;
 constexpr int LT = 128;            // threads per block = drones per tile
 constexpr int LP = LT + 1;         // padded factor-row length
-constexpr int EPT = (Y::NP + LT - 1) / LT;                                                  // entries per thread: 15
-using namespace learnt_rows;
 }  // namespace
 
+template <class M>
 __global__ void __launch_bounds__(LT) learnt_fwd_kernel(const float* __restrict__ params, const PhysConsts pc,
                                                         const float* __restrict__ s, const float* __restrict__ a,
                                                         float dt, int n, float* __restrict__ out) {
+  using RW = LearntRows<M::NPH>;
   extern __shared__ __align__(16) float sm[];
   float* sP = sm;                        // [NP]
-  float* sH = sm + Y::NP + 1;            // [64][LP]
-  for (int i = threadIdx.x; i < Y::NP; i += LT) sP[i] = params[i];
+  float* sH = sm + RW::NP + 1;           // [64][LP]
+  for (int i = threadIdx.x; i < RW::NP; i += LT) sP[i] = params[i];
   __syncthreads();
   for (int base = blockIdx.x * LT; base < n; base += gridDim.x * LT) {
     const int d = base + threadIdx.x;
     if (d < n) {
-      float si[12], ai[4], at[4], o[12];
+      float si[12], ai[4], x[16], o[12];
 #pragma unroll
       for (int j = 0; j < 12; ++j) si[j] = s[(size_t)d * 12 + j];
 #pragma unroll
       for (int j = 0; j < 4; ++j) ai[j] = a[(size_t)d * 4 + j];
-      LearntQuad<float>::forward(sP, pc.v, si, ai, dt, o, at, sH + threadIdx.x, LP);
+      M::fwd(sP, pc.v, si, ai, dt, o, x, sH + threadIdx.x, LP);
 #pragma unroll
       for (int j = 0; j < 12; ++j) out[(size_t)d * 12 + j] = o[j];
     }
   }
 }
 
+template <class M>
 __global__ void __launch_bounds__(LT) learnt_adj_kernel(const float* __restrict__ params, const PhysConsts pc,
                                                         const float* __restrict__ s, const float* __restrict__ a,
                                                         float dt, int n, const float* __restrict__ g,
                                                         float* __restrict__ gs, float* __restrict__ ga,
                                                         float* __restrict__ partials) {
+  using RW = LearntRows<M::NPH>;
+  constexpr int EPT = (RW::NP + LT - 1) / LT;      // entries per thread: 15
   extern __shared__ __align__(16) float sm[];
   float* sP = sm;                        // [NP]
-  float* sF = sm + Y::NP + 1;            // [R_TOTAL][LP] factor rows
+  float* sF = sm + RW::NP + 1;           // [R_TOTAL][LP] factor rows
   const int t = threadIdx.x;
-  for (int i = t; i < Y::NP; i += LT) sP[i] = params[i];
+  for (int i = t; i < RW::NP; i += LT) sP[i] = params[i];
   float acc[EPT];
 #pragma unroll
   for (int q = 0; q < EPT; ++q) acc[q] = 0.f;
@@ -65,46 +70,41 @@ __global__ void __launch_bounds__(LT) learnt_adj_kernel(const float* __restrict_
     const int valid = min(LT, n - base);
     // ---- phase 1: per-drone forward + adjoint, factors into the shared rows (column t)
     if (d < n) {
-      float si[12], ai[4], at[4], o[12], gi[12], gso[12], gao[4], gat[4], dk[3], dj[3];
+      float si[12], ai[4], x[16], o[12], gi[12], gso[12], gao[4], dph[M::NPH];
 #pragma unroll
       for (int j = 0; j < 12; ++j) { si[j] = s[(size_t)d * 12 + j]; gi[j] = g[(size_t)d * 12 + j]; }
 #pragma unroll
       for (int j = 0; j < 4; ++j) ai[j] = a[(size_t)d * 4 + j];
-      LearntQuad<float>::forward(sP, pc.v, si, ai, dt, o, at, sF + R_H * LP + t, LP);
-      LearntQuad<float>::adjoint(sP, pc.v, si, ai, at, sF + R_H * LP + t, LP, dt, gi, gso, gao, sF + R_DH * LP + t, gat,
-                                 dk, dj);
+      M::fwd(sP, pc.v, si, ai, dt, o, x, sF + RW::R_H * LP + t, LP);
+      M::adj(sP, pc.v, si, ai, x, sF + RW::R_H * LP + t, LP, dt, gi, gso, gao, sF + RW::R_DH * LP + t, dph);
 #pragma unroll
       for (int j = 0; j < 12; ++j) {
         if (gs) gs[(size_t)d * 12 + j] = gso[j];
-        sF[(R_G + j) * LP + t] = gi[j];
-        sF[(R_X + j) * LP + t] = si[j];
+        sF[(RW::R_G + j) * LP + t] = gi[j];
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sF[(RW::R_X + j) * LP + t] = x[j];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (ga) ga[(size_t)d * 4 + j] = gao[j];
-        sF[(R_X + 12 + j) * LP + t] = at[j];
-        sF[(R_GAT + j) * LP + t] = gat[j];
-        sF[(R_A + j) * LP + t] = ai[j];
       }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { sF[(R_DK + j) * LP + t] = dk[j]; sF[(R_DJ + j) * LP + t] = dj[j]; }
-      sF[R_ONE * LP + t] = 1.f;
+      for (int j = 0; j < M::NPH; ++j) sF[(RW::R_DP + j) * LP + t] = dph[j];
+      sF[RW::R_ONE * LP + t] = 1.f;
     }
     __syncthreads();
     // ---- phase 2: parameter-gradient entries t, t + 128, ... += dot of two factor rows over the tile's drones
 #pragma unroll
     for (int q = 0; q < EPT; ++q) {
       const int e = t + q * LT;
-      if (e < Y::NP) {
+      if (e < RW::NP) {
         int ra, rb;
-        learnt_entry_rows(e, &ra, &rb);
-        if (ra >= 0) {
-          const float* pa = sF + ra * LP;
-          const float* pb = sF + rb * LP;
-          float v = 0.f;
-          for (int k = 0; k < valid; ++k) v = fmaf(pa[k], pb[k], v);
-          acc[q] += v;
-        }
+        RW::entry_rows(e, &ra, &rb);
+        const float* pa = sF + ra * LP;
+        const float* pb = sF + rb * LP;
+        float v = 0.f;
+        for (int k = 0; k < valid; ++k) v = fmaf(pa[k], pb[k], v);
+        acc[q] += v;
       }
     }
     __syncthreads();
@@ -113,40 +113,64 @@ __global__ void __launch_bounds__(LT) learnt_adj_kernel(const float* __restrict_
 #pragma unroll
     for (int q = 0; q < EPT; ++q) {
       const int e = t + q * LT;
-      if (e < Y::NP) partials[(size_t)blockIdx.x * Y::NP + e] = acc[q];
+      if (e < RW::NP) partials[(size_t)blockIdx.x * RW::NP + e] = acc[q];
     }
   }
 }
 
+int learnt_num_params(int system) {
+  return system == SYS_WING ? LearntRows<LearntWing<float>::NPH>::NP : LearntRows<LearntQuad<float>::NPH>::NP;
+}
 int learnt_grid(int n, int sms) {
   const int tiles = (n + LT - 1) / LT;
   const int cap = (sms > 0 ? sms : 148) * 2;
   return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
 }
-size_t learnt_partials_floats(int n, int sms) { return (size_t)learnt_grid(n, sms) * Y::NP; }
+size_t learnt_partials_floats(int system, int n, int sms) { return (size_t)learnt_grid(n, sms) * learnt_num_params(system); }
 
-cudaError_t launch_learnt_fwd(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
-                              float* out, int sms, cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
-  const size_t smem = sizeof(float) * (Y::NP + 1 + (size_t)Y::HD * LP);
-  cudaError_t e = cudaFuncSetAttribute(learnt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <class M>
+static cudaError_t launch_fwd_t(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt,
+                                int n, float* out, int sms, cudaStream_t st) {
+  using RW = LearntRows<M::NPH>;
+  const size_t smem = sizeof(float) * (RW::NP + 1 + (size_t)RW::HD * LP);
+  cudaError_t e = cudaFuncSetAttribute(learnt_fwd_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  learnt_fwd_kernel<<<learnt_grid(n, sms), LT, smem, st>>>(params, pc, s, a, dt, n, out);
+  learnt_fwd_kernel<M><<<learnt_grid(n, sms), LT, smem, st>>>(params, pc, s, a, dt, n, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_learnt_adj(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
-                              const float* g, float* gs, float* ga, float* grad_params, float* partials, int sms,
-                              cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
-  const size_t smem = sizeof(float) * (Y::NP + 1 + (size_t)R_TOTAL * LP);
-  cudaError_t e = cudaFuncSetAttribute(learnt_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <class M>
+static cudaError_t launch_adj_t(const float* params, const PhysConsts& pc, const float* s, const float* a, float dt,
+                                int n, const float* g, float* gs, float* ga, float* grad_params, float* partials,
+                                int sms, cudaStream_t st) {
+  using RW = LearntRows<M::NPH>;
+  const size_t smem = sizeof(float) * (RW::NP + 1 + (size_t)RW::R_TOTAL * LP);
+  cudaError_t e = cudaFuncSetAttribute(learnt_adj_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int grid = learnt_grid(n, sms);
-  learnt_adj_kernel<<<grid, LT, smem, st>>>(params, pc, s, a, dt, n, g, gs, ga, grad_params ? partials : nullptr);
+  learnt_adj_kernel<M><<<grid, LT, smem, st>>>(params, pc, s, a, dt, n, g, gs, ga, grad_params ? partials : nullptr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (grad_params) return launch_reduce_grad(partials, grid, Y::NP, 1.0f, grad_params, st);
+  if (grad_params) return launch_reduce_grad(partials, grid, RW::NP, 1.0f, grad_params, st);
   return cudaSuccess;
+}
+
+cudaError_t launch_learnt_fwd(int system, const float* params, const PhysConsts& pc, const float* s, const float* a,
+                              float dt, int n, float* out, int sms, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (system == SYS_QUAD) return launch_fwd_t<LearntQuad<float>>(params, pc, s, a, dt, n, out, sms, st);
+  if (system == SYS_WING) return launch_fwd_t<LearntWing<float>>(params, pc, s, a, dt, n, out, sms, st);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_learnt_adj(int system, const float* params, const PhysConsts& pc, const float* s, const float* a,
+                              float dt, int n, const float* g, float* gs, float* ga, float* grad_params,
+                              float* partials, int sms, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (system == SYS_QUAD)
+    return launch_adj_t<LearntQuad<float>>(params, pc, s, a, dt, n, g, gs, ga, grad_params, partials, sms, st);
+  if (system == SYS_WING)
+    return launch_adj_t<LearntWing<float>>(params, pc, s, a, dt, n, g, gs, ga, grad_params, partials, sms, st);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace apg

@@ -22,24 +22,24 @@ struct LearntLayout {
 };
 
 // Factor rows the adjoint kernel leaves per drone (one shared-memory row per factor component) and the mapping from
-// a flat parameter-gradient entry to the two rows whose dot product over the drones it is.
-namespace learnt_rows {
-constexpr int R_G = 0, R_H = R_G + 12, R_DH = R_H + 64, R_X = R_DH + 64, R_GAT = R_X + 16, R_A = R_GAT + 4,
-              R_DK = R_A + 4, R_DJ = R_DK + 3, R_ONE = R_DJ + 3, R_TOTAL = R_ONE + 1;     // 171 rows
-}
-// entry e of the flat parameter gradient = dot(row ra, row rb) over the drones; ra < 0: identically zero (mass)
-APG_HD void learnt_entry_rows(int e, int* ra, int* rb) {
-  using Y = LearntLayout;
-  using namespace learnt_rows;
-  if (e < Y::O_MASS) { *ra = R_GAT + e / 4; *rb = R_A + (e & 3); }                                  // linear_at[r][c]
-  else if (e < Y::O_J) { *ra = -1; *rb = -1; }
-  else if (e < Y::O_K) { *ra = R_DJ + (e - Y::O_J); *rb = R_ONE; }
-  else if (e < Y::O_W1) { *ra = R_DK + (e - Y::O_K); *rb = R_ONE; }
-  else if (e < Y::O_B1) { const int q = e - Y::O_W1; *ra = R_DH + q / Y::XD; *rb = R_X + q % Y::XD; }
-  else if (e < Y::O_W2) { *ra = R_DH + (e - Y::O_B1); *rb = R_ONE; }
-  else if (e < Y::O_B2) { const int q = e - Y::O_W2; *ra = R_G + q / Y::HD; *rb = R_H + q % Y::HD; }
-  else { *ra = R_G + (e - Y::O_B2); *rb = R_ONE; }
-}
+// a flat parameter-gradient entry to the two rows whose dot product over the drones it is.  Generic in the number of
+// "physical" parameters NPH that precede the residual MLP in the flat vector: each of them is a per-drone scalar
+// cotangent (row R_DP + e) summed over the drones (dot with the row of ones).
+template <int NPH>
+struct LearntRows {
+  static constexpr int XD = 16, HD = 64, SD = 12;
+  static constexpr int R_G = 0, R_H = R_G + SD, R_DH = R_H + HD, R_X = R_DH + HD, R_DP = R_X + XD, R_ONE = R_DP + NPH,
+                       R_TOTAL = R_ONE + 1;
+  static constexpr int O_W1 = NPH, O_B1 = O_W1 + HD * XD, O_W2 = O_B1 + HD, O_B2 = O_W2 + SD * HD, NP = O_B2 + SD;
+  // entry e of the flat parameter gradient = dot(row ra, row rb) over the drones
+  APG_HD static void entry_rows(int e, int* ra, int* rb) {
+    if (e < O_W1) { *ra = R_DP + e; *rb = R_ONE; }
+    else if (e < O_B1) { const int q = e - O_W1; *ra = R_DH + q / XD; *rb = R_X + q % XD; }
+    else if (e < O_W2) { *ra = R_DH + (e - O_B1); *rb = R_ONE; }
+    else if (e < O_B2) { const int q = e - O_W2; *ra = R_G + q / HD; *rb = R_H + q % HD; }
+    else { *ra = R_G + (e - O_B2); *rb = R_ONE; }
+  }
+};
 
 template <typename T>
 struct LearntQuad {
@@ -113,6 +113,25 @@ struct LearntQuad {
       const T J = T(pc[Q_JX + i]);
       dj[i] = -dt * T(pc[Q_RDX + i]) / (J * J) * g[9 + i];
     }
+  }
+
+  // ---- the interface the kernels use (same for the fixed wing): x = the 16 inputs of the residual MLP,
+  //      dph = per-drone cotangents of the NPH = 23 parameters that precede the MLP in the flat vector
+  static constexpr int NPH = Y::O_W1;
+  APG_HD static void fwd(const T* P, const float* pc, const T* s, const T* a, T dt, T* out, T* x, T* h, int hs) {
+    T at[4];
+    forward(P, pc, s, a, dt, out, at, h, hs);
+    for (int k = 0; k < 12; ++k) x[k] = s[k];
+    for (int k = 0; k < 4; ++k) x[12 + k] = at[k];
+  }
+  APG_HD static void adj(const T* P, const float* pc, const T* s, const T* a, const T* x, const T* h, int hs, T dt,
+                         const T* g, T* gs, T* ga, T* dh, T* dph) {
+    T gat[4], dk[3], dj[3];
+    adjoint(P, pc, s, a, x + 12, h, hs, dt, g, gs, ga, dh, gat, dk, dj);
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) dph[Y::O_LAT + r * 4 + c] = gat[r] * a[c];
+    dph[Y::O_MASS] = T(0);
+    for (int i = 0; i < 3; ++i) { dph[Y::O_J + i] = dj[i]; dph[Y::O_K + i] = dk[i]; }
   }
 };
 

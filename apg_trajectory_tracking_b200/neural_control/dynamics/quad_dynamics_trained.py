@@ -19,8 +19,11 @@ from .quad_dynamics_flightmare import FlightmareDynamics
 
 
 class _LearntStep(torch.autograd.Function):
+    """one learnt-dynamics step (system 0 = quadrotor, 1 = fixed wing): forward kernel + hand-written adjoint kernel
+    that returns the cotangents of the flat parameter vector, the state and the action"""
+
     @staticmethod
-    def forward(ctx, flat, state, action, dt, phys):
+    def forward(ctx, flat, state, action, dt, phys, system=0):
         _require_cuda(flat, state, action)
         lib = _capi.lib()
         s = state.detach().contiguous().float()
@@ -28,10 +31,10 @@ class _LearntStep(torch.autograd.Function):
         p = flat.detach().contiguous().float()
         out = torch.empty_like(s)
         with torch.cuda.device(s.device):
-            _capi.check(lib.apg_learnt_step(_p(p), ctypes.c_void_p(phys.ctypes.data), _p(s), _p(a), ctypes.c_float(dt),
-                                            s.shape[0], _p(out), _stream(s)))
+            _capi.check(lib.apg_learnt_step(system, _p(p), ctypes.c_void_p(phys.ctypes.data), _p(s), _p(a),
+                                            ctypes.c_float(dt), s.shape[0], _p(out), _stream(s)))
         ctx.save_for_backward(p, s, a)
-        ctx.dt, ctx.phys = dt, phys
+        ctx.dt, ctx.phys, ctx.system = dt, phys, system
         return out
 
     @staticmethod
@@ -42,11 +45,11 @@ class _LearntStep(torch.autograd.Function):
         gs, ga, gp = torch.empty_like(s), torch.empty_like(a), torch.empty_like(p)
         n = s.shape[0]
         with torch.cuda.device(s.device):
-            ws = torch.empty(lib.apg_learnt_workspace_bytes(n), dtype=torch.uint8, device=s.device)
-            _capi.check(lib.apg_learnt_step_adjoint(_p(p), ctypes.c_void_p(ctx.phys.ctypes.data), _p(s), _p(a),
-                                                    ctypes.c_float(ctx.dt), n, _p(g), _p(gs), _p(ga), _p(gp), _p(ws),
-                                                    _stream(s)))
-        return gp, gs, ga, None, None
+            ws = torch.empty(lib.apg_learnt_workspace_bytes(ctx.system, n), dtype=torch.uint8, device=s.device)
+            _capi.check(lib.apg_learnt_step_adjoint(ctx.system, _p(p), ctypes.c_void_p(ctx.phys.ctypes.data), _p(s),
+                                                    _p(a), ctypes.c_float(ctx.dt), n, _p(g), _p(gs), _p(ga), _p(gp),
+                                                    _p(ws), _stream(s)))
+        return gp, gs, ga, None, None, None
 
 
 class LearntDynamics(nn.Module, FlightmareDynamics):
@@ -78,7 +81,7 @@ class LearntDynamics(nn.Module, FlightmareDynamics):
         return self.linear_state_2(torch.relu(self.linear_state_1(x)))
 
     def forward(self, state, action, dt):
-        return _LearntStep.apply(self._flat(), state, action, float(dt), self.phys)
+        return _LearntStep.apply(self._flat(), state, action, float(dt), self.phys, 0)
 
     def __call__(self, state, action, dt):
         return nn.Module.__call__(self, state, action, dt)

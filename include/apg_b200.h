@@ -141,22 +141,27 @@ int apg_eval_fly_to_points(const apg_config* cfg, const float* params, const flo
                            float* states_out, float* div_linear_out, float* actions_out, int* n_steps_out,
                            float* div_target_sum_out, float* div_target_cnt_out, void* stream);
 
-/* ---- learnt residual quadrotor dynamics: LearntDynamics.forward
- * (neural_control/dynamics/quad_dynamics_trained.py:10-69) = simulate_quadrotor(linear_at @ action, state, dt) +
- * linear_state_2(relu(linear_state_1([state, linear_at @ action]))), and what autograd records for it: the
- * vector-Jacobian products w.r.t. state, action and the flat parameter vector (named_parameters() order:
- * linear_at 16 | mass 1 | torch_inertia_vector 3 | torch_kinv_vector 3 | linear_state_1.weight 1024 | .bias 64 |
- * linear_state_2.weight 768 | .bias 12 = apg_learnt_num_params() = 1891).  `phys`: the simulator constants of the
- * construction-time parameters (the reference never refreshes its derived kinv / inertia matrices, :47-48).
- * n rows; grad_state / grad_action / grad_params may be NULL; workspace: apg_learnt_workspace_bytes(n) bytes,
+/* ---- learnt residual dynamics, system = APG_SYS_QUAD or APG_SYS_WING:
+ *   quad  LearntDynamics.forward (neural_control/dynamics/quad_dynamics_trained.py:10-69) =
+ *         simulate_quadrotor(linear_at @ action, state, dt) + linear_state_2(relu(linear_state_1([state, at])));
+ *         flat parameters (named_parameters() order): linear_at 16 | mass 1 | torch_inertia_vector 3 |
+ *         torch_kinv_vector 3 | linear_state_1.weight 1024 | .bias 64 | linear_state_2.weight 768 | .bias 12 = 1891;
+ *         `phys`: the simulator constants of the construction-time parameters (the reference never refreshes its
+ *         derived kinv / inertia matrices, :47-48).
+ *   wing  LearntFixedWingDynamics.forward (neural_control/dynamics/fixed_wing_dynamics.py:270-326) =
+ *         simulate_fixed_wing(state, action, dt) + the same residual MLP on [state, action]; every physical constant
+ *         is a live parameter: I [3][3] | the 37 config scalars in SORTED key order (ParameterDict) | the MLP = 1914;
+ *         `phys` is ignored.
+ * and what autograd records for them: the vector-Jacobian products w.r.t. state, action and the flat parameter vector.
+ * n rows; grad_state / grad_action / grad_params may be NULL; workspace: apg_learnt_workspace_bytes(system, n) bytes,
  * 16-byte aligned (per-block partial gradients, reduced in fixed order). */
-int apg_learnt_num_params(void);
-size_t apg_learnt_workspace_bytes(int n);
-int apg_learnt_step(const float* params, const float* phys, const float* state, const float* action, float dt, int n,
-                    float* out, void* stream);
-int apg_learnt_step_adjoint(const float* params, const float* phys, const float* state, const float* action, float dt,
-                            int n, const float* grad_out, float* grad_state, float* grad_action, float* grad_params,
-                            void* workspace, void* stream);
+int apg_learnt_num_params(int system);
+size_t apg_learnt_workspace_bytes(int system, int n);
+int apg_learnt_step(int system, const float* params, const float* phys, const float* state, const float* action,
+                    float dt, int n, float* out, void* stream);
+int apg_learnt_step_adjoint(int system, const float* params, const float* phys, const float* state, const float* action,
+                            float dt, int n, const float* grad_out, float* grad_state, float* grad_action,
+                            float* grad_params, void* workspace, void* stream);
 
 int apg_sm_count(void);
 int apg_version(void);

@@ -640,3 +640,79 @@ def eval_fly_to_points(params, targets, init_states, mean, std, steps, h, dt_dat
     dtc = dtc + maxed.float()
     return dict(states=states, div_linear=div_lin, actions=actions, n_steps=n_steps, div_target_sum=dts,
                 div_target_cnt=dtc)
+
+
+# --------------------------------------------------------------------------------------------
+# N3 (fixed wing)  learnt dynamics (neural_control/dynamics/fixed_wing_dynamics.py:270-326, LearntFixedWingDynamics):
+#     next = simulate_fixed_wing(state, action, dt) + linear_state_2(relu(linear_state_1([state, action])))
+#     with EVERY physical constant a parameter: the full 3x3 inertia matrix `I` and one 1-element parameter per
+#     config key (a ParameterDict, which orders its keys by sorting them), used live by the simulator.
+#     lparams in named_parameters() order: I (3,3), cfg.<key> for key in WING_LEARNT_KEYS (1,) each,
+#     linear_state_1.weight (64,16), .bias (64,), linear_state_2.weight (12,64), .bias (12,).
+#     Quirk kept: gravity enters through `torch.tensor(g_m)` (:197), which DETACHES g * mass -> `g` gets no gradient
+#     and `mass` only the one through 1/mass.
+# --------------------------------------------------------------------------------------------
+WING_LEARNT_KEYS = sorted(k for k in WING_CFG if not k.startswith("I_"))
+
+
+def wing_step_general(state, action, dt, c, inertia):
+    """wing_step with tensor-valued constants c[key] (0-dim or 1-element) and a general 3x3 inertia matrix, the
+    inverse and products written out like the reference (torch.inverse / matmul, :250-255)"""
+    x, y, z, u, v, w, phi, theta, psi, p, q, r = _cols(state)
+    a0, a1, a2, a3 = _cols(action)
+    pi = math.pi
+    T = a0 * 7
+    del_e = pi * (a1 * 40 - 20) / 180
+    del_a = pi * (a2 * 5 - 2.5) / 180
+    del_r = pi * (a3 * 40 - 20) / 180
+    g_m = (c["g"] * c["mass"]).detach()                                 # torch.tensor(g_m): no gradient (:197)
+    V = torch.sqrt(u ** 2 + v ** 2 + w ** 2)
+    alpha = torch.clamp(torch.arctan(w / u), -ALPHA_BOUND, ALPHA_BOUND)
+    beta = torch.clamp(torch.arctan(v / V), -ALPHA_BOUND, ALPHA_BOUND)
+    c2v, b2v = c["c"] / (2 * V), c["b"] / (2 * V)
+    CL = c["CL0"] + c["CL_alpha"] * alpha + c["CL_q"] * c2v * q + c["CL_del_e"] * del_e
+    CD = c["CD0"] + c["CD_alpha"] * alpha + c["CD_q"] * c2v * q + c["CD_del_e"] * del_e
+    CY = (c["CY0"] + c["CY_beta"] * beta + c["CY_p"] * b2v * p + c["CY_r"] * b2v * r + c["CY_del_a"] * del_a
+          + c["CY_del_r"] * del_r)
+    Cl = (c["Cl0"] + c["Cl_beta"] * beta + c["Cl_p"] * b2v * p + c["Cl_r"] * b2v * r + c["Cl_del_a"] * del_a
+          + c["Cl_del_r"] * del_r)
+    Cm = c["Cm0"] + c["Cm_alpha"] * alpha + c["Cm_q"] * c2v * q + c["Cm_del_e"] * del_e
+    Cn = (c["Cn0"] + c["Cn_beta"] * beta + c["Cn_p"] * b2v * p + c["Cn_r"] * b2v * r + c["Cn_del_a"] * del_a
+          + c["Cn_del_r"] * del_r)
+    qS = 0.5 * c["rho"] * V ** 2 * c["S"]
+    L, D, Y = qS * CL, qS * CD, qS * CY
+    l_m, m_m, n_m = qS * c["c"] * Cl, qS * c["c"] * Cm, qS * c["c"] * Cn
+    sa, ca, sb, cb = torch.sin(alpha), torch.cos(alpha), torch.sin(beta), torch.cos(beta)
+    sph, cph, sth, cth = torch.sin(phi), torch.cos(phi), torch.sin(theta), torch.cos(theta)
+    sps, cps = torch.sin(psi), torch.cos(psi)
+    ce, se = torch.cos(c["epsilon"]), torch.sin(c["epsilon"])
+    fx = ca * cb * (-D) + (-ca * sb) * Y + (-sa) * (-L) + (-sth) * g_m + T * ce
+    fy = sb * (-D) + cb * Y + (sph * cth) * g_m
+    fz = sa * cb * (-D) + (-sa * sb) * Y + ca * (-L) + (cph * cth) * g_m + T * se
+    xd = cth * cps * u + (-cph * sps + sph * sth * cps) * v + (sph * sps + cph * sth * cps) * w
+    yd = cth * sps * u + (cph * cps + sph * sth * sps) * v + (-sph * cps + cph * sth * sps) * w
+    zd = -sth * u + sph * cth * v + cph * cth * w
+    inv_m = 1.0 / c["mass"]
+    ud = inv_m * fx - (q * w - r * v)
+    vd = inv_m * fy - (r * u - p * w)
+    wd = inv_m * fz - (p * v - q * u)
+    tth = torch.tan(theta)
+    phid = p + sph * tth * q + cph * tth * r
+    thetad = cph * q - sph * r
+    psid = (sph / cth) * q + (cph / cth) * r
+    omega = torch.stack((p, q, r), dim=1)
+    iw = omega @ inertia.t()                                             # I omega, per row
+    mom = torch.stack((l_m, m_m, n_m), dim=1)
+    rhs = mom - torch.cross(omega, iw, dim=1)
+    od = rhs @ torch.inverse(inertia).t()                               # I^-1 rhs
+    dot = torch.stack((xd, yd, zd, ud, vd, wd, phid, thetad, psid, od[:, 0], od[:, 1], od[:, 2]), dim=1)
+    return state + float(dt) * dot
+
+
+def learnt_wing_step(lparams, state, action, dt):
+    inertia = lparams[0]
+    c = {k: lparams[1 + i].reshape(()) for i, k in enumerate(WING_LEARNT_KEYS)}
+    w1, b1, w2, b2 = lparams[1 + len(WING_LEARNT_KEYS):]
+    new_state = wing_step_general(state, action, dt, c, inertia)
+    x = torch.cat((state, action), dim=1)
+    return new_state + torch.relu(x @ w1.t() + b1) @ w2.t() + b2

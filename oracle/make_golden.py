@@ -212,6 +212,45 @@ def make_learnt_golden(args):
               "max |g mass| %.3g" % float(out[f"{tag}_gparam_1"].abs().max()),
               "max |g J| %.3g" % float(out[f"{tag}_gparam_2"].abs().max()))
     out["param_names"] = np.array(names)
+    # ---- fixed wing: LearntFixedWingDynamics.forward (fixed_wing_dynamics.py:270-326) with seeded non-zero residual
+    #      MLP; case "wa": the shipped constants, case "wb": every constant perturbed by a few percent and a general
+    #      (non-symmetric, fully populated) inertia matrix, which is what SGD turns `I` into after one step
+    from neural_control.dynamics.fixed_wing_dynamics import LearntFixedWingDynamics
+    import warnings
+    warnings.filterwarnings("ignore")
+    for tag in ("wa", "wb"):
+        dw_ = LearntFixedWingDynamics()
+        with torch.no_grad():
+            dw_.linear_state_1.weight.copy_(0.3 * torch.randn(64, 16))
+            dw_.linear_state_1.bias.copy_(0.1 * torch.randn(64))
+            dw_.linear_state_2.weight.copy_(0.1 * torch.randn(12, 64))
+            dw_.linear_state_2.bias.copy_(0.05 * torch.randn(12))
+            if tag == "wb":
+                dw_.I.add_(0.003 * torch.randn(3, 3))
+                for k, p in dw_.cfg.items():
+                    p.mul_(1 + 0.05 * float(torch.randn(())))
+                    if float(p.abs()) == 0.0:
+                        p.add_(0.02 * float(torch.randn(())))
+        n, dt = 29, 0.05
+        s = torch.zeros(n, 12)
+        s[:, :3] = torch.randn(n, 3)
+        s[:, 3] = 11.5 + 0.5 * torch.randn(n)
+        s[:, 4:6] = 0.4 * torch.randn(n, 2)
+        s[:, 6:9] = 0.1 * torch.randn(n, 3)
+        s[:, 9:] = 0.1 * torch.randn(n, 3)
+        s.requires_grad_(True)
+        a = torch.rand(n, 4).requires_grad_(True)
+        cot = torch.randn(n, 12)
+        o = dw_(s, a, dt)
+        wnames = [k for k, _ in dw_.named_parameters()]
+        grads = torch.autograd.grad(o, [s, a] + [p for _, p in dw_.named_parameters()], cot, allow_unused=True)
+        out.update({f"{tag}_state": s, f"{tag}_action": a, f"{tag}_cot": cot, f"{tag}_out": o, f"{tag}_dt": dt,
+                    f"{tag}_gstate": grads[0], f"{tag}_gaction": grads[1]})
+        for i, (k, p) in enumerate(dw_.named_parameters()):
+            out[f"{tag}_param_{i}"] = p
+            out[f"{tag}_gparam_{i}"] = grads[2 + i] if grads[2 + i] is not None else torch.zeros_like(p)
+        print("learnt wing", tag, "params", len(wnames), "max |gI| %.3g" % float(out[f"{tag}_gparam_0"].abs().max()))
+    out["wing_param_names"] = np.array(wnames)
     np.savez_compressed(os.path.join(args.out, "learnt_dyn.npz"), **npify(out))
 
 

@@ -183,7 +183,7 @@ def test_learnt_dynamics_mirror_has_reference_parameters_and_refuses_cpu(capi):
     assert names == [str(x) for x in g["param_names"]]
     for i, (_, p) in enumerate(d.named_parameters()):
         assert tuple(p.shape) == g[f"a_param_{i}"].shape
-    assert sum(p.numel() for p in d.parameters()) == capi.lib().apg_learnt_num_params() == 1891
+    assert sum(p.numel() for p in d.parameters()) == capi.lib().apg_learnt_num_params(0) == 1891
     assert torch.equal(d.linear_at.detach(), torch.eye(4)) and float(d.linear_state_2.weight.abs().max()) == 0.0
     with pytest.raises(ApgError):
         d(torch.zeros(2, 12), torch.zeros(2, 4), 0.1)
@@ -205,9 +205,11 @@ def test_new_entry_points_validate_their_arguments_before_touching_the_device(ca
     assert lib.apg_sample_windows(pb, 100, 8, 10, 20, 3, pb, pb, None) == BAD          # fewer than 9 columns
     assert lib.apg_sample_windows(pb, 100, 9, 10, 20, 6, pb, pb, None) == BAD          # would read past the table
     assert lib.apg_poly_reference(None, 4, 10, C.c_float(0.1), C.c_float(0.1), pb, None) == BAD
-    assert lib.apg_learnt_step(None, pb, pb, pb, C.c_float(0.1), 4, pb, None) == BAD
-    assert lib.apg_learnt_step_adjoint(pb, pb, pb, pb, C.c_float(0.1), 4, pb, pb, pb, pb, None, None) == BAD
-    assert lib.apg_learnt_workspace_bytes(1000) >= 1891 * 4
+    assert lib.apg_learnt_step(0, None, pb, pb, pb, C.c_float(0.1), 4, pb, None) == BAD
+    assert lib.apg_learnt_step(2, pb, pb, pb, pb, C.c_float(0.1), 4, pb, None) == UNSUP          # cartpole
+    assert lib.apg_learnt_step_adjoint(1, pb, pb, pb, pb, C.c_float(0.1), 4, pb, pb, pb, pb, None, None) == BAD
+    assert lib.apg_learnt_workspace_bytes(0, 1000) >= 1891 * 4 and lib.apg_learnt_workspace_bytes(1, 1000) >= 1914 * 4
+    assert lib.apg_learnt_num_params(1) == 1914 and lib.apg_learnt_num_params(2) == UNSUP
     ws = C.c_void_p((C.addressof(buf) + 255) & ~255)
     quad = R.RolloutSpec.quad_concurrent(10, 0.1).config(8)
     wing = R.RolloutSpec.wing_concurrent(10, 0.05).config(8)
@@ -224,3 +226,18 @@ def test_new_entry_points_validate_their_arguments_before_touching_the_device(ca
     assert fly(quad) == UNSUP and fly(wing, k=0) == BAD and fly(wing) == NODEV
     for code in (BAD, UNSUP, -3, NODEV):
         assert lib.apg_error_string(code).startswith(b"apg:")
+
+
+def test_learnt_wing_mirror_has_reference_parameters_and_refuses_cpu():
+    from neural_control.dynamics.fixed_wing_dynamics import LearntFixedWingDynamics
+    from apg_trajectory_tracking_b200._capi import ApgError
+    g = load_golden("learnt_dyn.npz")
+    d = LearntFixedWingDynamics()
+    assert [n for n, _ in d.named_parameters()] == [str(x) for x in g["wing_param_names"]]
+    for i, (n, p) in enumerate(d.named_parameters()):
+        assert tuple(p.shape) == g[f"wa_param_{i}"].shape
+        if "linear" not in n:
+            assert np.allclose(p.detach().numpy(), g[f"wa_param_{i}"]), n        # the shipped constants
+    assert d._flat().numel() == 1914
+    with pytest.raises(ApgError):
+        d(torch.zeros(2, 12), torch.zeros(2, 4), 0.05)

@@ -109,3 +109,78 @@ def test_tiled_factor_rows_reproduce_the_parameter_gradient(hl):
     assert np.array_equal(gs1, gs2) and np.array_equal(ga1, ga2)
     assert np.abs(gp1 - gp2).max() <= 2e-5 * np.abs(gp1).max()
     assert np.abs(gp2[16:17]).max() == 0.0 and np.abs(gp2).min() >= 0 and np.count_nonzero(gp2) > 1800
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fixed wing: LearntFixedWingDynamics (every physical constant a live parameter, general 3x3 inertia matrix)
+# ---------------------------------------------------------------------------------------------------------------
+def _wing_case(tag, dtype):
+    g = load_golden("learnt_dyn.npz")
+    flat = np.concatenate([np.asarray(g[f"{tag}_param_{i}"]).reshape(-1) for i in range(42)]).astype(dtype)
+    arr = lambda k: np.ascontiguousarray(g[f"{tag}_{k}"], dtype=dtype)          # noqa: E731
+    return g, flat, arr("state"), arr("action"), arr("cot"), float(g[f"{tag}_dt"])
+
+
+@pytest.mark.parametrize("tag", ["wa", "wb"])
+def test_wing_forward_and_adjoint_match_reference_fp32(hl, tag):
+    g, flat, s, a, cot, dt = _wing_case(tag, np.float32)
+    assert hl.hc_learnt_wing_num_params() == flat.size == 1914
+    assert [str(x) for x in g["wing_param_names"]][1:38] == ["cfg." + k for k in O.WING_LEARNT_KEYS]
+    n = s.shape[0]
+    out = np.zeros_like(s)
+    hl.hc_learnt_wing_fwd_f32(_p(flat), _p(s), _p(a), ctypes.c_float(dt), n, _p(out))
+    assert np.abs(out - g[f"{tag}_out"]).max() <= 5e-6 * np.abs(g[f"{tag}_out"]).max()
+    gs, ga, gp = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    hl.hc_learnt_wing_adj_f32(_p(flat), _p(s), _p(a), ctypes.c_float(dt), n, _p(cot), _p(gs), _p(ga), _p(gp))
+    assert np.abs(gs - g[f"{tag}_gstate"]).max() <= 5e-5 * np.abs(g[f"{tag}_gstate"]).max()
+    assert np.abs(ga - g[f"{tag}_gaction"]).max() <= 5e-5 * np.abs(g[f"{tag}_gaction"]).max()
+    off = np.cumsum([0] + [np.asarray(g[f"{tag}_param_{i}"]).size for i in range(42)])
+    names = [str(x) for x in g["wing_param_names"]]
+    for i in range(42):
+        got, want = gp[off[i]:off[i + 1]], np.asarray(g[f"{tag}_gparam_{i}"]).reshape(-1)
+        if names[i] == "cfg.g":
+            assert np.abs(got).max() == 0.0 and np.abs(want).max() == 0.0            # detached in the reference
+        else:
+            # fp32 sums over 29 drones of terms of mixed sign: relative to the tensor's own scale
+            assert np.abs(got - want).max() <= 2e-4 * max(np.abs(want).max(), 1e-2), names[i]
+
+
+@pytest.mark.parametrize("tag", ["wa", "wb"])
+def test_wing_adjoint_matches_oracle_autograd_fp64(hl, tag):
+    g, flat, s, a, cot, dt = _wing_case(tag, np.float64)
+    n = s.shape[0]
+    out = np.zeros_like(s)
+    hl.hc_learnt_wing_fwd_f64(_p(flat), _p(s), _p(a), ctypes.c_double(dt), n, _p(out))
+    gs, ga, gp = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    hl.hc_learnt_wing_adj_f64(_p(flat), _p(s), _p(a), ctypes.c_double(dt), n, _p(cot), _p(gs), _p(ga), _p(gp))
+    lparams = [torch.tensor(np.asarray(g[f"{tag}_param_{i}"]), dtype=torch.float64, requires_grad=True)
+               for i in range(42)]
+    ts, ta = torch.tensor(s, requires_grad=True), torch.tensor(a, requires_grad=True)
+    want_out = O.learnt_wing_step(lparams, ts, ta, dt)
+    assert np.abs(out - want_out.detach().numpy()).max() <= 1e-12 * np.abs(out).max()
+    grads = torch.autograd.grad(want_out, [ts, ta] + lparams, torch.tensor(cot), allow_unused=True)
+    assert np.abs(gs - grads[0].numpy()).max() <= 1e-10 * np.abs(gs).max()
+    assert np.abs(ga - grads[1].numpy()).max() <= 1e-10 * np.abs(ga).max()
+    off = np.cumsum([0] + [p.numel() for p in lparams])
+    for i in range(42):
+        want = (grads[2 + i] if grads[2 + i] is not None else torch.zeros_like(lparams[i])).numpy().reshape(-1)
+        assert np.abs(gp[off[i]:off[i + 1]] - want).max() <= 1e-10 * max(np.abs(want).max(), 1e-3), i
+
+
+def test_wing_tiled_factor_rows_reproduce_the_parameter_gradient(hl):
+    rng = np.random.default_rng(2)
+    g, flat, s0, _, _, dt = _wing_case("wb", np.float32)
+    n = 300
+    s = np.repeat(s0, 11, axis=0)[:n].copy()
+    s += (0.02 * rng.standard_normal(s.shape)).astype(np.float32)
+    a = rng.random((n, 4)).astype(np.float32)
+    cot = rng.standard_normal((n, 12)).astype(np.float32)
+    gs1, ga1, gp1 = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    gs2, ga2, gp2 = np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    hl.hc_learnt_wing_adj_f32(_p(flat), _p(s), _p(a), ctypes.c_float(dt), n, _p(cot), _p(gs1), _p(ga1), _p(gp1))
+    hl.hc_learnt_wing_adj_tiled_f32(_p(flat), _p(s), _p(a), ctypes.c_float(dt), n, _p(cot), _p(gs2), _p(ga2), _p(gp2),
+                                    128)
+    assert np.array_equal(gs1, gs2) and np.array_equal(ga1, ga2)
+    off = [0, 9, 46, 46 + 1024, 46 + 1088, 46 + 1088 + 768, 1914]
+    for lo, hi in zip(off, off[1:]):
+        assert np.abs(gp1[lo:hi] - gp2[lo:hi]).max() <= 5e-5 * max(np.abs(gp1[lo:hi]).max(), 1e-3)

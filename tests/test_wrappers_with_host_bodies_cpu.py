@@ -110,14 +110,22 @@ class _HostLib:
                              self._vp(_addr(n_steps)), self._vp(_addr(dts)), self._vp(_addr(dtc)))
         return 0
 
-    def apg_learnt_step(self, params, phys, state, action, dt, n, out, stream):
-        self.ln.hc_learnt_fwd_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
-                                  ctypes.c_float(_f(dt)), n, self._vp(_addr(out)))
+    def apg_learnt_step(self, system, params, phys, state, action, dt, n, out, stream):
+        if system == 0:
+            self.ln.hc_learnt_fwd_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
+                                      ctypes.c_float(_f(dt)), n, self._vp(_addr(out)))
+        else:
+            self.ln.hc_learnt_wing_fwd_f32(*[self._vp(_addr(x)) for x in (params, state, action)],
+                                           ctypes.c_float(_f(dt)), n, self._vp(_addr(out)))
         return 0
 
-    def apg_learnt_step_adjoint(self, params, phys, state, action, dt, n, g, gs, ga, gp, ws, stream):
-        self.ln.hc_learnt_adj_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
-                                  ctypes.c_float(_f(dt)), n, *[self._vp(_addr(x)) for x in (g, gs, ga, gp)])
+    def apg_learnt_step_adjoint(self, system, params, phys, state, action, dt, n, g, gs, ga, gp, ws, stream):
+        if system == 0:
+            self.ln.hc_learnt_adj_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
+                                      ctypes.c_float(_f(dt)), n, *[self._vp(_addr(x)) for x in (g, gs, ga, gp)])
+        else:
+            self.ln.hc_learnt_wing_adj_f32(*[self._vp(_addr(x)) for x in (params, state, action)],
+                                           ctypes.c_float(_f(dt)), n, *[self._vp(_addr(x)) for x in (g, gs, ga, gp)])
         return 0
 
 
@@ -244,3 +252,22 @@ def test_wing_target_evaluator_wrapper(hostlib):
         assert abs(m - dtg.mean()) <= 2e-4 * max(dtg.mean(), 1.0) and sd == 0.0
     slim = ev.fly(R.flatten_params(params), targets, steps=20, want=())
     assert set(slim) == {"n_steps", "div_target_sum", "div_target_cnt"} and int(slim["n_steps"][0]) == 20
+
+
+def test_learnt_wing_dynamics_wrapper(hostlib):
+    from apg_trajectory_tracking_b200.neural_control.dynamics.fixed_wing_dynamics import LearntFixedWingDynamics
+    g = load_golden("learnt_dyn.npz")
+    d = LearntFixedWingDynamics()
+    with torch.no_grad():
+        for i, (_, p) in enumerate(d.named_parameters()):
+            p.copy_(torch.tensor(g[f"wb_param_{i}"]))
+    s = torch.tensor(g["wb_state"]).requires_grad_(True)
+    a = torch.tensor(g["wb_action"]).requires_grad_(True)
+    out = d(s, a, float(g["wb_dt"]))
+    assert float((out.detach() - torch.tensor(g["wb_out"])).abs().max()) <= 5e-6 * float(np.abs(g["wb_out"]).max())
+    (out * torch.tensor(g["wb_cot"])).sum().backward()
+    assert torch.allclose(s.grad, torch.tensor(g["wb_gstate"]), atol=5e-5 * float(np.abs(g["wb_gstate"]).max()))
+    assert torch.allclose(a.grad, torch.tensor(g["wb_gaction"]), atol=5e-5 * float(np.abs(g["wb_gaction"]).max()))
+    for i, (name, p) in enumerate(d.named_parameters()):
+        want = torch.tensor(g[f"wb_gparam_{i}"])
+        assert float((p.grad - want).abs().max()) <= 2e-4 * max(float(want.abs().max()), 1e-2), name

@@ -295,6 +295,48 @@ def test_learnt_dynamics_matches_reference(tag):
             assert err <= 5e-5 * max(float(want.abs().max()), 1e-3 * scale), (name, err)
 
 
+@pytest.mark.parametrize("tag", ["wa", "wb"])
+def test_learnt_wing_dynamics_matches_reference(tag):
+    """LearntFixedWingDynamics: forward, state / action cotangents and the gradient of all 42 parameter tensors"""
+    from apg_trajectory_tracking_b200.neural_control.dynamics.fixed_wing_dynamics import LearntFixedWingDynamics
+    g = load_golden("learnt_dyn.npz")
+    d = LearntFixedWingDynamics()
+    with torch.no_grad():
+        for i, (_, p) in enumerate(d.named_parameters()):
+            p.copy_(torch.tensor(g[f"{tag}_param_{i}"]))
+    d = d.cuda()
+    s = torch.tensor(g[f"{tag}_state"]).cuda().requires_grad_(True)
+    a = torch.tensor(g[f"{tag}_action"]).cuda().requires_grad_(True)
+    out = d(s, a, float(g[f"{tag}_dt"]))
+    assert _close(out, g[f"{tag}_out"], 5e-6)
+    (out * torch.tensor(g[f"{tag}_cot"]).cuda()).sum().backward()
+    assert _close(s.grad, g[f"{tag}_gstate"], 5e-5) and _close(a.grad, g[f"{tag}_gaction"], 5e-5)
+    for i, (name, p) in enumerate(d.named_parameters()):
+        want = torch.tensor(g[f"{tag}_gparam_{i}"])
+        err = float((p.grad.cpu() - want).abs().max())
+        assert err <= 2e-4 * max(float(want.abs().max()), 1e-2), (name, err)
+    # several tiles per block, ragged: against fp32 autograd of the oracle
+    from oracle import apg_oracle as O
+    gen = torch.Generator().manual_seed(1)
+    n = 3000
+    s0 = torch.tensor(g[f"{tag}_state"])
+    sn = s0[torch.randint(0, s0.shape[0], (n,), generator=gen)] + 0.02 * torch.randn(n, 12, generator=gen)
+    an, cot = torch.rand(n, 4, generator=gen), torch.randn(n, 12, generator=gen)
+    lparams = [p.detach().cpu().clone().requires_grad_(True) for _, p in d.named_parameters()]
+    so, ao = sn.clone().requires_grad_(True), an.clone().requires_grad_(True)
+    want = O.learnt_wing_step(lparams, so, ao, 0.05)
+    wg = torch.autograd.grad(want, [so, ao] + lparams, cot, allow_unused=True)
+    d.zero_grad()
+    sc, ac = sn.cuda().requires_grad_(True), an.cuda().requires_grad_(True)
+    out = d(sc, ac, 0.05)
+    assert _close(out, want.detach(), 5e-6)
+    (out * cot.cuda()).sum().backward()
+    assert _close(sc.grad, wg[0], 5e-5) and _close(ac.grad, wg[1], 5e-5)
+    for i, (name, p) in enumerate(d.named_parameters()):
+        if wg[2 + i] is not None:
+            assert rel_err(p.grad, wg[2 + i]) <= 2e-4, name
+
+
 def test_learnt_dynamics_many_tiles_vs_oracle_and_training_step():
     """N = 5000 (several 128-drone tiles per block, ragged tail) against fp32 autograd of the oracle; then three
     train_dynamics_model steps of the trainer against the same steps on the oracle"""
