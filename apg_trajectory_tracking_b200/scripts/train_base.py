@@ -105,9 +105,20 @@ class TrainBase:
 
     def run_epoch(self, train="controller", epoch=0):
         running_loss, i = 0.0, 0
+        learnt = isinstance(self.train_dynamics, torch.nn.Module)      # LearntDynamics / LearntFixedWingDynamics
         for i, data in enumerate(self.trainloader, 0):
             in_state, current_state, in_ref_state, ref_states = data
-            loss = self.fused_train_step(in_state, current_state, in_ref_state, ref_states)
+            if learnt and self.train_mode == "concurrent":
+                # the controller is trained THROUGH the learnt dynamics (train_drone.py:262-279): the reference's
+                # own loop, autograd over the per-step CUDA ops (policy forward, learnt step + its adjoint kernel)
+                dev = self.fused.device
+                in_state, current_state, in_ref_state, ref_states = (x.to(dev) for x in (in_state, current_state,
+                                                                                          in_ref_state, ref_states))
+                actions = torch.sigmoid(self.net(in_state, in_ref_state))
+                action_seq = torch.reshape(actions, (-1, self.horizon, self.action_dim))
+                loss = self.train_controller_model(current_state, action_seq, in_ref_state, ref_states)
+            else:
+                loss = self.fused_train_step(in_state, current_state, in_ref_state, ref_states)
             running_loss += loss.item()
         epoch_loss = running_loss / max(i, 1)      # the reference divides by the last batch index (:213)
         self.results_dict["loss"].append(epoch_loss)

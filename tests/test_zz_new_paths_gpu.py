@@ -337,6 +337,28 @@ def test_learnt_wing_dynamics_matches_reference(tag):
             assert rel_err(p.grad, wg[2 + i]) <= 2e-4, name
 
 
+def test_learnt_controller_epoch_through_identity_learnt_dynamics_equals_fused_epoch():
+    """TrainDrone.run_epoch with train_dynamics = LearntDynamics at its initial values (identity action transform,
+    zero residual) takes the un-fused path through the learnt step and must reproduce the fused epoch"""
+    from apg_trajectory_tracking_b200.scripts.train_drone import TrainDrone
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_trained import LearntDynamics
+    PR, R, SY, T, DS = _mods()
+    n, h, dt = 512, 10, 0.1
+    raw = SY.quad_case(n, h, dt, seed=4)
+    cfg = dict(delta_t=dt, horizon=h, ref_dim=9, action_dim=4, state_size=12, batch_size=128, system="quad",
+               learning_rate_controller=1e-5, train_mode="concurrent", device="cuda:0")
+    losses = []
+    for dyn in (FlightmareDynamics(), LearntDynamics().cuda()):
+        torch.manual_seed(0)
+        tr = TrainDrone(dyn, FlightmareDynamics(), dict(cfg))
+        tr.initialize_model(state_data=DS.QuadDataset(raw["cur"].numpy(), raw["ref"].numpy()))
+        tr.trainloader = torch.utils.data.DataLoader(tr.state_data, batch_size=128, shuffle=False)
+        losses.append([tr.run_epoch(epoch=e) for e in range(2)])
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 1e-4 * abs(a), losses
+
+
 def test_learnt_dynamics_many_tiles_vs_oracle_and_training_step():
     """N = 5000 (several 128-drone tiles per block, ragged tail) against fp32 autograd of the oracle; then three
     train_dynamics_model steps of the trainer against the same steps on the oracle"""
