@@ -260,3 +260,28 @@ def test_eval_fly_to_points_matches_reference_evaluator(name):
     assert np.abs(out["div_linear"][0, :taken].numpy() - dl).max() <= 2e-5 * max(dl.max(), 1.0)
     assert int(out["div_target_cnt"][0]) == len(dtg)
     assert abs(float(out["div_target_sum"][0]) - dtg.sum()) <= 1e-4 * max(dtg.sum(), 1.0)
+
+
+@pytest.mark.parametrize("tag", ["wa", "wb"])
+def test_learnt_wing_dynamics_forward_and_vjp_match_reference(tag):
+    """LearntFixedWingDynamics (fixed_wing_dynamics.py:270-326): shipped constants (wa) and every constant perturbed
+    with a fully populated inertia matrix (wb)"""
+    g = load_golden("learnt_dyn.npz")
+    assert [str(x) for x in g["wing_param_names"]][1:38] == ["cfg." + k for k in O.WING_LEARNT_KEYS]
+    lparams = [torch.tensor(g[f"{tag}_param_{i}"], requires_grad=True) for i in range(42)]
+    s, a = t(g[f"{tag}_state"]).requires_grad_(True), t(g[f"{tag}_action"]).requires_grad_(True)
+    out = O.learnt_wing_step(lparams, s, a, float(g[f"{tag}_dt"]))
+    assert max_rel_to_scale(out, g[f"{tag}_out"]) <= 2e-6
+    grads = torch.autograd.grad(out, [s, a] + lparams, t(g[f"{tag}_cot"]), allow_unused=True)
+    assert max_rel_to_scale(grads[0], g[f"{tag}_gstate"]) <= 1e-5
+    assert max_rel_to_scale(grads[1], g[f"{tag}_gaction"]) <= 1e-5
+    for i in range(42):
+        want = t(g[f"{tag}_gparam_{i}"])
+        got = grads[2 + i] if grads[2 + i] is not None else torch.zeros_like(lparams[i])
+        assert float((got - want).abs().max()) <= 1e-5 * max(float(want.abs().max()), 1e-3), i
+    # with the shipped constants the general-inertia restatement reduces to the pinned wing_step
+    if tag == "wa":
+        assert max_rel_to_scale(O.learnt_wing_step([p.detach() for p in lparams[:38]] +
+                                                   [torch.zeros(64, 16), torch.zeros(64), torch.zeros(12, 64),
+                                                    torch.zeros(12)], s.detach(), a.detach(), 0.05),
+                                O.wing_step(s.detach(), a.detach(), 0.05)) <= 1e-6
