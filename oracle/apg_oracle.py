@@ -716,3 +716,50 @@ def learnt_wing_step(lparams, state, action, dt):
     new_state = wing_step_general(state, action, dt, c, inertia)
     x = torch.cat((state, action), dim=1)
     return new_state + torch.relu(x @ w1.t() + b1) @ w2.t() + b2
+
+
+# --------------------------------------------------------------------------------------------
+# N2 (cartpole)  closed-loop balancing evaluation: Evaluator.evaluate_in_environment (scripts/evaluate_cartpole.py:
+#     81-262, state-based controller) with CartpoleWrapper.predict_actions (controllers/network_wrapper.py:101-148)
+#     and CartPoleEnv._step / is_upright (environments/cartpole_env.py:52-84), for N independent runs at once.
+#     Kept quirk: simple_model.Net zeroes column 0 of its input IN PLACE (simple_model.py:21); from the second step on
+#     the wrapper's tensor shares memory with the environment's float32 state, so the cart POSITION of the
+#     environment itself is reset to zero before every policy call but the first.
+# --------------------------------------------------------------------------------------------
+def eval_cartpole_balance(params, init_states, max_steps, dt, thresh_div=0.21, burn_in_steps=50, cfg=CARTPOLE_CFG):
+    """Returns dict(states (N,max_steps,4) as returned by env._step, actions (N,max_steps), success (N,) = index of
+    the last step taken, n_steps (N,), mean_angle (N,) = mean |theta| after the burn-in (100 if none),
+    vel_sum (N,) = sum of |x_dot| over the steps)."""
+    n = init_states.shape[0]
+    s = init_states.float().clone()
+    alive = torch.ones(n, dtype=torch.bool)
+    states = torch.zeros(n, max_steps, 4)
+    actions = torch.zeros(n, max_steps)
+    n_steps = torch.zeros(n, dtype=torch.long)
+    ang_sum, ang_cnt, vel_sum = torch.zeros(n), torch.zeros(n), torch.zeros(n)
+    for i in range(max_steps):
+        if not bool(alive.any()):
+            break
+        if i > 0:
+            s = s.clone()
+            s[:, 0] = 0                                                   # the in-place zeroing reached the env state
+        x_in = s.clone()
+        with torch.no_grad():
+            a0 = simple_forward(params, x_in)[:, 0:1]                     # first of the h predicted actions
+        nxt = cartpole_step(s, a0, dt, cfg).float()
+        th = nxt[:, 2]
+        th = torch.where(th > math.pi, th - 2 * math.pi, torch.where(th <= -math.pi, th + 2 * math.pi, th))
+        nxt = torch.cat((nxt[:, :2], th[:, None], nxt[:, 3:]), dim=1)
+        states[alive, i] = nxt[alive]
+        actions[alive, i] = a0[alive, 0]
+        n_steps[alive] += 1
+        vel_sum = vel_sum + torch.where(alive, nxt[:, 1].abs(), torch.zeros(n))
+        if i > burn_in_steps:
+            ang_sum = ang_sum + torch.where(alive, nxt[:, 2].abs(), torch.zeros(n))
+            ang_cnt = ang_cnt + alive.float()
+        s = torch.where(alive[:, None], nxt, s)
+        upright = (nxt[:, 2] > -thresh_div) & (nxt[:, 2] < thresh_div)
+        alive = alive & upright
+    mean_angle = torch.where(ang_cnt > 0, ang_sum / ang_cnt.clamp(min=1), torch.full((n,), 100.0))
+    return dict(states=states, actions=actions, success=n_steps - 1, n_steps=n_steps, mean_angle=mean_angle,
+                vel_sum=vel_sum)

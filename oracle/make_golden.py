@@ -163,6 +163,55 @@ def make_wing_eval_golden(args):
     np.savez_compressed(os.path.join(args.out, "eval_wing.npz"), **npify(out))
 
 
+def make_cartpole_eval_golden(args):
+    """eval_cartpole.npz: Evaluator.evaluate_in_environment (scripts/evaluate_cartpole.py) of the unmodified reference
+    with the shipped model_cartpole: the state after every env._step and the success indices.  The reference always
+    starts from the zero state (:101-116); the runs with other start states and thresholds patch ONLY the start
+    state the reset leaves behind."""
+    import torch
+    cwd = os.getcwd()
+    os.chdir(args.ref)
+    import evaluate_cartpole as EC
+    from neural_control.environments.cartpole_env import CartPoleEnv
+    from neural_control.dynamics.cartpole_dynamics import CartpoleDynamics
+    from neural_control.controllers.network_wrapper import CartpoleWrapper
+    net = torch.load('trained_models/cartpole/current_model/model_cartpole', weights_only=False)
+    net.eval()
+    out = {}
+    for i, p in enumerate(net.parameters()):
+        out[f"param_{i}"] = p.detach()
+    # (name, start state or None (= the reference's zero start), max_steps, thresh_div, burn_in)
+    runs = [("zero_start", None, 80, 0.21, 10), ("tilted", [0.3, 0.2, 0.12, -0.3], 80, 0.21, 10),
+            ("falls", [0.4, -1.232, 0.068, 1.425], 60, 0.21, 5), ("tight", [-0.3, 1.13, 0.088, -0.595], 60, 0.12, 50),
+            ("falls_at_once", [0.0, 0.5, 0.19, 0.9], 60, 0.21, 5)]
+    for name, start, steps, tdiv, burn in runs:
+        env = CartPoleEnv(CartpoleDynamics(), 0.05, thresh_div=tdiv)
+        ev = EC.Evaluator(CartpoleWrapper(net, horizon=10, action_dim=1), env)
+        if start is not None:
+            ev.initialize_straight = 0
+            env._reset_upright = lambda _e=env, _s=start: setattr(_e, "state", np.array(_s, dtype=np.float64))
+        log = []
+        orig = env._step
+
+        def logged(*a, _orig=orig, _log=log, **k):
+            r = _orig(*a, **k)
+            _log.append(np.array(r, dtype=np.float64).copy())
+            return r
+        env._step = logged
+        np.random.seed(0)
+        succ, vel = ev.evaluate_in_environment(nr_iters=1, max_steps=steps, render=False, burn_in_steps=burn,
+                                               return_success=1)
+        out[f"{name}_init"] = np.zeros(4) if start is None else np.array(start, dtype=np.float64)
+        out[f"{name}_cfg"] = np.array([steps, tdiv, burn], dtype=np.float64)
+        out[f"{name}_states"] = np.array(log)
+        out[f"{name}_success"] = np.asarray(succ)
+        out[f"{name}_vel"] = np.asarray(vel)
+        print("cartpole eval", name, "steps", len(log), "success", succ)
+    out["run_names"] = np.array([r[0] for r in runs])
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(args.out, "eval_cartpole.npz"), **npify(out))
+
+
 def make_learnt_golden(args):
     """learnt_dyn.npz: LearntDynamics.forward (neural_control/dynamics/quad_dynamics_trained.py) of the unmodified
     reference with seeded NON-zero parameters (the reference initialises the residual MLP with zeros, which leaves it
@@ -261,6 +310,7 @@ def main():
     ap.add_argument("--only-prep", action="store_true", help="only (re)generate prep_data.npz")
     ap.add_argument("--only-eval", action="store_true", help="only (re)generate eval_rand.npz")
     ap.add_argument("--only-wing-eval", action="store_true", help="only (re)generate eval_wing.npz")
+    ap.add_argument("--only-cartpole-eval", action="store_true", help="only (re)generate eval_cartpole.npz")
     ap.add_argument("--only-learnt", action="store_true", help="only (re)generate learnt_dyn.npz")
     args = ap.parse_args()
     import_reference(args.ref)
@@ -273,6 +323,9 @@ def main():
         return
     if args.only_wing_eval:
         make_wing_eval_golden(args)
+        return
+    if args.only_cartpole_eval:
+        make_cartpole_eval_golden(args)
         return
 
     import torch

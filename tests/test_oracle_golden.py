@@ -285,3 +285,39 @@ def test_learnt_wing_dynamics_forward_and_vjp_match_reference(tag):
                                                    [torch.zeros(64, 16), torch.zeros(64), torch.zeros(12, 64),
                                                     torch.zeros(12)], s.detach(), a.detach(), 0.05),
                                 O.wing_step(s.detach(), a.detach(), 0.05)) <= 1e-6
+
+
+CARTPOLE_EVAL_RUNS = ["zero_start", "tilted", "falls", "tight", "falls_at_once"]
+
+
+@pytest.mark.parametrize("name", CARTPOLE_EVAL_RUNS)
+def test_eval_cartpole_balance_matches_reference_evaluator(name):
+    """Evaluator.evaluate_in_environment (scripts/evaluate_cartpole.py:78-262) with CartpoleWrapper on the shipped
+    model_cartpole: the states env._step returned, the success count and the |x_dot| log"""
+    g = load_golden("eval_cartpole.npz")
+    assert [str(x) for x in g["run_names"]] == CARTPOLE_EVAL_RUNS
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    steps, tdiv, burn = g[f"{name}_cfg"]
+    out = O.eval_cartpole_balance(params, torch.tensor(g[f"{name}_init"], dtype=torch.float32)[None], int(steps), 0.05,
+                                  float(tdiv), int(burn))
+    want = g[f"{name}_states"]
+    taken = len(want)
+    assert int(out["n_steps"][0]) == taken
+    assert int(out["success"][0]) == int(g[f"{name}_success"][0])
+    assert np.abs(out["states"][0, :taken].numpy() - want).max() <= 1e-6 * max(np.abs(want).max(), 1.0)
+    assert abs(float(out["vel_sum"][0]) - g[f"{name}_vel"].sum()) <= 1e-5 * max(g[f"{name}_vel"].sum(), 1.0)
+    if taken - 1 > burn:
+        assert abs(float(out["mean_angle"][0]) - np.abs(want[int(burn) + 1:, 2]).mean()) <= 1e-6
+    else:
+        assert float(out["mean_angle"][0]) == 100.0
+
+
+def test_eval_cartpole_balance_is_batched_consistently():
+    g = load_golden("eval_cartpole.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    init = torch.tensor(np.stack([g[f"{n}_init"] for n in CARTPOLE_EVAL_RUNS]), dtype=torch.float32)
+    out = O.eval_cartpole_balance(params, init, 60, 0.05, 0.21, 5)
+    for k, name in enumerate(CARTPOLE_EVAL_RUNS):
+        one = O.eval_cartpole_balance(params, init[k:k + 1], 60, 0.05, 0.21, 5)
+        assert int(one["n_steps"][0]) == int(out["n_steps"][k])
+        assert float((one["states"][0] - out["states"][k]).abs().max()) <= 1e-5
