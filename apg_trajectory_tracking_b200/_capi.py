@@ -42,6 +42,9 @@ EXPORTS = {
                                               c_float_p, c_float_p, ctypes.c_float, ctypes.c_int, ctypes.c_float,
                                               ctypes.c_float, ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p,
                                               c_float_p, ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_void_p]),
+    "apg_eval_cartpole": (ctypes.c_int, [ctypes.POINTER(ApgConfig), c_float_p, c_float_p, ctypes.c_int, ctypes.c_float,
+                                         ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_void_p,
+                                         c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "apg_learnt_num_params": (ctypes.c_int, [ctypes.c_int]),
     "apg_learnt_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "apg_learnt_step": (ctypes.c_int, [ctypes.c_int] + [c_float_p] * 4 + [ctypes.c_float, ctypes.c_int, c_float_p,

@@ -576,4 +576,33 @@ __attribute__((visibility("default"))) int apg_eval_fly_to_points(const apg_conf
   return 0;
 }
 
+// Closed-loop balancing evaluation of the cartpole (eval_kernels.cu).
+__attribute__((visibility("default"))) int apg_eval_cartpole(const apg_config* cfg, const float* params, const float* init_states, int steps,
+                      float thresh_div, int burn_in_steps, void* workspace, float* states_out, float* actions_out,
+                      int* n_steps_out, float* angle_sum_out, float* angle_cnt_out, float* vel_sum_out, void* stream) {
+  int e = check_config(cfg);
+  if (e) return e;
+  if (cfg->net != NET_SIMPLE || cfg->system != SYS_CARTPOLE || cfg->mode != MODE_CONCURRENT) return APG_ERR_UNSUPPORTED;
+  if (cfg->state_feat != 4) return APG_ERR_BAD_CONFIG;
+  if (!params || !init_states || !workspace || steps < 1 || burn_in_steps < 0) return APG_ERR_BAD_CONFIG;
+  if (!aligned16(params) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APG_ERR_ALIGNMENT;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Plan p = make_plan(cfg, net_info(cfg));
+  char* w = static_cast<char*>(workspace);
+  float* wf = reinterpret_cast<float*>(w + p.o_wf);
+  float* wb = reinterpret_cast<float*>(w + p.o_wb);
+  const SimpleLayout y = simple_layout(cfg);
+  cudaError_t ce;
+  if ((ce = launch_pack(simple_pack_table(y), params, wf, wb, st))) return (int)ce;
+  PhysConsts pc;
+  memcpy(pc.v, cfg->phys, sizeof(float) * MAX_PHYS);
+  CartpoleEvalParams ev;
+  ev.steps = steps; ev.burn_in = burn_in_steps; ev.thresh_div = thresh_div;
+  if ((ce = launch_eval_cartpole(y, wf, init_states, cfg->n_drones, cfg->dt, pc, ev, states_out, actions_out,
+                                 n_steps_out, angle_sum_out, angle_cnt_out, vel_sum_out, p.grid, st)))
+    return (int)ce;
+  return 0;
+}
+
 }  // extern "C"

@@ -268,6 +268,120 @@ __global__ void __launch_bounds__(NT, 1) eval_wing_kernel(const HutterLayout y, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// cartpole: Evaluator.evaluate_in_environment (scripts/evaluate_cartpole.py:78-262) with CartpoleWrapper -- how long
+// the simple Net (4->32->64->64->32->h, tanh everywhere) keeps the pole upright.  Per step: policy on the state with
+// column 0 zeroed (first of the h predicted actions) -> CartPoleEnv._step -> upright test (per-drone logic in
+// eval_math.cuh, including the in-place zeroing of the environment's cart position).
+// ------------------------------------------------------------------------------------------------------------
+struct CartpoleEvalArgs {
+  const float* wf;            // packed forward weights (apg_pack_kernel, SimpleLayout)
+  const float* init_states;   // [N][4]
+  int N;
+  float dt;
+  PhysConsts pc;
+  CartpoleEvalParams ev;
+  float* states_out;          // optional [N][steps][4]  (states returned by _step)
+  float* actions_out;         // optional [N][steps]
+  int* n_steps_out;           // optional [N]
+  float* angle_sum_out;       // optional [N]  sum of |theta| for step index > burn_in
+  float* angle_cnt_out;       // optional [N]  number of terms in it
+  float* vel_sum_out;         // optional [N]  sum of |x_dot| over the steps taken
+};
+
+__global__ void __launch_bounds__(NT, 1) eval_cartpole_kernel(const SimpleLayout y, const CartpoleEvalArgs g) {
+  extern __shared__ __align__(128) float smem[];
+  using Sys = Cartpole<float>;
+  constexpr int S = Sys::S;
+  const int steps = g.ev.steps;
+  float* s_w = smem;
+  float* s_in = s_w + y.f_total;
+  float* s_a = s_in + pad4(TM * y.F0);               // activation arena [rows_total][TMP]
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_a + y.rows_total * TMP);
+  const Lane L;
+  const int tid = threadIdx.x;
+  const int ntiles = (g.N + TM - 1) / TM;
+  const int LAST = SIMPLE_NL - 1;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, y.f_total * 4);
+    bulk_g2s_chunked(s_w, g.wf, y.f_total * 4, bar_w);
+  }
+  mbar_wait(bar_w, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int valid = min(TM, g.N - tile * TM);
+    const size_t drone = (size_t)tile * TM + tid;
+    const bool mine = tid < valid;
+    CartpoleEvalDrone D;
+    {
+      float init[S];
+#pragma unroll
+      for (int j = 0; j < S; ++j) init[j] = mine ? g.init_states[drone * S + j] : 0.f;
+      cartpole_eval_init(D, init, mine ? 1 : 0);
+    }
+    for (int i = 0; i < steps; ++i) {
+      if (tid < TM) {
+        if (D.alive) cartpole_eval_before_policy(D, i);
+        s_in[tid * y.F0 + 0] = 0.f;                                      // simple_model.py:21
+#pragma unroll
+        for (int j = 1; j < S; ++j) s_in[tid * y.F0 + j] = D.alive ? D.s[j] : 0.f;
+      }
+      __syncthreads();
+      dense<SrcAoS, EPI_ACT>(L, SrcAoS{s_in, y.F0, 0}, y.din[0], s_w + y.f_w[0], y.ldf[0], s_w + y.f_b[0],
+                             y.ldf[0] / 4, s_a, y.row[0], 1, ACT_TANH);
+      __syncthreads();
+      for (int l = 1; l < SIMPLE_NL; ++l) {
+        dense<SrcT, EPI_ACT>(L, SrcT{s_a + y.row[l - 1] * TMP}, y.din[l], s_w + y.f_w[l], y.ldf[l], s_w + y.f_b[l],
+                             y.ldf[l] / 4, s_a, y.row[l], 1, ACT_TANH);
+        __syncthreads();
+      }
+      if (D.alive) {
+        float a[1], nxt[S];
+        a[0] = s_a[y.row[LAST] * TMP + tid];                              // first of the h predicted actions
+        Sys::step(D.s, a, g.dt, g.pc.v, nxt);
+        cartpole_eval_post_step(D, nxt, i, g.ev);
+        if (g.states_out) {
+#pragma unroll
+          for (int j = 0; j < S; ++j) g.states_out[(drone * steps + i) * S + j] = nxt[j];
+        }
+        if (g.actions_out) g.actions_out[drone * steps + i] = a[0];
+      }
+      // barrier before the next step overwrites s_in / the arena; also the tile-wide early exit
+      if (!__syncthreads_or(D.alive)) break;
+    }
+    if (mine) {
+      if (g.n_steps_out) g.n_steps_out[drone] = D.nsteps;
+      if (g.angle_sum_out) g.angle_sum_out[drone] = D.ang_sum;
+      if (g.angle_cnt_out) g.angle_cnt_out[drone] = D.ang_cnt;
+      if (g.vel_sum_out) g.vel_sum_out[drone] = D.vel_sum;
+    }
+    __syncthreads();
+  }
+}
+
+size_t eval_cartpole_smem_bytes(const SimpleLayout& y) {
+  return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + y.rows_total * TMP) + 16;
+}
+
+cudaError_t launch_eval_cartpole(const SimpleLayout& y, const float* wf, const float* init_states, int n, float dt,
+                                 const PhysConsts& pc, const CartpoleEvalParams& ev, float* states_out,
+                                 float* actions_out, int* n_steps_out, float* angle_sum_out, float* angle_cnt_out,
+                                 float* vel_sum_out, int grid, cudaStream_t st) {
+  CartpoleEvalArgs a;
+  a.wf = wf; a.init_states = init_states; a.N = n; a.dt = dt; a.pc = pc; a.ev = ev;
+  a.states_out = states_out; a.actions_out = actions_out; a.n_steps_out = n_steps_out;
+  a.angle_sum_out = angle_sum_out; a.angle_cnt_out = angle_cnt_out; a.vel_sum_out = vel_sum_out;
+  const size_t smem = eval_cartpole_smem_bytes(y);
+  cudaError_t e = cudaFuncSetAttribute(eval_cartpole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  eval_cartpole_kernel<<<grid, NT, smem, st>>>(y, a);
+  return cudaGetLastError();
+}
+
 size_t eval_wing_smem_bytes(const HutterLayout& y) {
   return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP) + 16;
 }

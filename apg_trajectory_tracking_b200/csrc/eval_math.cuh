@@ -146,4 +146,45 @@ APG_HD void wing_eval_finish(WingEvalDrone& D, const WingEvalParams& e) {
   if (D.alive && D.nsteps == e.steps) { D.dt_sum += e.thresh_div; D.dt_cnt += 1.f; }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cartpole: Evaluator.evaluate_in_environment (scripts/evaluate_cartpole.py:78-262) with CartpoleWrapper
+// (neural_control/controllers/network_wrapper.py:101-113), CartPoleEnv._step / is_upright
+// (neural_control/environments/cartpole_env.py).  The policy input aliases the environment's float32 state and the
+// network zeroes column 0 in place (models/simple_model.py:21), so from the second policy call on the cart position
+// the ENVIRONMENT integrates starts from 0 every step; the first step still integrates from the start position.
+// ---------------------------------------------------------------------------------------------------------
+struct CartpoleEvalParams {
+  int steps;            // max_steps
+  int burn_in;          // |theta| enters the mean only for step index > burn_in
+  float thresh_div;     // upright: -thresh_div < theta < thresh_div
+};
+
+struct CartpoleEvalDrone {
+  float s[4];
+  int alive, nsteps;
+  float ang_sum, ang_cnt, vel_sum;
+};
+
+APG_HD void cartpole_eval_init(CartpoleEvalDrone& D, const float* init_state, int alive) {
+  for (int j = 0; j < 4; ++j) D.s[j] = init_state[j];
+  D.alive = alive; D.nsteps = 0; D.ang_sum = 0.f; D.ang_cnt = 0.f; D.vel_sum = 0.f;
+}
+
+// what the policy call of step i leaves in the environment state (the net's own input has column 0 zeroed anyway)
+APG_HD void cartpole_eval_before_policy(CartpoleEvalDrone& D, int i) {
+  if (i > 0) D.s[0] = 0.f;
+}
+
+// after the dynamics returned nxt (theta wrapped into (-pi, pi] by _step): bookkeeping and the upright test
+APG_HD void cartpole_eval_post_step(CartpoleEvalDrone& D, float* nxt, int i, const CartpoleEvalParams& e) {
+  const float PI_F = 3.14159265358979323846f;
+  if (nxt[2] > PI_F) nxt[2] -= 2.f * PI_F;
+  else if (nxt[2] <= -PI_F) nxt[2] += 2.f * PI_F;
+  for (int j = 0; j < 4; ++j) D.s[j] = nxt[j];
+  ++D.nsteps;
+  D.vel_sum += nxt[1] < 0.f ? -nxt[1] : nxt[1];
+  if (i > e.burn_in) { D.ang_sum += nxt[2] < 0.f ? -nxt[2] : nxt[2]; D.ang_cnt += 1.f; }
+  if (!(nxt[2] > -e.thresh_div && nxt[2] < e.thresh_div)) D.alive = 0;
+}
+
 }  // namespace apg

@@ -60,6 +60,11 @@ cudaError_t launch_eval_wing(const HutterLayout& y, const float* wf, const float
                              const WingEvalParams& ev, float* states_out, float* div_out, float* actions_out,
                              int* n_steps_out, float* dt_sum_out, float* dt_cnt_out, int grid, cudaStream_t st);
 
+cudaError_t launch_eval_cartpole(const SimpleLayout& y, const float* wf, const float* init_states, int n, float dt,
+                                 const PhysConsts& pc, const CartpoleEvalParams& ev, float* states_out,
+                                 float* actions_out, int* n_steps_out, float* angle_sum_out, float* angle_cnt_out,
+                                 float* vel_sum_out, int grid, cudaStream_t st);
+
 // learnt residual dynamics, quadrotor / fixed wing (learnt_kernels.cu)
 int learnt_num_params(int system);
 int learnt_grid(int n, int sms);

@@ -131,6 +131,67 @@ class WingTargetEvaluator:
         return out
 
 
+class CartpoleBalanceEvaluator:
+    """Cartpole: ``Evaluator.evaluate_in_environment`` (scripts/evaluate_cartpole.py:78-262) for N carts at once.
+    ``spec``: ``RolloutSpec.cartpole_concurrent(h, dt_env, modified_params)`` of the EVALUATION environment."""
+
+    def __init__(self, spec: R.RolloutSpec, n_drones: int, device=None):
+        if not torch.cuda.is_available():
+            raise _capi.ApgError("no CUDA device: the evaluation rollout only runs on the GPU")
+        if spec.system != "cartpole" or spec.net != "simple":
+            raise _capi.ApgError("balance evaluation is implemented for the cartpole simple net")
+        self.spec, self.n = spec, int(n_drones)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lib = _capi.lib()
+        with torch.cuda.device(self.device):
+            self.cfg = spec.config(self.n)
+            ws = self.lib.apg_workspace_bytes(ctypes.byref(self.cfg))
+            if ws == 0:
+                raise _capi.ApgError("bad rollout spec for the evaluation rollout")
+            self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)
+            off = (-self.workspace.data_ptr()) % 256
+            self._ws_ptr = ctypes.c_void_p(self.workspace.data_ptr() + off)
+
+    def balance(self, params_flat, init_states=None, steps=250, thresh_div=0.21, burn_in_steps=50,
+                want=("states", "actions")):
+        """init_states (N,4) or None (the reference's start: everything zero, evaluate_cartpole.py:100-113 with
+        ``center_at_x``).  Returns dict(states (N,steps,4) as returned by ``_step``, actions (N,steps), n_steps (N,)
+        int32, success (N,) = n_steps - 1 (the reference's step index at the end of the run), mean_angle (N,) = mean
+        |theta| after the burn-in (100 when there is none, :230), vel_sum (N,))."""
+        _require_cuda(params_flat, init_states)
+        n, dev = self.n, self.device
+        if init_states is None:
+            init_states = torch.zeros(n, 4, device=dev)
+        init_states = init_states.contiguous().float()
+        if tuple(init_states.shape) != (n, 4):
+            raise ValueError(f"init_states must be (N,4) with N = {n}")
+        out = {"n_steps": torch.zeros(n, dtype=torch.int32, device=dev)}
+        ang_sum, ang_cnt = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        out["vel_sum"] = torch.zeros(n, device=dev)
+        if "states" in want:
+            out["states"] = torch.zeros(n, steps, 4, device=dev)
+        if "actions" in want:
+            out["actions"] = torch.zeros(n, steps, device=dev)
+        opt = lambda k: None if k not in out else _p(out[k])          # noqa: E731
+        with torch.cuda.device(dev):
+            _capi.check(self.lib.apg_eval_cartpole(
+                ctypes.byref(self.cfg), _p(params_flat), _p(init_states), int(steps), ctypes.c_float(thresh_div),
+                int(burn_in_steps), self._ws_ptr, opt("states"), opt("actions"), _p(out["n_steps"]), _p(ang_sum),
+                _p(ang_cnt), _p(out["vel_sum"]), _stream(init_states)))
+        out["success"] = out["n_steps"] - 1
+        out["mean_angle"] = torch.where(ang_cnt > 0, ang_sum / ang_cnt.clamp(min=1), torch.full_like(ang_sum, 100.0))
+        return out
+
+
+def cartpole_eval_statistics(n_steps, vel_sum):
+    """``evaluate_in_environment``'s result dict (evaluate_cartpole.py:233-238) over the N runs of one ``balance``
+    call: mean_vel (mean |x_dot| over ALL steps of all runs), mean_stable, std_stable (of ``success``)"""
+    ns = n_steps.detach().cpu().double().numpy()
+    succ = ns - 1
+    return {"mean_vel": float(vel_sum.detach().cpu().double().sum() / max(ns.sum(), 1.0)),
+            "mean_stable": float(succ.mean()), "std_stable": float(succ.std())}
+
+
 def wing_eval_statistics(div_target_sum, div_target_cnt):
     """``FixedWingEvaluator.run_eval`` (evaluate_fixed_wing.py:157-178): mean and std over the flights of each
     flight's mean target error"""

@@ -141,6 +141,20 @@ int apg_eval_fly_to_points(const apg_config* cfg, const float* params, const flo
                            float* states_out, float* div_linear_out, float* actions_out, int* n_steps_out,
                            float* div_target_sum_out, float* div_target_cnt_out, void* stream);
 
+/* Cartpole: Evaluator.evaluate_in_environment (scripts/evaluate_cartpole.py:78-262) with CartpoleWrapper.predict_actions
+ * (controllers/network_wrapper.py:101-113) and CartPoleEnv._step / is_upright (environments/cartpole_env.py) for
+ * cfg->n_drones carts in one launch: how many steps the policy keeps |theta| < thresh_div.  cfg: cartpole, simple net,
+ * concurrent (out_dim h: the first predicted action is applied); cfg->dt / cfg->phys: the evaluation environment.
+ * Like the reference, the environment's cart position restarts from 0 at every step but the first (the network
+ * zeroes column 0 of its input in place and the input aliases the environment state).  init_states [N][4].
+ * Outputs (device, optional, caller zero-initialised): states_out [N][steps][4] (as returned by _step), actions_out
+ * [N][steps], n_steps_out [N] (int; the reference's `success` = n_steps - 1), angle_sum_out / angle_cnt_out [N]
+ * (sum and count of |theta| for step index > burn_in_steps), vel_sum_out [N] (sum of |x_dot| over the steps).
+ * workspace: apg_workspace_bytes(cfg). */
+int apg_eval_cartpole(const apg_config* cfg, const float* params, const float* init_states, int steps,
+                      float thresh_div, int burn_in_steps, void* workspace, float* states_out, float* actions_out,
+                      int* n_steps_out, float* angle_sum_out, float* angle_cnt_out, float* vel_sum_out, void* stream);
+
 /* ---- learnt residual dynamics, system = APG_SYS_QUAD or APG_SYS_WING:
  *   quad  LearntDynamics.forward (neural_control/dynamics/quad_dynamics_trained.py:10-69) =
  *         simulate_quadrotor(linear_at @ action, state, dt) + linear_state_2(relu(linear_state_1([state, at])));

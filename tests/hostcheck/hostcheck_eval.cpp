@@ -153,3 +153,48 @@ extern "C" void hc_eval_wing(const float* params, int h, const float* targets, i
     n_steps_out[d] = D.nsteps; dts_out[d] = D.dt_sum; dtc_out[d] = D.dt_cnt;
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// cartpole: mirrors the per-thread code of eval_cartpole_kernel (policy: scalar models/simple_model.py Net)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+float simple_first_action(const float* p, int h, const float* s4) {
+  const int dims[6] = {4, 32, 64, 64, 32, h};
+  float x[64], yv[64];
+  x[0] = 0.f;                                         // simple_model.py:21
+  for (int j = 1; j < 4; ++j) x[j] = s4[j];
+  for (int l = 0; l < 5; ++l) {
+    const float* w = p;  p += dims[l + 1] * dims[l];
+    const float* b = p;  p += dims[l + 1];
+    for (int j = 0; j < dims[l + 1]; ++j) {
+      float s = b[j];
+      for (int k = 0; k < dims[l]; ++k) s += w[j * dims[l] + k] * x[k];
+      yv[j] = tanhf(s);
+    }
+    for (int j = 0; j < dims[l + 1]; ++j) x[j] = yv[j];
+  }
+  return x[0];
+}
+}  // namespace
+
+extern "C" void hc_eval_cartpole(const float* params, int h, const float* init_states, int n, float dt,
+                                 const float* pc, int steps, float thresh_div, int burn_in, float* states_out,
+                                 float* actions_out, int* n_steps_out, float* ang_sum_out, float* ang_cnt_out,
+                                 float* vel_sum_out) {
+  CartpoleEvalParams e;
+  e.steps = steps; e.burn_in = burn_in; e.thresh_div = thresh_div;
+  for (int d = 0; d < n; ++d) {
+    CartpoleEvalDrone D;
+    cartpole_eval_init(D, init_states + d * 4, 1);
+    for (int i = 0; i < steps && D.alive; ++i) {
+      cartpole_eval_before_policy(D, i);
+      float a[1], nxt[4];
+      a[0] = simple_first_action(params, h, D.s);
+      Cartpole<float>::step(D.s, a, dt, pc, nxt);
+      cartpole_eval_post_step(D, nxt, i, e);
+      for (int j = 0; j < 4; ++j) states_out[((size_t)d * steps + i) * 4 + j] = nxt[j];
+      actions_out[(size_t)d * steps + i] = a[0];
+    }
+    n_steps_out[d] = D.nsteps; ang_sum_out[d] = D.ang_sum; ang_cnt_out[d] = D.ang_cnt; vel_sum_out[d] = D.vel_sum;
+  }
+}

@@ -120,3 +120,58 @@ def test_wing_kernel_logic_matches_reference_evaluator(he, name):
     assert np.abs(act[0, :taken] - traj[:, 12:]).max() <= 5e-5
     assert np.abs(div[0, :taken] - dl).max() <= 5e-5 * max(dl.max(), 1.0)
     assert int(dtc[0]) == len(dtg) and abs(float(dts[0]) - dtg.sum()) <= 2e-4 * max(dtg.sum(), 1.0)
+
+
+# ---- cartpole: Evaluator.evaluate_in_environment (tests/golden/eval_cartpole.npz) -------------------------------------
+CARTPOLE_EVAL_RUNS = ["zero_start", "tilted", "falls", "tight", "falls_at_once"]
+
+
+def _run_cartpole(he, params, init, steps, dt, tdiv, burn):
+    flat = np.ascontiguousarray(torch.cat([p.reshape(-1) for p in params]).numpy(), dtype=np.float32)
+    init = np.ascontiguousarray(init, dtype=np.float32)
+    n = init.shape[0]
+    states, act = np.zeros((n, steps, 4), np.float32), np.zeros((n, steps), np.float32)
+    nst = np.zeros(n, np.int32)
+    asum, acnt, vsum = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    pc = P.PHYS["cartpole"]()
+    he.hc_eval_cartpole(_p(flat), params[-1].shape[0], _p(init), n, ctypes.c_float(dt), _p(pc), steps,
+                        ctypes.c_float(tdiv), int(burn), _p(states), _p(act), _p(nst), _p(asum), _p(acnt), _p(vsum))
+    return states, act, nst, asum, acnt, vsum
+
+
+@pytest.mark.parametrize("name", CARTPOLE_EVAL_RUNS)
+def test_cartpole_kernel_logic_matches_reference_evaluator(he, name):
+    g = load_golden("eval_cartpole.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    steps, tdiv, burn = g[f"{name}_cfg"]
+    states, act, nst, asum, acnt, vsum = _run_cartpole(he, params, g[f"{name}_init"][None], int(steps), 0.05, tdiv,
+                                                       int(burn))
+    want = g[f"{name}_states"]
+    taken = len(want)
+    assert int(nst[0]) == taken and int(nst[0]) - 1 == int(g[f"{name}_success"][0])
+    assert np.abs(states[0, :taken] - want).max() <= 2e-5 * max(np.abs(want).max(), 1.0)
+    assert np.abs(states[0, taken:]).sum() == 0
+    assert abs(float(vsum[0]) - g[f"{name}_vel"].sum()) <= 1e-4 * max(g[f"{name}_vel"].sum(), 1.0)
+    late = np.abs(want[int(burn) + 1:, 2])
+    assert int(acnt[0]) == len(late)
+    assert abs(float(asum[0]) - late.sum()) <= 1e-4 * max(late.sum(), 1.0)
+    # from the second step on the cart position the environment integrates starts from 0 (x' = 0 + x_dot * dt)
+    if taken > 2:
+        assert np.abs(want[2:, 0] - want[1:-1, 1] * 0.05).max() <= 1e-6
+
+
+def test_cartpole_kernel_logic_matches_oracle_batched(he):
+    g = load_golden("eval_cartpole.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    rng = np.random.default_rng(1)
+    init = np.concatenate([np.stack([g[f"{n}_init"] for n in CARTPOLE_EVAL_RUNS]),
+                           rng.uniform(-1, 1, (27, 4)) * np.array([0.5, 1.5, 0.12, 1.8])]).astype(np.float32)
+    states, act, nst, asum, acnt, vsum = _run_cartpole(he, params, init, 60, 0.05, 0.21, 5)
+    out = O.eval_cartpole_balance(params, torch.tensor(init), 60, 0.05, 0.21, 5)
+    assert np.array_equal(nst, out["n_steps"].numpy())
+    assert 1 < len(set(nst.tolist()))                                   # runs of different length in one batch
+    assert np.abs(states - out["states"].numpy()).max() <= 5e-5
+    assert np.abs(act - out["actions"].numpy()).max() <= 5e-5
+    assert np.abs(vsum - out["vel_sum"].numpy()).max() <= 1e-3
+    mean_angle = np.where(acnt > 0, asum / np.maximum(acnt, 1), 100.0)
+    assert np.abs(mean_angle - out["mean_angle"].numpy()).max() <= 1e-4

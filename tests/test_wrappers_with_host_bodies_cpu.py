@@ -110,6 +110,19 @@ class _HostLib:
                              self._vp(_addr(n_steps)), self._vp(_addr(dts)), self._vp(_addr(dtc)))
         return 0
 
+    def apg_eval_cartpole(self, cfg, params, init, steps, tdiv, burn, ws, states, actions, n_steps, asum, acnt, vsum,
+                          stream):
+        c = cfg._obj
+        n = c.n_drones
+        tmp = {"states": np.zeros((n, steps, 4), np.float32), "actions": np.zeros((n, steps), np.float32)}
+        self.keep.append(tmp)
+        ptr = lambda given, k: self._vp(_addr(given) if given is not None else tmp[k].ctypes.data)   # noqa: E731
+        phys = (ctypes.c_float * 48)(*c.phys)
+        self.ev.hc_eval_cartpole(self._vp(_addr(params)), c.horizon, self._vp(_addr(init)), n, ctypes.c_float(c.dt),
+                                 phys, steps, ctypes.c_float(_f(tdiv)), int(burn), ptr(states, "states"),
+                                 ptr(actions, "actions"), *[self._vp(_addr(x)) for x in (n_steps, asum, acnt, vsum)])
+        return 0
+
     def apg_learnt_step(self, system, params, phys, state, action, dt, n, out, stream):
         if system == 0:
             self.ln.hc_learnt_fwd_f32(*[self._vp(_addr(x)) for x in (params, phys, state, action)],
@@ -271,3 +284,29 @@ def test_learnt_wing_dynamics_wrapper(hostlib):
     for i, (name, p) in enumerate(d.named_parameters()):
         want = torch.tensor(g[f"wb_gparam_{i}"])
         assert float((p.grad - want).abs().max()) <= 2e-4 * max(float(want.abs().max()), 1e-2), name
+
+
+def test_cartpole_balance_evaluator_wrapper(hostlib):
+    g = load_golden("eval_cartpole.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    flat = R.flatten_params(params)
+    for name in ("tilted", "falls"):
+        steps, tdiv, burn = g[f"{name}_cfg"]
+        ev = EV.CartpoleBalanceEvaluator(R.RolloutSpec.cartpole_concurrent(10, 0.05), 1, "cpu")
+        out = ev.balance(flat, torch.tensor(g[f"{name}_init"], dtype=torch.float32)[None], steps=int(steps),
+                         thresh_div=float(tdiv), burn_in_steps=int(burn))
+        want = g[f"{name}_states"]
+        taken = len(want)
+        assert int(out["n_steps"][0]) == taken and int(out["success"][0]) == int(g[f"{name}_success"][0])
+        assert np.abs(out["states"][0, :taken].numpy() - want).max() <= 2e-5 * max(np.abs(want).max(), 1.0)
+        late = np.abs(want[int(burn) + 1:, 2])
+        assert abs(float(out["mean_angle"][0]) - (late.mean() if len(late) else 100.0)) <= 1e-5
+        st = EV.cartpole_eval_statistics(out["n_steps"], out["vel_sum"])
+        assert abs(st["mean_vel"] - g[f"{name}_vel"].mean()) <= 1e-4 * max(g[f"{name}_vel"].mean(), 1.0)
+        assert st["mean_stable"] == taken - 1 and st["std_stable"] == 0.0
+    # the reference's own start (all zeros) for a batch, slim outputs
+    ev4 = EV.CartpoleBalanceEvaluator(R.RolloutSpec.cartpole_concurrent(10, 0.05), 4, "cpu")
+    slim = ev4.balance(flat, steps=30, want=())
+    assert set(slim) == {"n_steps", "vel_sum", "success", "mean_angle"} and slim["n_steps"].tolist() == [30] * 4
+    with pytest.raises(ValueError):
+        ev4.balance(flat, torch.zeros(3, 4))

@@ -518,6 +518,51 @@ def test_wing_fly_to_points_batched_vs_oracle():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# cartpole balance evaluation (apg_eval_cartpole): Evaluator.evaluate_in_environment for N carts in one launch
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["zero_start", "tilted", "falls", "tight", "falls_at_once"])
+def test_cartpole_balance_matches_reference_evaluator(name):
+    EV, R, O, _ = _eval_mods()
+    g = load_golden("eval_cartpole.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]                  # the shipped model_cartpole
+    steps, tdiv, burn = g[f"{name}_cfg"]
+    ev = EV.CartpoleBalanceEvaluator(R.RolloutSpec.cartpole_concurrent(10, 0.05), 1, "cuda:0")
+    out = ev.balance(R.flatten_params(params).cuda(), torch.tensor(g[f"{name}_init"], dtype=torch.float32)[None].cuda(),
+                     steps=int(steps), thresh_div=float(tdiv), burn_in_steps=int(burn))
+    want = g[f"{name}_states"]
+    taken = len(want)
+    assert int(out["n_steps"][0]) == taken and int(out["success"][0]) == int(g[f"{name}_success"][0])
+    # closed loop over up to 80 steps: fp32 (3xTF32 policy) vs the reference's fp32 policy / fp64 dynamics
+    assert np.abs(out["states"][0, :taken].cpu().numpy() - want).max() <= 2e-4 * max(np.abs(want).max(), 1.0)
+    assert float(out["states"][0, taken:].abs().sum()) == 0.0
+    assert abs(float(out["vel_sum"][0]) - g[f"{name}_vel"].sum()) <= 1e-3 * max(g[f"{name}_vel"].sum(), 1.0)
+    late = np.abs(want[int(burn) + 1:, 2])
+    assert abs(float(out["mean_angle"][0]) - (late.mean() if len(late) else 100.0)) <= 1e-4
+
+
+def test_cartpole_balance_batched_vs_oracle():
+    """partial tiles and several tiles per CTA, runs of different length in one batch"""
+    EV, R, O, _ = _eval_mods()
+    g = load_golden("eval_cartpole.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    n, steps = 20000, 60
+    gen = torch.Generator().manual_seed(5)
+    init = (torch.rand(n, 4, generator=gen) * 2 - 1) * torch.tensor([0.5, 1.5, 0.12, 1.8])
+    want = O.eval_cartpole_balance(params, init, steps, 0.05, 0.21, 5)
+    ev = EV.CartpoleBalanceEvaluator(R.RolloutSpec.cartpole_concurrent(10, 0.05), n, "cuda:0")
+    out = ev.balance(R.flatten_params(params).cuda(), init.cuda(), steps=steps, thresh_div=0.21, burn_in_steps=5)
+    same = out["n_steps"].cpu() == want["n_steps"].to(torch.int32)
+    assert float(same.float().mean()) >= 0.995              # a threshold within rounding can flip a decision
+    assert 1 < len(set(want["n_steps"].tolist()))
+    d = (out["states"].cpu() - want["states"]).abs().amax(dim=(1, 2))
+    assert float((d[same] <= 1e-3).float().mean()) >= 0.995
+    assert float((out["states"].cpu()[:, :3] - want["states"][:, :3]).abs().max()) <= 1e-4
+    assert float((out["mean_angle"].cpu() - want["mean_angle"])[same].abs().max()) <= 1e-3
+    st = EV.cartpole_eval_statistics(out["n_steps"], out["vel_sum"])
+    assert abs(st["mean_stable"] - float(want["success"].double().mean())) <= 0.05
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # optional split adjoint (APG_TC_DW=1): mma.sync dX chain + dZ stash (hutter_adj_dx_kernel), then the weight gradient
 # as a streaming tcgen05 GEMM over the drone axis (adj_dw_tc_kernel) -- same gradient as the default adjoint
 # ---------------------------------------------------------------------------------------------------------------
