@@ -494,7 +494,10 @@ def main():
     # ---- end-to-end from RAW host samples (input side on the device, chunked H2D overlapped with the kernels).
     #      Runs last and guarded: whatever happens here, the line below still carries the measurements above.
     e2e_raw = None
-    if not args.no_raw_e2e:
+    if world > 1 and os.environ.get("APG_BENCH_RAW_E2E_MULTI") != "1":
+        # every step of this arm contains collectives; until it has run once on a multi-GPU box it stays opt-in there
+        e2e_raw = {"ok": False, "skipped": "raw-sample e2e arm runs at N=1 (APG_BENCH_RAW_E2E_MULTI=1 enables it at N>1)"}
+    elif not args.no_raw_e2e:
         try:
             e2e_raw = measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier)
         except Exception as ex:                                   # noqa: BLE001 - reported in the JSON line

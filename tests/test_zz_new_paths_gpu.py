@@ -7,6 +7,7 @@ Tolerances (fp32): subtraction-only outputs bit-exact; outputs that go through s
 train steps from raw host samples vs the same steps from prepared device tensors: loss 1e-5 relative, gradient L2
 1e-4 relative (chunk-wise summation order + last-ulp feature differences)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -615,6 +616,14 @@ def _check_split_adjoint(n, flags):
 SPLIT_SIZES = [64, 1, 65, 300, 1000, 9600, 148 * 64 * 3 + 5]
 
 
+# The tcgen05 / TMEM kernels are compile-verified and host-emulated only (no GPU minutes were left when they were
+# written): their tests are opt-in until the first hardware run (tools/gpu_first_call.sh sets APG_TEST_TC=1), so a
+# first-run problem in an OPTIONAL path (product default: off) cannot stop `pytest -m gpu -x` of the verified paths.
+needs_tc_optin = pytest.mark.skipif(os.environ.get("APG_TEST_TC") != "1",
+                                    reason="optional tcgen05 paths: set APG_TEST_TC=1 (first hardware run pending)")
+
+
+@needs_tc_optin
 @pytest.mark.parametrize("n", SPLIT_SIZES)
 def test_tc1_split_adjoint_streaming_dw_gemm(n):
     """the most basic tcgen05 use first (SS MMAs, K-major unswizzled operands, M = 128): APG_TC_DW alone"""
@@ -625,6 +634,7 @@ def test_tc1_split_adjoint_streaming_dw_gemm(n):
 # optional tcgen05 / TMEM forward (csrc/hutter_tc_kernels.cu, APG_TC_FWD=1) vs the default forward kernel:
 # same loss / actions / states, and the same gradient when the unchanged adjoint kernel consumes its stash
 # ---------------------------------------------------------------------------------------------------------------
+@needs_tc_optin
 @pytest.mark.parametrize("n", [128, 1, 63, 300, 1000, 9600, 148 * 128 * 3 + 77])
 def test_tc2_forward_matches_default_forward(n):
     import os
@@ -664,6 +674,7 @@ def test_tc2_forward_matches_default_forward(n):
     assert ok, str(diag)
 
 
+@needs_tc_optin
 @pytest.mark.parametrize("n", SPLIT_SIZES)
 @pytest.mark.parametrize("flags", [("APG_TC_DW", "APG_TC_FWD"), ("APG_TC_DW", "APG_TC_DX"),
                                    ("APG_TC_DW", "APG_TC_DX", "APG_TC_FWD")])

@@ -12,7 +12,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 # 1. the previously verified parity suite (must stay green), then the new input-side / evaluation / learnt tests
 timeout 900 python -m pytest tests -q -m gpu -x --deselect tests/test_zz_new_paths_gpu.py > "$out/pytest_verified.log" 2>&1
 echo "exit=$?" >> "$out/pytest_verified.log"
-timeout 600 python -m pytest tests/test_zz_new_paths_gpu.py -q -m gpu > "$out/pytest_new.log" 2>&1
+APG_TEST_TC=1 timeout 600 python -m pytest tests/test_zz_new_paths_gpu.py -q -m gpu > "$out/pytest_new.log" 2>&1
 echo "exit=$?" >> "$out/pytest_new.log"
 
 # 2. bench, default workload (raw-sample e2e arm included), then the other workloads without the CPU baseline
