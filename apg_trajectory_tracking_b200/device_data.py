@@ -19,7 +19,10 @@ from . import _capi, prepare as PR
 class DeviceQuadDataset:
     """raw quadrotor samples on the GPU: ``states`` (N,12), ``ref_states`` (N,L,9) rows [pos, euler, vel]"""
 
-    def __init__(self, states, ref_states, device=None):
+    def __init__(self, states, ref_states, device=None, num_self_play=0):
+        """``num_self_play``: the last ``num_self_play`` rows are the ring of self-play slots ``add_self_play``
+        overwrites (``DroneDataset``: ``int(self_play * num_sampled_states)`` rows after the sampled ones,
+        dataset.py:40-58); until then they hold ordinary samples."""
         if not torch.cuda.is_available():
             raise _capi.ApgError("DeviceQuadDataset needs a CUDA device")
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -29,9 +32,36 @@ class DeviceQuadDataset:
                 self.ref_states.shape[2] != 9:
             raise ValueError("expected states (N,12) and ref_states (N,L,9)")
         self.device = dev
+        if not 0 <= int(num_self_play) < self.states.shape[0]:
+            raise ValueError("num_self_play must leave at least one sampled row")
+        self.num_self_play = int(num_self_play)
+        self.num_sampled_states = self.states.shape[0] - self.num_self_play
+        self.eval_counter = 0
+
+    def get_eval_index(self):
+        """slot the next self-play sample goes to (``DroneDataset.get_eval_index``, dataset.py:78-85)"""
+        if self.num_self_play > 0:
+            return self.eval_counter % self.num_self_play + self.num_sampled_states
+        return None
+
+    def add_self_play(self, states, ref_states):
+        """write M raw samples (``evaluate.selfplay_samples``) into the ring of self-play slots, one after the other
+        like M calls of ``get_and_add_eval_data(..., add_to_dataset=True)`` (dataset.py:103-119)"""
+        m = states.shape[0]
+        if self.num_self_play == 0 or m == 0:
+            return
+        if ref_states.shape[1] < self.ref_states.shape[1] or ref_states.shape[0] != m:
+            raise ValueError("self-play reference rows do not fit the dataset's")
+        keep = min(m, self.num_self_play)                            # older ones would be overwritten anyway
+        j = torch.arange(m - keep, m, device=self.device)
+        slots = (self.eval_counter + j) % self.num_self_play + self.num_sampled_states
+        self.states.index_copy_(0, slots, states[m - keep:].to(self.device, torch.float32))
+        self.ref_states.index_copy_(0, slots, ref_states[m - keep:, :self.ref_states.shape[1]]
+                                    .to(self.device, torch.float32))
+        self.eval_counter += m
 
     @classmethod
-    def from_trajectory(cls, traj, ref_length, sample_freq=None, device=None):
+    def from_trajectory(cls, traj, ref_length, sample_freq=None, device=None, num_self_play=0):
         """samples cut from one trajectory table (T, W>=9) like full_state_training_data: every ``sample_freq``-th row
         is a drone state, the following ``ref_length`` rows its reference"""
         traj = torch.as_tensor(traj)
@@ -40,10 +70,10 @@ class DeviceQuadDataset:
         sample_freq = sample_freq or 2 * ref_length
         n = len(range(0, traj.shape[0] - (ref_length + 1), sample_freq))
         states, refs = PR.sample_windows(traj, n, ref_length, sample_freq)
-        return cls(states, refs, dev)
+        return cls(states, refs, dev, num_self_play)
 
     @classmethod
-    def from_polynomials(cls, n, ref_length, dt, seed=0, device=None):
+    def from_polynomials(cls, n, ref_length, dt, seed=0, device=None, num_self_play=0):
         """the bench's synthetic samples: degree-5 polynomial references, drone near the start of its reference"""
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         g = torch.Generator(device=dev).manual_seed(seed)
@@ -55,7 +85,7 @@ class DeviceQuadDataset:
         states = torch.zeros(n, 12, device=dev)
         states[:, 3:6] = torch.rand(n, 3, device=dev, generator=g) * 0.4 - 0.2
         states[:, 6:9] = c[:, :, 1] + 0.3 * torch.randn(n, 3, device=dev, generator=g)
-        return cls(states, refs, dev)
+        return cls(states, refs, dev, num_self_play)
 
     def __len__(self):
         return self.states.shape[0]

@@ -71,6 +71,55 @@ class TableEvaluator:
         return out
 
 
+def selfplay_samples(out, tables, table_index=None, horizon=10, take_every_x=1000, thresh_div=1.0, thresh_stable=1.0,
+                     test_time=0, action_counter=0):
+    """The self-play feed of the evaluation: the raw (state, reference rows) pairs ``NetworkWrapper.predict_actions``
+    hands to ``DroneDataset.get_and_add_eval_data(..., add_to_dataset=True)`` (controllers/network_wrapper.py:42-52,
+    dataset.py:98-119) when the N runs of one ``TableEvaluator.follow`` call are counted one after the other like the
+    reference's sequential runs: policy call number c (1-based, continuing from ``action_counter``) is kept when
+    ``c % take_every_x == 0``.
+
+    ``out``: the dict ``follow`` returned (needs "states" and "div"); tables / table_index / thresholds / test_time
+    as passed to ``follow``.  The state a policy call saw is the recorded state, or - after a step that diverged or
+    was unstable with ``test_time == 0`` - the reference state the drone was reset to (``[table[ci], 0, 0, 0]``,
+    random_traj.py:89-92); its reference rows are ``Random.get_ref_traj`` at that step.  Pure index arithmetic and
+    gathers on the tensors' device.  Returns (states (M,12), ref_states (M,horizon,9), action counter afterwards)."""
+    states, div, n_steps = out["states"], out["div"], out["n_steps"].long()
+    dev, n, h = states.device, states.shape[0], int(horizon)
+    rl = tables.shape[1]
+    total = int(n_steps.sum())
+    x, ac = int(take_every_x), int(action_counter)
+    first = (ac // x + 1) * x                                         # first kept call number after the counter
+    if first > ac + total:
+        return states.new_zeros(0, 12), states.new_zeros(0, h, 9), ac + total
+    c = torch.arange(first, ac + total + 1, x, device=dev)
+    cum = torch.cumsum(n_steps, 0)
+    g = c - ac - 1                                                    # 0-based call index over all runs
+    run = torch.searchsorted(cum, g, right=True)
+    step = g - (cum - n_steps)[run]
+    tab = tables if table_index is None else tables[table_index.long()]
+    tab = tab[run].float()                                            # (M,RL,9)
+    m = run.numel()
+    ar = torch.arange(m, device=dev)
+    last = max(rl - h, 0)
+    ci = step.clamp(max=last)                                         # walking index before the call's window
+    seen = states[run, step]
+    if not test_time:
+        prev = (step - 1).clamp(min=0)
+        bad = (div[run, prev] > thresh_div) | ~((seen[:, 3].abs() < thresh_stable) & (seen[:, 4].abs() < thresh_stable))
+        reset = torch.cat((tab[ar, ci], seen.new_zeros(m, 3)), dim=1)
+        seen = torch.where(((step > 0) & bad)[:, None], reset, seen)
+    end = ci >= rl - h
+    start = torch.where(end, ci, ci + 1)
+    nreal = torch.where(end, rl - ci, torch.full_like(ci, h))
+    r = torch.arange(h, device=dev)[None, :]
+    rows = torch.gather(tab, 1, (start[:, None] + r).clamp(max=rl - 1)[:, :, None].expand(m, h, 9))
+    pad = torch.zeros_like(rows)
+    pad[:, :, :3] = tab[:, -1:, :3]
+    rows = torch.where((r < nreal[:, None])[:, :, None], rows, pad)
+    return seen, rows, ac + total
+
+
 class WingTargetEvaluator:
     """Fixed wing: ``FixedWingEvaluator.fly_to_point`` / ``run_eval`` (scripts/evaluate_fixed_wing.py:46-178) for N
     flights at once.  ``spec``: ``RolloutSpec.wing_concurrent(h, dt_env, modified_params)`` of the EVALUATION

@@ -454,7 +454,7 @@ def eval_window(tables, ci, h):
 
 
 def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0, thresh_stable=1.0, test_time=0,
-                       cfg=QUAD_CFG):
+                       cfg=QUAD_CFG, record_policy_inputs=False):
     """Batched restatement of QuadEvaluator.follow_trajectory("rand").
 
     params: hutter Net(15,h,9,4h) (concurrent: the first of the h predicted actions is applied,
@@ -463,7 +463,9 @@ def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0
     sigmoid -> clip -> dynamics (evaluated in float64 on the float64 env state and rounded to float32,
     drone_env.py:94-102) -> divergence to tables[ci,:3] -> if diverged / unstable: stop (test_time) or reset the
     drone to the reference state.  Returns dict(states (N,steps+1,12), div (N,steps), actions (N,steps,4),
-    n_steps (N,) = steps taken before the break; entries after a break are zero)."""
+    n_steps (N,) = steps taken before the break; entries after a break are zero); with record_policy_inputs also
+    policy_states (N,steps,12) and windows (N,steps,h,9): the raw (state, reference rows) every policy call hands to
+    the dataset (network_wrapper.py:47-52)."""
     n, rl, _ = tables.shape
     tables = tables.float()
     s = init_states.float().clone()
@@ -474,11 +476,14 @@ def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0
     divs, actions = torch.zeros(n, steps), torch.zeros(n, steps, 4)
     n_steps = torch.zeros(n, dtype=torch.long)
     out_dim = params[-1].shape[0]
+    pol_states, windows = torch.zeros(n, steps, 12), torch.zeros(n, steps, h, 9)
     for i in range(steps):
         if not bool(alive.any()):
             break
         rows, ci_new = eval_window(tables, ci, h)
         ci = torch.where(alive, ci_new, ci)
+        pol_states[alive, i] = s[alive]
+        windows[alive, i] = rows[alive]
         cur = s.clone()
         rel = rows.clone()
         rel[:, :, :3] = rel[:, :, :3] - cur[:, None, :3]                 # dataset.py:170-173
@@ -503,7 +508,28 @@ def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0
         else:
             s = torch.where((alive & bad)[:, None], reset_state, torch.where(alive[:, None], nxt, s))
         alive = alive & (i < rl)                                          # evaluate_drone.py:187-188
-    return dict(states=states, div=divs, actions=actions, n_steps=n_steps)
+    out = dict(states=states, div=divs, actions=actions, n_steps=n_steps)
+    if record_policy_inputs:
+        out.update(policy_states=pol_states, windows=windows)
+    return out
+
+
+def selfplay_kept_calls(n_steps, take_every_x, action_counter=0):
+    """Which policy calls of runs taken one after the other NetworkWrapper.predict_actions adds to the dataset
+    (network_wrapper.py:47: call number c, 1-based and running on over the runs, is kept when c % take_every_x == 0).
+    Returns ([(run, step), ...] in call order, the action counter afterwards)."""
+    kept, c = [], int(action_counter)
+    for run, ns in enumerate([int(x) for x in n_steps]):
+        for step in range(ns):
+            c += 1
+            if c % take_every_x == 0:
+                kept.append((run, step))
+    return kept, c
+
+
+def selfplay_ring_slots(n_kept, num_sampled, num_self_play, eval_counter=0):
+    """DroneDataset.get_eval_index (dataset.py:78-85) for n_kept consecutive additions: slot of each, counter after"""
+    return [num_sampled + (eval_counter + j) % num_self_play for j in range(n_kept)], eval_counter + n_kept
 
 
 def eval_statistics(div, n_steps, thresh_div):

@@ -112,6 +112,71 @@ def make_eval_golden(args):
     np.savez_compressed(os.path.join(args.out, "eval_rand.npz"), **out)
 
 
+def make_selfplay_golden(args):
+    """eval_selfplay.npz: the self-play feed of the evaluation (NetworkWrapper.predict_actions,
+    controllers/network_wrapper.py:42-52 -> DroneDataset.get_and_add_eval_data, dataset.py:98-119).  ONE controller
+    (its action counter runs on over the runs) evaluates three tables one after the other with take_every_x = 7 into a
+    dataset with 3 sampled rows and 5 self-play slots (the ring wraps).  Saved: the raw (state, window) pairs handed to
+    the dataset for the kept calls, and the dataset tensors afterwards.  Substitutions as in make_eval_golden (the
+    trajectory FILE reader); the dataset is allocated without its sampler (needs the absent data files)."""
+    import torch
+    cwd = os.getcwd()
+    os.chdir(args.ref)
+    _np_random = lambda seed=None: (np.random.RandomState(0), 0)
+    sys.modules['gym.utils'].seeding.np_random = _np_random
+    sys.modules['gym'].utils.seeding.np_random = _np_random
+    import neural_control.trajectory.random_traj as RT
+    import evaluate_drone as ED
+    from neural_control.environments.drone_env import QuadRotorEnvBase
+    from neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from neural_control.controllers.network_wrapper import NetworkWrapper
+    from neural_control.dataset import QuadDataset
+    net = torch.load('trained_models/quad/current_model/model_quad', weights_only=False)
+    net.eval()
+    h, dt, take, n_sampled, n_slots = 10, 0.1, 7, 3, 5
+    ds = QuadDataset.__new__(QuadDataset)
+    ds.num_sampled_states, ds.num_self_play, ds.eval_counter = n_sampled, n_slots, 0
+    tot = n_sampled + n_slots
+    ds.normed_states, ds.states = torch.zeros(tot, 15), torch.zeros(tot, 12)
+    ds.in_ref_states, ds.ref_states = torch.zeros(tot, h, 9), torch.zeros(tot, h, 9)
+    kept_states, kept_refs = [], []
+    real = ds.get_and_add_eval_data
+
+    def recording(st, rf, add_to_dataset=False):
+        if add_to_dataset:
+            kept_states.append(np.array(st, dtype=np.float64).copy())
+            kept_refs.append(np.array(rf, dtype=np.float64).copy())
+        return real(st, rf, add_to_dataset=add_to_dataset)
+    ds.get_and_add_eval_data = recording
+    ctrl = NetworkWrapper(net, ds, horizon=h, dt=dt, take_every_x=take)
+    out = {"cfg": np.array([h, dt, take, n_sampled, n_slots], dtype=np.float64)}
+    # (name, table seed, rows, speed, steps, thresh_div, thresh_stable): tracking, resets, end-of-table padding
+    runs = [("a", 5, 60, 0.3, 32, 1.0, 1.0), ("b", 2, 120, 1.0, 50, 1.0, 1.0), ("c", 3, 30, 0.3, 41, 1.0, 1.0)]
+    for name, seed, rows, speed, steps, tdiv, tstab in runs:
+        table = eval_table(seed, rows, dt, speed)
+        RT.load_prepare_trajectory = lambda base_dir, dt_, speed_factor, test=False, _t=table: _t.copy()
+        env = QuadRotorEnvBase(FlightmareDynamics(), dt)
+        ev = ED.QuadEvaluator(ctrl, env, ref_length=h, dt=dt, test_time=0, speed_factor=0.4, train_mode="concurrent")
+        _, drone_traj, div, _ = ev.follow_trajectory("rand", max_nr_steps=steps, thresh_stable=tstab, thresh_div=tdiv)
+        tab = table.copy()
+        tab[:, 2] += 3
+        out[f"{name}_table"] = tab
+        out[f"{name}_cfg"] = np.array([steps, tdiv, tstab], dtype=np.float64)
+        out[f"{name}_states"] = np.asarray(drone_traj)
+        out[f"{name}_div"] = np.asarray(div)
+        print("selfplay", name, "steps", len(div), "resets", int(np.sum(np.asarray(div) > tdiv)), "kept so far",
+              len(kept_states))
+    out["run_names"] = np.array([r[0] for r in runs])
+    out["kept_states"] = np.asarray(kept_states).reshape(len(kept_states), 12)
+    out["kept_refs"] = np.asarray(kept_refs).reshape(len(kept_refs), h, 9)
+    out["action_counter"] = np.array([ctrl.action_counter])
+    out["eval_counter"] = np.array([ds.eval_counter])
+    out["ds_normed_states"], out["ds_states"] = ds.normed_states, ds.states
+    out["ds_in_ref_states"], out["ds_ref_states"] = ds.in_ref_states, ds.ref_states
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(args.out, "eval_selfplay.npz"), **npify(out))
+
+
 def make_wing_eval_golden(args):
     """eval_wing.npz: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py) of the unmodified reference with
     the shipped model_wing and its config (mean / std / horizon / dt): trajectories, divergences and the target
@@ -311,6 +376,7 @@ def main():
     ap.add_argument("--only-eval", action="store_true", help="only (re)generate eval_rand.npz")
     ap.add_argument("--only-wing-eval", action="store_true", help="only (re)generate eval_wing.npz")
     ap.add_argument("--only-cartpole-eval", action="store_true", help="only (re)generate eval_cartpole.npz")
+    ap.add_argument("--only-selfplay", action="store_true", help="only (re)generate eval_selfplay.npz")
     ap.add_argument("--only-learnt", action="store_true", help="only (re)generate learnt_dyn.npz")
     args = ap.parse_args()
     import_reference(args.ref)
@@ -326,6 +392,9 @@ def main():
         return
     if args.only_cartpole_eval:
         make_cartpole_eval_golden(args)
+        return
+    if args.only_selfplay:
+        make_selfplay_golden(args)
         return
 
     import torch

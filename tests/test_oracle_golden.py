@@ -321,3 +321,33 @@ def test_eval_cartpole_balance_is_batched_consistently():
         one = O.eval_cartpole_balance(params, init[k:k + 1], 60, 0.05, 0.21, 5)
         assert int(one["n_steps"][0]) == int(out["n_steps"][k])
         assert float((one["states"][0] - out["states"][k]).abs().max()) <= 1e-5
+
+
+def test_eval_selfplay_feed_matches_reference_dataset():
+    """which policy calls NetworkWrapper.predict_actions adds to the dataset, the raw (state, window) it hands over
+    (also right after a reset) and the ring slots (network_wrapper.py:42-52, dataset.py:78-119): three runs with one
+    running action counter, take_every_x = 7, 3 sampled rows + 5 self-play slots"""
+    g = load_golden("eval_selfplay.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    h, dt, take, n_sampled, n_slots = [float(v) for v in g["cfg"]]
+    h, take = int(h), int(take)
+    ac, ks, kr = 0, [], []
+    for name in [str(v) for v in g["run_names"]]:
+        steps, tdiv, tstab = g[f"{name}_cfg"]
+        out = O.eval_follow_tables(params, torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None],
+                                   torch.tensor(g[f"{name}_states"][:1], dtype=torch.float32), int(steps), h, dt,
+                                   tdiv, tstab, 0, record_policy_inputs=True)
+        assert int(out["n_steps"][0]) == len(g[f"{name}_div"])
+        kept, ac = O.selfplay_kept_calls(out["n_steps"], take, ac)
+        ks += [out["policy_states"][r, i].numpy() for r, i in kept]
+        kr += [out["windows"][r, i].numpy() for r, i in kept]
+    assert ac == int(g["action_counter"][0]) and len(ks) == int(g["eval_counter"][0])
+    assert np.abs(np.array(ks) - g["kept_states"]).max() <= 5e-6
+    assert np.abs(np.array(kr) - g["kept_refs"]).max() <= 1e-6
+    slots, counter = O.selfplay_ring_slots(len(ks), int(n_sampled), int(n_slots))
+    final = {}
+    for slot, s in zip(slots, ks):
+        final[slot] = s
+    for slot, s in final.items():                                    # dataset `states`: position zeroed
+        assert np.abs(s[3:] - g["ds_states"][slot, 3:]).max() <= 5e-6 and np.abs(g["ds_states"][slot, :3]).max() == 0
+    assert counter == int(g["eval_counter"][0]) and sorted(final) == list(range(int(n_sampled), int(n_sampled + n_slots)))

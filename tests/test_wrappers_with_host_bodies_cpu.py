@@ -310,3 +310,68 @@ def test_cartpole_balance_evaluator_wrapper(hostlib):
     assert set(slim) == {"n_steps", "vel_sum", "success", "mean_angle"} and slim["n_steps"].tolist() == [30] * 4
     with pytest.raises(ValueError):
         ev4.balance(flat, torch.zeros(3, 4))
+
+
+def test_selfplay_feed_matches_reference_dataset(hostlib, monkeypatch):
+    """evaluation -> self-play slots of the dataset (network_wrapper.py:42-52, dataset.py:98-119): the three runs of
+    tests/golden/eval_selfplay.npz taken one after the other with ONE action counter, through the TableEvaluator
+    wrapper (host-compiled kernel logic) and evaluate.selfplay_samples, into a DeviceQuadDataset ring"""
+    from apg_trajectory_tracking_b200 import device_data as DD
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    g = load_golden("eval_selfplay.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    h, dt, take, n_sampled, n_slots = [float(v) for v in g["cfg"]]
+    h, take, n_sampled, n_slots = int(h), int(take), int(n_sampled), int(n_slots)
+    tot = n_sampled + n_slots
+    ds = DD.DeviceQuadDataset(torch.zeros(tot, 12), torch.zeros(tot, h, 9), "cpu", num_self_play=n_slots)
+    assert ds.num_sampled_states == n_sampled and ds.get_eval_index() == n_sampled
+    counter, kept_s, kept_r = 0, [], []
+    for name in [str(v) for v in g["run_names"]]:
+        steps, tdiv, tstab = g[f"{name}_cfg"]
+        tab = torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None]
+        ev = EV.TableEvaluator(R.RolloutSpec.quad_concurrent(h, dt), 1, "cpu")
+        out = ev.follow(R.flatten_params(params), tab, init_states=torch.tensor(g[f"{name}_states"][:1],
+                                                                               dtype=torch.float32),
+                        steps=int(steps), thresh_div=tdiv, thresh_stable=tstab, test_time=0)
+        assert int(out["n_steps"][0]) == len(g[f"{name}_div"])
+        s, r, counter = EV.selfplay_samples(out, tab, None, h, take, tdiv, tstab, 0, counter)
+        ds.add_self_play(s, r)
+        kept_s.append(s)
+        kept_r.append(r)
+    kept_s, kept_r = torch.cat(kept_s).numpy(), torch.cat(kept_r).numpy()
+    assert counter == int(g["action_counter"][0]) and ds.eval_counter == int(g["eval_counter"][0])
+    assert kept_s.shape == g["kept_states"].shape
+    assert np.abs(kept_s - g["kept_states"]).max() <= 2e-5 and np.abs(kept_r - g["kept_refs"]).max() <= 1e-6
+    # one kept call saw the state a reset left behind: exactly a table row with zero body rates
+    assert any(np.all(k[9:] == 0) and np.abs(g["b_table"] - k[:9]).max(axis=1).min() < 1e-6 for k in kept_s)
+    # the ring: what the reference's dataset holds afterwards (its `states` have the position zeroed and its
+    # `ref_states` are relative to it, dataset.py:170-175 - prepare the raw ring rows the same way to compare)
+    prep = PR.prepare_quad(ds.states, ds.ref_states, want=("cur", "ref"))
+    assert np.abs(prep["cur"].numpy() - g["ds_states"]).max() <= 2e-5
+    assert np.abs(prep["ref"].numpy() - g["ds_ref_states"]).max() <= 2e-5
+    assert float(ds.states[:n_sampled].abs().sum()) == 0.0              # the sampled rows are untouched
+
+
+def test_selfplay_samples_batched_selection_matches_sequential_runs():
+    """N runs of one follow call = N sequential runs of the reference: selection, reset states and windows against
+    the oracle's recorded policy inputs (no kernels involved: selfplay_samples is index arithmetic on the outputs)"""
+    g = load_golden("eval_rand.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    tabs = torch.tensor(np.stack([g["fast_reset_table"][:60], g["tight_table"][:60], g["gentle_table"][:60]]),
+                        dtype=torch.float32)
+    index = torch.tensor([0, 1, 2, 1, 0], dtype=torch.int32)
+    gen = torch.Generator().manual_seed(0)
+    init = torch.zeros(5, 12)
+    init[:, :3] = tabs[index.long(), 0, :3] + 0.05 * torch.randn(5, 3, generator=gen)
+    for test_time, steps in ((0, 70), (1, 40)):
+        out = O.eval_follow_tables(params, tabs[index.long()], init, steps, 10, 0.1, 0.4, 0.3, test_time,
+                                   record_policy_inputs=True)
+        assert test_time or int((out["div"] > 0.4).sum()) > 0           # there are resets in the batch
+        for take, ac in ((3, 0), (11, 7), (1000, 0)):
+            kept, after = O.selfplay_kept_calls(out["n_steps"], take, ac)
+            s, r, counter = EV.selfplay_samples(out, tabs, index, 10, take, 0.4, 0.3, test_time, ac)
+            assert counter == after and s.shape[0] == len(kept)
+            if kept:
+                want_s = torch.stack([out["policy_states"][j, i] for j, i in kept])
+                want_r = torch.stack([out["windows"][j, i] for j, i in kept])
+                assert torch.equal(s, want_s) and torch.equal(r, want_r)

@@ -230,6 +230,39 @@ def test_eval_rollout_matches_reference_evaluator(name):
     assert float(out["states"][0, taken + 1:].abs().sum()) == 0.0
 
 
+def test_eval_rollout_selfplay_feed_matches_reference_dataset():
+    """evaluation kernel -> evaluate.selfplay_samples -> DeviceQuadDataset ring, against what the reference's
+    NetworkWrapper / DroneDataset hold after the same three runs (tests/golden/eval_selfplay.npz)"""
+    from apg_trajectory_tracking_b200 import device_data as DD, prepare as PR
+    EV, R, O, golden_params = _eval_mods()
+    g = load_golden("eval_selfplay.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    h, dt, take, n_sampled, n_slots = [float(v) for v in g["cfg"]]
+    h, take, n_sampled, n_slots = int(h), int(take), int(n_sampled), int(n_slots)
+    tot = n_sampled + n_slots
+    ds = DD.DeviceQuadDataset(torch.zeros(tot, 12), torch.zeros(tot, h, 9), "cuda:0", num_self_play=n_slots)
+    flat = R.flatten_params(params).cuda()
+    counter, kept_s, kept_r = 0, [], []
+    for name in [str(v) for v in g["run_names"]]:
+        steps, tdiv, tstab = g[f"{name}_cfg"]
+        tab = torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None].cuda()
+        ev = EV.TableEvaluator(R.RolloutSpec.quad_concurrent(h, dt), 1, "cuda:0")
+        out = ev.follow(flat, tab, init_states=torch.tensor(g[f"{name}_states"][:1], dtype=torch.float32).cuda(),
+                        steps=int(steps), thresh_div=tdiv, thresh_stable=tstab, test_time=0)
+        assert int(out["n_steps"][0]) == len(g[f"{name}_div"])
+        s, r, counter = EV.selfplay_samples(out, tab, None, h, take, tdiv, tstab, 0, counter)
+        ds.add_self_play(s, r)
+        kept_s.append(s)
+        kept_r.append(r)
+    kept_s, kept_r = torch.cat(kept_s).cpu().numpy(), torch.cat(kept_r).cpu().numpy()
+    assert counter == int(g["action_counter"][0]) and ds.eval_counter == int(g["eval_counter"][0])
+    assert kept_s.shape == g["kept_states"].shape
+    assert np.abs(kept_s - g["kept_states"]).max() <= 1e-4 and np.abs(kept_r - g["kept_refs"]).max() <= 1e-6
+    prep = PR.prepare_quad(ds.states, ds.ref_states, want=("cur", "ref"))
+    assert np.abs(prep["cur"].cpu().numpy() - g["ds_states"]).max() <= 1e-4
+    assert np.abs(prep["ref"].cpu().numpy() - g["ds_ref_states"]).max() <= 1e-4
+
+
 @pytest.mark.parametrize("mode,n", [("concurrent", 333), ("autoregressive", 130)])
 def test_eval_rollout_batched_vs_oracle(mode, n):
     """many drones (partial tiles, several tiles per CTA), shared tables through the index, random policy"""
