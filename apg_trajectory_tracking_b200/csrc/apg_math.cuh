@@ -42,6 +42,8 @@ APG_HD float atan_(float x) { return atanf(x); }
 APG_HD double atan_(double x) { return atan(x); }
 APG_HD float atan2_(float y, float x) { return atan2f(y, x); }
 APG_HD double atan2_(double y, double x) { return atan2(y, x); }
+APG_HD float asin_(float x) { return asinf(x); }
+APG_HD double asin_(double x) { return asin(x); }
 APG_HD float tanh_(float x) { return tanhf(x); }
 APG_HD double tanh_(double x) { return tanh(x); }
 APG_HD float exp_(float x) { return expf(x); }

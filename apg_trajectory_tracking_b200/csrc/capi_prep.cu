@@ -47,6 +47,17 @@ APG_API int apg_sample_windows(const float* traj, int traj_rows, int traj_cols, 
                                     static_cast<cudaStream_t>(stream));
 }
 
+APG_API int apg_reference_table(const float* traj, int traj_rows, int traj_cols, int take_every_nth,
+                                float speed_factor, float z_offset, int table_rows, float* table_out, void* stream) {
+  if (!traj || !table_out || traj_cols < 10 || take_every_nth < 1 || table_rows < 0 || traj_rows < 0)
+    return APG_ERR_BAD_CONFIG;
+  // table row k reads raw row k * take_every_nth (numpy's traj[::nth] has ceil(T / nth) rows)
+  if (table_rows > 0 && (long long)(table_rows - 1) * take_every_nth > (long long)traj_rows - 1)
+    return APG_ERR_BAD_CONFIG;
+  return (int)launch_reference_table(traj, traj_cols, take_every_nth, speed_factor, z_offset, table_rows, table_out,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 // ---- learnt residual dynamics (learnt_kernels.cu): system = APG_SYS_QUAD / APG_SYS_WING
 #include <string.h>
 

@@ -95,4 +95,18 @@ cudaError_t launch_sample_windows(const float* traj, int W, int L, int stride, i
   return cudaGetLastError();
 }
 
+__global__ void apg_ref_table_kernel(const float* __restrict__ traj, int W, int nth, float speed, float z_offset,
+                                     size_t rows, float* __restrict__ out) {
+  const size_t k = flat_tid();
+  if (k < rows) ref_table_body(k, traj, W, nth, speed, z_offset, out);
+}
+
+cudaError_t launch_reference_table(const float* traj, int W, int nth, float speed, float z_offset, int rows,
+                                   float* out, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  apg_ref_table_kernel<<<blocks_for((size_t)rows), PREP_THREADS, 0, st>>>(traj, W, nth, speed, z_offset, (size_t)rows,
+                                                                         out);
+  return cudaGetLastError();
+}
+
 }  // namespace apg

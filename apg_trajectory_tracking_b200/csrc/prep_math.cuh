@@ -187,4 +187,40 @@ APG_HD void sample_windows_body(size_t idx, const float* traj, int W, int L, int
   }
 }
 
+// Reference table of the evaluation / training data from one raw trajectory file: load_prepare_trajectory
+// (neural_control/trajectory/generate_trajectory.py:566-603) + the z offset of Random.__init__
+// (trajectory/random_traj.py:35).  Raw rows [T][W >= 10] = [pos(3), quaternion w x y z (4), vel(3), ...] sampled at
+// 0.01 s; table row k = raw row k * nth -> [pos (z + z_offset), euler(q) * speed, vel * speed * 2].
+// euler(q) = q_funcs.quaternion_to_euler (:38-41) = pyquaternion's Quaternion.yaw_pitch_roll on the normalised
+// quaternion, returned as [roll, pitch, yaw].  pyquaternion is NOT in this image (nor pinned by the reference's
+// setup.py); its published formula is restated here:
+//   yaw = atan2(2(wz - xy), 1 - 2(y^2 + z^2)),  pitch = asin(2(wy + zx)),  roll = atan2(2(wx - yz), 1 - 2(x^2 + y^2))
+template <typename T>
+struct RefTable {
+  APG_HD static void euler(const T* q4, T* rpy) {
+    const T nrm = sqrt_(q4[0] * q4[0] + q4[1] * q4[1] + q4[2] * q4[2] + q4[3] * q4[3]);
+    const T w = q4[0] / nrm, x = q4[1] / nrm, y = q4[2] / nrm, z = q4[3] / nrm;
+    rpy[2] = atan2_(T(2) * (w * z - x * y), T(1) - T(2) * (y * y + z * z));
+    rpy[1] = asin_(T(2) * (w * y + z * x));
+    rpy[0] = atan2_(T(2) * (w * x - y * z), T(1) - T(2) * (x * x + y * y));
+  }
+  APG_HD static void row(const T* raw, T speed, T z_offset, T* o) {
+    T rpy[3];
+    euler(raw + 3, rpy);
+    o[0] = raw[0]; o[1] = raw[1]; o[2] = raw[2] + z_offset;
+    o[3] = rpy[0] * speed; o[4] = rpy[1] * speed; o[5] = rpy[2] * speed;
+    o[6] = raw[7] * speed * T(2); o[7] = raw[8] * speed * T(2); o[8] = raw[9] * speed * T(2);
+  }
+};
+
+// k over the table rows
+APG_HD void ref_table_body(size_t k, const float* traj, int W, int nth, float speed, float z_offset, float* out) {
+  float raw[10], o[9];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) raw[j] = traj[(k * (size_t)nth) * W + j];
+  RefTable<float>::row(raw, speed, z_offset, o);
+#pragma unroll
+  for (int j = 0; j < 9; ++j) out[k * 9 + j] = o[j];
+}
+
 }  // namespace apg

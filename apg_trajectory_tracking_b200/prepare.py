@@ -107,3 +107,24 @@ def poly_reference(coef, rows, dt, t_first=None):
                                                    ctypes.c_float(float(dt if t_first is None else t_first)),
                                                    ctypes.c_float(float(dt)), _p(out), _stream(c)))
     return out
+
+
+def reference_table(traj, dt, speed_factor, z_offset=3.0):
+    """``load_prepare_trajectory`` (neural_control/trajectory/generate_trajectory.py:566-603) on the device, for an
+    already loaded raw trajectory (T, W>=10) = [pos, quaternion wxyz, vel, ...] sampled every 0.01 s: every
+    ``int(dt / 0.01 * speed_factor)``-th row -> (rows, 9) = [pos, euler * speed_factor, vel * speed_factor * 2], with
+    the ``+3`` on z that ``Random.__init__`` applies (random_traj.py:35; pass ``z_offset=0`` for the bare table)."""
+    _require_cuda(traj)
+    t = _f32c(traj)
+    if t.dim() != 2 or t.shape[1] < 10:
+        raise ValueError(f"reference_table: expected a raw trajectory (T, W>=10), got {tuple(t.shape)}")
+    nth = int(dt / 0.01 * speed_factor)
+    if nth < 1 or not np.isclose(nth, dt / 0.01 * speed_factor):         # the reference asserts this too (:585)
+        raise ValueError("reference_table: dt / 0.01 * speed_factor must be a positive integer")
+    rows = (t.shape[0] + nth - 1) // nth                                  # len(traj[::nth])
+    out = torch.empty(rows, 9, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _capi.check(_capi.lib().apg_reference_table(_p(t), t.shape[0], t.shape[1], nth,
+                                                    ctypes.c_float(float(speed_factor)),
+                                                    ctypes.c_float(float(z_offset)), rows, _p(out), _stream(t)))
+    return out

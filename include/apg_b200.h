@@ -109,6 +109,14 @@ int apg_prepare_wing(const float* states, const float* targets, const float* mea
 int apg_sample_windows(const float* traj, int traj_rows, int traj_cols, int ref_rows, int stride, int n,
                        float* states, float* ref_states, void* stream);
 int apg_poly_reference(const float* coef, int n, int rows, float t_first, float dt, float* ref_out, void* stream);
+/* apg_reference_table  the table layout of load_prepare_trajectory (neural_control/trajectory/generate_trajectory.py:
+ *                    566-603) + the z offset of Random.__init__ (trajectory/random_traj.py:35) from one raw
+ *                    trajectory [traj_rows][traj_cols >= 10] = [pos, quaternion wxyz, vel, ...] (0.01 s steps):
+ *                    table_out [table_rows][9], row k = raw row k*take_every_nth -> [pos (z + z_offset),
+ *                    euler(q)*speed_factor, vel*speed_factor*2]; euler = q_funcs.quaternion_to_euler (:38-41,
+ *                    pyquaternion yaw_pitch_roll restated, see csrc/prep_math.cuh). */
+int apg_reference_table(const float* traj, int traj_rows, int traj_cols, int take_every_nth, float speed_factor,
+                        float z_offset, int table_rows, float* table_out, void* stream);
 
 /* ---- closed-loop evaluation on table references: QuadEvaluator.follow_trajectory("rand")
  * (scripts/evaluate_drone.py:81-194) with Random.get_ref_traj / project_on_ref / get_current_full_state

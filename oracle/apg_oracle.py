@@ -789,3 +789,36 @@ def eval_cartpole_balance(params, init_states, max_steps, dt, thresh_div=0.21, b
     mean_angle = torch.where(ang_cnt > 0, ang_sum / ang_cnt.clamp(min=1), torch.full((n,), 100.0))
     return dict(states=states, actions=actions, success=n_steps - 1, n_steps=n_steps, mean_angle=mean_angle,
                 vel_sum=vel_sum)
+
+
+# --------------------------------------------------------------------------------------------
+# N4  reference tables from raw trajectory files: load_prepare_trajectory
+#     (neural_control/trajectory/generate_trajectory.py:566-603), q_funcs.quaternion_to_euler (:38-41).
+#     The Euler angles come from pyquaternion (Quaternion.yaw_pitch_roll), which is NOT installed here and not
+#     pinned by the reference: its published formula is restated (PARITY UNPINNED for these three columns; the
+#     sub-sampling, the column layout and the speed scaling are pinned on the reference's own code run with a
+#     pyquaternion stand-in implementing the same formula, tests/golden/ref_table.npz).
+# --------------------------------------------------------------------------------------------
+def quaternion_to_euler(q):
+    """q (..., 4) = w, x, y, z -> (..., 3) = roll, pitch, yaw (float64 numpy)"""
+    import numpy as np
+    q = np.asarray(q, dtype=np.float64)
+    q = q / np.linalg.norm(q, axis=-1, keepdims=True)
+    w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    yaw = np.arctan2(2 * (w * z - x * y), 1 - 2 * (y ** 2 + z ** 2))
+    pitch = np.arcsin(2 * (w * y + z * x))
+    roll = np.arctan2(2 * (w * x - y * z), 1 - 2 * (x ** 2 + y ** 2))
+    return np.stack((roll, pitch, yaw), axis=-1)
+
+
+def reference_table(traj, dt, speed_factor, z_offset=0.0):
+    """raw trajectory (T, >=10) -> (ceil(T/nth), 9) = [pos, euler * speed, vel * speed * 2] (+ z_offset on z:
+    Random.__init__, random_traj.py:35)"""
+    import numpy as np
+    nth = int(dt / 0.01 * speed_factor)
+    assert np.isclose(nth, dt / 0.01 * speed_factor)
+    taken = np.asarray(traj, dtype=np.float64)[::nth]
+    out = np.hstack((taken[:, :3], quaternion_to_euler(taken[:, 3:7]) * speed_factor,
+                     taken[:, 7:10] * speed_factor * 2))
+    out[:, 2] += z_offset
+    return out

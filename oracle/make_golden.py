@@ -177,6 +177,52 @@ def make_selfplay_golden(args):
     np.savez_compressed(os.path.join(args.out, "eval_selfplay.npz"), **npify(out))
 
 
+def make_ref_table_golden(args):
+    """ref_table.npz: load_prepare_trajectory (neural_control/trajectory/generate_trajectory.py:566-603) of the
+    unmodified reference on synthetic raw trajectory files written to a temporary data directory (the real
+    data/traj_data_1 is not part of the checkout).  pyquaternion is not installed: `pyquaternion.Quaternion` is a
+    stand-in with the published yaw_pitch_roll formula (normalise; yaw = atan2(2(wz - xy), 1 - 2(y^2 + z^2)),
+    pitch = asin(2(wy + zx)), roll = atan2(2(wx - yz), 1 - 2(x^2 + y^2))), so the Euler columns pin the CALL SITE
+    (argument order w x y z, output order roll pitch yaw, scaling), not pyquaternion itself."""
+    import tempfile
+
+    class Quaternion:
+        def __init__(self, w, x, y, z):
+            q = np.array([w, x, y, z], dtype=np.float64)
+            self.q = q / np.linalg.norm(q)
+
+        @property
+        def yaw_pitch_roll(self):
+            w, x, y, z = self.q
+            return (np.arctan2(2 * (w * z - x * y), 1 - 2 * (y ** 2 + z ** 2)), np.arcsin(2 * (w * y + z * x)),
+                    np.arctan2(2 * (w * x - y * z), 1 - 2 * (x ** 2 + y ** 2)))
+    import neural_control.trajectory.q_funcs as QF
+    import neural_control.trajectory.generate_trajectory as GT
+    QF.pyquaternion.Quaternion = Quaternion
+    rng = np.random.default_rng(11)
+    out = {}
+    # (name, raw rows, dt, speed_factor)
+    cases = [("a", 401, 0.1, 0.4), ("b", 203, 0.05, 0.6), ("c", 77, 0.1, 1.0)]
+    for name, T, dt, speed in cases:
+        raw = np.zeros((T, 12))
+        t = np.arange(T) * 0.01
+        raw[:, :3] = np.stack((np.sin(t), np.cos(0.7 * t), 1 + 0.3 * t), 1) + rng.normal(0, 0.01, (T, 3))
+        q = rng.normal(0, 1, (T, 4)) * np.array([0.2, 0.3, 0.3, 0.2]) + np.array([1.0, 0, 0, 0])
+        raw[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True) * rng.uniform(0.9, 1.1, (T, 1))   # not quite unit
+        raw[:, 7:10] = rng.normal(0, 1, (T, 3))
+        raw[:, 10:] = rng.normal(0, 1, (T, 2))
+        raw = raw.astype(np.float32).astype(np.float64)          # exactly representable in the kernel's float32
+        with tempfile.TemporaryDirectory() as d:
+            os.makedirs(os.path.join(d, "train"))
+            np.save(os.path.join(d, "train", "traj_0.npy"), raw)
+            table = GT.load_prepare_trajectory(d, dt, speed, test=False)
+        out[f"{name}_raw"], out[f"{name}_table"] = raw.astype(np.float32), table
+        out[f"{name}_cfg"] = np.array([dt, speed], dtype=np.float64)
+        print("ref table", name, raw.shape, "->", table.shape)
+    out["case_names"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(args.out, "ref_table.npz"), **out)
+
+
 def make_wing_eval_golden(args):
     """eval_wing.npz: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py) of the unmodified reference with
     the shipped model_wing and its config (mean / std / horizon / dt): trajectories, divergences and the target
@@ -377,6 +423,7 @@ def main():
     ap.add_argument("--only-wing-eval", action="store_true", help="only (re)generate eval_wing.npz")
     ap.add_argument("--only-cartpole-eval", action="store_true", help="only (re)generate eval_cartpole.npz")
     ap.add_argument("--only-selfplay", action="store_true", help="only (re)generate eval_selfplay.npz")
+    ap.add_argument("--only-ref-table", action="store_true", help="only (re)generate ref_table.npz")
     ap.add_argument("--only-learnt", action="store_true", help="only (re)generate learnt_dyn.npz")
     args = ap.parse_args()
     import_reference(args.ref)
@@ -395,6 +442,9 @@ def main():
         return
     if args.only_selfplay:
         make_selfplay_golden(args)
+        return
+    if args.only_ref_table:
+        make_ref_table_golden(args)
         return
 
     import torch

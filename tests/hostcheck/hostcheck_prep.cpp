@@ -35,3 +35,8 @@ extern "C" void hc_sample_windows(const float* traj, int W, int L, int stride, i
   const size_t total_ref = (size_t)n * L * 9, total = total_ref + (size_t)n * 12;
   for (size_t idx = 0; idx < total; ++idx) sample_windows_body(idx, traj, W, L, stride, total_ref, states, refs);
 }
+
+extern "C" void hc_reference_table(const float* traj, int W, int nth, float speed, float z_offset, int rows,
+                                   float* out) {
+  for (size_t k = 0; k < (size_t)rows; ++k) ref_table_body(k, traj, W, nth, speed, z_offset, out);
+}

@@ -78,6 +78,13 @@ class _HostLib:
                                     ctypes.c_float(_f(dt)), self._vp(_addr(out)))
         return 0
 
+    def apg_reference_table(self, traj, rows, cols, nth, speed, zoff, table_rows, out, stream):
+        if table_rows > 0 and (table_rows - 1) * nth > rows - 1:
+            return -1
+        self.prep.hc_reference_table(self._vp(_addr(traj)), cols, nth, ctypes.c_float(_f(speed)),
+                                     ctypes.c_float(_f(zoff)), table_rows, self._vp(_addr(out)))
+        return 0
+
     def apg_eval_rollout(self, cfg, params, tables, index, n_tables, rows, init, steps, tdiv, tstab, test_time, ws,
                          states, div, actions, n_steps, stream):
         c = cfg._obj
@@ -375,3 +382,17 @@ def test_selfplay_samples_batched_selection_matches_sequential_runs():
                 want_s = torch.stack([out["policy_states"][j, i] for j, i in kept])
                 want_r = torch.stack([out["windows"][j, i] for j, i in kept])
                 assert torch.equal(s, want_s) and torch.equal(r, want_r)
+
+
+def test_reference_table_wrapper(hostlib):
+    g = load_golden("ref_table.npz")
+    for name in ("a", "b", "c"):
+        dt, speed = [float(v) for v in g[f"{name}_cfg"]]
+        tab = PR.reference_table(torch.tensor(g[f"{name}_raw"]), dt, speed)
+        want = g[f"{name}_table"].copy()
+        want[:, 2] += 3                                                  # Random.__init__ (random_traj.py:35)
+        assert tuple(tab.shape) == want.shape and np.abs(tab.numpy() - want).max() <= 3e-6
+    with pytest.raises(ValueError):
+        PR.reference_table(torch.zeros(50, 12), 0.1, 0.37)               # dt / 0.01 * speed not an integer
+    with pytest.raises(ValueError):
+        PR.reference_table(torch.zeros(50, 9), 0.1, 0.4)

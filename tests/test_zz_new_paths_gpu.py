@@ -230,6 +230,19 @@ def test_eval_rollout_matches_reference_evaluator(name):
     assert float(out["states"][0, taken + 1:].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_sample_windows_reference_table_matches_load_prepare_trajectory(name):
+    from apg_trajectory_tracking_b200 import prepare as PR
+    g = load_golden("ref_table.npz")
+    dt, speed = [float(v) for v in g[f"{name}_cfg"]]
+    tab = PR.reference_table(torch.tensor(g[f"{name}_raw"]).cuda(), dt, speed, z_offset=0.0).cpu().numpy()
+    want = g[f"{name}_table"]
+    assert tab.shape == want.shape
+    assert np.array_equal(tab[:, :3], want[:, :3].astype(np.float32))
+    assert np.abs(tab[:, 3:6] - want[:, 3:6]).max() <= 5e-6              # device atan2f / asinf
+    assert np.abs(tab[:, 6:] - want[:, 6:]).max() <= 1e-6 * np.abs(want[:, 6:]).max()
+
+
 def test_eval_rollout_selfplay_feed_matches_reference_dataset():
     """evaluation kernel -> evaluate.selfplay_samples -> DeviceQuadDataset ring, against what the reference's
     NetworkWrapper / DroneDataset hold after the same three runs (tests/golden/eval_selfplay.npz)"""
