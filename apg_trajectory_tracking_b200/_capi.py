@@ -58,6 +58,9 @@ EXPORTS = {
     "apg_sample_windows": (ctypes.c_int, [c_float_p] + [ctypes.c_int] * 5 + [c_float_p, c_float_p, ctypes.c_void_p]),
     "apg_poly_reference": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                           c_float_p, ctypes.c_void_p]),
+    "apg_polynomial_points": (ctypes.c_int, [c_float_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int, ctypes.c_double,
+                                             ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, c_float_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "apg_reference_table": (ctypes.c_int, [c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_int, c_float_p, ctypes.c_void_p]),
 }

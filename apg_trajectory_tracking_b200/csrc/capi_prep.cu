@@ -58,6 +58,16 @@ APG_API int apg_reference_table(const float* traj, int traj_rows, int traj_cols,
                                      static_cast<cudaStream_t>(stream));
 }
 
+APG_API int apg_polynomial_points(const double* coef, int degree, const double* rot, const double* start, int n,
+                                  double x_start, double x_range, double dist_points, int hover_steps, int max_rows,
+                                  float* points_out, int* ref_len_out, void* stream) {
+  if (!coef || !rot || !points_out || n < 0 || degree < 1 || degree > 11 || max_rows < 1 || hover_steps < 0)
+    return APG_ERR_BAD_CONFIG;
+  if (!(dist_points > 0.0) || !(x_range >= 0.0)) return APG_ERR_BAD_CONFIG;
+  return (int)launch_polynomial_points(coef, degree, rot, start, n, x_start, x_range, dist_points, hover_steps,
+                                       max_rows, points_out, ref_len_out, static_cast<cudaStream_t>(stream));
+}
+
 // ---- learnt residual dynamics (learnt_kernels.cu): system = APG_SYS_QUAD / APG_SYS_WING
 #include <string.h>
 

@@ -83,6 +83,9 @@ cudaError_t launch_prepare_wing(const float* states, const float* targets, const
                                 float* in_ref, float* ref_out, cudaStream_t st);
 cudaError_t launch_poly_reference(const float* coef, int n, int L, float t_first, float dt, float* out,
                                   cudaStream_t st);
+cudaError_t launch_polynomial_points(const double* coef, int degree, const double* rot, const double* start, int n,
+                                     double x_start, double x_range, double dist_points, int hover, int max_rows,
+                                     float* out, int* ref_len, cudaStream_t st);
 cudaError_t launch_reference_table(const float* traj, int W, int nth, float speed, float z_offset, int rows,
                                    float* out, cudaStream_t st);
 cudaError_t launch_sample_windows(const float* traj, int W, int L, int stride, int n, float* states, float* refs,

@@ -109,4 +109,25 @@ cudaError_t launch_reference_table(const float* traj, int W, int nth, float spee
   return cudaGetLastError();
 }
 
+__global__ void apg_poly_march_kernel(const double* __restrict__ coef, int degree, const double* __restrict__ rot,
+                                      const double* __restrict__ start, int n, double x_start, double x_range,
+                                      double dist_points, int hover, int max_rows, float* __restrict__ out,
+                                      int* __restrict__ ref_len) {
+  const size_t i = flat_tid();
+  if (i >= (size_t)n) return;
+  const int len = poly_march_body(coef + i * (degree + 1), degree, rot + i * 9, start ? start + i * 3 : nullptr,
+                                  x_start, x_range, dist_points, hover, max_rows, out + i * (size_t)max_rows * 3);
+  if (ref_len) ref_len[i] = len;
+}
+
+cudaError_t launch_polynomial_points(const double* coef, int degree, const double* rot, const double* start, int n,
+                                     double x_start, double x_range, double dist_points, int hover, int max_rows,
+                                     float* out, int* ref_len, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  // one thread per trajectory (sequential march): small blocks spread few trajectories over many SMs
+  apg_poly_march_kernel<<<(n + 31) / 32, 32, 0, st>>>(coef, degree, rot, start, n, x_start, x_range, dist_points,
+                                                      hover, max_rows, out, ref_len);
+  return cudaGetLastError();
+}
+
 }  // namespace apg

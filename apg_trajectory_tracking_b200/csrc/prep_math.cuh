@@ -223,4 +223,52 @@ APG_HD void ref_table_body(size_t k, const float* traj, int W, int nth, float sp
   for (int j = 0; j < 9; ++j) out[k * 9 + j] = o[j];
 }
 
+// Polynomial reference of the evaluation (neural_control/trajectory/polynomial.py): random_polynomial's march along
+// the fitted polynomial in steps of dist_points of arc length (:99-113), the lift to 3D and rotation (:115-125), the
+// shift to the drone's position and the hover padding at both ends (:41-47).  One trajectory per call (the march is
+// sequential); the march itself runs in double like the reference's numpy code, so the number of points agrees.
+//   coef [degree + 1] highest power first (np.poly1d order), rot [9] row-major 3x3, start [3] (may be null: no shift),
+//   all double like the numpy arrays they come from (x^5 at x ~ 20 amplifies a float32 rounding of the fit to ~1e-3)
+//   out [max_rows][3]: hover copies of the first point | the marched points | hover copies of the last point
+// Returns the number of rows the full reference has (rows beyond max_rows are not written).
+APG_HD int poly_march_body(const double* coef, int degree, const double* rot, const double* start, double x_start,
+                           double x_range, double dist_points, int hover, int max_rows, float* out) {
+  double c[12];
+  for (int i = 0; i <= degree; ++i) c[i] = coef[i];
+  auto poly = [&](double x) { double y = 0.0; for (int i = 0; i <= degree; ++i) y = y * x + c[i]; return y; };
+  auto grad = [&](double x) {
+    double gsum = 0.0;
+    for (int i = 0; i < degree; ++i) {
+      double pw = 1.0;
+      for (int e = 0; e < degree - i - 1; ++e) pw *= x;
+      gsum += (double)(degree - i) * c[i] * pw;
+    }
+    return gsum;
+  };
+  auto lift = [&](double x, double y, double* p3) {
+    for (int j = 0; j < 3; ++j) p3[j] = x * rot[j] + y * rot[6 + j];      // [x, 0, y] @ rot
+  };
+  double x = x_start;
+  const double x_final = x + x_range, step = dist_points;
+  double p0[3], p[3], sh[3];
+  lift(x, poly(x), p0);
+  for (int j = 0; j < 3; ++j) sh[j] = start ? start[j] - p0[j] : 0.0;
+  int row = 0;
+  auto emit = [&](const double* q) {
+    if (row < max_rows) { for (int j = 0; j < 3; ++j) out[(size_t)row * 3 + j] = (float)(q[j] + sh[j]); }
+    ++row;
+  };
+  for (int k = 0; k < hover; ++k) emit(p0);
+  emit(p0);
+  for (int j = 0; j < 3; ++j) p[j] = p0[j];
+  while (x < x_final) {
+    const double gr = grad(x);
+    x += (1.0 / sqrt(1.0 + gr * gr)) * step;                     // (vec / norm(vec) * dist_points)[0]
+    lift(x, poly(x), p);
+    emit(p);
+  }
+  for (int k = 0; k < hover; ++k) emit(p);
+  return row;
+}
+
 }  // namespace apg

@@ -18,6 +18,11 @@ def _f32c(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.contiguous().float()
 
 
+def _f64c(t):
+    t = torch.as_tensor(t)
+    return t if (t.dtype == torch.float64 and t.is_contiguous()) else t.contiguous().double()
+
+
 def _opt(t):
     return None if t is None else _p(t)
 
@@ -128,3 +133,36 @@ def reference_table(traj, dt, speed_factor, z_offset=3.0):
                                                     ctypes.c_float(float(speed_factor)),
                                                     ctypes.c_float(float(z_offset)), rows, _p(out), _stream(t)))
     return out
+
+
+def polynomial_points(coef, rot, start=None, x_range=20.0, max_drone_dist=0.25, horizon=10, hover_steps=50,
+                      x_start=1.0, max_rows=None, check=True):
+    """The reference rows of ``Polynomial`` (neural_control/trajectory/polynomial.py:8-125, ``random_polynomial`` branch)
+    for N trajectories on the device: coef (N, degree+1) as ``np.polyfit`` returns them, rot (N,3,3) rotations,
+    start (N,3) drone positions (or None) -> (points (N,max_rows,3), ref_len (N,) int32); trajectory i is
+    ``points[i, :ref_len[i]]`` (hover copies, marched points, hover copies).  ``check`` synchronises and raises when
+    ``max_rows`` (default: hover padding + 4x the straight-line number of steps) was too small for a trajectory."""
+    _require_cuda(coef, rot, start)
+    c, r = _f64c(coef), _f64c(rot)                 # double like the numpy fit: x^5 at x ~ 20 amplifies float32 rounding
+    n = c.shape[0]
+    if c.dim() != 2 or tuple(r.shape) != (n, 3, 3) or not 2 <= c.shape[1] <= 12:
+        raise ValueError(f"polynomial_points: expected coef (N,degree+1) and rot (N,3,3), got {tuple(c.shape)} and "
+                         f"{tuple(r.shape)}")
+    st = None
+    if start is not None:
+        st = _f64c(start)
+        if tuple(st.shape) != (n, 3):
+            raise ValueError("polynomial_points: start must be (N,3)")
+    dist = float(max_drone_dist) / int(horizon)
+    if max_rows is None:
+        max_rows = 2 * int(hover_steps) + 4 * int(float(x_range) / dist) + 8
+    pts = torch.zeros(n, int(max_rows), 3, dtype=torch.float32, device=c.device)
+    ref_len = torch.zeros(n, dtype=torch.int32, device=c.device)
+    with torch.cuda.device(c.device):
+        _capi.check(_capi.lib().apg_polynomial_points(_p(c), c.shape[1] - 1, _p(r), _opt(st), n,
+                                                      ctypes.c_double(float(x_start)), ctypes.c_double(float(x_range)),
+                                                      ctypes.c_double(dist), int(hover_steps), int(max_rows), _p(pts),
+                                                      _p(ref_len), _stream(c)))
+    if check and n and int(ref_len.max()) > max_rows:
+        raise ValueError(f"polynomial_points: a trajectory needs {int(ref_len.max())} rows, max_rows = {max_rows}")
+    return pts, ref_len

@@ -117,6 +117,16 @@ int apg_poly_reference(const float* coef, int n, int rows, float t_first, float 
  *                    pyquaternion yaw_pitch_roll restated, see csrc/prep_math.cuh). */
 int apg_reference_table(const float* traj, int traj_rows, int traj_cols, int take_every_nth, float speed_factor,
                         float z_offset, int table_rows, float* table_out, void* stream);
+/* apg_polynomial_points  the polynomial evaluation reference (neural_control/trajectory/polynomial.py:8-125):
+ *                    Polynomial.random_polynomial's march along a fitted polynomial in steps of dist_points of arc
+ *                    length, lifted to 3D ([x, 0, y] @ rot), shifted to `start` and padded with hover_steps copies of
+ *                    its first / last point, for n trajectories (one thread each; the march runs in double).
+ *                    coef [n][degree+1] highest power first (np.polyfit order), rot [n][9] row-major, start [n][3]
+ *                    (may be NULL), all DOUBLE like the numpy arrays they come from, x from x_start to x_start + x_range.  points_out [n][max_rows][3];
+ *                    ref_len_out [n] = rows of the full reference (rows beyond max_rows are not written). */
+int apg_polynomial_points(const double* coef, int degree, const double* rot, const double* start, int n, double x_start,
+                          double x_range, double dist_points, int hover_steps, int max_rows, float* points_out,
+                          int* ref_len_out, void* stream);
 
 /* ---- closed-loop evaluation on table references: QuadEvaluator.follow_trajectory("rand")
  * (scripts/evaluate_drone.py:81-194) with Random.get_ref_traj / project_on_ref / get_current_full_state

@@ -822,3 +822,25 @@ def reference_table(traj, dt, speed_factor, z_offset=0.0):
                      taken[:, 7:10] * speed_factor * 2))
     out[:, 2] += z_offset
     return out
+
+
+def polynomial_points(coef, rot, start, x_range=20.0, dist_points=0.025, hover_steps=50, x_start=1.0):
+    """Polynomial.__init__ with random_polynomial (neural_control/trajectory/polynomial.py:36-47, 84-125) for GIVEN
+    fit coefficients (np.poly1d order) and rotation: march in steps of dist_points of arc length, [x, 0, y] @ rot,
+    shift to `start`, hover padding.  float64 numpy, one trajectory."""
+    import numpy as np
+    coef = np.asarray(coef, dtype=np.float64)
+    degree = len(coef) - 1
+    poly = np.poly1d(coef)
+    grad = lambda x: np.sum([(degree - i) * coef[i] * x ** (degree - i - 1) for i in range(degree)])   # noqa: E731
+    x, x_final = float(x_start), float(x_start) + x_range
+    pts = [[x, poly(x)]]
+    while x < x_final:
+        vec = np.array([1, grad(x)])
+        x = x + (vec / np.linalg.norm(vec) * dist_points)[0]
+        pts.append([x, poly(x)])
+    pts = np.array(pts)
+    p3 = np.stack((pts[:, 0], np.zeros(len(pts)), pts[:, 1]), axis=1) @ np.asarray(rot, dtype=np.float64)
+    if start is not None:
+        p3 = p3 - p3[0] + np.asarray(start, dtype=np.float64)
+    return np.vstack([np.repeat(p3[:1], hover_steps, 0), p3, np.repeat(p3[-1:], hover_steps, 0)])

@@ -223,6 +223,44 @@ def make_ref_table_golden(args):
     np.savez_compressed(os.path.join(args.out, "ref_table.npz"), **out)
 
 
+def make_poly_traj_golden(args):
+    """poly_traj.npz: Polynomial(drone_state, ...) of the unmodified reference (neural_control/trajectory/
+    polynomial.py) with its random_polynomial branch; the fit coefficients and the random rotation it drew are
+    recorded (np.polyfit / special_ortho_group.rvs wrapped) next to the resulting reference points."""
+    import neural_control.trajectory.polynomial as PT
+    out = {}
+    rec = {}
+    real_fit, real_rvs = np.polyfit, PT.special_ortho_group.rvs
+
+    def fit(x, y, deg):
+        rec["coef"] = real_fit(x, y, deg)
+        return rec["coef"]
+
+    def rvs(dim):
+        rec["rot"] = real_rvs(dim)
+        return rec["rot"]
+    PT.np.polyfit = fit
+    PT.special_ortho_group.rvs = rvs
+    # (name, seed, start, x_range, degree, max_drone_dist, horizon, hover_steps)
+    cases = [("a", 0, [0.5, -1.0, 2.0], 20, 5, 0.25, 10, 50), ("b", 1, [0.0, 0.0, 3.0], 6, 5, 0.5, 10, 5),
+             ("c", 2, [-2.0, 1.0, 1.0], 10, 3, 0.25, 5, 2)]
+    try:
+        for name, seed, start, x_range, degree, mdd, h, hover in cases:
+            np.random.seed(seed)
+            tr = PT.Polynomial(np.array(start + [0.0] * 9), max_drone_dist=mdd, horizon=h, hover_steps=hover,
+                               x_range=x_range, degree=degree, dt=0.05)
+            out[f"{name}_coef"], out[f"{name}_rot"] = rec["coef"].copy(), rec["rot"].copy()
+            out[f"{name}_start"] = np.array(start)
+            out[f"{name}_cfg"] = np.array([x_range, degree, mdd, h, hover], dtype=np.float64)
+            out[f"{name}_points"] = np.asarray(tr.reference)
+            print("poly traj", name, "rows", tr.ref_len)
+    finally:
+        PT.np.polyfit = real_fit
+        PT.special_ortho_group.rvs = real_rvs
+    out["case_names"] = np.array([c[0] for c in cases])
+    np.savez_compressed(os.path.join(args.out, "poly_traj.npz"), **out)
+
+
 def make_wing_eval_golden(args):
     """eval_wing.npz: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py) of the unmodified reference with
     the shipped model_wing and its config (mean / std / horizon / dt): trajectories, divergences and the target
@@ -424,6 +462,7 @@ def main():
     ap.add_argument("--only-cartpole-eval", action="store_true", help="only (re)generate eval_cartpole.npz")
     ap.add_argument("--only-selfplay", action="store_true", help="only (re)generate eval_selfplay.npz")
     ap.add_argument("--only-ref-table", action="store_true", help="only (re)generate ref_table.npz")
+    ap.add_argument("--only-poly-traj", action="store_true", help="only (re)generate poly_traj.npz")
     ap.add_argument("--only-learnt", action="store_true", help="only (re)generate learnt_dyn.npz")
     args = ap.parse_args()
     import_reference(args.ref)
@@ -445,6 +484,9 @@ def main():
         return
     if args.only_ref_table:
         make_ref_table_golden(args)
+        return
+    if args.only_poly_traj:
+        make_poly_traj_golden(args)
         return
 
     import torch

@@ -40,3 +40,12 @@ extern "C" void hc_reference_table(const float* traj, int W, int nth, float spee
                                    float* out) {
   for (size_t k = 0; k < (size_t)rows; ++k) ref_table_body(k, traj, W, nth, speed, z_offset, out);
 }
+
+extern "C" void hc_polynomial_points(const double* coef, int degree, const double* rot, const double* start, int n,
+                                     double x_start, double x_range, double dist_points, int hover, int max_rows,
+                                     float* out, int* ref_len) {
+  for (int i = 0; i < n; ++i)
+    ref_len[i] = poly_march_body(coef + (size_t)i * (degree + 1), degree, rot + (size_t)i * 9,
+                                 start ? start + (size_t)i * 3 : nullptr, x_start, x_range, dist_points, hover,
+                                 max_rows, out + (size_t)i * max_rows * 3);
+}

@@ -85,6 +85,14 @@ class _HostLib:
                                      ctypes.c_float(_f(zoff)), table_rows, self._vp(_addr(out)))
         return 0
 
+    def apg_polynomial_points(self, coef, degree, rot, start, n, x_start, x_range, dist, hover, max_rows, out, ref_len,
+                              stream):
+        self.prep.hc_polynomial_points(self._vp(_addr(coef)), degree, self._vp(_addr(rot)), self._vp(_addr(start)), n,
+                                       ctypes.c_double(x_start.value), ctypes.c_double(x_range.value),
+                                       ctypes.c_double(dist.value), hover, max_rows, self._vp(_addr(out)),
+                                       self._vp(_addr(ref_len)))
+        return 0
+
     def apg_eval_rollout(self, cfg, params, tables, index, n_tables, rows, init, steps, tdiv, tstab, test_time, ws,
                          states, div, actions, n_steps, stream):
         c = cfg._obj
@@ -396,3 +404,24 @@ def test_reference_table_wrapper(hostlib):
         PR.reference_table(torch.zeros(50, 12), 0.1, 0.37)               # dt / 0.01 * speed not an integer
     with pytest.raises(ValueError):
         PR.reference_table(torch.zeros(50, 9), 0.1, 0.4)
+
+
+def test_polynomial_points_wrapper(hostlib):
+    g = load_golden("poly_traj.npz")
+    names = [str(v) for v in g["case_names"]]
+    for name in names:
+        x_range, degree, mdd, h, hover = g[f"{name}_cfg"]
+        pts, ref_len = PR.polynomial_points(torch.tensor(g[f"{name}_coef"])[None], torch.tensor(g[f"{name}_rot"])[None],
+                                            torch.tensor(g[f"{name}_start"])[None], x_range=x_range,
+                                            max_drone_dist=mdd, horizon=int(h), hover_steps=int(hover))
+        want = g[f"{name}_points"]
+        assert int(ref_len[0]) == len(want) and pts.shape[1] >= len(want)
+        assert np.array_equal(pts[0, :len(want)].numpy(), want.astype(np.float32))
+    # two trajectories of the same degree in one call, no shift; too small a buffer is reported
+    coef = torch.tensor(np.stack([g["a_coef"], g["b_coef"]]))
+    rot = torch.tensor(np.stack([g["a_rot"], g["b_rot"]]))
+    pts, ref_len = PR.polynomial_points(coef, rot, None, x_range=6, max_drone_dist=0.5, horizon=10, hover_steps=5)
+    assert int(ref_len[1]) == len(g["b_points"])
+    assert np.allclose(pts[1, :int(ref_len[1])].numpy() - pts[1, 0].numpy(), g["b_points"] - g["b_points"][0], atol=1e-5)
+    with pytest.raises(ValueError):
+        PR.polynomial_points(coef, rot, None, x_range=6, max_drone_dist=0.5, horizon=10, hover_steps=5, max_rows=20)

@@ -243,6 +243,30 @@ def test_sample_windows_reference_table_matches_load_prepare_trajectory(name):
     assert np.abs(tab[:, 6:] - want[:, 6:]).max() <= 1e-6 * np.abs(want[:, 6:]).max()
 
 
+def test_sample_windows_polynomial_points_match_reference_polynomial_class():
+    from apg_trajectory_tracking_b200 import prepare as PR
+    g = load_golden("poly_traj.npz")
+    for name in [str(v) for v in g["case_names"]]:
+        x_range, degree, mdd, h, hover = g[f"{name}_cfg"]
+        pts, ref_len = PR.polynomial_points(torch.tensor(g[f"{name}_coef"])[None].cuda(),
+                                            torch.tensor(g[f"{name}_rot"])[None].cuda(),
+                                            torch.tensor(g[f"{name}_start"])[None].cuda(), x_range=x_range,
+                                            max_drone_dist=mdd, horizon=int(h), hover_steps=int(hover))
+        want = g[f"{name}_points"]
+        assert int(ref_len[0]) == len(want)
+        assert np.abs(pts[0, :len(want)].cpu().numpy() - want).max() <= 2e-6     # double march (FMA-contracted)
+    # many trajectories at once: every thread marches its own polynomial
+    n = 300
+    coef = torch.tensor(g["a_coef"])[None].repeat(n, 1) * (1 + 0.01 * torch.arange(n, dtype=torch.float64)[:, None])
+    rot = torch.tensor(g["a_rot"])[None].repeat(n, 1, 1)
+    pts, ref_len = PR.polynomial_points(coef.cuda(), rot.cuda(), None, x_range=5, hover_steps=3)
+    from oracle import apg_oracle as O
+    for i in (0, 17, n - 1):
+        want = O.polynomial_points(coef[i].numpy(), rot[i].numpy(), None, 5.0, 0.025, 3)
+        assert int(ref_len[i]) == len(want)
+        assert np.abs(pts[i, :len(want)].cpu().numpy() - want).max() <= 1e-5 * max(np.abs(want).max(), 1.0)
+
+
 def test_eval_rollout_selfplay_feed_matches_reference_dataset():
     """evaluation kernel -> evaluate.selfplay_samples -> DeviceQuadDataset ring, against what the reference's
     NetworkWrapper / DroneDataset hold after the same three runs (tests/golden/eval_selfplay.npz)"""
