@@ -16,8 +16,8 @@ def pytest_configure(config):
 # order of the tests of tests/test_zz_new_paths_gpu.py (everything written after the round-1 GPU budget was spent):
 # from the simplest kernels to the tcgen05 paths, so that under `pytest -x` a failure hides as little as possible
 _NEW_PATH_ORDER = ["test_prepare", "test_sample_windows", "test_learnt", "test_eval_rollout", "test_wing_fly",
-                   "test_cartpole_balance", "test_step_host", "test_device_dataset", "test_tc1", "test_tc2", "test_tc3",
-                   "test_device_captured"]
+                   "test_cartpole_balance", "test_single_drone", "test_step_host", "test_device_dataset", "test_tc1",
+                   "test_tc2", "test_tc3", "test_device_captured"]
 
 
 def _new_path_rank(item):

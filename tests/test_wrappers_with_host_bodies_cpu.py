@@ -47,6 +47,7 @@ class _HostLib:
         self.real = _capi.lib()
         self.prep, self.ev, self.ln = _build(tmp, "hostcheck_prep"), _build(tmp, "hostcheck_eval"), \
             _build(tmp, "hostcheck_learnt")
+        self.dyn = _build(tmp, "hostcheck")
         self.keep = []
 
     def __getattr__(self, name):          # host-only queries go to the real library
@@ -91,6 +92,12 @@ class _HostLib:
                                        ctypes.c_double(x_start.value), ctypes.c_double(x_range.value),
                                        ctypes.c_double(dist.value), hover, max_rows, self._vp(_addr(out)),
                                        self._vp(_addr(ref_len)))
+        return 0
+
+    def apg_dynamics_step(self, system, phys, state, action, dt, n, out, stream):
+        fn = getattr(self.dyn, "hc_step_%s_f32" % ("quad", "wing", "cartpole")[system])
+        fn(self._vp(_addr(state)), self._vp(_addr(action)), ctypes.c_float(_f(dt)), self._vp(_addr(phys)),
+           self._vp(_addr(out)), n)
         return 0
 
     def apg_eval_rollout(self, cfg, params, tables, index, n_tables, rows, init, steps, tdiv, tstab, test_time, ws,
@@ -425,3 +432,113 @@ def test_polynomial_points_wrapper(hostlib):
     assert np.allclose(pts[1, :int(ref_len[1])].numpy() - pts[1, 0].numpy(), g["b_points"] - g["b_points"][0], atol=1e-5)
     with pytest.raises(ValueError):
         PR.polynomial_points(coef, rot, None, x_range=6, max_drone_dist=0.5, horizon=10, hover_steps=5, max_rows=20)
+
+
+def _single_drone_mirrors_on_cpu(monkeypatch):
+    """the batch-1 mirrors (controllers / environments) with the host-compiled dynamics and the policy on the CPU"""
+    from apg_trajectory_tracking_b200.neural_control import environments as ENV
+    from apg_trajectory_tracking_b200.neural_control.controllers import network_wrapper as NW
+    from apg_trajectory_tracking_b200.neural_control.models import hutter_model as HM, simple_model as SM
+    monkeypatch.setattr(ENV, "compute_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(NW, "_device_of", lambda net: torch.device("cpu"))
+    for mod in (HM, SM):
+        monkeypatch.setattr(mod, "_require_cuda", lambda *a, **k: None)
+    return NW
+
+
+def test_single_drone_mirrors_reproduce_reference_quad_evaluation(hostlib, monkeypatch):
+    """NetworkWrapper + QuadDataset + QuadRotorEnvBase + FlightmareDynamics mirrors driven by the reference's
+    follow_trajectory loop (scripts/evaluate_drone.py:136-188), against its golden run with resets"""
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.drone_env import QuadRotorEnvBase
+    from apg_trajectory_tracking_b200.neural_control.models.hutter_model import Net
+    NW = _single_drone_mirrors_on_cpu(monkeypatch)
+    g = load_golden("eval_rand.npz")
+    name = "fast_reset"
+    steps, test_time, tdiv, tstab, h, dt = [float(v) for v in g[f"{name}_cfg"]]
+    steps, h = int(steps), int(h)
+    net = Net(15, h, 9, 4 * h)
+    with torch.no_grad():
+        for p, q in zip(net.parameters(), golden_params(load_golden("conc_quad_kat4.npz"))):
+            p.copy_(q)
+    table = g[f"{name}_table"]
+    ds = DS.QuadDataset(np.zeros((4, 12)), np.zeros((4, h, 9)), self_play=1.0)
+    ctrl = NW.NetworkWrapper(net, ds, horizon=h, dt=dt, take_every_x=5)
+    env = QuadRotorEnvBase(FlightmareDynamics(), dt)
+    state = env.zero_reset(*table[0, :3])
+    ci, traj, divs = torch.zeros(1, dtype=torch.long), [state], []
+    for i in range(steps):
+        rows, ci = O.eval_window(torch.tensor(table)[None], ci, h)
+        action = ctrl.predict_actions(state, rows[0].numpy().copy())
+        state, stable = env.step(action[0], thresh=tstab)
+        traj.append(state)
+        div = float(np.linalg.norm(table[int(ci), :3] - state[:3]))
+        divs.append(div)
+        if div > tdiv or not stable:
+            state = np.hstack((table[int(ci)], np.zeros(3)))
+            env._state.from_np(state)
+        if i >= len(table):
+            break
+    want = g[f"{name}_states"]
+    assert len(traj) == len(want) and np.abs(np.array(traj) - want).max() <= 5e-5
+    assert np.abs(np.array(divs) - g[f"{name}_div"]).max() <= 5e-5 and (np.array(divs) > tdiv).sum() > 0
+    assert ctrl.action_counter == steps and ds.eval_counter == steps // 5       # the self-play feed ran
+
+
+def test_single_drone_mirrors_reproduce_reference_cartpole_evaluation(hostlib, monkeypatch):
+    """CartpoleWrapper + CartPoleEnv + CartpoleDynamics mirrors in the loop of evaluate_in_environment
+    (scripts/evaluate_cartpole.py:121-228), including the aliasing side effect on the environment state"""
+    from apg_trajectory_tracking_b200.neural_control.dynamics.cartpole_dynamics import CartpoleDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.cartpole_env import CartPoleEnv
+    from apg_trajectory_tracking_b200.neural_control.models.simple_model import Net
+    NW = _single_drone_mirrors_on_cpu(monkeypatch)
+    g = load_golden("eval_cartpole.npz")
+    net = Net(4, 10)
+    with torch.no_grad():
+        for i, p in enumerate(net.parameters()):
+            p.copy_(torch.tensor(g[f"param_{i}"]))
+    for name in ("tilted", "falls"):
+        steps, tdiv, burn = g[f"{name}_cfg"]
+        env = CartPoleEnv(CartpoleDynamics(), 0.05, thresh_div=float(tdiv))
+        ctrl = NW.CartpoleWrapper(net, horizon=10, action_dim=1)
+        env.state = np.array(g[f"{name}_init"], dtype=np.float64)
+        new_state, log = env.state, []
+        for i in range(int(steps)):
+            with torch.no_grad():
+                action_seq = ctrl.predict_actions(new_state, None)
+            new_state = env._step(action_seq[:, 0], is_torch=True)
+            log.append(new_state.copy())
+            if not env.is_upright():
+                break
+        want = g[f"{name}_states"]
+        assert len(log) == len(want) and np.abs(np.array(log) - want).max() <= 2e-5
+
+
+def test_single_drone_mirrors_reproduce_reference_wing_flight(hostlib, monkeypatch):
+    """FixedWingNetWrapper + WingDataset + SimpleWingEnv + FixedWingDynamics mirrors in the loop of fly_to_point
+    (scripts/evaluate_fixed_wing.py:66-92) on the part of a golden flight before the first target switch"""
+    from tests.test_oracle_golden import wing_eval_case
+    from apg_trajectory_tracking_b200.neural_control.dynamics.fixed_wing_dynamics import FixedWingDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.wing_env import SimpleWingEnv
+    from apg_trajectory_tracking_b200.neural_control.models.hutter_model import Net
+    NW = _single_drone_mirrors_on_cpu(monkeypatch)
+    g = load_golden("eval_wing.npz")
+    params, targets, init, h, dt_data, dt_env, steps, test_time, tdiv, tstab = wing_eval_case(g, "one_target")
+    net = Net(9, 1, 3, 4 * h, conv=False)
+    with torch.no_grad():
+        for p, q in zip(net.parameters(), params):
+            p.copy_(q)
+    ds = DS.WingDataset(np.zeros((2, 12)), np.ones((2, 3)), mean=g["mean"], std=g["std"], delta_t=dt_data, horizon=h)
+    ctrl = NW.FixedWingNetWrapper(net, ds, horizon=h)
+    env = SimpleWingEnv(FixedWingDynamics(), dt_env)
+    env.zero_reset()
+    state, target = env._state, targets[0, 0].numpy()
+    traj = g["one_target_traj"]
+    n_check = 40
+    assert traj[:n_check, 0].max() < target[0]                           # still before the target: no switching
+    for i in range(n_check):
+        action = ctrl.predict_actions(state, target)
+        assert np.abs(action[0] - traj[i, 12:]).max() <= 1e-4
+        state, stable = env.step(action[0], thresh_stable=tstab)
+        assert stable and np.abs(state - traj[i, :12]).max() <= 2e-4 * np.abs(traj[:, :12]).max()
+    assert ctrl.action_counter == n_check

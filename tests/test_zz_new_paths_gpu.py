@@ -686,6 +686,65 @@ def _check_split_adjoint(n, flags):
 SPLIT_SIZES = [64, 1, 65, 300, 1000, 9600, 148 * 64 * 3 + 5]
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# single-drone mirrors of the evaluation loop (neural_control.controllers / .environments): batch-1 callers on CUDA
+# ---------------------------------------------------------------------------------------------------------------
+def test_single_drone_quad_mirrors_follow_reference_run():
+    from apg_trajectory_tracking_b200.neural_control import dataset as DS
+    from apg_trajectory_tracking_b200.neural_control.controllers.network_wrapper import NetworkWrapper
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.drone_env import QuadRotorEnvBase
+    from apg_trajectory_tracking_b200.neural_control.models.hutter_model import Net
+    EV, R, O, golden_params = _eval_mods()
+    g = load_golden("eval_rand.npz")
+    name = "gentle"
+    steps, test_time, tdiv, tstab, h, dt = [float(v) for v in g[f"{name}_cfg"]]
+    h = int(h)
+    net = Net(15, h, 9, 4 * h)
+    with torch.no_grad():
+        for p, q in zip(net.parameters(), golden_params(load_golden("conc_quad_kat4.npz"))):
+            p.copy_(q)
+    net.cuda()
+    table = g[f"{name}_table"]
+    ds = DS.QuadDataset(np.zeros((4, 12)), np.zeros((4, h, 9)), self_play=1.0)
+    ctrl = NetworkWrapper(net, ds, horizon=h, dt=dt, take_every_x=4)
+    env = QuadRotorEnvBase(FlightmareDynamics(), dt)
+    state = env.zero_reset(*table[0, :3])
+    ci, want = torch.zeros(1, dtype=torch.long), g[f"{name}_states"]
+    for i in range(25):
+        rows, ci = O.eval_window(torch.tensor(table)[None], ci, h)
+        action = ctrl.predict_actions(state, rows[0].numpy().copy())
+        state, stable = env.step(action[0], thresh=tstab)
+        assert stable and np.abs(state - want[i + 1]).max() <= 1e-4, i
+    assert ctrl.action_counter == 25 and ds.eval_counter == 6
+
+
+def test_single_drone_cartpole_mirrors_follow_reference_run():
+    from apg_trajectory_tracking_b200.neural_control.controllers.network_wrapper import CartpoleWrapper
+    from apg_trajectory_tracking_b200.neural_control.dynamics.cartpole_dynamics import CartpoleDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.cartpole_env import CartPoleEnv
+    from apg_trajectory_tracking_b200.neural_control.models.simple_model import Net
+    g = load_golden("eval_cartpole.npz")
+    net = Net(4, 10)
+    with torch.no_grad():
+        for i, p in enumerate(net.parameters()):
+            p.copy_(torch.tensor(g[f"param_{i}"]))
+    net.cuda()
+    env = CartPoleEnv(CartpoleDynamics(), 0.05, thresh_div=0.21)
+    ctrl = CartpoleWrapper(net, horizon=10, action_dim=1)
+    env.state = np.array(g["falls_init"], dtype=np.float64)
+    new_state, log = env.state, []
+    for i in range(60):
+        with torch.no_grad():
+            action_seq = ctrl.predict_actions(new_state, None)
+        new_state = env._step(action_seq[:, 0], is_torch=True)
+        log.append(new_state.copy())
+        if not env.is_upright():
+            break
+    want = g["falls_states"]
+    assert len(log) == len(want) and np.abs(np.array(log) - want).max() <= 1e-4
+
+
 # The tcgen05 / TMEM kernels are compile-verified and host-emulated only (no GPU minutes were left when they were
 # written): their tests are opt-in until the first hardware run (tools/gpu_first_call.sh sets APG_TEST_TC=1), so a
 # first-run problem in an OPTIONAL path (product default: off) cannot stop `pytest -m gpu -x` of the verified paths.
