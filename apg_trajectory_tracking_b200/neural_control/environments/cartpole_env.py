@@ -1,51 +1,66 @@
 """Single cartpole environment of the evaluation loop (reference: ``neural_control/environments/cartpole_env.py:26-115``
 without rendering / image dynamics).  N carts at once: ``evaluate.CartpoleBalanceEvaluator``."""
+import math
+
 import numpy as np
 import torch
 
 from .. import environments as _env
 
+_LIMITS = (2.4, 7.5, math.pi, 7.5)          # |x|, |x_dot|, |theta|, |theta_dot| of a uniformly drawn state
+
+
+def _wrap_angle(theta):
+    """theta in (-pi, pi] (:76-80)"""
+    if theta > math.pi:
+        return theta - 2 * math.pi
+    if theta <= -math.pi:
+        return theta + 2 * math.pi
+    return theta
+
 
 class CartPoleEnv:
     def __init__(self, dynamics, dt, thresh_div=.21):
         self.dynamics, self.dt, self.thresh_div = dynamics, dt, thresh_div
-        self.x_threshold = 2.4
-        self.state_limits = np.array([2.4, 7.5, np.pi, 7.5])
-        self.viewer = None
+        self.x_threshold = _LIMITS[0]
+        self.state_limits = np.array(_LIMITS)
+        self.viewer, self.steps_beyond_done = None, None
         self.state = self._reset()
-        self.steps_beyond_done = None
 
     def is_upright(self):
-        return bool(-self.thresh_div < self.state[2] < self.thresh_div)
+        return bool(abs(self.state[2]) < self.thresh_div)
 
     def _step(self, action, image=None, state_action_buffer=None, is_torch=True):
-        """action: (1,) tensor (or a list with ``is_torch=False``) -> new state (4,) float32, theta in (-pi, pi]"""
+        """action: (1,) tensor (or a list with ``is_torch=False``) -> new state (4,) float32, theta wrapped"""
         dev = _env.compute_device()
-        s = torch.tensor([list(self.state)]).float().to(dev)
-        a = (action if is_torch else torch.tensor([action])).float().reshape(1, -1).to(dev)
-        self.state = self.dynamics(s, a, dt=self.dt)[0].cpu().numpy()
-        theta = self.state[2]
-        if theta > np.pi:
-            self.state[2] = theta - 2 * np.pi
-        if theta <= -np.pi:
-            self.state[2] = 2 * np.pi + theta
+        force = action if is_torch else torch.as_tensor(action)
+        cart = torch.as_tensor(np.asarray(self.state, dtype=np.float32))[None].to(dev)
+        nxt = self.dynamics(cart, force.float().reshape(1, -1).to(dev), dt=self.dt)
+        self.state = nxt[0].cpu().numpy()
+        self.state[2] = _wrap_angle(self.state[2])
         return self.state
 
+    def _uniform_state(self):
+        return (2 * np.random.rand(4) - 1) * self.state_limits
+
     def _reset(self):
-        self.state = (np.random.rand(4) * 2 - 1) * self.state_limits
-        self.steps_beyond_done = None
-        return np.array(self.state)
+        """anywhere in the state box (:84-93)"""
+        self.state, self.steps_beyond_done = self._uniform_state(), None
+        return self.state.copy()
 
     def _reset_swingup(self):
-        self.state = (np.random.rand(4) * 2 - 1) * self.state_limits
-        self.state[0] = 0
-        self.state[1] *= 0.1
-        rand_sign = (-1) if np.random.rand() > .5 else 1
-        self.state[2] = rand_sign * (2.8 + np.random.rand() * .3)
-        self.state[3] *= 0.1
+        """cart centred and slow, pole hanging: |theta| in [2.8, 3.1) with a random sign (:95-105)"""
+        s = self._uniform_state()
+        s[0], s[1] = 0.0, 0.1 * s[1]
+        sign = -1.0 if np.random.rand() > 0.5 else 1.0
+        s[2] = sign * (2.8 + 0.3 * np.random.rand())
+        s[3] = 0.1 * s[3]
+        self.state = s
         return self.state
 
     def _reset_upright(self):
-        self.state = (np.random.rand(4) - .5) * .3
-        self.state[2] = (np.random.rand(1) - .5) * .1
+        """close to upright: every component within +-0.15, theta within +-0.05 (:107-115)"""
+        s = 0.3 * (np.random.rand(4) - 0.5)
+        s[2] = 0.1 * (np.random.rand() - 0.5)
+        self.state = s
         return self.state
