@@ -542,3 +542,94 @@ def test_single_drone_mirrors_reproduce_reference_wing_flight(hostlib, monkeypat
         state, stable = env.step(action[0], thresh_stable=tstab)
         assert stable and np.abs(state - traj[i, :12]).max() <= 2e-4 * np.abs(traj[:, :12]).max()
     assert ctrl.action_counter == n_check
+
+
+def test_evaluator_mirrors_run_eval_batched(hostlib, monkeypatch):
+    """scripts.evaluate_drone.QuadEvaluator / evaluate_fixed_wing.FixedWingEvaluator / evaluate_cartpole.Evaluator:
+    the reference's constructors and run_eval / evaluate_in_environment results with all runs in one launch"""
+    from apg_trajectory_tracking_b200.scripts import evaluate_cartpole as EC, evaluate_drone as ED, \
+        evaluate_fixed_wing as EF
+    from apg_trajectory_tracking_b200.neural_control.dynamics.cartpole_dynamics import CartpoleDynamics
+    from apg_trajectory_tracking_b200.neural_control.dynamics.fixed_wing_dynamics import FixedWingDynamics
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.cartpole_env import CartPoleEnv
+    from apg_trajectory_tracking_b200.neural_control.environments.drone_env import QuadRotorEnvBase
+    from apg_trajectory_tracking_b200.neural_control.environments.wing_env import SimpleWingEnv
+    from apg_trajectory_tracking_b200.neural_control.models import hutter_model as HM, simple_model as SM
+    NW = _single_drone_mirrors_on_cpu(monkeypatch)
+    # ---- quadrotor: two golden runs as one batch
+    g = load_golden("eval_rand.npz")
+    h, dt = 10, 0.1
+    net = HM.Net(15, h, 9, 4 * h)
+    with torch.no_grad():
+        for p, q in zip(net.parameters(), golden_params(load_golden("conc_quad_kat4.npz"))):
+            p.copy_(q)
+    ds = DS.QuadDataset(np.zeros((6, 12)), np.zeros((6, h, 9)), self_play=1.0)
+    ctrl = NW.NetworkWrapper(net, ds, horizon=h, dt=dt, take_every_x=9)
+    ev = ED.QuadEvaluator(ctrl, QuadRotorEnvBase(FlightmareDynamics(), dt), ref_length=h, dt=dt, speed_factor=0.4)
+    tables = torch.tensor(np.stack([g["gentle_table"], g["fast_reset_table"]]), dtype=torch.float32)
+    got = ev.run_eval("rand", nr_test=2, max_steps=80, thresh_div=1.0, thresh_stable=1.0, tables=tables)
+    divs = [g["gentle_div"], g["fast_reset_div"]]
+    per_run = np.array([d.mean() for d in divs])
+    stable = np.array([(d < 1.0).sum() for d in divs])
+    full = per_run[stable == len(divs[-1])]
+    want = (stable.mean(), stable.std(), full.mean() if len(full) else np.nan, full.std() if len(full) else np.nan,
+            per_run.mean(), per_run.std())
+    assert np.allclose(np.array(got, dtype=np.float64), np.array(want, dtype=np.float64), atol=2e-4, equal_nan=True)
+    assert ctrl.action_counter == 160 and ds.eval_counter == 160 // 9
+    # ---- fixed wing: random targets drawn like run_eval, against the single-flight wrapper
+    gw = load_golden("eval_wing.npz")
+    hw, dt_data, dt_env = int(gw["cfg"][0]), float(gw["cfg"][1]), float(gw["cfg"][2])
+    wnet = HM.Net(9, 1, 3, 4 * hw, conv=False)
+    with torch.no_grad():
+        for i, p in enumerate(wnet.parameters()):
+            p.copy_(torch.tensor(gw[f"param_{i}"]))
+    wds = DS.WingDataset(np.zeros((2, 12)), np.ones((2, 3)), mean=gw["mean"], std=gw["std"], delta_t=dt_data,
+                         horizon=hw)
+    wev = EF.FixedWingEvaluator(NW.FixedWingNetWrapper(wnet, wds, horizon=hw), SimpleWingEnv(FixedWingDynamics(), dt_env),
+                                dt=dt_env, horizon=hw, thresh_div=4.0, thresh_stable=0.4)
+    np.random.seed(3)
+    mean_err, std_err = wev.run_eval(nr_test=3, printout=False)
+    np.random.seed(3)
+    targets = np.array([[[50.0, *((np.random.rand(2) - .5) * 10)]] for _ in range(3)])
+    one = EV.WingTargetEvaluator(R.RolloutSpec.wing_concurrent(hw, dt_env), 3, gw["mean"], gw["std"], dt_data, "cpu")
+    params = [torch.tensor(gw[f"param_{i}"]) for i in range(14)]
+    ref = one.fly(R.flatten_params(params), torch.tensor(targets, dtype=torch.float32), steps=1000, thresh_div=4.0,
+                  thresh_stable=0.4)
+    m, sd = EV.wing_eval_statistics(ref["div_target_sum"], ref["div_target_cnt"])
+    assert abs(mean_err - m) <= 1e-6 and abs(std_err - sd) <= 1e-6 and np.isfinite(m)
+    assert wev.controller.action_counter == int(ref["n_steps"].sum())
+    # ---- cartpole: golden starts as one batch
+    gc = load_golden("eval_cartpole.npz")
+    cnet = SM.Net(4, 10)
+    with torch.no_grad():
+        for i, p in enumerate(cnet.parameters()):
+            p.copy_(torch.tensor(gc[f"param_{i}"]))
+    cev = EC.Evaluator(NW.CartpoleWrapper(cnet, horizon=10), CartPoleEnv(CartpoleDynamics(), 0.05, thresh_div=0.21))
+    names = ["zero_start", "tilted", "falls", "falls_at_once"]                   # the runs with thresh_div 0.21
+    init = np.stack([gc[f"{n}_init"] for n in names])
+    succ, vel = cev.evaluate_in_environment(nr_iters=4, max_steps=60, burn_in_steps=5, return_success=1,
+                                            init_states=init)
+    want_succ = [min(int(gc[f"{n}_success"][0]), 59) for n in names]
+    assert succ.tolist() == want_succ
+    want_vel = np.concatenate([gc[f"{n}_vel"][:60] for n in names])
+    assert len(vel) == len(want_vel) and np.abs(np.array(vel) - want_vel).max() <= 2e-5
+    res = cev.evaluate_in_environment(nr_iters=2, max_steps=20)
+    assert res["mean_stable"] == 19.0 and res["std_stable"] == 0.0 and res["mean_vel"] >= 0.0
+
+
+def test_quad_evaluator_loads_tables_like_random_reference(hostlib, monkeypatch, tmp_path):
+    """QuadEvaluator.load_tables = Random.__init__ over trajectory files (random_traj.py:29-36)"""
+    from apg_trajectory_tracking_b200.scripts import evaluate_drone as ED
+    from apg_trajectory_tracking_b200.neural_control.models import hutter_model as HM
+    NW = _single_drone_mirrors_on_cpu(monkeypatch)
+    g = load_golden("ref_table.npz")
+    (tmp_path / "train").mkdir()
+    np.save(tmp_path / "train" / "traj_0.npy", g["a_raw"].astype(np.float64))
+    dt, speed = [float(v) for v in g["a_cfg"]]
+    ctrl = NW.NetworkWrapper(HM.Net(15, 10, 9, 40), None, horizon=10, dt=dt)
+    ev = ED.QuadEvaluator(ctrl, None, ref_length=10, dt=dt, speed_factor=speed, data_dir=str(tmp_path))
+    tabs = ev.load_tables(3, "cpu")
+    want = g["a_table"].copy()
+    want[:, 2] += 3
+    assert tuple(tabs.shape) == (3,) + want.shape and np.abs(tabs[1].numpy() - want).max() <= 3e-6
