@@ -745,6 +745,34 @@ def test_single_drone_cartpole_mirrors_follow_reference_run():
     assert len(log) == len(want) and np.abs(np.array(log) - want).max() <= 1e-4
 
 
+def test_single_drone_evaluator_classes_run_eval_in_one_launch():
+    """scripts.evaluate_drone.QuadEvaluator.run_eval on CUDA: two golden runs of the reference as one batch"""
+    from apg_trajectory_tracking_b200.neural_control import dataset as DS
+    from apg_trajectory_tracking_b200.neural_control.controllers.network_wrapper import NetworkWrapper
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.drone_env import QuadRotorEnvBase
+    from apg_trajectory_tracking_b200.neural_control.models.hutter_model import Net
+    from apg_trajectory_tracking_b200.scripts import evaluate_drone as ED
+    EV, R, O, golden_params = _eval_mods()
+    g = load_golden("eval_rand.npz")
+    h, dt = 10, 0.1
+    net = Net(15, h, 9, 4 * h)
+    with torch.no_grad():
+        for p, q in zip(net.parameters(), golden_params(load_golden("conc_quad_kat4.npz"))):
+            p.copy_(q)
+    net.cuda()
+    ds = DS.QuadDataset(np.zeros((6, 12)), np.zeros((6, h, 9)), self_play=1.0)
+    ctrl = NetworkWrapper(net, ds, horizon=h, dt=dt, take_every_x=9)
+    ev = ED.QuadEvaluator(ctrl, QuadRotorEnvBase(FlightmareDynamics(), dt), ref_length=h, dt=dt, speed_factor=0.4)
+    tables = torch.tensor(np.stack([g["gentle_table"], g["fast_reset_table"]]), dtype=torch.float32)
+    got = ev.run_eval("rand", nr_test=2, max_steps=80, thresh_div=1.0, thresh_stable=1.0, tables=tables)
+    divs = [g["gentle_div"], g["fast_reset_div"]]
+    per_run = np.array([d.mean() for d in divs])
+    stable = np.array([(d < 1.0).sum() for d in divs])
+    assert abs(got[0] - stable.mean()) <= 1e-9 and abs(got[4] - per_run.mean()) <= 1e-3
+    assert ctrl.action_counter == 160 and ds.eval_counter == 160 // 9
+
+
 # The tcgen05 / TMEM kernels are compile-verified and host-emulated only (no GPU minutes were left when they were
 # written): their tests are opt-in until the first hardware run (tools/gpu_first_call.sh sets APG_TEST_TC=1), so a
 # first-run problem in an OPTIONAL path (product default: off) cannot stop `pytest -m gpu -x` of the verified paths.
