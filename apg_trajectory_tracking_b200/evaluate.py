@@ -85,18 +85,12 @@ def selfplay_samples(out, tables, table_index=None, horizon=10, take_every_x=100
     random_traj.py:89-92); its reference rows are ``Random.get_ref_traj`` at that step.  Pure index arithmetic and
     gathers on the tensors' device.  Returns (states (M,12), ref_states (M,horizon,9), action counter afterwards)."""
     states, div, n_steps = out["states"], out["div"], out["n_steps"].long()
-    dev, n, h = states.device, states.shape[0], int(horizon)
+    dev, h = states.device, int(horizon)
     rl = tables.shape[1]
-    total = int(n_steps.sum())
-    x, ac = int(take_every_x), int(action_counter)
-    first = (ac // x + 1) * x                                         # first kept call number after the counter
-    if first > ac + total:
-        return states.new_zeros(0, 12), states.new_zeros(0, h, 9), ac + total
-    c = torch.arange(first, ac + total + 1, x, device=dev)
-    cum = torch.cumsum(n_steps, 0)
-    g = c - ac - 1                                                    # 0-based call index over all runs
-    run = torch.searchsorted(cum, g, right=True)
-    step = g - (cum - n_steps)[run]
+    sel, counter = _kept_calls(n_steps, take_every_x, action_counter)
+    if sel is None:
+        return states.new_zeros(0, 12), states.new_zeros(0, h, 9), counter
+    run, step = sel
     tab = tables if table_index is None else tables[table_index.long()]
     tab = tab[run].float()                                            # (M,RL,9)
     m = run.numel()
@@ -117,7 +111,49 @@ def selfplay_samples(out, tables, table_index=None, horizon=10, take_every_x=100
     pad = torch.zeros_like(rows)
     pad[:, :, :3] = tab[:, -1:, :3]
     rows = torch.where((r < nreal[:, None])[:, :, None], rows, pad)
-    return seen, rows, ac + total
+    return seen, rows, counter
+
+
+def _kept_calls(n_steps, take_every_x, action_counter):
+    """(run, step) of the policy calls whose running number (1-based, continuing from ``action_counter`` over the
+    runs taken one after the other) is a multiple of ``take_every_x``; None when there is none"""
+    total, x, ac = int(n_steps.sum()), int(take_every_x), int(action_counter)
+    first = (ac // x + 1) * x
+    if first > ac + total:
+        return None, ac + total
+    g = torch.arange(first, ac + total + 1, x, device=n_steps.device) - ac - 1     # 0-based index over all runs
+    cum = torch.cumsum(n_steps, 0)
+    run = torch.searchsorted(cum, g, right=True)
+    return (run, g - (cum - n_steps)[run]), ac + total
+
+
+def wing_selfplay_samples(out, targets, take_every_x=1000, action_counter=0):
+    """The fixed-wing counterpart of ``selfplay_samples``: the raw (state, target) pairs
+    ``FixedWingNetWrapper.predict_actions`` hands to ``get_and_add_eval_data(..., add_to_dataset=True)``
+    (controllers/network_wrapper.py:81-90) for the N flights of one ``WingTargetEvaluator.fly`` call counted one after
+    the other.  The state a call saw is the state ``env.step`` returned before it (the evaluator's local ``state`` is
+    not refreshed by a reset); its target is the one current at that step: target k+1 from the step after the
+    first one whose x position passed target k (evaluate_fixed_wing.py:93-110).
+    ``out`` needs "states".  Returns (states (M,12), targets (M,3), action counter afterwards)."""
+    states, n_steps = out["states"], out["n_steps"].long()
+    dev, n, K = states.device, states.shape[0], targets.shape[1]
+    sel, counter = _kept_calls(n_steps, take_every_x, action_counter)
+    if sel is None:
+        return states.new_zeros(0, 12), states.new_zeros(0, 3), counter
+    run, step = sel
+    targets = targets.to(dev, torch.float32)
+    # step index at which target k was passed (first step >= the previous switch whose new x lies beyond it)
+    steps = states.shape[1] - 1
+    idx = torch.arange(steps, device=dev)[None, :]
+    x_after = states[:, 1:, 0]
+    start = torch.zeros(n, dtype=torch.long, device=dev)
+    ti = torch.zeros(run.numel(), dtype=torch.long, device=dev)
+    for k in range(K - 1):
+        cond = (x_after > targets[:, k, 0:1]) & (idx >= start[:, None]) & (idx < n_steps[:, None])
+        first = torch.where(cond.any(dim=1), cond.float().argmax(dim=1), torch.full_like(start, steps + 1))
+        ti = ti + (step > first[run]).long()
+        start = first + 1
+    return states[run, step], targets[run, ti], counter
 
 
 class WingTargetEvaluator:

@@ -25,8 +25,16 @@ class FixedWingEvaluator:
         flat = R.flatten_params([p.detach() for p in net.parameters()]).to(dev).float().contiguous()
         out = ev.fly(flat, targets, steps=max_steps, thresh_div=self.thresh_div, thresh_stable=self.thresh_stable,
                      test_time=self.test_time)
-        if hasattr(self.controller, "action_counter"):
-            self.controller.action_counter += int(out["n_steps"].sum())
+        ctrl = self.controller
+        take = getattr(ctrl, "take_every_x", 0)
+        if take and ds is not None and hasattr(ctrl, "action_counter"):
+            # self-play feed (network_wrapper.py:81-90): the kept calls' (state, target) go into the dataset's ring
+            s, tg, _ = EV.wing_selfplay_samples(out, targets, take, ctrl.action_counter)
+            s, tg = s.cpu().numpy(), tg.cpu().numpy()
+            for i in range(len(s)):
+                ds.get_and_add_eval_data(s[i].copy(), tg[i].copy(), add_to_dataset=True)
+        if hasattr(ctrl, "action_counter"):
+            ctrl.action_counter += int(out["n_steps"].sum())
         return out
 
     def run_eval(self, nr_test, return_dists=False, x_dist=50, x_std=5, printout=True):

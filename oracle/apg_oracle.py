@@ -591,13 +591,14 @@ def project_to_line(a, b, p):
 
 
 def eval_fly_to_points(params, targets, init_states, mean, std, steps, h, dt_data, dt_env, thresh_div=10.0,
-                       thresh_stable=0.8, test_time=0, des_speed=11.5, cfg=WING_CFG):
+                       thresh_stable=0.8, test_time=0, des_speed=11.5, cfg=WING_CFG, record_policy_inputs=False):
     """Batched restatement of FixedWingEvaluator.fly_to_point.  params: hutter Net(9,1,3,4h, conv=False);
     targets (N,K,3); init_states (N,12) (zero_reset: zeros with u = 11.5).  Kept quirk: after a reset the policy
     still sees the PRE-reset state for one step (the evaluator's local `state` is not refreshed, :118-129) while the
     environment continues from the reset state.
     Returns dict(states (N,steps+1,12) as returned by env.step, div_linear (N,steps), actions (N,steps,4),
-    n_steps (N,), div_target_sum (N,), div_target_cnt (N,))."""
+    n_steps (N,), div_target_sum (N,), div_target_cnt (N,)); with record_policy_inputs also policy_states
+    (N,steps,12) and target_index (N,steps): what every policy call hands to the dataset (network_wrapper.py:85-87)."""
     n, K, _ = targets.shape
     mean, std = torch.as_tensor(mean).float(), torch.as_tensor(std).float()
     env = init_states.float().clone()               # the environment's state
@@ -613,10 +614,13 @@ def eval_fly_to_points(params, targets, init_states, mean, std, steps, h, dt_dat
     dts, dtc = torch.zeros(n), torch.zeros(n)
     vlen = torch.tensor(12 * dt_data, dtype=torch.float32)
     ar = torch.arange(n)
+    pol_states, pol_ti = torch.zeros(n, steps, 12), torch.zeros(n, steps, dtype=torch.long)
     for i in range(steps):
         if not bool(alive.any()):
             break
         tgt = targets[ar, ti].float()
+        pol_states[alive, i] = obs[alive]
+        pol_ti[alive, i] = ti[alive]
         normed = ((obs - mean) / std)[:, 3:]                                      # dataset.py:336
         rel = tgt - obs[:, :3]
         unit = rel / torch.sqrt((rel ** 2).sum(dim=1, keepdim=True))
@@ -664,8 +668,11 @@ def eval_fly_to_points(params, targets, init_states, mean, std, steps, h, dt_dat
     maxed = alive & (n_steps == steps)                                             # :130-132
     dts = dts + torch.where(maxed, torch.full((n,), float(thresh_div)), torch.zeros(n))
     dtc = dtc + maxed.float()
-    return dict(states=states, div_linear=div_lin, actions=actions, n_steps=n_steps, div_target_sum=dts,
-                div_target_cnt=dtc)
+    out = dict(states=states, div_linear=div_lin, actions=actions, n_steps=n_steps, div_target_sum=dts,
+               div_target_cnt=dtc)
+    if record_policy_inputs:
+        out.update(policy_states=pol_states, target_index=pol_ti)
+    return out
 
 
 # --------------------------------------------------------------------------------------------

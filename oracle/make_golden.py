@@ -312,6 +312,66 @@ def make_wing_eval_golden(args):
     np.savez_compressed(os.path.join(args.out, "eval_wing.npz"), **npify(out))
 
 
+def make_wing_selfplay_golden(args):
+    """eval_wing_selfplay.npz: the self-play feed of the fixed-wing evaluation (FixedWingNetWrapper.predict_actions,
+    controllers/network_wrapper.py:81-98 -> DroneDataset.get_and_add_eval_data): ONE controller (take_every_x = 11,
+    counter running on) flies three target lists one after the other; the raw (state, target) pairs handed to the
+    dataset for the kept calls are recorded, and the dataset's slots afterwards (2 sampled rows + 4 slots)."""
+    import json
+    import torch
+    cwd = os.getcwd()
+    os.chdir(args.ref)
+    import evaluate_fixed_wing as EF
+    from neural_control.environments.wing_env import SimpleWingEnv
+    from neural_control.dynamics.fixed_wing_dynamics import FixedWingDynamics
+    from neural_control.controllers.network_wrapper import FixedWingNetWrapper
+    from neural_control.dataset import WingDataset
+    net = torch.load('trained_models/wing/current_model/model_wing', weights_only=False)
+    net.eval()
+    cfg = json.load(open('trained_models/wing/current_model/config.json'))
+    h = cfg["horizon"]
+    take, n_sampled, n_slots = 11, 2, 4
+    ds = WingDataset.__new__(WingDataset)
+    ds.dt, ds.horizon = cfg["delta_t"], h
+    ds.mean, ds.std = torch.tensor(cfg["mean"]).float(), torch.tensor(cfg["std"]).float()
+    ds.num_sampled_states, ds.num_self_play, ds.eval_counter = n_sampled, n_slots, 0
+    tot = n_sampled + n_slots
+    ds.normed_states, ds.states = torch.zeros(tot, 9), torch.zeros(tot, 12)
+    ds.in_ref_states, ds.ref_states = torch.zeros(tot, 3), torch.zeros(tot, h, 3)
+    kept_states, kept_targets = [], []
+    real = ds.get_and_add_eval_data
+
+    def recording(st, rf, add_to_dataset=False):
+        if add_to_dataset:
+            kept_states.append(np.array(st, dtype=np.float64).copy())
+            kept_targets.append(np.array(rf, dtype=np.float64).copy())
+        return real(st, rf, add_to_dataset=add_to_dataset)
+    ds.get_and_add_eval_data = recording
+    ctrl = FixedWingNetWrapper(net, ds, horizon=h, take_every_x=take)
+    out = {"cfg": np.array([h, cfg["delta_t"], cfg["dt"], take, n_sampled, n_slots], dtype=np.float64)}
+    # (name, targets, max_steps, thresh_div, thresh_stable)
+    runs = [("a", [[30., 2., -2.], [60., -4., 1.]], 300, 4.0, 0.4), ("b", [[50., -3., 3.]], 300, 4.0, 0.4),
+            ("c", [[50., 8., -8.]], 120, 0.25, 0.4)]
+    for name, targets, steps, tdiv, tstab in runs:
+        env = SimpleWingEnv(FixedWingDynamics(), cfg["dt"])
+        ev = EF.FixedWingEvaluator(ctrl, env, dt=cfg["dt"], horizon=h, thresh_div=tdiv, thresh_stable=tstab,
+                                   test_time=0)
+        div_target, div_linear = ev.fly_to_point(np.array(targets), max_steps=steps)
+        out[f"{name}_targets"] = np.array(targets)
+        out[f"{name}_cfg"] = np.array([steps, tdiv, tstab], dtype=np.float64)
+        out[f"{name}_n_steps"] = np.array([len(div_linear)])
+        print("wing selfplay", name, "steps", len(div_linear), "kept so far", len(kept_states))
+    out["run_names"] = np.array([r[0] for r in runs])
+    out["kept_states"] = np.asarray(kept_states).reshape(len(kept_states), 12)
+    out["kept_targets"] = np.asarray(kept_targets).reshape(len(kept_targets), 3)
+    out["action_counter"] = np.array([ctrl.action_counter])
+    out["eval_counter"] = np.array([ds.eval_counter])
+    out["ds_states"], out["ds_normed_states"] = ds.states, ds.normed_states
+    out["ds_in_ref_states"], out["ds_ref_states"] = ds.in_ref_states, ds.ref_states
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(args.out, "eval_wing_selfplay.npz"), **npify(out))
+
+
 def make_cartpole_eval_golden(args):
     """eval_cartpole.npz: Evaluator.evaluate_in_environment (scripts/evaluate_cartpole.py) of the unmodified reference
     with the shipped model_cartpole: the state after every env._step and the success indices.  The reference always
@@ -461,6 +521,7 @@ def main():
     ap.add_argument("--only-wing-eval", action="store_true", help="only (re)generate eval_wing.npz")
     ap.add_argument("--only-cartpole-eval", action="store_true", help="only (re)generate eval_cartpole.npz")
     ap.add_argument("--only-selfplay", action="store_true", help="only (re)generate eval_selfplay.npz")
+    ap.add_argument("--only-wing-selfplay", action="store_true", help="only (re)generate eval_wing_selfplay.npz")
     ap.add_argument("--only-ref-table", action="store_true", help="only (re)generate ref_table.npz")
     ap.add_argument("--only-poly-traj", action="store_true", help="only (re)generate poly_traj.npz")
     ap.add_argument("--only-learnt", action="store_true", help="only (re)generate learnt_dyn.npz")
@@ -484,6 +545,9 @@ def main():
         return
     if args.only_ref_table:
         make_ref_table_golden(args)
+        return
+    if args.only_wing_selfplay:
+        make_wing_selfplay_golden(args)
         return
     if args.only_poly_traj:
         make_poly_traj_golden(args)

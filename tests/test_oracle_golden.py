@@ -351,3 +351,36 @@ def test_eval_selfplay_feed_matches_reference_dataset():
     for slot, s in final.items():                                    # dataset `states`: position zeroed
         assert np.abs(s[3:] - g["ds_states"][slot, 3:]).max() <= 5e-6 and np.abs(g["ds_states"][slot, :3]).max() == 0
     assert counter == int(g["eval_counter"][0]) and sorted(final) == list(range(int(n_sampled), int(n_sampled + n_slots)))
+
+
+def _wing_selfplay_runs(g):
+    params = [torch.tensor(load_golden("eval_wing.npz")[f"param_{i}"]) for i in range(14)]
+    h, dt_data, dt_env, take, n_sampled, n_slots = [float(v) for v in g["cfg"]]
+    gw = load_golden("eval_wing.npz")
+    for name in [str(v) for v in g["run_names"]]:
+        steps, tdiv, tstab = g[f"{name}_cfg"]
+        init = torch.zeros(1, 12)
+        init[0, 3] = 11.5
+        targets = torch.tensor(g[f"{name}_targets"], dtype=torch.float32)[None]
+        yield (name, params, targets, init, gw["mean"], gw["std"], int(steps), int(h), dt_data, dt_env, float(tdiv),
+               float(tstab))
+
+
+def test_eval_wing_selfplay_feed_matches_reference_dataset():
+    """FixedWingNetWrapper.predict_actions -> get_and_add_eval_data(add_to_dataset=True) (network_wrapper.py:81-90):
+    three flights with one running action counter, take_every_x = 11; kept (state, target) pairs incl. the target
+    switch of the two-target flight and states shown right after a reset"""
+    g = load_golden("eval_wing_selfplay.npz")
+    take = int(g["cfg"][3])
+    ac, ks, kt = 0, [], []
+    for name, params, targets, init, mean, std, steps, h, dt_data, dt_env, tdiv, tstab in _wing_selfplay_runs(g):
+        out = O.eval_fly_to_points(params, targets, init, mean, std, steps, h, dt_data, dt_env, tdiv, tstab, 0,
+                                   record_policy_inputs=True)
+        assert int(out["n_steps"][0]) == int(g[f"{name}_n_steps"][0])
+        kept, ac = O.selfplay_kept_calls(out["n_steps"], take, ac)
+        ks += [out["policy_states"][r, i].numpy() for r, i in kept]
+        kt += [targets[r, int(out["target_index"][r, i])].numpy() for r, i in kept]
+    assert ac == int(g["action_counter"][0]) and len(ks) == int(g["eval_counter"][0])
+    assert np.abs(np.array(kt) - g["kept_targets"]).max() == 0
+    assert len({tuple(t) for t in g["kept_targets"][:9]}) == 2                   # both targets of flight "a" occur
+    assert np.abs(np.array(ks) - g["kept_states"]).max() <= 2e-5 * np.abs(g["kept_states"]).max()

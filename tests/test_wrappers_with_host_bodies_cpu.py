@@ -633,3 +633,72 @@ def test_quad_evaluator_loads_tables_like_random_reference(hostlib, monkeypatch,
     want = g["a_table"].copy()
     want[:, 2] += 3
     assert tuple(tabs.shape) == (3,) + want.shape and np.abs(tabs[1].numpy() - want).max() <= 3e-6
+
+
+def test_wing_selfplay_feed_matches_reference_dataset(hostlib, monkeypatch):
+    """fixed-wing evaluation -> self-play slots (network_wrapper.py:81-90, dataset.py:98-119): the three flights of
+    tests/golden/eval_wing_selfplay.npz through FixedWingEvaluator.fly_to_points (host-compiled kernel logic) with
+    ONE controller / dataset, against what the reference's wrapper + dataset hold afterwards"""
+    from apg_trajectory_tracking_b200.scripts import evaluate_fixed_wing as EF
+    from apg_trajectory_tracking_b200.neural_control.dynamics.fixed_wing_dynamics import FixedWingDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments.wing_env import SimpleWingEnv
+    from apg_trajectory_tracking_b200.neural_control.models import hutter_model as HM
+    NW = _single_drone_mirrors_on_cpu(monkeypatch)
+    g, gw = load_golden("eval_wing_selfplay.npz"), load_golden("eval_wing.npz")
+    h, dt_data, dt_env, take, n_sampled, n_slots = [float(v) for v in g["cfg"]]
+    h, take, n_sampled, n_slots = int(h), int(take), int(n_sampled), int(n_slots)
+    net = HM.Net(9, 1, 3, 4 * h, conv=False)
+    with torch.no_grad():
+        for i, p in enumerate(net.parameters()):
+            p.copy_(torch.tensor(gw[f"param_{i}"]))
+    tot = n_sampled + n_slots
+    ds = DS.WingDataset(np.zeros((tot, 12)), np.ones((tot, 3)), mean=gw["mean"], std=gw["std"], delta_t=dt_data,
+                        horizon=h, self_play=n_slots / n_sampled)
+    assert ds.num_sampled_states == n_sampled and ds.num_self_play == n_slots
+    ctrl = NW.FixedWingNetWrapper(net, ds, horizon=h, take_every_x=take)
+    recorded = []
+    real = ds.get_and_add_eval_data
+
+    def recording(st, rf, add_to_dataset=False):
+        if add_to_dataset:
+            recorded.append((np.array(st), np.array(rf)))
+        return real(st, rf, add_to_dataset=add_to_dataset)
+    ds.get_and_add_eval_data = recording
+    for name in [str(v) for v in g["run_names"]]:
+        steps, tdiv, tstab = g[f"{name}_cfg"]
+        ev = EF.FixedWingEvaluator(ctrl, SimpleWingEnv(FixedWingDynamics(), dt_env), dt=dt_env, horizon=h,
+                                   thresh_div=float(tdiv), thresh_stable=float(tstab), test_time=0)
+        out = ev.fly_to_points(g[f"{name}_targets"][None], max_steps=int(steps))
+        assert int(out["n_steps"][0]) == int(g[f"{name}_n_steps"][0])
+    assert ctrl.action_counter == int(g["action_counter"][0]) and ds.eval_counter == int(g["eval_counter"][0])
+    ks, kt = np.array([r[0] for r in recorded]), np.array([r[1] for r in recorded])
+    assert np.abs(kt - g["kept_targets"]).max() <= 1e-6
+    assert np.abs(ks - g["kept_states"]).max() <= 1e-4 * np.abs(g["kept_states"]).max()
+    # the ring afterwards (the reference stores the prepared tensors of each kept sample)
+    sl = slice(n_sampled, tot)
+    assert np.abs(ds.states[sl].numpy() - g["ds_states"][sl]).max() <= 1e-4 * np.abs(g["ds_states"]).max()
+    assert np.abs(ds.normed_states[sl].numpy() - g["ds_normed_states"][sl]).max() <= 5e-4
+    assert np.abs(ds.ref_states[sl].numpy() - g["ds_ref_states"][sl]).max() <= 1e-4 * np.abs(g["ds_ref_states"]).max()
+
+
+def test_wing_selfplay_samples_batched_selection_matches_sequential_runs():
+    gw = load_golden("eval_wing.npz")
+    params = [torch.tensor(gw[f"param_{i}"]) for i in range(14)]
+    h, dt_data, dt_env = int(gw["cfg"][0]), float(gw["cfg"][1]), float(gw["cfg"][2])
+    n, K, steps = 6, 3, 160
+    gen = torch.Generator().manual_seed(2)
+    targets = torch.zeros(n, K, 3)
+    for k, x in enumerate((20.0, 40.0, 62.0)):
+        targets[:, k] = torch.tensor([x, 0, 0]) + (torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([4.0, 6, 6])
+    init = torch.zeros(n, 12)
+    init[:, 3] = 11.5
+    out = O.eval_fly_to_points(params, targets, init, gw["mean"], gw["std"], steps, h, dt_data, dt_env, 2.0, 0.4, 0,
+                               record_policy_inputs=True)
+    assert int(out["target_index"].max()) == K - 1                       # flights that switch targets twice
+    for take, ac in ((3, 0), (7, 5), (10000, 0)):
+        kept, after = O.selfplay_kept_calls(out["n_steps"], take, ac)
+        s, tg, counter = EV.wing_selfplay_samples(out, targets, take, ac)
+        assert counter == after and s.shape[0] == len(kept)
+        if kept:
+            assert torch.equal(s, torch.stack([out["policy_states"][j, i] for j, i in kept]))
+            assert torch.equal(tg, torch.stack([targets[j, int(out["target_index"][j, i])] for j, i in kept]))
