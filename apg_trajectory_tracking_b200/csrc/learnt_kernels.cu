@@ -165,7 +165,8 @@ cudaError_t launch_learnt_fwd(int system, const float* params, const PhysConsts&
 cudaError_t launch_learnt_adj(int system, const float* params, const PhysConsts& pc, const float* s, const float* a,
                               float dt, int n, const float* g, float* gs, float* ga, float* grad_params,
                               float* partials, int sms, cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
+  if (n <= 0)                                   // empty batch: the parameter gradient is zero, not "untouched"
+    return grad_params ? cudaMemsetAsync(grad_params, 0, sizeof(float) * learnt_num_params(system), st) : cudaSuccess;
   if (system == SYS_QUAD)
     return launch_adj_t<LearntQuad<float>>(params, pc, s, a, dt, n, g, gs, ga, grad_params, partials, sms, st);
   if (system == SYS_WING)
