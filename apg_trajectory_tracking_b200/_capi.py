@@ -17,6 +17,11 @@ class ApgConfig(ctypes.Structure):
                 ("dt", ctypes.c_float), ("phys", ctypes.c_float * MAX_PHYS)]
 
 
+class ApgGradComm(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("slot_ptrs", ctypes.c_void_p),
+                ("flag_ptrs", ctypes.c_void_p), ("epoch", ctypes.c_uint), ("ticket", ctypes.c_void_p)]
+
+
 EXPORTS = {
     "apg_version": (ctypes.c_int, []),
     "apg_sm_count": (ctypes.c_int, []),
@@ -28,6 +33,14 @@ EXPORTS = {
     "apg_rollout_backward": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p,
                              ctypes.c_float, c_float_p, ctypes.c_void_p]),
     "apg_rollout_value_and_grad_host": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 8),
+    "apg_grad_comm_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "apg_grad_comm_offsets": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "apg_rollout_backward_p2p": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p,
+                                 ctypes.c_float, ctypes.POINTER(ApgGradComm), ctypes.c_void_p]),
+    "apg_grad_gather_sgd_p2p": (ctypes.c_int, [ctypes.POINTER(ApgGradComm), ctypes.c_void_p, ctypes.c_int, c_float_p,
+                                               c_float_p, c_float_p, ctypes.c_float, ctypes.c_float,
+                                               ctypes.c_void_p]),
     "apg_dynamics_step": (ctypes.c_int, [ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_float, ctypes.c_int,
                                          c_float_p, ctypes.c_void_p]),
     "apg_dynamics_step_adjoint": (ctypes.c_int, [ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_float,

@@ -365,13 +365,33 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
   return 0;
 }
 
-__attribute__((visibility("default"))) int apg_rollout_backward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
-                         const float* in_ref, const float* ref, const float* h0c0, void* workspace, float grad_loss,
-                         float* grad_params, void* stream) {
+}  // extern "C"
+
+namespace {
+// gradient reduction that ends the adjoint pass: into `grad_params` (default), or - `comm` given - straight into
+// every rank's receive slot over peer memory (p2p_kernels.cu)
+cudaError_t finish_gradient(const float* partials, int ncta, int n, float scale, float* grad_params,
+                            const apg_grad_comm* comm, int pm_off, int pm_k1, int pm_npos, bool sliced,
+                            cudaStream_t st) {
+  if (comm)
+    return launch_reduce_scatter_p2p(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
+                                     static_cast<float* const*>(comm->slot_ptrs),
+                                     static_cast<unsigned* const*>(comm->flag_ptrs), comm->rank, comm->world,
+                                     comm->epoch, static_cast<unsigned*>(comm->ticket), st);
+  if (sliced) return launch_reduce_grad4(partials, ncta, n, scale, grad_params, st);
+  return launch_reduce_grad(partials, ncta, n, scale, grad_params, st, pm_off, pm_k1, pm_npos);
+}
+
+int rollout_backward_impl(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                          const float* in_ref, const float* ref, const float* h0c0, void* workspace, float grad_loss,
+                          float* grad_params, const apg_grad_comm* comm, void* stream) {
   int e = check_config(cfg);
   if (e) return e;
   if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, workspace))) return e;
-  if (!grad_params) return APG_ERR_BAD_CONFIG;
+  if (!grad_params && !comm) return APG_ERR_BAD_CONFIG;
+  if (comm && (!comm->slot_ptrs || !comm->flag_ptrs || !comm->ticket || comm->world < 1 || comm->rank < 0 ||
+               comm->rank >= comm->world))
+    return APG_ERR_BAD_CONFIG;
   if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const NetInfo ni = net_info(cfg);
@@ -397,7 +417,8 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
       } else if ((ce = launch_hutter_adj_dx(cfg->system, y, a, z, p.grid, st))) return (int)ce;
       if ((ce = launch_adj_dw_tc(y, a, z, p.grid, st))) return (int)ce;
       // the partials are already in torch column order: plain sliced reduction
-      if ((ce = launch_reduce_grad4(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st))) return (int)ce;
+      if ((ce = finish_gradient(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, comm, 0, 0, 0, true, st)))
+        return (int)ce;
       return 0;
     }
     else if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
@@ -411,9 +432,56 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
     const HutterLayout y = hutter_layout(cfg);
     pm_off = y.t_w1; pm_k1 = y.K1; pm_npos = y.perm_npos;
   }
-  if ((ce = launch_reduce_grad(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, st, pm_off, pm_k1, pm_npos)))
+  if ((ce = finish_gradient(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, comm, pm_off, pm_k1, pm_npos,
+                            false, st)))
     return (int)ce;
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) int apg_rollout_backward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                         const float* in_ref, const float* ref, const float* h0c0, void* workspace, float grad_loss,
+                         float* grad_params, void* stream) {
+  if (!grad_params) return APG_ERR_BAD_CONFIG;
+  return rollout_backward_impl(cfg, params, in_state, cur, in_ref, ref, h0c0, workspace, grad_loss, grad_params,
+                               nullptr, stream);
+}
+
+// ---- the gradient all-reduce as this library's own kernels over NVLink peer memory (p2p_kernels.cu, p2p_math.cuh)
+__attribute__((visibility("default"))) size_t apg_grad_comm_bytes(int world, int n_params) {
+  if (world < 1 || n_params < 1) return 0;
+  GradCommLayout L{world, n_params};
+  return sizeof(float) * L.total_floats();
+}
+
+__attribute__((visibility("default"))) int apg_grad_comm_offsets(int world, int n_params, int set, size_t* slots_offset_bytes, size_t* flags_offset_bytes) {
+  if (world < 1 || n_params < 1 || set < 0 || set > 1 || !slots_offset_bytes || !flags_offset_bytes)
+    return APG_ERR_BAD_CONFIG;
+  GradCommLayout L{world, n_params};
+  *slots_offset_bytes = sizeof(float) * L.slot_off(set, 0);
+  *flags_offset_bytes = sizeof(float) * L.flag_off(set, 0);
+  return 0;
+}
+
+__attribute__((visibility("default"))) int apg_rollout_backward_p2p(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                             const float* in_ref, const float* ref, const float* h0c0, void* workspace,
+                             float grad_loss, const apg_grad_comm* comm, void* stream) {
+  if (!comm) return APG_ERR_BAD_CONFIG;
+  return rollout_backward_impl(cfg, params, in_state, cur, in_ref, ref, h0c0, workspace, grad_loss, nullptr, comm,
+                               stream);
+}
+
+__attribute__((visibility("default"))) int apg_grad_gather_sgd_p2p(const apg_grad_comm* comm, const void* local_set, int n_params, float* grad_out,
+                            float* params, float* momentum_buf, float lr, float momentum, void* stream) {
+  if (!comm || !local_set || n_params < 1 || comm->world < 1) return APG_ERR_BAD_CONFIG;
+  if (params && !momentum_buf) return APG_ERR_BAD_CONFIG;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  const float* slots = static_cast<const float*>(local_set);
+  const unsigned* flags = reinterpret_cast<const unsigned*>(slots + (size_t)comm->world * n_params);
+  return (int)launch_gather_sgd_p2p(slots, flags, comm->world, n_params, comm->epoch, grad_out, params, momentum_buf,
+                                    lr, momentum, static_cast<cudaStream_t>(stream));
 }
 
 __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const apg_config* cfg, const float* params_host, const float* in_state_host,

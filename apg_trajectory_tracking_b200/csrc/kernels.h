@@ -4,6 +4,7 @@
 #include "layouts.h"
 #include "rollout_args.h"
 #include "eval_math.cuh"
+#include "p2p_math.cuh"
 
 namespace apg {
 
@@ -41,6 +42,13 @@ cudaError_t launch_simple_adj(const SimpleLayout& y, const RolloutArgs& a, int g
 cudaError_t launch_pack(const PackTable& t, const float* params, float* wf, float* wb, cudaStream_t st);
 cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st,
                                int pm_off = 0, int pm_k1 = 0, int pm_npos = 0);
+// gradient reduction + exchange over NVLink peer memory (p2p_kernels.cu; layout and protocol: p2p_math.cuh)
+cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, float scale, int pm_off, int pm_k1,
+                                      int pm_npos, float* const* slots, unsigned* const* flags, int rank, int world,
+                                      unsigned epoch, unsigned* ticket, cudaStream_t st);
+cudaError_t launch_gather_sgd_p2p(const float* slots_local, const unsigned* flags_local, int world, int n,
+                                  unsigned epoch, float* grad_out, float* param, float* momentum_buf, float lr,
+                                  float momentum, cudaStream_t st);
 cudaError_t launch_sum_loss(const float* partials, int ncta, float* loss, cudaStream_t st);
 cudaError_t launch_step(int system, const PhysConsts& pc, const float* s, const float* a, float dt, int n, float* out,
                         cudaStream_t st);

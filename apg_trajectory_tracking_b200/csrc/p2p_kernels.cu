@@ -1,0 +1,94 @@
+// The path's collective as this package's own kernels over NVLink peer memory (OPTIONAL, APG_P2P_GRAD=1 in the Python
+// layer; default: NCCL all-reduce).  Protocol and memory layout: p2p_math.cuh.
+//
+//   apg_reduce_scatter_p2p_kernel   the gradient reduction that ends the adjoint pass (sum of the per-CTA partials in
+//       fixed order) with its result stored straight into slot `rank` of every rank's receive set (coalesced 4-byte
+//       stores through the peer mappings); the last CTA to finish raises this rank's flag on every peer.
+//   apg_gather_sgd_p2p_kernel       waits for the `world` flags of the local set, sums the slots in rank order and, if
+//       asked, applies the SGD-momentum update in the same pass (replaces the all-reduce AND the two optimizer
+//       launches).  The wait is bounded (~10 s of SM clocks; ranks that iterate together are microseconds apart):
+//       a lost peer poisons the gradient with NaN instead of hanging the GPU.
+#include "p2p_math.cuh"
+#include "kernels.h"
+
+namespace apg {
+
+namespace {
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+}  // namespace
+
+__global__ void apg_reduce_scatter_p2p_kernel(const float* __restrict__ partials, int ncta, int n, float scale,
+                                              int pm_off, int pm_k1, int pm_npos, float* const* __restrict__ slots,
+                                              unsigned* const* __restrict__ flags, int rank, int world,
+                                              unsigned epoch, unsigned* __restrict__ ticket) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) {
+    const float v = p2p_reduce_entry(partials, ncta, n, p2p_partial_column(p, pm_off, pm_k1, pm_npos), scale);
+    for (int q = 0; q < world; ++q) slots[q][(size_t)rank * n + p] = v;
+  }
+  __threadfence_system();                       // this thread's peer stores are ordered before the barrier ...
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                     // ... and the CTA's stores before its ticket (cumulative fence)
+    const unsigned t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {                   // every CTA's stores have been fenced: signal all peers
+      *ticket = 0u;                             // ready for the next launch (stream order)
+      __threadfence_system();
+      for (int q = 0; q < world; ++q) st_release_sys(flags[q] + rank, epoch);
+    }
+  }
+}
+
+__global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local, const unsigned* __restrict__ flags_local,
+                                          int world, int n, unsigned epoch, float* __restrict__ grad_out,
+                                          float* __restrict__ param, float* __restrict__ momentum_buf, float lr,
+                                          float momentum) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    int ok = 1;
+    const long long t0 = clock64();
+    for (int q = 0; q < world && ok; ++q) {
+      // flags only grow; (int)(flag - epoch) >= 0 also survives the 32-bit wrap of the step counter
+      while ((int)(ld_acquire_sys(flags_local + q) - epoch) < 0) {
+        if (clock64() - t0 > 20000000000LL) { ok = 0; break; }
+      }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float g = 0.f;
+  if (s_ok) {
+    for (int q = 0; q < world; ++q) g += __ldcg(slots_local + (size_t)q * n + p);    // L2: where the peers' stores land
+  } else {
+    g = __int_as_float(0x7fc00000);
+  }
+  if (grad_out) grad_out[p] = g;
+  if (param) p2p_sgd_entry(g, lr, momentum, momentum_buf + p, param + p);
+}
+
+cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, float scale, int pm_off, int pm_k1,
+                                      int pm_npos, float* const* slots, unsigned* const* flags, int rank, int world,
+                                      unsigned epoch, unsigned* ticket, cudaStream_t st) {
+  apg_reduce_scatter_p2p_kernel<<<(n + 127) / 128, 128, 0, st>>>(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
+                                                                 slots, flags, rank, world, epoch, ticket);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_sgd_p2p(const float* slots_local, const unsigned* flags_local, int world, int n,
+                                  unsigned epoch, float* grad_out, float* param, float* momentum_buf, float lr,
+                                  float momentum, cudaStream_t st) {
+  apg_gather_sgd_p2p_kernel<<<(n + 127) / 128, 128, 0, st>>>(slots_local, flags_local, world, n, epoch, grad_out, param,
+                                                             momentum_buf, lr, momentum);
+  return cudaGetLastError();
+}
+
+}  // namespace apg

@@ -137,6 +137,15 @@ class Rollout:
                                                       self._stream()))
         return out
 
+    def backward_p2p(self, comm, grad_loss=1.0):
+        """Adjoint of the last forward() whose final gradient reduction stores its result into every rank's receive
+        slot over peer memory (``dist.PeerGradExchange.next_step()`` gives ``comm``); complete the step with
+        ``PeerGradExchange.gather``."""
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.apg_rollout_backward_p2p(ctypes.byref(self.cfg), *[_ptr(x) for x in self._inputs],
+                                                          self._ws_ptr, ctypes.c_float(float(grad_loss)),
+                                                          ctypes.byref(comm), self._stream()))
+
     def value_and_grad(self, params_flat, in_state, cur, in_ref=None, ref=None, h0c0=None, out=None):
         loss, _, _ = self.forward(params_flat, in_state, cur, in_ref, ref, h0c0)
         return loss, self.backward(1.0, out=out)

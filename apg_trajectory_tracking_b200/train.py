@@ -10,6 +10,8 @@ as two kernel launches (+ pack / reduce helpers) on a flat parameter vector.  Ba
 drone axis; the only collective is one sum-allreduce of the flat gradient (the loss is a sum over drones,
 drone_loss.py:22-33, so the summed gradient equals the single-device large-batch gradient).
 """
+import os
+
 import torch
 
 from . import _capi, prepare as PR, rollout as R, synthetic as _syn
@@ -40,8 +42,10 @@ class HostLoss:
 
 class FusedTrainStep:
     def __init__(self, params, spec: R.RolloutSpec, n_drones: int, lr: float, momentum: float = 0.9, device=None,
-                 process_group=None, distributed=None):
-        """params: iterable of tensors in net.parameters() order (or an nn.Module)."""
+                 process_group=None, distributed=None, peer_exchange=None):
+        """params: iterable of tensors in net.parameters() order (or an nn.Module).  ``peer_exchange`` (default: the
+        environment variable APG_P2P_GRAD == "1"): with more than one rank, exchange the gradient with this
+        package's own kernels over NVLink peer memory (``dist.PeerGradExchange``) instead of an NCCL all-reduce."""
         if isinstance(params, torch.nn.Module):
             params = list(params.parameters())
         self.like = [p.detach() for p in params]
@@ -60,6 +64,13 @@ class FusedTrainStep:
                 torch.distributed.get_world_size(process_group) > 1
         self.distributed = distributed
         self.kernel_launches_per_step = 5      # pack, forward, loss-sum, adjoint, grad-reduce
+        if peer_exchange is None:
+            peer_exchange = os.environ.get("APG_P2P_GRAD") == "1"
+        self.peer = None
+        if peer_exchange and self.distributed:
+            from . import dist as D
+            self.peer = D.PeerGradExchange(self.runner.n_params, self.device, process_group)
+            self.kernel_launches_per_step = 6  # + the gather / SGD kernel (the exchange rides on the grad-reduce)
 
     def _dev(self, x):
         if x is None:
@@ -69,14 +80,31 @@ class FusedTrainStep:
         return x
 
     def value_and_grad(self, in_state, cur, in_ref=None, ref=None, h0c0=None):
+        if self.peer is not None:
+            loss = self._forward_and_scatter(in_state, cur, in_ref, ref, h0c0)
+            self.peer.gather(*self._peer_step, grad_out=self.grad)
+            return loss, self.grad
         loss, _ = self.runner.value_and_grad(self.flat, self._dev(in_state), self._dev(cur), self._dev(in_ref),
                                              self._dev(ref), self._dev(h0c0), out=self.grad)
         if self.distributed:
             torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
         return loss, self.grad
 
+    def _forward_and_scatter(self, in_state, cur, in_ref, ref, h0c0):
+        loss, _, _ = self.runner.forward(self.flat, self._dev(in_state), self._dev(cur), self._dev(in_ref),
+                                         self._dev(ref), self._dev(h0c0))
+        self._peer_step = self.peer.next_step()
+        self.runner.backward_p2p(self._peer_step[0])
+        return loss
+
     def step(self, in_state, cur, in_ref=None, ref=None, h0c0=None):
         """one full train iteration; returns the (local-shard) loss as a 1-element device tensor"""
+        if self.peer is not None:
+            # adjoint + reduction + peer scatter, then ONE kernel: wait, rank-ordered sum, SGD(momentum) update
+            loss = self._forward_and_scatter(in_state, cur, in_ref, ref, h0c0)
+            self.peer.gather(*self._peer_step, grad_out=self.grad, params=self.flat, momentum_buf=self.buf,
+                             lr=self.lr, momentum=self.momentum)
+            return loss
         loss, grad = self.value_and_grad(in_state, cur, in_ref, ref, h0c0)
         # optim.SGD(momentum=0.9): buf = momentum*buf + g ; p -= lr*buf   (first step: buf = g)
         self.buf.mul_(self.momentum).add_(grad)

@@ -351,6 +351,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-raw-e2e", action="store_true", help="skip the raw-sample (step_host) end-to-end arm")
+    ap.add_argument("--p2p-grad", action="store_true",
+                    help="N>1: exchange the gradient with the package's own kernels over NVLink peer memory "
+                         "(APG_P2P_GRAD=1) instead of the NCCL all-reduce")
     ap.add_argument("--tc-forward", action="store_true",
                     help="use the optional tcgen05/TMEM forward kernel (APG_TC_FWD=1; quad_concurrent only)")
     ap.add_argument("--tc-dw", action="store_true",
@@ -370,6 +373,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, w, rank)
         return
+    if args.p2p_grad:
+        os.environ["APG_P2P_GRAD"] = "1"
     if args.tc_forward:
         os.environ["APG_TC_FWD"] = "1"
     if args.tc_dw:
@@ -423,12 +428,21 @@ def main():
         e[0].record()
         loss, _, _ = stepper.runner.forward(stepper.flat, *args_step)
         e[1].record()
-        stepper.runner.backward(1.0, out=stepper.grad)
-        e[2].record()
-        if world > 1:
-            dist.all_reduce(stepper.grad)
-        stepper.buf.mul_(stepper.momentum).add_(stepper.grad)
-        stepper.flat.add_(stepper.buf, alpha=-stepper.lr)
+        if stepper.peer is not None:
+            # adjoint whose gradient reduction scatters into every rank's slot over peer memory, then one kernel:
+            # wait for all ranks, rank-ordered sum, SGD(momentum) update
+            comm, local_set = stepper.peer.next_step()
+            stepper.runner.backward_p2p(comm)
+            e[2].record()
+            stepper.peer.gather(comm, local_set, grad_out=stepper.grad, params=stepper.flat,
+                                momentum_buf=stepper.buf, lr=stepper.lr, momentum=stepper.momentum)
+        else:
+            stepper.runner.backward(1.0, out=stepper.grad)
+            e[2].record()
+            if world > 1:
+                dist.all_reduce(stepper.grad)
+            stepper.buf.mul_(stepper.momentum).add_(stepper.grad)
+            stepper.flat.add_(stepper.buf, alpha=-stepper.lr)
         e[3].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -535,7 +549,10 @@ def main():
                        if os.environ.get("APG_TC_DW") == "1" and args.workload == "quad_concurrent" else "default (mma.sync)",
                        "policy_init": "torch default init, seed 0", "optimizer": "SGD lr %g momentum 0.9" % LR[w["system"]],
                        "l2": "flushed between timed steps (256 MiB write, untimed)" if flush_buf is not None else "not flushed",
-                       "parallelism": f"dp{world} (drone-axis shards, one NCCL sum-allreduce of the flat gradient)"},
+                       "parallelism": f"dp{world} (drone-axis shards, " + (
+                           "gradient exchanged by apg_reduce_scatter_p2p_kernel / apg_gather_sgd_p2p_kernel over "
+                           "NVLink peer memory)" if stepper.peer is not None else
+                           "one NCCL sum-allreduce of the flat gradient)")},
             "ms_forward_kernel": ms_fwd, "ms_adjoint_kernel": ms_adj, "wall_s_timed_region": t_wall,
             "final_loss": final_loss,
             "roofline": {"bound": "hbm", "kernel": f"adjoint ({kname} + apg_reduce_kernel)", "achieved": achieved,

@@ -195,6 +195,36 @@ int apg_learnt_step_adjoint(int system, const float* params, const float* phys, 
                             float dt, int n, const float* grad_out, float* grad_state, float* grad_action,
                             float* grad_params, void* workspace, void* stream);
 
+/* ---- the path's one collective (sum of the flat weight gradient over the drone-axis shards) as this
+ * library's own kernels over NVLink peer memory, instead of a library all-reduce after the adjoint pass:
+ *   apg_rollout_backward_p2p   = apg_rollout_backward whose final gradient reduction stores its result straight into
+ *                                slot `rank` of EVERY rank's receive set (peer-mapped symmetric memory) and raises
+ *                                this rank's flag there (one kernel: reduction + exchange);
+ *   apg_grad_gather_sgd_p2p    waits for all `world` flags of the local set, sums the slots in rank order (bitwise
+ *                                identical on every rank) into grad_out (may be NULL) and, when `params` is given,
+ *                                applies torch.optim.SGD's momentum update in the same pass
+ *                                (scripts/train_base.py:139-143: buf = momentum*buf + g; p -= lr*buf).
+ * Symmetric buffer of apg_grad_comm_bytes(world, n_params) bytes per rank, zero-initialised, mapped on all ranks
+ * (e.g. torch.distributed._symmetric_memory); two sets used by alternate steps, set = epoch & 1, at the byte offsets
+ * apg_grad_comm_offsets returns.  comm->slot_ptrs / flag_ptrs: DEVICE arrays of `world` pointers, entry q = rank q's
+ * slots / flags of the current set; comm->epoch = step number 1, 2, ... (the same on every rank); comm->ticket: a
+ * local device word, zero before the first call.  `local_set`: this rank's own current set.  The wait is bounded:
+ * a missing peer yields a NaN gradient, not a hang. */
+typedef struct apg_grad_comm {
+  int rank, world;
+  void* slot_ptrs;
+  void* flag_ptrs;
+  unsigned epoch;
+  void* ticket;
+} apg_grad_comm;
+size_t apg_grad_comm_bytes(int world, int n_params);
+int apg_grad_comm_offsets(int world, int n_params, int set, size_t* slots_offset_bytes, size_t* flags_offset_bytes);
+int apg_rollout_backward_p2p(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                             const float* in_ref, const float* ref, const float* h0c0, void* workspace,
+                             float grad_loss, const apg_grad_comm* comm, void* stream);
+int apg_grad_gather_sgd_p2p(const apg_grad_comm* comm, const void* local_set, int n_params, float* grad_out,
+                            float* params, float* momentum_buf, float lr, float momentum, void* stream);
+
 int apg_sm_count(void);
 int apg_version(void);
 const char* apg_error_string(int code);

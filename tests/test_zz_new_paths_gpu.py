@@ -837,3 +837,24 @@ def test_tc2_forward_matches_default_forward(n):
                                    ("APG_TC_DW", "APG_TC_DX", "APG_TC_FWD")])
 def test_tc3_combined_tcgen05_paths(n, flags):
     _check_split_adjoint(n, flags)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the gradient exchange over NVLink peer memory (optional path, needs 2 GPUs; opt-in like the tcgen05 tests until its
+# first hardware run):  APG_TEST_P2P=1 python -m pytest tests/test_zz_new_paths_gpu.py -k p2p
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("APG_TEST_P2P") != "1",
+                    reason="needs 2 GPUs and APG_TEST_P2P=1 (first hardware run pending)")
+def test_tc3_p2p_gradient_exchange_matches_nccl():
+    import json
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_p2p_check.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", script], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["finite"] and res["p2p_params_bitwise_equal_across_ranks"], res
+    assert res["grad_rel_diff_vs_nccl"] <= 1e-6 and res["params_rel_diff_vs_nccl"] <= 1e-6, res
+    assert res["loss_rel_diff_vs_nccl"] <= 1e-6, res
