@@ -4,8 +4,9 @@
   (N,15) policy features, differentiable, one CUDA kernel forward / one backward (csrc/apg_math.cuh ``Quad::features``).
 * ``QuadDataset`` / ``WingDataset`` / ``CartpoleDataset``: the HOST-side containers that turn raw (state, reference)
   samples into the four tensors of a train batch -- ``(in_state, current_state, in_ref_state, ref_states)`` -- with the
-  reference's layouts (``prepare_data`` :155-204 and :326-350).  Like in the reference they live in CPU memory (data
-  preparation, not rollout math); the train step copies each batch to the GPU.  The reference's constructors sample
+  reference's layouts (``prepare_data`` :155-204 and :326-350).  Like in the reference they live in CPU memory by
+  default (data preparation, not rollout math; the train step copies each batch to the GPU); with ``device=`` a CUDA
+  device their ``prepare_data`` is the device kernels of ``prepare.py`` and the prepared tensors stay in HBM.  The reference's constructors sample
   their data from its environments / trajectory files, which are outside the scope of this package: here the raw
   samples are passed in (``states``, ``ref_states`` arrays), everything downstream is the same.
 """
@@ -13,7 +14,7 @@ import numpy as np
 import torch
 
 from ..ops import quad_features
-from .. import synthetic as _syn
+from .. import prepare as _prep, synthetic as _syn
 
 
 def state_preprocessing(drone_states):
@@ -29,8 +30,12 @@ def _as_tensor(x):
 class DroneDataset(torch.utils.data.Dataset):
     """common container: holds the prepared tensors, hands out 4-tuples, supports replacing samples (self play)"""
 
-    def __init__(self, states, ref_states, mean=None, std=None, self_play=0, **kwargs):
+    def __init__(self, states, ref_states, mean=None, std=None, self_play=0, device=None, **kwargs):
+        """``device``: None (default) keeps the container and its ``prepare_data`` on the host like the reference;
+        a CUDA device makes ``prepare_data`` the device kernels of ``prepare.py`` and keeps the four
+        prepared tensors in HBM, so that batches need no host->device copy."""
         states_np = np.asarray(states, dtype=np.float64)
+        self.device = None if device is None else torch.device(device)
         self.kwargs = kwargs
         self.num_sampled_states = int(len(states_np) / (1 + self_play)) if self_play else len(states_np)
         self.num_self_play = len(states_np) - self.num_sampled_states
@@ -92,6 +97,9 @@ class QuadDataset(DroneDataset):
         cur, ref = _as_tensor(states), _as_tensor(ref_states)
         if cur.dim() == 1:
             cur, ref = cur[None], ref[None]
+        if self.device is not None:
+            out = _prep.prepare_quad(cur.to(self.device), ref.to(self.device))
+            return out["in_state"], out["cur"], out["in_ref"], out["ref"]
         ref[:, :, :3] -= cur[:, None, :3]
         cur[:, :3] = 0
         drone_vel = cur[:, None, 6:9]
@@ -117,6 +125,10 @@ class WingDataset(DroneDataset):
         cur, target = _as_tensor(states), _as_tensor(ref_states)
         if cur.dim() == 1:
             cur, target = cur[None], target[None]
+        if self.device is not None:
+            out = _prep.prepare_wing(cur.to(self.device), target.to(self.device), self.mean, self.std, self.dt,
+                                     self.horizon)
+            return out["in_state"], out["cur"], out["in_ref"], out["ref"]
         normed = ((cur - self.mean) / self.std)[:, 3:]
         rel = target - cur[:, :3]
         unit = rel / rel.norm(dim=1, keepdim=True)

@@ -54,8 +54,10 @@ class TrainBase:
     def init_optimizer(self):
         if self.state_data is not None:
             # pinned batches: the H2D copies of the train step are asynchronous DMA transfers
+            on_host = getattr(self.state_data, "device", None) is None        # device-resident datasets: nothing to pin
             self.trainloader = torch.utils.data.DataLoader(self.state_data, batch_size=self.batch_size, shuffle=True,
-                                                           num_workers=0, pin_memory=torch.cuda.is_available())
+                                                           num_workers=0,
+                                                           pin_memory=torch.cuda.is_available() and on_host)
         spec = T.spec_for_net(self.net, self.system, self.horizon, self.rollout_dt(), self.train_mode, self.window,
                               self.modified_params())
         self.fused = T.ModuleRollout(self.net, spec, self.device)

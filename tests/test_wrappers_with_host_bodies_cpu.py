@@ -702,3 +702,26 @@ def test_wing_selfplay_samples_batched_selection_matches_sequential_runs():
         if kept:
             assert torch.equal(s, torch.stack([out["policy_states"][j, i] for j, i in kept]))
             assert torch.equal(tg, torch.stack([targets[j, int(out["target_index"][j, i])] for j, i in kept]))
+
+
+def test_datasets_with_device_prepare_match_host_containers(hostlib):
+    """QuadDataset / WingDataset(device=...) run prepare_data through the prepare kernels (here: their host-compiled
+    bodies) and must hand out the same 4-tuples as the host containers, self-play slots included"""
+    g = load_golden("prep_data.npz")
+    qs, qr = g["quad_raw_states"], g["quad_raw_refs"]
+    host, dev = DS.QuadDataset(qs, qr, self_play=0.5), DS.QuadDataset(qs, qr, self_play=0.5, device="cpu")
+    assert dev.num_self_play == host.num_self_play > 0
+    for a, b in zip(host[3], dev[3]):
+        assert torch.allclose(a, b, atol=2e-6)
+    for d in (host, dev):
+        d.get_and_add_eval_data(qs[1].copy(), qr[1].copy(), add_to_dataset=True)
+    at = host.num_sampled_states
+    assert torch.allclose(host.states[at], dev.states[at], atol=2e-6) and dev.eval_counter == 1
+    assert torch.allclose(host.in_ref_states[at], dev.in_ref_states[at], atol=2e-6)
+    ws, wt = g["wing_raw_states"], g["wing_targets"]
+    kw = dict(mean=g["wing_mean"], std=g["wing_std"], delta_t=float(g["wing_dt"]), horizon=int(g["wing_h"]))
+    wh, wd = DS.WingDataset(ws, wt, **kw), DS.WingDataset(ws, wt, device="cpu", **kw)
+    for a, b in zip(wh[2], wd[2]):
+        assert torch.allclose(a, b, atol=5e-6)
+    loader = torch.utils.data.DataLoader(dev, batch_size=4, shuffle=False)
+    assert next(iter(loader))[0].shape == (4, 15)
