@@ -97,7 +97,7 @@ class QuadDataset(DroneDataset):
         cur, ref = _as_tensor(states), _as_tensor(ref_states)
         if cur.dim() == 1:
             cur, ref = cur[None], ref[None]
-        if self.device is not None:
+        if getattr(self, "device", None) is not None:
             out = _prep.prepare_quad(cur.to(self.device), ref.to(self.device))
             return out["in_state"], out["cur"], out["in_ref"], out["ref"]
         ref[:, :, :3] -= cur[:, None, :3]
@@ -125,7 +125,7 @@ class WingDataset(DroneDataset):
         cur, target = _as_tensor(states), _as_tensor(ref_states)
         if cur.dim() == 1:
             cur, target = cur[None], target[None]
-        if self.device is not None:
+        if getattr(self, "device", None) is not None:
             out = _prep.prepare_wing(cur.to(self.device), target.to(self.device), self.mean, self.std, self.dt,
                                      self.horizon)
             return out["in_state"], out["cur"], out["in_ref"], out["ref"]
