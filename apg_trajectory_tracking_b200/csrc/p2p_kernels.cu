@@ -22,6 +22,13 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// the slots are written by OTHER GPUs: read them at system scope (no L1, coherent with the peers' stores once the
+// acquire on the flag has been observed)
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 }  // namespace
 
 __global__ void apg_reduce_scatter_p2p_kernel(const float* __restrict__ partials, int ncta, int n, float scale,
@@ -67,7 +74,7 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
   if (p >= n) return;
   float g = 0.f;
   if (s_ok) {
-    for (int q = 0; q < world; ++q) g += __ldcg(slots_local + (size_t)q * n + p);    // L2: where the peers' stores land
+    for (int q = 0; q < world; ++q) g += ld_relaxed_sys(slots_local + (size_t)q * n + p);
   } else {
     g = __int_as_float(0x7fc00000);
   }
