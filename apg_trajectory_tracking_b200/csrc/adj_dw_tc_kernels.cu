@@ -10,9 +10,12 @@
 // the fixed-order reduction over CTAs stays bitwise reproducible).  The kernel is HBM-bound by construction:
 // 3.6 KB per drone.  Layout / index arithmetic: adj_dw_layout.cuh (host-checked).
 #include "adj_dw_layout.cuh"
-#include "tile_engine.cuh"
+#include "tc_prims.cuh"
 #include "rollout_args.h"
+#ifndef APG_TC_SIM
+#include "tile_engine.cuh"
 #include "kernels.h"
+#endif
 
 namespace apg {
 
@@ -25,45 +28,25 @@ constexpr int DW_THREADS = DW_LOADERS + 32;
 constexpr int DW_SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES;
 
 __device__ __forceinline__ void dw_mma_ss(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(a), "l"(b), "r"(idesc), "r"(acc)
-      : "memory");
+  tcp::mma_ss(d_tmem, a, b, idesc, acc);
 }
-__device__ __forceinline__ void dw_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void dw_mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void dw_mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
+__device__ __forceinline__ void dw_commit(uint32_t bar) { tcp::commit(bar); }
+__device__ __forceinline__ void dw_mbar_init(uint32_t bar, int count) { tcp::mbar_init(bar, count); }
+__device__ __forceinline__ void dw_mbar_arrive(uint32_t bar) { tcp::mbar_arrive(bar); }
 // clock-bounded wait (a protocol error ends the launch with a NaN gradient instead of hanging the GPU)
 __device__ __forceinline__ void dw_mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-  const long long t0 = clock64();
+  const long long t0 = tcp::clock_now();
   for (int spin = 0;; ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
+    if (tcp::mbar_try_wait(bar, parity)) return;
     if ((spin & 63) == 63) {
       if (*abort_flag) return;
-      if (clock64() - t0 > 2000000000LL) { *abort_flag = 1; return; }
+      if (tcp::clock_now() - t0 > 2000000000LL) { *abort_flag = 1; return; }
     }
   }
 }
 __device__ __forceinline__ void dw_tmem_ld8(uint32_t addr, float* v) {
   uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(addr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  tcp::tmem_ld8(addr, r);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
@@ -88,7 +71,7 @@ struct DwBars {
 
 __global__ void __launch_bounds__(DW_THREADS, 1)
     adj_dw_tc_kernel(const HutterLayout y, const RolloutArgs g, const DzStash z) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  APG_TC_DYNAMIC_SMEM(smem_raw);
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) DwBars s_bars;
   __shared__ uint32_t s_tmem;
@@ -107,17 +90,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
     }
     dw_mbar_init(smem_u32(&s_bars.done), 1);
     s_abort = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tcp::fence_mbar_init();
   }
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)),
-                 "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    tcp::tmem_alloc512(&s_tmem);
   }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  tcp::fence_before_thread_sync();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  tcp::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
 
   if (warp == 8) {
@@ -131,7 +111,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
           const Op op = op_of(i);
           dw_mbar_wait(smem_u32(&s_bars.full[s]), full_par[s], abort_flag);
           full_par[s] ^= 1;
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          tcp::fence_after_thread_sync();
           unsigned char* st = base + s * STAGE_BYTES;
           const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG_BYTES, b_hi = a_lo + A_IMG_BYTES,
                          b_lo = b_hi + B_IMG_BYTES;
@@ -185,7 +165,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
           b_chunk(op, S, tile, r, d4, x);
           store_split4(b_hi, b_lo, chunk_off(r, d4), make_float4(x[0], x[1], x[2], x[3]));
         }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic writes -> tensor core reads
+        tcp::fence_proxy_async_smem();       // generic writes -> tensor core reads
         dw_mbar_arrive(smem_u32(&s_bars.full[s]));
       }
     }
@@ -199,7 +179,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   }
   if (my_tiles > 0 && warp < 4) {
     dw_mbar_wait(smem_u32(&s_bars.done), 0, abort_flag);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    tcp::fence_after_thread_sync();
     const int r = warp * 32 + lane;                            // TMEM lane = A row
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
     const float poison = __int_as_float(0x7fc00000);
@@ -227,7 +207,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
       }
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  tcp::fence_before_thread_sync();
   __syncthreads();
   if (my_tiles > 0) {
     const float* s_T = reinterpret_cast<const float*>(base);
@@ -245,10 +225,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
     for (int i = tid; i < NC * RD * 3 + NC; i += DW_THREADS) P[y.t_wc + i] = 0.f;
   }
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+    tcp::tmem_dealloc512(tmem);
   }
 }
 
+#ifndef APG_TC_SIM
 // grad[p] = scale * sum over CTAs of partials[c][p]: 32 parameters x 4 CTA slices per block of 128 threads
 __global__ void __launch_bounds__(128) apg_reduce4_kernel(const float* __restrict__ partials, int ncta, int n,
                                                           float scale, float* __restrict__ grad) {
@@ -277,5 +258,7 @@ cudaError_t launch_adj_dw_tc(const HutterLayout& y, const RolloutArgs& a, const 
   adj_dw_tc_kernel<<<grid, DW_THREADS, DW_SMEM_BYTES, st>>>(y, a, z);
   return cudaGetLastError();
 }
+
+#endif  // APG_TC_SIM
 
 }  // namespace apg

@@ -11,9 +11,12 @@
 // group owns TMEM lane r = drone r of the tile); warp 8 lane 0 issues every tcgen05.mma.  Hand-off by mbarriers:
 // a_ready[s] (128 arrivals: the A operand of the next op is in TMEM), d_ready[s] (tcgen05.commit: the op is done).
 #include "tc_layout.cuh"
-#include "tile_engine.cuh"
+#include "tc_prims.cuh"
 #include "rollout_args.h"
+#ifndef APG_TC_SIM
+#include "tile_engine.cuh"
 #include "kernels.h"
+#endif
 
 namespace apg {
 
@@ -25,58 +28,28 @@ constexpr int TC_THREADS = 288;
 constexpr int TC_SMEM_BYTES = 1024 + BLOB_BYTES;
 static_assert(TC_SMEM_BYTES <= 232448 - 512, "weight images do not fit in shared memory");
 
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
+using tcp::mma_ts;
+__device__ __forceinline__ void mma_commit(uint32_t bar) { tcp::commit(bar); }
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, int count) { tcp::mbar_init(bar, count); }
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) { tcp::mbar_arrive(bar); }
 // bounded wait: a protocol error must end the launch (wrong results are caught by the parity tests), never hang
 // the GPU.  A wait that lasts longer than ~1 s of SM clocks sets the CTA's abort flag; from then on every wait of
 // the CTA returns at once and the CTA reports a NaN loss.
 __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-  const long long t0 = clock64();
+  const long long t0 = tcp::clock_now();
   for (int spin = 0;; ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
+    if (tcp::mbar_try_wait(bar, parity)) return;
     if ((spin & 63) == 63) {
       if (*abort_flag) return;
-      if (clock64() - t0 > 2000000000LL) { *abort_flag = 1; return; }
+      if (tcp::clock_now() - t0 > 2000000000LL) { *abort_flag = 1; return; }
     }
   }
 }
 // non-blocking phase test
-__device__ __forceinline__ bool tc_mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
+__device__ __forceinline__ bool tc_mbar_test(uint32_t bar, uint32_t parity) { return tcp::mbar_test_wait(bar, parity); }
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, float* v) {
   uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(addr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+  tcp::tmem_ld8(addr, r);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
@@ -88,16 +61,12 @@ __device__ __forceinline__ void tmem_st8_split(uint32_t a_hi, uint32_t a_lo, con
     h[j] = __float_as_uint(x[j]) & 0xffffe000u;
     l[j] = __float_as_uint(x[j] - __uint_as_float(h[j]));
   }
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(a_hi), "r"(h[0]),
-               "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7])
-               : "memory");
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(a_lo), "r"(l[0]),
-               "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7])
-               : "memory");
+  tcp::tmem_st8(a_hi, h);
+  tcp::tmem_st8(a_lo, l);
 }
 __device__ __forceinline__ void a_operand_ready(uint32_t bar) {
-  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  tcp::wait_st();
+  tcp::fence_before_thread_sync();
   tc_mbar_arrive(bar);
 }
 
@@ -117,7 +86,7 @@ __global__ void apg_pack_tc_kernel(const float* __restrict__ params, const Hutte
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
     hutter_fwd_tc_kernel(const unsigned char* __restrict__ blob, const HutterLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  APG_TC_DYNAMIC_SMEM(smem_raw);
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const float* s_bias = (const float*)(base + IMG_TOTAL);
   __shared__ __align__(8) TcBars s_bars;
@@ -135,18 +104,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_mbar_init(smem_u32(&s_bars.d_ready[s]), 1);
     }
     s_abort = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tcp::fence_mbar_init();
   }
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy image writes -> tensor core reads
+  tcp::fence_proxy_async_smem();     // generic-proxy image writes -> tensor core reads
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)),
-                 "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    tcp::tmem_alloc512(&s_tmem);
   }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  tcp::fence_before_thread_sync();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  tcp::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
   const int n = g.N;
   const int ntiles = (n + TMT - 1) / TMT;                     // tcgen05 tiles of 128 drones
@@ -163,7 +129,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t par[2] = {0, 0};
       int op_i[2] = {0, 0}, tile_j[2] = {0, 1};
       int remaining = my_tiles * NOPS;
-      long long t_idle = clock64();
+      long long t_idle = tcp::clock_now();
       while (remaining > 0) {
         bool progressed = false;
 #pragma unroll
@@ -171,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           if (tile_j[s] >= my_tiles) continue;
           if (!tc_mbar_test(smem_u32(&s_bars.a_ready[s]), par[s])) continue;
           par[s] ^= 1;
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          tcp::fence_after_thread_sync();
           const Op op = op_of(op_i[s]);
           const uint32_t idesc = idesc_tf32(TMT, op.N);
           const uint32_t whi = smem_u32(base + op.img_off), wlo = whi + img_bytes(op.rows, op.K);
@@ -189,8 +155,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           progressed = true;
         }
         if (progressed) {
-          t_idle = clock64();
-        } else if (*abort_flag || clock64() - t_idle > 2000000000LL) {
+          t_idle = tcp::clock_now();
+        } else if (*abort_flag || tcp::clock_now() - t_idle > 2000000000LL) {
           *abort_flag = 1;                                    // protocol error: give up, the CTA reports NaN
           break;
         }
@@ -206,7 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     auto wait_d = [&]() {
       tc_mbar_wait(bar_d, par, abort_flag);
       par ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      tcp::fence_after_thread_sync();
     };
     for (int j = s; j < my_tiles; j += 2) {
       const int tile = (int)blockIdx.x + j * (int)gridDim.x;
@@ -332,7 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
   if (lane == 0 && warp < 8) s_red[warp] = my_loss;
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  tcp::fence_before_thread_sync();
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
@@ -342,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     g.loss_partials[blockIdx.x] = s_abort ? __int_as_float(0x7fc00000) : t;
   }
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+    tcp::tmem_dealloc512(tmem);
   }
 }
 
@@ -360,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 __global__ void __launch_bounds__(TC_THREADS, 1)
     hutter_adj_dx_tc_kernel(const unsigned char* __restrict__ blob, const HutterLayout y, const RolloutArgs g,
                             const DzStash z) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  APG_TC_DYNAMIC_SMEM(smem_raw);
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) TcBars s_bars;
   __shared__ uint32_t s_tmem;
@@ -376,18 +342,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_mbar_init(smem_u32(&s_bars.d_ready[s]), 1);
     }
     s_abort = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    tcp::fence_mbar_init();
   }
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  tcp::fence_proxy_async_smem();
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)),
-                 "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    tcp::tmem_alloc512(&s_tmem);
   }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  tcp::fence_before_thread_sync();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  tcp::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
   const int n = g.N;
   const int ntiles = (n + TMT - 1) / TMT;
@@ -400,7 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t par[2] = {0, 0};
       int op_i[2] = {0, 0}, tile_j[2] = {0, 1};
       int remaining = my_tiles * NROPS;
-      long long t_idle = clock64();
+      long long t_idle = tcp::clock_now();
       while (remaining > 0) {
         bool progressed = false;
 #pragma unroll
@@ -408,7 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           if (tile_j[s] >= my_tiles) continue;
           if (!tc_mbar_test(smem_u32(&s_bars.a_ready[s]), par[s])) continue;
           par[s] ^= 1;
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          tcp::fence_after_thread_sync();
           const ROp op = rop_of(op_i[s]);
           const uint32_t idesc = idesc_tf32(TMT, op.N, 1);
           const uint32_t whi = smem_u32(base + op.img_off), wlo = whi + img_bytes(op.rows, op.Kf);
@@ -426,8 +389,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           progressed = true;
         }
         if (progressed) {
-          t_idle = clock64();
-        } else if (*abort_flag || clock64() - t_idle > 2000000000LL) {
+          t_idle = tcp::clock_now();
+        } else if (*abort_flag || tcp::clock_now() - t_idle > 2000000000LL) {
           *abort_flag = 1;
           break;
         }
@@ -444,7 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     auto wait_d = [&]() {
       tc_mbar_wait(bar_d, par, abort_flag);
       par ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      tcp::fence_after_thread_sync();
     };
     for (int j = s; j < my_tiles; j += 2) {
       const int tile = (int)blockIdx.x + j * (int)gridDim.x;
@@ -525,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      tcp::fence_before_thread_sync();
       tc_mbar_arrive(bar_a);                                   // D_main has been read: go on with the conv pieces
 #pragma unroll
       for (int gp = 0; gp < 4; ++gp) {
@@ -544,19 +507,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
         if (gp < 3) {
-          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          tcp::fence_before_thread_sync();
           tc_mbar_arrive(bar_a);                               // D_conv is free for the next position pair
         }
       }
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  tcp::fence_before_thread_sync();
   __syncthreads();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512) : "memory");
+    tcp::tmem_dealloc512(tmem);
   }
 }
 
+#ifndef APG_TC_SIM
 cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, unsigned char* blob,
                                     const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
@@ -586,5 +550,6 @@ cudaError_t launch_hutter_fwd_tc(const HutterLayout& y, const float* params, uns
   hutter_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(blob, y, a);
   return cudaGetLastError();
 }
+#endif  // APG_TC_SIM
 
 }  // namespace apg

@@ -21,7 +21,7 @@ cudaError_t launch_hutter_fwd_tc(const HutterLayout& y, const float* params, uns
 
 // optional split adjoint (APG_TC_DW=1): dX chain + dZ stash (hutter_adjdx_kernels.cu), then the weight gradient as a
 // streaming tcgen05 GEMM over the drone axis (adj_dw_tc_kernels.cu)
-struct DzStash { float *o, *z3, *z2, *z1, *x; };      // [tile][Mo4 | 64 | 64 | 64 | K1][TMP]
+// (struct DzStash: rollout_args.h)
 cudaError_t launch_hutter_adj_dx(int system, const HutterLayout& y, const RolloutArgs& a, const DzStash& z, int grid,
                                  cudaStream_t st);
 cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, unsigned char* blob,

@@ -1,0 +1,125 @@
+// Every tcgen05 / TMEM / mbarrier instruction the tcgen05 kernels use, as named functions: the kernels contain no
+// inline PTX of their own.  Two implementations of the same interface:
+//   * default: the PTX (sm_100a);
+//   * -DAPG_TC_SIM: declarations only - tests/hostcheck/tc_sim.h implements them with a software model (TMEM as an
+//     array, mbarriers as phase counters, tcgen05.mma decoded from its descriptors and executed at commit time) so
+//     that the UNCHANGED kernel source runs on the CPU, one OS thread per GPU thread, and the hand-off protocol, the
+//     operand placement and the epilogues are exercised end to end before the kernels ever meet hardware.
+#pragma once
+#include <stdint.h>
+
+// the CTA's dynamic shared memory (the simulator hands out its own buffer)
+#ifdef APG_TC_SIM
+#define APG_TC_DYNAMIC_SMEM(name) unsigned char* name = ::apg::tcp::dynamic_smem()
+#else
+#define APG_TC_DYNAMIC_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+namespace apg {
+namespace tcp {
+
+#ifdef APG_TC_SIM
+unsigned char* dynamic_smem();
+void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate);
+void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate);
+void commit(uint32_t bar);
+void mbar_init(uint32_t bar, int count);
+void mbar_arrive(uint32_t bar);
+bool mbar_try_wait(uint32_t bar, uint32_t parity);
+bool mbar_test_wait(uint32_t bar, uint32_t parity);
+void tmem_ld8(uint32_t addr, uint32_t* r);
+void tmem_st8(uint32_t addr, const uint32_t* r);
+void wait_st();
+void fence_before_thread_sync();
+void fence_after_thread_sync();
+void fence_mbar_init();
+void fence_proxy_async_smem();
+void tmem_alloc512(uint32_t* slot_in_smem);
+void tmem_dealloc512(uint32_t addr);
+long long clock_now();
+#else
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, one CTA
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on `bar` once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// this thread's TMEM lane, 8 consecutive 32-bit columns (32x32b.x8); the load is complete on return
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(addr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_before_thread_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_after_thread_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the tensor core (async proxy)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// whole warp: allocate all 512 TMEM columns, the base address lands in *slot_in_smem
+__device__ __forceinline__ void tmem_alloc512(uint32_t* slot_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(slot_in_smem))),
+               "n"(512)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc512(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "n"(512) : "memory");
+}
+__device__ __forceinline__ long long clock_now() { return clock64(); }
+#endif
+
+}  // namespace tcp
+}  // namespace apg

@@ -83,6 +83,7 @@ extern "C" void hc_tc_emulate(const unsigned char* blob, const float* in_state, 
 // emulated from the images (fp64 accumulation), then the accumulator -> gradient map of the kernel's epilogue
 // ---------------------------------------------------------------------------------------------------------------
 #include "adj_dw_layout.cuh"
+#include "tc_emu.h"
 
 extern "C" int hc_dw_num_params() { return make_hutter_layout(F0, H, RD, MO, 1).n_params; }
 
@@ -176,40 +177,9 @@ extern "C" void hc_dw_emulate(const float* st_x1, const float* st_h1, const floa
 // ---------------------------------------------------------------------------------------------------------------
 namespace emu {
 struct Tmem { std::vector<float> v; Tmem() : v(128 * 512, 0.f) {} float& at(int lane, int col) { return v[lane * 512 + col]; } };
-struct Desc { uint32_t start, lbo, sbo; bool ok; };
-static Desc decode(uint64_t d) {
-  Desc r;
-  r.start = (uint32_t)(d & 0x3fff) << 4; r.lbo = (uint32_t)((d >> 16) & 0x3fff) << 4; r.sbo = (uint32_t)((d >> 32) & 0x3fff) << 4;
-  r.ok = ((d >> 46) & 3) == 1 && (d >> 61) == 0;
-  return r;
-}
-static float tf32(float x) { union { float f; uint32_t u; } v; v.f = x; v.u &= 0xffffe000u; return v.f; }
-static float smem_f(const std::vector<unsigned char>& sm, uint32_t addr) {
-  float v; if (addr + 4 > sm.size()) return NAN; memcpy(&v, sm.data() + addr, 4); return v;
-}
-static float elem(const std::vector<unsigned char>& sm, const Desc& d, bool mn_major, int i, int k) {
-  const uint32_t off = mn_major ? (uint32_t)((i / 4) * d.sbo + (k % 8) * 16 + (k / 8) * d.lbo + (i % 4) * 4)
-                                : (uint32_t)((i % 8) * 16 + (i / 8) * d.sbo + (k / 4) * d.lbo + (k % 4) * 4);
-  return smem_f(sm, d.start + off);
-}
-// D[lane][d_col + n] (+)= sum_k A[lane][k] B[n][k], K = 8.  A from TMEM columns (a_col >= 0) or from a K-major descriptor
 static bool mma(Tmem& T, const std::vector<unsigned char>& sm, int d_col, int a_col, uint64_t a_desc, uint64_t b_desc,
                 uint32_t idesc, bool acc) {
-  const int M = (int)((idesc >> 24) & 31) * 16, N = (int)((idesc >> 17) & 63) * 8;
-  const bool bmn = (idesc >> 16) & 1, amn = (idesc >> 15) & 1;
-  if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 2 || ((idesc >> 10) & 7) != 2 || amn || M != 128 || N % 16) return false;
-  const Desc bd = decode(b_desc), ad = decode(a_desc);
-  if (!bd.ok || (a_col < 0 && !ad.ok)) return false;
-  for (int m = 0; m < M; ++m)
-    for (int n = 0; n < N; ++n) {
-      double s = acc ? (double)T.at(m, d_col + n) : 0.0;
-      for (int k = 0; k < 8; ++k) {
-        const float a = a_col >= 0 ? T.at(m, a_col + k) : elem(sm, ad, false, m, k);
-        s += (double)tf32(a) * (double)tf32(elem(sm, bd, bmn, n, k));
-      }
-      T.at(m, d_col + n) = (float)s;
-    }
-  return true;
+  return mma(T.v.data(), sm.data(), sm.size(), d_col, a_col, a_desc, b_desc, idesc, acc);
 }
 static void st_split(Tmem& T, int lane, int ahi, int alo, int col, float x) {
   float h, l; split_hi_lo(x, &h, &l); T.at(lane, ahi + col) = h; T.at(lane, alo + col) = l;
