@@ -7,7 +7,9 @@
 #include "hutter_policy.cuh"
 #include "layouts.h"
 #include "tile_engine.cuh"
+#ifndef APG_SIM
 #include "kernels.h"
+#endif
 
 namespace apg {
 
@@ -27,7 +29,7 @@ struct EvalArgs {
 };
 
 __global__ void __launch_bounds__(NT, 1) eval_rollout_kernel(const HutterLayout y, const EvalArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Quad<float>;
   constexpr int S = Sys::S, A = Sys::A;
   const int h = g.h, RL = g.ev.table_rows, steps = g.ev.steps;
@@ -167,7 +169,7 @@ struct WingEvalArgs {
 };
 
 __global__ void __launch_bounds__(NT, 1) eval_wing_kernel(const HutterLayout y, const WingEvalArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Wing<float>;
   constexpr int S = Sys::S, A = Sys::A;
   const int steps = g.ev.steps, K = g.ev.n_targets;
@@ -290,7 +292,7 @@ struct CartpoleEvalArgs {
 };
 
 __global__ void __launch_bounds__(NT, 1) eval_cartpole_kernel(const SimpleLayout y, const CartpoleEvalArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Cartpole<float>;
   constexpr int S = Sys::S;
   const int steps = g.ev.steps;
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(NT, 1) eval_cartpole_kernel(const SimpleLayout
   }
 }
 
+#ifndef APG_SIM
 size_t eval_cartpole_smem_bytes(const SimpleLayout& y) {
   return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + y.rows_total * TMP) + 16;
 }
@@ -381,7 +384,9 @@ cudaError_t launch_eval_cartpole(const SimpleLayout& y, const float* wf, const f
   eval_cartpole_kernel<<<grid, NT, smem, st>>>(y, a);
   return cudaGetLastError();
 }
+#endif  // APG_SIM
 
+#ifndef APG_SIM
 size_t eval_wing_smem_bytes(const HutterLayout& y) {
   return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP) + 16;
 }
@@ -421,5 +426,7 @@ cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const fl
   eval_rollout_kernel<<<grid, NT, smem, st>>>(y, a);
   return cudaGetLastError();
 }
+
+#endif  // APG_SIM
 
 }  // namespace apg

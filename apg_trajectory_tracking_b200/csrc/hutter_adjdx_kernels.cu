@@ -20,7 +20,7 @@ constexpr int NTH_DX = NT + TM;     // 8 GEMM warps + 2 dynamics warps, as in hu
 template <template <typename> class SysT, bool CONV>
 __global__ void __launch_bounds__(NTH_DX, 1) hutter_adj_dx_kernel(const HutterLayout y, const RolloutArgs g,
                                                                   const DzStash z) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = SysT<float>;
   constexpr int S = Sys::S, R = Sys::REFW;
   const int wb_floats = y.b_ws;              // no first-layer dX: the policy inputs need no gradient

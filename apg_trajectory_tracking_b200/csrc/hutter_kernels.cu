@@ -38,7 +38,7 @@ constexpr int NTH = NT + TM;     // 320 threads
 // ------------------------------------------------------------------------------------------------------------
 template <template <typename> class SysT, bool CONV>
 __global__ void __launch_bounds__(NTH, 1) hutter_fwd_kernel(const HutterLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = SysT<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
   float* s_w = smem;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NTH, 1) hutter_fwd_kernel(const HutterLayout y
 // ------------------------------------------------------------------------------------------------------------
 template <template <typename> class SysT, bool CONV>
 __global__ void __launch_bounds__(NTH, 1) hutter_adj_kernel(const HutterLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = SysT<float>;
   constexpr int S = Sys::S, R = Sys::REFW;
   const int wb_floats = y.b_ws;              // concurrent mode needs no first-layer dX weights

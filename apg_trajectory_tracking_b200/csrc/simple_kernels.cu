@@ -18,7 +18,7 @@ __device__ __forceinline__ void load_state_tile(float* dst, const float* __restr
 }
 
 __global__ void __launch_bounds__(NT, 1) simple_fwd_kernel(const SimpleLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Cartpole<float>;
   constexpr int S = Sys::S, A = Sys::A;
   float* s_w = smem;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NT, 1) simple_fwd_kernel(const SimpleLayout y,
 }
 
 __global__ void __launch_bounds__(NT, 1) simple_adj_kernel(const SimpleLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Cartpole<float>;
   constexpr int S = Sys::S;
   float* s_w = smem;

@@ -15,9 +15,13 @@
 //  A = dZ and multiplies by the stored activation's derivative in place.  fp32 parity (1e-5 on the loss) is required,
 //  hence 3xTF32 and not plain TF32; see DESIGN.md section 3.
 #pragma once
+#ifndef APG_SIM
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "layouts.h"
+// -DAPG_SIM (tests only): every PTX helper below calls the software model of tests/hostcheck/te_sim.h instead, so
+// that the unchanged kernel sources built on this header run on the CPU (one OS thread per GPU thread).
 
 // ---- optional per-phase cycle accounting (build with -DAPG_PROFILE; tools/phase_profile.py) ----------------
 #ifdef APG_PROFILE
@@ -32,6 +36,13 @@
 #define PROF_FLUSH(k) do { } while (0)
 #endif
 
+// the CTA's dynamic shared memory as a float array (the simulator hands out its own buffer)
+#ifdef APG_SIM
+#define APG_DYNAMIC_SMEM_F32(name) float* name = reinterpret_cast<float*>(::simte::dynamic_smem())
+#else
+#define APG_DYNAMIC_SMEM_F32(name) extern __shared__ __align__(128) float name[]
+#endif
+
 namespace apg {
 
 
@@ -41,6 +52,12 @@ enum Epi { EPI_ACT = 0, EPI_DTANH = 1, EPI_DRELU = 2, EPI_DNONE = 3, EPI_DSIGMOI
 // ------------------------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (TMA 1-D) helpers
 // ------------------------------------------------------------------------------------------------------------
+#ifdef APG_SIM
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { simte::mbar_init(bar, count); }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { simte::mbar_arrive(bar); }
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -56,12 +73,31 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#endif
 // barrier of the GEMM warp group (threads 0..255) in the warp-specialised kernels; plain __syncthreads otherwise
 template <bool WS>
 __device__ __forceinline__ void gsync() {
+#ifdef APG_SIM
+  if (WS) simte::named_barrier_256();
+#else
   if (WS) asm volatile("bar.sync 1, 256;" ::: "memory");
+#endif
   else __syncthreads();
 }
+#ifdef APG_SIM
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { simte::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { simte::mbar_wait(bar, parity); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  simte::bulk_g2s(dst_smem, src_gmem, bytes, bar);
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  simte::bulk_s2g(dst_gmem, src_smem, bytes);
+}
+__device__ __forceinline__ void bulk_commit() { simte::bulk_commit(); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { simte::bulk_wait(N); }
+__device__ __forceinline__ void bulk_wait_all() { simte::bulk_wait(0); }
+#else
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
@@ -102,6 +138,7 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#endif
 
 // Copy `bytes` (multiple of 16) global -> shared in chunks, all signalled on one barrier. Call from ONE thread,
 // after mbar_expect_tx(bar, bytes).
@@ -117,14 +154,23 @@ __device__ __forceinline__ void bulk_g2s_chunked(void* dst, const void* src, uin
 // owned by exactly one thread of one CTA for the whole launch (same-address reductions of one thread retire in
 // program order), so the result is deterministic although the instruction is an atomic.
 __device__ __forceinline__ void red_add(float* addr, float v) {
+#ifdef APG_SIM
+  simte::red_add(addr, v);
+#else
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+#endif
 }
 
 // Destination column of gradient column k.  Conv activations are kept position-major (64 + t*20 + c) in shared
 // memory / the stash while the reference's fc1 weight is channel-major (64 + c*npos + t): perm_npos > 0 maps back.
 // two adjacent floats (8-byte aligned) in one reduction: the (col 2t, 2t+1) pair of an mma C fragment
 __device__ __forceinline__ void red_add2(float* addr, float a, float b) {
+#ifdef APG_SIM
+  simte::red_add(addr, a);
+  simte::red_add(addr + 1, b);
+#else
   asm volatile("red.global.v2.f32.add [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+#endif
 }
 
 __device__ __forceinline__ int perm_col(int k, int perm_npos) {
@@ -246,9 +292,13 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef APG_SIM
+  simte::mma_m16n8k8_tf32(c, a, b0, b1);
+#else
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
 }
 // Y[row0 + n][d] = epi(bias[n] + sum_k A[k][d] * W[k][n]) for the 64 drones of the tile; A feature-major [K][TMP],
 // W [K][ldw] (swizzled when sw), K % 8 == 0, N % 8 == 0.  Warp w: drones 16*(w&3) .., groups of 4 n-tiles
