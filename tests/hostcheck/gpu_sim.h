@@ -1,0 +1,125 @@
+// Test-only: the execution environment shared by the CPU models of the kernels (tc_sim.h: tcgen05 kernels, te_sim.h:
+// tile-engine kernels): one OS thread per GPU thread, one CTA at a time; CUDA built-ins the kernels use (threadIdx /
+// blockIdx, __syncthreads, __syncthreads_or, __shfl_xor_sync, bit casts, float2 / float4 / uint4); a per-CTA state
+// object with the dynamic shared memory, mbarrier table, warp scratch and the list of model violations.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <barrier>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct SimDim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local SimDim3 threadIdx, blockIdx, blockDim, gridDim;
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct uint4 { unsigned x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
+
+namespace sim {
+
+constexpr size_t DYN_SMEM = 232448;
+struct Mbar { int count = 0, pending = 0; long long tx = 0; unsigned phase = 0; bool init = false; };
+
+struct State {
+  alignas(1024) unsigned char smem[DYN_SMEM];
+  float tmem[128 * 512];
+  bool tmem_allocated = false;
+  std::mutex m;
+  std::condition_variable cv;
+  std::unordered_map<uint32_t, Mbar> bars;
+  std::unordered_map<const void*, Mbar> pbars;          // mbarriers addressed by pointer (tile engine)
+  std::unique_ptr<std::barrier<>> named_barrier;        // bar.sync 1, 256
+  std::atomic<int> or_accum{0};
+  std::function<void()> on_thread_exit;                 // e.g. complete the thread's outstanding bulk stores
+  std::vector<const void*> static_ptrs;                 // handles of shared objects outside the dynamic buffer
+  std::unique_ptr<std::barrier<>> cta_barrier;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
+  std::vector<std::vector<float>> warp_buf;
+  std::vector<std::string> errors;
+  long long mma_count = 0;
+};
+inline State& S() { static State s; return s; }
+inline void fail(const std::string& msg) {
+  std::lock_guard<std::mutex> lk(S().m);
+  if (S().errors.size() < 32) S().errors.push_back(msg);
+}
+inline std::vector<std::string>& errors() { return S().errors; }
+
+// run `body` once per thread of every CTA of the grid (CTAs one after the other)
+inline void launch(int grid, int block, const std::function<void()>& body) {
+  State& st = S();
+  for (int b = 0; b < grid; ++b) {
+    memset(st.tmem, 0xff, sizeof st.tmem);              // NaN pattern: reading an unwritten accumulator shows
+    st.tmem_allocated = false;
+    st.bars.clear();
+    st.pbars.clear();
+    st.static_ptrs.clear();
+    st.or_accum = 0;
+    if (block >= 256) st.named_barrier.reset(new std::barrier<>(256));
+    st.cta_barrier.reset(new std::barrier<>(block));
+    const int nwarp = (block + 31) / 32;
+    st.warp_barrier.clear();
+    st.warp_buf.assign(nwarp, std::vector<float>(32, 0.f));
+    for (int w = 0; w < nwarp; ++w) st.warp_barrier.emplace_back(new std::barrier<>(std::min(32, block - 32 * w)));
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (int t = 0; t < block; ++t)
+      th.emplace_back([=, &body]() {
+        threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)b; blockDim.x = (unsigned)block; gridDim.x = (unsigned)grid;
+        body();
+        if (sim::S().on_thread_exit) sim::S().on_thread_exit();
+      });
+    for (auto& t : th) t.join();
+    if (st.tmem_allocated) fail("CTA " + std::to_string(b) + " exited without tcgen05.dealloc");
+  }
+}
+}  // namespace sim
+
+static inline void __syncthreads() { sim::S().cta_barrier->arrive_and_wait(); }
+// barrier + OR of the predicate over the CTA
+static inline int __syncthreads_or(int pred) {
+  sim::State& st = sim::S();
+  if (pred) st.or_accum.store(1);
+  st.cta_barrier->arrive_and_wait();
+  const int r = st.or_accum.load();
+  st.cta_barrier->arrive_and_wait();
+  if (threadIdx.x == 0) st.or_accum.store(0);
+  st.cta_barrier->arrive_and_wait();
+  return r;
+}
+static inline void __trap() { sim::fail("__trap()"); throw std::runtime_error("__trap"); }
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  sim::State& st = sim::S();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  st.warp_buf[w][l] = v;
+  st.warp_barrier[w]->arrive_and_wait();
+  const float r = st.warp_buf[w][l ^ lane_mask];
+  st.warp_barrier[w]->arrive_and_wait();
+  return r;
+}
+

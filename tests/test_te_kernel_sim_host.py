@@ -1,0 +1,129 @@
+"""The evaluation kernels THEMSELVES on the CPU: csrc/eval_kernels.cu (unchanged source, -DAPG_SIM) compiled with g++ on
+top of the software model of tests/hostcheck/te_sim.h (one OS thread per GPU thread; mma.sync fragments, TMA bulk
+copies, mbarriers, __syncthreads_or in software), against the golden runs of the reference's own evaluators and the
+oracle.  Covers what the per-drone host checks (tests/test_eval_math_host.py) cannot: shared-memory carve-up, tile
+engine call sites, barriers / early exit, packed-weight layouts, output addressing of whole launches."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from apg_trajectory_tracking_b200 import params as P
+from oracle import apg_oracle as O
+from tests.helpers import golden_params, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def te(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostcheck_tesim") / "libhostcheck_tesim.so"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
+                           "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "hostcheck", "hostcheck_tesim.cpp"), "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _flat(params):
+    return np.ascontiguousarray(torch.cat([p.reshape(-1) for p in params]).numpy(), dtype=np.float32)
+
+
+def test_cartpole_kernel_on_the_model_matches_reference_runs(te):
+    g = load_golden("eval_cartpole.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    names = ["tilted", "falls", "falls_at_once", "zero_start"]
+    steps, n = 12, 70                                                   # two tiles, the second partial
+    rng = np.random.default_rng(0)
+    init = np.concatenate([np.stack([g[f"{k}_init"] for k in names]),
+                           rng.uniform(-1, 1, (n - 4, 4)) * np.array([0.5, 1.5, 0.12, 1.8])]).astype(np.float32)
+    states, act = np.zeros((n, steps, 4), np.float32), np.zeros((n, steps), np.float32)
+    nst = np.zeros(n, np.int32)
+    asum, acnt, vsum = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    err = ctypes.create_string_buffer(2048)
+    nerr = te.hc_tesim_eval_cartpole(_p(_flat(params)), 10, _p(init), n, ctypes.c_float(0.05), _p(P.PHYS["cartpole"]()),
+                                     steps, ctypes.c_float(0.21), 5, 2, _p(states), _p(act), _p(nst), _p(asum),
+                                     _p(acnt), _p(vsum), err, 2048)
+    assert nerr == 0, err.value.decode()
+    for k, name in enumerate(names):
+        want = g[f"{name}_states"][:steps]
+        taken = min(len(g[f"{name}_states"]), steps)
+        assert int(nst[k]) == taken
+        assert np.abs(states[k, :taken] - want[:taken]).max() <= 2e-5
+    out = O.eval_cartpole_balance(params, torch.tensor(init), steps, 0.05, 0.21, 5)
+    assert np.array_equal(nst, out["n_steps"].numpy()) and len(set(nst.tolist())) > 1
+    assert np.abs(states - out["states"].numpy()).max() <= 5e-5
+    assert np.abs(vsum - out["vel_sum"].numpy()).max() <= 1e-3
+
+
+def test_quad_eval_kernel_on_the_model_matches_reference_run_with_reset(te):
+    g = load_golden("eval_rand.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    name = "fast_reset"
+    steps_all, test_time, tdiv, tstab, h, dt = [float(v) for v in g[f"{name}_cfg"]]
+    h = int(h)
+    steps = 34                                                           # the first reset happens at step 29
+    tabs = np.ascontiguousarray(np.stack([g[f"{name}_table"], g["gentle_table"]]), np.float32)
+    n = 66                                                               # two tiles (64 + 2 drones)
+    index = np.array([0, 1] * 33, np.int32)
+    rng = np.random.default_rng(1)
+    init = np.zeros((n, 12), np.float32)
+    init[:, :3] = tabs[index, 0, :3] + rng.normal(0, 0.03, (n, 3))
+    init[0], init[1] = g[f"{name}_states"][0], g["gentle_states"][0]
+    states = np.zeros((n, steps + 1, 12), np.float32)
+    div, act = np.zeros((n, steps), np.float32), np.zeros((n, steps, 4), np.float32)
+    nst = np.zeros(n, np.int32)
+    err = ctypes.create_string_buffer(2048)
+    nerr = te.hc_tesim_eval_rollout(_p(_flat(params)), h, 4 * h, _p(tabs), _p(index), tabs.shape[1], _p(init), n, steps,
+                                    ctypes.c_float(dt), _p(P.PHYS["quad"]()), ctypes.c_float(tdiv),
+                                    ctypes.c_float(tstab), 0, 2, _p(states), _p(div), _p(act), _p(nst), err, 2048)
+    assert nerr == 0, err.value.decode()
+    assert (nst == steps).all()
+    for k, nm in ((0, name), (1, "gentle")):
+        assert np.abs(states[k] - g[f"{nm}_states"][:steps + 1]).max() <= 5e-5, nm
+        assert np.abs(div[k] - g[f"{nm}_div"][:steps]).max() <= 5e-5
+        assert np.abs(act[k] - g[f"{nm}_actions"][:steps]).max() <= 5e-5
+    assert (g[f"{name}_div"][:steps] > tdiv).sum() >= 1                  # the run contains a reset
+    want = O.eval_follow_tables(params, torch.tensor(tabs)[index.astype(np.int64)], torch.tensor(init), steps, h, dt,
+                                tdiv, tstab, 0)
+    assert np.abs(states - want["states"].numpy()).max() <= 2e-4
+
+
+def test_wing_eval_kernel_on_the_model_matches_reference_flight(te):
+    from tests.test_oracle_golden import wing_eval_case
+    g = load_golden("eval_wing.npz")
+    params, targets, init1, h, dt_data, dt_env, steps_all, test_time, tdiv, tstab = wing_eval_case(g, "two_targets")
+    steps, n = 70, 65                                                    # the target switch happens around step 50
+    tg = np.ascontiguousarray(np.repeat(targets.numpy(), n, 0), np.float32)
+    rng = np.random.default_rng(2)
+    tg[1:, :, 1:] += rng.uniform(-1, 1, (n - 1, tg.shape[1], 2)).astype(np.float32)
+    init = np.zeros((n, 12), np.float32)
+    init[:, 3] = 11.5
+    states = np.zeros((n, steps + 1, 12), np.float32)
+    div, act = np.zeros((n, steps), np.float32), np.zeros((n, steps, 4), np.float32)
+    nst = np.zeros(n, np.int32)
+    dts, dtc = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    mean, std = np.ascontiguousarray(g["mean"], np.float32), np.ascontiguousarray(g["std"], np.float32)
+    err = ctypes.create_string_buffer(2048)
+    nerr = te.hc_tesim_eval_wing(_p(_flat(params)), h, _p(tg), tg.shape[1], _p(init), n, _p(mean), _p(std),
+                                 ctypes.c_float(dt_data), ctypes.c_float(dt_env), _p(P.PHYS["wing"]()), steps,
+                                 ctypes.c_float(tdiv), ctypes.c_float(tstab), 0, 2, _p(states), _p(div), _p(act),
+                                 _p(nst), _p(dts), _p(dtc), err, 2048)
+    assert nerr == 0, err.value.decode()
+    traj = g["two_targets_traj"]
+    scale = np.abs(traj[:, :12]).max()
+    assert int(nst[0]) == steps
+    assert np.abs(states[0, 1:steps + 1] - traj[:steps, :12]).max() <= 1e-4 * scale
+    assert np.abs(act[0] - traj[:steps, 12:]).max() <= 1e-4
+    assert dtc[0] >= 1                                                   # the first target was passed
+    want = O.eval_fly_to_points(params, torch.tensor(tg), torch.tensor(init), g["mean"], g["std"], steps, h, dt_data,
+                                dt_env, tdiv, tstab, 0)
+    assert np.array_equal(nst, want["n_steps"].numpy())
+    assert np.abs(states - want["states"].numpy()).max() <= 2e-4 * scale
+    assert np.abs(dts - want["div_target_sum"].numpy()).max() <= 1e-3
