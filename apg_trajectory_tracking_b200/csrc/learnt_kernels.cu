@@ -14,7 +14,12 @@
 //            block, summed in fixed order by apg_reduce_kernel -> bitwise reproducible.
 #include "learnt_math.cuh"
 #include "learnt_wing_math.cuh"
+#ifdef APG_SIM
+#define APG_LEARNT_DYNAMIC_SMEM(name) float* name = reinterpret_cast<float*>(::simte::dynamic_smem())
+#else
 #include "kernels.h"
+#define APG_LEARNT_DYNAMIC_SMEM(name) extern __shared__ __align__(16) float name[]
+#endif
 
 namespace apg {
 
@@ -28,7 +33,7 @@ __global__ void __launch_bounds__(LT) learnt_fwd_kernel(const float* __restrict_
                                                         const float* __restrict__ s, const float* __restrict__ a,
                                                         float dt, int n, float* __restrict__ out) {
   using RW = LearntRows<M::NPH>;
-  extern __shared__ __align__(16) float sm[];
+  APG_LEARNT_DYNAMIC_SMEM(sm);
   float* sP = sm;                        // [NP]
   float* sH = sm + RW::NP + 1;           // [64][LP]
   for (int i = threadIdx.x; i < RW::NP; i += LT) sP[i] = params[i];
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(LT) learnt_adj_kernel(const float* __restrict_
                                                         float* __restrict__ partials) {
   using RW = LearntRows<M::NPH>;
   constexpr int EPT = (RW::NP + LT - 1) / LT;      // entries per thread: 15
-  extern __shared__ __align__(16) float sm[];
+  APG_LEARNT_DYNAMIC_SMEM(sm);
   float* sP = sm;                        // [NP]
   float* sF = sm + RW::NP + 1;           // [R_TOTAL][LP] factor rows
   const int t = threadIdx.x;
@@ -118,6 +123,7 @@ __global__ void __launch_bounds__(LT) learnt_adj_kernel(const float* __restrict_
   }
 }
 
+#ifndef APG_SIM
 int learnt_num_params(int system) {
   return system == SYS_WING ? LearntRows<LearntWing<float>::NPH>::NP : LearntRows<LearntQuad<float>::NPH>::NP;
 }
@@ -173,5 +179,7 @@ cudaError_t launch_learnt_adj(int system, const float* params, const PhysConsts&
     return launch_adj_t<LearntWing<float>>(params, pc, s, a, dt, n, g, gs, ga, grad_params, partials, sms, st);
   return cudaErrorInvalidValue;
 }
+
+#endif  // APG_SIM
 
 }  // namespace apg

@@ -127,3 +127,47 @@ def test_wing_eval_kernel_on_the_model_matches_reference_flight(te):
     assert np.array_equal(nst, want["n_steps"].numpy())
     assert np.abs(states - want["states"].numpy()).max() <= 2e-4 * scale
     assert np.abs(dts - want["div_target_sum"].numpy()).max() <= 1e-3
+
+
+# ---- learnt residual dynamics: csrc/learnt_kernels.cu (unchanged source) on the CPU thread model ------------------
+@pytest.fixture(scope="module")
+def ln(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostcheck_lnsim") / "libhostcheck_lnsim.so"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
+                           "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "hostcheck", "hostcheck_lnsim.cpp"), "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+@pytest.mark.parametrize("system,tag,nparam_tensors", [(0, "b", 8), (1, "wb", 42)])
+def test_learnt_kernels_on_the_model_match_reference_autograd(ln, system, tag, nparam_tensors):
+    """forward + adjoint launches over several blocks / tiles (the golden batch tiled up to 300 rows): outputs and
+    state / action gradients per row, parameter gradient = sum over the rows"""
+    g = load_golden("learnt_dyn.npz")
+    flat = np.concatenate([np.asarray(g[f"{tag}_param_{i}"]).reshape(-1) for i in range(nparam_tensors)])
+    flat = np.ascontiguousarray(flat, np.float32)
+    assert ln.hc_lnsim_num_params(system) == flat.size
+    pc = P.PHYS["quad"]({"rotational_drag": [float(x) for x in g[f"{tag}_rot_drag"]]}) if system == 0 \
+        else P.PHYS["wing"]()
+    reps = 300 // len(g[f"{tag}_state"]) + 1
+    tile = lambda k: np.ascontiguousarray(np.tile(g[f"{tag}_{k}"], (reps, 1))[:300], np.float32)   # noqa: E731
+    s, a, cot = tile("state"), tile("action"), tile("cot")
+    n, m = 300, len(g[f"{tag}_state"])
+    out, gs, ga, gp = np.zeros_like(s), np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    err = ctypes.create_string_buffer(2048)
+    nerr = ln.hc_lnsim_step_and_adjoint(system, _p(flat), _p(pc), _p(s), _p(a), ctypes.c_float(float(g[f"{tag}_dt"])),
+                                        n, 2, _p(cot), _p(out), _p(gs), _p(ga), _p(gp), err, 2048)
+    assert nerr == 0, err.value.decode()
+    rel = lambda x, w: np.abs(x - w).max() / max(np.abs(w).max(), 1e-6)          # noqa: E731
+    assert rel(out[:m], g[f"{tag}_out"]) <= 5e-6 and np.array_equal(out[m:2 * m], out[:m])
+    assert rel(gs[:m], g[f"{tag}_gstate"]) <= 5e-5 and rel(ga[:m], g[f"{tag}_gaction"]) <= 5e-5
+    # parameter gradient of the tiled batch = sum over complete copies + the partial last copy: compare through the
+    # oracle-free identity on the first `m` rows only when the batch is one exact multiple
+    want = np.concatenate([np.asarray(g[f"{tag}_gparam_{i}"]).reshape(-1) for i in range(nparam_tensors)])
+    full = (n // m) * m
+    out2, gs2, ga2, gp2 = np.zeros_like(s), np.zeros_like(s), np.zeros_like(a), np.zeros_like(flat)
+    nerr = ln.hc_lnsim_step_and_adjoint(system, _p(flat), _p(pc), _p(s), _p(a), ctypes.c_float(float(g[f"{tag}_dt"])),
+                                        full, 3, _p(cot), _p(out2), _p(gs2), _p(ga2), _p(gp2), err, 2048)
+    assert nerr == 0, err.value.decode()
+    scale = np.abs(want).max() * (full // m)
+    assert np.abs(gp2 - want * (full // m)).max() <= 1e-4 * scale
