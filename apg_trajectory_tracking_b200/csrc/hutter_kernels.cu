@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NTH, 1) hutter_fwd_kernel(const HutterLayout y
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
     if ((d & 31) == 0) s_red[d >> 5] = my_loss;
-    asm volatile("bar.sync 2, 64;" ::: "memory");
+    dyn_group_sync();
     if (d == 0) g.loss_partials[blockIdx.x] = s_red[0] + s_red[1];
   }
   if (tid == 0) bulk_wait_all();
@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(NTH, 1) hutter_adj_kernel(const HutterLayout y
   }
 }
 
+#ifndef APG_SIM
 // ------------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------------
@@ -346,5 +347,7 @@ cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutAr
   }
   return cudaGetLastError();
 }
+
+#endif  // APG_SIM
 
 }  // namespace apg

@@ -74,6 +74,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 #endif
+// barrier of the two dynamics warps (64 threads) of the warp-specialised kernels
+__device__ __forceinline__ void dyn_group_sync() {
+#ifdef APG_SIM
+  simte::named_barrier_64();
+#else
+  asm volatile("bar.sync 2, 64;" ::: "memory");
+#endif
+}
 // barrier of the GEMM warp group (threads 0..255) in the warp-specialised kernels; plain __syncthreads otherwise
 template <bool WS>
 __device__ __forceinline__ void gsync() {

@@ -39,6 +39,9 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
+template <class T> static inline void __stcg(T* p, T v) { *p = v; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 
 namespace sim {
 
@@ -54,6 +57,7 @@ struct State {
   std::unordered_map<uint32_t, Mbar> bars;
   std::unordered_map<const void*, Mbar> pbars;          // mbarriers addressed by pointer (tile engine)
   std::unique_ptr<std::barrier<>> named_barrier;        // bar.sync 1, 256
+  std::unique_ptr<std::barrier<>> named_barrier64;      // bar.sync 2, 64
   std::atomic<int> or_accum{0};
   std::function<void()> on_thread_exit;                 // e.g. complete the thread's outstanding bulk stores
   std::vector<const void*> static_ptrs;                 // handles of shared objects outside the dynamic buffer
@@ -81,6 +85,7 @@ inline void launch(int grid, int block, const std::function<void()>& body) {
     st.static_ptrs.clear();
     st.or_accum = 0;
     if (block >= 256) st.named_barrier.reset(new std::barrier<>(256));
+    st.named_barrier64.reset(new std::barrier<>(64));
     st.cta_barrier.reset(new std::barrier<>(block));
     const int nwarp = (block + 31) / 32;
     st.warp_barrier.clear();

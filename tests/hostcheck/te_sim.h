@@ -88,6 +88,7 @@ inline void thread_exit() {
   bulk_wait(0);
 }
 inline void named_barrier_256() { sim::S().named_barrier->arrive_and_wait(); }
+inline void named_barrier_64() { sim::S().named_barrier64->arrive_and_wait(); }
 inline void red_add(float* addr, float v) {
   std::atomic_ref<float> a(*addr);
   a.fetch_add(v, std::memory_order_relaxed);

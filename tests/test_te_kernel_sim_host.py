@@ -171,3 +171,78 @@ def test_learnt_kernels_on_the_model_match_reference_autograd(ln, system, tag, n
     assert nerr == 0, err.value.decode()
     scale = np.abs(want).max() * (full // m)
     assert np.abs(gp2 - want * (full // m)).max() <= 1e-4 * scale
+
+
+# ---- the concurrent hutter rollout kernels on the model -------------------------------------------------------------
+TM, TMP = 64, 68
+
+
+def _build(tmp, name):
+    out = tmp / f"lib{name}.so"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
+                           "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "hostcheck", f"{name}.cpp"), "-o", str(out)])
+    return ctypes.CDLL(str(out))
+
+
+@pytest.fixture(scope="module")
+def hk(tmp_path_factory):
+    tmp = tmp_path_factory.mktemp("hostcheck_hksim")
+    return _build(tmp, "hostcheck_hksim"), _build(tmp, "hostcheck_tcsim_dw")
+
+
+def _check_grad(grad, params, want_grad, tol):
+    o = 0
+    for i, (p, g) in enumerate(zip(params, want_grad)):
+        got = grad[o:o + p.numel()].reshape(p.shape)
+        o += p.numel()
+        if g is None:
+            assert np.abs(got).max() == 0
+            continue
+        scale = max(float(g.abs().max()), 1e-6)
+        assert np.abs(got - g.detach().double().numpy()).max() <= tol * scale, i
+
+
+def test_hutter_kernels_on_the_model_reproduce_oracle_loss_and_gradient(hk):
+    """hutter_fwd_kernel / hutter_adj_kernel are GPU-verified: that their unchanged source ALSO reproduces the oracle
+    on the software model validates the model itself (warp specialisation, named barriers, mbarrier hand-offs, TMA
+    bulk loads / stores with deferred reads, mma.sync fragment layout).  Then the not-yet-run split adjoint:
+    hutter_adj_dx_kernel on the same model -> adj_dw_tc_kernel on the tcgen05 model -> the same gradient."""
+    import bench as B
+    from apg_trajectory_tracking_b200 import synthetic as SY
+    lib, dwl = hk
+    n, h, grid = 150, 10, 2                                              # 3 tiles: CTA 0 gets two, the last is partial
+    params = B.default_init("quad", h, seed=4)
+    case = SY.quad_case(n, h, 0.1, seed=4)
+    flat = _flat(params)
+    f32 = lambda t: np.ascontiguousarray(t.numpy(), np.float32)                 # noqa: E731
+    ins, cur, inr, ref = f32(case["in_state"]), f32(case["cur"]), f32(case["in_ref"]), f32(case["ref"])
+    pc = P.PHYS["quad"]()
+    nt = (n + TM - 1) // TM
+    nan = lambda rows: np.full(nt * rows * TMP, np.nan, np.float32)             # noqa: E731
+    x1, h1, h2, h3, act, sts = nan(224), nan(64), nan(64), nan(64), nan(40), nan(h * 12)
+    lossp = np.zeros(grid, np.float32)
+    err = ctypes.create_string_buffer(2048)
+    common = (_p(flat), _p(ins), _p(cur), _p(inr), _p(ref), n, h, ctypes.c_float(0.1), _p(pc), grid, _p(x1), _p(h1),
+              _p(h2), _p(h3), _p(act), _p(sts))
+    assert lib.hc_hksim_forward(*common, _p(lossp), err, 2048) == 0, err.value.decode()
+    want_loss, want_grad, _, _ = O.concurrent_value_and_grad("quad", params, case["in_state"], case["cur"],
+                                                             case["in_ref"], case["ref"], h, 0.1)
+    assert abs(float(lossp.sum()) - float(want_loss)) <= 2e-5 * abs(float(want_loss))
+    npar = lib.hc_hksim_num_params(h)
+    assert npar == flat.size
+    parts = np.zeros((grid, npar), np.float32)
+    assert lib.hc_hksim_adjoint(*common, _p(parts), err, 2048) == 0, err.value.decode()
+    grad = np.zeros(npar, np.float32)
+    lib.hc_hksim_reduce(_p(parts), grid, h, _p(grad))
+    _check_grad(grad.astype(np.float64), params, want_grad, 5e-5)
+
+    # ---- split adjoint: mma.sync dX chain + dZ stash (te model), streaming tcgen05 dW GEMM (tc model)
+    dzo, dz3, dz2, dz1, dzx = nan(40), nan(64), nan(64), nan(64), nan(224)
+    assert lib.hc_hksim_adj_dx(*common, _p(dzo), _p(dz3), _p(dz2), _p(dz1), _p(dzx), err, 2048) == 0, err.value.decode()
+    parts2 = np.full((grid, npar), np.nan, np.float32)
+    nerr = dwl.hc_simdw_adj_dw(_p(ins), _p(inr), n, grid, _p(x1), _p(h1), _p(h2), _p(h3), _p(dzo), _p(dz3), _p(dz2),
+                               _p(dz1), _p(dzx), _p(parts2), err, 2048)
+    assert nerr == 0, err.value.decode()
+    assert np.isfinite(parts2).all()
+    _check_grad(parts2.astype(np.float64).sum(0), params, want_grad, 5e-5)
