@@ -9,11 +9,22 @@
 //       launches).  The wait is bounded (~10 s of SM clocks; ranks that iterate together are microseconds apart):
 //       a lost peer poisons the gradient with NaN instead of hanging the GPU.
 #include "p2p_math.cuh"
+#ifndef APG_SIM
 #include "kernels.h"
+#endif
 
 namespace apg {
 
 namespace {
+#ifdef APG_SIM
+// CPU model (tests/hostcheck): sequentially consistent atomics stand in for the system-scope release / acquire
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { simte::st_release(p, v); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { return simte::ld_acquire(p); }
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) { return *p; }
+__device__ __forceinline__ unsigned ticket_add(unsigned* p) { return simte::atomic_inc(p); }
+__device__ __forceinline__ void fence_system() {}
+__device__ __forceinline__ long long p2p_clock() { return simte::slow_clock(); }
+#else
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -29,6 +40,10 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ticket_add(unsigned* p) { return atomicAdd(p, 1u); }
+__device__ __forceinline__ void fence_system() { __threadfence_system(); }
+__device__ __forceinline__ long long p2p_clock() { return clock64(); }
+#endif
 }  // namespace
 
 __global__ void apg_reduce_scatter_p2p_kernel(const float* __restrict__ partials, int ncta, int n, float scale,
@@ -40,14 +55,14 @@ __global__ void apg_reduce_scatter_p2p_kernel(const float* __restrict__ partials
     const float v = p2p_reduce_entry(partials, ncta, n, p2p_partial_column(p, pm_off, pm_k1, pm_npos), scale);
     for (int q = 0; q < world; ++q) slots[q][(size_t)rank * n + p] = v;
   }
-  __threadfence_system();                       // this thread's peer stores are ordered before the barrier ...
+  fence_system();                               // this thread's peer stores are ordered before the barrier ...
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();                     // ... and the CTA's stores before its ticket (cumulative fence)
-    const unsigned t = atomicAdd(ticket, 1u);
+    fence_system();                             // ... and the CTA's stores before its ticket (cumulative fence)
+    const unsigned t = ticket_add(ticket);
     if (t == gridDim.x - 1) {                   // every CTA's stores have been fenced: signal all peers
       *ticket = 0u;                             // ready for the next launch (stream order)
-      __threadfence_system();
+      fence_system();
       for (int q = 0; q < world; ++q) st_release_sys(flags[q] + rank, epoch);
     }
   }
@@ -60,11 +75,11 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
   __shared__ int s_ok;
   if (threadIdx.x == 0) {
     int ok = 1;
-    const long long t0 = clock64();
+    const long long t0 = p2p_clock();
     for (int q = 0; q < world && ok; ++q) {
       // flags only grow; (int)(flag - epoch) >= 0 also survives the 32-bit wrap of the step counter
       while ((int)(ld_acquire_sys(flags_local + q) - epoch) < 0) {
-        if (clock64() - t0 > 20000000000LL) { ok = 0; break; }
+        if (p2p_clock() - t0 > 20000000000LL) { ok = 0; break; }
       }
     }
     s_ok = ok;
@@ -82,6 +97,7 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
   if (param) p2p_sgd_entry(g, lr, momentum, momentum_buf + p, param + p);
 }
 
+#ifndef APG_SIM
 cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, float scale, int pm_off, int pm_k1,
                                       int pm_npos, float* const* slots, unsigned* const* flags, int rank, int world,
                                       unsigned epoch, unsigned* ticket, cudaStream_t st) {
@@ -97,5 +113,7 @@ cudaError_t launch_gather_sgd_p2p(const float* slots_local, const unsigned* flag
                                                              momentum_buf, lr, momentum);
   return cudaGetLastError();
 }
+
+#endif  // APG_SIM
 
 }  // namespace apg

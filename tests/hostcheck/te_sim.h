@@ -118,6 +118,14 @@ inline void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
   for (int e = 0; e < 4; ++e) c[e] = out[e];
 }
 
+inline void st_release(unsigned* p, unsigned v) { std::atomic_ref<unsigned>(*p).store(v); }
+inline unsigned ld_acquire(const unsigned* p) { return std::atomic_ref<unsigned>(*const_cast<unsigned*>(p)).load(); }
+inline unsigned atomic_inc(unsigned* p) { return std::atomic_ref<unsigned>(*p).fetch_add(1u); }
+inline long long slow_clock() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+             .count() / 1000;
+}
+
 struct Install { Install() { sim::S().on_thread_exit = thread_exit; } };
 static Install install_hooks;
 

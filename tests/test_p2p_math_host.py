@@ -153,3 +153,39 @@ def test_peer_grad_exchange_tables_and_descriptors(hp, monkeypatch):
             assert mem[off + n:off + n + 1].view(np.uint32)[0] == step
     finally:
         dist.destroy_process_group()
+
+
+def test_p2p_kernels_themselves_on_the_thread_model(tmp_path_factory):
+    """csrc/p2p_kernels.cu (unchanged source, -DAPG_SIM): every rank a launch of 128-thread CTAs on the CPU thread
+    model - ticket / last-CTA flag raise, flag wait, rank-ordered sum and fused SGD as written in the kernels"""
+    out = tmp_path_factory.mktemp("hostcheck_p2psim") / "libhostcheck_p2psim.so"
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
+                           "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "hostcheck", "hostcheck_p2psim.cpp"), "-o", str(out)])
+    lib = ctypes.CDLL(str(out))
+    world, n, ncta = 3, 300, 5
+    rng = np.random.default_rng(9)
+    total = 2 * (world * n + world)
+    mem = np.zeros(world * total, np.float32)
+    tickets = np.zeros(world, np.uint32)
+    params = np.tile(rng.standard_normal(n).astype(np.float32), (world, 1))
+    bufs = np.zeros((world, n), np.float32)
+    ref_p, ref_b = params[0].copy(), np.zeros(n, np.float32)
+    lr, mom = np.float32(1e-2), np.float32(0.9)
+    err = ctypes.create_string_buffer(1024)
+    for epoch in (1, 2, 3):
+        parts = rng.standard_normal((world, ncta, n)).astype(np.float32)
+        order = rng.permutation(world).astype(np.int32)
+        grads = np.zeros((world, n), np.float32)
+        ne = lib.hc_p2psim_step(_p(mem), world, n, epoch, _p(parts), ncta, ctypes.c_float(1.0), _p(order), _p(grads),
+                                _p(params), _p(bufs), ctypes.c_float(lr), ctypes.c_float(mom), _p(tickets), err, 1024)
+        assert ne == 0, err.value.decode()
+        want = np.zeros(n, np.float32)
+        for q in range(world):
+            want = want + _reduce_like_kernel(parts[q], 1.0)
+        ref_b = mom * ref_b + want
+        ref_p = ref_p - lr * ref_b
+        for r in range(world):
+            assert np.array_equal(grads[r], want)
+            assert np.array_equal(params[r], ref_p) and np.array_equal(bufs[r], ref_b)
+        assert (tickets == 0).all()                                       # reset by the last CTA of each launch

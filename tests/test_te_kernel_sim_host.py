@@ -246,3 +246,29 @@ def test_hutter_kernels_on_the_model_reproduce_oracle_loss_and_gradient(hk):
     assert nerr == 0, err.value.decode()
     assert np.isfinite(parts2).all()
     _check_grad(parts2.astype(np.float64).sum(0), params, want_grad, 5e-5)
+
+
+def test_quad_eval_kernel_on_the_model_autoregressive_policy(te):
+    """Net(15, h, 9, 4) (out_dim 4: the policy is called once per step and its whole output is the action)"""
+    import bench as B
+    g = load_golden("eval_rand.npz")
+    h, dt, steps, n = 10, 0.1, 8, 40
+    params = B.default_init("quad", h, seed=3, mode="autoregressive")
+    tabs = np.ascontiguousarray(g["tight_table"][None, :60], np.float32)
+    index = np.zeros(n, np.int32)
+    rng = np.random.default_rng(4)
+    init = np.zeros((n, 12), np.float32)
+    init[:, :3] = tabs[0, 0, :3] + rng.normal(0, 0.05, (n, 3))
+    init[:, 6:9] = rng.normal(0, 0.1, (n, 3))
+    states = np.zeros((n, steps + 1, 12), np.float32)
+    div, act = np.zeros((n, steps), np.float32), np.zeros((n, steps, 4), np.float32)
+    nst = np.zeros(n, np.int32)
+    err = ctypes.create_string_buffer(2048)
+    nerr = te.hc_tesim_eval_rollout(_p(_flat(params)), h, 4, _p(tabs), _p(index), tabs.shape[1], _p(init), n, steps,
+                                    ctypes.c_float(dt), _p(P.PHYS["quad"]()), ctypes.c_float(0.5), ctypes.c_float(0.4),
+                                    1, 1, _p(states), _p(div), _p(act), _p(nst), err, 2048)
+    assert nerr == 0, err.value.decode()
+    want = O.eval_follow_tables(params, torch.tensor(tabs).repeat(n, 1, 1), torch.tensor(init), steps, h, dt, 0.5, 0.4, 1)
+    assert np.array_equal(nst, want["n_steps"].numpy())
+    assert np.abs(states - want["states"].numpy()).max() <= 1e-4
+    assert np.abs(act - want["actions"].numpy()).max() <= 1e-4
