@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(128) apg_reduce4_kernel(const float* __restric
 }
 
 cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st) {
-  apg_reduce4_kernel<<<(n + 31) / 32, 128, 0, st>>>(partials, ncta, n, scale, grad);
+  APG_LAUNCH((n + 31) / 32, 128, 0, st, apg_reduce4_kernel)(partials, ncta, n, scale, grad);
   return cudaGetLastError();
 }
 
@@ -255,7 +255,7 @@ bool adj_dw_tc_supported(const HutterLayout& y, int h) {
 cudaError_t launch_adj_dw_tc(const HutterLayout& y, const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(adj_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  adj_dw_tc_kernel<<<grid, DW_THREADS, DW_SMEM_BYTES, st>>>(y, a, z);
+  APG_LAUNCH(grid, DW_THREADS, DW_SMEM_BYTES, st, adj_dw_tc_kernel)(y, a, z);
   return cudaGetLastError();
 }
 

@@ -381,7 +381,7 @@ cudaError_t launch_eval_cartpole(const SimpleLayout& y, const float* wf, const f
   const size_t smem = eval_cartpole_smem_bytes(y);
   cudaError_t e = cudaFuncSetAttribute(eval_cartpole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  eval_cartpole_kernel<<<grid, NT, smem, st>>>(y, a);
+  APG_LAUNCH(grid, NT, smem, st, eval_cartpole_kernel)(y, a);
   return cudaGetLastError();
 }
 #endif  // APG_SIM
@@ -403,7 +403,7 @@ cudaError_t launch_eval_wing(const HutterLayout& y, const float* wf, const float
   const size_t smem = eval_wing_smem_bytes(y);
   cudaError_t e = cudaFuncSetAttribute(eval_wing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  eval_wing_kernel<<<grid, NT, smem, st>>>(y, a);
+  APG_LAUNCH(grid, NT, smem, st, eval_wing_kernel)(y, a);
   return cudaGetLastError();
 }
 
@@ -423,7 +423,7 @@ cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const fl
   const size_t smem = eval_smem_bytes(y);
   cudaError_t e = cudaFuncSetAttribute(eval_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  eval_rollout_kernel<<<grid, NT, smem, st>>>(y, a);
+  APG_LAUNCH(grid, NT, smem, st, eval_rollout_kernel)(y, a);
   return cudaGetLastError();
 }
 

@@ -156,7 +156,7 @@ cudaError_t launch_hutter_adj_dx(int system, const HutterLayout& y, const Rollou
   cudaError_t e = cudaFuncSetAttribute(hutter_adj_dx_kernel<Quad, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
-  hutter_adj_dx_kernel<Quad, true><<<grid, NTH_DX, smem, st>>>(y, a, z);
+  APG_LAUNCH(grid, NTH_DX, smem, st, hutter_adj_dx_kernel<Quad, true>)(y, a, z);
   return cudaGetLastError();
 }
 

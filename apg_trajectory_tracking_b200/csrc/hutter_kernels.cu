@@ -323,10 +323,10 @@ cudaError_t launch_hutter_fwd(int system, const HutterLayout& y, const RolloutAr
   cudaError_t e;
   if (system == SYS_QUAD && y.conv) {
     if ((e = set_smem(hutter_fwd_kernel<Quad, true>, smem)) != cudaSuccess) return e;
-    hutter_fwd_kernel<Quad, true><<<grid, NTH, smem, st>>>(y, a);
+    APG_LAUNCH(grid, NTH, smem, st, hutter_fwd_kernel<Quad, true>)(y, a);
   } else if (system == SYS_WING && !y.conv) {
     if ((e = set_smem(hutter_fwd_kernel<Wing, false>, smem)) != cudaSuccess) return e;
-    hutter_fwd_kernel<Wing, false><<<grid, NTH, smem, st>>>(y, a);
+    APG_LAUNCH(grid, NTH, smem, st, hutter_fwd_kernel<Wing, false>)(y, a);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -338,10 +338,10 @@ cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutAr
   cudaError_t e;
   if (system == SYS_QUAD && y.conv) {
     if ((e = set_smem(hutter_adj_kernel<Quad, true>, smem)) != cudaSuccess) return e;
-    hutter_adj_kernel<Quad, true><<<grid, NTH, smem, st>>>(y, a);
+    APG_LAUNCH(grid, NTH, smem, st, hutter_adj_kernel<Quad, true>)(y, a);
   } else if (system == SYS_WING && !y.conv) {
     if ((e = set_smem(hutter_adj_kernel<Wing, false>, smem)) != cudaSuccess) return e;
-    hutter_adj_kernel<Wing, false><<<grid, NTH, smem, st>>>(y, a);
+    APG_LAUNCH(grid, NTH, smem, st, hutter_adj_kernel<Wing, false>)(y, a);
   } else {
     return cudaErrorInvalidValue;
   }

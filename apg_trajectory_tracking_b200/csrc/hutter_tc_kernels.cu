@@ -525,12 +525,12 @@ cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, 
                                     const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
   if (params) {                                  // nullptr: the images of the tcgen05 forward call are still valid
-    apg_pack_tc_kernel<<<(PAIRS_TOTAL + B_TOTAL + 255) / 256, 256, 0, st>>>(params, y, blob);
+    APG_LAUNCH((PAIRS_TOTAL + B_TOTAL + 255) / 256, 256, 0, st, apg_pack_tc_kernel)(params, y, blob);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   e = cudaFuncSetAttribute(hutter_adj_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  hutter_adj_dx_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(blob, y, a, z);
+  APG_LAUNCH(grid, TC_THREADS, TC_SMEM_BYTES, st, hutter_adj_dx_tc_kernel)(blob, y, a, z);
   return cudaGetLastError();
 }
 
@@ -542,12 +542,12 @@ bool tc_fwd_supported(const HutterLayout& y, int h) {
 
 cudaError_t launch_hutter_fwd_tc(const HutterLayout& y, const float* params, unsigned char* blob,
                                  const RolloutArgs& a, int grid, cudaStream_t st) {
-  apg_pack_tc_kernel<<<(PAIRS_TOTAL + B_TOTAL + 255) / 256, 256, 0, st>>>(params, y, blob);
+  APG_LAUNCH((PAIRS_TOTAL + B_TOTAL + 255) / 256, 256, 0, st, apg_pack_tc_kernel)(params, y, blob);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(hutter_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  hutter_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(blob, y, a);
+  APG_LAUNCH(grid, TC_THREADS, TC_SMEM_BYTES, st, hutter_fwd_tc_kernel)(blob, y, a);
   return cudaGetLastError();
 }
 #endif  // APG_TC_SIM

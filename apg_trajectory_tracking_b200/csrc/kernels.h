@@ -1,6 +1,8 @@
 // Host-side launcher declarations (definitions in the *_kernels.cu files).
 #pragma once
+#ifndef APG_SIM
 #include <cuda_runtime.h>
+#endif
 #include "layouts.h"
 #include "rollout_args.h"
 #include "eval_math.cuh"

@@ -13,6 +13,16 @@
 // by apg_pack_kernel once per call from the torch-flat vector.
 #pragma once
 
+// Kernel launch.  CUDA: expands to exactly `kernel<<<grid, block, smem, stream>>>` (the kernel name comes last so that
+// template arguments with commas survive the preprocessor).  -DAPG_SIM (tests only): every CTA of the grid runs on
+// the CPU model of tests/hostcheck/gpu_sim.h, one OS thread per GPU thread.
+#ifdef APG_SIM
+#define APG_LAUNCH(grid, block, smem, stream, ...) \
+  ::sim::Launcher((grid), (block)).bind([&](auto&&... sim_args_) { __VA_ARGS__(sim_args_...); })
+#else
+#define APG_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
+#endif
+
 namespace apg {
 
 enum NetKind { NET_HUTTER_CONV = 0, NET_HUTTER_LIN = 1, NET_SIMPLE = 2, NET_LSTM = 3 };

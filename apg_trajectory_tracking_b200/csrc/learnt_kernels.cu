@@ -141,7 +141,7 @@ static cudaError_t launch_fwd_t(const float* params, const PhysConsts& pc, const
   const size_t smem = sizeof(float) * (RW::NP + 1 + (size_t)RW::HD * LP);
   cudaError_t e = cudaFuncSetAttribute(learnt_fwd_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  learnt_fwd_kernel<M><<<learnt_grid(n, sms), LT, smem, st>>>(params, pc, s, a, dt, n, out);
+  APG_LAUNCH(learnt_grid(n, sms), LT, smem, st, learnt_fwd_kernel<M>)(params, pc, s, a, dt, n, out);
   return cudaGetLastError();
 }
 
@@ -154,7 +154,7 @@ static cudaError_t launch_adj_t(const float* params, const PhysConsts& pc, const
   cudaError_t e = cudaFuncSetAttribute(learnt_adj_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int grid = learnt_grid(n, sms);
-  learnt_adj_kernel<M><<<grid, LT, smem, st>>>(params, pc, s, a, dt, n, g, gs, ga, grad_params ? partials : nullptr);
+  APG_LAUNCH(grid, LT, smem, st, learnt_adj_kernel<M>)(params, pc, s, a, dt, n, g, gs, ga, grad_params ? partials : nullptr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (grad_params) return launch_reduce_grad(partials, grid, RW::NP, 1.0f, grad_params, st);
   return cudaSuccess;

@@ -363,7 +363,7 @@ cudaError_t launch_lstm_fwd(const LstmLayout& y, const RolloutArgs& a, int grid,
   const size_t smem = lstm_fwd_smem_bytes(y, a.h);
   cudaError_t e = cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  lstm_fwd_kernel<<<grid, NT, smem, st>>>(y, a);
+  APG_LAUNCH(grid, NT, smem, st, lstm_fwd_kernel)(y, a);
   return cudaGetLastError();
 }
 
@@ -371,7 +371,7 @@ cudaError_t launch_lstm_adj(const LstmLayout& y, const RolloutArgs& a, int grid,
   const size_t smem = lstm_adj_smem_bytes(y, a.h);
   cudaError_t e = cudaFuncSetAttribute(lstm_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  lstm_adj_kernel<<<grid, NT, smem, st>>>(y, a);
+  APG_LAUNCH(grid, NT, smem, st, lstm_adj_kernel)(y, a);
   return cudaGetLastError();
 }
 

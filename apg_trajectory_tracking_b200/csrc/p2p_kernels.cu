@@ -101,7 +101,7 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
 cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, float scale, int pm_off, int pm_k1,
                                       int pm_npos, float* const* slots, unsigned* const* flags, int rank, int world,
                                       unsigned epoch, unsigned* ticket, cudaStream_t st) {
-  apg_reduce_scatter_p2p_kernel<<<(n + 127) / 128, 128, 0, st>>>(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
+  APG_LAUNCH((n + 127) / 128, 128, 0, st, apg_reduce_scatter_p2p_kernel)(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
                                                                  slots, flags, rank, world, epoch, ticket);
   return cudaGetLastError();
 }
@@ -109,7 +109,7 @@ cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, fl
 cudaError_t launch_gather_sgd_p2p(const float* slots_local, const unsigned* flags_local, int world, int n,
                                   unsigned epoch, float* grad_out, float* param, float* momentum_buf, float lr,
                                   float momentum, cudaStream_t st) {
-  apg_gather_sgd_p2p_kernel<<<(n + 127) / 128, 128, 0, st>>>(slots_local, flags_local, world, n, epoch, grad_out, param,
+  APG_LAUNCH((n + 127) / 128, 128, 0, st, apg_gather_sgd_p2p_kernel)(slots_local, flags_local, world, n, epoch, grad_out, param,
                                                              momentum_buf, lr, momentum);
   return cudaGetLastError();
 }

@@ -26,17 +26,19 @@ __global__ void apg_prep_quad_state_kernel(const float* s, size_t n, float* cur_
   if (i < n) prep_quad_state_body(i, s, cur_out, in_state);
 }
 
+#ifndef APG_SIM
 cudaError_t launch_prepare_quad(const float* states, const float* ref, int n, int L, float* in_state, float* cur_out,
                                 float* in_ref, float* ref_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const size_t total = (size_t)n * L * 9;
   // rows first: they read the raw drone position that the state kernel may zero in place
   if ((in_ref || ref_out) && total)
-    apg_prep_quad_rows_kernel<<<blocks_for(total), PREP_THREADS, 0, st>>>(states, ref, total, L, in_ref, ref_out);
+    APG_LAUNCH(blocks_for(total), PREP_THREADS, 0, st, apg_prep_quad_rows_kernel)(states, ref, total, L, in_ref, ref_out);
   if (in_state || cur_out)
-    apg_prep_quad_state_kernel<<<blocks_for((size_t)n), PREP_THREADS, 0, st>>>(states, (size_t)n, cur_out, in_state);
+    APG_LAUNCH(blocks_for((size_t)n), PREP_THREADS, 0, st, apg_prep_quad_state_kernel)(states, (size_t)n, cur_out, in_state);
   return cudaGetLastError();
 }
+#endif  // APG_SIM
 
 __global__ void apg_prep_wing_line_kernel(const float* __restrict__ s, const float* __restrict__ target, float vlen,
                                           int h, size_t total, float* __restrict__ ref_out) {
@@ -50,6 +52,7 @@ __global__ void apg_prep_wing_state_kernel(const float* s, const float* target, 
   if (i < n) prep_wing_state_body(i, s, target, nc, vlen, h, in_state, in_ref, cur_out);
 }
 
+#ifndef APG_SIM
 cudaError_t launch_prepare_wing(const float* states, const float* targets, const float* mean_host,
                                 const float* std_host, float dt, int h, int n, float* in_state, float* cur_out,
                                 float* in_ref, float* ref_out, cudaStream_t st) {
@@ -59,12 +62,13 @@ cudaError_t launch_prepare_wing(const float* states, const float* targets, const
   const float vlen = (float)(12.0 * (double)dt);          // `12 * self.dt` is a Python double, cast once
   const size_t total = (size_t)n * h * 3;
   if (ref_out && total)
-    apg_prep_wing_line_kernel<<<blocks_for(total), PREP_THREADS, 0, st>>>(states, targets, vlen, h, total, ref_out);
+    APG_LAUNCH(blocks_for(total), PREP_THREADS, 0, st, apg_prep_wing_line_kernel)(states, targets, vlen, h, total, ref_out);
   if (in_state || in_ref || cur_out)
-    apg_prep_wing_state_kernel<<<blocks_for((size_t)n), PREP_THREADS, 0, st>>>(states, targets, nc, vlen, h, (size_t)n,
+    APG_LAUNCH(blocks_for((size_t)n), PREP_THREADS, 0, st, apg_prep_wing_state_kernel)(states, targets, nc, vlen, h, (size_t)n,
                                                                                in_state, in_ref, cur_out);
   return cudaGetLastError();
 }
+#endif  // APG_SIM
 
 __global__ void apg_poly_rows_kernel(const float* __restrict__ coef, size_t rows, int L, float t_first, float dt,
                                      float* __restrict__ out) {
@@ -72,13 +76,15 @@ __global__ void apg_poly_rows_kernel(const float* __restrict__ coef, size_t rows
   if (row < rows) poly_rows_body(row, coef, L, t_first, dt, out);
 }
 
+#ifndef APG_SIM
 cudaError_t launch_poly_reference(const float* coef, int n, int L, float t_first, float dt, float* out,
                                   cudaStream_t st) {
   const size_t rows = (size_t)n * L;
   if (rows == 0) return cudaSuccess;
-  apg_poly_rows_kernel<<<blocks_for(rows), PREP_THREADS, 0, st>>>(coef, rows, L, t_first, dt, out);
+  APG_LAUNCH(blocks_for(rows), PREP_THREADS, 0, st, apg_poly_rows_kernel)(coef, rows, L, t_first, dt, out);
   return cudaGetLastError();
 }
+#endif  // APG_SIM
 
 __global__ void apg_sample_windows_kernel(const float* __restrict__ traj, int W, int L, int stride, size_t total_ref,
                                           size_t total, float* __restrict__ states, float* __restrict__ refs) {
@@ -86,14 +92,16 @@ __global__ void apg_sample_windows_kernel(const float* __restrict__ traj, int W,
   if (idx < total) sample_windows_body(idx, traj, W, L, stride, total_ref, states, refs);
 }
 
+#ifndef APG_SIM
 cudaError_t launch_sample_windows(const float* traj, int W, int L, int stride, int n, float* states, float* refs,
                                   cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const size_t total_ref = (size_t)n * L * 9, total = total_ref + (size_t)n * 12;
-  apg_sample_windows_kernel<<<blocks_for(total), PREP_THREADS, 0, st>>>(traj, W, L, stride, total_ref, total, states,
+  APG_LAUNCH(blocks_for(total), PREP_THREADS, 0, st, apg_sample_windows_kernel)(traj, W, L, stride, total_ref, total, states,
                                                                         refs);
   return cudaGetLastError();
 }
+#endif  // APG_SIM
 
 __global__ void apg_ref_table_kernel(const float* __restrict__ traj, int W, int nth, float speed, float z_offset,
                                      size_t rows, float* __restrict__ out) {
@@ -101,13 +109,15 @@ __global__ void apg_ref_table_kernel(const float* __restrict__ traj, int W, int 
   if (k < rows) ref_table_body(k, traj, W, nth, speed, z_offset, out);
 }
 
+#ifndef APG_SIM
 cudaError_t launch_reference_table(const float* traj, int W, int nth, float speed, float z_offset, int rows,
                                    float* out, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  apg_ref_table_kernel<<<blocks_for((size_t)rows), PREP_THREADS, 0, st>>>(traj, W, nth, speed, z_offset, (size_t)rows,
+  APG_LAUNCH(blocks_for((size_t)rows), PREP_THREADS, 0, st, apg_ref_table_kernel)(traj, W, nth, speed, z_offset, (size_t)rows,
                                                                          out);
   return cudaGetLastError();
 }
+#endif  // APG_SIM
 
 __global__ void apg_poly_march_kernel(const double* __restrict__ coef, int degree, const double* __restrict__ rot,
                                       const double* __restrict__ start, int n, double x_start, double x_range,
@@ -120,14 +130,16 @@ __global__ void apg_poly_march_kernel(const double* __restrict__ coef, int degre
   if (ref_len) ref_len[i] = len;
 }
 
+#ifndef APG_SIM
 cudaError_t launch_polynomial_points(const double* coef, int degree, const double* rot, const double* start, int n,
                                      double x_start, double x_range, double dist_points, int hover, int max_rows,
                                      float* out, int* ref_len, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   // one thread per trajectory (sequential march): small blocks spread few trajectories over many SMs
-  apg_poly_march_kernel<<<(n + 31) / 32, 32, 0, st>>>(coef, degree, rot, start, n, x_start, x_range, dist_points,
+  APG_LAUNCH((n + 31) / 32, 32, 0, st, apg_poly_march_kernel)(coef, degree, rot, start, n, x_start, x_range, dist_points,
                                                       hover, max_rows, out, ref_len);
   return cudaGetLastError();
 }
+#endif  // APG_SIM
 
 }  // namespace apg

@@ -294,7 +294,7 @@ cudaError_t launch_rec_fwd(const HutterLayout& y, const RolloutArgs& a, int grid
   const size_t smem = rec_fwd_smem_bytes(y, a.h);
   cudaError_t e = cudaFuncSetAttribute(rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  rec_fwd_kernel<<<grid, NT, smem, st>>>(y, a);
+  APG_LAUNCH(grid, NT, smem, st, rec_fwd_kernel)(y, a);
   return cudaGetLastError();
 }
 
@@ -302,7 +302,7 @@ cudaError_t launch_rec_adj(const HutterLayout& y, const RolloutArgs& a, int grid
   const size_t smem = rec_adj_smem_bytes(y, a.h);
   cudaError_t e = cudaFuncSetAttribute(rec_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  rec_adj_kernel<<<grid, NT, smem, st>>>(y, a);
+  APG_LAUNCH(grid, NT, smem, st, rec_adj_kernel)(y, a);
   return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct SimDim3 { unsigned x = 0, y = 0, z = 0; };
-static thread_local SimDim3 threadIdx, blockIdx, blockDim, gridDim;
+inline thread_local SimDim3 threadIdx, blockIdx, blockDim, gridDim;
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

@@ -44,7 +44,7 @@ namespace apg {
 namespace tcp {
 
 struct QueuedMma { uint32_t d, a_tmem; uint64_t a_desc, b_desc; uint32_t idesc, acc; bool ts; };
-static thread_local std::vector<QueuedMma> t_queue;
+inline thread_local std::vector<QueuedMma> t_queue;
 
 inline unsigned char* dynamic_smem() { return sim::S().smem; }
 inline void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {

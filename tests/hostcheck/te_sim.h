@@ -68,8 +68,8 @@ inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint6
   sim::S().cv.notify_all();
 }
 struct PendingStore { void* dst; const void* src; uint32_t bytes; };
-static thread_local std::vector<std::vector<PendingStore>> t_groups;      // committed groups, oldest first
-static thread_local std::vector<PendingStore> t_open;
+inline thread_local std::vector<std::vector<PendingStore>> t_groups;      // committed groups, oldest first
+inline thread_local std::vector<PendingStore> t_open;
 inline void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
   if ((bytes & 15u) || ((uintptr_t)dst_gmem & 15u) || ((uintptr_t)src_smem & 15u))
     sim::fail("cp.async.bulk s2g: size / address not 16-byte aligned");
@@ -127,6 +127,6 @@ inline long long slow_clock() {
 }
 
 struct Install { Install() { sim::S().on_thread_exit = thread_exit; } };
-static Install install_hooks;
+inline Install install_hooks;
 
 }  // namespace simte
