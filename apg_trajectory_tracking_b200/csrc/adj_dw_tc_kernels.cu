@@ -14,8 +14,8 @@
 #include "rollout_args.h"
 #ifndef APG_TC_SIM
 #include "tile_engine.cuh"
-#include "kernels.h"
 #endif
+#include "kernels.h"
 
 namespace apg {
 
@@ -229,7 +229,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   }
 }
 
-#ifndef APG_TC_SIM
 // grad[p] = scale * sum over CTAs of partials[c][p]: 32 parameters x 4 CTA slices per block of 128 threads
 __global__ void __launch_bounds__(128) apg_reduce4_kernel(const float* __restrict__ partials, int ncta, int n,
                                                           float scale, float* __restrict__ grad) {
@@ -259,6 +258,5 @@ cudaError_t launch_adj_dw_tc(const HutterLayout& y, const RolloutArgs& a, const 
   return cudaGetLastError();
 }
 
-#endif  // APG_TC_SIM
 
 }  // namespace apg

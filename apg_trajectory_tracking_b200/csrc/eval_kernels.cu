@@ -7,9 +7,7 @@
 #include "hutter_policy.cuh"
 #include "layouts.h"
 #include "tile_engine.cuh"
-#ifndef APG_SIM
 #include "kernels.h"
-#endif
 
 namespace apg {
 
@@ -365,7 +363,6 @@ __global__ void __launch_bounds__(NT, 1) eval_cartpole_kernel(const SimpleLayout
   }
 }
 
-#ifndef APG_SIM
 size_t eval_cartpole_smem_bytes(const SimpleLayout& y) {
   return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + y.rows_total * TMP) + 16;
 }
@@ -384,9 +381,7 @@ cudaError_t launch_eval_cartpole(const SimpleLayout& y, const float* wf, const f
   APG_LAUNCH(grid, NT, smem, st, eval_cartpole_kernel)(y, a);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
-#ifndef APG_SIM
 size_t eval_wing_smem_bytes(const HutterLayout& y) {
   return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + pad4(TM * y.LR) + y.XR * TMP + HID * TMP) + 16;
 }
@@ -427,6 +422,5 @@ cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const fl
   return cudaGetLastError();
 }
 
-#endif  // APG_SIM
 
 }  // namespace apg

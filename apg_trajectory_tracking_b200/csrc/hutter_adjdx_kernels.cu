@@ -9,9 +9,7 @@
 #include "rollout_args.h"
 #include "tile_engine.cuh"
 #include "hutter_policy.cuh"
-#ifndef APG_SIM
 #include "kernels.h"
-#endif
 
 namespace apg {
 
@@ -144,7 +142,6 @@ __global__ void __launch_bounds__(NTH_DX, 1) hutter_adj_dx_kernel(const HutterLa
   }
 }
 
-#ifndef APG_SIM
 size_t hutter_adj_dx_smem_bytes(const HutterLayout& y) {
   return sizeof(float) * (size_t)(y.b_ws + y.K1 * TMP + 3 * HID * TMP + y.Mo4 * TMP + 8) + 80;
 }
@@ -160,6 +157,5 @@ cudaError_t launch_hutter_adj_dx(int system, const HutterLayout& y, const Rollou
   return cudaGetLastError();
 }
 
-#endif  // APG_SIM
 
 }  // namespace apg

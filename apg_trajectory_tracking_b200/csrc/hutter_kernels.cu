@@ -301,7 +301,6 @@ __global__ void __launch_bounds__(NTH, 1) hutter_adj_kernel(const HutterLayout y
   }
 }
 
-#ifndef APG_SIM
 // ------------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------------
@@ -348,6 +347,5 @@ cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutAr
   return cudaGetLastError();
 }
 
-#endif  // APG_SIM
 
 }  // namespace apg

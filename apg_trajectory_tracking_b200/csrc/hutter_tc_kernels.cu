@@ -15,8 +15,8 @@
 #include "rollout_args.h"
 #ifndef APG_TC_SIM
 #include "tile_engine.cuh"
-#include "kernels.h"
 #endif
+#include "kernels.h"
 
 namespace apg {
 
@@ -520,7 +520,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-#ifndef APG_TC_SIM
 cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, unsigned char* blob,
                                     const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st) {
   cudaError_t e = cudaSuccess;
@@ -550,6 +549,5 @@ cudaError_t launch_hutter_fwd_tc(const HutterLayout& y, const float* params, uns
   APG_LAUNCH(grid, TC_THREADS, TC_SMEM_BYTES, st, hutter_fwd_tc_kernel)(blob, y, a);
   return cudaGetLastError();
 }
-#endif  // APG_TC_SIM
 
 }  // namespace apg

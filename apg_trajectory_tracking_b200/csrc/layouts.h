@@ -18,7 +18,7 @@
 // the CPU model of tests/hostcheck/gpu_sim.h, one OS thread per GPU thread.
 #ifdef APG_SIM
 #define APG_LAUNCH(grid, block, smem, stream, ...) \
-  ::sim::Launcher((grid), (block)).bind([&](auto&&... sim_args_) { __VA_ARGS__(sim_args_...); })
+  ::sim::Launcher((grid), (block), (size_t)(smem)).bind([&](auto&&... sim_args_) { __VA_ARGS__(sim_args_...); })
 #else
 #define APG_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
 #endif

@@ -14,10 +14,10 @@
 //            block, summed in fixed order by apg_reduce_kernel -> bitwise reproducible.
 #include "learnt_math.cuh"
 #include "learnt_wing_math.cuh"
+#include "kernels.h"
 #ifdef APG_SIM
 #define APG_LEARNT_DYNAMIC_SMEM(name) float* name = reinterpret_cast<float*>(::simte::dynamic_smem())
 #else
-#include "kernels.h"
 #define APG_LEARNT_DYNAMIC_SMEM(name) extern __shared__ __align__(16) float name[]
 #endif
 
@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(LT) learnt_adj_kernel(const float* __restrict_
   }
 }
 
-#ifndef APG_SIM
 int learnt_num_params(int system) {
   return system == SYS_WING ? LearntRows<LearntWing<float>::NPH>::NP : LearntRows<LearntQuad<float>::NPH>::NP;
 }
@@ -180,6 +179,5 @@ cudaError_t launch_learnt_adj(int system, const float* params, const PhysConsts&
   return cudaErrorInvalidValue;
 }
 
-#endif  // APG_SIM
 
 }  // namespace apg

@@ -18,7 +18,7 @@ namespace apg {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(NT, 1) lstm_fwd_kernel(const LstmLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Quad<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW, HS = LSTM_HS;
   const int h = g.h;
@@ -206,7 +206,7 @@ __device__ __forceinline__ void lstm_dw_gates(const Lane& L, const LstmLayout& y
 }
 
 __global__ void __launch_bounds__(NT, 1) lstm_adj_kernel(const LstmLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Quad<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW, HS = LSTM_HS;
   const int h = g.h;

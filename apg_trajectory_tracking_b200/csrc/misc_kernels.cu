@@ -47,13 +47,11 @@ __global__ void apg_pack_kernel(const PackTable t, const float* __restrict__ par
   }
 }
 
-#ifndef APG_SIM
 cudaError_t launch_pack(const PackTable& t, const float* params, float* wf, float* wb, cudaStream_t st) {
   dim3 grid(8, t.n);
   APG_LAUNCH(grid, 256, 0, st, apg_pack_kernel)(t, params, wf, wb);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 // grad[p] = scale * sum_c partials[c][p], fixed summation order -> bitwise reproducible
 // The kernels keep the fc1 weight-gradient block [64][K1] of the hutter conv nets in their position-major column
@@ -83,13 +81,11 @@ __global__ void apg_reduce_kernel(const float* __restrict__ partials, int ncta, 
   grad[p] = scale * ((s0 + s1) + (s2 + s3));
 }
 
-#ifndef APG_SIM
 cudaError_t launch_reduce_grad(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st,
                                int pm_off, int pm_k1, int pm_npos) {
   APG_LAUNCH((n + 127) / 128, 128, 0, st, apg_reduce_kernel)(partials, ncta, n, scale, grad, pm_off, pm_k1, pm_npos);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 __global__ void apg_sum_loss_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ loss) {
   // one warp, fixed order; accumulate in double (148 partials of ~1e5 magnitude)
@@ -99,12 +95,10 @@ __global__ void apg_sum_loss_kernel(const float* __restrict__ partials, int ncta
   if (threadIdx.x == 0) *loss = (float)s;
 }
 
-#ifndef APG_SIM
 cudaError_t launch_sum_loss(const float* partials, int ncta, float* loss, cudaStream_t st) {
   APG_LAUNCH(1, 32, 0, st, apg_sum_loss_kernel)(partials, ncta, loss);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 // ---- single dynamics steps (un-fused callers: Dynamics.__call__)
 template <template <typename> class SysT>
@@ -142,7 +136,6 @@ __global__ void apg_step_adj_kernel(const PhysConsts pc, const float* __restrict
   for (int j = 0; j < Sys::A; ++j) ga[(size_t)i * Sys::A + j] = gao[j];
 }
 
-#ifndef APG_SIM
 cudaError_t launch_step(int system, const PhysConsts& pc, const float* s, const float* a, float dt, int n, float* out,
                         cudaStream_t st) {
   const int b = 128, gr = (n + b - 1) / b;
@@ -153,9 +146,7 @@ cudaError_t launch_step(int system, const PhysConsts& pc, const float* s, const 
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
-#ifndef APG_SIM
 cudaError_t launch_step_adj(int system, const PhysConsts& pc, const float* s, const float* a, float dt, int n,
                             const float* g, float* gs, float* ga, cudaStream_t st) {
   const int b = 128, gr = (n + b - 1) / b;
@@ -166,7 +157,6 @@ cudaError_t launch_step_adj(int system, const PhysConsts& pc, const float* s, co
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 __global__ void apg_features_kernel(const float* __restrict__ s, int n, float* __restrict__ f) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,19 +183,15 @@ __global__ void apg_features_adj_kernel(const float* __restrict__ s, const float
   for (int j = 0; j < 12; ++j) gs[(size_t)i * 12 + j] = go[j];
 }
 
-#ifndef APG_SIM
 cudaError_t launch_features(const float* s, int n, float* f, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   APG_LAUNCH((n + 127) / 128, 128, 0, st, apg_features_kernel)(s, n, f);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
-#ifndef APG_SIM
 cudaError_t launch_features_adj(const float* s, const float* gf, int n, float* gs, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   APG_LAUNCH((n + 127) / 128, 128, 0, st, apg_features_adj_kernel)(s, gf, n, gs);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 }  // namespace apg

@@ -9,9 +9,7 @@
 //       launches).  The wait is bounded (~10 s of SM clocks; ranks that iterate together are microseconds apart):
 //       a lost peer poisons the gradient with NaN instead of hanging the GPU.
 #include "p2p_math.cuh"
-#ifndef APG_SIM
 #include "kernels.h"
-#endif
 
 namespace apg {
 
@@ -97,7 +95,6 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
   if (param) p2p_sgd_entry(g, lr, momentum, momentum_buf + p, param + p);
 }
 
-#ifndef APG_SIM
 cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, float scale, int pm_off, int pm_k1,
                                       int pm_npos, float* const* slots, unsigned* const* flags, int rank, int world,
                                       unsigned epoch, unsigned* ticket, cudaStream_t st) {
@@ -114,6 +111,5 @@ cudaError_t launch_gather_sgd_p2p(const float* slots_local, const unsigned* flag
   return cudaGetLastError();
 }
 
-#endif  // APG_SIM
 
 }  // namespace apg

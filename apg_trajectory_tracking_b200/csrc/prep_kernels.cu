@@ -26,7 +26,6 @@ __global__ void apg_prep_quad_state_kernel(const float* s, size_t n, float* cur_
   if (i < n) prep_quad_state_body(i, s, cur_out, in_state);
 }
 
-#ifndef APG_SIM
 cudaError_t launch_prepare_quad(const float* states, const float* ref, int n, int L, float* in_state, float* cur_out,
                                 float* in_ref, float* ref_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
@@ -38,7 +37,6 @@ cudaError_t launch_prepare_quad(const float* states, const float* ref, int n, in
     APG_LAUNCH(blocks_for((size_t)n), PREP_THREADS, 0, st, apg_prep_quad_state_kernel)(states, (size_t)n, cur_out, in_state);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 __global__ void apg_prep_wing_line_kernel(const float* __restrict__ s, const float* __restrict__ target, float vlen,
                                           int h, size_t total, float* __restrict__ ref_out) {
@@ -52,7 +50,6 @@ __global__ void apg_prep_wing_state_kernel(const float* s, const float* target, 
   if (i < n) prep_wing_state_body(i, s, target, nc, vlen, h, in_state, in_ref, cur_out);
 }
 
-#ifndef APG_SIM
 cudaError_t launch_prepare_wing(const float* states, const float* targets, const float* mean_host,
                                 const float* std_host, float dt, int h, int n, float* in_state, float* cur_out,
                                 float* in_ref, float* ref_out, cudaStream_t st) {
@@ -68,7 +65,6 @@ cudaError_t launch_prepare_wing(const float* states, const float* targets, const
                                                                                in_state, in_ref, cur_out);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 __global__ void apg_poly_rows_kernel(const float* __restrict__ coef, size_t rows, int L, float t_first, float dt,
                                      float* __restrict__ out) {
@@ -76,7 +72,6 @@ __global__ void apg_poly_rows_kernel(const float* __restrict__ coef, size_t rows
   if (row < rows) poly_rows_body(row, coef, L, t_first, dt, out);
 }
 
-#ifndef APG_SIM
 cudaError_t launch_poly_reference(const float* coef, int n, int L, float t_first, float dt, float* out,
                                   cudaStream_t st) {
   const size_t rows = (size_t)n * L;
@@ -84,7 +79,6 @@ cudaError_t launch_poly_reference(const float* coef, int n, int L, float t_first
   APG_LAUNCH(blocks_for(rows), PREP_THREADS, 0, st, apg_poly_rows_kernel)(coef, rows, L, t_first, dt, out);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 __global__ void apg_sample_windows_kernel(const float* __restrict__ traj, int W, int L, int stride, size_t total_ref,
                                           size_t total, float* __restrict__ states, float* __restrict__ refs) {
@@ -92,7 +86,6 @@ __global__ void apg_sample_windows_kernel(const float* __restrict__ traj, int W,
   if (idx < total) sample_windows_body(idx, traj, W, L, stride, total_ref, states, refs);
 }
 
-#ifndef APG_SIM
 cudaError_t launch_sample_windows(const float* traj, int W, int L, int stride, int n, float* states, float* refs,
                                   cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
@@ -101,7 +94,6 @@ cudaError_t launch_sample_windows(const float* traj, int W, int L, int stride, i
                                                                         refs);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 __global__ void apg_ref_table_kernel(const float* __restrict__ traj, int W, int nth, float speed, float z_offset,
                                      size_t rows, float* __restrict__ out) {
@@ -109,7 +101,6 @@ __global__ void apg_ref_table_kernel(const float* __restrict__ traj, int W, int 
   if (k < rows) ref_table_body(k, traj, W, nth, speed, z_offset, out);
 }
 
-#ifndef APG_SIM
 cudaError_t launch_reference_table(const float* traj, int W, int nth, float speed, float z_offset, int rows,
                                    float* out, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
@@ -117,7 +108,6 @@ cudaError_t launch_reference_table(const float* traj, int W, int nth, float spee
                                                                          out);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 __global__ void apg_poly_march_kernel(const double* __restrict__ coef, int degree, const double* __restrict__ rot,
                                       const double* __restrict__ start, int n, double x_start, double x_range,
@@ -130,7 +120,6 @@ __global__ void apg_poly_march_kernel(const double* __restrict__ coef, int degre
   if (ref_len) ref_len[i] = len;
 }
 
-#ifndef APG_SIM
 cudaError_t launch_polynomial_points(const double* coef, int degree, const double* rot, const double* start, int n,
                                      double x_start, double x_range, double dist_points, int hover, int max_rows,
                                      float* out, int* ref_len, cudaStream_t st) {
@@ -140,6 +129,5 @@ cudaError_t launch_polynomial_points(const double* coef, int degree, const doubl
                                                       hover, max_rows, out, ref_len);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 }  // namespace apg

@@ -23,7 +23,7 @@ namespace apg {
 // autoregressive forward
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1) rec_fwd_kernel(const HutterLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Quad<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
   const int h = g.h;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NT, 1) rec_fwd_kernel(const HutterLayout y, co
 // autoregressive adjoint (back-propagation through time)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1) rec_adj_kernel(const HutterLayout y, const RolloutArgs g) {
-  extern __shared__ __align__(128) float smem[];
+  APG_DYNAMIC_SMEM_F32(smem);
   using Sys = Quad<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
   const int h = g.h;

@@ -154,7 +154,6 @@ size_t simple_adj_smem_bytes(const SimpleLayout& y) {
   return sizeof(float) * (size_t)(y.b_total + pad4(TM * y.F0) + (y.rows_total + y.Mo4) * TMP + 8) + 32;
 }
 
-#ifndef APG_SIM
 cudaError_t launch_simple_fwd(const SimpleLayout& y, const RolloutArgs& a, int grid, cudaStream_t st) {
   const size_t smem = simple_fwd_smem_bytes(y);
   cudaError_t e = cudaFuncSetAttribute(simple_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -162,9 +161,7 @@ cudaError_t launch_simple_fwd(const SimpleLayout& y, const RolloutArgs& a, int g
   APG_LAUNCH(grid, NT, smem, st, simple_fwd_kernel)(y, a);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
-#ifndef APG_SIM
 cudaError_t launch_simple_adj(const SimpleLayout& y, const RolloutArgs& a, int grid, cudaStream_t st) {
   const size_t smem = simple_adj_smem_bytes(y);
   cudaError_t e = cudaFuncSetAttribute(simple_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -172,6 +169,5 @@ cudaError_t launch_simple_adj(const SimpleLayout& y, const RolloutArgs& a, int g
   APG_LAUNCH(grid, NT, smem, st, simple_adj_kernel)(y, a);
   return cudaGetLastError();
 }
-#endif  // APG_SIM
 
 }  // namespace apg

@@ -11,6 +11,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: long CPU-model runs (whole kernels on the software models); skipped "
+                                       "unless APG_RUN_SLOW=1 so that the default CPU suite stays within minutes")
 
 
 # order of the tests of tests/test_zz_new_paths_gpu.py (everything written after the round-1 GPU budget was spent):
@@ -35,6 +37,11 @@ def pytest_collection_modifyitems(config, items):
         rest = [it for it in items if "test_zz_new_paths_gpu" not in it.nodeid]
         new.sort(key=_new_path_rank)                       # stable: keeps the file order inside a group
         items[:] = rest + new
+    if os.environ.get("APG_RUN_SLOW") != "1":
+        skip_slow = pytest.mark.skip(reason="slow CPU-model run: set APG_RUN_SLOW=1")
+        for item in items:
+            if "slow" in item.keywords:
+                item.add_marker(skip_slow)
     try:
         import torch
         has_gpu = torch.cuda.is_available()

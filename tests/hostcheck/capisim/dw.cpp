@@ -1,0 +1,6 @@
+// libapg_b200_sim.so, part 4: streaming tcgen05 dW GEMM (csrc/adj_dw_tc_kernels.cu) on the tcgen05 model.
+#define APG_TC_SIM 1
+#define APG_SIM 1
+#include "../tc_sim.h"
+
+#include "../../../apg_trajectory_tracking_b200/csrc/adj_dw_tc_kernels.cu"

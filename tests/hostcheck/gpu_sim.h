@@ -4,6 +4,7 @@
 // object with the dynamic shared memory, mbarrier table, warp scratch and the list of model violations.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -103,6 +104,79 @@ inline void launch(int grid, int block, const std::function<void()>& body) {
     if (st.tmem_allocated) fail("CTA " + std::to_string(b) + " exited without tcgen05.dealloc");
   }
 }
+}  // namespace sim
+
+// ---- the few CUDA runtime names the launchers and the C-ABI layer use -------------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+typedef void* cudaStream_t;
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+enum { cudaStreamNonBlocking = 1 };
+namespace sim {
+inline int& max_dynamic_smem_set() { static int v = 0; return v; }     // last cudaFuncSetAttribute value
+}
+template <class K>
+static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int bytes) {
+  if (bytes < 0 || (size_t)bytes > sim::DYN_SMEM) { sim::fail("dynamic shared memory request of " + std::to_string(bytes) + " B exceeds the 227 KB limit"); return cudaErrorInvalidValue; }
+  sim::max_dynamic_smem_set() = bytes;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "simulated CUDA error"; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = reinterpret_cast<void*>(1); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+// the "device" of the model: a handful of SMs (APG_SIM_SMS, default 3) keeps the grids small
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
+  const char* e = getenv("APG_SIM_SMS");
+  *v = e ? atoi(e) : 3;
+  return cudaSuccess;
+}
+
+namespace sim {
+// kernel<<<grid, block, smem>>>(args...) on the model.  Shared-memory guard: everything beyond the requested dynamic
+// shared memory is filled with a canary before every CTA and checked afterwards (a kernel that writes past the size
+// its launcher computed is caught here; on hardware it would fault or corrupt silently).
+struct LaunchCfg { dim3 grid; int block; size_t smem; };
+template <class F>
+struct BoundLaunch {
+  LaunchCfg l;
+  F f;
+  template <class... A>
+  void operator()(A&&... args) {
+    State& st = S();
+    if (l.smem > DYN_SMEM) { fail("launch with more dynamic shared memory than an SM has"); return; }
+    if ((int)l.smem > max_dynamic_smem_set() && l.smem > 48 * 1024)
+      fail("launch with " + std::to_string(l.smem) + " B of dynamic shared memory without cudaFuncSetAttribute");
+    const size_t guard = std::min<size_t>(DYN_SMEM - l.smem, 8192);
+    for (unsigned by = 0; by < l.grid.y; ++by) {
+      memset(st.smem + l.smem, 0xA5, guard);
+      launch((int)l.grid.x, l.block, [&]() { blockIdx.y = by; gridDim.y = l.grid.y; f(args...); });
+      for (size_t i = 0; i < guard; ++i)
+        if (st.smem[l.smem + i] != 0xA5) {
+          fail("a kernel wrote beyond its dynamic shared memory (" + std::to_string(l.smem) + " B requested, byte +" +
+               std::to_string(i) + ")");
+          break;
+        }
+    }
+  }
+};
+struct Launcher {
+  LaunchCfg cfg;
+  Launcher(dim3 g, int b, size_t s) : cfg{g, b, s} {}
+  Launcher(int g, int b, size_t s) : cfg{dim3((unsigned)g), b, s} {}
+  Launcher(unsigned g, int b, size_t s) : cfg{dim3(g), b, s} {}
+  template <class F>
+  BoundLaunch<F> bind(F f) { return BoundLaunch<F>{cfg, f}; }
+};
 }  // namespace sim
 
 static inline void __syncthreads() { sim::S().cta_barrier->arrive_and_wait(); }

@@ -5,6 +5,7 @@
 #include "te_sim.h"
 
 #include "../../apg_trajectory_tracking_b200/csrc/learnt_kernels.cu"
+#include "../../apg_trajectory_tracking_b200/csrc/misc_kernels.cu"      // launch_reduce_grad of the real launcher
 
 using namespace apg;
 

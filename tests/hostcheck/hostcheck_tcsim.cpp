@@ -3,6 +3,7 @@
 // running on the CPU on top of the software model of tc_sim.h - roles, mbarrier hand-off, TMEM operand placement,
 // issue order / accumulate flags, epilogues, stash addressing, gradient mapping, end to end.
 #define APG_TC_SIM 1
+#define APG_SIM 1
 #include "tc_sim.h"
 
 #include "../../apg_trajectory_tracking_b200/csrc/hutter_tc_kernels.cu"

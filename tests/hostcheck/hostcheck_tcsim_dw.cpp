@@ -1,6 +1,7 @@
 // Test-only: adj_dw_tc_kernel ITSELF (csrc/adj_dw_tc_kernels.cu, unchanged source) running on the CPU on top of the
 // software model of tc_sim.h (see hostcheck_tcsim.cpp).
 #define APG_TC_SIM 1
+#define APG_SIM 1
 #include "tc_sim.h"
 
 #include "../../apg_trajectory_tracking_b200/csrc/adj_dw_tc_kernels.cu"

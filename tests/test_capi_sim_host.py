@@ -1,0 +1,156 @@
+"""The WHOLE library on the CPU: tests/hostcheck/capisim builds libapg_b200_sim.so from the unchanged product sources
+(csrc/capi.cu, capi_prep.cu and every *_kernels.cu) with -DAPG_SIM: the C-ABI layer runs on a CUDA-runtime shim,
+every kernel launch (through the real launchers: grid / block / dynamic shared memory sizes) on the software models
+of tests/hostcheck (gpu_sim.h, te_sim.h, tc_sim.h); a canary behind the requested dynamic shared memory catches
+kernels that write past the size their launcher computed.  The product's own Python wrappers are pointed at that
+library ("device" pointers = host pointers), so the tests below are the GPU parity tests in miniature - what they
+add over the per-kernel model tests is the host side: argument checks, workspace plan offsets, weight packing by the
+real pack kernel, kernel selection by configuration and by the APG_TC_* / peer-exchange switches."""
+import contextlib
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import bench as B
+from apg_trajectory_tracking_b200 import _capi, evaluate as EV, ops, prepare as PR, rollout as R, synthetic as SY
+from oracle import apg_oracle as O
+from tests.helpers import golden_params, load_golden, rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def simlib_path(tmp_path_factory):
+    tmp = tmp_path_factory.mktemp("capisim")
+    objs = []
+    for name in ("host", "te", "tc", "dw"):
+        obj = tmp / f"{name}.o"
+        subprocess.check_call(["g++", "-O1", "-c", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
+                               "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
+                               os.path.join(ROOT, "tests", "hostcheck", "capisim", f"{name}.cpp"), "-o", str(obj)])
+        objs.append(str(obj))
+    out = tmp / "libapg_b200_sim.so"
+    subprocess.check_call(["g++", "-shared", "-pthread"] + objs + ["-o", str(out)])
+    return str(out)
+
+
+class _FakeStream:
+    cuda_stream = 0
+
+
+@pytest.fixture
+def simlib(simlib_path, monkeypatch):
+    lib = ctypes.CDLL(simlib_path)
+    for name, (res, args) in _capi.EXPORTS.items():
+        fn = getattr(lib, name)                       # every declared entry point exists in the model library too
+        fn.restype, fn.argtypes = res, args
+    lib.apg_sim_take_errors.restype = ctypes.c_int
+    monkeypatch.setattr(_capi, "lib", lambda: lib)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: _FakeStream())
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(R, "_dev_f32", lambda t, name: None if t is None else t.contiguous().float())
+    for mod in (ops, PR, EV):
+        monkeypatch.setattr(mod, "_require_cuda", lambda *a, **k: None, raising=False)
+        monkeypatch.setattr(mod, "_stream", lambda t: ctypes.c_void_p(0), raising=False)
+    for k in ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX"):
+        monkeypatch.delenv(k, raising=False)
+    yield lib
+    buf = ctypes.create_string_buffer(4096)
+    n = lib.apg_sim_take_errors(buf, 4096)
+    assert n == 0, buf.value.decode()
+
+
+def _quad_case(n, seed):
+    params = B.default_init("quad", 10, seed=seed)
+    case = SY.quad_case(n, 10, 0.1, seed=seed)
+    want = O.concurrent_value_and_grad("quad", params, case["in_state"], case["cur"], case["in_ref"], case["ref"], 10,
+                                       0.1)
+    return params, case, want
+
+
+def _check(loss, grad, params, want, tol=5e-5):
+    want_loss, want_grad = want[0], want[1]
+    assert abs(float(loss) - float(want_loss)) <= 2e-5 * abs(float(want_loss))
+    for got, g in zip(R.split_flat(grad, params), want_grad):
+        if g is None:
+            assert float(got.abs().max()) == 0
+        else:
+            assert float((got - g).abs().max()) <= tol * max(float(g.abs().max()), 1e-6)
+
+
+_SLOW = pytest.mark.slow
+@pytest.mark.parametrize("flags", [(), pytest.param(("APG_TC_FWD",), marks=_SLOW), pytest.param(("APG_TC_DW",), marks=_SLOW),
+                                   pytest.param(("APG_TC_DW", "APG_TC_DX"), marks=_SLOW),
+                                   ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX")])
+def test_rollout_forward_backward_through_the_c_abi_all_kernel_selections(simlib, monkeypatch, flags):
+    """apg_rollout_forward + apg_rollout_backward, quadrotor concurrent, 100 drones on a 3-SM model: the default
+    mma.sync kernels and every combination of the optional tcgen05 paths give the oracle's loss and gradient"""
+    for k in flags:
+        monkeypatch.setenv(k, "1")
+    n = 100                                            # two 64-drone stash tiles, one (partial) 128-drone tcgen05 tile
+    params, case, want = _quad_case(n, 21)
+    runner = R.Rollout(R.RolloutSpec.quad_concurrent(10, 0.1), n, "cpu")
+    flat = R.flatten_params(params)
+    loss, grad = runner.value_and_grad(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
+    _check(loss, grad, params, want)
+
+
+def test_peer_exchange_entry_points_single_rank(simlib):
+    """apg_rollout_backward_p2p + apg_grad_gather_sgd_p2p with world = 1 on a host buffer: the gradient that comes
+    out of the slot equals the plain backward's, and the fused SGD update equals the torch ops"""
+    n = 130
+    params, case, want = _quad_case(n, 5)
+    runner = R.Rollout(R.RolloutSpec.quad_concurrent(10, 0.1), n, "cpu")
+    flat = R.flatten_params(params).clone()
+    loss, grad = runner.value_and_grad(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
+    npar = flat.numel()
+    nbytes = simlib.apg_grad_comm_bytes(1, npar)
+    buf = torch.zeros(nbytes // 4)
+    so, fo = ctypes.c_size_t(), ctypes.c_size_t()
+    assert simlib.apg_grad_comm_offsets(1, npar, 1, ctypes.byref(so), ctypes.byref(fo)) == 0
+    slot_tab = torch.tensor([buf.data_ptr() + so.value], dtype=torch.int64)
+    flag_tab = torch.tensor([buf.data_ptr() + fo.value], dtype=torch.int64)
+    ticket = torch.zeros(1, dtype=torch.int32)
+    comm = _capi.ApgGradComm(0, 1, ctypes.c_void_p(slot_tab.data_ptr()), ctypes.c_void_p(flag_tab.data_ptr()), 1,
+                             ctypes.c_void_p(ticket.data_ptr()))
+    runner.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
+    runner.backward_p2p(comm)
+    g2, mom = torch.zeros(npar), torch.zeros(npar)
+    p2 = flat.clone()
+    _capi.check(simlib.apg_grad_gather_sgd_p2p(ctypes.byref(comm), ctypes.c_void_p(buf.data_ptr() + so.value), npar,
+                                               ctypes.c_void_p(g2.data_ptr()), ctypes.c_void_p(p2.data_ptr()),
+                                               ctypes.c_void_p(mom.data_ptr()), ctypes.c_float(1e-6),
+                                               ctypes.c_float(0.9), None))
+    assert torch.equal(g2, grad) and torch.equal(mom, grad)
+    assert torch.allclose(p2, flat - 1e-6 * grad, rtol=0, atol=1e-9) and int(ticket[0]) == 0
+
+
+@pytest.mark.slow
+def test_other_train_modes_through_the_c_abi(simlib):
+    """wing and cartpole concurrent, quadrotor autoregressive and LSTM (GPU-verified kernels: their agreement with the
+    oracle on the model also validates the model on four more kernel pairs)"""
+    for workload in ("wing_concurrent", "cartpole_concurrent", "quad_autoregressive", "quad_lstm"):
+        w = dict(B.WORKLOADS[workload])
+        n, h = 66, min(w["h"], 4)
+        w["h"] = h
+        case = B.make_case(w, n, 3, "cpu")
+        params = B.default_init(w["system"], h, mode=w.get("mode", "concurrent"))
+        spec = B.make_spec(w)
+        runner = R.Rollout(spec, n, "cpu")
+        flat = R.flatten_params(params)
+        loss, grad = runner.value_and_grad(flat, case.get("in_state"), case["cur"], case.get("in_ref"), case.get("ref"),
+                                           case.get("h0c0"))
+        if w.get("mode", "concurrent") == "concurrent":
+            want = O.concurrent_value_and_grad(w["system"], params, case["in_state"], case["cur"], case.get("in_ref"),
+                                               case.get("ref"), h, spec.dt)
+        else:
+            hc = (case["h0c0"][0], case["h0c0"][1]) if case.get("h0c0") is not None else None
+            want = O.recurrent_value_and_grad(w["mode"].lower(), params, case["cur"], case["in_ref"], case["ref"], h,
+                                              spec.dt, hc0=hc)
+        _check(loss, grad, params, want, tol=2e-4)

@@ -44,7 +44,8 @@ def _unstash(st, rows, n):
     return st.reshape(nt, rows, TMP)[:, :, :TM].transpose(0, 2, 1).reshape(nt * TM, rows)[:n]
 
 
-@pytest.mark.parametrize("n,grid", [(300, 2), (128, 1), (70, 3)])
+@pytest.mark.parametrize("n,grid", [(300, 2), pytest.param(128, 1, marks=pytest.mark.slow),
+                                    pytest.param(70, 3, marks=pytest.mark.slow)])
 def test_tcgen05_forward_and_split_adjoint_run_end_to_end_on_the_model(sim, n, grid):
     fw, dwl = sim
     params = B.default_init("quad", H, seed=n)

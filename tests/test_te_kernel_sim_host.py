@@ -203,6 +203,7 @@ def _check_grad(grad, params, want_grad, tol):
         assert np.abs(got - g.detach().double().numpy()).max() <= tol * scale, i
 
 
+@pytest.mark.slow
 def test_hutter_kernels_on_the_model_reproduce_oracle_loss_and_gradient(hk):
     """hutter_fwd_kernel / hutter_adj_kernel are GPU-verified: that their unchanged source ALSO reproduces the oracle
     on the software model validates the model itself (warp specialisation, named barriers, mbarrier hand-offs, TMA
