@@ -154,3 +154,64 @@ def test_other_train_modes_through_the_c_abi(simlib):
             want = O.recurrent_value_and_grad(w["mode"].lower(), params, case["cur"], case["in_ref"], case["ref"], h,
                                               spec.dt, hc0=hc)
         _check(loss, grad, params, want, tol=2e-4)
+
+
+def test_evaluation_entry_points_through_the_c_abi(simlib):
+    """apg_eval_rollout / apg_eval_fly_to_points / apg_eval_cartpole through the product's evaluator classes on the
+    model library: host-side argument checks, workspace plan, real pack kernel, real launchers"""
+    from tests.test_oracle_golden import wing_eval_case
+    g = load_golden("eval_rand.npz")
+    params = golden_params(load_golden("conc_quad_kat4.npz"))
+    steps = 12
+    ev = EV.TableEvaluator(R.RolloutSpec.quad_concurrent(10, 0.1), 2, "cpu")
+    tabs = torch.tensor(np.stack([g["gentle_table"], g["fast_reset_table"]]), dtype=torch.float32)
+    out = ev.follow(R.flatten_params(params), tabs, steps=steps, thresh_div=1.0, thresh_stable=1.0, test_time=0)
+    assert out["n_steps"].tolist() == [steps, steps]
+    for k, name in enumerate(("gentle", "fast_reset")):
+        assert np.abs(out["states"][k].numpy() - g[f"{name}_states"][:steps + 1]).max() <= 5e-5
+    gw = load_golden("eval_wing.npz")
+    wparams, targets, init, h, dt_data, dt_env, _, test_time, tdiv, tstab = wing_eval_case(gw, "one_target")
+    wev = EV.WingTargetEvaluator(R.RolloutSpec.wing_concurrent(h, dt_env), 1, gw["mean"], gw["std"], dt_data, "cpu")
+    wout = wev.fly(R.flatten_params(wparams), targets, steps=15, thresh_div=tdiv, thresh_stable=tstab)
+    traj = gw["one_target_traj"]
+    assert np.abs(wout["states"][0, 1:16].numpy() - traj[:15, :12]).max() <= 1e-4 * np.abs(traj[:, :12]).max()
+    gc = load_golden("eval_cartpole.npz")
+    cparams = [torch.tensor(gc[f"param_{i}"]) for i in range(10)]
+    cev = EV.CartpoleBalanceEvaluator(R.RolloutSpec.cartpole_concurrent(10, 0.05), 2, "cpu")
+    init = torch.tensor(np.stack([gc["falls_init"], gc["tilted_init"]]), dtype=torch.float32)
+    cout = cev.balance(R.flatten_params(cparams), init, steps=10, thresh_div=0.21, burn_in_steps=5)
+    assert cout["n_steps"].tolist() == [7, 10]
+    assert np.abs(cout["states"][0, :7].numpy() - gc["falls_states"]).max() <= 2e-5
+
+
+def test_input_side_and_learnt_entry_points_through_the_c_abi(simlib):
+    g = load_golden("prep_data.npz")
+    out = PR.prepare_quad(torch.tensor(g["quad_raw_states"]), torch.tensor(g["quad_raw_refs"]))
+    assert np.abs(out["in_state"].numpy() - g["quad_in_state"]).max() <= 2e-6
+    assert np.abs(out["in_ref"].numpy() - g["quad_in_ref"]).max() <= 2e-6
+    wo = PR.prepare_wing(torch.tensor(g["wing_raw_states"]), torch.tensor(g["wing_targets"]), g["wing_mean"],
+                         g["wing_std"], float(g["wing_dt"]), int(g["wing_h"]))
+    assert np.abs(wo["ref"].numpy() - g["wing_ref"]).max() <= 1e-5 * np.abs(g["wing_ref"]).max()
+    gp = load_golden("poly_traj.npz")
+    pts, ref_len = PR.polynomial_points(torch.tensor(gp["b_coef"])[None], torch.tensor(gp["b_rot"])[None],
+                                        torch.tensor(gp["b_start"])[None], x_range=6, max_drone_dist=0.5, horizon=10,
+                                        hover_steps=5)
+    assert int(ref_len[0]) == len(gp["b_points"])
+    assert np.array_equal(pts[0, :len(gp["b_points"])].numpy(), gp["b_points"].astype(np.float32))
+    gt = load_golden("ref_table.npz")
+    tab = PR.reference_table(torch.tensor(gt["c_raw"]), float(gt["c_cfg"][0]), float(gt["c_cfg"][1]), z_offset=0.0)
+    assert np.abs(tab.numpy() - gt["c_table"]).max() <= 3e-6
+    # learnt residual dynamics: forward + adjoint (wing: all 46 physical parameters live)
+    from apg_trajectory_tracking_b200.neural_control.dynamics import quad_dynamics_trained as QT
+    gl = load_golden("learnt_dyn.npz")
+    flat = torch.tensor(np.concatenate([np.asarray(gl[f"wb_param_{i}"]).reshape(-1) for i in range(42)]),
+                        dtype=torch.float32, requires_grad=True)
+    s = torch.tensor(gl["wb_state"], dtype=torch.float32, requires_grad=True)
+    a = torch.tensor(gl["wb_action"], dtype=torch.float32, requires_grad=True)
+    phys = np.zeros(48, np.float32)
+    o = QT._LearntStep.apply(flat, s, a, float(gl["wb_dt"]), phys, 1)
+    assert rel_err(o.detach(), torch.tensor(gl["wb_out"])) <= 5e-6
+    (o * torch.tensor(gl["wb_cot"])).sum().backward()
+    want = np.concatenate([np.asarray(gl[f"wb_gparam_{i}"]).reshape(-1) for i in range(42)])
+    assert np.abs(flat.grad.numpy() - want).max() <= 1e-4 * np.abs(want).max()
+    assert rel_err(s.grad, torch.tensor(gl["wb_gstate"])) <= 5e-5
