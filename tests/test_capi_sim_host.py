@@ -17,6 +17,7 @@ import torch
 
 import bench as B
 from apg_trajectory_tracking_b200 import _capi, evaluate as EV, ops, prepare as PR, rollout as R, synthetic as SY
+from apg_trajectory_tracking_b200.neural_control.dynamics import quad_dynamics_trained as QT
 from oracle import apg_oracle as O
 from tests.helpers import golden_params, load_golden, rel_err
 
@@ -55,7 +56,7 @@ def simlib(simlib_path, monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: _FakeStream())
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(R, "_dev_f32", lambda t, name: None if t is None else t.contiguous().float())
-    for mod in (ops, PR, EV):
+    for mod in (ops, PR, EV, QT):
         monkeypatch.setattr(mod, "_require_cuda", lambda *a, **k: None, raising=False)
         monkeypatch.setattr(mod, "_stream", lambda t: ctypes.c_void_p(0), raising=False)
     for k in ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX"):
@@ -202,7 +203,6 @@ def test_input_side_and_learnt_entry_points_through_the_c_abi(simlib):
     tab = PR.reference_table(torch.tensor(gt["c_raw"]), float(gt["c_cfg"][0]), float(gt["c_cfg"][1]), z_offset=0.0)
     assert np.abs(tab.numpy() - gt["c_table"]).max() <= 3e-6
     # learnt residual dynamics: forward + adjoint (wing: all 46 physical parameters live)
-    from apg_trajectory_tracking_b200.neural_control.dynamics import quad_dynamics_trained as QT
     gl = load_golden("learnt_dyn.npz")
     flat = torch.tensor(np.concatenate([np.asarray(gl[f"wb_param_{i}"]).reshape(-1) for i in range(42)]),
                         dtype=torch.float32, requires_grad=True)
