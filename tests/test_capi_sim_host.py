@@ -249,3 +249,59 @@ def test_raw_sample_train_step_on_the_model_library(simlib, monkeypatch):
     assert abs(float(la) - float(lb)) <= 2e-5 * abs(float(la))
     assert rel_err(b.grad, a.grad) <= 2e-4 and rel_err(b.flat, a.flat) <= 1e-6
     assert b.host_launches_per_step == 3 * 7
+
+
+def test_plain_c_demo_against_the_model_library(simlib_path, tmp_path):
+    """examples/c_abi_demo.c linked against libapg_b200_sim.so: apg_rollout_value_and_grad_host (device buffer cache,
+    H2D / D2H copies, forward, backward) from plain C; its loss against the oracle, its own finite-difference check"""
+    import re
+    from tests.test_zy_c_abi_example import _lcg_inputs
+    exe = str(tmp_path / "c_abi_demo_sim")
+    libdir = os.path.dirname(simlib_path)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, "-L", libdir, "-lapg_b200_sim",
+                           "-lm", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    loss = float(re.search(r"^loss (\S+)", r.stdout, re.M).group(1))
+    params, st = _lcg_inputs(256, 5)
+    want, _, _, _ = O.concurrent_value_and_grad("cartpole", params, st, st, None, None, 5, 0.05)
+    assert abs(loss - float(want)) <= 2e-5 * abs(float(want))
+
+
+@pytest.mark.slow
+def test_two_ranks_exchange_gradients_through_peer_slots(simlib):
+    """data-parallel step of two "ranks" (two runners, two symmetric buffers in this process): each rank's
+    apg_rollout_backward_p2p scatters into both buffers, each rank's gather sums the slots in rank order - the result
+    equals the gradient of the concatenated batch and is bitwise identical on both ranks"""
+    world, n_each = 2, 70
+    params, case, want = _quad_case(world * n_each, 8)
+    flat = R.flatten_params(params)
+    npar = flat.numel()
+    nbytes = simlib.apg_grad_comm_bytes(world, npar)
+    bufs = [torch.zeros(nbytes // 4) for _ in range(world)]
+    so, fo = ctypes.c_size_t(), ctypes.c_size_t()
+    assert simlib.apg_grad_comm_offsets(world, npar, 1, ctypes.byref(so), ctypes.byref(fo)) == 0
+    slot_tab = torch.tensor([b.data_ptr() + so.value for b in bufs], dtype=torch.int64)
+    flag_tab = torch.tensor([b.data_ptr() + fo.value for b in bufs], dtype=torch.int64)
+    tickets = [torch.zeros(1, dtype=torch.int32) for _ in range(world)]
+    comms, losses = [], []
+    for r in (1, 0):                                                        # arrival order must not matter
+        sl = slice(r * n_each, (r + 1) * n_each)
+        runner = R.Rollout(R.RolloutSpec.quad_concurrent(10, 0.1), n_each, "cpu")
+        shard = [case[k][sl].clone() for k in ("in_state", "cur", "in_ref", "ref")]    # own (aligned) allocations
+        loss, _, _ = runner.forward(flat, *shard)
+        losses.append(float(loss))
+        comm = _capi.ApgGradComm(r, world, ctypes.c_void_p(slot_tab.data_ptr()), ctypes.c_void_p(flag_tab.data_ptr()),
+                                 1, ctypes.c_void_p(tickets[r].data_ptr()))
+        runner.backward_p2p(comm)
+        comms.append((r, comm))
+    grads = {}
+    for r, comm in comms:
+        g = torch.zeros(npar)
+        _capi.check(simlib.apg_grad_gather_sgd_p2p(ctypes.byref(comm), ctypes.c_void_p(bufs[r].data_ptr() + so.value),
+                                                   npar, ctypes.c_void_p(g.data_ptr()), None, None,
+                                                   ctypes.c_float(0), ctypes.c_float(0), None))
+        grads[r] = g
+    assert torch.equal(grads[0], grads[1])
+    _check(sum(losses), grads[0], params, want)
