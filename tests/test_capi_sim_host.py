@@ -305,3 +305,41 @@ def test_two_ranks_exchange_gradients_through_peer_slots(simlib):
         grads[r] = g
     assert torch.equal(grads[0], grads[1])
     _check(sum(losses), grads[0], params, want)
+
+
+@pytest.mark.slow
+def test_device_dataset_epoch_on_the_model_library(simlib):
+    """DeviceQuadDataset + run_epoch_device (raw samples -> prepare kernels -> fused rollout -> torch SGD on the module's
+    flat views) against the same epoch through the host QuadDataset batches: tests/test_zz_new_paths_gpu.py::
+    test_device_dataset_epoch_equals_host_dataset_epoch in miniature on the model library"""
+    from apg_trajectory_tracking_b200 import device_data as DD, train as T
+    from apg_trajectory_tracking_b200.neural_control import dataset as DS
+    from apg_trajectory_tracking_b200.neural_control.models.hutter_model import Net
+    n, h, dt, bs = 150, 10, 0.1, 64
+    raw = SY.quad_case(n, h, dt, seed=2)
+    off = torch.randn(n, 3, generator=torch.Generator().manual_seed(0))
+    states, refs = raw["cur"].clone(), raw["ref"].clone()
+    states[:, :3] += off
+    refs[:, :, :3] += off[:, None]
+    nets = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        nets.append(Net(15, h, 9, 4 * h, conv=1))
+    spec = R.RolloutSpec.quad_concurrent(h, dt)
+    ma, mb = T.ModuleRollout(nets[0], spec, "cpu"), T.ModuleRollout(nets[1], spec, "cpu")
+    oa = torch.optim.SGD(nets[0].parameters(), lr=1e-5, momentum=0.9)
+    ob = torch.optim.SGD(nets[1].parameters(), lr=1e-5, momentum=0.9)
+    host = DS.QuadDataset(states.numpy(), refs.numpy())
+    dev = DD.DeviceQuadDataset(states, refs, "cpu")
+    tot, i = 0.0, 0
+    for i, lo in enumerate(range(0, n, bs)):
+        b = [t[lo:lo + bs].clone() for t in (host.normed_states, host.states, host.in_ref_states, host.ref_states)]
+        oa.zero_grad()
+        tot += float(ma.loss_and_grad(*b))
+        oa.step()
+    la = tot / max(i, 1)
+    lb = DD.run_epoch_device(mb, ob, dev, bs, shuffle=False)
+    assert abs(la - lb) <= 2e-5 * abs(la), (la, lb)
+    assert rel_err(mb.flat, ma.flat) <= 1e-6
+    d3 = DD.DeviceQuadDataset.from_trajectory(torch.randn(301, 9), h, device="cpu")
+    assert len(d3) == len(range(0, 301 - (h + 1), 2 * h))
