@@ -80,6 +80,10 @@ inline void launch(int grid, int block, const std::function<void()>& body) {
   State& st = S();
   for (int b = 0; b < grid; ++b) {
     memset(st.tmem, 0xff, sizeof st.tmem);              // NaN pattern: reading an unwritten accumulator shows
+    if (getenv("APG_SIM_POISON_SMEM")) {                  // stress: shared memory starts as NaNs, not as zeros
+      const uint32_t nan_bits = 0x7fc00000u;
+      for (size_t i = 0; i + 4 <= DYN_SMEM; i += 4) memcpy(st.smem + i, &nan_bits, 4);
+    }
     st.tmem_allocated = false;
     st.bars.clear();
     st.pbars.clear();
@@ -156,16 +160,21 @@ struct BoundLaunch {
     if (l.smem > DYN_SMEM) { fail("launch with more dynamic shared memory than an SM has"); return; }
     if ((int)l.smem > max_dynamic_smem_set() && l.smem > 48 * 1024)
       fail("launch with " + std::to_string(l.smem) + " B of dynamic shared memory without cudaFuncSetAttribute");
-    const size_t guard = std::min<size_t>(DYN_SMEM - l.smem, 8192);
+    // canary = quiet NaNs: a READ past the requested size poisons the result, a WRITE is found afterwards
+    const size_t first = (l.smem + 3) / 4 * 4, words = std::min<size_t>((DYN_SMEM - first) / 4, 4096);
+    const uint32_t nan_bits = 0x7fc00000u;
     for (unsigned by = 0; by < l.grid.y; ++by) {
-      memset(st.smem + l.smem, 0xA5, guard);
+      for (size_t i = 0; i < words; ++i) memcpy(st.smem + first + 4 * i, &nan_bits, 4);
       launch((int)l.grid.x, l.block, [&]() { blockIdx.y = by; gridDim.y = l.grid.y; f(args...); });
-      for (size_t i = 0; i < guard; ++i)
-        if (st.smem[l.smem + i] != 0xA5) {
-          fail("a kernel wrote beyond its dynamic shared memory (" + std::to_string(l.smem) + " B requested, byte +" +
+      for (size_t i = 0; i < words; ++i) {
+        uint32_t v;
+        memcpy(&v, st.smem + first + 4 * i, 4);
+        if (v != nan_bits) {
+          fail("a kernel wrote beyond its dynamic shared memory (" + std::to_string(l.smem) + " B requested, word +" +
                std::to_string(i) + ")");
           break;
         }
+      }
     }
   }
 };
