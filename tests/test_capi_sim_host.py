@@ -61,6 +61,14 @@ def simlib(simlib_path, monkeypatch):
         monkeypatch.setattr(mod, "_stream", lambda t: ctypes.c_void_p(0), raising=False)
     for k in ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX"):
         monkeypatch.delenv(k, raising=False)
+    if os.environ.get("APG_SIM_POISON_SMEM"):
+        # stress run: the workspace (stashes, partials, packed weights) starts as NaN patterns, like recycled HBM may
+        real_init = R.Rollout.__init__
+
+        def poisoned_init(self, *a, **k):
+            real_init(self, *a, **k)
+            self.workspace.fill_(0xFF)
+        monkeypatch.setattr(R.Rollout, "__init__", poisoned_init)
     yield lib
     buf = ctypes.create_string_buffer(4096)
     n = lib.apg_sim_take_errors(buf, 4096)
