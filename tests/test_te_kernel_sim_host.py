@@ -62,6 +62,7 @@ def test_cartpole_kernel_on_the_model_matches_reference_runs(te):
     assert np.abs(vsum - out["vel_sum"].numpy()).max() <= 1e-3
 
 
+@pytest.mark.slow
 def test_quad_eval_kernel_on_the_model_matches_reference_run_with_reset(te):
     g = load_golden("eval_rand.npz")
     params = golden_params(load_golden("conc_quad_kat4.npz"))
@@ -95,6 +96,7 @@ def test_quad_eval_kernel_on_the_model_matches_reference_run_with_reset(te):
     assert np.abs(states - want["states"].numpy()).max() <= 2e-4
 
 
+@pytest.mark.slow
 def test_wing_eval_kernel_on_the_model_matches_reference_flight(te):
     from tests.test_oracle_golden import wing_eval_case
     g = load_golden("eval_wing.npz")
