@@ -18,6 +18,13 @@ import torch
 import bench as B
 from apg_trajectory_tracking_b200 import _capi, evaluate as EV, ops, prepare as PR, rollout as R, synthetic as SY
 from apg_trajectory_tracking_b200.neural_control.dynamics import quad_dynamics_trained as QT
+# imported HERE, before any fixture patches ops._require_cuda: these modules bind that name at import time, and a first
+# import under the patch would leave them without their CUDA-only guard for the rest of the session
+from apg_trajectory_tracking_b200 import device_data, train  # noqa: F401
+from apg_trajectory_tracking_b200.neural_control import dataset as _ds, drone_loss as _dl  # noqa: F401
+from apg_trajectory_tracking_b200.neural_control.dynamics import (cartpole_dynamics, fixed_wing_dynamics,  # noqa: F401
+                                                                   quad_dynamics_flightmare)
+from apg_trajectory_tracking_b200.neural_control.models import hutter_model, rnn, simple_model  # noqa: F401
 from oracle import apg_oracle as O
 from tests.helpers import golden_params, load_golden, rel_err
 
