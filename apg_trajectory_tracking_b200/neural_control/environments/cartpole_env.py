@@ -64,3 +64,25 @@ class CartPoleEnv:
         s[2] = 0.1 * (np.random.rand() - 0.5)
         self.state = s
         return self.state
+
+
+def construct_states(num_data, dt, save_path=None, thresh_div=.21, **kwargs):
+    """Training states of the cartpole trainer (reference: ``construct_states``, environments/cartpole_env.py:178-236):
+    80 % from runs of 20 small random pushes out of slowed-down random states, the rest from random pushes near the
+    upright position until the pole leaves the threshold.  Every push is one launch of the CUDA dynamics op."""
+    from ..dynamics.cartpole_dynamics import CartpoleDynamics
+    env = CartPoleEnv(CartpoleDynamics(), dt, thresh_div=thresh_div)
+    data = []
+    while len(data) < num_data * .8:
+        env._reset()
+        env.state[1] *= .2
+        env.state[3] *= .2
+        for _ in range(20):
+            data.append(env._step((np.random.rand() - 0.5) * .2, is_torch=False))
+        env._reset()
+    while len(data) < num_data:
+        env.state = (np.random.rand(4) - .5) * .1
+        while env.is_upright():
+            data.append(env._step(np.random.rand() - 0.5, is_torch=False))
+        env._reset()
+    return np.array(data)[:num_data]

@@ -94,3 +94,31 @@ class QuadRotorEnvBase:
 
     def close(self):
         pass
+
+
+def full_state_training_data(len_data, ref_length=5, dt=0.02, speed_factor=.6, data_dir="data/traj_data_1", device=None,
+                             **kwargs):
+    """Training samples cut from random trajectory files (reference: ``full_state_training_data``,
+    environments/drone_env.py:232-269): every ``2 * ref_length``-th row of a table is a drone state (body rates 0),
+    the following ``ref_length`` rows its reference.  The table layout (``load_prepare_trajectory``) and the window
+    cutting run on the device (``prepare.reference_table`` / ``prepare.sample_windows``); file choice by
+    ``np.random.choice`` like the reference.  Returns numpy (states (len_data,12), ref_states (len_data,ref_length,9))."""
+    import os
+    from ... import prepare as PR
+    from .. import environments as _e
+    dev = torch.device(device) if device is not None else _e.compute_device()
+    folder = os.path.join(data_dir, "train")
+    names = sorted(os.listdir(folder))
+    states, refs, have = [], [], 0
+    sample_freq = 2 * ref_length
+    while have < len_data:
+        raw = np.load(os.path.join(folder, np.random.choice(names)))
+        table = PR.reference_table(torch.as_tensor(raw, dtype=torch.float32).to(dev), dt, speed_factor, z_offset=0.0)
+        n = len(range(0, table.shape[0] - (ref_length + 1), sample_freq))
+        if n <= 0:
+            raise ValueError("trajectory file too short for the requested reference length")
+        s, r = PR.sample_windows(table, n, ref_length, sample_freq)
+        states.append(s.cpu().numpy().astype(np.float64))
+        refs.append(r.cpu().numpy().astype(np.float64))
+        have += n
+    return np.concatenate(states)[:len_data], np.concatenate(refs)[:len_data]

@@ -725,3 +725,35 @@ def test_datasets_with_device_prepare_match_host_containers(hostlib):
         assert torch.allclose(a, b, atol=5e-6)
     loader = torch.utils.data.DataLoader(dev, batch_size=4, shuffle=False)
     assert next(iter(loader))[0].shape == (4, 15)
+
+
+def test_environment_data_sampling_mirrors(hostlib, monkeypatch, tmp_path):
+    """full_state_training_data (drone_env.py:232-269) over trajectory files and construct_states
+    (cartpole_env.py:178-236) on the mirrors"""
+    from apg_trajectory_tracking_b200.neural_control.environments import cartpole_env as CE, drone_env as DE
+    _single_drone_mirrors_on_cpu(monkeypatch)
+    g = load_golden("ref_table.npz")
+    (tmp_path / "train").mkdir()
+    np.save(tmp_path / "train" / "traj_0.npy", g["a_raw"].astype(np.float64))
+    dt, speed = [float(v) for v in g["a_cfg"]]
+    L = 5
+    np.random.seed(0)
+    states, refs = DE.full_state_training_data(25, ref_length=L, dt=dt, speed_factor=speed, data_dir=str(tmp_path))
+    assert states.shape == (25, 12) and refs.shape == (25, L, 9)
+    traj = g["a_table"]                                   # what the reference's load_prepare_trajectory returns
+    cut = traj[:-(L + 1)]
+    starts = cut[::2 * L]
+    n = len(starts)
+    want_states = np.hstack((starts, np.zeros((n, 3))))
+    want_refs = np.zeros((n, L, 9))
+    for i in range(1, L + 1):
+        want_refs[:, i - 1] = traj[i::2 * L][:n]
+    reps = 25 // n + 1
+    assert np.abs(states - np.tile(want_states, (reps, 1))[:25]).max() <= 3e-6
+    assert np.abs(refs - np.tile(want_refs, (reps, 1, 1))[:25]).max() <= 3e-6
+    np.random.seed(1)
+    data = CE.construct_states(60, 0.05)
+    assert data.shape == (60, 4) and np.isfinite(data).all() and np.abs(data[:, 2]).max() <= np.pi
+    # the first run: 20 pushes from one slowed-down random state, each state the dynamics step of the previous one
+    nxt = O.cartpole_step(torch.tensor(data[:19], dtype=torch.float32), torch.zeros(19, 1), 0.05).numpy()
+    assert np.abs(nxt[:, 0] - data[1:20, 0]).max() <= 1e-5           # x' = x + x_dot * dt does not depend on the push
