@@ -15,6 +15,13 @@ class SimpleWingEnv:
         self._state = np.zeros(12)
         self._state[3] = 11.5
 
+    def reset(self):
+        """the reference's randomised start (:30-42): a 6-entry longitudinal state [x, z, u ~ 10 +- .5, w +- .5,
+        pitch +- 2 deg, pitch rate +- .005] - kept as it is there (``zero_reset`` is what the evaluators use)"""
+        u, w = np.random.rand(1) - .5 + 10, np.random.rand(1) - .5
+        pitch, rate = np.deg2rad(np.random.rand(1) * 4 - 2), np.random.rand(1) * 0.01 - 0.005
+        self._state = np.array([0, 0, u[0], w[0], pitch[0], rate[0]])
+
     def step(self, action, thresh_stable=.7):
         """-> (new state (12,) float32, |roll| and |pitch| below thresh_stable)   (:44-58)"""
         dev = _env.compute_device()
@@ -25,3 +32,27 @@ class SimpleWingEnv:
 
     def close(self):
         pass
+
+
+def run_wing_flight(env, traj_len=1000, render=0, **kwargs):
+    """one open-loop flight from ``zero_reset`` with actions around the prior [.25, .5, .5, .5], redrawn every 10
+    steps (N(0, .15), clipped to [0, 1]); stops at the first unstable state; returns the visited states (:72-95)"""
+    prior = np.array([.25, .5, .5, .5])
+    env.zero_reset()
+    visited, action = [], prior
+    for j in range(traj_len):
+        if j % 10 == 0:
+            action = np.clip(np.random.normal(scale=.15, size=4) + prior, 0, 1)
+        state, stable = env.step(action)
+        if not stable:
+            break
+        visited.append(state)
+    return np.array(visited)
+
+
+def generate_unit_vecs(num_vecs, mean_vec=[1, 0, 0], std=.15):
+    """direction vectors normally distributed around ``mean_vec`` (covariance std * I); x components below 0.01 are
+    set to 1 (:98-109; not normalised there either)"""
+    vecs = np.random.multivariate_normal(mean_vec, np.eye(3) * std, size=num_vecs)
+    vecs[vecs[:, 0] < 0.01, 0] = 1
+    return vecs

@@ -757,3 +757,22 @@ def test_environment_data_sampling_mirrors(hostlib, monkeypatch, tmp_path):
     # the first run: 20 pushes from one slowed-down random state, each state the dynamics step of the previous one
     nxt = O.cartpole_step(torch.tensor(data[:19], dtype=torch.float32), torch.zeros(19, 1), 0.05).numpy()
     assert np.abs(nxt[:, 0] - data[1:20, 0]).max() <= 1e-5           # x' = x + x_dot * dt does not depend on the push
+
+
+def test_wing_flight_sampler_mirror(hostlib, monkeypatch):
+    from apg_trajectory_tracking_b200.neural_control.dynamics.fixed_wing_dynamics import FixedWingDynamics
+    from apg_trajectory_tracking_b200.neural_control.environments import wing_env as WE
+    _single_drone_mirrors_on_cpu(monkeypatch)
+    np.random.seed(0)
+    env = WE.SimpleWingEnv(FixedWingDynamics(), 0.05)
+    traj = WE.run_wing_flight(env, traj_len=25)
+    assert traj.ndim == 2 and traj.shape[1] == 12 and 1 <= len(traj) <= 25 and np.isfinite(traj).all()
+    # first state = one step of the oracle dynamics from zero_reset with the first drawn action
+    np.random.seed(0)
+    a0 = np.clip(np.random.normal(scale=.15, size=4) + np.array([.25, .5, .5, .5]), 0, 1)
+    s0 = torch.zeros(1, 12)
+    s0[0, 3] = 11.5
+    want = O.wing_step(s0, torch.tensor(a0, dtype=torch.float32)[None], 0.05)[0].numpy()
+    assert np.abs(traj[0] - want).max() <= 1e-5 * np.abs(want).max()
+    v = WE.generate_unit_vecs(50)
+    assert v.shape == (50, 3) and (v[:, 0] >= 0.01).all()
