@@ -230,6 +230,21 @@ def test_input_side_and_learnt_entry_points_through_the_c_abi(simlib):
     want = np.concatenate([np.asarray(gl[f"wb_gparam_{i}"]).reshape(-1) for i in range(42)])
     assert np.abs(flat.grad.numpy() - want).max() <= 1e-4 * np.abs(want).max()
     assert rel_err(s.grad, torch.tensor(gl["wb_gstate"])) <= 5e-5
+    # quadrotor: the construction-time simulator constants travel as `phys`
+    from apg_trajectory_tracking_b200 import params as P
+    qflat = torch.tensor(np.concatenate([np.asarray(gl[f"b_param_{i}"]).reshape(-1) for i in range(8)]),
+                         dtype=torch.float32, requires_grad=True)
+    qs = torch.tensor(gl["b_state"], dtype=torch.float32, requires_grad=True)
+    qa = torch.tensor(gl["b_action"], dtype=torch.float32, requires_grad=True)
+    qphys = P.PHYS["quad"]({"rotational_drag": [float(x) for x in gl["b_rot_drag"]]})
+    qo = QT._LearntStep.apply(qflat, qs, qa, float(gl["b_dt"]), qphys, 0)
+    assert rel_err(qo.detach(), torch.tensor(gl["b_out"])) <= 5e-6
+    (qo * torch.tensor(gl["b_cot"])).sum().backward()
+    qwant = np.concatenate([np.asarray(gl[f"b_gparam_{i}"]).reshape(-1) for i in range(8)])
+    keep = np.ones(qwant.size, bool)
+    keep[16] = False                                   # mass: cancels analytically, autograd leaves rounding noise
+    assert np.abs(qflat.grad.numpy() - qwant)[keep].max() <= 1e-4 * np.abs(qwant).max()
+    assert rel_err(qa.grad, torch.tensor(gl["b_gaction"])) <= 5e-5
 
 
 @pytest.mark.slow
