@@ -248,10 +248,11 @@ def test_input_side_and_learnt_entry_points_through_the_c_abi(simlib):
 
 
 @pytest.mark.slow
-def test_raw_sample_train_step_on_the_model_library(simlib, monkeypatch):
+@pytest.mark.parametrize("system", ["quad", "wing", "cartpole"])
+def test_raw_sample_train_step_on_the_model_library(simlib, monkeypatch, system):
     """FusedTrainStep.step_host (raw samples -> chunked staging -> prepare kernels -> forward -> adjoint per chunk)
     with the REAL prepare / rollout kernels of the model library behind it (CUDA streams / events stubbed), against
-    the whole-batch step from prepared inputs: quadrotor, 130 drones in chunks of 64"""
+    the whole-batch step from prepared inputs: 130 drones in chunks of 64"""
     from apg_trajectory_tracking_b200 import train as T
     from tests.test_step_host_logic_cpu import _Event, _Stream as _BaseStream
 
@@ -261,24 +262,24 @@ def test_raw_sample_train_step_on_the_model_library(simlib, monkeypatch):
     monkeypatch.setattr(torch.cuda, "Event", _Event)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     real_empty = torch.empty
     monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items()
                                                                         if kk != "pin_memory"}))
-    n, h, dt = 130, 10, 0.1
-    w = dict(system="quad", mode="concurrent", h=h, dt=dt)
-    params = B.default_init("quad", h, seed=4)
+    n = 130
+    h, dt = {"quad": (10, 0.1), "wing": (6, 0.05), "cartpole": (5, 0.05)}[system]
+    w = dict(system=system, mode="concurrent", h=h, dt=dt)
+    params = B.default_init(system, h, seed=4)
     spec = B.make_spec(w)
     case = B.make_case(w, n, 21, "cpu")
     a = T.FusedTrainStep(params, spec, n, lr=1e-4, device="cpu", distributed=False)
     b = T.FusedTrainStep(params, spec, n, lr=1e-4, device="cpu", distributed=False)
     a._dev = lambda x: x
-    la = a.step(case["in_state"], case["cur"], case["in_ref"], case["ref"])
-    raw = B.raw_host_inputs(dict(B.WORKLOADS["quad_concurrent"], n=n), {k: v for k, v in case.items()})
+    la = a.step(case.get("in_state"), case["cur"], case.get("in_ref"), case.get("ref"))
+    raw = B.raw_host_inputs(w, case)
     lb = b.step_host(chunk=64, **raw)
     assert abs(float(la) - float(lb)) <= 2e-5 * abs(float(la))
     assert rel_err(b.grad, a.grad) <= 2e-4 and rel_err(b.flat, a.flat) <= 1e-6
-    assert b.host_launches_per_step == 3 * 7
+    assert b.host_launches_per_step == 3 * (5 if system == "cartpole" else 7)
 
 
 def test_plain_c_demo_against_the_model_library(simlib_path, tmp_path):
