@@ -248,7 +248,7 @@ def test_input_side_and_learnt_entry_points_through_the_c_abi(simlib):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("system", ["quad", "wing", "cartpole"])
+@pytest.mark.parametrize("system", ["quad", "wing", "cartpole", "autoregressive", "lstm"])
 def test_raw_sample_train_step_on_the_model_library(simlib, monkeypatch, system):
     """FusedTrainStep.step_host (raw samples -> chunked staging -> prepare kernels -> forward -> adjoint per chunk)
     with the REAL prepare / rollout kernels of the model library behind it (CUDA streams / events stubbed), against
@@ -266,15 +266,18 @@ def test_raw_sample_train_step_on_the_model_library(simlib, monkeypatch, system)
     monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items()
                                                                         if kk != "pin_memory"}))
     n = 130
-    h, dt = {"quad": (10, 0.1), "wing": (6, 0.05), "cartpole": (5, 0.05)}[system]
-    w = dict(system=system, mode="concurrent", h=h, dt=dt)
-    params = B.default_init(system, h, seed=4)
+    h, dt = {"quad": (10, 0.1), "wing": (6, 0.05), "cartpole": (5, 0.05), "autoregressive": (4, 0.1),
+             "lstm": (4, 0.1)}[system]
+    mode = system if system in ("autoregressive", "lstm") else "concurrent"
+    system = "quad" if mode != "concurrent" else system
+    w = dict(system=system, mode=mode, h=h, dt=dt)
+    params = B.default_init(system, h, seed=4, mode=mode)
     spec = B.make_spec(w)
     case = B.make_case(w, n, 21, "cpu")
     a = T.FusedTrainStep(params, spec, n, lr=1e-4, device="cpu", distributed=False)
     b = T.FusedTrainStep(params, spec, n, lr=1e-4, device="cpu", distributed=False)
     a._dev = lambda x: x
-    la = a.step(case.get("in_state"), case["cur"], case.get("in_ref"), case.get("ref"))
+    la = a.step(case.get("in_state"), case["cur"], case.get("in_ref"), case.get("ref"), case.get("h0c0"))
     raw = B.raw_host_inputs(w, case)
     lb = b.step_host(chunk=64, **raw)
     assert abs(float(la) - float(lb)) <= 2e-5 * abs(float(la))
