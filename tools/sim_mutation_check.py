@@ -1,6 +1,7 @@
 """How sharp are the CPU models?  Applies known-bad one-line mutations to a scratch copy of the kernel sources, rebuilds
 the model harness and reports whether the model run notices (wrong numbers, a recorded violation, or a timeout of the
-kernels' own bounded waits).  Usage: python tools/sim_mutation_check.py  (a few minutes; prints one line per mutant)."""
+kernels' own bounded waits).  Usage: python tools/sim_mutation_check.py  (a few minutes; prints one line per mutant);
+python tools/sim_mutation_check.py --smem  (a launcher requesting too little shared memory, on the model library)."""
 import ctypes
 import os
 import shutil
@@ -84,5 +85,48 @@ def main():
         shutil.rmtree(scratch, ignore_errors=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--smem" not in sys.argv:
     main()
+
+
+# ---- a launcher that requests too little dynamic shared memory: caught by the canary of the model library ------------
+def smem_mutant():
+    from apg_trajectory_tracking_b200 import _capi, rollout as R
+    scratch = tempfile.mkdtemp()
+    for d in ("apg_trajectory_tracking_b200/csrc", "tests/hostcheck", "include"):
+        shutil.copytree(os.path.join(ROOT, d), os.path.join(scratch, d), ignore=shutil.ignore_patterns("*.so", "*.o"))
+    path = os.path.join(scratch, "apg_trajectory_tracking_b200", "csrc", "eval_kernels.cu")
+    s = open(path).read()
+    old = "return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + y.rows_total * TMP) + 16;"
+    assert old in s
+    open(path, "w").write(s.replace(old, "return sizeof(float) * (size_t)(y.f_total + pad4(TM * y.F0) + (y.rows_total - 8) * TMP) + 16;"))
+    objs = []
+    for name in ("host", "te", "tc", "dw"):
+        obj = os.path.join(scratch, name + ".o")
+        subprocess.check_call(["g++", "-O1", "-c", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
+                               "-I", os.path.join(scratch, "apg_trajectory_tracking_b200", "csrc"),
+                               os.path.join(scratch, "tests", "hostcheck", "capisim", name + ".cpp"), "-o", obj])
+        objs.append(obj)
+    libp = os.path.join(scratch, "libsim.so")
+    subprocess.check_call(["g++", "-shared", "-pthread"] + objs + ["-o", libp])
+    lib = ctypes.CDLL(libp)
+    lib.apg_workspace_bytes.restype = ctypes.c_size_t
+    n, steps = 8, 3
+    cfg = R.RolloutSpec.cartpole_concurrent(10, 0.05).config(n)
+    ws = torch.zeros(lib.apg_workspace_bytes(ctypes.byref(cfg)) + 512, dtype=torch.uint8)
+    wsp = ctypes.c_void_p(ws.data_ptr() + (-ws.data_ptr()) % 256)
+    params = torch.cat([p.reshape(-1) for p in B.default_init("cartpole", 10, seed=0)]).contiguous()
+    init = torch.zeros(n, 4)
+    states, nst = torch.zeros(n, steps, 4), torch.zeros(n, dtype=torch.int32)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())                                 # noqa: E731
+    rc = lib.apg_eval_cartpole(ctypes.byref(cfg), vp(params), vp(init), steps, ctypes.c_float(0.21), 1, wsp,
+                               vp(states), None, vp(nst), None, None, None, None)
+    buf = ctypes.create_string_buffer(1024)
+    ne = lib.apg_sim_take_errors(buf, 1024)
+    print("launcher of eval_cartpole_kernel requests 8 rows of shared memory too few: rc", rc, "->",
+          (buf.value.decode()[:110] if ne else "NOT noticed"), flush=True)
+    shutil.rmtree(scratch, ignore_errors=True)
+
+
+if __name__ == "__main__" and "--smem" in sys.argv:
+    smem_mutant()
