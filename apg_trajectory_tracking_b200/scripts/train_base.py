@@ -48,8 +48,18 @@ class TrainBase:
         return self.delta_t
 
     def modified_params(self):
+        """Physical constants of the fused rollout = those of the dynamics object the trainer was GIVEN (the reference
+        differentiates through ``self.train_dynamics``, train_drone.py:186-190), not the config's ``modified_params``
+        entry (which in the reference's fine-tuning set-ups describes the EVALUATION dynamics)."""
+        if isinstance(self.train_dynamics, torch.nn.Module):
+            if self.train_mode != "concurrent":
+                raise ValueError("learnt dynamics are only supported with train_mode='concurrent' (the recurrent "
+                                 "kernels integrate the analytic model)")
+            return {}
         cfg = getattr(self.train_dynamics, "cfg", None)
-        return self.config.get("modified_params", {}) if cfg is None else self.config.get("modified_params", {})
+        if cfg is not None:
+            return dict(cfg)
+        return dict(self.config.get("modified_params", {}))
 
     def init_optimizer(self):
         if self.state_data is not None:

@@ -26,14 +26,20 @@ def t(x, dtype=torch.float32):
     return torch.tensor(np.asarray(x), dtype=dtype)
 
 
+def _cpu64(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().to(device="cpu", dtype=torch.float64)
+    return torch.as_tensor(x, dtype=torch.float64)
+
+
 def rel_err(a, b):
-    a = torch.as_tensor(a, dtype=torch.float64).detach()
-    b = torch.as_tensor(b, dtype=torch.float64).detach()
+    a = _cpu64(a)
+    b = _cpu64(b)
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
 def max_rel_to_scale(a, b):
     """max |a-b| / max|b|  -- elementwise error relative to the tensor's scale."""
-    a = torch.as_tensor(a, dtype=torch.float64).detach()
-    b = torch.as_tensor(b, dtype=torch.float64).detach()
+    a = _cpu64(a)
+    b = _cpu64(b)
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))

@@ -386,17 +386,27 @@ def test_learnt_wing_dynamics_matches_reference(tag):
         want = torch.tensor(g[f"{tag}_gparam_{i}"])
         err = float((p.grad.cpu() - want).abs().max())
         assert err <= 2e-4 * max(float(want.abs().max()), 1e-2), (name, err)
-    # several tiles per block, ragged: against fp32 autograd of the oracle
+    # several tiles per block, ragged: against fp64 autograd of the oracle.  A parameter gradient is a sum over the
+    # drones that can cancel by orders of magnitude (cfg.CL_del_e in case wb: 0.012 out of per-drone terms summing to
+    # 72 in magnitude; the fp32 oracle itself is 1e-4 off there), so the bar is 2e-4 of the gradient plus 2e-7 (a few
+    # fp32 ulps) of the cancellation scale = the sum of |per-chunk gradients| over 50-drone chunks.
     from oracle import apg_oracle as O
     gen = torch.Generator().manual_seed(1)
     n = 3000
     s0 = torch.tensor(g[f"{tag}_state"])
     sn = s0[torch.randint(0, s0.shape[0], (n,), generator=gen)] + 0.02 * torch.randn(n, 12, generator=gen)
     an, cot = torch.rand(n, 4, generator=gen), torch.randn(n, 12, generator=gen)
-    lparams = [p.detach().cpu().clone().requires_grad_(True) for _, p in d.named_parameters()]
-    so, ao = sn.clone().requires_grad_(True), an.clone().requires_grad_(True)
+    lparams = [p.detach().cpu().double().clone().requires_grad_(True) for _, p in d.named_parameters()]
+    so, ao = sn.double().requires_grad_(True), an.double().requires_grad_(True)
     want = O.learnt_wing_step(lparams, so, ao, 0.05)
-    wg = torch.autograd.grad(want, [so, ao] + lparams, cot, allow_unused=True)
+    wg = torch.autograd.grad(want, [so, ao] + lparams, cot.double(), allow_unused=True)
+    scale = [torch.zeros_like(p) for p in lparams]
+    for c in range(0, n, 50):
+        part = O.learnt_wing_step(lparams, sn[c:c + 50].double(), an[c:c + 50].double(), 0.05)
+        pg = torch.autograd.grad(part, lparams, cot[c:c + 50].double(), allow_unused=True)
+        for acc, x in zip(scale, pg):
+            if x is not None:
+                acc += x.abs()
     d.zero_grad()
     sc, ac = sn.cuda().requires_grad_(True), an.cuda().requires_grad_(True)
     out = d(sc, ac, 0.05)
@@ -405,7 +415,9 @@ def test_learnt_wing_dynamics_matches_reference(tag):
     assert _close(sc.grad, wg[0], 5e-5) and _close(ac.grad, wg[1], 5e-5)
     for i, (name, p) in enumerate(d.named_parameters()):
         if wg[2 + i] is not None:
-            assert rel_err(p.grad, wg[2 + i]) <= 2e-4, name
+            err = float((p.grad.cpu().double() - wg[2 + i]).norm())
+            bar = 2e-4 * float(wg[2 + i].norm()) + 2e-7 * float(scale[i].norm())
+            assert err <= bar, (name, err, bar)
 
 
 def test_learnt_controller_epoch_through_identity_learnt_dynamics_equals_fused_epoch():
