@@ -86,7 +86,9 @@ HutterLayout hutter_layout(const apg_config* c) {
 
 struct Plan {
   int grid, ntiles;
-  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_tc, o_dzo, o_dz3, o_dz2, o_dz1, o_dzx, total;
+  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_tc, o_dzo, o_dz3, o_dz2, o_dz1, o_dzx,
+      o_hdr, o_tq_t, o_tq_f, o_tq_z, total;
+  int tq_grid;
 };
 
 NetInfo net_info(const apg_config* c) {
@@ -136,6 +138,15 @@ Plan make_plan(const apg_config* c, const NetInfo& y) {
   p.o_dz2 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
   p.o_dz1 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
   p.o_dzx = o;    o += up256(sizeof(float) * dzt * y.x1_rows * TMP);
+  // header: which forward variant produced the stash / weight images of this workspace (read by backward)
+  p.o_hdr = o;    o += 256;
+  // tcgen05 path, second generation (quadrotor concurrent): transposed weight images, X stash and dZ stash in operand-
+  // image format (tq_layout.cuh); the forward images live at o_tc
+  const bool tq_cfg = is_hutter(c) && !is_recurrent(c) && c->system == SYS_QUAD && tq_supported(hutter_layout(c), c->horizon);
+  p.o_tq_t = o;   o += tq_cfg ? up256(tq_tblob_bytes()) : 0;
+  p.o_tq_f = o;   o += tq_cfg ? up256(tq_fstash_bytes(c->n_drones)) + 1024 : 0;
+  p.o_tq_z = o;   o += tq_cfg ? up256(tq_zstash_bytes(c->n_drones)) + 1024 : 0;
+  p.tq_grid = tq_cfg ? tq_grid(c->n_drones, sms) : 0;
   p.total = o;
   return p;
 }
@@ -193,6 +204,18 @@ bool use_tc_dw(const apg_config* c, const HutterLayout& y) {
   return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && adj_dw_tc_supported(y, c->horizon);
 }
 
+// The tcgen05 path (tq_kernels.cu / tq_dw_kernels.cu) is THE path of the quadrotor concurrent configuration it is
+// written for (Net(15,10,9,40,conv), h = 10); APG_LEGACY_MMA=1 selects the mma.sync kernels instead (kept for the other
+// configurations and as a cross-check).
+bool use_tq(const apg_config* c, const HutterLayout& y) {
+  if (env_flag("APG_LEGACY_MMA") || env_flag("APG_TC_FWD") || env_flag("APG_TC_DW")) return false;
+  return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && tq_supported(y, c->horizon);
+}
+inline unsigned char* align1024(unsigned char* p) {
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+enum FwdVariant { FWD_LEGACY = 1, FWD_TC1 = 2, FWD_TQ = 3 };
+
 // cached device buffers of the host-buffer entry point
 struct HostCache {
   void* buf = nullptr;
@@ -245,11 +268,23 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
   if (is_hutter(cfg)) {
     const HutterLayout y = hutter_layout(cfg);
     // the mma.sync kernels' packed weights; not needed when forward AND both adjoint halves run on the tcgen05 images
-    const bool all_tc = use_tc_forward(cfg, y) && use_tc_dw(cfg, y) && env_flag("APG_TC_DX");
+    const bool tq = !is_recurrent(cfg) && use_tq(cfg, y);
+    const bool all_tc = tq || (use_tc_forward(cfg, y) && use_tc_dw(cfg, y) && env_flag("APG_TC_DX"));
+    const int variant = tq ? FWD_TQ : (use_tc_forward(cfg, y) ? FWD_TC1 : FWD_LEGACY);
+    // stamp the workspace with the variant that fills its stash (one byte value, capturable memset node); the adjoint
+    // kernels of the tcgen05 path check it on the device and poison the gradient on a mismatch
+    if ((ce = cudaMemsetAsync(static_cast<char*>(workspace) + p.o_hdr, variant, 16, st))) return (int)ce;
     if (!all_tc &&
         (ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
       return (int)ce;
     if (is_recurrent(cfg)) { if ((ce = launch_rec_fwd(y, a, p.grid, st))) return (int)ce; }
+    else if (tq) {
+      unsigned char* w = static_cast<unsigned char*>(workspace);
+      if ((ce = launch_tq_fwd(y, params, w + p.o_tc, w + p.o_tq_t, a, align1024(w + p.o_tq_f), p.tq_grid, st)))
+        return (int)ce;
+      if (loss && (ce = launch_sum_loss(a.loss_partials, p.tq_grid, loss, st))) return (int)ce;
+      return 0;
+    }
     else if (use_tc_forward(cfg, y)) {
       // optional tcgen05 / TMEM forward (APG_TC_FWD=1): same stash, consumed by the same adjoint kernel
       unsigned char* blob = static_cast<unsigned char*>(workspace) + p.o_tc;
@@ -307,6 +342,18 @@ int rollout_backward_impl(const apg_config* cfg, const float* params, const floa
   cudaError_t ce;
   if (is_hutter(cfg)) {
     if (is_recurrent(cfg)) { if ((ce = launch_rec_adj(hutter_layout(cfg), a, p.grid, st))) return (int)ce; }
+    else if (use_tq(cfg, hutter_layout(cfg))) {
+      // tcgen05 path: dX chain (reverse sweep + dZ stash), then the streaming weight-gradient GEMM on the two stashes
+      const HutterLayout y = hutter_layout(cfg);
+      unsigned char* w = static_cast<unsigned char*>(workspace);
+      unsigned char* fs = align1024(w + p.o_tq_f);
+      unsigned char* zs = align1024(w + p.o_tq_z);
+      if ((ce = launch_tq_dx(w + p.o_tq_t, a, fs, zs, w + p.o_hdr, FWD_TQ, p.tq_grid, st))) return (int)ce;
+      if ((ce = launch_tq_dw(y, a, fs, zs, p.tq_grid, st))) return (int)ce;
+      if ((ce = finish_gradient(a.grad_partials, p.tq_grid, ni.n_params, grad_loss, grad_params, comm, 0, 0, 0, true, st)))
+        return (int)ce;
+      return 0;
+    }
     else if (use_tc_dw(cfg, hutter_layout(cfg))) {
       // optional split adjoint (APG_TC_DW=1): dX chain + dZ stash, then the streaming tcgen05 weight-gradient GEMM
       const HutterLayout y = hutter_layout(cfg);

@@ -32,6 +32,21 @@ cudaError_t launch_adj_dw_tc(const HutterLayout& y, const RolloutArgs& a, const 
 bool adj_dw_tc_supported(const HutterLayout& y, int h);
 cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st);
 
+// tcgen05 / TMEM path of the quadrotor concurrent rollout, second generation (tq_kernels.cu, tq_dw_kernels.cu,
+// tq_layout.cuh): forward, dX chain and streaming weight-gradient GEMM on operand-image stashes
+bool tq_supported(const HutterLayout& y, int h);
+size_t tq_blob_bytes();
+size_t tq_tblob_bytes();
+size_t tq_fstash_bytes(int n);
+size_t tq_zstash_bytes(int n);
+int tq_grid(int n, int sms);
+cudaError_t launch_tq_fwd(const HutterLayout& y, const float* params, unsigned char* blob, unsigned char* tblob,
+                          const RolloutArgs& a, unsigned char* fstash, int grid, cudaStream_t st);
+cudaError_t launch_tq_dx(const unsigned char* tblob, const RolloutArgs& a, unsigned char* fstash,
+                         unsigned char* zstash, const unsigned char* stamp, int want_stamp, int grid, cudaStream_t st);
+cudaError_t launch_tq_dw(const HutterLayout& y, const RolloutArgs& a, const unsigned char* fstash,
+                         const unsigned char* zstash, int grid, cudaStream_t st);
+
 cudaError_t launch_rec_fwd(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_rec_adj(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_lstm_fwd(const LstmLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);

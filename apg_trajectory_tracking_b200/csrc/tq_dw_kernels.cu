@@ -1,0 +1,238 @@
+// Weight gradient of the quadrotor concurrent rollout as ONE streaming tcgen05 GEMM over the drone axis,
+//     dW_l[out][in] = sum over drones dZ_l[drone][out] * X_l[drone][in]          (loss.backward() of train_base.py:205),
+// on the two operand-image stashes written by tq_fwd_kernel (X_l) and tq_dx_kernel (dZ_l): tq_layout.cuh.
+// Accumulators of all layers resident in TMEM (416 columns) for the whole launch: D[M = in (+ ones row -> bias)][N = out].
+//
+// Pipeline (4 stages of 48 KiB, one 32-drone panel of one op per stage):
+//   warp 0 lane 0   producer  : two 1-D bulk copies per stage (A panel, B panel) straight from the stash - the stash IS
+//                               the 128B-swizzled K-major image, so there is no loader arithmetic and no tensor map
+//   warps 2-9       converters: lo image = x - tf32(x) next to each raw image (the tensor core truncates the raw fp32
+//                               image itself: that is the hi part), the constant ones rows of the bias gradients
+//   warp 1 lane 0   MMA issuer: per stage 4 k-steps x 3 MMAs (3xTF32), tcgen05.commit frees the stage
+// HBM-bound by construction: 4.2 KB per drone.  Op list / accumulator columns / gradient map: adj_dw_layout.cuh.
+#include "tq_layout.cuh"
+#include "tc_prims.cuh"
+#include "rollout_args.h"
+#ifndef APG_TC_SIM
+#include "tile_engine.cuh"
+#endif
+#include "kernels.h"
+
+namespace apg {
+
+namespace {
+
+constexpr int DWQ_CONV = 256;                                 // converter threads (warps 2..9)
+constexpr int DWQ_THREADS = 64 + DWQ_CONV;
+constexpr int DWQ_SMEM = 1024 + tq::DW_NSTAGE * tq::DW_STAGE_BYTES;
+constexpr int O_ALO = tq::DW_A_BYTES, O_BRAW = 2 * tq::DW_A_BYTES, O_BLO = 2 * tq::DW_A_BYTES + tq::DW_B_BYTES;
+
+struct DwqBars {
+  unsigned long long full[tq::DW_NSTAGE];        // bulk copies landed (1 arrival + bytes)
+  unsigned long long conv[tq::DW_NSTAGE];        // lo images written (256 arrivals)
+  unsigned long long empty[tq::DW_NSTAGE];       // MMAs that read the stage are complete (tcgen05.commit)
+  unsigned long long done;
+};
+
+__device__ __forceinline__ void dwq_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  if (tcp::mbar_try_wait(bar, parity)) return;
+  const long long t0 = tcp::clock_now();
+  for (int spin = 0;; ++spin) {
+    if (tcp::mbar_try_wait(bar, parity)) return;
+    if ((spin & 63) == 63) {
+      if (*abort_flag) return;
+      if (tcp::clock_now() - t0 > 2000000000LL) { *abort_flag = 1; return; }
+    }
+  }
+}
+__device__ __forceinline__ float4 lo_of(float4 x) {
+  float4 l;
+  l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+  l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+  l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+  l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  return l;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(DWQ_THREADS, 1)
+    tq_dw_kernel(const HutterLayout y, const RolloutArgs g, const unsigned char* __restrict__ fstash,
+                 const unsigned char* __restrict__ zstash) {
+  APG_TC_DYNAMIC_SMEM(smem_raw);
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) DwqBars s_bars;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_abort;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = g.N;
+  const int ntiles = (n + tc::TMT - 1) / tc::TMT;
+  const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
+  volatile int* abort_flag = &s_abort;
+  constexpr int NS = tq::DW_NSTAGE;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      tcp::mbar_init(smem_u32(&s_bars.full[s]), 1);
+      tcp::mbar_init(smem_u32(&s_bars.conv[s]), DWQ_CONV);
+      tcp::mbar_init(smem_u32(&s_bars.empty[s]), 1);
+    }
+    tcp::mbar_init(smem_u32(&s_bars.done), 1);
+    s_abort = 0;
+    tcp::fence_mbar_init();
+  }
+  if (warp == 0) tcp::tmem_alloc512(&s_tmem);
+  tcp::fence_before_thread_sync();
+  __syncthreads();
+  tcp::fence_after_thread_sync();
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===================================================== producer
+    if (lane == 0) {
+      int u = 0;
+      for (int j = 0; j < my_tiles; ++j) {
+        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+        const unsigned char* fb = fstash + (size_t)tile * tq::F_TILE_BYTES;
+        const unsigned char* zb = zstash + (size_t)tile * tq::Z_TILE_BYTES;
+        for (int i = 0; i < dw::NOPS; ++i) {
+          const tq::DwSrc src = tq::dw_src(i);
+          const uint32_t a_bytes = (uint32_t)src.a_rows * 128u, b_bytes = (uint32_t)src.b_rows * 128u;
+          for (int p = 0; p < tq::NPANEL; ++p, ++u) {
+            const int s = u % NS;
+            if (u >= NS) dwq_wait(smem_u32(&s_bars.empty[s]), (uint32_t)(u / NS - 1) & 1u, abort_flag);
+            unsigned char* st = base + s * tq::DW_STAGE_BYTES;
+            const uint32_t bar = smem_u32(&s_bars.full[s]);
+            tcp::mbar_expect_tx(bar, a_bytes + b_bytes);
+            tcp::bulk_g2s(smem_u32(st), fb + tq::set_base(src.a_set) + (size_t)p * (size_t)(src.a_R * 128) +
+                                            (size_t)src.a_row0 * 128, a_bytes, bar);
+            tcp::bulk_g2s(smem_u32(st + O_BRAW), zb + tq::set_base(src.b_set) + (size_t)p * (size_t)(src.b_R * 128) +
+                                                     (size_t)src.b_row0 * 128, b_bytes, bar);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      int u = 0;
+      for (int j = 0; j < my_tiles; ++j)
+        for (int i = 0; i < dw::NOPS; ++i) {
+          const dw::Op op = dw::op_of(i);
+          const uint32_t idesc = tc::idesc_tf32(128, op.N);
+          const uint32_t d = tmem + op.d_col;
+          for (int p = 0; p < tq::NPANEL; ++p, ++u) {
+            const int s = u % NS;
+            dwq_wait(smem_u32(&s_bars.conv[s]), (uint32_t)(u / NS) & 1u, abort_flag);
+            tcp::fence_after_thread_sync();
+            const uint32_t a_raw = smem_u32(base + s * tq::DW_STAGE_BYTES), a_lo = a_raw + O_ALO,
+                           b_raw = a_raw + O_BRAW, b_lo = a_raw + O_BLO;
+            const bool clear = (j == 0) && op.first && (p == 0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ah = tq::sw128_desc(a_raw, ks), al = tq::sw128_desc(a_lo, ks);
+              const uint64_t bh = tq::sw128_desc(b_raw, ks), bl = tq::sw128_desc(b_lo, ks);
+              tcp::mma_ss(d, al, bh, idesc, (ks > 0 || !clear) ? 1u : 0u);
+              tcp::mma_ss(d, ah, bl, idesc, 1u);
+              tcp::mma_ss(d, ah, bh, idesc, 1u);
+            }
+            tcp::commit(smem_u32(&s_bars.empty[s]));      // the stage is free once these MMAs have read it
+          }
+        }
+      tcp::commit(smem_u32(&s_bars.done));                // all accumulators final
+    }
+  } else {
+    // ===================================================== converters: lo images + constant ones rows
+    const int ct = tid - 64;
+    int u = 0;
+    for (int j = 0; j < my_tiles; ++j)
+      for (int i = 0; i < dw::NOPS; ++i) {
+        const tq::DwSrc src = tq::dw_src(i);
+        const int na = src.a_rows * 8, nb = src.b_rows * 8;  // 16-byte chunks
+        for (int p = 0; p < tq::NPANEL; ++p, ++u) {
+          const int s = u % NS;
+          dwq_wait(smem_u32(&s_bars.full[s]), (uint32_t)(u / NS) & 1u, abort_flag);
+          unsigned char* st = base + s * tq::DW_STAGE_BYTES;
+          float4* a_raw = reinterpret_cast<float4*>(st);
+          float4* a_lo = reinterpret_cast<float4*>(st + O_ALO);
+          float4* b_raw = reinterpret_cast<float4*>(st + O_BRAW);
+          float4* b_lo = reinterpret_cast<float4*>(st + O_BLO);
+          for (int q = ct; q < na; q += DWQ_CONV) a_lo[q] = lo_of(a_raw[q]);
+          for (int q = ct; q < nb; q += DWQ_CONV) b_lo[q] = lo_of(b_raw[q]);
+          if (src.ones >= 0 && ct < 64) {                    // 8-row group [ones, ones + 8): row `ones` = 1, rest 0
+            const float v = (ct >> 3) == 0 ? 1.f : 0.f;
+            a_raw[src.ones * 8 + ct] = make_float4(v, v, v, v);
+            a_lo[src.ones * 8 + ct] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tcp::fence_proxy_async_smem();                     // generic writes -> tensor core reads
+          tcp::mbar_arrive(smem_u32(&s_bars.conv[s]));
+        }
+      }
+  }
+
+  // ===================================================== epilogue: accumulators -> this CTA's gradient partial
+  // unused tensors (ref_in.*) and padding stay zero; every entry of the partial is written exactly once
+  for (int i = tid; i < y.n_params; i += DWQ_THREADS) {
+    const bool conv_w = i >= y.t_wc && i < y.t_wc + tc::NC * tc::RD * 3 + tc::NC;    // conv_ref weight + bias: below
+    if (!conv_w && (my_tiles == 0 || (i >= y.t_wr && i < y.t_br + HID))) P[i] = 0.f;
+  }
+  if (my_tiles > 0 && warp >= 2 && warp < 6) {                 // four converter warps, one per TMEM lane quarter
+    dwq_wait(smem_u32(&s_bars.done), 0, abort_flag);
+    tcp::fence_after_thread_sync();
+    const int r = (warp & 3) * 32 + lane;                      // TMEM lane = A row
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float poison = __int_as_float(0x7fc00000);
+    float* s_T = reinterpret_cast<float*>(base);               // [37][48] conv Toeplitz block (stage memory is free)
+    const int col0[6] = {dw::C_WO, dw::C_W3, dw::C_W2, dw::C_W1A, dw::C_W1B, dw::C_WS};
+    const int ncol[6] = {48, 64, 64, 64, 64, 64};
+#pragma unroll
+    for (int reg = 0; reg < 6; ++reg) {
+      for (int c0 = 0; c0 < ncol[reg]; c0 += 8) {
+        uint32_t vb[8];
+        tcp::tmem_ld8(lane_addr + col0[reg] + c0, vb);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int idx = dw::grad_index(y, reg, r, c0 + q);
+          if (idx >= 0) P[idx] = *abort_flag ? poison : __uint_as_float(vb[q]);
+        }
+      }
+    }
+    for (int c0 = 0; c0 < 48; c0 += 8) {
+      uint32_t vb[8];
+      tcp::tmem_ld8(lane_addr + dw::C_WT + c0, vb);
+      if (r <= 4 * tc::RD) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_T[r * 48 + c0 + q] = __uint_as_float(vb[q]);
+      }
+    }
+  }
+  tcp::fence_before_thread_sync();
+  __syncthreads();
+  if (my_tiles > 0) {
+    const float* s_T = reinterpret_cast<const float*>(base);
+    for (int i = tid; i < tc::NC * tc::RD * 3 + tc::NC; i += DWQ_THREADS) {
+      float v;
+      if (i < tc::NC * tc::RD * 3) {
+        const int c = i / (tc::RD * 3), ci = (i / 3) % tc::RD, jj = i % 3;
+        v = dw::conv_weight_from_block(s_T, 48, c, ci, jj);
+      } else {
+        v = dw::conv_bias_from_block(s_T, 48, i - tc::NC * tc::RD * 3);
+      }
+      P[y.t_wc + i] = *abort_flag ? __int_as_float(0x7fc00000) : v;
+    }
+  } else {
+    for (int i = tid; i < tc::NC * tc::RD * 3 + tc::NC; i += DWQ_THREADS) P[y.t_wc + i] = 0.f;
+  }
+  if (warp == 0) tcp::tmem_dealloc512(tmem);
+}
+
+cudaError_t launch_tq_dw(const HutterLayout& y, const RolloutArgs& a, const unsigned char* fstash,
+                         const unsigned char* zstash, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tq_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWQ_SMEM);
+  if (e != cudaSuccess) return e;
+  APG_LAUNCH(grid, DWQ_THREADS, DWQ_SMEM, st, tq_dw_kernel)(y, a, fstash, zstash);
+  return cudaGetLastError();
+}
+
+}  // namespace apg

@@ -58,6 +58,9 @@ inline void mbar_init(uint32_t bar, int count) {
   sim::Mbar& b = sim::S().bars[bar];
   b.count = b.pending = count; b.phase = 0; b.init = true;
 }
+inline void settle(sim::Mbar& b) {
+  if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.count; }
+}
 inline void mbar_arrive(uint32_t bar) {
   sim::State& st = sim::S();
   bool bad = false;
@@ -65,11 +68,39 @@ inline void mbar_arrive(uint32_t bar) {
     std::lock_guard<std::mutex> lk(st.m);
     sim::Mbar& b = st.bars[bar];
     if (!b.init) bad = true;
-    else if (--b.pending == 0) { b.phase ^= 1u; b.pending = b.count; }
+    else { --b.pending; settle(b); }
   }
   if (bad) sim::fail("arrive on an uninitialised mbarrier");
   st.cv.notify_all();
 }
+// arrive + expected transaction bytes; the phase completes when the arrivals AND the bytes are in
+inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  sim::State& st = sim::S();
+  bool bad = false;
+  {
+    std::lock_guard<std::mutex> lk(st.m);
+    sim::Mbar& b = st.bars[bar];
+    if (!b.init) bad = true;
+    else { b.tx += bytes; --b.pending; settle(b); }
+  }
+  if (bad) sim::fail("expect_tx on an uninitialised mbarrier");
+  st.cv.notify_all();
+}
+// cp.async.bulk global -> shared: copied at issue, then complete_tx on the barrier
+inline void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  sim::State& st = sim::S();
+  if ((bytes & 15u) || (dst_smem & 15u) || ((uintptr_t)src & 15u)) sim::fail("cp.async.bulk: size / address not 16-byte aligned");
+  if ((dst_smem >> 30) != 0 || (size_t)dst_smem + bytes > sim::DYN_SMEM) { sim::fail("cp.async.bulk: destination outside the dynamic shared memory"); return; }
+  memcpy(st.smem + dst_smem, src, bytes);
+  {
+    std::lock_guard<std::mutex> lk(st.m);
+    sim::Mbar& b = st.bars[bar];
+    b.tx -= bytes;
+    settle(b);
+  }
+  st.cv.notify_all();
+}
+inline void prefetch_l2(const void*) {}
 // true once the phase with the given parity has completed (PTX mbarrier.try_wait.parity)
 inline bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   sim::State& st = sim::S();
@@ -99,26 +130,32 @@ inline void commit(uint32_t bar) {
   t_queue.clear();
   mbar_arrive(bar);
 }
-inline bool lane_rule(uint32_t addr, int* lane, int* col) {
+inline bool lane_rule(uint32_t addr, int* lane, int* col, int ncol = 8) {
   const int lane0 = (int)(addr >> 16), c = (int)(addr & 0xffff);
   const int warp = (int)(threadIdx.x >> 5);
   *lane = lane0 + (int)(threadIdx.x & 31);
   *col = c;
   if (lane0 != 32 * (warp & 3)) { sim::fail("tcgen05.ld/st: warp " + std::to_string(warp) + " addressed lane base " +
                                             std::to_string(lane0)); return false; }
-  if (c < 0 || c + 8 > 512) { sim::fail("tcgen05.ld/st: column range " + std::to_string(c)); return false; }
+  if (c < 0 || c + ncol > 512) { sim::fail("tcgen05.ld/st: column range " + std::to_string(c)); return false; }
   return true;
 }
-inline void tmem_ld8(uint32_t addr, uint32_t* r) {
+inline void tmem_ldn(uint32_t addr, uint32_t* r, int ncol) {
   int lane, col;
-  if (!lane_rule(addr, &lane, &col)) { for (int j = 0; j < 8; ++j) r[j] = 0x7fc00000u; return; }
-  memcpy(r, &sim::S().tmem[lane * 512 + col], 32);
+  if (!lane_rule(addr, &lane, &col, ncol)) { for (int j = 0; j < ncol; ++j) r[j] = 0x7fc00000u; return; }
+  memcpy(r, &sim::S().tmem[lane * 512 + col], 4 * ncol);
 }
-inline void tmem_st8(uint32_t addr, const uint32_t* r) {
+inline void tmem_stn(uint32_t addr, const uint32_t* r, int ncol) {
   int lane, col;
-  if (!lane_rule(addr, &lane, &col)) return;
-  memcpy(&sim::S().tmem[lane * 512 + col], r, 32);
+  if (!lane_rule(addr, &lane, &col, ncol)) return;
+  memcpy(&sim::S().tmem[lane * 512 + col], r, 4 * ncol);
 }
+inline void tmem_ld8(uint32_t addr, uint32_t* r) { tmem_ldn(addr, r, 8); }
+inline void tmem_st8(uint32_t addr, const uint32_t* r) { tmem_stn(addr, r, 8); }
+inline void tmem_ld16(uint32_t addr, uint32_t* r) { tmem_ldn(addr, r, 16); }
+inline void tmem_st16(uint32_t addr, const uint32_t* r) { tmem_stn(addr, r, 16); }
+inline void tmem_ld32(uint32_t addr, uint32_t* r) { tmem_ldn(addr, r, 32); }
+inline void tmem_st32(uint32_t addr, const uint32_t* r) { tmem_stn(addr, r, 32); }
 inline void wait_st() {}
 inline void fence_before_thread_sync() {}
 inline void fence_after_thread_sync() {}
@@ -135,9 +172,11 @@ inline void tmem_dealloc512(uint32_t addr) {
   sim::S().tmem_allocated = false;
 }
 // slow clock: the kernels' 2e9-tick timeouts become ~200 s of wall time here
+// (APG_SIM_FAST_TIMEOUT=1: ~5 s, for debugging a protocol dead-lock)
 inline long long clock_now() {
+  static const long long div = getenv("APG_SIM_FAST_TIMEOUT") ? 2 : 100;
   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
-             .count() / 100;
+             .count() / div;
 }
 
 }  // namespace tcp
