@@ -88,7 +88,7 @@ struct Plan {
   int grid, ntiles;
   size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_tc, o_dzo, o_dz3, o_dz2, o_dz1, o_dzx,
       o_hdr, o_tq_t, o_tq_f, o_tq_z, total;
-  int tq_grid;
+  int tq_grid, tq_dyn_grid;
 };
 
 NetInfo net_info(const apg_config* c) {
@@ -147,6 +147,7 @@ Plan make_plan(const apg_config* c, const NetInfo& y) {
   p.o_tq_f = o;   o += tq_cfg ? up256(tq_fstash_bytes(c->n_drones)) + 1024 : 0;
   p.o_tq_z = o;   o += tq_cfg ? up256(tq_zstash_bytes(c->n_drones)) + 1024 : 0;
   p.tq_grid = tq_cfg ? tq_grid(c->n_drones, sms) : 0;
+  p.tq_dyn_grid = tq_cfg ? tq_dyn_grid(c->n_drones, sms) : 0;
   p.total = o;
   return p;
 }
@@ -280,9 +281,10 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
     if (is_recurrent(cfg)) { if ((ce = launch_rec_fwd(y, a, p.grid, st))) return (int)ce; }
     else if (tq) {
       unsigned char* w = static_cast<unsigned char*>(workspace);
-      if ((ce = launch_tq_fwd(y, params, w + p.o_tc, w + p.o_tq_t, a, align1024(w + p.o_tq_f), p.tq_grid, st)))
+      if ((ce = launch_tq_fwd(y, params, w + p.o_tc, w + p.o_tq_t, a, align1024(w + p.o_tq_f), align1024(w + p.o_tq_z),
+                              p.tq_grid, p.tq_dyn_grid, st)))
         return (int)ce;
-      if (loss && (ce = launch_sum_loss(a.loss_partials, p.tq_grid, loss, st))) return (int)ce;
+      if (loss && (ce = launch_sum_loss(a.loss_partials, p.tq_dyn_grid, loss, st))) return (int)ce;
       return 0;
     }
     else if (use_tc_forward(cfg, y)) {

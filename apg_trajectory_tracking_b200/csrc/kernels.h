@@ -40,8 +40,10 @@ size_t tq_tblob_bytes();
 size_t tq_fstash_bytes(int n);
 size_t tq_zstash_bytes(int n);
 int tq_grid(int n, int sms);
+int tq_dyn_grid(int n, int sms);
 cudaError_t launch_tq_fwd(const HutterLayout& y, const float* params, unsigned char* blob, unsigned char* tblob,
-                          const RolloutArgs& a, unsigned char* fstash, int grid, cudaStream_t st);
+                          const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int grid, int dyn_grid,
+                          cudaStream_t st);
 cudaError_t launch_tq_dx(const unsigned char* tblob, const RolloutArgs& a, unsigned char* fstash,
                          unsigned char* zstash, const unsigned char* stamp, int want_stamp, int grid, cudaStream_t st);
 cudaError_t launch_tq_dw(const HutterLayout& y, const RolloutArgs& a, const unsigned char* fstash,

@@ -3,12 +3,14 @@
 // on the two operand-image stashes written by tq_fwd_kernel (X_l) and tq_dx_kernel (dZ_l): tq_layout.cuh.
 // Accumulators of all layers resident in TMEM (416 columns) for the whole launch: D[M = in (+ ones row -> bias)][N = out].
 //
-// Pipeline (4 stages of 48 KiB, one 32-drone panel of one op per stage):
-//   warp 0 lane 0   producer  : two 1-D bulk copies per stage (A panel, B panel) straight from the stash - the stash IS
+// Pipeline (unit = one 32-drone panel of one op; a ring of 7 RAW stages of 24 KiB that the bulk copies land in, and a
+// ring of 2 LO stages that only live from conversion to the MMAs - the copies in flight are what hides the HBM latency,
+// so the raw ring is deep and the lo images do not take shared memory away from it):
+//   warp 0 lane 0   producer  : two 1-D bulk copies per unit (A panel, B panel) straight from the stash - the stash IS
 //                               the 128B-swizzled K-major image, so there is no loader arithmetic and no tensor map
-//   warps 2-9       converters: lo image = x - tf32(x) next to each raw image (the tensor core truncates the raw fp32
+//   warps 2-9       converters: lo image = x - tf32(x) of each raw image (the tensor core truncates the raw fp32
 //                               image itself: that is the hi part), the constant ones rows of the bias gradients
-//   warp 1 lane 0   MMA issuer: per stage 4 k-steps x 3 MMAs (3xTF32), tcgen05.commit frees the stage
+//   warp 1 lane 0   MMA issuer: per unit 4 k-steps x 3 MMAs (3xTF32), two tcgen05.commit free the raw and the lo stage
 // HBM-bound by construction: 4.2 KB per drone.  Op list / accumulator columns / gradient map: adj_dw_layout.cuh.
 #include "tq_layout.cuh"
 #include "tc_prims.cuh"
@@ -18,19 +20,30 @@
 #endif
 #include "kernels.h"
 
+#ifdef APG_PROFILE
+__device__ long long g_tq_prof_dw[3][148][TQ_NPROF];
+#define TQ_PROF_ARRAY g_tq_prof_dw
+extern "C" __attribute__((visibility("default"))) int apg_debug_profile_tq_dw(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_tq_prof_dw, sizeof(long long) * 3 * 148 * TQ_NPROF);
+}
+#endif
+
 namespace apg {
 
 namespace {
 
 constexpr int DWQ_CONV = 256;                                 // converter threads (warps 2..9)
 constexpr int DWQ_THREADS = 64 + DWQ_CONV;
-constexpr int DWQ_SMEM = 1024 + tq::DW_NSTAGE * tq::DW_STAGE_BYTES;
-constexpr int O_ALO = tq::DW_A_BYTES, O_BRAW = 2 * tq::DW_A_BYTES, O_BLO = 2 * tq::DW_A_BYTES + tq::DW_B_BYTES;
+constexpr int NR = tq::DW_NRAW, NL = tq::DW_NLO;
+constexpr int STAGE = tq::DW_A_BYTES + tq::DW_B_BYTES;        // one raw or lo stage: A panel (128 rows) | B panel (64 rows)
+constexpr int DWQ_SMEM = 1024 + (NR + NL) * STAGE;
+static_assert(DWQ_SMEM <= 232448, "stage rings do not fit in shared memory");
 
 struct DwqBars {
-  unsigned long long full[tq::DW_NSTAGE];        // bulk copies landed (1 arrival + bytes)
-  unsigned long long conv[tq::DW_NSTAGE];        // lo images written (256 arrivals)
-  unsigned long long empty[tq::DW_NSTAGE];       // MMAs that read the stage are complete (tcgen05.commit)
+  unsigned long long full[NR];                   // bulk copies landed (1 arrival + bytes)
+  unsigned long long rfree[NR];                  // MMAs that read the raw stage are complete (tcgen05.commit)
+  unsigned long long lo_ready[NL];               // lo images written (256 arrivals)
+  unsigned long long lo_free[NL];                // MMAs that read the lo stage are complete (tcgen05.commit)
   unsigned long long done;
 };
 
@@ -70,13 +83,16 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
   volatile int* abort_flag = &s_abort;
-  constexpr int NS = tq::DW_NSTAGE;
+  unsigned char* lo_base = base + NR * STAGE;
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NR; ++s) {
       tcp::mbar_init(smem_u32(&s_bars.full[s]), 1);
-      tcp::mbar_init(smem_u32(&s_bars.conv[s]), DWQ_CONV);
-      tcp::mbar_init(smem_u32(&s_bars.empty[s]), 1);
+      tcp::mbar_init(smem_u32(&s_bars.rfree[s]), 1);
+    }
+    for (int s = 0; s < NL; ++s) {
+      tcp::mbar_init(smem_u32(&s_bars.lo_ready[s]), DWQ_CONV);
+      tcp::mbar_init(smem_u32(&s_bars.lo_free[s]), 1);
     }
     tcp::mbar_init(smem_u32(&s_bars.done), 1);
     s_abort = 0;
@@ -91,6 +107,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   if (warp == 0) {
     // ===================================================== producer
     if (lane == 0) {
+      TQP_DECL
       int u = 0;
       for (int j = 0; j < my_tiles; ++j) {
         const int tile = (int)blockIdx.x + j * (int)gridDim.x;
@@ -100,22 +117,29 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
           const tq::DwSrc src = tq::dw_src(i);
           const uint32_t a_bytes = (uint32_t)src.a_rows * 128u, b_bytes = (uint32_t)src.b_rows * 128u;
           for (int p = 0; p < tq::NPANEL; ++p, ++u) {
-            const int s = u % NS;
-            if (u >= NS) dwq_wait(smem_u32(&s_bars.empty[s]), (uint32_t)(u / NS - 1) & 1u, abort_flag);
-            unsigned char* st = base + s * tq::DW_STAGE_BYTES;
-            const uint32_t bar = smem_u32(&s_bars.full[s]);
+            const int r = u % NR;
+            if (u >= NR) dwq_wait(smem_u32(&s_bars.rfree[r]), (uint32_t)(u / NR - 1) & 1u, abort_flag);
+            TQP(0);
+            unsigned char* st = base + r * STAGE;
+            const uint32_t bar = smem_u32(&s_bars.full[r]);
             tcp::mbar_expect_tx(bar, a_bytes + b_bytes);
             tcp::bulk_g2s(smem_u32(st), fb + tq::set_base(src.a_set) + (size_t)p * (size_t)(src.a_R * 128) +
                                             (size_t)src.a_row0 * 128, a_bytes, bar);
-            tcp::bulk_g2s(smem_u32(st + O_BRAW), zb + tq::set_base(src.b_set) + (size_t)p * (size_t)(src.b_R * 128) +
-                                                     (size_t)src.b_row0 * 128, b_bytes, bar);
+            tcp::bulk_g2s(smem_u32(st + tq::DW_A_BYTES), zb + tq::set_base(src.b_set) +
+                                                             (size_t)p * (size_t)(src.b_R * 128) +
+                                                             (size_t)src.b_row0 * 128, b_bytes, bar);
+            TQP(1);
           }
         }
       }
+      TQP_FLUSH(2, 0, 2);
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
+      TQP_DECL
+      const uint32_t raw0 = smem_u32(base), lo0 = smem_u32(lo_base);
+      const uint64_t DESC_HI = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
       int u = 0;
       for (int j = 0; j < my_tiles; ++j)
         for (int i = 0; i < dw::NOPS; ++i) {
@@ -123,41 +147,49 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
           const uint32_t idesc = tc::idesc_tf32(128, op.N);
           const uint32_t d = tmem + op.d_col;
           for (int p = 0; p < tq::NPANEL; ++p, ++u) {
-            const int s = u % NS;
-            dwq_wait(smem_u32(&s_bars.conv[s]), (uint32_t)(u / NS) & 1u, abort_flag);
+            const int r = u % NR, l = u % NL;
+            dwq_wait(smem_u32(&s_bars.lo_ready[l]), (uint32_t)(u / NL) & 1u, abort_flag);
+            TQP(0);
             tcp::fence_after_thread_sync();
-            const uint32_t a_raw = smem_u32(base + s * tq::DW_STAGE_BYTES), a_lo = a_raw + O_ALO,
-                           b_raw = a_raw + O_BRAW, b_lo = a_raw + O_BLO;
+            // descriptors: constant high word (SBO 1024, version, SWIZZLE_128B), low word = address >> 4 | LBO field;
+            // k-step ks adds 2 (32 bytes >> 4)
+            uint32_t ar = ((raw0 + (uint32_t)r * STAGE) >> 4) | (1u << 16), br = ar + (tq::DW_A_BYTES >> 4);
+            uint32_t al = ((lo0 + (uint32_t)l * STAGE) >> 4) | (1u << 16), bl = al + (tq::DW_A_BYTES >> 4);
             const bool clear = (j == 0) && op.first && (p == 0);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ah = tq::sw128_desc(a_raw, ks), al = tq::sw128_desc(a_lo, ks);
-              const uint64_t bh = tq::sw128_desc(b_raw, ks), bl = tq::sw128_desc(b_lo, ks);
-              tcp::mma_ss(d, al, bh, idesc, (ks > 0 || !clear) ? 1u : 0u);
-              tcp::mma_ss(d, ah, bl, idesc, 1u);
-              tcp::mma_ss(d, ah, bh, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks, ar += 2, br += 2, al += 2, bl += 2) {
+              const uint64_t dah = DESC_HI | ar, dal = DESC_HI | al, dbh = DESC_HI | br, dbl = DESC_HI | bl;
+              tcp::mma_ss(d, dal, dbh, idesc, (ks > 0 || !clear) ? 1u : 0u);
+              tcp::mma_ss(d, dah, dbl, idesc, 1u);
+              tcp::mma_ss(d, dah, dbh, idesc, 1u);
             }
-            tcp::commit(smem_u32(&s_bars.empty[s]));      // the stage is free once these MMAs have read it
+            tcp::commit(smem_u32(&s_bars.rfree[r]));      // both stages are free once these MMAs have read them
+            tcp::commit(smem_u32(&s_bars.lo_free[l]));
+            TQP(1);
           }
         }
+      TQP_FLUSH(2, 2, 2);
       tcp::commit(smem_u32(&s_bars.done));                // all accumulators final
     }
   } else {
     // ===================================================== converters: lo images + constant ones rows
     const int ct = tid - 64;
+    TQP_DECL
     int u = 0;
     for (int j = 0; j < my_tiles; ++j)
       for (int i = 0; i < dw::NOPS; ++i) {
         const tq::DwSrc src = tq::dw_src(i);
         const int na = src.a_rows * 8, nb = src.b_rows * 8;  // 16-byte chunks
         for (int p = 0; p < tq::NPANEL; ++p, ++u) {
-          const int s = u % NS;
-          dwq_wait(smem_u32(&s_bars.full[s]), (uint32_t)(u / NS) & 1u, abort_flag);
-          unsigned char* st = base + s * tq::DW_STAGE_BYTES;
-          float4* a_raw = reinterpret_cast<float4*>(st);
-          float4* a_lo = reinterpret_cast<float4*>(st + O_ALO);
-          float4* b_raw = reinterpret_cast<float4*>(st + O_BRAW);
-          float4* b_lo = reinterpret_cast<float4*>(st + O_BLO);
+          const int r = u % NR, l = u % NL;
+          dwq_wait(smem_u32(&s_bars.full[r]), (uint32_t)(u / NR) & 1u, abort_flag);
+          TQP(0);
+          if (u >= NL) dwq_wait(smem_u32(&s_bars.lo_free[l]), (uint32_t)(u / NL - 1) & 1u, abort_flag);
+          TQP(1);
+          float4* a_raw = reinterpret_cast<float4*>(base + r * STAGE);
+          float4* b_raw = reinterpret_cast<float4*>(base + r * STAGE + tq::DW_A_BYTES);
+          float4* a_lo = reinterpret_cast<float4*>(lo_base + l * STAGE);
+          float4* b_lo = reinterpret_cast<float4*>(lo_base + l * STAGE + tq::DW_A_BYTES);
           for (int q = ct; q < na; q += DWQ_CONV) a_lo[q] = lo_of(a_raw[q]);
           for (int q = ct; q < nb; q += DWQ_CONV) b_lo[q] = lo_of(b_raw[q]);
           if (src.ones >= 0 && ct < 64) {                    // 8-row group [ones, ones + 8): row `ones` = 1, rest 0
@@ -166,9 +198,11 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
             a_lo[src.ones * 8 + ct] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           tcp::fence_proxy_async_smem();                     // generic writes -> tensor core reads
-          tcp::mbar_arrive(smem_u32(&s_bars.conv[s]));
+          tcp::mbar_arrive(smem_u32(&s_bars.lo_ready[l]));
+          TQP(2);
         }
       }
+    if (ct == 0) TQP_FLUSH(2, 4, 3);
   }
 
   // ===================================================== epilogue: accumulators -> this CTA's gradient partial

@@ -1,19 +1,21 @@
 // tcgen05 / TMEM kernels of the quadrotor CONCURRENT rollout (Net(15,10,9,40,conv), h = 10), second generation:
 //   tq_fwd_kernel : policy forward on the 5th-generation tensor cores (A operands and accumulators in TMEM, weight
-//                   images resident in shared memory, 3xTF32) -> sigmoid -> h dynamics steps + tracking loss by the
-//                   thread that owns the drone; every activation goes to the stash in UMMA operand-image format.
-//   tq_dx_kernel  : reverse sweep through dynamics / loss by the owning thread -> d loss / d logits -> dX chain on the
-//                   tensor cores against TRANSPOSED K-major weight images -> dZ of every layer to the dZ stash.
+//                   images resident in shared memory, 3xTF32) -> sigmoid; every activation goes to the stash in UMMA
+//                   operand-image format (tq_layout.cuh).
+//   tq_dyn_kernel : one thread per drone at full occupancy: h dynamics steps + tracking loss from the stashed actions,
+//                   then at once the reverse sweep through dynamics / loss -> d loss / d logits (dZ stash, set ZO).
+//   tq_dx_kernel  : dX chain on the tensor cores against TRANSPOSED K-major weight images -> dZ of every layer.
 // The weight gradient is tq_dw_kernels.cu (streaming GEMM over the drone axis on the two stashes).
 // Reference path: scripts/train_base.py:188-218 + scripts/train_drone.py:175-203 (forward), loss.backward() (adjoint).
 //
-// Roles (544 threads): warps 0-15 = four epilogue GROUPS of 128 threads (thread r of a group owns TMEM lane r = drone r
-// of the group's tile); warp 16 lane 0 loads the weight images (one bulk copy) and issues every tcgen05.mma.
-// Two TMEM slots of 256 columns = two tiles in the tensor chain at any time; group g works in slot g & 1, so each
-// slot is shared by two groups that alternate: while one group runs the thread-per-drone dynamics phase of its tile
-// (no TMEM needed), the other one runs the GEMM chain of the next tile in the same slot.  Hand-off by mbarriers:
-// a_ready[s] (128 arrivals: the A operand of the next op is in TMEM), d_ready[s] (tcgen05.commit), slot_free[s] (128
-// arrivals: the group has read the last accumulator of its tile, the slot belongs to the other group now).
+// Chain kernels (544 threads): two TMEM slots of 256 columns = two 128-drone tiles in the tensor chain; slot s is
+// served by warps 8s .. 8s+7: warp w owns TMEM lanes 32 (w & 3) .. +31 (= drones of the tile) and the column half
+// (w >> 2) & 1 of every epilogue, so both threads of a drone split each 64-column epilogue 32 / 32 (and 40-column
+// pieces 24 / 16).  Warp 16 lane 0 loads the weight images (bulk copies) and issues every tcgen05.mma.  Hand-off by
+// mbarriers: a_ready[s] (256 arrivals: the A operand of the next op is in TMEM), d_ready[s] (tcgen05.commit).
+// Why the dynamics are NOT in these kernels: measured (profiles/r2): with the horizon loop on the epilogue threads a
+// quarter of all warp samples sat at the final barrier and only two tiles per SM were ever in the chain; a plain
+// thread-per-drone kernel runs the same loop at full occupancy in a fraction of the time.
 #include "tq_layout.cuh"
 #include "tc_prims.cuh"
 #include "rollout_args.h"
@@ -21,6 +23,14 @@
 #include "tile_engine.cuh"
 #endif
 #include "kernels.h"
+
+#ifdef APG_PROFILE
+__device__ long long g_tq_prof_chain[3][148][TQ_NPROF];
+#define TQ_PROF_ARRAY g_tq_prof_chain
+extern "C" __attribute__((visibility("default"))) int apg_debug_profile_tq_chain(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, g_tq_prof_chain, sizeof(long long) * 3 * 148 * TQ_NPROF);
+}
+#endif
 
 namespace apg {
 
@@ -33,13 +43,14 @@ constexpr int TQ_THREADS = (TQ_EPI_WARPS + 1) * 32;          // 544
 constexpr int TQ_FWD_SMEM = 1024 + BLOB_BYTES;
 constexpr int TQ_DX_SMEM = 1024 + tq::TBLOB_BYTES;
 constexpr int BULK_CHUNK = 32768;
+constexpr int TQ_DYN_THREADS = 64;                            // one thread per drone, half a tile per block
+constexpr int TQ_DYN_SMEM = H * 12 * TQ_DYN_THREADS * 4;      // states of the horizon, [k*12 + q][thread]
 static_assert(TQ_FWD_SMEM <= 232448 - 1024, "forward weight images do not fit in shared memory");
 static_assert(BLOB_BYTES % 16 == 0 && tq::TBLOB_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 struct TqBars {
   unsigned long long a_ready[2];
   unsigned long long d_ready[2];
-  unsigned long long slot_free[2];
   unsigned long long w_ready;
 };
 
@@ -51,13 +62,7 @@ __device__ __forceinline__ void tq_wait(uint32_t bar, uint32_t parity, volatile 
     if (tcp::mbar_try_wait(bar, parity)) return;
     if ((spin & 63) == 63) {
       if (*abort_flag) return;
-      if (tcp::clock_now() - t0 > 2000000000LL) {
-#ifdef APG_TC_SIM
-        if (getenv("APG_SIM_FAST_TIMEOUT")) fprintf(stderr, "tq_wait timeout: thread %u bar %x parity %u\n", threadIdx.x, bar, parity);
-#endif
-        *abort_flag = 1;
-        return;
-      }
+      if (tcp::clock_now() - t0 > 2000000000LL) { *abort_flag = 1; return; }
     }
   }
 }
@@ -110,28 +115,67 @@ __device__ __forceinline__ void a_operand_ready(uint32_t bar) {
   tcp::fence_before_thread_sync();
   tcp::mbar_arrive(bar);
 }
-// values x[0, 8*n8) -> (hi, lo) A-operand columns
-template <int N8>
+// L2 prefetch of the 128-byte lines [first, first + nlines) of a contiguous region, spread over the lanes of a warp
+__device__ __forceinline__ void prefetch_lines(const unsigned char* p, int nlines, int lane) {
+  for (int i = lane; i < nlines; i += 32) tcp::prefetch_l2(p + (size_t)i * 128);
+}
+// N consecutive TMEM columns (N in {8, 16, 24, 32}) <-> registers
+template <int N>
+__device__ __forceinline__ void tm_ld(uint32_t addr, uint32_t* v) {
+  static_assert(N == 8 || N == 16 || N == 24 || N == 32, "column count");
+  if (N == 8) tcp::tmem_ld8(addr, v);
+  if (N == 16) tcp::tmem_ld16(addr, v);
+  if (N == 24) { tcp::tmem_ld16(addr, v); tcp::tmem_ld8(addr + 16, v + 16); }
+  if (N == 32) tcp::tmem_ld32(addr, v);
+}
+template <int N>
+__device__ __forceinline__ void tm_st(uint32_t addr, const uint32_t* v) {
+  if (N == 8) tcp::tmem_st8(addr, v);
+  if (N == 16) tcp::tmem_st16(addr, v);
+  if (N == 24) { tcp::tmem_st16(addr, v); tcp::tmem_st8(addr + 16, v + 16); }
+  if (N == 32) tcp::tmem_st32(addr, v);
+}
+// values x[0, N) -> (hi, lo) A-operand columns [c0, c0 + N)
+template <int N>
 __device__ __forceinline__ void a_store(uint32_t ahi, uint32_t alo, const float* x) {
+  uint32_t h[N], l[N];
 #pragma unroll
-  for (int c0 = 0; c0 < N8 * 8; c0 += 8) {
-    uint32_t h[8], l[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) split_bits(x[c0 + q], &h[q], &l[q]);
-    tcp::tmem_st8(ahi + c0, h);
-    tcp::tmem_st8(alo + c0, l);
+  for (int q = 0; q < N; ++q) split_bits(x[q], &h[q], &l[q]);
+  tm_st<N>(ahi, h);
+  tm_st<N>(alo, l);
+}
+
+// One MMA series as the issuing thread wants it: descriptors of k-step 0 already encoded (the weight images are
+// resident, so they never change), k-step ks adds 16 to the low words (256 bytes >> 4).  Built once per CTA into
+// shared memory: measured (profiles/r2): building descriptors inside the issue loop made the single issuing thread
+// the bottleneck of all three kernels.
+struct OpRec { uint32_t bh_lo, bl_lo, desc_hi, idesc, d_col, ksteps, acc0, pad; };
+__device__ __forceinline__ OpRec make_oprec(uint32_t whi, uint32_t wlo, int K_img, int K, int N, int d_col, int acc0) {
+  OpRec r;
+  const uint64_t dh = kmajor_desc(whi, 0, K_img), dl = kmajor_desc(wlo, 0, K_img);
+  r.bh_lo = (uint32_t)dh; r.bl_lo = (uint32_t)dl; r.desc_hi = (uint32_t)(dh >> 32);
+  r.idesc = idesc_tf32(TMT, N); r.d_col = (uint32_t)d_col; r.ksteps = (uint32_t)(K / 8); r.acc0 = (uint32_t)acc0; r.pad = 0;
+  return r;
+}
+__device__ __forceinline__ void issue_series(const OpRec& op, uint32_t slot, uint32_t ahi, uint32_t alo) {
+  const uint32_t d = slot + op.d_col;
+  uint32_t bh = op.bh_lo, bl = op.bl_lo;
+  for (uint32_t ks = 0; ks < op.ksteps; ++ks, bh += 16, bl += 16) {
+    const uint64_t dbh = ((uint64_t)op.desc_hi << 32) | bh, dbl = ((uint64_t)op.desc_hi << 32) | bl;
+    tcp::mma_ts(d, alo + ks * 8, dbh, op.idesc, (ks > 0 || op.acc0) ? 1u : 0u);
+    tcp::mma_ts(d, ahi + ks * 8, dbl, op.idesc, 1u);
+    tcp::mma_ts(d, ahi + ks * 8, dbh, op.idesc, 1u);
   }
 }
 
-// common prologue: barriers, TMEM, one bulk copy of the weight images; returns the TMEM base
+// common prologue: barriers, TMEM, bulk copies of the weight images; returns the TMEM base
 __device__ __forceinline__ uint32_t tq_setup(TqBars& bars, uint32_t* s_tmem, int* s_abort, unsigned char* base,
                                              const unsigned char* blob, int blob_bytes) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      tcp::mbar_init(smem_u32(&bars.a_ready[s]), 128);
+      tcp::mbar_init(smem_u32(&bars.a_ready[s]), 256);
       tcp::mbar_init(smem_u32(&bars.d_ready[s]), 1);
-      tcp::mbar_init(smem_u32(&bars.slot_free[s]), 128);
     }
     tcp::mbar_init(smem_u32(&bars.w_ready), 1);
     *s_abort = 0;
@@ -168,16 +212,18 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   __shared__ __align__(8) TqBars s_bars;
   __shared__ uint32_t s_tmem;
   __shared__ int s_abort;
-  __shared__ float s_red[TQ_EPI_WARPS];
-  using Sys = Quad<float>;
-  constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
+  __shared__ OpRec s_ops[NOPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < NOPS) {
+    const Op op = op_of(tid);
+    const uint32_t whi = smem_u32(base + op.img_off);
+    s_ops[tid] = make_oprec(whi, whi + img_bytes(op.rows, op.K), op.K, op.K, op.N, op.d_col, op.clear ? 0 : 1);
+  }
   const uint32_t tmem = tq_setup(s_bars, &s_tmem, &s_abort, base, blob, BLOB_BYTES);
   const int n = g.N;
   const int ntiles = (n + TMT - 1) / TMT;
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   volatile int* abort_flag = &s_abort;
-  float my_loss = 0.f;
   tq_wait(smem_u32(&s_bars.w_ready), 0, abort_flag);          // weight images + biases have landed
 
   if (warp == TQ_EPI_WARPS) {
@@ -195,17 +241,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           if (!tcp::mbar_test_wait(smem_u32(&s_bars.a_ready[s]), par[s])) continue;
           par[s] ^= 1;
           tcp::fence_after_thread_sync();
-          const Op op = op_of(op_i[s]);
-          const uint32_t idesc = idesc_tf32(TMT, op.N);
-          const uint32_t whi = smem_u32(base + op.img_off), wlo = whi + img_bytes(op.rows, op.K);
           const uint32_t slot = tmem + s * SLOT_COLS;
-          const uint32_t d = slot + op.d_col, ahi = slot + C_AHI, alo = slot + C_ALO;
-          for (int ks = 0; ks < op.K / 8; ++ks) {
-            const uint64_t bh = kmajor_desc(whi, ks, op.K), bl = kmajor_desc(wlo, ks, op.K);
-            tcp::mma_ts(d, alo + ks * 8, bh, idesc, (ks > 0 || !op.clear) ? 1u : 0u);
-            tcp::mma_ts(d, ahi + ks * 8, bl, idesc, 1u);
-            tcp::mma_ts(d, ahi + ks * 8, bh, idesc, 1u);
-          }
+          issue_series(s_ops[op_i[s]], slot, slot + C_AHI, slot + C_ALO);
           tcp::commit(smem_u32(&s_bars.d_ready[s]));
           if (++op_i[s] == NOPS) { op_i[s] = 0; tile_j[s] += 2; }
           --remaining;
@@ -220,178 +257,271 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       }
     }
   } else {
-    const int grp = warp >> 2, s = grp & 1;
+    const int s = warp >> 3, hf = (warp >> 2) & 1;
     const int row = (warp & 3) * 32 + lane;                  // TMEM lane = drone of the tile
     const uint32_t slot = tmem + s * SLOT_COLS + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t d_main = slot + C_DMAIN, d_conv = slot + C_DCONV, ahi = slot + C_AHI, alo = slot + C_ALO;
-    const uint32_t bar_a = smem_u32(&s_bars.a_ready[s]), bar_d = smem_u32(&s_bars.d_ready[s]),
-                   bar_f = smem_u32(&s_bars.slot_free[s]);
-    for (int j = grp; j < my_tiles; j += 4) {
+    const uint32_t bar_a = smem_u32(&s_bars.a_ready[s]), bar_d = smem_u32(&s_bars.d_ready[s]);
+    uint32_t dcnt = 0;                                        // commits of this slot seen so far
+    TQP_DECL
+    auto wait_d = [&]() {
+      TQP(1);
+      tq_wait(bar_d, dcnt & 1u, abort_flag);
+      TQP(0);
+      ++dcnt;
+      tcp::fence_after_thread_sync();
+    };
+    for (int j = s; j < my_tiles; j += 2) {
       const int tile = (int)blockIdx.x + j * (int)gridDim.x;
       const size_t drone = (size_t)tile * TMT + row;
       const bool live = drone < (size_t)n;
-      const int t = j >> 1;                                   // this tile is the t-th one of its slot
-      uint32_t dcnt = (uint32_t)t * NOPS;                     // commits of the slot before this tile
       unsigned char* tb = fstash + (size_t)tile * tq::F_TILE_BYTES;
-      auto wait_d = [&]() {
-        tq_wait(bar_d, dcnt & 1u, abort_flag);
-        ++dcnt;
-        tcp::fence_after_thread_sync();
-      };
-      // D_main (64 columns) -> tanh(x + b) -> A operand (hi, lo) + stash rows [row0, row0 + 64) of set `sp`
-      auto dense_epilogue = [&](const float* b, const SetPtr& sp, int row0) {
+      if (j + 2 < my_tiles && hf == 0) {                       // next tile of this slot: its inputs into L2 now
+        const size_t d0n = ((size_t)tile + 2 * (size_t)gridDim.x) * TMT + (size_t)(warp & 3) * 32;
+        if (d0n + 32 <= (size_t)n) {
+          prefetch_lines(reinterpret_cast<const unsigned char*>(g.in_ref + d0n * REFW), 32 * REFW * 4 / 128, lane);
+          prefetch_lines(reinterpret_cast<const unsigned char*>(g.in_state + d0n * F0), 32 * F0 * 4 / 128, lane);
+        }
+      }
+      // D_main columns [32 hf, +32) -> tanh(x + b) -> A operand (hi, lo) + stash rows of set `sp`
+      auto dense_epilogue = [&](const float* b, const SetPtr& sp) {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t v[32], l[32];
-          tcp::tmem_ld32(d_main + hf * 32, v);
+        for (int c0 = 0; c0 < 32; c0 += 16) {                  // 16 columns at a time: register budget (96 / thread)
+          uint32_t v[16], l[16];
+          tcp::tmem_ld16(d_main + hf * 32 + c0, v);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const float yv = tq_tanh(__uint_as_float(v[q]) + b[hf * 32 + q]);
-            set_store(sp, row0 + hf * 32 + q, yv);
+          for (int q = 0; q < 16; ++q) {
+            const float yv = tq_tanh(__uint_as_float(v[q]) + b[hf * 32 + c0 + q]);
+            set_store(sp, hf * 32 + c0 + q, yv);
             split_bits(yv, &v[q], &l[q]);
           }
-          tcp::tmem_st32(ahi + hf * 32, v);
-          tcp::tmem_st32(alo + hf * 32, l);
+          tcp::tmem_st16(ahi + hf * 32 + c0, v);
+          tcp::tmem_st16(alo + hf * 32 + c0, l);
         }
         a_operand_ready(bar_a);
       };
-      // ---- op 0 operand: in_state (15) + 1 (the ones row of the states_in weight gradient; its image column is 0)
-      float x0[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) x0[k] = (live && k < F0) ? g.in_state[drone * F0 + k] : 0.f;
-      x0[F0] = live ? 1.f : 0.f;
-      // the slot's previous tile (the other group's) has left TMEM.  Parity waits alias with period 2, so a thread
-      // must first see the hand-over of its OWN previous tile complete (all 128 arrivals, not just its own) before it
-      // may ask for the next one.
-      if (t >= 2) tq_wait(bar_f, (uint32_t)(t - 2) & 1u, abort_flag);
-      if (t >= 2) tq_wait(bar_f, (uint32_t)(t - 2) & 1u, abort_flag);     // see tq_fwd_kernel
-      if (t >= 1) {
-        tq_wait(bar_f, (uint32_t)(t - 1) & 1u, abort_flag);
-        tcp::fence_after_thread_sync();
-      }
-      a_store<2>(ahi, alo, x0);
-      a_operand_ready(bar_a);
+      // ---- op 0 operand: in_state (15) + 1 (the ones row of the states_in weight gradient; its image column is 0);
+      //      this thread's eight columns [8 hf, +8)
       {
+        float x0[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int kk = hf * 8 + k;
+          x0[k] = (live && kk < F0) ? g.in_state[drone * F0 + kk] : 0.f;
+        }
+        if (hf) x0[7] = live ? 1.f : 0.f;
+        a_store<8>(ahi + hf * 8, alo + hf * 8, x0);
+        a_operand_ready(bar_a);
         const SetPtr sp = set_ptr(tb, tq::O_XS, tq::R_XS, row);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) set_store(sp, k, x0[k]);
+        for (int k = 0; k < 8; ++k) set_store(sp, hf * 8 + k, x0[k]);
       }
       const SetPtr sp_x1 = set_ptr(tb, tq::O_X1, tq::R_X1, row);
       wait_d();                                               // op 0: states_in
-      dense_epilogue(s_bias + B_S, sp_x1, 0);                 // s -> X1 rows [0, 64), operand of op 1
+      dense_epilogue(s_bias + B_S, sp_x1);                    // s -> X1 rows [0, 64), operand of op 1
       const float* rr = g.in_ref + drone * REFW;
 #pragma unroll 1
       for (int gq = 0; gq < 4; ++gq) {
-        float x[40];
+        // window of position pair gq: in_ref rows 2gq .. 2gq+3 (36 values) | 1 (ones row of the conv weight
+        // gradient; its image column is 0) | 0 0 0; this thread's columns [0,24) or [24,40)
+        const SetPtr sp_w = set_ptr(tb, tq::O_WIN + tq::R_WIN * gq, tq::R_WIN, row);
+        if (hf == 0) {
+          float x[24];
 #pragma unroll
-        for (int k = 0; k < 36; k += 2) {
-          const float2 tt = live ? *(const float2*)(rr + 18 * gq + k) : make_float2(0.f, 0.f);
-          x[k] = tt.x;
-          x[k + 1] = tt.y;
-        }
-        x[36] = live ? 1.f : 0.f;                             // ones row of the conv weight gradient (image column 0)
-        x[37] = x[38] = x[39] = 0.f;
-        wait_d();        // op 1 (gq = 0) or the fc1 piece of the previous pair: the A columns are free again
-        a_store<5>(ahi, alo, x);
-        a_operand_ready(bar_a);
-        {
-          const SetPtr sp = set_ptr(tb, tq::O_WIN + tq::R_WIN * gq, tq::R_WIN, row);
+          for (int k = 0; k < 24; k += 2) {
+            const float2 tt = live ? *(const float2*)(rr + 18 * gq + k) : make_float2(0.f, 0.f);
+            x[k] = tt.x;
+            x[k + 1] = tt.y;
+          }
+          wait_d();      // op 1 (gq = 0) or the fc1 piece of the previous pair: the A columns are free again
+          a_store<24>(ahi, alo, x);
+          a_operand_ready(bar_a);
 #pragma unroll
-          for (int k = 0; k < 40; ++k) set_store(sp, k, x[k]);
+          for (int k = 0; k < 24; ++k) set_store(sp_w, k, x[k]);
+        } else {
+          float x[16];
+#pragma unroll
+          for (int k = 0; k < 12; k += 2) {
+            const float2 tt = live ? *(const float2*)(rr + 18 * gq + 24 + k) : make_float2(0.f, 0.f);
+            x[k] = tt.x;
+            x[k + 1] = tt.y;
+          }
+          x[12] = live ? 1.f : 0.f;
+          x[13] = x[14] = x[15] = 0.f;
+          wait_d();
+          a_store<16>(ahi + 24, alo + 24, x);
+          a_operand_ready(bar_a);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) set_store(sp_w, 24 + k, x[k]);
         }
         wait_d();        // conv of this position pair
         {
           const float* b = s_bias + B_C;
-          uint32_t v[40], l[40];
-          tcp::tmem_ld32(d_conv, v);
-          tcp::tmem_ld8(d_conv + 32, v + 32);
+          // position-major x1 row of (pair gq, output q): 64 + 40 gq + q; the row phase only depends on q
+          const size_t xoff = (size_t)gq * (40 * 128);
+          if (hf == 0) {
+            uint32_t v[24], l[24];
+            tm_ld<24>(d_conv, v);
 #pragma unroll
-          for (int q = 0; q < 40; ++q) {
-            const float yv = fmaxf(__uint_as_float(v[q]) + b[q], 0.f);
-            // position-major x1 row of (pair gq, output q): 64 + 40 gq + q; the row phase only depends on q
-            *reinterpret_cast<float*>(sp_x1.p[q & 7] + (HID + q) * 128 + gq * (40 * 128)) = yv;
-            split_bits(yv, &v[q], &l[q]);
+            for (int q = 0; q < 24; ++q) {
+              const float yv = fmaxf(__uint_as_float(v[q]) + b[q], 0.f);
+              *reinterpret_cast<float*>(sp_x1.p[q & 7] + (HID + q) * 128 + xoff) = yv;
+              split_bits(yv, &v[q], &l[q]);
+            }
+            tm_st<24>(ahi, v);
+            tm_st<24>(alo, l);
+          } else {
+            uint32_t v[16], l[16];
+            tm_ld<16>(d_conv + 24, v);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float yv = fmaxf(__uint_as_float(v[q]) + b[24 + q], 0.f);
+              *reinterpret_cast<float*>(sp_x1.p[(24 + q) & 7] + (HID + 24 + q) * 128 + xoff) = yv;
+              split_bits(yv, &v[q], &l[q]);
+            }
+            tm_st<16>(ahi + 24, v);
+            tm_st<16>(alo + 24, l);
           }
-          tcp::tmem_st32(ahi, v);
-          tcp::tmem_st8(ahi + 32, v + 32);
-          tcp::tmem_st32(alo, l);
-          tcp::tmem_st8(alo + 32, l + 32);
           a_operand_ready(bar_a);
         }
       }
       wait_d();                                               // last fc1 piece
-      dense_epilogue(s_bias + B_1, set_ptr(tb, tq::O_H1, tq::R_H, row), 0);
+      dense_epilogue(s_bias + B_1, set_ptr(tb, tq::O_H1, tq::R_H, row));
       wait_d();                                               // fc2
-      dense_epilogue(s_bias + B_2, set_ptr(tb, tq::O_H2, tq::R_H, row), 0);
+      dense_epilogue(s_bias + B_2, set_ptr(tb, tq::O_H2, tq::R_H, row));
       wait_d();                                               // fc3
-      dense_epilogue(s_bias + B_3, set_ptr(tb, tq::O_H3, tq::R_H, row), 0);
+      dense_epilogue(s_bias + B_3, set_ptr(tb, tq::O_H3, tq::R_H, row));
       wait_d();                                               // fc_out
-      float act[MO];
       {
         const float* b = s_bias + B_O;
         const SetPtr sp = set_ptr(tb, tq::O_ACT, tq::R_ACT, row);
-        uint32_t v[40];
-        tcp::tmem_ld32(d_main, v);
-        tcp::tmem_ld8(d_main + 32, v + 32);
+        if (hf == 0) {
+          uint32_t v[24];
+          tm_ld<24>(d_main, v);
 #pragma unroll
-        for (int q = 0; q < MO; ++q) {
-          act[q] = tq_sigmoid(__uint_as_float(v[q]) + b[q]);                 // train_base.py:203
-          set_store(sp, q, act[q]);
+          for (int q = 0; q < 24; ++q) set_store(sp, q, tq_sigmoid(__uint_as_float(v[q]) + b[q]));   // train_base.py:203
+        } else {
+          uint32_t v[16];
+          tm_ld<16>(d_main + 24, v);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) set_store(sp, 24 + q, tq_sigmoid(__uint_as_float(v[q]) + b[24 + q]));
         }
       }
-      // every tcgen05.ld of this tile has completed: the slot belongs to the other group of this slot now
-      tcp::fence_before_thread_sync();
-      tcp::mbar_arrive(bar_f);
-      // ---- h dynamics steps + tracking loss of this drone (train_drone.py:175-203), states to the stash
-      if (live) {
-        const SetPtr sp = set_ptr(tb, tq::O_ST, tq::R_ST, row);
-        float sc[S], s0[S], sn[S], rf[R];
-        const float* cur_g = g.cur + drone * S;
-        const float* ref_g = g.ref + drone * g.ref_rows * R;
-#pragma unroll
-        for (int q = 0; q < S; ++q) s0[q] = sc[q] = cur_g[q];
-#pragma unroll
-        for (int k = 0; k < H; ++k) {
-          const float* a = act + k * A;
-#pragma unroll
-          for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
-          Sys::step(sc, a, g.dt, g.pc.v, sn);
-          my_loss += Sys::loss(sn, rf, a, s0, k, H);
-#pragma unroll
-          for (int q = 0; q < S; ++q) {
-            sc[q] = sn[q];
-            set_store(sp, k * S + q, sn[q]);
-          }
-          if (g.states_out) {
-#pragma unroll
-            for (int q = 0; q < S; ++q) g.states_out[(drone * H + k) * S + q] = sn[q];
-          }
-          if (g.actions_out) {
-#pragma unroll
-            for (int c = 0; c < A; ++c) g.actions_out[(drone * H + k) * A + c] = a[c];
-          }
-        }
-      }
+      // every tcgen05.ld of this tile has completed before the next tile's first A-operand arrival (same threads)
     }
+    TQP(1);
+    if (tid == 0) TQP_FLUSH(0, 0, 2);
   }
-  // ---- loss of this CTA: fixed-order sum over the epilogue threads
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
-  if (lane == 0 && warp < TQ_EPI_WARPS) s_red[warp] = my_loss;
   tcp::fence_before_thread_sync();
   __syncthreads();
-  if (tid == 0) {
-    float tsum = 0.f;
-#pragma unroll
-    for (int w = 0; w < TQ_EPI_WARPS; ++w) tsum += s_red[w];
-    // a protocol timeout poisons the loss on purpose: the caller must never take such a launch for a result
-    g.loss_partials[blockIdx.x] = s_abort ? __int_as_float(0x7fc00000) : tsum;
-  }
+  if (tid == 0 && s_abort && my_tiles > 0)                     // poison: the dynamics kernel turns it into a NaN loss
+    *reinterpret_cast<float*>(fstash + (size_t)blockIdx.x * tq::F_TILE_BYTES + tq::set_base(tq::O_ACT)) =
+        __int_as_float(0x7fc00000);
   if (warp == TQ_EPI_WARPS) tcp::tmem_dealloc512(tmem);
 }
 
 // =========================================================================================================
-// dX chain: d loss / d logits from the reverse sweep of the owning thread, then
+// Thread per drone: the h dynamics steps + tracking loss from the stashed actions (train_drone.py:175-203), then at
+// once the reverse sweep (hand-written adjoints, apg_math.cuh) -> d loss / d logits into set ZO of the dZ stash.
+// States of the horizon live in shared memory ([k*12 + q][thread], conflict free); nothing but the actions is read
+// from the stash and nothing but ZO is written.  Dead drones of a ragged tile write zeros.
+// =========================================================================================================
+__global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
+    tq_dyn_kernel(const RolloutArgs g, unsigned char* __restrict__ fstash, unsigned char* __restrict__ zstash) {
+  APG_TC_DYNAMIC_SMEM(smem_raw);
+  float* s_st = reinterpret_cast<float*>(smem_raw);           // [H*12][TQ_DYN_THREADS]
+  __shared__ float s_red[TQ_DYN_THREADS / 32];
+  using Sys = Quad<float>;
+  constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW, TD = TQ_DYN_THREADS;
+  const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
+  const int n = g.N;
+  const int nhalf = ((n + TMT - 1) / TMT) * (TMT / TD);       // half tiles (dead drones of a ragged tile included)
+  float my_loss = 0.f;
+  // the horizon loops are NOT unrolled (measured: the unrolled body thrashed the instruction cache, 6 of 10 issue
+  // slots lost to instruction fetch); actions / logit gradients go straight from / to the stash sets per step
+  for (int hb = blockIdx.x; hb < nhalf; hb += gridDim.x) {
+    const int tile = hb / (TMT / TD), row = (hb % (TMT / TD)) * TD + tx;
+    const uint32_t c4 = ((uint32_t)(row & 31) >> 2) << 4;     // this thread's 16-byte chunk, before the row XOR
+    const size_t drone = (size_t)tile * TMT + row;
+    const bool live = drone < (size_t)n;
+    const unsigned char* act_b = fstash + (size_t)tile * tq::F_TILE_BYTES + tq::set_base(tq::O_ACT) +
+                                 (size_t)(row >> 5) * (tq::R_ACT * 128) + (row & 3) * 4;
+    unsigned char* zo_b = zstash + (size_t)tile * tq::Z_TILE_BYTES + tq::set_base(tq::O_ZO) +
+                          (size_t)(row >> 5) * (MO * 128) + (row & 3) * 4;
+    auto elem = [&](int r) { return (uint32_t)r * 128u + (c4 ^ ((uint32_t)(r & 7) << 4)); };
+    if (live) {
+      float sc[S], s0[S], sn[S], rf[R], a[A];
+      const float* cur_g = g.cur + drone * S;
+      const float* ref_g = g.ref + drone * g.ref_rows * R;
+#pragma unroll
+      for (int q = 0; q < S; ++q) s0[q] = sc[q] = cur_g[q];
+#pragma unroll 1
+      for (int k = 0; k < H; ++k) {
+#pragma unroll
+        for (int c = 0; c < A; ++c) a[c] = *reinterpret_cast<const float*>(act_b + elem(k * A + c));
+#pragma unroll
+        for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
+        Sys::step(sc, a, g.dt, g.pc.v, sn);
+        my_loss += Sys::loss(sn, rf, a, s0, k, H);
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+          sc[q] = sn[q];
+          s_st[(k * S + q) * TD + tx] = sn[q];
+        }
+        if (g.states_out) {
+#pragma unroll
+          for (int q = 0; q < S; ++q) g.states_out[(drone * H + k) * S + q] = sn[q];
+        }
+        if (g.actions_out) {
+#pragma unroll
+          for (int c = 0; c < A; ++c) g.actions_out[(drone * H + k) * A + c] = a[c];
+        }
+      }
+      // ---- reverse sweep (dyn_phase.cuh dyn_adjoint_conc on this thread's registers / shared-memory column)
+      float sk[S], gq[S], gs[S], ga[A], ga2[A];
+#pragma unroll
+      for (int q = 0; q < S; ++q) gq[q] = 0.f;
+#pragma unroll 1
+      for (int k = H - 1; k >= 0; --k) {
+#pragma unroll
+        for (int c = 0; c < A; ++c) { a[c] = *reinterpret_cast<const float*>(act_b + elem(k * A + c)); ga[c] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
+        if (k > 0) {
+#pragma unroll
+          for (int q = 0; q < S; ++q) sk[q] = s_st[((k - 1) * S + q) * TD + tx];
+        } else {
+#pragma unroll
+          for (int q = 0; q < S; ++q) sk[q] = s0[q];
+        }
+        Sys::loss_grad(sn, rf, a, s0, k, H, gq, ga);
+        Sys::step_adj(sk, a, g.dt, g.pc.v, gq, gs, ga2);
+#pragma unroll
+        for (int c = 0; c < A; ++c)
+          *reinterpret_cast<float*>(zo_b + elem(k * A + c)) = (ga[c] + ga2[c]) * a[c] * (1.f - a[c]);      // sigmoid'
+#pragma unroll
+        for (int q = 0; q < S; ++q) { gq[q] = gs[q]; sn[q] = sk[q]; }
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < MO; ++q) *reinterpret_cast<float*>(zo_b + elem(q)) = 0.f;
+    }
+  }
+  // ---- loss of this block: fixed-order sum
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+  if (lane == 0) s_red[warp] = my_loss;
+  __syncthreads();
+  if (tx == 0) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < TQ_DYN_THREADS / 32; ++w) tsum += s_red[w];
+    g.loss_partials[blockIdx.x] = tsum;
+  }
+}
+
+// =========================================================================================================
+// dX chain: A operand of the first op = d loss / d logits (set ZO, written by tq_dyn_kernel), then
 //   dZ3 = (dZo Wo) (.) (1 - h3^2), dZ2, dZ1 likewise, ds = (dZ1 W1[:, :64]) (.) (1 - s^2), dconv = (dZ1 W1[:, 64:]) (.) relu'
 // with the B operands = transposed K-major weight images (tq_layout.cuh T_*).  Five hand-offs per tile; the first
 // layer's 224 columns come out of two of them (accumulator columns [0,128) of the slot).
@@ -404,9 +534,14 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   __shared__ __align__(8) TqBars s_bars;
   __shared__ uint32_t s_tmem;
   __shared__ int s_abort;
-  using Sys = Quad<float>;
-  constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
+  __shared__ OpRec s_ops[tq::NXS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < tq::NXS) {
+    const tq::XOp op = tq::xop_of(tid);
+    const tq::TImg im = tq::timage_of(op.img);
+    const uint32_t whi = smem_u32(base + im.off) + (uint32_t)(op.row0 >> 3) * (uint32_t)((im.K >> 2) * 128);
+    s_ops[tid] = make_oprec(whi, whi + img_bytes(im.rows, im.K), im.K, op.K, op.N, tq::XC_D + op.d_col, 0);
+  }
   const uint32_t tmem = tq_setup(s_bars, &s_tmem, &s_abort, base, tblob, tq::TBLOB_BYTES);
   const int n = g.N;
   const int ntiles = (n + TMT - 1) / TMT;
@@ -429,21 +564,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           par[s] ^= 1;
           tcp::fence_after_thread_sync();
           const uint32_t slot = tmem + s * tq::SLOT_COLS;
-          const uint32_t ahi = slot + tq::XC_AHI, alo = slot + tq::XC_ALO;
-          for (int i = tq::xh_first(h_i[s]); i < tq::xh_first(h_i[s] + 1); ++i) {
-            const tq::XOp op = tq::xop_of(i);
-            const tq::TImg im = tq::timage_of(op.img);
-            const uint32_t whi = smem_u32(base + im.off) + (uint32_t)(op.row0 >> 3) * (uint32_t)((im.K >> 2) * 128);
-            const uint32_t wlo = whi + img_bytes(im.rows, im.K);
-            const uint32_t idesc = idesc_tf32(TMT, op.N);
-            const uint32_t d = slot + tq::XC_D + op.d_col;
-            for (int ks = 0; ks < op.K / 8; ++ks) {
-              const uint64_t bh = kmajor_desc(whi, ks, im.K), bl = kmajor_desc(wlo, ks, im.K);
-              tcp::mma_ts(d, alo + ks * 8, bh, idesc, ks > 0 ? 1u : 0u);
-              tcp::mma_ts(d, ahi + ks * 8, bl, idesc, 1u);
-              tcp::mma_ts(d, ahi + ks * 8, bh, idesc, 1u);
-            }
-          }
+          for (int i = tq::xh_first(h_i[s]); i < tq::xh_first(h_i[s] + 1); ++i)
+            issue_series(s_ops[i], slot, slot + tq::XC_AHI, slot + tq::XC_ALO);
           tcp::commit(smem_u32(&s_bars.d_ready[s]));
           if (++h_i[s] == tq::NXH) { h_i[s] = 0; tile_j[s] += 2; }
           --remaining;
@@ -458,94 +580,71 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       }
     }
   } else {
-    const int grp = warp >> 2, s = grp & 1;
+    const int s = warp >> 3, hf = (warp >> 2) & 1;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t slot = tmem + s * tq::SLOT_COLS + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t d0 = slot + tq::XC_D, ahi = slot + tq::XC_AHI, alo = slot + tq::XC_ALO;
-    const uint32_t bar_a = smem_u32(&s_bars.a_ready[s]), bar_d = smem_u32(&s_bars.d_ready[s]),
-                   bar_f = smem_u32(&s_bars.slot_free[s]);
-    for (int j = grp; j < my_tiles; j += 4) {
-      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-      const size_t drone = (size_t)tile * TMT + row;
-      const bool live = drone < (size_t)n;
-      const int t = j >> 1;
-      uint32_t dcnt = (uint32_t)t * tq::NXH;
+    const uint32_t bar_a = smem_u32(&s_bars.a_ready[s]), bar_d = smem_u32(&s_bars.d_ready[s]);
+    uint32_t dcnt = 0;
+    TQP_DECL
+    auto wait_d = [&]() {
+      TQP(1);
+      tq_wait(bar_d, dcnt & 1u, abort_flag);
+      TQP(0);
+      ++dcnt;
+      tcp::fence_after_thread_sync();
+    };
+    for (int j = s; j < my_tiles; j += 2) {
+      // this CTA's tiles in REVERSE order of the forward kernel: what it wrote last is still in L2
+      const int tile = (int)blockIdx.x + (my_tiles - 1 - j) * (int)gridDim.x;
       unsigned char* tb = fstash + (size_t)tile * tq::F_TILE_BYTES;
       unsigned char* zb = zstash + (size_t)tile * tq::Z_TILE_BYTES;
-      auto wait_d = [&]() {
-        tq_wait(bar_d, dcnt & 1u, abort_flag);
-        ++dcnt;
-        tcp::fence_after_thread_sync();
-      };
-      // ---- reverse dynamics sweep of this drone (dyn_phase.cuh dyn_adjoint_conc on the stash sets): dlog[40]
-      float dlog[MO];
-#pragma unroll
-      for (int q = 0; q < MO; ++q) dlog[q] = 0.f;
-      if (live) {
-        const SetPtr sp_st = set_ptr(tb, tq::O_ST, tq::R_ST, row);
-        const SetPtr sp_act = set_ptr(tb, tq::O_ACT, tq::R_ACT, row);
-        float s0[S], sk[S], sn[S], a[A], rf[R], gq[S], gs[S], ga[A], ga2[A];
-        const float* cur_g = g.cur + drone * S;
-        const float* ref_g = g.ref + drone * g.ref_rows * R;
-#pragma unroll
-        for (int q = 0; q < S; ++q) { s0[q] = cur_g[q]; gq[q] = 0.f; }
-#pragma unroll
-        for (int q = 0; q < S; ++q) sn[q] = set_load(sp_st, (H - 1) * S + q);
-#pragma unroll
-        for (int k = H - 1; k >= 0; --k) {
-#pragma unroll
-          for (int c = 0; c < A; ++c) { a[c] = set_load(sp_act, k * A + c); ga[c] = 0.f; }
-#pragma unroll
-          for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
-          if (k > 0) {
-#pragma unroll
-            for (int q = 0; q < S; ++q) sk[q] = set_load(sp_st, (k - 1) * S + q);
-          } else {
-#pragma unroll
-            for (int q = 0; q < S; ++q) sk[q] = s0[q];
-          }
-          Sys::loss_grad(sn, rf, a, s0, k, H, gq, ga);
-          Sys::step_adj(sk, a, g.dt, g.pc.v, gq, gs, ga2);
-#pragma unroll
-          for (int c = 0; c < A; ++c) dlog[k * A + c] = (ga[c] + ga2[c]) * a[c] * (1.f - a[c]);      // sigmoid'
-#pragma unroll
-          for (int q = 0; q < S; ++q) { gq[q] = gs[q]; sn[q] = sk[q]; }
-        }
+      {
+        // pull everything this warp will read of the tile into L2 now (its panel = rows x 128 B, one line per row):
+        // the dependent loads further down then cost an L2 hit instead of an HBM round trip
+        const int pnl = warp & 3;
+        prefetch_lines(tb + tq::set_base(tq::O_H3) + (size_t)pnl * (tq::R_H * 128) + hf * 32 * 128, 32, lane);
+        prefetch_lines(tb + tq::set_base(tq::O_H2) + (size_t)pnl * (tq::R_H * 128) + hf * 32 * 128, 32, lane);
+        prefetch_lines(tb + tq::set_base(tq::O_H1) + (size_t)pnl * (tq::R_H * 128) + hf * 32 * 128, 32, lane);
+        prefetch_lines(tb + tq::set_base(tq::O_X1) + (size_t)pnl * (tq::R_X1 * 128) + hf * 112 * 128, 112, lane);
       }
-      if (t >= 2) tq_wait(bar_f, (uint32_t)(t - 2) & 1u, abort_flag);     // see tq_fwd_kernel
-      if (t >= 1) {
-        tq_wait(bar_f, (uint32_t)(t - 1) & 1u, abort_flag);
-        tcp::fence_after_thread_sync();
-      }
-      a_store<5>(ahi, alo, dlog);
-      a_operand_ready(bar_a);
+      // ---- op 0 operand: d loss / d logits of this drone (set ZO), this thread's columns [0,24) or [24,40)
       {
         const SetPtr sp = set_ptr(zb, tq::O_ZO, MO, row);
+        if (hf == 0) {
+          float x[24];
 #pragma unroll
-        for (int q = 0; q < MO; ++q) set_store(sp, q, dlog[q]);
+          for (int q = 0; q < 24; ++q) x[q] = set_load(sp, q);
+          a_store<24>(ahi, alo, x);
+        } else {
+          float x[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) x[q] = set_load(sp, 24 + q);
+          a_store<16>(ahi + 24, alo + 24, x);
+        }
+        a_operand_ready(bar_a);
       }
-      // ---- dZ_l = (dZ_{l+1} W_{l+1}) (.) (1 - X_l^2) for h3, h2, h1: D -> A operand + dZ stash
+      // ---- dZ_l = (dZ_{l+1} W_{l+1}) (.) (1 - X_l^2) for h3, h2, h1: D -> A operand + dZ stash; columns [32 hf, +32)
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
         const SetPtr sp_y = set_ptr(tb, l == 0 ? tq::O_H3 : (l == 1 ? tq::O_H2 : tq::O_H1), tq::R_H, row);
         const SetPtr sp_z = set_ptr(zb, l == 0 ? tq::O_Z3 : (l == 1 ? tq::O_Z2 : tq::O_Z1), HID, row);
-        float yv[64];                                          // issued before the wait: hides the stash latency
+        float yv[32];                                          // issued before the wait: hides the stash latency
 #pragma unroll
-        for (int q = 0; q < 64; ++q) yv[q] = set_load(sp_y, q);
+        for (int q = 0; q < 32; ++q) yv[q] = set_load(sp_y, hf * 32 + q);
         wait_d();
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int c0 = 0; c0 < 32; c0 += 16) {
           uint32_t v[16], lo[16];
-          tcp::tmem_ld16(d0 + c0, v);
+          tcp::tmem_ld16(d0 + hf * 32 + c0, v);
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const float yy = yv[c0 + q];
-            const float z = __uint_as_float(v[q]) * (1.f - yy * yy);
-            set_store(sp_z, c0 + q, z);
+            const float z = __uint_as_float(v[q]) * (1.f - yv[c0 + q] * yv[c0 + q]);
+            set_store(sp_z, hf * 32 + c0 + q, z);
             split_bits(z, &v[q], &lo[q]);
           }
-          tcp::tmem_st16(ahi + c0, v);
-          tcp::tmem_st16(alo + c0, lo);
+          tcp::tmem_st16(ahi + hf * 32 + c0, v);
+          tcp::tmem_st16(alo + hf * 32 + c0, lo);
         }
         a_operand_ready(bar_a);
       }
@@ -553,57 +652,61 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       //      pairs 1, 2 [0,80) + pair 3 [80,120)
       const SetPtr sp_x1 = set_ptr(tb, tq::O_X1, tq::R_X1, row);
       const SetPtr sp_zx = set_ptr(zb, tq::O_ZX, K1, row);
-      {
-        float yv[64];
+      // relu' of one position pair: this thread's columns of D[dc, dc + 40), x1 / zx rows 64 + 40 gp + q (the row
+      // phase only depends on q)
+      auto pair_epilogue = [&](int gp, uint32_t dc) {
+        const size_t xoff = (size_t)gp * (40 * 128);
+        if (hf == 0) {
+          float yv[24];
 #pragma unroll
-        for (int q = 0; q < 64; ++q) yv[q] = set_load(sp_x1, q);
-        wait_d();
+          for (int q = 0; q < 24; ++q) yv[q] = *reinterpret_cast<const float*>(sp_x1.p[q & 7] + (HID + q) * 128 + xoff);
+          uint32_t v[24];
+          tm_ld<24>(dc, v);
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t v[16];
-          tcp::tmem_ld16(d0 + c0, v);
+          for (int q = 0; q < 24; ++q)
+            *reinterpret_cast<float*>(sp_zx.p[q & 7] + (HID + q) * 128 + xoff) = yv[q] > 0.f ? __uint_as_float(v[q]) : 0.f;
+        } else {
+          float yv[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q)
-            set_store(sp_zx, c0 + q, __uint_as_float(v[q]) * (1.f - yv[c0 + q] * yv[c0 + q]));
-        }
-      }
-      {
-        uint32_t v[40];
-        tcp::tmem_ld32(d0 + 64, v);
-        tcp::tmem_ld8(d0 + 96, v + 32);
+            yv[q] = *reinterpret_cast<const float*>(sp_x1.p[(24 + q) & 7] + (HID + 24 + q) * 128 + xoff);
+          uint32_t v[16];
+          tm_ld<16>(dc + 24, v);
 #pragma unroll
-        for (int q = 0; q < 40; ++q) {
-          const float yy = set_load(sp_x1, HID + q);
-          set_store(sp_zx, HID + q, yy > 0.f ? __uint_as_float(v[q]) : 0.f);             // relu'
+          for (int q = 0; q < 16; ++q)
+            *reinterpret_cast<float*>(sp_zx.p[(24 + q) & 7] + (HID + 24 + q) * 128 + xoff) =
+                yv[q] > 0.f ? __uint_as_float(v[q]) : 0.f;
         }
+      };
+      {
+        float yv[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) yv[q] = set_load(sp_x1, hf * 32 + q);
+        wait_d();
+        uint32_t v[32];
+        tcp::tmem_ld32(d0 + hf * 32, v);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) set_store(sp_zx, hf * 32 + q, __uint_as_float(v[q]) * (1.f - yv[q] * yv[q]));
       }
+      pair_epilogue(0, d0 + 64);
       tcp::fence_before_thread_sync();
       tcp::mbar_arrive(bar_a);                                 // D has been read: go on with the other three pairs
       wait_d();
-#pragma unroll 1
-      for (int gp = 1; gp < 4; ++gp) {
-        uint32_t v[40];
-        const uint32_t dc = d0 + (gp - 1) * 40;
-        tcp::tmem_ld32(dc, v);
-        tcp::tmem_ld8(dc + 32, v + 32);
-#pragma unroll
-        for (int q = 0; q < 40; ++q) {
-          // x1 / zx row 64 + 40 gp + q: the row phase only depends on q
-          const float yy = *reinterpret_cast<const float*>(sp_x1.p[q & 7] + (HID + q) * 128 + gp * (40 * 128));
-          *reinterpret_cast<float*>(sp_zx.p[q & 7] + (HID + q) * 128 + gp * (40 * 128)) =
-              yy > 0.f ? __uint_as_float(v[q]) : 0.f;
-        }
-      }
-      tcp::fence_before_thread_sync();
-      tcp::mbar_arrive(bar_f);                                 // the slot belongs to the other group now
+      pair_epilogue(1, d0);
+      pair_epilogue(2, d0 + 40);
+      pair_epilogue(3, d0 + 80);
+      tcp::fence_before_thread_sync();                         // orders these loads before the next tile's arrivals
     }
+    TQP(1);
+    if (tid == 0) TQP_FLUSH(1, 0, 2);
   }
   tcp::fence_before_thread_sync();
   __syncthreads();
   // the stash / weight images must come from the forward of THIS path (workspace stamp, capi.cu)
   if (tid == 0 && stamp && (int)stamp[0] != want_stamp) s_abort = 1;
   if (tid == 0 && s_abort && my_tiles > 0)                     // poison the gradient: never a silent wrong result
-    *reinterpret_cast<float*>(zstash + (size_t)blockIdx.x * tq::Z_TILE_BYTES) = __int_as_float(0x7fc00000);
+    *reinterpret_cast<float*>(zstash + (size_t)blockIdx.x * tq::Z_TILE_BYTES + tq::set_base(tq::O_Z3)) =
+        __int_as_float(0x7fc00000);
   if (warp == TQ_EPI_WARPS) tcp::tmem_dealloc512(tmem);
 }
 
@@ -612,13 +715,21 @@ size_t tq_tblob_bytes() { return (size_t)tq::TBLOB_BYTES; }
 size_t tq_fstash_bytes(int n) { return (size_t)((n + TMT - 1) / TMT) * tq::F_TILE_BYTES; }
 size_t tq_zstash_bytes(int n) { return (size_t)((n + TMT - 1) / TMT) * tq::Z_TILE_BYTES; }
 int tq_grid(int n, int sms) { const int nt = (n + TMT - 1) / TMT; return nt < sms ? nt : sms; }
+int tq_dyn_grid(int n, int sms) {
+  const int nh = ((n + TMT - 1) / TMT) * (TMT / TQ_DYN_THREADS);
+  const int cap = 7 * sms < 1024 ? 7 * sms : 1024;            // one wave of 64-thread blocks; <= 1024 loss partials
+  return nh < cap ? nh : cap;
+}
 
 bool tq_supported(const HutterLayout& y, int h) {
   return y.conv && y.F0 == F0 && y.L == H && y.RD == RD && y.Mo == MO && h == H;
 }
 
+// forward = pack + tensor chain + dynamics / loss / reverse sweep (the loss partials come from the dynamics kernel:
+// tq_dyn_grid(n, sms) of them)
 cudaError_t launch_tq_fwd(const HutterLayout& y, const float* params, unsigned char* blob, unsigned char* tblob,
-                          const RolloutArgs& a, unsigned char* fstash, int grid, cudaStream_t st) {
+                          const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int grid, int dyn_grid,
+                          cudaStream_t st) {
   const int items = PAIRS_TOTAL + B_TOTAL + tq::TPAIRS_TOTAL;
   APG_LAUNCH((items + 255) / 256, 256, 0, st, tq_pack_kernel)(params, y, blob, tblob);
   cudaError_t e = cudaGetLastError();
@@ -626,6 +737,10 @@ cudaError_t launch_tq_fwd(const HutterLayout& y, const float* params, unsigned c
   e = cudaFuncSetAttribute(tq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_FWD_SMEM);
   if (e != cudaSuccess) return e;
   APG_LAUNCH(grid, TQ_THREADS, TQ_FWD_SMEM, st, tq_fwd_kernel)(blob, a, fstash);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(tq_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
+  if (e != cudaSuccess) return e;
+  APG_LAUNCH(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel)(a, fstash, zstash);
   return cudaGetLastError();
 }
 

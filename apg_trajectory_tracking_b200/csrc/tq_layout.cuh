@@ -22,6 +22,18 @@
 #include "tc_layout.cuh"
 #include "adj_dw_layout.cuh"
 
+// ---- optional per-role cycle accounting (build with -DAPG_PROFILE; tools/tq_profile.py): kernel k, CTA, counter
+#ifdef APG_PROFILE
+#define TQ_NPROF 16
+#define TQP_DECL long long tqp_t_ = clock64(); long long tqp_a_[6] = {0, 0, 0, 0, 0, 0};
+#define TQP(i) do { const long long t_ = clock64(); tqp_a_[i] += t_ - tqp_t_; tqp_t_ = t_; } while (0)
+#define TQP_FLUSH(k, base, n) do { if (blockIdx.x < 148) for (int i_ = 0; i_ < (n); ++i_) TQ_PROF_ARRAY[k][blockIdx.x][(base) + i_] = tqp_a_[i_]; } while (0)
+#else
+#define TQP_DECL
+#define TQP(i)
+#define TQP_FLUSH(k, base, n)
+#endif
+
 namespace apg {
 namespace tq {
 
@@ -35,14 +47,13 @@ constexpr int R_WIN = 40;         // per position pair g: in_ref rows 2g..2g+3 (
 constexpr int R_X1 = K1;          // 224: s (64) | conv outputs, position-major (64 + 20 t + c)
 constexpr int R_H = HID;          // 64
 constexpr int R_ACT = MO;         // 40 sigmoid outputs
-constexpr int R_ST = H * 12;      // 120: states after each step
 constexpr int O_XS = 0, O_WIN = O_XS + R_XS, O_X1 = O_WIN + 4 * R_WIN, O_H1 = O_X1 + R_X1, O_H2 = O_H1 + R_H,
-              O_H3 = O_H2 + R_H, O_ACT = O_H3 + R_H, O_ST = O_ACT + R_ACT, F_ROWS = O_ST + R_ST;     // 752
+              O_H3 = O_H2 + R_H, O_ACT = O_H3 + R_H, F_ROWS = O_ACT + R_ACT;                        // 632
 // ---- dZ stash sets
 constexpr int O_ZO = 0, O_Z3 = O_ZO + MO, O_Z2 = O_Z3 + HID, O_Z1 = O_Z2 + HID, O_ZX = O_Z1 + HID,
               Z_ROWS = O_ZX + K1;                                                                   // 456
 constexpr size_t ROW_BYTES = (size_t)TMT * 4;                  // bytes of one row over the whole tile (4 panels)
-constexpr size_t F_TILE_BYTES = (size_t)F_ROWS * ROW_BYTES;    // 385,024
+constexpr size_t F_TILE_BYTES = (size_t)F_ROWS * ROW_BYTES;    // 323,584
 constexpr size_t Z_TILE_BYTES = (size_t)Z_ROWS * ROW_BYTES;    // 233,472
 
 // byte offset of (row, drone-in-tile d) inside a set with R rows
@@ -104,6 +115,9 @@ APG_HD void pack_t_body(int e, const float* P, const HutterLayout& y, unsigned c
   }
 }
 
+// a 40-column piece is split [0,24) / [24,40) between the two column halves of a slot's epilogue threads
+constexpr int P40_SPLIT = 24;
+
 // ---- TMEM columns of one 256-column slot
 // forward (as tc_layout.cuh): D_main [0,64) | D_conv [64,112) | A_hi [112,176) | A_lo [176,240)
 // dX chain:                   D [0,128) | A_hi [128,192) | A_lo [192,256)
@@ -140,8 +154,7 @@ APG_HD DwSrc dw_src(int i) {
 }
 constexpr int DW_A_ROWS = 128, DW_B_ROWS = 64;
 constexpr int DW_A_BYTES = DW_A_ROWS * 128, DW_B_BYTES = DW_B_ROWS * 128;          // one panel image (raw or lo)
-constexpr int DW_STAGE_BYTES = 2 * DW_A_BYTES + 2 * DW_B_BYTES;                    // 49,152
-constexpr int DW_NSTAGE = 4;
+constexpr int DW_NRAW = 7, DW_NLO = 2;                                            // stage rings (tq_dw_kernels.cu)
 
 }  // namespace tq
 }  // namespace apg

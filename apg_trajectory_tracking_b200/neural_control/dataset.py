@@ -6,9 +6,17 @@
   samples into the four tensors of a train batch -- ``(in_state, current_state, in_ref_state, ref_states)`` -- with the
   reference's layouts (``prepare_data`` :155-204 and :326-350).  Like in the reference they live in CPU memory by
   default (data preparation, not rollout math; the train step copies each batch to the GPU); with ``device=`` a CUDA
-  device their ``prepare_data`` is the device kernels of ``prepare.py`` and the prepared tensors stay in HBM.  The reference's constructors sample
-  their data from its environments / trajectory files, which are outside the scope of this package: here the raw
-  samples are passed in (``states``, ``ref_states`` arrays), everything downstream is the same.
+  device their ``prepare_data`` is the device kernels of ``prepare.py`` and the prepared tensors stay in HBM.
+
+Two constructor forms, told apart by the first argument:
+  * the REFERENCE's (``dataset.py:46-73, 135-153, 223-240, 261-283``): ``QuadDataset(num_states, self_play, mean=None,
+    std=None, **kwargs)``, ``WingDataset(num_states, self_play=0, mean=None, std=None, ref_mean=None, ref_std=None,
+    delta_t=0.05, horizon=10, **kwargs)``, ``CartpoleDataset(num_states=1000, thresh_div=.21, dt=0.05, **kwargs)``:
+    the samples come from ``sample_data`` -> ``full_state_training_data`` / ``sample_training_data`` /
+    ``construct_states`` of the mirrored environments (device kernels: table layout, window cutting, dynamics steps),
+    with ``resample_data`` and ``get_and_add_eval_data`` as in the reference - so ``scripts/train_*.py`` of the
+    reference construct them unchanged;
+  * raw samples: ``QuadDataset(states, ref_states, ...)`` (arrays), used by the batched device pipeline and the tests.
 """
 import numpy as np
 import torch
@@ -27,25 +35,48 @@ def _as_tensor(x):
     return torch.from_numpy(np.array(x, dtype=np.float64)).float()
 
 
+def _is_count(x):
+    return isinstance(x, (int, np.integer)) and not isinstance(x, bool)
+
+
 class DroneDataset(torch.utils.data.Dataset):
     """common container: holds the prepared tensors, hands out 4-tuples, supports replacing samples (self play)"""
 
-    def __init__(self, states, ref_states, mean=None, std=None, self_play=0, device=None, **kwargs):
+    def __init__(self, states, ref_states=None, mean=None, std=None, self_play=0, device=None, **kwargs):
         """``device``: None (default) keeps the container and its ``prepare_data`` on the host like the reference;
         a CUDA device makes ``prepare_data`` the device kernels of ``prepare.py`` and keeps the four
         prepared tensors in HBM, so that batches need no host->device copy."""
-        states_np = np.asarray(states, dtype=np.float64)
         self.device = None if device is None else torch.device(device)
         self.kwargs = kwargs
-        self.num_sampled_states = int(len(states_np) / (1 + self_play)) if self_play else len(states_np)
-        self.num_self_play = len(states_np) - self.num_sampled_states
-        self.total_dataset_size = len(states_np)
+        if _is_count(states):
+            # the reference's constructor (dataset.py:46-73): (num_states, self_play, mean, std, **kwargs); the second
+            # positional argument is the self-play FRACTION there
+            num_states = int(states)
+            frac = ref_states if ref_states is not None else self_play
+            self.num_sampled_states = num_states
+            self.num_self_play = int(frac * num_states)
+            self.total_dataset_size = self.num_sampled_states + self.num_self_play
+            states, ref_states = self.sample_data(self.total_dataset_size)
+            states_np = np.asarray(states, dtype=np.float64)
+        else:
+            states_np = np.asarray(states, dtype=np.float64)
+            self.num_sampled_states = int(len(states_np) / (1 + self_play)) if self_play else len(states_np)
+            self.num_self_play = len(states_np) - self.num_sampled_states
+            self.total_dataset_size = len(states_np)
         if mean is None:
             mean, std = states_np.mean(axis=0), states_np.std(axis=0)
         self.mean = torch.as_tensor(np.asarray(mean)).float()
         self.std = torch.as_tensor(np.asarray(std)).float()
         self.normed_states, self.states, self.in_ref_states, self.ref_states = self.prepare_data(states, ref_states)
         self.eval_counter = 0
+
+    def sample_data(self, num_states):
+        raise NotImplementedError
+
+    def resample_data(self):
+        """new samples into the sampled part of the dataset (dataset.py:89-102)"""
+        states, ref_states = self.sample_data(self.num_sampled_states)
+        self.replace_sampled(states, ref_states)
 
     def prepare_data(self, states, ref_states):
         raise NotImplementedError
@@ -89,6 +120,11 @@ class QuadDataset(DroneDataset):
     [world vel, first two columns of the world->body matrix, body vel, body rates], reference input =
     [rel. position, velocity, velocity - drone velocity] per horizon row"""
 
+    def sample_data(self, num_states):
+        """dataset.py:140-144: windows cut from random trajectory tables"""
+        from .environments.drone_env import full_state_training_data
+        return full_state_training_data(num_states, **self.kwargs)
+
     @staticmethod
     def rot_world_to_body(state_vector, world_to_body):
         return torch.matmul(world_to_body, state_vector.unsqueeze(2))[:, :, 0]
@@ -111,11 +147,32 @@ class WingDataset(DroneDataset):
     """fixed-wing batches: normalised state without position, unit vector towards the target scaled to the last point
     of a 12 m/s straight-line reference, the straight-line reference itself for the loss"""
 
-    def __init__(self, states, ref_states, mean=None, std=None, delta_t=0.05, horizon=10, **kwargs):
+    def __init__(self, states, ref_states=None, mean=None, std=None, ref_mean=None, ref_std=None, delta_t=0.05,
+                 horizon=10, self_play=0, **kwargs):
+        """reference form (dataset.py:263-283): ``WingDataset(num_states, self_play=0, mean=None, std=None, ref_mean=
+        None, ref_std=None, delta_t=0.05, horizon=10, **kwargs)``; raw form: ``WingDataset(states, targets, ...)``"""
         self.dt, self.horizon = delta_t, horizon
+        if _is_count(states):
+            frac = ref_states if ref_states is not None else self_play
+            if mean is None:
+                super().__init__(states, frac, mean=_syn.WING_MEAN.numpy(), std=_syn.WING_STD.numpy(), **kwargs)
+                self.set_fixed_mean()                           # dataset.py:280-283: fixed statistics
+            else:
+                super().__init__(states, frac, mean=mean, std=std, **kwargs)
+            return
         if mean is None:
             mean, std = _syn.WING_MEAN.numpy(), _syn.WING_STD.numpy()       # fixed statistics (dataset.py:284-300)
-        super().__init__(states, ref_states, mean=mean, std=std, **kwargs)
+        super().__init__(states, ref_states, mean=mean, std=std, self_play=self_play, **kwargs)
+
+    def set_fixed_mean(self):
+        self.mean, self.std = _syn.WING_MEAN.clone().float(), _syn.WING_STD.clone().float()
+
+    def sample_data(self, num_samples):
+        """dataset.py:302-307"""
+        from .environments.wing_env import sample_training_data
+        if num_samples == 0:                                    # the trainer starts from an empty dataset + self play
+            return np.zeros((0, 12)), np.zeros((0, 3))
+        return sample_training_data(num_samples, **self.kwargs)
 
     def _compute_target_pos(self, current_state, ref_vector):
         steps = (torch.arange(self.horizon, dtype=torch.float32) + 1)[None, :, None]
@@ -139,9 +196,24 @@ class WingDataset(DroneDataset):
 class CartpoleDataset(torch.utils.data.Dataset):
     """cartpole batches are (state, state): the policy input is the raw state (dataset.py:223-258)"""
 
-    def __init__(self, states, **kwargs):
-        self.labels = _as_tensor(states)
+    def __init__(self, states=1000, thresh_div=.21, dt=0.05, **kwargs):
+        """reference form (dataset.py:228-230): ``CartpoleDataset(num_states=1000, thresh_div=.21, dt=0.05)``;
+        raw form: ``CartpoleDataset(states)``"""
+        self.dt = dt
+        if _is_count(states):
+            self.resample_data(int(states), thresh_div)
+        else:
+            self.labels = _as_tensor(states)
+            self.states = self.labels.clone()
+
+    def resample_data(self, num_states, thresh_div):
+        """dataset.py:232-240"""
+        from .environments.cartpole_env import construct_states
+        self.labels = _as_tensor(construct_states(num_states, self.dt, thresh_div=thresh_div))
         self.states = self.labels.clone()
+
+    def to_torch(self, states):
+        return _as_tensor(states)
 
     def __len__(self):
         return len(self.states)

@@ -108,6 +108,10 @@ def full_state_training_data(len_data, ref_length=5, dt=0.02, speed_factor=.6, d
     from .. import environments as _e
     dev = torch.device(device) if device is not None else _e.compute_device()
     folder = os.path.join(data_dir, "train")
+    if not os.path.isdir(folder):
+        # the reference's trajectory files (data/traj_data_1, made by its casadi generator) are not part of its
+        # checkout: seeded polynomial trajectories in the same table layout instead (BASELINE.md synthetic inputs)
+        return synthetic_training_data(len_data, ref_length=ref_length, dt=dt, device=dev)
     names = sorted(os.listdir(folder))
     states, refs, have = [], [], 0
     sample_freq = 2 * ref_length
@@ -122,3 +126,29 @@ def full_state_training_data(len_data, ref_length=5, dt=0.02, speed_factor=.6, d
         refs.append(r.cpu().numpy().astype(np.float64))
         have += n
     return np.concatenate(states)[:len_data], np.concatenate(refs)[:len_data]
+
+
+def synthetic_training_data(len_data, ref_length=5, dt=0.02, device=None, seed=None):
+    """Stand-in for ``full_state_training_data`` when no trajectory files exist: per sample a degree-5 polynomial per
+    axis (coefficients as SURVEY.md 8d: c1 ~ U(-1.5, 1.5), c_i ~ U(-.5, .5) / i!), sampled on the device
+    (``prepare.poly_reference``: rows ``[p(t), 0, p'(t)]`` at t = dt .. ref_length * dt); the drone starts on the
+    trajectory at t = 0 (random position in [-1, 1]^3 added to both) with small attitude and velocity noise.
+    Returns numpy (states (len_data, 12), ref_states (len_data, ref_length, 9)) like the reference function."""
+    from ... import prepare as PR
+    from .. import environments as _e
+    dev = torch.device(device) if device is not None else _e.compute_device()
+    rs = np.random.RandomState(seed)
+    coef = np.zeros((len_data, 3, 6), dtype=np.float32)
+    coef[:, :, 1] = rs.uniform(-1.5, 1.5, size=(len_data, 3))
+    fact = 1.0
+    for i in range(2, 6):
+        fact *= i
+        coef[:, :, i] = rs.uniform(-0.5, 0.5, size=(len_data, 3)) / fact
+    refs = PR.poly_reference(torch.as_tensor(coef).to(dev), ref_length, dt).cpu().numpy().astype(np.float64)
+    start = rs.uniform(-1.0, 1.0, size=(len_data, 3))
+    refs[:, :, :3] += start[:, None, :]
+    states = np.zeros((len_data, 12))
+    states[:, :3] = start
+    states[:, 3:6] = rs.uniform(-0.2, 0.2, size=(len_data, 3))
+    states[:, 6:9] = coef[:, :, 1] + rs.normal(0.0, 0.3, size=(len_data, 3))
+    return states, refs

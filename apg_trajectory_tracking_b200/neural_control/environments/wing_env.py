@@ -56,3 +56,27 @@ def generate_unit_vecs(num_vecs, mean_vec=[1, 0, 0], std=.15):
     vecs = np.random.multivariate_normal(mean_vec, np.eye(3) * std, size=num_vecs)
     vecs[vecs[:, 0] < 0.01, 0] = 1
     return vecs
+
+
+def sample_training_data(num_samples, dt=0.01, take_every=10, traj_len=500, vec_std=.15, **kwargs):
+    """(state, target point) pairs from open-loop flights (reference: ``sample_training_data``, environments/
+    wing_env.py:112-162): every ``take_every``-th state of a flight (with a random offset below 5) is paired with the
+    positions of up to 20 randomly chosen later states of the same flight (at least 10 steps ahead).  The flights run
+    on the CUDA dynamics op (``run_wing_flight``).  Like the reference says, the shipped baseline model is trained on
+    self-play data only; this seeds the dataset."""
+    from ..dynamics.fixed_wing_dynamics import FixedWingDynamics
+    use_at_each = 20
+    env = SimpleWingEnv(FixedWingDynamics(), dt)
+    states, refs = [], []
+    leftover = num_samples
+    while leftover > 0:
+        traj = run_wing_flight(env, traj_len=traj_len, **kwargs)
+        n_traj = len(traj)
+        for i in range(min(n_traj // take_every, leftover)):
+            at = int(i * take_every + np.random.rand() * 5)
+            later = np.random.permutation(np.arange(at + 10, n_traj))[:use_at_each]
+            for k in later:
+                states.append(traj[at])
+                refs.append(traj[k, :3])
+        leftover = num_samples - len(refs)
+    return np.array(states)[:num_samples], np.array(refs)[:num_samples]

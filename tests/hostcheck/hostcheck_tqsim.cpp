@@ -35,7 +35,7 @@ extern "C" void hc_tq_sizes(int n, long long* out) {
 extern "C" int hc_tq_step(const float* params, const float* in_state, const float* cur, const float* in_ref,
                           const float* ref, int n, float dt, const float* pc, int grid, unsigned char* blob,
                           unsigned char* tblob, unsigned char* fstash, unsigned char* zstash, float* loss_partials,
-                          float* grad_partials, float* states_out, float* actions_out, int stages, char* err,
+                          float* grad_partials, float* states_out, float* actions_out, int stages, int dyn_grid, char* err,
                           int err_len) {
   const HutterLayout y = layout();
   RolloutArgs a;
@@ -46,7 +46,7 @@ extern "C" int hc_tq_step(const float* params, const float* in_state, const floa
   a.loss_partials = loss_partials; a.grad_partials = grad_partials; a.states_out = states_out; a.actions_out = actions_out;
   unsigned char stamp[16];
   memset(stamp, 3, sizeof stamp);
-  if (stages >= 1) launch_tq_fwd(y, params, blob, tblob, a, fstash, grid, nullptr);
+  if (stages >= 1) launch_tq_fwd(y, params, blob, tblob, a, fstash, zstash, grid, dyn_grid, nullptr);
   if (stages >= 2) launch_tq_dx(tblob, a, fstash, zstash, stamp, 3, grid, nullptr);
   if (stages >= 3) launch_tq_dw(y, a, fstash, zstash, grid, nullptr);
   return report(err, err_len);

@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def simlib_path(tmp_path_factory):
     tmp = tmp_path_factory.mktemp("capisim")
     objs = []
-    for name in ("host", "te", "tc", "dw"):
+    for name in ("host", "te", "tc", "dw", "tq"):
         obj = tmp / f"{name}.o"
         subprocess.check_call(["g++", "-O1", "-c", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
                                "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
