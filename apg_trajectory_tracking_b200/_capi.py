@@ -25,6 +25,9 @@ class ApgGradComm(ctypes.Structure):
 EXPORTS = {
     "apg_version": (ctypes.c_int, []),
     "apg_sm_count": (ctypes.c_int, []),
+    "apg_rollout_kernel_path": (ctypes.c_int, [ctypes.POINTER(ApgConfig)]),
+    "apg_debug_timing": (ctypes.c_int, [ctypes.c_int]),
+    "apg_debug_kernel_times": (ctypes.c_int, [ctypes.c_void_p]),
     "apg_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "apg_num_params": (ctypes.c_int, [ctypes.POINTER(ApgConfig)]),
     "apg_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ApgConfig)]),
@@ -32,6 +35,8 @@ EXPORTS = {
                             [c_float_p] * 3 + [ctypes.c_void_p]),
     "apg_rollout_backward": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p,
                              ctypes.c_float, c_float_p, ctypes.c_void_p]),
+    "apg_rollout_backward_sgd": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p,
+                                 ctypes.c_float, c_float_p, c_float_p, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     "apg_rollout_value_and_grad_host": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 8),
     "apg_grad_comm_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "apg_grad_comm_offsets": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libapg_b200.so")
-SOURCES = ["capi.cu", "capi_prep.cu", "prep_kernels.cu", "eval_kernels.cu", "learnt_kernels.cu", "misc_kernels.cu", "p2p_kernels.cu", "hutter_kernels.cu", "hutter_tc_kernels.cu", "hutter_adjdx_kernels.cu", "adj_dw_tc_kernels.cu", "tq_kernels.cu", "tq_dw_kernels.cu", "simple_kernels.cu", "rec_kernels.cu", "lstm_kernels.cu"]
+SOURCES = ["capi.cu", "capi_prep.cu", "prep_kernels.cu", "eval_kernels.cu", "learnt_kernels.cu", "misc_kernels.cu", "p2p_kernels.cu", "hutter_kernels.cu", "tq_kernels.cu", "tq_dw_kernels.cu", "simple_kernels.cu", "rec_kernels.cu", "lstm_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-Xcudafe", "--diag_suppress=177"]

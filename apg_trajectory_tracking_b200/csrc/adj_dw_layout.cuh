@@ -1,11 +1,10 @@
-// Streaming weight-gradient GEMM of the split adjoint (adj_dw_tc_kernels.cu): op list, operand sources and the map
-// from accumulator entries to the torch-flat gradient.  Plain `__host__ __device__` index arithmetic, shared with the
-// CPU check (tests/hostcheck/hostcheck_tc.cpp).  Quadrotor concurrent net Net(15,10,9,40,conv), see tc_layout.cuh.
+// Streaming weight-gradient GEMM (tq_dw_kernels.cu): op list, accumulator columns and the map from accumulator
+// entries to the torch-flat gradient.  Plain `__host__ __device__` index arithmetic, shared with the CPU checks.
+// Quadrotor concurrent net Net(15,10,9,40,conv), see tc_layout.cuh; operand sources (stash sets): tq_layout.cuh.
 //
 //   dW_l[out][in] = sum over drones dZ_l[drone][out] * X_l[drone][in]
-// as  D[M = in (+ a row of ones -> bias gradient)][N = out] += A[in][K = drone] * B[out][K = drone]^T  per 64-drone
-// stash tile (K = 64, eight tcgen05 k-steps), both operands K-major unswizzled (hi, lo) images filled by the loader
-// warps from the feature-major stash tiles [rows][TMP]; the accumulators stay in TMEM for the whole launch.
+// as  D[M = in (+ a row of ones -> bias gradient)][N = out] += A[in][K = drone] * B[out][K = drone]^T  per 32-drone
+// panel, both operands K-major 128B-swizzled (raw, lo) images; the accumulators stay in TMEM for the whole launch.
 #pragma once
 #include "tc_layout.cuh"
 
@@ -13,14 +12,6 @@ namespace apg {
 namespace dw {
 
 using tc::F0; using tc::H; using tc::RD; using tc::NC; using tc::NPOS; using tc::MO; using tc::K1; using tc::REFW;
-
-constexpr int KD = 64;                         // drones per K block = one stash tile
-constexpr int AM = 128;                        // rows of every A image (M of the MMA)
-constexpr int A_IMG_BYTES = AM * KD * 4;       // 32 KiB per hi or lo image
-constexpr int B_ROWS = 64;
-constexpr int B_IMG_BYTES = B_ROWS * KD * 4;   // 16 KiB
-constexpr int STAGE_BYTES = 2 * A_IMG_BYTES + 2 * B_IMG_BYTES;     // 96 KiB
-constexpr int NSTAGE = 2;
 
 enum ASrc { A_H3 = 0, A_H2, A_H1, A_X1_LO, A_X1_HI, A_INSTATE, A_WINDOW };
 enum BSrc { B_DZO = 0, B_DZ3, B_DZ2, B_DZ1, B_DZS, B_DZC };
@@ -40,63 +31,6 @@ APG_HD Op op_of(int i) {
   if (i == 5) return {A_INSTATE, 0, F0, F0, B_DZS, 0, 64, 64, C_WS, 1};
   const int g = i - 6;                                   // conv position pair g: window rows 2g .. 2g+3 of in_ref
   return {A_WINDOW, 18 * g, 4 * RD, 4 * RD, B_DZC, HID + 2 * NC * g, 2 * NC, 48, C_WT, g == 0};
-}
-
-// byte offset of the 16-byte chunk (row r, drones 4*d4 .. 4*d4+3) inside a K-major unswizzled image with K = 64
-APG_HD constexpr uint32_t chunk_off(int r, int d4) { return (uint32_t)((r >> 3) * 2048 + d4 * 128 + (r & 7) * 16); }
-
-// loader work item q -> (image row r, chunk d4): a warp's 32 items cover 8 rows x 4 chunks = 512 contiguous bytes of
-// the image (conflict-free st.shared.v4) and 8 x 64 B of the stash tile
-APG_HD void chunk_of_item(int q, int* r, int* d4) { *r = (q & 7) + ((q >> 7) << 3); *d4 = (q >> 3) & 15; }
-
-// base pointers of everything the GEMM streams (tile-major stashes [tile][rows][TMP], drone-major policy inputs)
-struct Sources {
-  const float *h3, *h2, *h1, *x1, *in_state, *in_ref;     // X_l
-  const float *dzo, *dz3, *dz2, *dz1, *dzx;                 // dZ_l
-};
-
-APG_HD void load4(const float* p, float* o) {
-#if defined(__CUDA_ARCH__)
-  const float4 v = *reinterpret_cast<const float4*>(p);
-  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-#else
-  o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3];
-#endif
-}
-
-// the four values (row r, drones 4*d4 .. 4*d4+3) of the A image of op for stash tile `tile` (`valid` live drones)
-APG_HD void a_chunk(const Op& op, const Sources& S, int tile, int valid, int r, int d4, float* o) {
-  o[0] = o[1] = o[2] = o[3] = 0.f;
-  if (r < op.a_rows) {
-    const float* t = nullptr;
-    if (op.a_src == A_H3) t = S.h3 + (size_t)tile * HID * TMP;
-    else if (op.a_src == A_H2) t = S.h2 + (size_t)tile * HID * TMP;
-    else if (op.a_src == A_H1) t = S.h1 + (size_t)tile * HID * TMP;
-    else if (op.a_src == A_X1_LO || op.a_src == A_X1_HI) t = S.x1 + ((size_t)tile * K1 + op.a_row0) * TMP;
-    if (t) {
-      load4(t + r * TMP + 4 * d4, o);
-    } else {
-      for (int c = 0; c < 4; ++c) {
-        const int dd = 4 * d4 + c;
-        const size_t drone = (size_t)tile * TM + dd;
-        if (dd < valid)
-          o[c] = op.a_src == A_INSTATE ? S.in_state[drone * F0 + r] : S.in_ref[drone * REFW + op.a_row0 + r];
-      }
-    }
-  } else if (r == op.ones) {
-    o[0] = o[1] = o[2] = o[3] = 1.f;
-  }
-}
-// the same for the B image (dZ rows [b_row0, b_row0 + b_rows), zero above)
-APG_HD void b_chunk(const Op& op, const Sources& S, int tile, int r, int d4, float* o) {
-  o[0] = o[1] = o[2] = o[3] = 0.f;
-  if (r >= op.b_rows) return;
-  const float* t = op.b_src == B_DZO   ? S.dzo + (size_t)tile * MO * TMP
-                   : op.b_src == B_DZ3 ? S.dz3 + (size_t)tile * HID * TMP
-                   : op.b_src == B_DZ2 ? S.dz2 + (size_t)tile * HID * TMP
-                   : op.b_src == B_DZ1 ? S.dz1 + (size_t)tile * HID * TMP
-                                       : S.dzx + ((size_t)tile * K1 + op.b_row0) * TMP;
-  load4(t + r * TMP + 4 * d4, o);
 }
 
 // x1 row (position-major: 64 + t*20 + c) -> torch fc1 column (channel-major: 64 + c*8 + t)

@@ -86,8 +86,8 @@ HutterLayout hutter_layout(const apg_config* c) {
 
 struct Plan {
   int grid, ntiles;
-  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_tc, o_dzo, o_dz3, o_dz2, o_dz1, o_dzx,
-      o_hdr, o_tq_t, o_tq_f, o_tq_z, total;
+  size_t o_wf, o_wb, o_lossp, o_gradp, o_x1, o_h1, o_h2, o_h3, o_act, o_states, o_hdr, o_tq_w, o_tq_t, o_tq_f, o_tq_z,
+      total;
   int tq_grid, tq_dyn_grid;
 };
 
@@ -129,20 +129,12 @@ Plan make_plan(const apg_config* c, const NetInfo& y) {
   p.o_h3 = o;     o += up256(sizeof(float) * nst * y.h_rows * TMP);
   p.o_act = o;    o += up256(sizeof(float) * nst * y.act_rows * TMP);
   p.o_states = o; o += up256(sizeof(float) * (size_t)p.ntiles * c->horizon * S * TMP);
-  // weight images of the optional tcgen05 forward (appended: the offsets above do not move)
-  p.o_tc = o;     o += up256(tc_blob_bytes());
-  // dZ stash of the optional split adjoint (concurrent hutter nets only; appended as well)
-  const size_t dzt = (is_hutter(c) && !is_recurrent(c)) ? (size_t)p.ntiles : 0;
-  p.o_dzo = o;    o += up256(sizeof(float) * dzt * y.act_rows * TMP);
-  p.o_dz3 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
-  p.o_dz2 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
-  p.o_dz1 = o;    o += up256(sizeof(float) * dzt * y.h_rows * TMP);
-  p.o_dzx = o;    o += up256(sizeof(float) * dzt * y.x1_rows * TMP);
   // header: which forward variant produced the stash / weight images of this workspace (read by backward)
   p.o_hdr = o;    o += 256;
-  // tcgen05 path, second generation (quadrotor concurrent): transposed weight images, X stash and dZ stash in operand-
-  // image format (tq_layout.cuh); the forward images live at o_tc
+  // tcgen05 path (quadrotor concurrent): forward / transposed weight images, X stash and dZ stash in operand-image
+  // format (tq_layout.cuh)
   const bool tq_cfg = is_hutter(c) && !is_recurrent(c) && c->system == SYS_QUAD && tq_supported(hutter_layout(c), c->horizon);
+  p.o_tq_w = o;   o += tq_cfg ? up256(tq_blob_bytes()) : 0;
   p.o_tq_t = o;   o += tq_cfg ? up256(tq_tblob_bytes()) : 0;
   p.o_tq_f = o;   o += tq_cfg ? up256(tq_fstash_bytes(c->n_drones)) + 1024 : 0;
   p.o_tq_z = o;   o += tq_cfg ? up256(tq_zstash_bytes(c->n_drones)) + 1024 : 0;
@@ -190,32 +182,33 @@ bool env_flag(const char* name) {
   return e && e[0] == '1';
 }
 
-// APG_TC_FWD=1 selects the tcgen05 forward for the configuration it is written for (quadrotor concurrent,
-// Net(15,10,9,40,conv), h = 10); everything else, and the default, runs hutter_fwd_kernel.
-bool use_tc_forward(const apg_config* c, const HutterLayout& y) {
-  const char* e = getenv("APG_TC_FWD");
-  if (!e || e[0] != '1') return false;
-  return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && tc_fwd_supported(y, c->horizon);
-}
-
-// APG_TC_DW=1 selects the split adjoint (mma.sync dX chain + tcgen05 streaming dW GEMM) for the same configuration
-bool use_tc_dw(const apg_config* c, const HutterLayout& y) {
-  const char* e = getenv("APG_TC_DW");
-  if (!e || e[0] != '1') return false;
-  return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && adj_dw_tc_supported(y, c->horizon);
-}
-
 // The tcgen05 path (tq_kernels.cu / tq_dw_kernels.cu) is THE path of the quadrotor concurrent configuration it is
 // written for (Net(15,10,9,40,conv), h = 10); APG_LEGACY_MMA=1 selects the mma.sync kernels instead (kept for the other
 // configurations and as a cross-check).
 bool use_tq(const apg_config* c, const HutterLayout& y) {
-  if (env_flag("APG_LEGACY_MMA") || env_flag("APG_TC_FWD") || env_flag("APG_TC_DW")) return false;
+  if (env_flag("APG_LEGACY_MMA")) return false;
   return c->system == SYS_QUAD && c->mode == MODE_CONCURRENT && tq_supported(y, c->horizon);
 }
 inline unsigned char* align1024(unsigned char* p) {
   return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
-enum FwdVariant { FWD_LEGACY = 1, FWD_TC1 = 2, FWD_TQ = 3 };
+enum FwdVariant { FWD_LEGACY = 1, FWD_TQ = 3 };
+
+// Optional per-kernel device timing of the tcgen05 path (apg_debug_timing / apg_debug_kernel_times): CUDA events on
+// the launching stream between the launches, so that a caller (bench.py) can attribute the step time to kernels
+// without a profiler.  Off by default; not part of any timed measurement.
+#ifndef APG_SIM
+constexpr int N_TMARK = 9;                 // [pack | fwd | dyn | sum_loss] [dx | dw | reduce]
+bool g_timing = false;
+cudaEvent_t g_tev[N_TMARK] = {};
+void tmark(int i, cudaStream_t st) {
+  if (!g_timing) return;
+  if (!g_tev[i]) cudaEventCreate(&g_tev[i]);
+  cudaEventRecord(g_tev[i], st);
+}
+#else
+void tmark(int, cudaStream_t) {}
+#endif
 
 // cached device buffers of the host-buffer entry point
 struct HostCache {
@@ -240,6 +233,35 @@ __attribute__((visibility("default"))) const char* apg_error_string(int code) {
     case APG_ERR_NO_DEVICE: return "apg: no CUDA device";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "apg: unknown error";
   }
+}
+
+// per-kernel device times of the LAST forward + backward on the tcgen05 path (see tmark above): ms_out[7] =
+// pack, forward chain, dynamics + reverse sweep, loss sum, dX chain, dW GEMM, gradient reduce.  Synchronises.
+__attribute__((visibility("default"))) int apg_debug_timing(int enable) {
+#ifndef APG_SIM
+  g_timing = enable != 0;
+#endif
+  return 0;
+}
+__attribute__((visibility("default"))) int apg_debug_kernel_times(float* ms_out) {
+#ifndef APG_SIM
+  if (!ms_out) return APG_ERR_BAD_CONFIG;
+  for (int i = 0; i < N_TMARK; ++i) if (!g_tev[i]) return APG_ERR_BAD_CONFIG;
+  cudaError_t ce = cudaEventSynchronize(g_tev[N_TMARK - 1]);
+  if (ce) return (int)ce;
+  const int pairs[7][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {7, 8}};
+  for (int k = 0; k < 7; ++k)
+    if ((ce = cudaEventElapsedTime(&ms_out[k], g_tev[pairs[k][0]], g_tev[pairs[k][1]]))) return (int)ce;
+#endif
+  return 0;
+}
+
+// which kernels apg_rollout_forward / backward launch for this configuration (and environment): 1 = the tcgen05 /
+// TMEM path (tq_*_kernel), 0 = the mma.sync / FFMA tile-engine kernels
+__attribute__((visibility("default"))) int apg_rollout_kernel_path(const apg_config* cfg) {
+  const int e = check_config(cfg);
+  if (e) return e;
+  return (is_hutter(cfg) && !is_recurrent(cfg) && use_tq(cfg, hutter_layout(cfg))) ? 1 : 0;
 }
 
 __attribute__((visibility("default"))) int apg_num_params(const apg_config* cfg) {
@@ -270,27 +292,29 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
     const HutterLayout y = hutter_layout(cfg);
     // the mma.sync kernels' packed weights; not needed when forward AND both adjoint halves run on the tcgen05 images
     const bool tq = !is_recurrent(cfg) && use_tq(cfg, y);
-    const bool all_tc = tq || (use_tc_forward(cfg, y) && use_tc_dw(cfg, y) && env_flag("APG_TC_DX"));
-    const int variant = tq ? FWD_TQ : (use_tc_forward(cfg, y) ? FWD_TC1 : FWD_LEGACY);
+    const int variant = tq ? FWD_TQ : FWD_LEGACY;
     // stamp the workspace with the variant that fills its stash (one byte value, capturable memset node); the adjoint
     // kernels of the tcgen05 path check it on the device and poison the gradient on a mismatch
     if ((ce = cudaMemsetAsync(static_cast<char*>(workspace) + p.o_hdr, variant, 16, st))) return (int)ce;
-    if (!all_tc &&
+    // the mma.sync kernels' packed weights (not needed on the tcgen05 path, which packs its own images)
+    if (!tq &&
         (ce = launch_pack(hutter_pack_table(y), params, const_cast<float*>(a.wf), const_cast<float*>(a.wb), st)))
       return (int)ce;
     if (is_recurrent(cfg)) { if ((ce = launch_rec_fwd(y, a, p.grid, st))) return (int)ce; }
     else if (tq) {
       unsigned char* w = static_cast<unsigned char*>(workspace);
-      if ((ce = launch_tq_fwd(y, params, w + p.o_tc, w + p.o_tq_t, a, align1024(w + p.o_tq_f), align1024(w + p.o_tq_z),
-                              p.tq_grid, p.tq_dyn_grid, st)))
-        return (int)ce;
+      unsigned char* fs = align1024(w + p.o_tq_f);
+      unsigned char* zs = align1024(w + p.o_tq_z);
+      tmark(0, st);
+      if ((ce = launch_tq_pack(y, params, w + p.o_tq_w, w + p.o_tq_t, st))) return (int)ce;
+      tmark(1, st);
+      if ((ce = launch_tq_fwd(w + p.o_tq_w, a, fs, p.tq_grid, st))) return (int)ce;
+      tmark(2, st);
+      if ((ce = launch_tq_dyn(a, fs, zs, p.tq_dyn_grid, st))) return (int)ce;
+      tmark(3, st);
       if (loss && (ce = launch_sum_loss(a.loss_partials, p.tq_dyn_grid, loss, st))) return (int)ce;
+      tmark(4, st);
       return 0;
-    }
-    else if (use_tc_forward(cfg, y)) {
-      // optional tcgen05 / TMEM forward (APG_TC_FWD=1): same stash, consumed by the same adjoint kernel
-      unsigned char* blob = static_cast<unsigned char*>(workspace) + p.o_tc;
-      if ((ce = launch_hutter_fwd_tc(y, params, blob, a, p.grid, st))) return (int)ce;
     }
     else if ((ce = launch_hutter_fwd(cfg->system, y, a, p.grid, st))) return (int)ce;
   } else if (cfg->net == NET_LSTM) {
@@ -326,13 +350,16 @@ cudaError_t finish_gradient(const float* partials, int ncta, int n, float scale,
   return launch_reduce_grad(partials, ncta, n, scale, grad_params, st, pm_off, pm_k1, pm_npos);
 }
 
+// optimizer step fused into the gradient reduction (tcgen05 path only)
+struct SgdFuse { float* params; float* momentum_buf; float lr, momentum; };
+
 int rollout_backward_impl(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
                           const float* in_ref, const float* ref, const float* h0c0, void* workspace, float grad_loss,
-                          float* grad_params, const apg_grad_comm* comm, void* stream) {
+                          float* grad_params, const apg_grad_comm* comm, void* stream, const SgdFuse* sgd = nullptr) {
   int e = check_config(cfg);
   if (e) return e;
   if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, workspace))) return e;
-  if (!grad_params && !comm) return APG_ERR_BAD_CONFIG;
+  if (!grad_params && !comm && !sgd) return APG_ERR_BAD_CONFIG;
   if (comm && (!comm->slot_ptrs || !comm->flag_ptrs || !comm->ticket || comm->world < 1 || comm->rank < 0 ||
                comm->rank >= comm->world))
     return APG_ERR_BAD_CONFIG;
@@ -350,34 +377,25 @@ int rollout_backward_impl(const apg_config* cfg, const float* params, const floa
       unsigned char* w = static_cast<unsigned char*>(workspace);
       unsigned char* fs = align1024(w + p.o_tq_f);
       unsigned char* zs = align1024(w + p.o_tq_z);
+      tmark(5, st);
       if ((ce = launch_tq_dx(w + p.o_tq_t, a, fs, zs, w + p.o_hdr, FWD_TQ, p.tq_grid, st))) return (int)ce;
+      tmark(6, st);
       if ((ce = launch_tq_dw(y, a, fs, zs, p.tq_grid, st))) return (int)ce;
-      if ((ce = finish_gradient(a.grad_partials, p.tq_grid, ni.n_params, grad_loss, grad_params, comm, 0, 0, 0, true, st)))
-        return (int)ce;
-      return 0;
-    }
-    else if (use_tc_dw(cfg, hutter_layout(cfg))) {
-      // optional split adjoint (APG_TC_DW=1): dX chain + dZ stash, then the streaming tcgen05 weight-gradient GEMM
-      const HutterLayout y = hutter_layout(cfg);
-      char* w = static_cast<char*>(workspace);
-      DzStash z;
-      z.o = reinterpret_cast<float*>(w + p.o_dzo);  z.z3 = reinterpret_cast<float*>(w + p.o_dz3);
-      z.z2 = reinterpret_cast<float*>(w + p.o_dz2); z.z1 = reinterpret_cast<float*>(w + p.o_dz1);
-      z.x = reinterpret_cast<float*>(w + p.o_dzx);
-      if (env_flag("APG_TC_DX")) {
-        // dX chain on tcgen05 as well (forward weight images read MN-major).  The images of the forward call are
-        // reused when that ran on tcgen05 (same parameters by the API contract), otherwise they are packed here.
-        unsigned char* blob = static_cast<unsigned char*>(workspace) + p.o_tc;
-        if ((ce = launch_hutter_adj_dx_tc(y, use_tc_forward(cfg, y) ? nullptr : params, blob, a, z, p.grid, st)))
+      tmark(7, st);
+      if (sgd) {
+        if ((ce = launch_reduce_grad4_sgd(a.grad_partials, p.tq_grid, ni.n_params, grad_loss, grad_params, sgd->params,
+                                          sgd->momentum_buf, sgd->lr, sgd->momentum, st)))
           return (int)ce;
-      } else if ((ce = launch_hutter_adj_dx(cfg->system, y, a, z, p.grid, st))) return (int)ce;
-      if ((ce = launch_adj_dw_tc(y, a, z, p.grid, st))) return (int)ce;
-      // the partials are already in torch column order: plain sliced reduction
-      if ((ce = finish_gradient(a.grad_partials, p.grid, ni.n_params, grad_loss, grad_params, comm, 0, 0, 0, true, st)))
+      } else if ((ce = finish_gradient(a.grad_partials, p.tq_grid, ni.n_params, grad_loss, grad_params, comm, 0, 0, 0,
+                                       true, st)))
         return (int)ce;
+      tmark(8, st);
       return 0;
     }
+    else if (sgd) return APG_ERR_UNSUPPORTED;
     else if ((ce = launch_hutter_adj(cfg->system, hutter_layout(cfg), a, p.grid, st))) return (int)ce;
+  } else if (sgd) {
+    return APG_ERR_UNSUPPORTED;
   } else if (cfg->net == NET_LSTM) {
     if ((ce = launch_lstm_adj(lstm_layout(cfg), a, p.grid, st))) return (int)ce;
   } else {
@@ -403,6 +421,21 @@ __attribute__((visibility("default"))) int apg_rollout_backward(const apg_config
   if (!grad_params) return APG_ERR_BAD_CONFIG;
   return rollout_backward_impl(cfg, params, in_state, cur, in_ref, ref, h0c0, workspace, grad_loss, grad_params,
                                nullptr, stream);
+}
+
+// apg_rollout_backward + the reference's optimizer step (optim.SGD(momentum): buf = momentum * buf + g; p -= lr * buf,
+// train_base.py:139-143) fused into the gradient reduction: `params_rw` (the vector the forward read) and
+// `momentum_buf` are updated in place; `grad_params` may be NULL.  Configurations served by the tcgen05 path only
+// (apg_rollout_kernel_path(cfg) == 1), APG_ERR_UNSUPPORTED otherwise.
+__attribute__((visibility("default"))) int apg_rollout_backward_sgd(const apg_config* cfg, float* params_rw, const float* in_state, const float* cur,
+                             const float* in_ref, const float* ref, const float* h0c0, void* workspace,
+                             float grad_loss, float* grad_params, float* momentum_buf, float lr, float momentum,
+                             void* stream) {
+  if (!params_rw || !momentum_buf) return APG_ERR_BAD_CONFIG;
+  if (!aligned16(momentum_buf) || (grad_params && !aligned16(grad_params))) return APG_ERR_ALIGNMENT;
+  const SgdFuse sgd{params_rw, momentum_buf, lr, momentum};
+  return rollout_backward_impl(cfg, params_rw, in_state, cur, in_ref, ref, h0c0, workspace, grad_loss, grad_params,
+                               nullptr, stream, &sgd);
 }
 
 // ---- the gradient all-reduce as this library's own kernels over NVLink peer memory (p2p_kernels.cu, p2p_math.cuh)

@@ -15,25 +15,8 @@ size_t hutter_adj_smem_bytes(const HutterLayout& y);
 cudaError_t launch_hutter_fwd(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_hutter_adj(int system, const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 
-// optional tcgen05 / TMEM forward of the quadrotor concurrent rollout (hutter_tc_kernels.cu)
-size_t tc_blob_bytes();
-bool tc_fwd_supported(const HutterLayout& y, int h);
-cudaError_t launch_hutter_fwd_tc(const HutterLayout& y, const float* params, unsigned char* blob,
-                                 const RolloutArgs& a, int grid, cudaStream_t st);
-
-// optional split adjoint (APG_TC_DW=1): dX chain + dZ stash (hutter_adjdx_kernels.cu), then the weight gradient as a
-// streaming tcgen05 GEMM over the drone axis (adj_dw_tc_kernels.cu)
-// (struct DzStash: rollout_args.h)
-cudaError_t launch_hutter_adj_dx(int system, const HutterLayout& y, const RolloutArgs& a, const DzStash& z, int grid,
-                                 cudaStream_t st);
-cudaError_t launch_hutter_adj_dx_tc(const HutterLayout& y, const float* params, unsigned char* blob,
-                                    const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st);
-cudaError_t launch_adj_dw_tc(const HutterLayout& y, const RolloutArgs& a, const DzStash& z, int grid, cudaStream_t st);
-bool adj_dw_tc_supported(const HutterLayout& y, int h);
-cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st);
-
-// tcgen05 / TMEM path of the quadrotor concurrent rollout, second generation (tq_kernels.cu, tq_dw_kernels.cu,
-// tq_layout.cuh): forward, dX chain and streaming weight-gradient GEMM on operand-image stashes
+// tcgen05 / TMEM path of the quadrotor concurrent rollout (tq_kernels.cu, tq_dw_kernels.cu, tq_layout.cuh): forward,
+// dynamics + reverse sweep, dX chain and streaming weight-gradient GEMM on operand-image stashes
 bool tq_supported(const HutterLayout& y, int h);
 size_t tq_blob_bytes();
 size_t tq_tblob_bytes();
@@ -41,13 +24,19 @@ size_t tq_fstash_bytes(int n);
 size_t tq_zstash_bytes(int n);
 int tq_grid(int n, int sms);
 int tq_dyn_grid(int n, int sms);
-cudaError_t launch_tq_fwd(const HutterLayout& y, const float* params, unsigned char* blob, unsigned char* tblob,
-                          const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int grid, int dyn_grid,
+cudaError_t launch_tq_pack(const HutterLayout& y, const float* params, unsigned char* blob, unsigned char* tblob,
+                           cudaStream_t st);
+cudaError_t launch_tq_fwd(const unsigned char* blob, const RolloutArgs& a, unsigned char* fstash, int grid,
+                          cudaStream_t st);
+cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int dyn_grid,
                           cudaStream_t st);
 cudaError_t launch_tq_dx(const unsigned char* tblob, const RolloutArgs& a, unsigned char* fstash,
                          unsigned char* zstash, const unsigned char* stamp, int want_stamp, int grid, cudaStream_t st);
 cudaError_t launch_tq_dw(const HutterLayout& y, const RolloutArgs& a, const unsigned char* fstash,
                          const unsigned char* zstash, int grid, cudaStream_t st);
+cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st);
+cudaError_t launch_reduce_grad4_sgd(const float* partials, int ncta, int n, float scale, float* grad, float* param,
+                                    float* buf, float lr, float momentum, cudaStream_t st);
 
 cudaError_t launch_rec_fwd(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_rec_adj(const HutterLayout& y, const RolloutArgs& a, int grid, cudaStream_t st);

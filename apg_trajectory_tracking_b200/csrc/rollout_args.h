@@ -34,7 +34,4 @@ struct RolloutArgs {
   float* actions_out;      // optional [N][h][A]
 };
 
-// dZ stash of the split adjoint (hutter_adjdx_kernels.cu / hutter_tc_kernels.cu -> adj_dw_tc_kernels.cu), tile-major
-struct DzStash { float *o, *z3, *z2, *z1, *x; };      // [tile][Mo4 | 64 | 64 | 64 | K1][TMP]
-
 }  // namespace apg

@@ -1,8 +1,8 @@
 // tcgen05 / TMEM forward of the quadrotor concurrent policy Net(15, 10, 9, 40, conv=True): shared-memory weight
-// images, op list and stash addressing, shared by the device code (hutter_tc_kernels.cu) and the CPU checks
-// (tests/hostcheck/hostcheck_tc.cpp).  Everything here is plain `__host__ __device__` index arithmetic.
+// images and op list, shared by the device code (tq_kernels.cu) and the CPU checks (tests/hostcheck).  Everything
+// here is plain `__host__ __device__` index arithmetic.  Stash format, dX chain and dW GEMM: tq_layout.cuh.
 //
-// Design (measured prototype: tools/micro/tcgen05_policy.cu; DESIGN.md 8.1):
+// Design (measured prototype: tools/micro/tcgen05_policy.cu; DESIGN.md 3):
 //   * tile = 128 drones = 128 TMEM lanes; epilogue thread r owns drone r of the tile.
 //   * every weight matrix is resident in shared memory as a (hi, lo) pair of K-major, unswizzled TF32 images
 //     (core matrix = 8 rows x 16 B); 3xTF32: D = A_lo W_hi + A_hi W_lo + A_hi W_hi, fp32 accumulation in TMEM.
@@ -136,17 +136,11 @@ APG_HD uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
 // K-major unswizzled image with K columns, k-step ks (8 tf32 = two 16-byte chunks): K-adjacent core matrices 128 B
 // apart (LBO), 8-row groups (K/4)*128 B apart (SBO)
 APG_HD uint64_t kmajor_desc(uint32_t base, int ks, int K) { return smem_desc(base + ks * 256, 128, (K >> 2) * 128); }
-// the same image read MN-major (operand = the transposed matrix): k-step ks = image rows 8*ks .. 8*ks+7; 8-row
-// groups (Kf/4)*128 B apart (LBO), adjacent 16-byte chunks = adjacent groups of four mn elements (SBO = 128)
-APG_HD uint64_t mnmajor_desc(uint32_t base, int ks, int Kf) {
-  const uint32_t lbo = (Kf >> 2) * 128;
-  return smem_desc(base + ks * lbo, lbo, 128);
-}
-// instruction descriptor, kind::tf32: c_format F32 (bit 4), a/b format TF32 (bits 7, 10), b_major at bit 16,
-// N >> 3 at bit 17, M >> 4 at bit 24
-APG_HD uint32_t idesc_tf32(int M, int N, int b_mn_major = 0) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(b_mn_major & 1) << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+// instruction descriptor, kind::tf32: c_format F32 (bit 4), a/b format TF32 (bits 7, 10), N >> 3 at bit 17, M >> 4 at
+// bit 24; both operands K-major (bits 15 / 16 = 0: an MN-major tf32 operand yields zeros on B200, measured with
+// tools/micro/tcgen05_probe.cu)
+APG_HD uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // one GEMM of the op list: D[d_col, +N) (=|+=) A[0, K) * W^T
@@ -164,27 +158,6 @@ APG_HD Op op_of(int i) {
   if (i == 11) return {I_W3.off, 64, 64, C_DMAIN, 64, 1};
   return {I_WO.off, 48, 64, C_DMAIN, 48, 1};
 }
-
-// reverse op list of the tcgen05 dX chain: D[d_col, +N) = A[0, K) * W  with W's forward image (rows, Kf) read MN-major
-struct ROp { int img_off, rows, Kf, K, N, d_col; };
-constexpr int NROPS = 8;
-APG_HD ROp rop_of(int i) {
-  if (i == 0) return {I_WO.off, 48, 64, 40, 64, C_DMAIN};                         // dH3 = dZo Wo
-  if (i == 1) return {I_W3.off, 64, 64, 64, 64, C_DMAIN};                         // dH2 = dZ3 W3
-  if (i == 2) return {I_W2.off, 64, 64, 64, 64, C_DMAIN};                         // dH1 = dZ2 W2
-  if (i == 3) return {I_W1S.off, 64, 64, 64, 64, C_DMAIN};                        // ds  = dZ1 W1[:, :64]
-  return {I_W1G.off + (i - 4) * 2 * img_bytes(64, 40), 64, 40, 64, 48, C_DCONV};  // dconv of position pair i - 4
-}
-
-// Stash addressing: the adjoint kernel (hutter_adj_kernel) reads tile-major blocks of 64 drones,
-// [tile64][rows][TMP] floats.  Row `row` of drone `r128` of tcgen05 tile `tile128` in a stash with `rows` rows:
-APG_HD size_t stash_index(int tile128, int r128, int rows, int row) {
-  const size_t tile64 = (size_t)tile128 * 2 + (r128 >> 6);
-  return (tile64 * rows + row) * TMP + (r128 & 63);
-}
-// x1 row of output n (= position-in-pair * 20 + channel) of the conv block of position pair g: position-major rows
-// 64 + t*20 + c with t = 2g + tl, i.e. 64 + 40 g + n  (layouts.h: conv_cs = 1, conv_ts = 20)
-APG_HD constexpr int x1_row_of_conv(int g, int n) { return HID + 2 * NC * g + n; }
 
 }  // namespace tc
 }  // namespace apg

@@ -36,6 +36,7 @@ void tmem_st32(uint32_t addr, const uint32_t* r);
 void mbar_expect_tx(uint32_t bar, uint32_t bytes);
 void bulk_g2s(uint32_t dst_smem, const void* src_global, uint32_t bytes, uint32_t bar);
 void prefetch_l2(const void* p);
+bool elect_one();
 void wait_st();
 void fence_before_thread_sync();
 void fence_after_thread_sync();
@@ -156,6 +157,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_glob
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_smem),
                "l"(src_global), "r"(bytes), "r"(bar)
                : "memory");
+}
+// one lane of the (converged) warp: the issuing roles run their loops warp-uniformly and predicate only the issuing
+// instruction on this, so that the compiler keeps descriptors and addresses in uniform registers (a lane-0-only branch
+// around the whole loop made every tcgen05.mma cost ~90 issue cycles: measured, profiles/r2)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}\n"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }

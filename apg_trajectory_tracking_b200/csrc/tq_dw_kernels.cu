@@ -54,7 +54,13 @@ __device__ __forceinline__ void dwq_wait(uint32_t bar, uint32_t parity, volatile
     if (tcp::mbar_try_wait(bar, parity)) return;
     if ((spin & 63) == 63) {
       if (*abort_flag) return;
-      if (tcp::clock_now() - t0 > 2000000000LL) { *abort_flag = 1; return; }
+      if (tcp::clock_now() - t0 > 2000000000LL) {
+#ifdef APG_TC_SIM
+        if (getenv("APG_SIM_FAST_TIMEOUT")) fprintf(stderr, "dwq_wait timeout: thread %u bar %x parity %u\n", threadIdx.x, bar, parity);
+#endif
+        *abort_flag = 1;
+        return;
+      }
     }
   }
 }
@@ -78,6 +84,10 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   __shared__ uint32_t s_tmem;
   __shared__ int s_abort;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef APG_PROFILE
+  const long long tqp_k0_ = clock64();
+  long long tqp_k1_ = 0, tqp_k2_ = 0;
+#endif
   const int n = g.N;
   const int ntiles = (n + tc::TMT - 1) / tc::TMT;
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -103,10 +113,14 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   __syncthreads();
   tcp::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
+#ifdef APG_PROFILE
+  tqp_k1_ = clock64();
+#endif
 
   if (warp == 0) {
-    // ===================================================== producer
-    if (lane == 0) {
+    // ===================================================== producer (warp-uniform loop, the elected lane issues)
+    {
+      const bool leader = tcp::elect_one();
       TQP_DECL
       int u = 0;
       for (int j = 0; j < my_tiles; ++j) {
@@ -122,21 +136,25 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
             TQP(0);
             unsigned char* st = base + r * STAGE;
             const uint32_t bar = smem_u32(&s_bars.full[r]);
+            if (leader) {
             tcp::mbar_expect_tx(bar, a_bytes + b_bytes);
             tcp::bulk_g2s(smem_u32(st), fb + tq::set_base(src.a_set) + (size_t)p * (size_t)(src.a_R * 128) +
                                             (size_t)src.a_row0 * 128, a_bytes, bar);
             tcp::bulk_g2s(smem_u32(st + tq::DW_A_BYTES), zb + tq::set_base(src.b_set) +
                                                              (size_t)p * (size_t)(src.b_R * 128) +
                                                              (size_t)src.b_row0 * 128, b_bytes, bar);
+            }
+            __syncwarp();          // lanes stay within one unit of each other (parity waits alias with period 2)
             TQP(1);
           }
         }
       }
-      TQP_FLUSH(2, 0, 2);
+      if (leader) TQP_FLUSH(2, 0, 2);
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer (warp-uniform loop, the elected lane issues)
+    {
+      const bool leader = tcp::elect_one();
       TQP_DECL
       const uint32_t raw0 = smem_u32(base), lo0 = smem_u32(lo_base);
       const uint64_t DESC_HI = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
@@ -148,7 +166,10 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
           const uint32_t d = tmem + op.d_col;
           for (int p = 0; p < tq::NPANEL; ++p, ++u) {
             const int r = u % NR, l = u % NL;
-            dwq_wait(smem_u32(&s_bars.lo_ready[l]), (uint32_t)(u / NL) & 1u, abort_flag);
+            // only the issuing lane polls: lo_ready[l] can complete AGAIN (unit u + NL) as soon as this unit's
+            // MMAs are committed, so a lane that looked late would see the parity it is waiting for already gone
+            if (leader) dwq_wait(smem_u32(&s_bars.lo_ready[l]), (uint32_t)(u / NL) & 1u, abort_flag);
+            __syncwarp();
             TQP(0);
             tcp::fence_after_thread_sync();
             // descriptors: constant high word (SBO 1024, version, SWIZZLE_128B), low word = address >> 4 | LBO field;
@@ -159,17 +180,22 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks, ar += 2, br += 2, al += 2, bl += 2) {
               const uint64_t dah = DESC_HI | ar, dal = DESC_HI | al, dbh = DESC_HI | br, dbl = DESC_HI | bl;
-              tcp::mma_ss(d, dal, dbh, idesc, (ks > 0 || !clear) ? 1u : 0u);
-              tcp::mma_ss(d, dah, dbl, idesc, 1u);
-              tcp::mma_ss(d, dah, dbh, idesc, 1u);
+              if (leader) {
+                tcp::mma_ss(d, dal, dbh, idesc, (ks > 0 || !clear) ? 1u : 0u);
+                tcp::mma_ss(d, dah, dbl, idesc, 1u);
+                tcp::mma_ss(d, dah, dbh, idesc, 1u);
+              }
             }
-            tcp::commit(smem_u32(&s_bars.rfree[r]));      // both stages are free once these MMAs have read them
-            tcp::commit(smem_u32(&s_bars.lo_free[l]));
+            if (leader) {
+              tcp::commit(smem_u32(&s_bars.rfree[r]));    // both stages are free once these MMAs have read them
+              tcp::commit(smem_u32(&s_bars.lo_free[l]));
+            }
+            __syncwarp();          // lanes stay within one unit of each other (parity waits alias with period 2)
             TQP(1);
           }
         }
-      TQP_FLUSH(2, 2, 2);
-      tcp::commit(smem_u32(&s_bars.done));                // all accumulators final
+      if (leader) TQP_FLUSH(2, 2, 2);
+      if (leader) tcp::commit(smem_u32(&s_bars.done));    // all accumulators final
     }
   } else {
     // ===================================================== converters: lo images + constant ones rows
@@ -190,8 +216,19 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
           float4* b_raw = reinterpret_cast<float4*>(base + r * STAGE + tq::DW_A_BYTES);
           float4* a_lo = reinterpret_cast<float4*>(lo_base + l * STAGE);
           float4* b_lo = reinterpret_cast<float4*>(lo_base + l * STAGE + tq::DW_A_BYTES);
-          for (int q = ct; q < na; q += DWQ_CONV) a_lo[q] = lo_of(a_raw[q]);
-          for (int q = ct; q < nb; q += DWQ_CONV) b_lo[q] = lo_of(b_raw[q]);
+          {
+            // all loads first (up to 4 + 2 chunks of 16 bytes per thread), then split and store: one exposed
+            // shared-memory latency per unit instead of six
+            float4 va[4], vb[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (ct + i * DWQ_CONV < na) va[i] = a_raw[ct + i * DWQ_CONV];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) if (ct + i * DWQ_CONV < nb) vb[i] = b_raw[ct + i * DWQ_CONV];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (ct + i * DWQ_CONV < na) a_lo[ct + i * DWQ_CONV] = lo_of(va[i]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) if (ct + i * DWQ_CONV < nb) b_lo[ct + i * DWQ_CONV] = lo_of(vb[i]);
+          }
           if (src.ones >= 0 && ct < 64) {                    // 8-row group [ones, ones + 8): row `ones` = 1, rest 0
             const float v = (ct >> 3) == 0 ? 1.f : 0.f;
             a_raw[src.ones * 8 + ct] = make_float4(v, v, v, v);
@@ -204,6 +241,9 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       }
     if (ct == 0) TQP_FLUSH(2, 4, 3);
   }
+#ifdef APG_PROFILE
+  tqp_k2_ = clock64();
+#endif
 
   // ===================================================== epilogue: accumulators -> this CTA's gradient partial
   // unused tensors (ref_in.*) and padding stay zero; every entry of the partial is written exactly once
@@ -211,28 +251,36 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
     const bool conv_w = i >= y.t_wc && i < y.t_wc + tc::NC * tc::RD * 3 + tc::NC;    // conv_ref weight + bias: below
     if (!conv_w && (my_tiles == 0 || (i >= y.t_wr && i < y.t_br + HID))) P[i] = 0.f;
   }
-  if (my_tiles > 0 && warp >= 2 && warp < 6) {                 // four converter warps, one per TMEM lane quarter
+  if (my_tiles > 0 && warp >= 2) {
+    // the eight converter warps: warp w reads TMEM lanes 32 (w & 3) .. +31 (= A rows) and one half of every region's
+    // columns.  The row -> gradient map (base + column * stride) is worked out ONCE per thread and region - measured:
+    // with the index arithmetic (divisions by 20, the switch of grad_index) inside the element loop on four warps this
+    // epilogue took 73 k cycles, a third of the kernel.
     dwq_wait(smem_u32(&s_bars.done), 0, abort_flag);
     tcp::fence_after_thread_sync();
-    const int r = (warp & 3) * 32 + lane;                      // TMEM lane = A row
+    const int r = (warp & 3) * 32 + lane, half = (warp - 2) >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const float poison = __int_as_float(0x7fc00000);
     float* s_T = reinterpret_cast<float*>(base);               // [37][48] conv Toeplitz block (stage memory is free)
     const int col0[6] = {dw::C_WO, dw::C_W3, dw::C_W2, dw::C_W1A, dw::C_W1B, dw::C_WS};
     const int ncol[6] = {48, 64, 64, 64, 64, 64};
 #pragma unroll
     for (int reg = 0; reg < 6; ++reg) {
-      for (int c0 = 0; c0 < ncol[reg]; c0 += 8) {
+      // entry (r, n) -> P[i0 + n * stride]; i0 < 0: this row is padding in this region
+      const int i0 = dw::grad_index(y, reg, r, 0);
+      const int stride = i0 < 0 ? 0 : dw::grad_index(y, reg, r, 1) - i0;
+      const int nvalid = reg == 0 ? tc::MO : ncol[reg];
+      const int c_lo = half * (ncol[reg] / 2), c_hi = c_lo + ncol[reg] / 2;
+      for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
         uint32_t vb[8];
         tcp::tmem_ld8(lane_addr + col0[reg] + c0, vb);
+        if (i0 >= 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int idx = dw::grad_index(y, reg, r, c0 + q);
-          if (idx >= 0) P[idx] = *abort_flag ? poison : __uint_as_float(vb[q]);
+          for (int q = 0; q < 8; ++q)
+            if (c0 + q < nvalid) P[i0 + (c0 + q) * stride] = __uint_as_float(vb[q]);
         }
       }
     }
-    for (int c0 = 0; c0 < 48; c0 += 8) {
+    for (int c0 = half * 24; c0 < half * 24 + 24; c0 += 8) {
       uint32_t vb[8];
       tcp::tmem_ld8(lane_addr + dw::C_WT + c0, vb);
       if (r <= 4 * tc::RD) {
@@ -253,12 +301,67 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       } else {
         v = dw::conv_bias_from_block(s_T, 48, i - tc::NC * tc::RD * 3);
       }
-      P[y.t_wc + i] = *abort_flag ? __int_as_float(0x7fc00000) : v;
+      P[y.t_wc + i] = v;
     }
+    if (tid == 0 && *abort_flag) P[0] = __int_as_float(0x7fc00000);       // protocol timeout: poison the gradient
   } else {
     for (int i = tid; i < tc::NC * tc::RD * 3 + tc::NC; i += DWQ_THREADS) P[y.t_wc + i] = 0.f;
   }
   if (warp == 0) tcp::tmem_dealloc512(tmem);
+#ifdef APG_PROFILE
+  if (tid == 64 && blockIdx.x < 148) {                       // setup | main loop (converter 0) | epilogue
+    TQ_PROF_ARRAY[2][blockIdx.x][8] = tqp_k1_ - tqp_k0_;
+    TQ_PROF_ARRAY[2][blockIdx.x][9] = tqp_k2_ - tqp_k1_;
+    TQ_PROF_ARRAY[2][blockIdx.x][10] = clock64() - tqp_k2_;
+  }
+#endif
+}
+
+// grad[p] = scale * sum over CTAs of partials[c][p]: 32 parameters x 4 CTA slices per block of 128 threads (fixed
+// order -> bitwise reproducible; the partials are already in torch order)
+__global__ void __launch_bounds__(128) apg_reduce4_kernel(const float* __restrict__ partials, int ncta, int n,
+                                                          float scale, float* __restrict__ grad) {
+  __shared__ float s_part[dw::RED_SLICES][32];
+  const int pl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + pl;
+  int c0, c1;
+  dw::reduce_slice_bounds(ncta, slice, &c0, &c1);
+  s_part[slice][pl] = p < n ? dw::reduce_slice_sum(partials, n, p, c0, c1) : 0.f;
+  __syncthreads();
+  if (slice == 0 && p < n) grad[p] = scale * ((s_part[0][pl] + s_part[1][pl]) + (s_part[2][pl] + s_part[3][pl]));
+}
+
+// the same reduction with the optimizer step of the reference fused in (optim.SGD(momentum), train_base.py:139-143:
+// buf = momentum * buf + g; p -= lr * buf) - one launch instead of the reduction + two element-wise passes
+__global__ void __launch_bounds__(128) apg_reduce4_sgd_kernel(const float* __restrict__ partials, int ncta, int n,
+                                                              float scale, float* __restrict__ grad,
+                                                              float* __restrict__ param, float* __restrict__ buf,
+                                                              float lr, float momentum) {
+  __shared__ float s_part[dw::RED_SLICES][32];
+  const int pl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + pl;
+  int c0, c1;
+  dw::reduce_slice_bounds(ncta, slice, &c0, &c1);
+  s_part[slice][pl] = p < n ? dw::reduce_slice_sum(partials, n, p, c0, c1) : 0.f;
+  __syncthreads();
+  if (slice == 0 && p < n) {
+    const float gsum = scale * ((s_part[0][pl] + s_part[1][pl]) + (s_part[2][pl] + s_part[3][pl]));
+    if (grad) grad[p] = gsum;
+    const float b = momentum * buf[p] + gsum;
+    buf[p] = b;
+    param[p] -= lr * b;
+  }
+}
+
+cudaError_t launch_reduce_grad4_sgd(const float* partials, int ncta, int n, float scale, float* grad, float* param,
+                                    float* buf, float lr, float momentum, cudaStream_t st) {
+  APG_LAUNCH((n + 31) / 32, 128, 0, st, apg_reduce4_sgd_kernel)(partials, ncta, n, scale, grad, param, buf, lr, momentum);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st) {
+  APG_LAUNCH((n + 31) / 32, 128, 0, st, apg_reduce4_kernel)(partials, ncta, n, scale, grad);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_tq_dw(const HutterLayout& y, const RolloutArgs& a, const unsigned char* fstash,

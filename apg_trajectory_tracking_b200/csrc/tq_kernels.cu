@@ -12,7 +12,7 @@
 // served by warps 8s .. 8s+7: warp w owns TMEM lanes 32 (w & 3) .. +31 (= drones of the tile) and the column half
 // (w >> 2) & 1 of every epilogue, so both threads of a drone split each 64-column epilogue 32 / 32 (and 40-column
 // pieces 24 / 16).  Warp 16 lane 0 loads the weight images (bulk copies) and issues every tcgen05.mma.  Hand-off by
-// mbarriers: a_ready[s] (256 arrivals: the A operand of the next op is in TMEM), d_ready[s] (tcgen05.commit).
+// mbarriers: a_ready[s] (8 arrivals, one per warp: the A operand of the next op is in TMEM), d_ready[s] (tcgen05.commit).
 // Why the dynamics are NOT in these kernels: measured (profiles/r2): with the horizon loop on the epilogue threads a
 // quarter of all warp samples sat at the final barrier and only two tiles per SM were ever in the chain; a plain
 // thread-per-drone kernel runs the same loop at full occupancy in a fraction of the time.
@@ -73,16 +73,20 @@ inline float tq_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 #else
 __device__ __forceinline__ float tq_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tq_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// branch-free tanh: odd Taylor polynomial below 0.25 (truncation error 2e-9), 1 - 2 / (exp(2x) + 1) on the SFU above
-// (absolute error <= 3e-7); saturates correctly for large |x|
+// branch-free tanh on the SFU: 1 - 2 / (exp(2x) + 1) (absolute error <= 3e-7, saturates correctly for large |x|);
+// -DTQ_TANH_POLY adds an odd Taylor polynomial below 0.25 (relative accuracy near 0, +6 instructions per element)
 __device__ __forceinline__ float tq_tanh(float x) {
+  const float big = fmaf(-2.f, tq_rcp(tq_ex2(x * 2.885390082f) + 1.f), 1.f);
+#ifdef TQ_TANH_POLY
   const float x2 = x * x;
   float p = fmaf(x2, 0.0218694885f, -0.0539682540f);
   p = fmaf(x2, p, 0.133333333f);
   p = fmaf(x2, p, -0.333333333f);
   const float small = fmaf(x * x2, p, x);
-  const float big = fmaf(-2.f, tq_rcp(tq_ex2(x * 2.885390082f) + 1.f), 1.f);
   return fabsf(x) < 0.25f ? small : big;
+#else
+  return big;
+#endif
 }
 __device__ __forceinline__ float tq_sigmoid(float x) { return tq_rcp(1.f + tq_ex2(x * -1.442695041f)); }
 #endif
@@ -110,10 +114,12 @@ __device__ __forceinline__ void split_bits(float y, uint32_t* hi, uint32_t* lo) 
   *hi = h;
   *lo = __float_as_uint(y - __uint_as_float(h));
 }
+// every lane's TMEM stores are complete and ordered, then ONE lane arrives for the warp (the barriers count 8 warps)
 __device__ __forceinline__ void a_operand_ready(uint32_t bar) {
   tcp::wait_st();
   tcp::fence_before_thread_sync();
-  tcp::mbar_arrive(bar);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) tcp::mbar_arrive(bar);
 }
 // L2 prefetch of the 128-byte lines [first, first + nlines) of a contiguous region, spread over the lanes of a warp
 __device__ __forceinline__ void prefetch_lines(const unsigned char* p, int nlines, int lane) {
@@ -157,14 +163,17 @@ __device__ __forceinline__ OpRec make_oprec(uint32_t whi, uint32_t wlo, int K_im
   r.idesc = idesc_tf32(TMT, N); r.d_col = (uint32_t)d_col; r.ksteps = (uint32_t)(K / 8); r.acc0 = (uint32_t)acc0; r.pad = 0;
   return r;
 }
-__device__ __forceinline__ void issue_series(const OpRec& op, uint32_t slot, uint32_t ahi, uint32_t alo) {
+// executed by the WHOLE issuing warp (uniform values -> uniform registers); only the elected lane issues
+__device__ __forceinline__ void issue_series(const OpRec& op, uint32_t slot, uint32_t ahi, uint32_t alo, bool leader) {
   const uint32_t d = slot + op.d_col;
   uint32_t bh = op.bh_lo, bl = op.bl_lo;
   for (uint32_t ks = 0; ks < op.ksteps; ++ks, bh += 16, bl += 16) {
     const uint64_t dbh = ((uint64_t)op.desc_hi << 32) | bh, dbl = ((uint64_t)op.desc_hi << 32) | bl;
-    tcp::mma_ts(d, alo + ks * 8, dbh, op.idesc, (ks > 0 || op.acc0) ? 1u : 0u);
-    tcp::mma_ts(d, ahi + ks * 8, dbl, op.idesc, 1u);
-    tcp::mma_ts(d, ahi + ks * 8, dbh, op.idesc, 1u);
+    if (leader) {
+      tcp::mma_ts(d, alo + ks * 8, dbh, op.idesc, (ks > 0 || op.acc0) ? 1u : 0u);
+      tcp::mma_ts(d, ahi + ks * 8, dbl, op.idesc, 1u);
+      tcp::mma_ts(d, ahi + ks * 8, dbh, op.idesc, 1u);
+    }
   }
 }
 
@@ -174,7 +183,7 @@ __device__ __forceinline__ uint32_t tq_setup(TqBars& bars, uint32_t* s_tmem, int
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      tcp::mbar_init(smem_u32(&bars.a_ready[s]), 256);
+      tcp::mbar_init(smem_u32(&bars.a_ready[s]), 8);
       tcp::mbar_init(smem_u32(&bars.d_ready[s]), 1);
     }
     tcp::mbar_init(smem_u32(&bars.w_ready), 1);
@@ -224,10 +233,11 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   const int ntiles = (n + TMT - 1) / TMT;
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   volatile int* abort_flag = &s_abort;
-  tq_wait(smem_u32(&s_bars.w_ready), 0, abort_flag);          // weight images + biases have landed
 
   if (warp == TQ_EPI_WARPS) {
-    if (lane == 0) {
+    {
+      const bool leader = tcp::elect_one();
+      tq_wait(smem_u32(&s_bars.w_ready), 0, abort_flag);      // weight images have landed
       // the two slots advance independently: whichever has its next A operand ready gets its next op issued
       uint32_t par[2] = {0, 0};
       int op_i[2] = {0, 0}, tile_j[2] = {0, 1};
@@ -238,15 +248,27 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (tile_j[s] >= my_tiles) continue;
-          if (!tcp::mbar_test_wait(smem_u32(&s_bars.a_ready[s]), par[s])) continue;
+          // warp vote: the decision is uniform by construction (and known to be so by the compiler)
+          if (!__all_sync(0xffffffffu, tcp::mbar_test_wait(smem_u32(&s_bars.a_ready[s]), par[s]))) continue;
           par[s] ^= 1;
           tcp::fence_after_thread_sync();
           const uint32_t slot = tmem + s * SLOT_COLS;
-          issue_series(s_ops[op_i[s]], slot, slot + C_AHI, slot + C_ALO);
-          tcp::commit(smem_u32(&s_bars.d_ready[s]));
+#ifdef APG_PROFILE
+          const bool stamp_ = (leader && s == 0 && tile_j[0] == 0 && op_i[0] == 10 && blockIdx.x < 148);
+          if (stamp_) TQ_PROF_ARRAY[0][blockIdx.x][8] = clock64();          // a_ready observed
+#endif
+          issue_series(s_ops[op_i[s]], slot, slot + C_AHI, slot + C_ALO, leader);
+#ifdef APG_PROFILE
+          if (stamp_) TQ_PROF_ARRAY[0][blockIdx.x][9] = clock64();          // MMAs issued
+#endif
+          if (leader) tcp::commit(smem_u32(&s_bars.d_ready[s]));
+#ifdef APG_PROFILE
+          if (stamp_) TQ_PROF_ARRAY[0][blockIdx.x][10] = clock64();         // commit issued
+#endif
           if (++op_i[s] == NOPS) { op_i[s] = 0; tile_j[s] += 2; }
           --remaining;
           progressed = true;
+          __syncwarp();            // lanes stay within one op of each other (parity tests alias with period 2)
         }
         if (progressed) {
           t_idle = tcp::clock_now();
@@ -285,20 +307,25 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       }
       // D_main columns [32 hf, +32) -> tanh(x + b) -> A operand (hi, lo) + stash rows of set `sp`
       auto dense_epilogue = [&](const float* b, const SetPtr& sp) {
+        TQP(1);
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 16) {                  // 16 columns at a time: register budget (96 / thread)
           uint32_t v[16], l[16];
           tcp::tmem_ld16(d_main + hf * 32 + c0, v);
+          TQP(2);
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const float yv = tq_tanh(__uint_as_float(v[q]) + b[hf * 32 + c0 + q]);
             set_store(sp, hf * 32 + c0 + q, yv);
             split_bits(yv, &v[q], &l[q]);
           }
+          TQP(3);
           tcp::tmem_st16(ahi + hf * 32 + c0, v);
           tcp::tmem_st16(alo + hf * 32 + c0, l);
+          TQP(4);
         }
         a_operand_ready(bar_a);
+        TQP(5);
       };
       // ---- op 0 operand: in_state (15) + 1 (the ones row of the states_in weight gradient; its image column is 0);
       //      this thread's eight columns [8 hf, +8)
@@ -317,6 +344,9 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
         for (int k = 0; k < 8; ++k) set_store(sp, hf * 8 + k, x0[k]);
       }
       const SetPtr sp_x1 = set_ptr(tb, tq::O_X1, tq::R_X1, row);
+      // the first tile's input loads / operand stores above overlap the bulk copy of the weight images; the biases
+      // (same copy) are first needed here
+      if (j == s) tq_wait(smem_u32(&s_bars.w_ready), 0, abort_flag);
       wait_d();                                               // op 0: states_in
       dense_epilogue(s_bias + B_S, sp_x1);                    // s -> X1 rows [0, 64), operand of op 1
       const float* rr = g.in_ref + drone * REFW;
@@ -386,8 +416,17 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
         }
       }
       wait_d();                                               // last fc1 piece
+#ifdef APG_PROFILE
+      if (tid == 0 && j == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][6] = clock64();    // epilogue starts
+#endif
       dense_epilogue(s_bias + B_1, set_ptr(tb, tq::O_H1, tq::R_H, row));
+#ifdef APG_PROFILE
+      if (tid == 0 && j == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][7] = clock64();    // this warp arrived
+#endif
       wait_d();                                               // fc2
+#ifdef APG_PROFILE
+      if (tid == 0 && j == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][11] = clock64();   // d_ready observed
+#endif
       dense_epilogue(s_bias + B_2, set_ptr(tb, tq::O_H2, tq::R_H, row));
       wait_d();                                               // fc3
       dense_epilogue(s_bias + B_3, set_ptr(tb, tq::O_H3, tq::R_H, row));
@@ -410,7 +449,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       // every tcgen05.ld of this tile has completed before the next tile's first A-operand arrival (same threads)
     }
     TQP(1);
-    if (tid == 0) TQP_FLUSH(0, 0, 2);
+    if (tid == 0) TQP_FLUSH(0, 0, 6);
   }
   tcp::fence_before_thread_sync();
   __syncthreads();
@@ -549,7 +588,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   volatile int* abort_flag = &s_abort;
 
   if (warp == TQ_EPI_WARPS) {
-    if (lane == 0) {
+    {
+      const bool leader = tcp::elect_one();
       tq_wait(smem_u32(&s_bars.w_ready), 0, abort_flag);
       uint32_t par[2] = {0, 0};
       int h_i[2] = {0, 0}, tile_j[2] = {0, 1};
@@ -560,16 +600,18 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (tile_j[s] >= my_tiles) continue;
-          if (!tcp::mbar_test_wait(smem_u32(&s_bars.a_ready[s]), par[s])) continue;
+          // warp vote: the decision is uniform by construction (and known to be so by the compiler)
+          if (!__all_sync(0xffffffffu, tcp::mbar_test_wait(smem_u32(&s_bars.a_ready[s]), par[s]))) continue;
           par[s] ^= 1;
           tcp::fence_after_thread_sync();
           const uint32_t slot = tmem + s * tq::SLOT_COLS;
           for (int i = tq::xh_first(h_i[s]); i < tq::xh_first(h_i[s] + 1); ++i)
-            issue_series(s_ops[i], slot, slot + tq::XC_AHI, slot + tq::XC_ALO);
-          tcp::commit(smem_u32(&s_bars.d_ready[s]));
+            issue_series(s_ops[i], slot, slot + tq::XC_AHI, slot + tq::XC_ALO, leader);
+          if (leader) tcp::commit(smem_u32(&s_bars.d_ready[s]));
           if (++h_i[s] == tq::NXH) { h_i[s] = 0; tile_j[s] += 2; }
           --remaining;
           progressed = true;
+          __syncwarp();            // lanes stay within one hand-off of each other
         }
         if (progressed) {
           t_idle = tcp::clock_now();
@@ -690,7 +732,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       }
       pair_epilogue(0, d0 + 64);
       tcp::fence_before_thread_sync();
-      tcp::mbar_arrive(bar_a);                                 // D has been read: go on with the other three pairs
+      __syncwarp();
+      if (lane == 0) tcp::mbar_arrive(bar_a);                  // D has been read: go on with the other three pairs
       wait_d();
       pair_epilogue(1, d0);
       pair_epilogue(2, d0 + 40);
@@ -725,20 +768,25 @@ bool tq_supported(const HutterLayout& y, int h) {
   return y.conv && y.F0 == F0 && y.L == H && y.RD == RD && y.Mo == MO && h == H;
 }
 
-// forward = pack + tensor chain + dynamics / loss / reverse sweep (the loss partials come from the dynamics kernel:
-// tq_dyn_grid(n, sms) of them)
-cudaError_t launch_tq_fwd(const HutterLayout& y, const float* params, unsigned char* blob, unsigned char* tblob,
-                          const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int grid, int dyn_grid,
-                          cudaStream_t st) {
+cudaError_t launch_tq_pack(const HutterLayout& y, const float* params, unsigned char* blob, unsigned char* tblob,
+                           cudaStream_t st) {
   const int items = PAIRS_TOTAL + B_TOTAL + tq::TPAIRS_TOTAL;
   APG_LAUNCH((items + 255) / 256, 256, 0, st, tq_pack_kernel)(params, y, blob, tblob);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(tq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_FWD_SMEM);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tq_fwd(const unsigned char* blob, const RolloutArgs& a, unsigned char* fstash, int grid,
+                          cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_FWD_SMEM);
   if (e != cudaSuccess) return e;
   APG_LAUNCH(grid, TQ_THREADS, TQ_FWD_SMEM, st, tq_fwd_kernel)(blob, a, fstash);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(tq_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
+  return cudaGetLastError();
+}
+
+// dynamics / loss / reverse sweep: writes tq_dyn_grid(n, sms) loss partials
+cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int dyn_grid,
+                          cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(tq_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
   if (e != cudaSuccess) return e;
   APG_LAUNCH(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel)(a, fstash, zstash);
   return cudaGetLastError();

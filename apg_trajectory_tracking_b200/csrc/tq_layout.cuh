@@ -154,7 +154,7 @@ APG_HD DwSrc dw_src(int i) {
 }
 constexpr int DW_A_ROWS = 128, DW_B_ROWS = 64;
 constexpr int DW_A_BYTES = DW_A_ROWS * 128, DW_B_BYTES = DW_B_ROWS * 128;          // one panel image (raw or lo)
-constexpr int DW_NRAW = 7, DW_NLO = 2;                                            // stage rings (tq_dw_kernels.cu)
+constexpr int DW_NRAW = 6, DW_NLO = 3;                                            // stage rings (tq_dw_kernels.cu)
 
 }  // namespace tq
 }  // namespace apg

@@ -105,6 +105,9 @@ class Rollout:
             if n_params < 0:
                 _capi.check(n_params)
             self.n_params = n_params
+            # True: the tcgen05 / TMEM kernels serve this configuration (pack, chain, dynamics, loss sum | dX chain,
+            # dW GEMM, reduce = 7 launches per iteration); False: the tile-engine kernels (5 launches)
+            self.tcgen05 = self.lib.apg_rollout_kernel_path(ctypes.byref(self.cfg)) == 1
             ws = self.lib.apg_workspace_bytes(ctypes.byref(self.cfg))
             self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)
             off = (-self.workspace.data_ptr()) % 256
@@ -135,6 +138,18 @@ class Rollout:
             _capi.check(self.lib.apg_rollout_backward(ctypes.byref(self.cfg), *[_ptr(x) for x in self._inputs],
                                                       self._ws_ptr, ctypes.c_float(float(grad_loss)), _ptr(out),
                                                       self._stream()))
+        return out
+
+    def backward_sgd(self, params_flat, momentum_buf, lr, momentum, grad_loss=1.0, out=None):
+        """Adjoint of the last forward() with the SGD(momentum) update fused into the gradient reduction (tcgen05 path
+        only): ``params_flat`` (the vector the forward read) and ``momentum_buf`` are updated in place."""
+        ins = list(self._inputs)
+        ins[0] = _dev_f32(params_flat, "params")
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.apg_rollout_backward_sgd(ctypes.byref(self.cfg), *[_ptr(x) for x in ins],
+                                                          self._ws_ptr, ctypes.c_float(float(grad_loss)), _ptr(out),
+                                                          _ptr(momentum_buf), ctypes.c_float(float(lr)),
+                                                          ctypes.c_float(float(momentum)), self._stream()))
         return out
 
     def backward_p2p(self, comm, grad_loss=1.0):

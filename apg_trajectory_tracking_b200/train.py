@@ -63,14 +63,17 @@ class FusedTrainStep:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size(process_group) > 1
         self.distributed = distributed
-        self.kernel_launches_per_step = 5      # pack, forward, loss-sum, adjoint, grad-reduce
+        # own kernels per iteration: pack, forward, loss-sum, adjoint, grad-reduce (tile-engine kernels) or pack,
+        # forward chain, dynamics, loss-sum, dX chain, dW GEMM, grad-reduce (tcgen05 path); the SGD update adds two torch
+        # element-wise launches, N > 1 one NCCL all-reduce kernel
+        self.kernel_launches_per_step = 7 if self.runner.tcgen05 else 5
         if peer_exchange is None:
             peer_exchange = os.environ.get("APG_P2P_GRAD") == "1"
         self.peer = None
         if peer_exchange and self.distributed:
             from . import dist as D
             self.peer = D.PeerGradExchange(self.runner.n_params, self.device, process_group)
-            self.kernel_launches_per_step = 6  # + the gather / SGD kernel (the exchange rides on the grad-reduce)
+            self.kernel_launches_per_step += 1  # + the gather / SGD kernel (the exchange rides on the grad-reduce)
 
     def _dev(self, x):
         if x is None:
@@ -104,6 +107,12 @@ class FusedTrainStep:
             loss = self._forward_and_scatter(in_state, cur, in_ref, ref, h0c0)
             self.peer.gather(*self._peer_step, grad_out=self.grad, params=self.flat, momentum_buf=self.buf,
                              lr=self.lr, momentum=self.momentum)
+            return loss
+        if self.runner.tcgen05 and not self.distributed:
+            # single device, tcgen05 path: the optimizer step rides on the gradient reduction (one launch)
+            loss, _, _ = self.runner.forward(self.flat, self._dev(in_state), self._dev(cur), self._dev(in_ref),
+                                             self._dev(ref), self._dev(h0c0))
+            self.runner.backward_sgd(self.flat, self.buf, self.lr, self.momentum, out=self.grad)
             return loss
         loss, grad = self.value_and_grad(in_state, cur, in_ref, ref, h0c0)
         # optim.SGD(momentum=0.9): buf = momentum*buf + g ; p -= lr*buf   (first step: buf = g)

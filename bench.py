@@ -274,7 +274,7 @@ def measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier):
     sink += prev.item()
     barrier()
     t_async = agree((time.perf_counter() - t0) / e2e_steps, "MAX")
-    t = min(t_sync, t_async)
+    t = t_sync                          # headline: every step's loss is read before the next step is issued
     return {"ok": True, "value": world * n * h / t, "unit": "drone-steps/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": 4, "steps": e2e_steps, "chunk": chunk if chunk else n,
             "chunk_candidates_ms": {str(c if c else n): round(v * 1e3, 4) for c, v in times.items()}, "check": check,
@@ -282,7 +282,8 @@ def measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier):
             "value_loss_read_one_step_late": world * n * h / t_async,
             "api": "apg_trajectory_tracking_b200.train.FusedTrainStep.step_host / step_host_async(raw host samples): "
                    "chunked H2D on a copy stream overlapped with prepare + forward + adjoint of the previous chunk; "
-                   "value = the faster of reading each loss right away and reading it one step late"}
+                   "value = loss read on the host after EVERY step (value_loss_read_one_step_late: the pipelined "
+                   "variant, reported next to it)"}
 
 
 def physical_cores():
@@ -330,7 +331,7 @@ def run_reference(args, w, rank):
         "impl": "reference", "metric": "drone-steps/sec (fwd+bwd)", "value": value, "unit": "drone-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["label"].replace("/GPU", " (one host)"), "horizon": w["h"], "n_drones": n,
+        "config": {"workload": w["label"], "horizon": w["h"], "n_drones": n,
                    "note": "CPU arm: oracle port of the reference's PyTorch op chain (autograd tape) + SGD step"},
         "cpu_baseline": {"value": value, "unit": "drone-steps/s", "cores": threads, "kind": "port",
                          "sample": f"N={n} drones x h={w['h']} per step, {args.steps} iterations"},
@@ -354,12 +355,8 @@ def main():
     ap.add_argument("--p2p-grad", action="store_true",
                     help="N>1: exchange the gradient with the package's own kernels over NVLink peer memory "
                          "(APG_P2P_GRAD=1) instead of the NCCL all-reduce")
-    ap.add_argument("--tc-forward", action="store_true",
-                    help="use the optional tcgen05/TMEM forward kernel (APG_TC_FWD=1; quad_concurrent only)")
-    ap.add_argument("--tc-dw", action="store_true",
-                    help="use the optional split adjoint: mma.sync dX chain + tcgen05 streaming dW GEMM (APG_TC_DW=1)")
-    ap.add_argument("--tc-dx", action="store_true",
-                    help="split adjoint with the dX chain on tcgen05 as well (APG_TC_DW=1 APG_TC_DX=1)")
+    ap.add_argument("--legacy-mma", action="store_true",
+                    help="quad_concurrent: run the mma.sync kernels (APG_LEGACY_MMA=1) instead of the tcgen05 path")
     args = ap.parse_args()
     # hard wall-clock bound for the whole process: dump the Python stacks and exit instead of hanging a GPU box
     faulthandler.dump_traceback_later(int(os.environ.get("APG_BENCH_WATCHDOG_S", "1500")), exit=True)
@@ -375,13 +372,8 @@ def main():
         return
     if args.p2p_grad:
         os.environ["APG_P2P_GRAD"] = "1"
-    if args.tc_forward:
-        os.environ["APG_TC_FWD"] = "1"
-    if args.tc_dw:
-        os.environ["APG_TC_DW"] = "1"
-    if args.tc_dx:
-        os.environ["APG_TC_DW"] = "1"
-        os.environ["APG_TC_DX"] = "1"
+    if args.legacy_mma:
+        os.environ["APG_LEGACY_MMA"] = "1"
 
     if args.warmup < 3:
         args.warmup = 3
@@ -436,6 +428,10 @@ def main():
             e[2].record()
             stepper.peer.gather(comm, local_set, grad_out=stepper.grad, params=stepper.flat,
                                 momentum_buf=stepper.buf, lr=stepper.lr, momentum=stepper.momentum)
+        elif stepper.runner.tcgen05 and world == 1:
+            # tcgen05 path, one device: the SGD(momentum) update rides on the gradient reduction (one launch)
+            stepper.runner.backward_sgd(stepper.flat, stepper.buf, stepper.lr, stepper.momentum, out=stepper.grad)
+            e[2].record()
         else:
             stepper.runner.backward(1.0, out=stepper.grad)
             e[2].record()
@@ -458,6 +454,28 @@ def main():
     barrier()
     clocks = sampler.stop()
     clocks["note"] = f"sampled over warm-up + timed region + {extra_steps} identical untimed steps"
+    # ---- per-kernel device times of the tcgen05 path (CUDA events between the launches inside the C-ABI calls,
+    #      apg_debug_timing): 10 extra steps, outside every timed region, L2 flushed before each like the timed steps
+    kernel_ms = None
+    if stepper.runner.tcgen05 and stepper.peer is None:
+        import ctypes
+        import numpy as np
+        from apg_trajectory_tracking_b200 import _capi
+        lib = _capi.lib()
+        lib.apg_debug_timing(1)
+        acc, reps = np.zeros(7), 10
+        for _ in range(reps):
+            if flush_buf is not None:
+                flush_buf.zero_()
+            stepper.runner.forward(stepper.flat, *args_step)
+            stepper.runner.backward(1.0, out=stepper.grad)
+            out = np.zeros(7, np.float32)
+            _capi.check(lib.apg_debug_kernel_times(ctypes.c_void_p(out.ctypes.data)))
+            acc += out
+        lib.apg_debug_timing(0)
+        names = ["tq_pack_kernel", "tq_fwd_kernel", "tq_dyn_kernel", "apg_sum_loss_kernel", "tq_dx_kernel",
+                 "tq_dw_kernel", "apg_reduce4_kernel"]
+        kernel_ms = {k: float(v) / reps for k, v in zip(names, acc)}
     t_step = [e[0].elapsed_time(e[3]) for e in ev]
     t_fwd = [e[0].elapsed_time(e[1]) for e in ev]
     t_adj = [e[1].elapsed_time(e[2]) for e in ev]
@@ -508,10 +526,7 @@ def main():
     # ---- end-to-end from RAW host samples (input side on the device, chunked H2D overlapped with the kernels).
     #      Runs last and guarded: whatever happens here, the line below still carries the measurements above.
     e2e_raw = None
-    if world > 1 and os.environ.get("APG_BENCH_RAW_E2E_MULTI") != "1":
-        # every step of this arm contains collectives; until it has run once on a multi-GPU box it stays opt-in there
-        e2e_raw = {"ok": False, "skipped": "raw-sample e2e arm runs at N=1 (APG_BENCH_RAW_E2E_MULTI=1 enables it at N>1)"}
-    elif not args.no_raw_e2e:
+    if not args.no_raw_e2e:
         try:
             e2e_raw = measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier)
         except Exception as ex:                                   # noqa: BLE001 - reported in the JSON line
@@ -519,71 +534,96 @@ def main():
 
     if rank == 0:
         peak, peak_src, _ = measured_peaks()
-        # dominant kernel = the adjoint kernel (+ its tiny gradient-reduce epilogue launch): it re-reads every
-        # per-drone input once -> algorithmic bytes per launch = half of the fwd+bwd per-step figure
-        adj_bytes = 0.5 * w["bytes_per_step"] * n * h
-        kname = {"concurrent": "hutter_adj_kernel", "autoregressive": "rec_adj_kernel", "lstm": "lstm_adj_kernel"}[
-            w.get("mode", "concurrent")] if w["system"] != "cartpole" else "simple_adj_kernel"
-        achieved = adj_bytes / (ms_adj * 1e-3) / 1e9
+        tq = stepper.runner.tcgen05
+        mode = w.get("mode", "concurrent")
+        sm_max = clocks.get("sm_max_mhz") or 1965.0
+        _, _, pk = measured_peaks()
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        if tq:
+            fwd_name = "tq_fwd_kernel (tcgen05/TMEM policy chain) + tq_dyn_kernel (thread-per-drone dynamics, loss, reverse sweep)"
+            adj_name = "tq_dx_kernel (tcgen05/TMEM dX chain) + tq_dw_kernel (tcgen05/TMEM streaming dW GEMM)"
+            # dominant kernel = the longest launch of the step; algorithmic bytes of the adjoint pass (the
+            # per-drone inputs read once = half of the fwd+bwd per-step figure) over ITS duration
+            if kernel_ms is not None:
+                dom = max(("tq_fwd_kernel", "tq_dyn_kernel", "tq_dx_kernel", "tq_dw_kernel"), key=lambda k: kernel_ms[k])
+                dom_ms = kernel_ms[dom]
+            else:
+                dom, dom_ms = "tq_dx_kernel + tq_dw_kernel (adjoint pass)", ms_adj
+            rows_f, rows_z = 632, 456                       # stash rows per drone (tq_layout.cuh F_ROWS / Z_ROWS), fp32
+            model = {"tq_fwd_kernel": (15 + 90) * 4 + rows_f * 4, "tq_dyn_kernel": (12 + 90 + 40 + 40) * 4,
+                     "tq_dx_kernel": (40 + 416 + 416) * 4, "tq_dw_kernel": (rows_f - 40 + rows_z) * 4}
+        else:
+            fwd_name = adj_name = "tile-engine kernels (mma.sync 3xTF32 / FFMA)"
+            dom = {"concurrent": "hutter_adj_kernel", "autoregressive": "rec_adj_kernel", "lstm": "lstm_adj_kernel"}[
+                mode] if w["system"] != "cartpole" else "simple_adj_kernel"
+            dom_ms, model = ms_adj, {}
+        alg_bytes = 0.5 * w["bytes_per_step"] * n * h
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.workload, {}).get("adjoint_dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
             except Exception:
                 traffic = None
-        sm_max = clocks.get("sm_max_mhz") or 1965.0
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
-        # legacy-path tensor rate measured on this pool (tools/micro/rates.cu): mma.sync m16n8k8 tf32 = 476 MAC/clk/SM;
-        # the kernels spend 3 tensor instructions per product (3xTF32) -> fp32-equivalent peak = a third of that
-        mma_tf32_peak = 148 * 476 * 2 * sm_max * 1e6 / 1e12
+        flops = w["flops_per_step"] * n * h
+        if tq:
+            tf32_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1650.0))) / 2.0
+            rc = {"bound": "tensor (tcgen05 kind::tf32, 3xTF32 split = 3 tensor instructions per fp32-level product)",
+                  "achieved": flops / (ms_fwd + ms_adj) / 1e9, "peak": tf32_peak / 3.0,
+                  "unit": "TFLOP/s (fp32-equivalent algorithmic flops)",
+                  "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32) / 3 (3xTF32); fp32 FFMA peak "
+                                 "for reference: %.1f TFLOP/s" % fp32_peak}
+        else:
+            mma_tf32_peak = 148 * 476 * 2 * sm_max * 1e6 / 1e12
+            rc = {"bound": "tensor (mma.sync tf32, 3xTF32 split = 3 instructions per product)",
+                  "achieved": flops / (ms_fwd + ms_adj) / 1e9, "peak": mma_tf32_peak / 3.0,
+                  "unit": "TFLOP/s (fp32-equivalent algorithmic flops)",
+                  "peak_source": "measured mma.sync m16n8k8 tf32 rate 476 MAC/clk/SM x 148 SM x clocks.max.sm / 3 "
+                                 "(tools/micro/rates.cu); fp32 FFMA peak for reference: %.1f TFLOP/s" % fp32_peak}
+        rc["frac"] = rc["achieved"] / rc["peak"]
+        own = stepper.kernel_launches_per_step
+        fused_sgd = tq and world == 1 and stepper.peer is None
         line = {
             "metric": "drone-steps/sec (fwd+bwd)", "value": value, "unit": "drone-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["label"], "horizon": h, "n_drones_per_gpu": n, "n_drones_total": n * world,
-                       "forward_kernel": "hutter_fwd_tc_kernel (tcgen05/TMEM)" if os.environ.get("APG_TC_FWD") == "1"
-                       and args.workload == "quad_concurrent" else "default (mma.sync)",
-                       "adjoint_kernel": ("hutter_adj_dx_tc_kernel" if os.environ.get("APG_TC_DX") == "1" else
-                                          "hutter_adj_dx_kernel") + " + adj_dw_tc_kernel (tcgen05/TMEM)"
-                       if os.environ.get("APG_TC_DW") == "1" and args.workload == "quad_concurrent" else "default (mma.sync)",
-                       "policy_init": "torch default init, seed 0", "optimizer": "SGD lr %g momentum 0.9" % LR[w["system"]],
+                       "forward_kernel": fwd_name, "adjoint_kernel": adj_name,
+                       "policy_init": "torch default init, seed 0", "optimizer": "SGD lr %g momentum 0.9" % LR[w["system"]]
+                       + (" (fused into the gradient reduction kernel)" if fused_sgd else " (two torch element-wise launches)"),
                        "l2": "flushed between timed steps (256 MiB write, untimed)" if flush_buf is not None else "not flushed",
                        "parallelism": f"dp{world} (drone-axis shards, " + (
                            "gradient exchanged by apg_reduce_scatter_p2p_kernel / apg_gather_sgd_p2p_kernel over "
                            "NVLink peer memory)" if stepper.peer is not None else
-                           "one NCCL sum-allreduce of the flat gradient)")},
+                           ("one NCCL sum-allreduce of the flat gradient)" if world > 1 else "single device, no collective)"))},
             "ms_forward_kernel": ms_fwd, "ms_adjoint_kernel": ms_adj, "wall_s_timed_region": t_wall,
             "final_loss": final_loss,
-            "roofline": {"bound": "hbm", "kernel": f"adjoint ({kname} + apg_reduce_kernel)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src,
-                         "note": "algorithmic bytes = per-drone inputs read once by the adjoint pass; traffic = ncu dram "
-                                 "bytes of one adjoint launch (it reads the 2.3 KB/drone activation stash); the path "
-                                 "is compute bound (arithmetic intensity ~100 flop/B), see roofline_compute"},
-            "roofline_compute": {"bound": "tensor (mma.sync tf32, 3xTF32 split = 3 instructions per product)",
-                                 "achieved": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9,
-                                 "peak": mma_tf32_peak / 3.0, "unit": "TFLOP/s (fp32-equivalent algorithmic flops)",
-                                 "frac": w["flops_per_step"] * n * h / (ms_fwd + ms_adj) / 1e9 / (mma_tf32_peak / 3.0),
-                                 "peak_source": "measured mma.sync m16n8k8 tf32 rate 476 MAC/clk/SM x 148 SM x "
-                                                "clocks.max.sm / 3 (tools/micro/rates.cu); fp32 FFMA peak for "
-                                                "reference: %.1f TFLOP/s" % fp32_peak},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "ms_kernel": dom_ms,
+                         "note": "algorithmic bytes = the per-drone inputs read once by the adjoint pass (SURVEY 8d: "
+                                 "828 B per drone for this workload) over the duration of the dominant launch; "
+                                 "traffic = ncu dram bytes of one launch of that kernel (profiles/ncu_traffic.json); "
+                                 "the kernels move more than the algorithmic bytes by design (operand-image stash, "
+                                 "see roofline_stash); the path as a whole is compute / latency bound, see "
+                                 "roofline_compute"},
+            "roofline_compute": rc,
             "e2e": {"value": e2e_value, "unit": "drone-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "api": "apg_trajectory_tracking_b200.train.FusedTrainStep.step(host tensors)"},
-            "gpu_launches": stepper.kernel_launches_per_step * args.steps,
+            "gpu_launches": own * args.steps,
+            "launches_per_step": {"own_kernels": own, "torch_elementwise": 0 if (fused_sgd or stepper.peer is not None) else 2,
+                                  "nccl": 1 if (world > 1 and stepper.peer is None) else 0,
+                                  "memset_nodes": 1 if tq else 0},
             "clocks": clocks,
         }
-        tc_on = [k for k in ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX") if os.environ.get(k) == "1"]
-        if tc_on and args.workload == "quad_concurrent":
-            # optional tcgen05 kernels in use: quote the compute roofline against the tcgen05 TF32 rate instead
-            # (half of the measured dense bf16 rate; three tensor instructions per fp32-level product)
-            _, _, pk = measured_peaks()
-            tf32_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1650.0))) / 2.0
-            rc = line["roofline_compute"]
-            rc.update({"bound": "tensor (tcgen05 kind::tf32, 3xTF32 split; kernels: %s)" % ",".join(tc_on),
-                       "peak": tf32_peak / 3.0, "frac": rc["achieved"] / (tf32_peak / 3.0),
-                       "peak_source": "MEASURED_PEAKS.json dense bf16 rate / 2 (tf32) / 3 (3xTF32)"})
-            line["gpu_launches"] = (stepper.kernel_launches_per_step + len(tc_on)) * args.steps
+        if kernel_ms is not None:
+            line["kernel_ms"] = kernel_ms
+            # how close each kernel is to the HBM roof on the bytes it moves BY CONSTRUCTION (stash sets it reads /
+            # writes + per-drone inputs; model, per drone x N) - the streaming dW GEMM is the HBM-bound one
+            line["roofline_stash"] = {k: {"model_bytes": model[k] * n, "GB/s": model[k] * n / (kernel_ms[k] * 1e-3) / 1e9,
+                                          "frac_of_hbm_peak": model[k] * n / (kernel_ms[k] * 1e-3) / 1e9 / peak}
+                                      for k in model}
         if e2e_raw is not None:
             # the raw-sample path is the headline e2e when it ran, matched the prepared-input path and is faster;
             # the prepared-input measurement is kept next to it

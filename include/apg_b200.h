@@ -72,6 +72,15 @@ int apg_rollout_backward(const apg_config* cfg, const float* params, const float
                          const float* in_ref, const float* ref, const float* h0c0, void* workspace,
                          float grad_loss, float* grad_params, void* stream);
 
+/* apg_rollout_backward with the reference's optimizer step fused into the gradient reduction (optim.SGD(momentum=...),
+ * scripts/train_base.py:139-143: buf = momentum * buf + g; p -= lr * buf).  `params_rw` (the vector the forward read) and
+ * `momentum_buf` are updated in place; `grad_params` may be NULL.  Only for configurations served by the tcgen05 path
+ * (apg_rollout_kernel_path(cfg) == 1); APG_ERR_UNSUPPORTED otherwise. */
+int apg_rollout_backward_sgd(const apg_config* cfg, float* params_rw, const float* in_state, const float* cur,
+                             const float* in_ref, const float* ref, const float* h0c0, void* workspace,
+                             float grad_loss, float* grad_params, float* momentum_buf, float lr, float momentum,
+                             void* stream);
+
 /* One train-step evaluation with HOST buffers: H2D of params and inputs, forward, backward, D2H of the loss and
  * the gradient, synchronous.  Device buffers are cached inside the library between calls. */
 int apg_rollout_value_and_grad_host(const apg_config* cfg, const float* params_host, const float* in_state_host,
@@ -227,6 +236,12 @@ int apg_grad_gather_sgd_p2p(const apg_grad_comm* comm, const void* local_set, in
 
 int apg_sm_count(void);
 int apg_version(void);
+/* Optional per-kernel device timing of the tcgen05 path (CUDA events between the launches of the last forward +
+ * backward): ms_out[7] = pack, forward chain, dynamics + reverse sweep, loss sum, dX chain, dW GEMM, gradient reduce. */
+/* 1: apg_rollout_forward / backward run the tcgen05 / TMEM kernels for this configuration, 0: the mma.sync ones */
+int apg_rollout_kernel_path(const apg_config* cfg);
+int apg_debug_timing(int enable);
+int apg_debug_kernel_times(float* ms_out);
 const char* apg_error_string(int code);
 
 #ifdef __cplusplus

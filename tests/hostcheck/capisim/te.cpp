@@ -5,7 +5,6 @@
 #include "../../../apg_trajectory_tracking_b200/csrc/misc_kernels.cu"
 #include "../../../apg_trajectory_tracking_b200/csrc/prep_kernels.cu"
 #include "../../../apg_trajectory_tracking_b200/csrc/hutter_kernels.cu"
-#include "../../../apg_trajectory_tracking_b200/csrc/hutter_adjdx_kernels.cu"
 #include "../../../apg_trajectory_tracking_b200/csrc/eval_kernels.cu"
 #include "../../../apg_trajectory_tracking_b200/csrc/simple_kernels.cu"
 #include "../../../apg_trajectory_tracking_b200/csrc/learnt_kernels.cu"

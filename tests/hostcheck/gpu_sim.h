@@ -200,6 +200,18 @@ static inline int __syncthreads_or(int pred) {
   st.cta_barrier->arrive_and_wait();
   return r;
 }
+// warp vote: true iff the predicate holds on every lane of the warp
+static inline int __all_sync(unsigned, int pred) {
+  sim::State& st = sim::S();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  st.warp_buf[w][l] = pred ? 1.f : 0.f;
+  st.warp_barrier[w]->arrive_and_wait();
+  int all = 1;
+  for (size_t i = 0; i < 32 && 32 * (size_t)w + i < blockDim.x; ++i) all &= st.warp_buf[w][i] != 0.f;
+  st.warp_barrier[w]->arrive_and_wait();
+  return all;
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { sim::S().warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 static inline void __trap() { sim::fail("__trap()"); throw std::runtime_error("__trap"); }
 static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   sim::State& st = sim::S();

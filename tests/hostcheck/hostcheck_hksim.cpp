@@ -1,12 +1,10 @@
 // Test-only: the concurrent hutter rollout kernels THEMSELVES on the CPU model of te_sim.h (-DAPG_SIM, unchanged
 // sources): hutter_fwd_kernel / hutter_adj_kernel (csrc/hutter_kernels.cu - GPU-verified, so this run also validates
-// the MODEL: warp specialisation, named barrier, mbarrier hand-offs, TMA bulk loads / stores, mma fragments) and the
-// optional split adjoint's first half hutter_adj_dx_kernel (csrc/hutter_adjdx_kernels.cu, not yet run on hardware).
+// the MODEL: warp specialisation, named barrier, mbarrier hand-offs, TMA bulk loads / stores, mma fragments).
 #define APG_SIM 1
 #include "te_sim.h"
 
 #include "../../apg_trajectory_tracking_b200/csrc/hutter_kernels.cu"
-#include "../../apg_trajectory_tracking_b200/csrc/hutter_adjdx_kernels.cu"
 #include "../../apg_trajectory_tracking_b200/csrc/pack_tables.h"
 
 using namespace apg;
@@ -113,17 +111,6 @@ extern "C" int hc_hksim_adjoint(const float* params, const float* in_state, cons
   Ctx c = make_ctx(params, in_state, cur, in_ref, ref, n, h, dt, pc, st_x1, st_h1, st_h2, st_h3, st_act, st_states);
   c.a.wf = c.wf.data(); c.a.wb = c.wb.data(); c.a.grad_partials = grad_partials;
   return run(grid, NTH, [&]() { hutter_adj_kernel<Quad, true>(c.y, c.a); }, err, err_len);
-}
-
-// hutter_adj_dx_kernel<Quad, true><<<grid, 320>>>: dZ stash for adj_dw_tc_kernel
-extern "C" int hc_hksim_adj_dx(const float* params, const float* in_state, const float* cur, const float* in_ref,
-                               const float* ref, int n, int h, float dt, const float* pc, int grid, float* st_x1,
-                               float* st_h1, float* st_h2, float* st_h3, float* st_act, float* st_states, float* dzo,
-                               float* dz3, float* dz2, float* dz1, float* dzx, char* err, int err_len) {
-  Ctx c = make_ctx(params, in_state, cur, in_ref, ref, n, h, dt, pc, st_x1, st_h1, st_h2, st_h3, st_act, st_states);
-  c.a.wf = c.wf.data(); c.a.wb = c.wb.data();
-  DzStash z{dzo, dz3, dz2, dz1, dzx};
-  return run(grid, NTH_DX, [&]() { hutter_adj_dx_kernel<Quad, true>(c.y, c.a, z); }, err, err_len);
 }
 
 // torch entry p of the fc1 block <- kernel (position-major) column, as apg_reduce_kernel maps it

@@ -46,7 +46,11 @@ extern "C" int hc_tq_step(const float* params, const float* in_state, const floa
   a.loss_partials = loss_partials; a.grad_partials = grad_partials; a.states_out = states_out; a.actions_out = actions_out;
   unsigned char stamp[16];
   memset(stamp, 3, sizeof stamp);
-  if (stages >= 1) launch_tq_fwd(y, params, blob, tblob, a, fstash, zstash, grid, dyn_grid, nullptr);
+  if (stages >= 1) {
+    launch_tq_pack(y, params, blob, tblob, nullptr);
+    launch_tq_fwd(blob, a, fstash, grid, nullptr);
+    launch_tq_dyn(a, fstash, zstash, dyn_grid, nullptr);
+  }
   if (stages >= 2) launch_tq_dx(tblob, a, fstash, zstash, stamp, 3, grid, nullptr);
   if (stages >= 3) launch_tq_dw(y, a, fstash, zstash, grid, nullptr);
   return report(err, err_len);

@@ -5,7 +5,7 @@ of tests/hostcheck (gpu_sim.h, te_sim.h, tc_sim.h); a canary behind the requeste
 kernels that write past the size their launcher computed.  The product's own Python wrappers are pointed at that
 library ("device" pointers = host pointers), so the tests below are the GPU parity tests in miniature - what they
 add over the per-kernel model tests is the host side: argument checks, workspace plan offsets, weight packing by the
-real pack kernel, kernel selection by configuration and by the APG_TC_* / peer-exchange switches."""
+real pack kernels, kernel selection by configuration and by the APG_LEGACY_MMA / peer-exchange switches."""
 import contextlib
 import ctypes
 import os
@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def simlib_path(tmp_path_factory):
     tmp = tmp_path_factory.mktemp("capisim")
     objs = []
-    for name in ("host", "te", "tc", "dw", "tq"):
+    for name in ("host", "te", "tq"):
         obj = tmp / f"{name}.o"
         subprocess.check_call(["g++", "-O1", "-c", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
                                "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
@@ -66,8 +66,7 @@ def simlib(simlib_path, monkeypatch):
     for mod in (ops, PR, EV, QT):
         monkeypatch.setattr(mod, "_require_cuda", lambda *a, **k: None, raising=False)
         monkeypatch.setattr(mod, "_stream", lambda t: ctypes.c_void_p(0), raising=False)
-    for k in ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX"):
-        monkeypatch.delenv(k, raising=False)
+    monkeypatch.delenv("APG_LEGACY_MMA", raising=False)
     if os.environ.get("APG_SIM_POISON_SMEM"):
         # stress run: the workspace (stashes, partials, packed weights) starts as NaN patterns, like recycled HBM may
         real_init = R.Rollout.__init__
@@ -101,9 +100,7 @@ def _check(loss, grad, params, want, tol=5e-5):
 
 
 _SLOW = pytest.mark.slow
-@pytest.mark.parametrize("flags", [(), pytest.param(("APG_TC_FWD",), marks=_SLOW), pytest.param(("APG_TC_DW",), marks=_SLOW),
-                                   pytest.param(("APG_TC_DW", "APG_TC_DX"), marks=_SLOW),
-                                   ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX")])
+@pytest.mark.parametrize("flags", [(), ("APG_LEGACY_MMA",)])
 def test_rollout_forward_backward_through_the_c_abi_all_kernel_selections(simlib, monkeypatch, flags):
     """apg_rollout_forward + apg_rollout_backward, quadrotor concurrent, 100 drones on a 3-SM model: the default
     mma.sync kernels and every combination of the optional tcgen05 paths give the oracle's loss and gradient"""

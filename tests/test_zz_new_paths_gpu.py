@@ -1,6 +1,6 @@
 """GPU tests of everything built after the round-1 GPU budget was spent: the input side of the path (SURVEY.md 8f N1 /
 N4: dataset layouts on the device, chunked host-batch train step, device-resident dataset), the closed-loop evaluation
-rollouts (N2, quadrotor + fixed wing), the learnt residual dynamics (N3) and the optional tcgen05 forward kernel.
+rollouts (N2, quadrotor + fixed wing), the learnt residual dynamics (N3) and the tcgen05 path against the mma.sync one.
 The file name sorts last on purpose: under `pytest -x` these run after every previously verified parity test.
 
 Tolerances (fp32): subtraction-only outputs bit-exact; outputs that go through sin/cos/sqrt/div 2e-6 of scale;
@@ -646,13 +646,12 @@ def test_cartpole_balance_batched_vs_oracle():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# optional split adjoint (APG_TC_DW=1): mma.sync dX chain + dZ stash (hutter_adj_dx_kernel), then the weight gradient
-# as a streaming tcgen05 GEMM over the drone axis (adj_dw_tc_kernel) -- same gradient as the default adjoint
+# The tcgen05 / TMEM path (tq_kernels.cu, tq_dw_kernels.cu) is the DEFAULT path of the quadrotor concurrent rollout;
+# the mma.sync kernels (APG_LEGACY_MMA=1) are an independent second implementation of the same math: both must give
+# the same loss / actions / states / gradient, for ragged sizes down to one drone and up to several tiles per SM.
+# (Both are also checked against the oracle and the reference goldens in tests/test_gpu_parity.py.)
 # ---------------------------------------------------------------------------------------------------------------
-def _check_split_adjoint(n, flags):
-    """APG_TC_DW: mma.sync dX chain + tcgen05 dW GEMM; + APG_TC_DX: the dX chain on tcgen05 too (forward weight images
-    read MN-major); + APG_TC_FWD: the tcgen05 forward writes the stash"""
-    import os
+def _check_tcgen05_vs_legacy(n):
     import bench as B
     PR, R, SY, T, DS = _mods()
     h, dt = 10, 0.1
@@ -663,39 +662,36 @@ def _check_split_adjoint(n, flags):
 
     def run():
         r = R.Rollout(spec, n, "cuda:0")
-        loss, _, _ = r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
+        loss, states, actions = r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"],
+                                          want_states=True, want_actions=True)
         grad = r.backward(1.0)
         grad2 = r.backward(0.5)                      # the adjoint can be repeated and scales with grad_loss
         torch.cuda.synchronize()
-        return float(loss.item()), grad.cpu(), grad2.cpu()
-    all_flags = ("APG_TC_FWD", "APG_TC_DW", "APG_TC_DX")
-    for k in all_flags:
-        os.environ.pop(k, None)
-    l0, g0, _ = run()
-    for k in flags:
-        os.environ[k] = "1"
+        return float(loss.item()), states.cpu(), actions.cpu(), grad.cpu(), grad2.cpu()
+    os.environ["APG_LEGACY_MMA"] = "1"
     try:
-        l1, g1, g1h = run()
+        l0, s0, a0, g0, _ = run()
     finally:
-        for k in all_flags:
-            os.environ.pop(k, None)
+        os.environ.pop("APG_LEGACY_MMA", None)
+    l1, s1, a1, g1, g1h = run()
+    # one message with every diagnostic: a failure here is the only feedback a GPU run gives
     like = [torch.empty_like(p) for p in params]
     per_tensor = [round(rel_err(a, b), 7) if float(b.norm()) > 0 else float(a.abs().max())
                   for a, b in zip(R.split_flat(g1, like), R.split_flat(g0, like))]
-    diag = dict(n=n, flags=flags, loss_default=l0, loss=l1, grad_nan=int(torch.isnan(g1).sum()),
+    diag = dict(n=n, loss_legacy=l0, loss_tcgen05=l1, grad_nan=int(torch.isnan(g1).sum()),
+                actions_max_abs=float((a1 - a0).abs().max()), states_max_abs=float((s1 - s0).abs().max()),
                 grad_rel=rel_err(torch.nan_to_num(g1), g0), grad_rel_per_tensor=per_tensor,
                 half_scale_rel=rel_err(2.0 * torch.nan_to_num(g1h), torch.nan_to_num(g1)))
     assert np.isfinite(l1) and bool(torch.isfinite(g1).all()), f"tcgen05 kernel reported a protocol timeout (NaN): {diag}"
-    ok = abs(l1 - l0) <= 1e-5 * abs(l0) and rel_err(g1, g0) <= 1e-4 and rel_err(2.0 * g1h, g1) <= 1e-6
+    ok = (abs(l1 - l0) <= 1e-5 * abs(l0) and float((a1 - a0).abs().max()) <= 1e-5 and
+          float((s1 - s0).abs().max()) <= 1e-5 * max(float(s0.abs().max()), 1.0) and rel_err(g1, g0) <= 1e-4 and
+          rel_err(2.0 * g1h, g1) <= 1e-6)
     for a, b in zip(R.split_flat(g1, like), R.split_flat(g0, like)):
         if float(b.norm()) > 0:
             ok = ok and rel_err(a, b) <= 2e-4
         else:
             ok = ok and float(a.abs().max()) == 0.0          # ref_in.*: unused by the conv net -> exactly zero
     assert ok, str(diag)
-
-
-SPLIT_SIZES = [64, 1, 65, 300, 1000, 9600, 148 * 64 * 3 + 5]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -785,70 +781,30 @@ def test_single_drone_evaluator_classes_run_eval_in_one_launch():
     assert ctrl.action_counter == 160 and ds.eval_counter == 160 // 9
 
 
-# The tcgen05 / TMEM kernels are compile-verified and host-emulated only (no GPU minutes were left when they were
-# written): their tests are opt-in until the first hardware run (tools/gpu_first_call.sh sets APG_TEST_TC=1), so a
-# first-run problem in an OPTIONAL path (product default: off) cannot stop `pytest -m gpu -x` of the verified paths.
-needs_tc_optin = pytest.mark.skipif(os.environ.get("APG_TEST_TC") != "1",
-                                    reason="optional tcgen05 paths: set APG_TEST_TC=1 (first hardware run pending)")
+@pytest.mark.parametrize("n", [128, 1, 63, 65, 300, 1000, 9600, 148 * 128 * 3 + 77])
+def test_tc1_tcgen05_path_matches_legacy_mma_path(n):
+    _check_tcgen05_vs_legacy(n)
 
 
-@needs_tc_optin
-@pytest.mark.parametrize("n", SPLIT_SIZES)
-def test_tc1_split_adjoint_streaming_dw_gemm(n):
-    """the most basic tcgen05 use first (SS MMAs, K-major unswizzled operands, M = 128): APG_TC_DW alone"""
-    _check_split_adjoint(n, ("APG_TC_DW",))
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# optional tcgen05 / TMEM forward (csrc/hutter_tc_kernels.cu, APG_TC_FWD=1) vs the default forward kernel:
-# same loss / actions / states, and the same gradient when the unchanged adjoint kernel consumes its stash
-# ---------------------------------------------------------------------------------------------------------------
-@needs_tc_optin
-@pytest.mark.parametrize("n", [128, 1, 63, 300, 1000, 9600, 148 * 128 * 3 + 77])
-def test_tc2_forward_matches_default_forward(n):
-    import os
+def test_tc2_backward_after_a_forward_of_the_other_path_poisons_the_gradient():
+    """the workspace is stamped by the forward that filled its stash; an adjoint of the tcgen05 path run on a
+    workspace whose last forward was the legacy one must not return a silently wrong gradient"""
     import bench as B
     PR, R, SY, T, DS = _mods()
-    h, dt = 10, 0.1
-    params = B.default_init("quad", h, seed=n % 97)
-    case = {k: v.cuda() for k, v in SY.quad_case(n, h, dt, seed=n % 89).items()}
+    n, h, dt = 300, 10, 0.1
+    params = B.default_init("quad", h, seed=5)
+    case = {k: v.cuda() for k, v in SY.quad_case(n, h, dt, seed=5).items()}
     flat = R.flatten_params(params).cuda()
-    spec = R.RolloutSpec.quad_concurrent(h, dt)
-
-    def run():
-        r = R.Rollout(spec, n, "cuda:0")
-        loss, states, actions = r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"],
-                                          want_states=True, want_actions=True)
-        grad = r.backward(1.0)
-        torch.cuda.synchronize()
-        return float(loss.item()), states.cpu(), actions.cpu(), grad.cpu()
-    os.environ.pop("APG_TC_FWD", None)
-    l0, s0, a0, g0 = run()
-    os.environ["APG_TC_FWD"] = "1"
+    r = R.Rollout(R.RolloutSpec.quad_concurrent(h, dt), n, "cuda:0")
+    r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])      # tcgen05 forward: stash is valid
+    os.environ["APG_LEGACY_MMA"] = "1"
     try:
-        l1, s1, a1, g1 = run()
+        r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])  # legacy forward re-stamps
     finally:
-        os.environ.pop("APG_TC_FWD", None)
-    # one message with every diagnostic: a failure here is the only feedback a GPU run gives
-    like = [torch.empty_like(p) for p in params]
-    per_tensor = [round(rel_err(a, b), 7) if float(b.norm()) > 0 else float(a.abs().max())
-                  for a, b in zip(R.split_flat(g1, like), R.split_flat(g0, like))]
-    diag = dict(n=n, loss_default=l0, loss_tc=l1, loss_rel=abs(l1 - l0) / abs(l0) if np.isfinite(l1) else None,
-                actions_max_abs=float((a1 - a0).abs().max()), actions_nan=int(torch.isnan(a1).sum()),
-                first_action_default=a0[0, 0].tolist(), first_action_tc=a1[0, 0].tolist(),
-                states_max_abs=float((s1 - s0).abs().max()), grad_rel=rel_err(g1, g0), grad_rel_per_tensor=per_tensor)
-    assert np.isfinite(l1), f"tcgen05 forward reported a protocol timeout (NaN loss): {diag}"
-    ok = (abs(l1 - l0) <= 1e-5 * abs(l0) and float((a1 - a0).abs().max()) <= 1e-5 and
-          float((s1 - s0).abs().max()) <= 1e-5 * max(float(s0.abs().max()), 1.0) and rel_err(g1, g0) <= 1e-4)
-    assert ok, str(diag)
-
-
-@needs_tc_optin
-@pytest.mark.parametrize("n", SPLIT_SIZES)
-@pytest.mark.parametrize("flags", [("APG_TC_DW", "APG_TC_FWD"), ("APG_TC_DW", "APG_TC_DX"),
-                                   ("APG_TC_DW", "APG_TC_DX", "APG_TC_FWD")])
-def test_tc3_combined_tcgen05_paths(n, flags):
-    _check_split_adjoint(n, flags)
+        os.environ.pop("APG_LEGACY_MMA", None)
+    g = r.backward(1.0)                                                              # tcgen05 adjoint on a legacy stamp
+    torch.cuda.synchronize()
+    assert not bool(torch.isfinite(g).all())
 
 
 # ---------------------------------------------------------------------------------------------------------------

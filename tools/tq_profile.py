@@ -24,8 +24,17 @@ def main():
     rc = lib.apg_debug_profile_tq_dw(ctypes.c_void_p(out_dw.ctypes.data))
     assert rc == 0, rc
     out[2] = out_dw[2]
-    names = {0: ["epi wait_d", "epi work"], 1: ["epi wait_d", "epi work"],
-             2: ["prod wait rfree", "prod issue", "mma wait lo_ready", "mma issue", "conv wait full", "conv wait lo_free", "conv work"]}
+    names = {0: ["epi wait_d", "epi other work", "dense: tmem ld16+wait", "dense: tanh/stash/split", "dense: tmem st16 x2", "dense: wait::st+fence+arrive"], 1: ["epi wait_d", "epi work"],
+             2: ["prod wait rfree", "prod issue", "mma wait lo_ready", "mma issue", "conv wait full", "conv wait lo_free", "conv work", "-", "setup", "main loop", "epilogue + exit"]}
+    t = out[0][:, 6:12].astype(np.float64)
+    seg = [("H1 epilogue of warp 0 (ld, tanh, stash, st, arrive)", t[:, 1] - t[:, 0]),
+           ("warp 0 arrived -> issuer saw all 8 warps", t[:, 2] - t[:, 1]),
+           ("issue 24 MMAs", t[:, 3] - t[:, 2]), ("commit instruction", t[:, 4] - t[:, 3]),
+           ("commit issued -> warp 0 sees d_ready (tensor exec + wake-up)", t[:, 5] - t[:, 4]),
+           ("whole hand-off", t[:, 5] - t[:, 0])]
+    print("one hand-off of tq_fwd (tile 0, slot 0, H1 -> fc2), cycles, mean / max over CTAs")
+    for nm, v in seg:
+        print(f"  {nm:62s} {v.mean():8.0f} {v.max():8.0f}")
     for k, kn in ((0, "tq_fwd"), (1, "tq_dx"), (2, "tq_dw")):
         m = out[k].mean(0); mx = out[k].max(0)
         print(kn)
