@@ -310,9 +310,11 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
       tmark(1, st);
       if ((ce = launch_tq_fwd(w + p.o_tq_w, a, fs, p.tq_grid, st))) return (int)ce;
       tmark(2, st);
-      if ((ce = launch_tq_dyn(a, fs, zs, p.tq_dyn_grid, st))) return (int)ce;
+      // the loss sum rides on the dynamics kernel (last block; the ticket word is part of the stamp set above)
+      if ((ce = launch_tq_dyn(a, fs, zs, loss, reinterpret_cast<unsigned*>(w + p.o_hdr + 8), 0x01010101u * FWD_TQ,
+                              p.tq_dyn_grid, st)))
+        return (int)ce;
       tmark(3, st);
-      if (loss && (ce = launch_sum_loss(a.loss_partials, p.tq_dyn_grid, loss, st))) return (int)ce;
       tmark(4, st);
       return 0;
     }

@@ -28,8 +28,8 @@ cudaError_t launch_tq_pack(const HutterLayout& y, const float* params, unsigned 
                            cudaStream_t st);
 cudaError_t launch_tq_fwd(const unsigned char* blob, const RolloutArgs& a, unsigned char* fstash, int grid,
                           cudaStream_t st);
-cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int dyn_grid,
-                          cudaStream_t st);
+cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, float* loss_out,
+                          unsigned* ticket, unsigned ticket0, int dyn_grid, cudaStream_t st);
 cudaError_t launch_tq_dx(const unsigned char* tblob, const RolloutArgs& a, unsigned char* fstash,
                          unsigned char* zstash, const unsigned char* stamp, int want_stamp, int grid, cudaStream_t st);
 cudaError_t launch_tq_dw(const HutterLayout& y, const RolloutArgs& a, const unsigned char* fstash,

@@ -44,19 +44,27 @@ __device__ __forceinline__ long long p2p_clock() { return clock64(); }
 #endif
 }  // namespace
 
-__global__ void apg_reduce_scatter_p2p_kernel(const float* __restrict__ partials, int ncta, int n, float scale,
-                                              int pm_off, int pm_k1, int pm_npos, float* const* __restrict__ slots,
-                                              unsigned* const* __restrict__ flags, int rank, int world,
-                                              unsigned epoch, unsigned* __restrict__ ticket) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) {
-    const float v = p2p_reduce_entry(partials, ncta, n, p2p_partial_column(p, pm_off, pm_k1, pm_npos), scale);
+// 32 parameters x 4 CTA slices per block of 128 threads (the association of apg_reduce4_kernel when `sliced`, of
+// apg_reduce_kernel otherwise: fixed order either way -> bitwise reproducible on every rank)
+__global__ void __launch_bounds__(128)
+    apg_reduce_scatter_p2p_kernel(const float* __restrict__ partials, int ncta, int n, float scale, int pm_off,
+                                  int pm_k1, int pm_npos, float* const* __restrict__ slots,
+                                  unsigned* const* __restrict__ flags, int rank, int world, unsigned epoch,
+                                  unsigned* __restrict__ ticket) {
+  __shared__ float s_part[4][32];
+  const int pl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + pl;
+  const int per = (ncta + 3) / 4;
+  const int c0 = slice * per < ncta ? slice * per : ncta, c1 = (slice + 1) * per < ncta ? (slice + 1) * per : ncta;
+  s_part[slice][pl] = p < n ? p2p_reduce_slice(partials, n, p2p_partial_column(p, pm_off, pm_k1, pm_npos), c0, c1) : 0.f;
+  __syncthreads();
+  if (slice == 0 && p < n) {
+    const float v = scale * ((s_part[0][pl] + s_part[1][pl]) + (s_part[2][pl] + s_part[3][pl]));
     for (int q = 0; q < world; ++q) slots[q][(size_t)rank * n + p] = v;
   }
-  fence_system();                               // this thread's peer stores are ordered before the barrier ...
-  __syncthreads();
+  __syncthreads();                              // the CTA's peer stores happen-before thread 0's fence (cumulative)
   if (threadIdx.x == 0) {
-    fence_system();                             // ... and the CTA's stores before its ticket (cumulative fence)
+    fence_system();
     const unsigned t = ticket_add(ticket);
     if (t == gridDim.x - 1) {                   // every CTA's stores have been fenced: signal all peers
       *ticket = 0u;                             // ready for the next launch (stream order)
@@ -98,7 +106,7 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
 cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, float scale, int pm_off, int pm_k1,
                                       int pm_npos, float* const* slots, unsigned* const* flags, int rank, int world,
                                       unsigned epoch, unsigned* ticket, cudaStream_t st) {
-  APG_LAUNCH((n + 127) / 128, 128, 0, st, apg_reduce_scatter_p2p_kernel)(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
+  APG_LAUNCH((n + 31) / 32, 128, 0, st, apg_reduce_scatter_p2p_kernel)(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
                                                                  slots, flags, rank, world, epoch, ticket);
   return cudaGetLastError();
 }

@@ -54,6 +54,30 @@ APG_HD float p2p_reduce_entry(const float* partials, int ncta, int n, int q, flo
   return scale * ((s0 + s1) + (s2 + s3));
 }
 
+// the CTAs [c0, c1) of one slice: four interleaved running sums, then (s0+s1)+(s2+s3)
+APG_HD float p2p_reduce_slice(const float* partials, int n, int q, int c0, int c1) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = c0;
+  for (; c + 3 < c1; c += 4) {
+    s0 += partials[(size_t)(c + 0) * n + q];
+    s1 += partials[(size_t)(c + 1) * n + q];
+    s2 += partials[(size_t)(c + 2) * n + q];
+    s3 += partials[(size_t)(c + 3) * n + q];
+  }
+  for (; c < c1; ++c) s0 += partials[(size_t)c * n + q];
+  return (s0 + s1) + (s2 + s3);
+}
+// value of slot entry q as apg_reduce_scatter_p2p_kernel computes it (four slices of CTAs)
+APG_HD float p2p_reduce_entry4(const float* partials, int ncta, int n, int q, float scale) {
+  const int per = (ncta + 3) / 4;
+  float s[4];
+  for (int k = 0; k < 4; ++k) {
+    const int c0 = k * per < ncta ? k * per : ncta, c1 = (k + 1) * per < ncta ? (k + 1) * per : ncta;
+    s[k] = p2p_reduce_slice(partials, n, q, c0, c1);
+  }
+  return scale * ((s[0] + s[1]) + (s[2] + s[3]));
+}
+
 // SGD with momentum as torch.optim.SGD applies it (train_base.py:139-143): buf = momentum * buf + g; p -= lr * buf
 APG_HD void p2p_sgd_entry(float g, float lr, float momentum, float* buf, float* param) {
   const float b = momentum * (*buf) + g;

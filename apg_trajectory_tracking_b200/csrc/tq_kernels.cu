@@ -90,6 +90,22 @@ __device__ __forceinline__ float tq_tanh(float x) {
 }
 __device__ __forceinline__ float tq_sigmoid(float x) { return tq_rcp(1.f + tq_ex2(x * -1.442695041f)); }
 #endif
+// tanh of two values with THREE SFU operations instead of four: 1/a and 1/b from one reciprocal of a*b.  The SFU
+// (16 lanes per SM) is what a tanh epilogue of a 128-drone tile waits for (measured, profiles/r2): 1024 cycles per
+// 64-wide layer with two SFU operations per element.  |x| is clamped to 15 (tanh = +-1 in fp32 beyond 9) so that a*b
+// stays finite.
+__device__ __forceinline__ void tq_tanh2(float x0, float x1, float* y0, float* y1) {
+#ifdef APG_TC_SIM
+  *y0 = tanhf(x0); *y1 = tanhf(x1);
+#else
+  x0 = fminf(fmaxf(x0, -15.f), 15.f);
+  x1 = fminf(fmaxf(x1, -15.f), 15.f);
+  const float a0 = tq_ex2(x0 * 2.885390082f) + 1.f, a1 = tq_ex2(x1 * 2.885390082f) + 1.f;
+  const float r = tq_rcp(a0 * a1);
+  *y0 = fmaf(-2.f, r * a1, 1.f);
+  *y1 = fmaf(-2.f, r * a0, 1.f);
+#endif
+}
 
 // the eight row-phase pointers of one stash set for the thread that owns drone `row` of the tile:
 // element (set row r) lives at p[r & 7] + r * 128
@@ -163,18 +179,27 @@ __device__ __forceinline__ OpRec make_oprec(uint32_t whi, uint32_t wlo, int K_im
   r.idesc = idesc_tf32(TMT, N); r.d_col = (uint32_t)d_col; r.ksteps = (uint32_t)(K / 8); r.acc0 = (uint32_t)acc0; r.pad = 0;
   return r;
 }
-// executed by the WHOLE issuing warp (uniform values -> uniform registers); only the elected lane issues
-__device__ __forceinline__ void issue_series(const OpRec& op, uint32_t slot, uint32_t ahi, uint32_t alo, bool leader) {
-  const uint32_t d = slot + op.d_col;
-  uint32_t bh = op.bh_lo, bl = op.bl_lo;
-  for (uint32_t ks = 0; ks < op.ksteps; ++ks, bh += 16, bl += 16) {
-    const uint64_t dbh = ((uint64_t)op.desc_hi << 32) | bh, dbl = ((uint64_t)op.desc_hi << 32) | bl;
+// executed by the WHOLE issuing warp (uniform values -> uniform registers); only the elected lane issues.  The op
+// record is taken BY VALUE (the "memory" clobber of the MMA asm would force a shared-memory reload of every field per
+// k-step otherwise) and the k loop is unrolled for the three k-step counts that occur (K = 16, 40, 64).
+template <int KS>
+__device__ __forceinline__ void issue_ks(uint32_t d, uint32_t ahi, uint32_t alo, uint32_t bh, uint32_t bl, uint32_t dhi,
+                                         uint32_t idesc, uint32_t acc0, bool leader) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const uint64_t dbh = ((uint64_t)dhi << 32) | (bh + 16u * ks), dbl = ((uint64_t)dhi << 32) | (bl + 16u * ks);
     if (leader) {
-      tcp::mma_ts(d, alo + ks * 8, dbh, op.idesc, (ks > 0 || op.acc0) ? 1u : 0u);
-      tcp::mma_ts(d, ahi + ks * 8, dbl, op.idesc, 1u);
-      tcp::mma_ts(d, ahi + ks * 8, dbh, op.idesc, 1u);
+      tcp::mma_ts(d, alo + ks * 8, dbh, idesc, (ks > 0) ? 1u : acc0);
+      tcp::mma_ts(d, ahi + ks * 8, dbl, idesc, 1u);
+      tcp::mma_ts(d, ahi + ks * 8, dbh, idesc, 1u);
     }
   }
+}
+__device__ __forceinline__ void issue_series(const OpRec op, uint32_t slot, uint32_t ahi, uint32_t alo, bool leader) {
+  const uint32_t d = slot + op.d_col;
+  if (op.ksteps == 8) issue_ks<8>(d, ahi, alo, op.bh_lo, op.bl_lo, op.desc_hi, op.idesc, op.acc0, leader);
+  else if (op.ksteps == 5) issue_ks<5>(d, ahi, alo, op.bh_lo, op.bl_lo, op.desc_hi, op.idesc, op.acc0, leader);
+  else issue_ks<2>(d, ahi, alo, op.bh_lo, op.bl_lo, op.desc_hi, op.idesc, op.acc0, leader);
 }
 
 // common prologue: barriers, TMEM, bulk copies of the weight images; returns the TMEM base
@@ -257,7 +282,10 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           const bool stamp_ = (leader && s == 0 && tile_j[0] == 0 && op_i[0] == 10 && blockIdx.x < 148);
           if (stamp_) TQ_PROF_ARRAY[0][blockIdx.x][8] = clock64();          // a_ready observed
 #endif
-          issue_series(s_ops[op_i[s]], slot, slot + C_AHI, slot + C_ALO, leader);
+          {
+            const OpRec op = s_ops[op_i[s]];
+            issue_series(op, slot, slot + C_AHI, slot + C_ALO, leader);
+          }
 #ifdef APG_PROFILE
           if (stamp_) TQ_PROF_ARRAY[0][blockIdx.x][9] = clock64();          // MMAs issued
 #endif
@@ -314,10 +342,14 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           tcp::tmem_ld16(d_main + hf * 32 + c0, v);
           TQP(2);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float yv = tq_tanh(__uint_as_float(v[q]) + b[hf * 32 + c0 + q]);
-            set_store(sp, hf * 32 + c0 + q, yv);
-            split_bits(yv, &v[q], &l[q]);
+          for (int q = 0; q < 16; q += 2) {
+            float y0, y1;
+            tq_tanh2(__uint_as_float(v[q]) + b[hf * 32 + c0 + q], __uint_as_float(v[q + 1]) + b[hf * 32 + c0 + q + 1],
+                     &y0, &y1);
+            set_store(sp, hf * 32 + c0 + q, y0);
+            set_store(sp, hf * 32 + c0 + q + 1, y1);
+            split_bits(y0, &v[q], &l[q]);
+            split_bits(y1, &v[q + 1], &l[q + 1]);
           }
           TQP(3);
           tcp::tmem_st16(ahi + hf * 32 + c0, v);
@@ -354,6 +386,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       for (int gq = 0; gq < 4; ++gq) {
         // window of position pair gq: in_ref rows 2gq .. 2gq+3 (36 values) | 1 (ones row of the conv weight
         // gradient; its image column is 0) | 0 0 0; this thread's columns [0,24) or [24,40)
+        // (measured: issuing the loads of window gq + 1 one hand-off early costs more in spills than it hides)
         const SetPtr sp_w = set_ptr(tb, tq::O_WIN + tq::R_WIN * gq, tq::R_WIN, row);
         if (hf == 0) {
           float x[24];
@@ -466,10 +499,13 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
 // from the stash and nothing but ZO is written.  Dead drones of a ragged tile write zeros.
 // =========================================================================================================
 __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
-    tq_dyn_kernel(const RolloutArgs g, unsigned char* __restrict__ fstash, unsigned char* __restrict__ zstash) {
+    tq_dyn_kernel(const RolloutArgs g, unsigned char* __restrict__ fstash, unsigned char* __restrict__ zstash,
+                  float* __restrict__ loss_out, unsigned* __restrict__ ticket, unsigned ticket0) {
   APG_TC_DYNAMIC_SMEM(smem_raw);
   float* s_st = reinterpret_cast<float*>(smem_raw);           // [H*12][TQ_DYN_THREADS]
   __shared__ float s_red[TQ_DYN_THREADS / 32];
+  __shared__ double s_dsum[TQ_DYN_THREADS];
+  __shared__ int s_last;
   using Sys = Quad<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW, TD = TQ_DYN_THREADS;
   const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
@@ -556,6 +592,26 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
 #pragma unroll
     for (int w = 0; w < TQ_DYN_THREADS / 32; ++w) tsum += s_red[w];
     g.loss_partials[blockIdx.x] = tsum;
+    // the last block to get here adds up the partials (fixed order, double): no separate loss-sum launch.  The ticket
+    // word lies inside the workspace stamp, which a memset node sets to `ticket0` before every forward.
+    s_last = 0;
+    if (loss_out) {
+      __threadfence();
+      s_last = atomicAdd(ticket, 1u) == ticket0 + gridDim.x - 1u;
+    }
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double acc = 0.0;
+    for (int c = tx; c < (int)gridDim.x; c += TQ_DYN_THREADS) acc += (double)__ldcg(&g.loss_partials[c]);
+    s_dsum[tx] = acc;
+    __syncthreads();
+    if (tx == 0) {
+      double t = 0.0;
+      for (int i = 0; i < TQ_DYN_THREADS; ++i) t += s_dsum[i];
+      *loss_out = (float)t;
+    }
   }
 }
 
@@ -606,7 +662,10 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           tcp::fence_after_thread_sync();
           const uint32_t slot = tmem + s * tq::SLOT_COLS;
           for (int i = tq::xh_first(h_i[s]); i < tq::xh_first(h_i[s] + 1); ++i)
-            issue_series(s_ops[i], slot, slot + tq::XC_AHI, slot + tq::XC_ALO, leader);
+          {
+            const OpRec op = s_ops[i];
+            issue_series(op, slot, slot + tq::XC_AHI, slot + tq::XC_ALO, leader);
+          }
           if (leader) tcp::commit(smem_u32(&s_bars.d_ready[s]));
           if (++h_i[s] == tq::NXH) { h_i[s] = 0; tile_j[s] += 2; }
           --remaining;
@@ -783,12 +842,12 @@ cudaError_t launch_tq_fwd(const unsigned char* blob, const RolloutArgs& a, unsig
   return cudaGetLastError();
 }
 
-// dynamics / loss / reverse sweep: writes tq_dyn_grid(n, sms) loss partials
-cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, int dyn_grid,
-                          cudaStream_t st) {
+// dynamics / loss / reverse sweep: writes tq_dyn_grid(n, sms) loss partials and (loss_out != NULL) their sum
+cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, float* loss_out,
+                          unsigned* ticket, unsigned ticket0, int dyn_grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tq_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
   if (e != cudaSuccess) return e;
-  APG_LAUNCH(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel)(a, fstash, zstash);
+  APG_LAUNCH(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel)(a, fstash, zstash, loss_out, ticket, ticket0);
   return cudaGetLastError();
 }
 

@@ -105,8 +105,8 @@ class Rollout:
             if n_params < 0:
                 _capi.check(n_params)
             self.n_params = n_params
-            # True: the tcgen05 / TMEM kernels serve this configuration (pack, chain, dynamics, loss sum | dX chain,
-            # dW GEMM, reduce = 7 launches per iteration); False: the tile-engine kernels (5 launches)
+            # True: the tcgen05 / TMEM kernels serve this configuration (pack, chain, dynamics + loss sum | dX chain,
+            # dW GEMM, reduce = 6 launches per iteration); False: the tile-engine kernels (5 launches)
             self.tcgen05 = self.lib.apg_rollout_kernel_path(ctypes.byref(self.cfg)) == 1
             ws = self.lib.apg_workspace_bytes(ctypes.byref(self.cfg))
             self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)

@@ -64,9 +64,9 @@ class FusedTrainStep:
                 torch.distributed.get_world_size(process_group) > 1
         self.distributed = distributed
         # own kernels per iteration: pack, forward, loss-sum, adjoint, grad-reduce (tile-engine kernels) or pack,
-        # forward chain, dynamics, loss-sum, dX chain, dW GEMM, grad-reduce (tcgen05 path); the SGD update adds two torch
-        # element-wise launches, N > 1 one NCCL all-reduce kernel
-        self.kernel_launches_per_step = 7 if self.runner.tcgen05 else 5
+        # forward chain, dynamics (+ loss sum), dX chain, dW GEMM, grad-reduce (+ SGD on one device) on the tcgen05 path;
+        # elsewhere the SGD update adds two torch element-wise launches, N > 1 one NCCL all-reduce kernel
+        self.kernel_launches_per_step = 6 if getattr(self.runner, "tcgen05", False) else 5
         if peer_exchange is None:
             peer_exchange = os.environ.get("APG_P2P_GRAD") == "1"
         self.peer = None
@@ -108,7 +108,7 @@ class FusedTrainStep:
             self.peer.gather(*self._peer_step, grad_out=self.grad, params=self.flat, momentum_buf=self.buf,
                              lr=self.lr, momentum=self.momentum)
             return loss
-        if self.runner.tcgen05 and not self.distributed:
+        if getattr(self.runner, "tcgen05", False) and not self.distributed:
             # single device, tcgen05 path: the optimizer step rides on the gradient reduction (one launch)
             loss, _, _ = self.runner.forward(self.flat, self._dev(in_state), self._dev(cur), self._dev(in_ref),
                                              self._dev(ref), self._dev(h0c0))

@@ -200,6 +200,8 @@ static inline int __syncthreads_or(int pred) {
   st.cta_barrier->arrive_and_wait();
   return r;
 }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
 // warp vote: true iff the predicate holds on every lane of the warp
 static inline int __all_sync(unsigned, int pred) {
   sim::State& st = sim::S();

@@ -15,7 +15,7 @@ extern "C" void hc_p2p_reduce_scatter(float* mem, int world, int n, int rank, un
   const GradCommLayout L{world, n};
   const int set = (int)(epoch & 1u);
   for (int p = 0; p < n; ++p) {
-    const float v = p2p_reduce_entry(partials, ncta, n, p2p_partial_column(p, pm_off, pm_k1, pm_npos), scale);
+    const float v = p2p_reduce_entry4(partials, ncta, n, p2p_partial_column(p, pm_off, pm_k1, pm_npos), scale);
     for (int q = 0; q < world; ++q) (mem + (size_t)q * L.total_floats() + L.slot_off(set, 0))[(size_t)rank * n + p] = v;
   }
   for (int q = 0; q < world; ++q) {

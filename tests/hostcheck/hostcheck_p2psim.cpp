@@ -25,7 +25,7 @@ extern "C" int hc_p2psim_step(float* mem, int world, int n, unsigned epoch, cons
   try {
     for (int i = 0; i < world; ++i) {
       const int r = order[i];
-      sim::launch(blocks, 128, [&]() {
+      sim::launch((n + 31) / 32, 128, [&]() {               // 32 parameters x 4 CTA slices per block (the real launcher)
         apg_reduce_scatter_p2p_kernel(partials + (size_t)r * ncta * n, ncta, n, scale, 0, 0, 0, slots.data(),
                                       flags.data(), r, world, epoch, tickets + r);
       });

@@ -35,7 +35,8 @@ extern "C" void hc_tq_sizes(int n, long long* out) {
 extern "C" int hc_tq_step(const float* params, const float* in_state, const float* cur, const float* in_ref,
                           const float* ref, int n, float dt, const float* pc, int grid, unsigned char* blob,
                           unsigned char* tblob, unsigned char* fstash, unsigned char* zstash, float* loss_partials,
-                          float* grad_partials, float* states_out, float* actions_out, int stages, int dyn_grid, char* err,
+                          float* grad_partials, float* states_out, float* actions_out, int stages, int dyn_grid, float* loss_total,
+                          char* err,
                           int err_len) {
   const HutterLayout y = layout();
   RolloutArgs a;
@@ -49,7 +50,10 @@ extern "C" int hc_tq_step(const float* params, const float* in_state, const floa
   if (stages >= 1) {
     launch_tq_pack(y, params, blob, tblob, nullptr);
     launch_tq_fwd(blob, a, fstash, grid, nullptr);
-    launch_tq_dyn(a, fstash, zstash, dyn_grid, nullptr);
+    unsigned ticket = 77u;
+    float loss_sum = 0.f;
+    launch_tq_dyn(a, fstash, zstash, &loss_sum, &ticket, 77u, dyn_grid, nullptr);
+    if (loss_total) *loss_total = loss_sum;
   }
   if (stages >= 2) launch_tq_dx(tblob, a, fstash, zstash, stamp, 3, grid, nullptr);
   if (stages >= 3) launch_tq_dw(y, a, fstash, zstash, grid, nullptr);

@@ -28,8 +28,8 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _reduce_like_kernel(partials, scale, perm=None):
-    """apg_reduce_kernel's association: four interleaved running sums over the CTAs, then (s0+s1)+(s2+s3)"""
+def _reduce_slice(partials):
+    """four interleaved running sums over the CTAs of one slice, then (s0+s1)+(s2+s3)"""
     ncta, n = partials.shape
     s = np.zeros((4, n), np.float32)
     c = 0
@@ -40,7 +40,17 @@ def _reduce_like_kernel(partials, scale, perm=None):
     while c < ncta:
         s[0] += partials[c]
         c += 1
-    out = np.float32(scale) * ((s[0] + s[1]) + (s[2] + s[3]))
+    return (s[0] + s[1]) + (s[2] + s[3])
+
+
+def _reduce_like_kernel(partials, scale, perm=None):
+    """apg_reduce_scatter_p2p_kernel's association (= apg_reduce4_kernel's): four slices of CTAs, each summed with four
+    interleaved running sums, then (t0+t1)+(t2+t3)"""
+    ncta, n = partials.shape
+    per = (ncta + 3) // 4
+    t = [_reduce_slice(partials[min(k * per, ncta):min((k + 1) * per, ncta)]) if min(k * per, ncta) < ncta
+         else np.zeros(n, np.float32) for k in range(4)]
+    out = np.float32(scale) * ((t[0] + t[1]) + (t[2] + t[3]))
     return out if perm is None else out[perm]
 
 

@@ -77,16 +77,18 @@ def test_tq_forward_dx_chain_and_streaming_dw_gemm_on_the_model(sim, n, grid):
     blob, tblob, fst, zst = bufs
     dyn_grid = 2
     lossp = np.zeros(dyn_grid, np.float32)
+    loss_total = np.zeros(1, np.float32)
     parts = np.full((grid, npar), np.nan, np.float32)
     states, actions = np.zeros((n, H, 12), np.float32), np.zeros((n, H, 4), np.float32)
     err = ctypes.create_string_buffer(4096)
     nerr = sim.hc_tq_step(_p(flat), _p(ins), _p(cur), _p(inr), _p(ref), n, ctypes.c_float(0.1), _p(pc), grid, _p(blob),
-                          _p(tblob), _p(fst), _p(zst), _p(lossp), _p(parts), _p(states), _p(actions), 3, dyn_grid, err, 4096)
+                          _p(tblob), _p(fst), _p(zst), _p(lossp), _p(parts), _p(states), _p(actions), 3, dyn_grid, _p(loss_total), err, 4096)
     assert nerr == 0, err.value.decode()
     want_loss, want_grad, want_states, want_actions = O.concurrent_value_and_grad(
         "quad", params, case["in_state"], case["cur"], case["in_ref"], case["ref"], H, 0.1)
     assert np.isfinite(lossp).all()
     assert abs(float(lossp.sum()) - float(want_loss)) <= 2e-5 * abs(float(want_loss))
+    assert abs(float(loss_total[0]) - float(lossp.astype(np.float64).sum())) <= 1e-6 * abs(float(want_loss))   # last-block sum
     assert np.abs(actions - want_actions.detach().numpy()).max() <= 2e-5
     assert np.abs(states - want_states.detach().numpy()).max() <= 1e-4
     # stash set the dynamics kernel reads: actions [k*4 + c] (first row 592)
