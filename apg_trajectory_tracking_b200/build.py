@@ -30,17 +30,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False, profile=False):
-    """profile=True builds libapg_b200_prof.so with per-phase cycle counters (tools/phase_profile.py).
-    The translation units are compiled in parallel (one nvcc per .cu) and linked into one shared library."""
+def build(force=False, verbose=False, profile=False, variant=None, defines=()):
+    """profile=True builds libapg_b200_prof.so with per-phase cycle counters (tools/tq_profile.py);
+    variant="name" with defines=("-DX", ...) builds libapg_b200_<name>.so for A/B timing experiments (load it with
+    APG_B200_LIB=<path>).  The translation units are compiled in parallel (one nvcc per .cu) and linked into one
+    shared library."""
     from concurrent.futures import ThreadPoolExecutor
-    out = LIB.replace(".so", "_prof.so") if profile else LIB
-    if not force and not profile and not needs_build():
+    if profile:
+        variant, defines = "prof", ("-DAPG_PROFILE",) + tuple(defines)
+    out = LIB.replace(".so", f"_{variant}.so") if variant else LIB
+    if not force and not variant and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build", "prof" if profile else "obj")
+    objdir = os.path.join(HERE, "build", variant or "obj")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else []) + \
-            (["-DAPG_PROFILE"] if profile else [])
+    flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else []) + list(defines)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
@@ -66,4 +69,6 @@ def build(force=False, verbose=False, profile=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profile="--profile" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profile="--profile" in sys.argv,
+                variant=_variant, defines=tuple(a for a in sys.argv if a.startswith("-D"))))

@@ -152,6 +152,7 @@ RolloutArgs make_args(const apg_config* c, const Plan& p, const float* in_state,
   a.in_state = in_state; a.cur = cur; a.in_ref = in_ref; a.ref = ref; a.h0c0 = h0c0;
   a.N = c->n_drones; a.h = c->horizon; a.ref_rows = is_recurrent(c) ? 2 * c->horizon : c->horizon;
   a.window = c->window; a.dt = c->dt;
+  a.raw_inputs = (!is_recurrent(c) && is_hutter(c) && !in_state && !in_ref) ? 1 : 0;
   memcpy(a.pc.v, c->phys, sizeof(float) * MAX_PHYS);
   a.wf = reinterpret_cast<float*>(w + p.o_wf);
   a.wb = reinterpret_cast<float*>(w + p.o_wb);
@@ -166,11 +167,17 @@ RolloutArgs make_args(const apg_config* c, const Plan& p, const float* in_state,
   return a;
 }
 
+bool env_flag(const char* name);
+bool use_tq(const apg_config* c, const HutterLayout& y);
+
 int check_ptrs(const apg_config* c, const float* params, const float* in_state, const float* cur, const float* in_ref,
                const float* ref, void* workspace) {
   if (!params || !cur || !workspace) return APG_ERR_BAD_CONFIG;
-  if (!in_state && !is_recurrent(c)) return APG_ERR_BAD_CONFIG;   // recurrent modes featurise `cur` in-kernel
-  if (c->system != SYS_CARTPOLE && (!in_ref || !ref)) return APG_ERR_BAD_CONFIG;
+  // recurrent modes featurise `cur` in-kernel; the tcgen05 path takes RAW samples when in_state and in_ref are both
+  // NULL (cur = raw states, ref = raw reference rows: QuadDataset.prepare_data runs in the kernels' prologue)
+  const bool raw_ok = is_hutter(c) && !is_recurrent(c) && use_tq(c, hutter_layout(c)) && !in_state && !in_ref && ref;
+  if (!in_state && !is_recurrent(c) && !raw_ok) return APG_ERR_BAD_CONFIG;
+  if (c->system != SYS_CARTPOLE && ((!in_ref && !raw_ok) || !ref)) return APG_ERR_BAD_CONFIG;
   if (!aligned16(params) || !aligned16(in_state) || !aligned16(cur) || !aligned16(in_ref) || !aligned16(ref) ||
       (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return APG_ERR_ALIGNMENT;

@@ -14,6 +14,8 @@ struct RolloutArgs {
   int N, h;
   int ref_rows;            // rows per drone in `ref` (h in concurrent mode, 2h in recurrent mode)
   int window;              // Window enum (recurrent modes)
+  int raw_inputs;          // tcgen05 path: `cur` / `ref` are RAW samples (absolute positions), in_state / in_ref are
+                           // derived in the kernels' prologue (QuadDataset.prepare_data, dataset.py:155-204)
   float dt;
   PhysConsts pc;
   // packed weights

@@ -73,20 +73,17 @@ inline float tq_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 #else
 __device__ __forceinline__ float tq_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tq_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// branch-free tanh on the SFU: 1 - 2 / (exp(2x) + 1) (absolute error <= 3e-7, saturates correctly for large |x|);
-// -DTQ_TANH_POLY adds an odd Taylor polynomial below 0.25 (relative accuracy near 0, +6 instructions per element)
-__device__ __forceinline__ float tq_tanh(float x) {
-  const float big = fmaf(-2.f, tq_rcp(tq_ex2(x * 2.885390082f) + 1.f), 1.f);
-#ifdef TQ_TANH_POLY
+// branch-free tanh: 1 - 2 / (exp(2x) + 1) on the SFU (absolute error <= 3e-7, saturates correctly for large |x|) and,
+// below |x| = 0.25, an odd Taylor polynomial (the SFU form loses RELATIVE accuracy near 0: 1 - 2/a cancels).  The
+// relative accuracy matters: the batch gradient is a sum with ~300x cancellation at N = 65536, and with the SFU form
+// alone an ulp-level change of the inputs moved the gradient by 5e-4 of its norm (profiles/r2, bench raw-input check);
+// with the polynomial it is 1e-5.  -DTQ_TANH_SFU_ONLY drops the polynomial (timing experiments only).
+__device__ __forceinline__ float tq_tanh_small(float x) {
   const float x2 = x * x;
   float p = fmaf(x2, 0.0218694885f, -0.0539682540f);
   p = fmaf(x2, p, 0.133333333f);
   p = fmaf(x2, p, -0.333333333f);
-  const float small = fmaf(x * x2, p, x);
-  return fabsf(x) < 0.25f ? small : big;
-#else
-  return big;
-#endif
+  return fmaf(x * x2, p, x);
 }
 __device__ __forceinline__ float tq_sigmoid(float x) { return tq_rcp(1.f + tq_ex2(x * -1.442695041f)); }
 #endif
@@ -98,12 +95,17 @@ __device__ __forceinline__ void tq_tanh2(float x0, float x1, float* y0, float* y
 #ifdef APG_TC_SIM
   *y0 = tanhf(x0); *y1 = tanhf(x1);
 #else
-  x0 = fminf(fmaxf(x0, -15.f), 15.f);
-  x1 = fminf(fmaxf(x1, -15.f), 15.f);
-  const float a0 = tq_ex2(x0 * 2.885390082f) + 1.f, a1 = tq_ex2(x1 * 2.885390082f) + 1.f;
+  const float c0 = fminf(fmaxf(x0, -15.f), 15.f);
+  const float c1 = fminf(fmaxf(x1, -15.f), 15.f);
+  const float a0 = tq_ex2(c0 * 2.885390082f) + 1.f, a1 = tq_ex2(c1 * 2.885390082f) + 1.f;
   const float r = tq_rcp(a0 * a1);
-  *y0 = fmaf(-2.f, r * a1, 1.f);
-  *y1 = fmaf(-2.f, r * a0, 1.f);
+  const float b0 = fmaf(-2.f, r * a1, 1.f), b1 = fmaf(-2.f, r * a0, 1.f);
+#ifdef TQ_TANH_SFU_ONLY
+  *y0 = b0; *y1 = b1;
+#else
+  *y0 = fabsf(x0) < 0.25f ? tq_tanh_small(x0) : b0;
+  *y1 = fabsf(x1) < 0.25f ? tq_tanh_small(x1) : b1;
+#endif
 #endif
 }
 
@@ -136,6 +138,16 @@ __device__ __forceinline__ void a_operand_ready(uint32_t bar) {
   tcp::fence_before_thread_sync();
   __syncwarp();
   if ((threadIdx.x & 31) == 0) tcp::mbar_arrive(bar);
+}
+// element e (= row * 9 + c) of the policy's reference input built from the RAW reference rows of one drone
+// (QuadDataset.prepare_data, dataset.py:170-201): [ref_pos - pos | ref_vel | ref_vel - vel] per row
+__device__ __forceinline__ float raw_in_ref(const float* ref_drone, int e, const float* pos, const float* vel, bool live) {
+  if (!live) return 0.f;
+  const int r = e / 9, c = e - 9 * r;
+  const float* row = ref_drone + 9 * r;
+  if (c < 3) return row[c] - pos[c];
+  if (c < 6) return row[6 + (c - 3)];
+  return row[6 + (c - 6)] - vel[c - 6];
 }
 // L2 prefetch of the 128-byte lines [first, first + nlines) of a contiguous region, spread over the lanes of a warp
 __device__ __forceinline__ void prefetch_lines(const unsigned char* p, int nlines, int lane) {
@@ -248,6 +260,9 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   __shared__ int s_abort;
   __shared__ OpRec s_ops[NOPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef APG_PROFILE
+  const long long t_entry_ = clock64();
+#endif
   if (tid < NOPS) {
     const Op op = op_of(tid);
     const uint32_t whi = smem_u32(base + op.img_off);
@@ -314,10 +329,16 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
     const uint32_t bar_a = smem_u32(&s_bars.a_ready[s]), bar_d = smem_u32(&s_bars.d_ready[s]);
     uint32_t dcnt = 0;                                        // commits of this slot seen so far
     TQP_DECL
+#ifdef APG_PROFILE
+    if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][12] = clock64() - t_entry_;     // setup done
+#endif
     auto wait_d = [&]() {
       TQP(1);
       tq_wait(bar_d, dcnt & 1u, abort_flag);
       TQP(0);
+#ifdef APG_PROFILE
+      if (tid == 0 && dcnt == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][13] = clock64() - t_entry_;   // first D
+#endif
       ++dcnt;
       tcp::fence_after_thread_sync();
     };
@@ -329,8 +350,13 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       if (j + 2 < my_tiles && hf == 0) {                       // next tile of this slot: its inputs into L2 now
         const size_t d0n = ((size_t)tile + 2 * (size_t)gridDim.x) * TMT + (size_t)(warp & 3) * 32;
         if (d0n + 32 <= (size_t)n) {
-          prefetch_lines(reinterpret_cast<const unsigned char*>(g.in_ref + d0n * REFW), 32 * REFW * 4 / 128, lane);
-          prefetch_lines(reinterpret_cast<const unsigned char*>(g.in_state + d0n * F0), 32 * F0 * 4 / 128, lane);
+          if (g.raw_inputs) {
+            prefetch_lines(reinterpret_cast<const unsigned char*>(g.ref + d0n * REFW), 32 * REFW * 4 / 128, lane);
+            prefetch_lines(reinterpret_cast<const unsigned char*>(g.cur + d0n * 12), 32 * 12 * 4 / 128, lane);
+          } else {
+            prefetch_lines(reinterpret_cast<const unsigned char*>(g.in_ref + d0n * REFW), 32 * REFW * 4 / 128, lane);
+            prefetch_lines(reinterpret_cast<const unsigned char*>(g.in_state + d0n * F0), 32 * F0 * 4 / 128, lane);
+          }
         }
       }
       // D_main columns [32 hf, +32) -> tanh(x + b) -> A operand (hi, lo) + stash rows of set `sp`
@@ -361,12 +387,28 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       };
       // ---- op 0 operand: in_state (15) + 1 (the ones row of the states_in weight gradient; its image column is 0);
       //      this thread's eight columns [8 hf, +8)
+      // raw mode (QuadDataset.prepare_data dataset.py:155-204 in the prologue): the policy inputs are
+      // derived here from the raw sample - features of the state (position plays no role), reference rows relative
+      // to the drone's position / velocity - instead of being read as two more tensors (420 B per drone)
+      float cpos[3] = {0.f, 0.f, 0.f}, cvel[3] = {0.f, 0.f, 0.f};
       {
         float x0[8];
+        if (g.raw_inputs) {
+          float st12[12], f15[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int kk = hf * 8 + k;
-          x0[k] = (live && kk < F0) ? g.in_state[drone * F0 + kk] : 0.f;
+          for (int q = 0; q < 12; ++q) st12[q] = live ? g.cur[drone * 12 + q] : 0.f;
+          Quad<float>::features(st12, f15);
+          f15[15] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x0[k] = live ? f15[hf * 8 + k] : 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { cpos[c] = st12[c]; cvel[c] = st12[6 + c]; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int kk = hf * 8 + k;
+            x0[k] = (live && kk < F0) ? g.in_state[drone * F0 + kk] : 0.f;
+          }
         }
         if (hf) x0[7] = live ? 1.f : 0.f;
         a_store<8>(ahi + hf * 8, alo + hf * 8, x0);
@@ -390,11 +432,16 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
         const SetPtr sp_w = set_ptr(tb, tq::O_WIN + tq::R_WIN * gq, tq::R_WIN, row);
         if (hf == 0) {
           float x[24];
+          if (g.raw_inputs) {
 #pragma unroll
-          for (int k = 0; k < 24; k += 2) {
-            const float2 tt = live ? *(const float2*)(rr + 18 * gq + k) : make_float2(0.f, 0.f);
-            x[k] = tt.x;
-            x[k + 1] = tt.y;
+            for (int k = 0; k < 24; ++k) x[k] = raw_in_ref(g.ref + drone * REFW, 18 * gq + k, cpos, cvel, live);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 24; k += 2) {
+              const float2 tt = live ? *(const float2*)(rr + 18 * gq + k) : make_float2(0.f, 0.f);
+              x[k] = tt.x;
+              x[k + 1] = tt.y;
+            }
           }
           wait_d();      // op 1 (gq = 0) or the fc1 piece of the previous pair: the A columns are free again
           a_store<24>(ahi, alo, x);
@@ -403,11 +450,16 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           for (int k = 0; k < 24; ++k) set_store(sp_w, k, x[k]);
         } else {
           float x[16];
+          if (g.raw_inputs) {
 #pragma unroll
-          for (int k = 0; k < 12; k += 2) {
-            const float2 tt = live ? *(const float2*)(rr + 18 * gq + 24 + k) : make_float2(0.f, 0.f);
-            x[k] = tt.x;
-            x[k + 1] = tt.y;
+            for (int k = 0; k < 12; ++k) x[k] = raw_in_ref(g.ref + drone * REFW, 18 * gq + 24 + k, cpos, cvel, live);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 12; k += 2) {
+              const float2 tt = live ? *(const float2*)(rr + 18 * gq + 24 + k) : make_float2(0.f, 0.f);
+              x[k] = tt.x;
+              x[k + 1] = tt.y;
+            }
           }
           x[12] = live ? 1.f : 0.f;
           x[13] = x[14] = x[15] = 0.f;
@@ -483,9 +535,15 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
     }
     TQP(1);
     if (tid == 0) TQP_FLUSH(0, 0, 6);
+#ifdef APG_PROFILE
+    if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][14] = clock64() - t_entry_;     // warp 0 done
+#endif
   }
   tcp::fence_before_thread_sync();
   __syncthreads();
+#ifdef APG_PROFILE
+  if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][15] = clock64() - t_entry_;       // all warps done
+#endif
   if (tid == 0 && s_abort && my_tiles > 0)                     // poison: the dynamics kernel turns it into a NaN loss
     *reinterpret_cast<float*>(fstash + (size_t)blockIdx.x * tq::F_TILE_BYTES + tq::set_base(tq::O_ACT)) =
         __int_as_float(0x7fc00000);
@@ -530,12 +588,17 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
       const float* ref_g = g.ref + drone * g.ref_rows * R;
 #pragma unroll
       for (int q = 0; q < S; ++q) s0[q] = sc[q] = cur_g[q];
+      float p0[3] = {0.f, 0.f, 0.f};                          // raw mode: the drone starts at the origin and the
+      if (g.raw_inputs) {                                      // reference positions are relative to it (dataset.py:170-175)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { p0[c] = s0[c]; s0[c] = sc[c] = 0.f; }
+      }
 #pragma unroll 1
       for (int k = 0; k < H; ++k) {
 #pragma unroll
         for (int c = 0; c < A; ++c) a[c] = *reinterpret_cast<const float*>(act_b + elem(k * A + c));
 #pragma unroll
-        for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
+        for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c] - (c < 3 ? p0[c] : 0.f);
         Sys::step(sc, a, g.dt, g.pc.v, sn);
         my_loss += Sys::loss(sn, rf, a, s0, k, H);
 #pragma unroll
@@ -561,7 +624,7 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
 #pragma unroll
         for (int c = 0; c < A; ++c) { a[c] = *reinterpret_cast<const float*>(act_b + elem(k * A + c)); ga[c] = 0.f; }
 #pragma unroll
-        for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
+        for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c] - (c < 3 ? p0[c] : 0.f);
         if (k > 0) {
 #pragma unroll
           for (int q = 0; q < S; ++q) sk[q] = s_st[((k - 1) * S + q) * TD + tx];
@@ -631,6 +694,9 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   __shared__ int s_abort;
   __shared__ OpRec s_ops[tq::NXS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef APG_PROFILE
+  const long long t_entry_ = clock64();
+#endif
   if (tid < tq::NXS) {
     const tq::XOp op = tq::xop_of(tid);
     const tq::TImg im = tq::timage_of(op.img);
@@ -688,10 +754,16 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
     const uint32_t bar_a = smem_u32(&s_bars.a_ready[s]), bar_d = smem_u32(&s_bars.d_ready[s]);
     uint32_t dcnt = 0;
     TQP_DECL
+#ifdef APG_PROFILE
+    if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[1][blockIdx.x][12] = clock64() - t_entry_;     // setup done
+#endif
     auto wait_d = [&]() {
       TQP(1);
       tq_wait(bar_d, dcnt & 1u, abort_flag);
       TQP(0);
+#ifdef APG_PROFILE
+      if (tid == 0 && dcnt == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[1][blockIdx.x][13] = clock64() - t_entry_;   // first D
+#endif
       ++dcnt;
       tcp::fence_after_thread_sync();
     };
@@ -801,9 +873,15 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
     }
     TQP(1);
     if (tid == 0) TQP_FLUSH(1, 0, 2);
+#ifdef APG_PROFILE
+    if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[1][blockIdx.x][14] = clock64() - t_entry_;     // warp 0 done
+#endif
   }
   tcp::fence_before_thread_sync();
   __syncthreads();
+#ifdef APG_PROFILE
+  if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[1][blockIdx.x][15] = clock64() - t_entry_;       // all warps done
+#endif
   // the stash / weight images must come from the forward of THIS path (workspace stamp, capi.cu)
   if (tid == 0 && stamp && (int)stamp[0] != want_stamp) s_abort = 1;
   if (tid == 0 && s_abort && my_tiles > 0)                     // poison the gradient: never a silent wrong result

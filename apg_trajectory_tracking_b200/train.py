@@ -254,7 +254,10 @@ class FusedTrainStep:
             compute.wait_event(ev)
             c_cur = sg["cur"][a:b]
             hc = None
-            if spec.system == "quad":
+            if spec.system == "quad" and spec.mode == "concurrent" and getattr(self.runner, "tcgen05", False):
+                # tcgen05 path: the kernels take the RAW samples (prepare_data runs in their prologue)
+                c_ins, c_inr, c_ref = None, None, sg["ref"][a:b]
+            elif spec.system == "quad":
                 want = ("in_state", "cur", "in_ref", "ref") if sg["in_state"] is not None else ("cur", "in_ref", "ref")
                 outs = {"cur": c_cur, "ref": sg["ref"][a:b], "in_ref": sg["in_ref"][a:b]}
                 if sg["in_state"] is not None:
@@ -285,8 +288,9 @@ class FusedTrainStep:
         sg["done"] = torch.cuda.Event()
         sg["done"].record(compute)
         # launches of this package's kernels: per chunk the rollout's 5 + the prepare kernels (quad / wing: 2)
+        raw_mode = spec.system == "quad" and spec.mode == "concurrent" and getattr(self.runner, "tcgen05", False)
         self.host_launches_per_step = len(bounds) * (self.kernel_launches_per_step +
-                                                     (0 if spec.system == "cartpole" else 2))
+                                                     (0 if (spec.system == "cartpole" or raw_mode) else 2))
         return st["loss"], self.grad
 
     def parameters(self):

@@ -42,6 +42,7 @@ extern "C" int hc_tq_step(const float* params, const float* in_state, const floa
   RolloutArgs a;
   memset(&a, 0, sizeof a);
   a.in_state = in_state; a.cur = cur; a.in_ref = in_ref; a.ref = ref;
+  a.raw_inputs = (in_state == nullptr && in_ref == nullptr) ? 1 : 0;   // capi.cu make_args: RAW samples, prepare in the prologue
   a.N = n; a.h = tc::H; a.ref_rows = tc::H; a.dt = dt;
   memcpy(a.pc.v, pc, sizeof(float) * MAX_PHYS);
   a.loss_partials = loss_partials; a.grad_partials = grad_partials; a.states_out = states_out; a.actions_out = actions_out;

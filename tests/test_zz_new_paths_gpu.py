@@ -786,6 +786,37 @@ def test_tc1_tcgen05_path_matches_legacy_mma_path(n):
     _check_tcgen05_vs_legacy(n)
 
 
+@pytest.mark.parametrize("n", [1, 129, 1000, 148 * 128 * 2 + 5])
+def test_tc3_raw_samples_in_the_kernel_prologue_equal_prepared_inputs(n):
+    """SURVEY 8f N1 as specified: with in_state = in_ref = NULL the tcgen05 kernels take the RAW (state, reference
+    rows) samples and run QuadDataset.prepare_data (dataset.py:155-204) in their prologue; loss, states, actions and
+    gradient equal the prepared-input call on the tensors the prepare kernels produce from the same samples."""
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    h, dt = 10, 0.1
+    params = B.default_init("quad", h, seed=n % 31)
+    case = SY.quad_case(n, h, dt, seed=n % 29)
+    gen = torch.Generator().manual_seed(n)
+    pos = (torch.rand(n, 3, generator=gen) * 6 - 3)
+    cur_raw = case["cur"].clone()
+    cur_raw[:, :3] = pos
+    ref_raw = case["ref"].clone()
+    ref_raw[:, :, :3] += pos[:, None, :]
+    flat = R.flatten_params(params).cuda()
+    prep = PR.prepare_quad(cur_raw.cuda(), ref_raw.cuda())
+    r = R.Rollout(R.RolloutSpec.quad_concurrent(h, dt), n, "cuda:0")
+    assert r.tcgen05
+    l0, s0, a0 = r.forward(flat, prep["in_state"], prep["cur"], prep["in_ref"], prep["ref"], want_states=True,
+                           want_actions=True)
+    l0, g0 = float(l0.item()), r.backward(1.0).clone()
+    l1, s1, a1 = r.forward(flat, None, cur_raw.cuda(), None, ref_raw.cuda(), want_states=True, want_actions=True)
+    l1, g1 = float(l1.item()), r.backward(1.0)
+    torch.cuda.synchronize()
+    assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
+    assert float((a1 - a0).abs().max()) <= 1e-5 and float((s1 - s0).abs().max()) <= 2e-5 * max(float(s0.abs().max()), 1.0)
+    assert rel_err(g1, g0) <= 1e-4
+
+
 def test_tc2_backward_after_a_forward_of_the_other_path_poisons_the_gradient():
     """the workspace is stamped by the forward that filled its stash; an adjoint of the tcgen05 path run on a
     workspace whose last forward was the legacy one must not return a silently wrong gradient"""

@@ -35,6 +35,12 @@ def main():
     print("one hand-off of tq_fwd (tile 0, slot 0, H1 -> fc2), cycles, mean / max over CTAs")
     for nm, v in seg:
         print(f"  {nm:62s} {v.mean():8.0f} {v.max():8.0f}")
+    for k, kn in ((0, "tq_fwd"), (1, "tq_dx")):
+        tl = out[k][:, 12:16].astype(np.float64)
+        print(f"{kn} timeline of thread 0, cycles from kernel entry, mean / min / max over CTAs")
+        for i, nm in enumerate(["setup done (TMEM, barriers, bulk copy issued)", "first accumulator ready",
+                                "warp 0 finished its tiles", "all warps finished"]):
+            print(f"  {nm:50s} {tl[:, i].mean():9.0f} {tl[:, i].min():9.0f} {tl[:, i].max():9.0f}")
     for k, kn in ((0, "tq_fwd"), (1, "tq_dx"), (2, "tq_dw")):
         m = out[k].mean(0); mx = out[k].max(0)
         print(kn)
