@@ -4,7 +4,7 @@
 //
 //   dW_l[out][in] = sum over drones dZ_l[drone][out] * X_l[drone][in]
 // as  D[M = in (+ a row of ones -> bias gradient)][N = out] += A[in][K = drone] * B[out][K = drone]^T  per 32-drone
-// panel, both operands K-major 128B-swizzled (raw, lo) images; the accumulators stay in TMEM for the whole launch.
+// panel; the accumulators stay in TMEM for a whole pass over the CTA's tiles.
 #pragma once
 #include "tc_layout.cuh"
 
@@ -19,9 +19,15 @@ enum BSrc { B_DZO = 0, B_DZ3, B_DZ2, B_DZ1, B_DZS, B_DZC };
 // one GEMM per (tile, op): A rows [0, a_rows) real, row a_rows = ones (if ones >= 0), the rest zero
 struct Op { int a_src, a_row0, a_rows, ones, b_src, b_row0, b_rows, N, d_col, first; };
 constexpr int NOPS = 10;
-// accumulator columns: fc_out [0,48) | fc3 [48,112) | fc2 [112,176) | fc1 rows 0..127 [176,240) | fc1 rows 128..223
-// [240,304) | states_in [304,368) | conv Toeplitz block [368,416)
-constexpr int C_WO = 0, C_W3 = 48, C_W2 = 112, C_W1A = 176, C_W1B = 240, C_WS = 304, C_WT = 368, C_TOTAL = 416;
+// Two PASSES over the CTA's tiles, so that the accumulators of one pass leave TMEM columns for the ring the A operand
+// is fed through (tq_dw_kernels.cu): pass 0 = every op but fc1 (288 columns), pass 1 = the two fc1 ops (128 columns).
+// Every operand panel is still read exactly once.  Accumulator columns, pass 0: fc_out [0,48) | fc3 [48,112) | fc2
+// [112,176) | states_in [176,240) | conv Toeplitz block [240,288); pass 1: fc1 rows 0..127 [0,64) | fc1 rows 128..223
+// [64,128).  The A ring starts at C_ARING in both passes.
+constexpr int C_WO = 0, C_W3 = 48, C_W2 = 112, C_WS = 176, C_WT = 240, C_W1A = 0, C_W1B = 64, C_ARING = 288;
+constexpr int NPASS = 2;
+APG_HD constexpr int pass_nops(int pass) { return pass == 0 ? 8 : 2; }
+APG_HD constexpr int pass_op(int pass, int k) { return pass == 0 ? (k < 3 ? k : k + 2) : 3 + k; }
 APG_HD Op op_of(int i) {
   if (i == 0) return {A_H3, 0, 64, 64, B_DZO, 0, MO, 48, C_WO, 1};
   if (i == 1) return {A_H2, 0, 64, 64, B_DZ3, 0, 64, 64, C_W3, 1};

@@ -19,8 +19,36 @@
 #ifdef APG_SIM
 #define APG_LAUNCH(grid, block, smem, stream, ...) \
   ::sim::Launcher((grid), (block), (size_t)(smem)).bind([&](auto&&... sim_args_) { __VA_ARGS__(sim_args_...); })
+#define APG_LAUNCH_PDL APG_LAUNCH
 #else
 #define APG_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
+#ifdef __CUDACC__
+// The same launch with programmatic stream serialization: the kernel's CTAs may start while the preceding kernel of
+// the stream is still draining (as its CTAs leave their SMs); the kernel itself executes griddepcontrol.wait
+// (tcp::griddep_wait) before it touches anything the preceding kernels wrote.  What it buys here: the 5-7 us between
+// the end of one 148-CTA kernel and the first instruction of the next (measured with %globaltimer, profiles/r2).
+namespace apg {
+template <typename... KArgs>
+struct PdlLaunch {
+  void (*kernel)(KArgs...);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  PdlLaunch(void (*k)(KArgs...), int grid, int block, size_t smem, cudaStream_t st) : kernel(k), cfg{} {
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  template <typename... Args>
+  void operator()(Args&&... args) { (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...); }
+};
+template <typename... KArgs>
+PdlLaunch<KArgs...> pdl_launch(void (*k)(KArgs...), int grid, int block, size_t smem, cudaStream_t st) {
+  return PdlLaunch<KArgs...>(k, grid, block, smem, st);
+}
+}  // namespace apg
+#define APG_LAUNCH_PDL(grid, block, smem, stream, ...) ::apg::pdl_launch(__VA_ARGS__, (grid), (block), (smem), (stream))
+#endif
 #endif
 
 namespace apg {

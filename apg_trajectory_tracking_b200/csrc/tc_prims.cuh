@@ -45,6 +45,8 @@ void fence_proxy_async_smem();
 void tmem_alloc512(uint32_t* slot_in_smem);
 void tmem_dealloc512(uint32_t addr);
 long long clock_now();
+void griddep_wait();
+void griddep_launch();
 #else
 // D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, one CTA
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -193,6 +195,10 @@ __device__ __forceinline__ void tmem_dealloc512(uint32_t addr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "n"(512) : "memory");
 }
 __device__ __forceinline__ long long clock_now() { return clock64(); }
+// programmatic dependent launch (kernels launched with APG_LAUNCH_PDL): wait = the preceding kernel of the stream has
+// completed and its writes are visible; launch = the following kernel's CTAs may start (they wait themselves)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 #endif
 
 }  // namespace tcp

@@ -1,16 +1,26 @@
 // Weight gradient of the quadrotor concurrent rollout as ONE streaming tcgen05 GEMM over the drone axis,
 //     dW_l[out][in] = sum over drones dZ_l[drone][out] * X_l[drone][in]          (loss.backward() of train_base.py:205),
 // on the two operand-image stashes written by tq_fwd_kernel (X_l) and tq_dx_kernel (dZ_l): tq_layout.cuh.
-// Accumulators of all layers resident in TMEM (416 columns) for the whole launch: D[M = in (+ ones row -> bias)][N = out].
+// Accumulators resident in TMEM, D[M = in (+ ones row -> bias)][N = out], in two passes over the CTA's tiles (pass 0:
+// every layer but fc1, 288 columns; pass 1: fc1, 128 columns - adj_dw_layout.cuh) so that 224 columns are left for the
+// ring the A operand is fed through.
 //
-// Pipeline (unit = one 32-drone panel of one op; a ring of 7 RAW stages of 24 KiB that the bulk copies land in, and a
-// ring of 2 LO stages that only live from conversion to the MMAs - the copies in flight are what hides the HBM latency,
-// so the raw ring is deep and the lo images do not take shared memory away from it):
-//   warp 0 lane 0   producer  : two 1-D bulk copies per unit (A panel, B panel) straight from the stash - the stash IS
-//                               the 128B-swizzled K-major image, so there is no loader arithmetic and no tensor map
-//   warps 2-9       converters: lo image = x - tf32(x) of each raw image (the tensor core truncates the raw fp32
-//                               image itself: that is the hi part), the constant ones rows of the bias gradients
-//   warp 1 lane 0   MMA issuer: per unit 4 k-steps x 3 MMAs (3xTF32), two tcgen05.commit free the raw and the lo stage
+// Pipeline (unit = one 32-drone panel of one op):
+//   warp 0       producer  : two 1-D bulk copies per unit (A panel, B panel) straight from the stash into a ring of
+//                            7 raw stages - the stash IS the 128B-swizzled K-major image, so there is no loader
+//                            arithmetic and no tensor map; the copies in flight are what hides the HBM latency
+//   warps 2-5    A feeders : thread = A row (= TMEM lane).  Reads its 128-byte row of the raw panel from shared memory
+//                            ONCE (conflict free: the swizzle spreads 8 rows over the 8 bank groups), splits it into
+//                            (raw, lo = x - tf32(x)) and writes both with tcgen05.st into a 7-stage ring of TMEM columns
+//                            (16 drones each; measured with 3 stages: every role waited on the round trip commit ->
+//                            feeder wake-up -> tcgen05.st -> issuer wake-up, ~1000 cycles per 3 stages).  Rows past the op's A rows are neither read nor written: row m of A
+//                            only ever reaches row m of D, and the epilogue ignores those rows
+//   warps 6-9    B feeders : lo image of the B panel into a ring of 6 shared-memory stages
+//   warp 1       MMA issuer: per unit 2 halves x 2 k-steps x 3 MMAs (3xTF32), A FROM TMEM, B from shared memory
+// Why A from TMEM (measured, profiles/r2): with both operands in shared memory every MMA re-read a full 128-row A panel
+// (16 KiB, three times per unit, also for the 16-row and 37-row ops) and the feeders wrote a second 16 KiB lo image:
+// ~144 KiB of shared-memory traffic per unit at 128 B/clk = the kernel's bound (1660 MMAs per CTA at 54 cycles each vs the
+// 32-cycle tensor floor).  Now shared memory sees the raw panels once each and the B panel three times.
 // HBM-bound by construction: 4.2 KB per drone.  Op list / accumulator columns / gradient map: adj_dw_layout.cuh.
 #include "tq_layout.cuh"
 #include "tc_prims.cuh"
@@ -32,19 +42,24 @@ namespace apg {
 
 namespace {
 
-constexpr int DWQ_CONV = 256;                                 // converter threads (warps 2..9)
-constexpr int DWQ_THREADS = 64 + DWQ_CONV;
-constexpr int NR = tq::DW_NRAW, NL = tq::DW_NLO;
-constexpr int STAGE = tq::DW_A_BYTES + tq::DW_B_BYTES;        // one raw or lo stage: A panel (128 rows) | B panel (64 rows)
-constexpr int DWQ_SMEM = 1024 + (NR + NL) * STAGE;
+constexpr int DWQ_THREADS = 320;                              // warps: producer, MMA issuer, 4 A feeders, 4 B feeders
+constexpr int DWQ_B_THREADS = 128;
+constexpr int NR = tq::DW_NRAW, NL = tq::DW_NLO, NTM = tq::DW_NTMEM;
+constexpr int STAGE = tq::DW_A_BYTES + tq::DW_B_BYTES;        // one raw stage: A panel (128 rows) | B panel (64 rows)
+constexpr int DWQ_T_FLOATS = (4 * tc::RD + 1) * 48;           // conv Toeplitz block between its flush and the fold
+constexpr int DWQ_SMEM = 1024 + NR * STAGE + NL * tq::DW_B_BYTES + ((DWQ_T_FLOATS * 4 + 1023) / 1024) * 1024;
 static_assert(DWQ_SMEM <= 232448, "stage rings do not fit in shared memory");
+static_assert(dw::C_ARING + NTM * 32 <= 512, "accumulators + A ring do not fit in TMEM");
 
 struct DwqBars {
   unsigned long long full[NR];                   // bulk copies landed (1 arrival + bytes)
-  unsigned long long rfree[NR];                  // MMAs that read the raw stage are complete (tcgen05.commit)
-  unsigned long long lo_ready[NL];               // lo images written (256 arrivals)
+  unsigned long long rfree[NR];                  // MMAs of the unit are complete (tcgen05.commit): raw stage reusable
+  unsigned long long lo_ready[NL];               // B lo image written (128 arrivals)
   unsigned long long lo_free[NL];                // MMAs that read the lo stage are complete (tcgen05.commit)
-  unsigned long long done;
+  unsigned long long a_ready[NTM];                // A columns written (4 arrivals: lane 0 of each feeder warp)
+  unsigned long long tfree[NTM];                  // MMAs that read the A columns are complete (tcgen05.commit)
+  unsigned long long done[dw::NPASS];            // accumulators of the pass are final (tcgen05.commit)
+  unsigned long long flushed;                    // pass-0 accumulators are in the partial (8 arrivals): columns reusable
 };
 
 __device__ __forceinline__ void dwq_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
@@ -73,6 +88,10 @@ __device__ __forceinline__ float4 lo_of(float4 x) {
   return l;
 }
 
+__device__ __forceinline__ uint32_t lo_bits(uint32_t x) {
+  return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xffffe000u));
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(DWQ_THREADS, 1)
@@ -86,6 +105,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef APG_PROFILE
   const long long tqp_k0_ = clock64();
+  if (threadIdx.x == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[2][blockIdx.x][16] = tq_globaltimer();
   long long tqp_k1_ = 0, tqp_k2_ = 0;
 #endif
   const int n = g.N;
@@ -94,6 +114,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
   volatile int* abort_flag = &s_abort;
   unsigned char* lo_base = base + NR * STAGE;
+  float* s_T = reinterpret_cast<float*>(lo_base + NL * tq::DW_B_BYTES);     // [37][48] conv Toeplitz block
 
   if (tid == 0) {
     for (int s = 0; s < NR; ++s) {
@@ -101,10 +122,15 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       tcp::mbar_init(smem_u32(&s_bars.rfree[s]), 1);
     }
     for (int s = 0; s < NL; ++s) {
-      tcp::mbar_init(smem_u32(&s_bars.lo_ready[s]), DWQ_CONV);
+      tcp::mbar_init(smem_u32(&s_bars.lo_ready[s]), DWQ_B_THREADS);
       tcp::mbar_init(smem_u32(&s_bars.lo_free[s]), 1);
     }
-    tcp::mbar_init(smem_u32(&s_bars.done), 1);
+    for (int s = 0; s < NTM; ++s) {
+      tcp::mbar_init(smem_u32(&s_bars.a_ready[s]), 4);
+      tcp::mbar_init(smem_u32(&s_bars.tfree[s]), 1);
+    }
+    for (int s = 0; s < dw::NPASS; ++s) tcp::mbar_init(smem_u32(&s_bars.done[s]), 1);
+    tcp::mbar_init(smem_u32(&s_bars.flushed), 8);
     s_abort = 0;
     tcp::fence_mbar_init();
   }
@@ -113,9 +139,62 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   __syncthreads();
   tcp::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
+  // launched with programmatic serialization behind the dX chain: the set-up above overlaps its tail
+  tcp::griddep_wait();
+  tcp::griddep_launch();
 #ifdef APG_PROFILE
   tqp_k1_ = clock64();
 #endif
+
+  // ---- accumulators of a pass -> this CTA's gradient partial, by the eight feeder warps: warp w reads TMEM lanes
+  // 32 (w & 3) .. +31 (= A rows) and one half of every region's columns.  The row -> gradient map (base + column *
+  // stride) is worked out ONCE per thread and region - measured: with the index arithmetic (divisions by 20, the switch
+  // of grad_index) inside the element loop on four warps this took 73 k cycles, a third of the kernel.
+  // Every entry of the partial is written exactly once per launch; unused tensors (ref_in.*) and padding are zeroed.
+  auto flush = [&](int pass) {
+    dwq_wait(smem_u32(&s_bars.done[pass]), 0, abort_flag);
+    tcp::fence_after_thread_sync();
+    const int r = (warp & 3) * 32 + lane, half = (warp - 2) >> 2;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int col0[6] = {dw::C_WO, dw::C_W3, dw::C_W2, dw::C_W1A, dw::C_W1B, dw::C_WS};
+    const int ncol[6] = {48, 64, 64, 64, 64, 64};
+#pragma unroll
+    for (int reg = 0; reg < 6; ++reg) {
+      if ((reg == 3 || reg == 4) != (pass == 1)) continue;      // fc1 regions belong to pass 1
+      // entry (r, n) -> P[i0 + n * stride]; i0 < 0: this row is padding in this region
+      const int i0 = dw::grad_index(y, reg, r, 0);
+      const int stride = i0 < 0 ? 0 : dw::grad_index(y, reg, r, 1) - i0;
+      const int nvalid = reg == 0 ? tc::MO : ncol[reg];
+      const int c_lo = half * (ncol[reg] / 2), c_hi = c_lo + ncol[reg] / 2;
+      for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+        uint32_t vb[8];
+        tcp::tmem_ld8(lane_addr + col0[reg] + c0, vb);
+        if (i0 >= 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (c0 + q < nvalid) P[i0 + (c0 + q) * stride] = __uint_as_float(vb[q]);
+        }
+      }
+    }
+    if (pass == 0) {
+      for (int c0 = half * 24; c0 < half * 24 + 24; c0 += 8) {
+        uint32_t vb[8];
+        tcp::tmem_ld8(lane_addr + dw::C_WT + c0, vb);
+        if (r <= 4 * tc::RD) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s_T[r * 48 + c0 + q] = __uint_as_float(vb[q]);   // folded after the last pass
+        }
+      }
+      // every tcgen05.ld above has completed (tmem_ld8 waits): the issuer may overwrite the columns
+      tcp::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) tcp::mbar_arrive(smem_u32(&s_bars.flushed));
+    }
+  };
+  for (int i = tid; i < y.n_params; i += DWQ_THREADS) {
+    const bool conv_w = i >= y.t_wc && i < y.t_wc + tc::NC * tc::RD * 3 + tc::NC;    // conv_ref weight + bias: at the end
+    if (!conv_w && (my_tiles == 0 || (i >= y.t_wr && i < y.t_br + HID))) P[i] = 0.f;
+  }
 
   if (warp == 0) {
     // ===================================================== producer (warp-uniform loop, the elected lane issues)
@@ -123,12 +202,13 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       const bool leader = tcp::elect_one();
       TQP_DECL
       int u = 0;
+      for (int pass = 0; pass < dw::NPASS; ++pass)
       for (int j = 0; j < my_tiles; ++j) {
         const int tile = (int)blockIdx.x + j * (int)gridDim.x;
         const unsigned char* fb = fstash + (size_t)tile * tq::F_TILE_BYTES;
         const unsigned char* zb = zstash + (size_t)tile * tq::Z_TILE_BYTES;
-        for (int i = 0; i < dw::NOPS; ++i) {
-          const tq::DwSrc src = tq::dw_src(i);
+        for (int k = 0; k < dw::pass_nops(pass); ++k) {
+          const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
           const uint32_t a_bytes = (uint32_t)src.a_rows * 128u, b_bytes = (uint32_t)src.b_rows * 128u;
           for (int p = 0; p < tq::NPANEL; ++p, ++u) {
             const int r = u % NR;
@@ -159,32 +239,52 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       const uint32_t raw0 = smem_u32(base), lo0 = smem_u32(lo_base);
       const uint64_t DESC_HI = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
       int u = 0;
+      for (int pass = 0; pass < dw::NPASS; ++pass) {
+      if (pass > 0 && my_tiles > 0) {                      // the columns of pass 0 must have been flushed
+        if (leader) dwq_wait(smem_u32(&s_bars.flushed), 0, abort_flag);
+        __syncwarp();
+        tcp::fence_after_thread_sync();
+      }
       for (int j = 0; j < my_tiles; ++j)
-        for (int i = 0; i < dw::NOPS; ++i) {
-          const dw::Op op = dw::op_of(i);
+        for (int k = 0; k < dw::pass_nops(pass); ++k) {
+          const dw::Op op = dw::op_of(dw::pass_op(pass, k));
           const uint32_t idesc = tc::idesc_tf32(128, op.N);
           const uint32_t d = tmem + op.d_col;
           for (int p = 0; p < tq::NPANEL; ++p, ++u) {
             const int r = u % NR, l = u % NL;
-            // only the issuing lane polls: lo_ready[l] can complete AGAIN (unit u + NL) as soon as this unit's
-            // MMAs are committed, so a lane that looked late would see the parity it is waiting for already gone
+            // only the issuing lane polls: a barrier of a short ring can complete AGAIN as soon as this unit's MMAs
+            // are committed, so a lane that looked late would see the parity it is waiting for already gone
             if (leader) dwq_wait(smem_u32(&s_bars.lo_ready[l]), (uint32_t)(u / NL) & 1u, abort_flag);
             __syncwarp();
             TQP(0);
-            tcp::fence_after_thread_sync();
-            // descriptors: constant high word (SBO 1024, version, SWIZZLE_128B), low word = address >> 4 | LBO field;
-            // k-step ks adds 2 (32 bytes >> 4)
-            uint32_t ar = ((raw0 + (uint32_t)r * STAGE) >> 4) | (1u << 16), br = ar + (tq::DW_A_BYTES >> 4);
-            uint32_t al = ((lo0 + (uint32_t)l * STAGE) >> 4) | (1u << 16), bl = al + (tq::DW_A_BYTES >> 4);
+            // B descriptors: constant high word (SBO 1024, version, SWIZZLE_128B), low word = address >> 4 | LBO
+            // field; k-step ks adds 2 (32 bytes >> 4)
+            uint32_t br = ((raw0 + (uint32_t)r * STAGE + tq::DW_A_BYTES) >> 4) | (1u << 16);
+            uint32_t bl = ((lo0 + (uint32_t)l * tq::DW_B_BYTES) >> 4) | (1u << 16);
             const bool clear = (j == 0) && op.first && (p == 0);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks, ar += 2, br += 2, al += 2, bl += 2) {
-              const uint64_t dah = DESC_HI | ar, dal = DESC_HI | al, dbh = DESC_HI | br, dbl = DESC_HI | bl;
-              if (leader) {
-                tcp::mma_ss(d, dal, dbh, idesc, (ks > 0 || !clear) ? 1u : 0u);
-                tcp::mma_ss(d, dah, dbl, idesc, 1u);
-                tcp::mma_ss(d, dah, dbh, idesc, 1u);
+            for (int hh = 0; hh < 2; ++hh) {
+              const int h = 2 * u + hh, ts = h % NTM;
+              TQP(1);
+              if (leader) dwq_wait(smem_u32(&s_bars.a_ready[ts]), (uint32_t)(h / NTM) & 1u, abort_flag);
+              __syncwarp();
+              TQP(2);
+              tcp::fence_after_thread_sync();
+              const uint32_t a_hi = tmem + dw::C_ARING + ts * 32, a_lo = a_hi + 16;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk, br += 2, bl += 2) {
+                const uint64_t dbh = DESC_HI | br, dbl = DESC_HI | bl;
+#ifdef DWQ_PROBE_NO_MMA      // timing experiment: how fast can the operands be delivered at all (wrong results)
+                if (false) {
+#else
+                if (leader) {
+#endif
+                  tcp::mma_ts(d, a_lo + kk * 8, dbh, idesc, (hh + kk > 0 || !clear) ? 1u : 0u);
+                  tcp::mma_ts(d, a_hi + kk * 8, dbl, idesc, 1u);
+                  tcp::mma_ts(d, a_hi + kk * 8, dbh, idesc, 1u);
+                }
               }
+              if (leader) tcp::commit(smem_u32(&s_bars.tfree[ts]));
             }
             if (leader) {
               tcp::commit(smem_u32(&s_bars.rfree[r]));    // both stages are free once these MMAs have read them
@@ -194,105 +294,117 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
             TQP(1);
           }
         }
+      if (leader) tcp::commit(smem_u32(&s_bars.done[pass]));    // the accumulators of this pass are final
+      __syncwarp();
+      }
       if (leader) TQP_FLUSH(2, 2, 2);
-      if (leader) tcp::commit(smem_u32(&s_bars.done));    // all accumulators final
+#ifdef APG_PROFILE
+      if (leader && blockIdx.x < 148) TQ_PROF_ARRAY[2][blockIdx.x][19] = tqp_a_[2];          // wait a_ready
+#endif
     }
-  } else {
-    // ===================================================== converters: lo images + constant ones rows
-    const int ct = tid - 64;
+  } else if (warp < 6) {
+    // ===================================================== A feeders: raw panel row -> (raw, lo) TMEM columns
+    const int q = warp & 3, row = q * 32 + lane, ph = row & 7;
+    const uint32_t a_cols = tmem + ((uint32_t)(q * 32) << 16) + dw::C_ARING;
     TQP_DECL
     int u = 0;
+    for (int pass = 0; pass < dw::NPASS; ++pass) {
     for (int j = 0; j < my_tiles; ++j)
-      for (int i = 0; i < dw::NOPS; ++i) {
-        const tq::DwSrc src = tq::dw_src(i);
-        const int na = src.a_rows * 8, nb = src.b_rows * 8;  // 16-byte chunks
+      for (int k = 0; k < dw::pass_nops(pass); ++k) {
+        const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
+        // rows of this warp that exist in the op (the ones row included); a warp without any neither reads nor writes
+        const bool warp_active = q * 32 < src.a_rows + (src.ones >= 0 ? 1 : 0);
+        const bool has_row = row < src.a_rows;
+        const uint32_t fill = (row == src.ones) ? 0x3f800000u : 0u;       // constant ones row of a bias gradient
+        for (int p = 0; p < tq::NPANEL; ++p, ++u) {
+          const int r = u % NR;
+          uint4 v[8];
+          if (warp_active) {
+            dwq_wait(smem_u32(&s_bars.full[r]), (uint32_t)(u / NR) & 1u, abort_flag);
+            TQP(0);
+            // logical 16-byte chunk c (drones 4c .. 4c+3) of row `row` sits at chunk c ^ (row & 7) of its 128 bytes
+            const unsigned char* a_row = base + r * STAGE + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              v[c] = has_row ? *reinterpret_cast<const uint4*>(a_row + ((c ^ ph) << 4)) : make_uint4(fill, fill, fill, fill);
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int h = 2 * u + hh, ts = h % NTM;
+            if (h >= NTM) dwq_wait(smem_u32(&s_bars.tfree[ts]), (uint32_t)(h / NTM - 1) & 1u, abort_flag);
+            TQP(1);
+            tcp::fence_after_thread_sync();
+#ifdef DWQ_PROBE_NO_FEED
+            if (false) {
+#else
+            if (warp_active) {
+#endif
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 x = v[4 * hh + c];
+                hi[4 * c + 0] = x.x; hi[4 * c + 1] = x.y; hi[4 * c + 2] = x.z; hi[4 * c + 3] = x.w;
+                lo[4 * c + 0] = has_row ? lo_bits(x.x) : 0u; lo[4 * c + 1] = has_row ? lo_bits(x.y) : 0u;
+                lo[4 * c + 2] = has_row ? lo_bits(x.z) : 0u; lo[4 * c + 3] = has_row ? lo_bits(x.w) : 0u;
+              }
+              tcp::tmem_st16(a_cols + ts * 32, hi);          // the tensor core truncates the raw image: the hi part
+              tcp::tmem_st16(a_cols + ts * 32 + 16, lo);
+              tcp::wait_st();
+            }
+            tcp::fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) tcp::mbar_arrive(smem_u32(&s_bars.a_ready[ts]));
+            TQP(2);
+          }
+        }
+      }
+    if (my_tiles > 0) flush(pass);
+    TQP(3);
+    }
+    if (tid == 64) TQP_FLUSH(2, 4, 4);
+  } else {
+    // ===================================================== B feeders: lo image of the B panel
+    const int bt = tid - 192;
+    TQP_DECL
+    int u = 0;
+    for (int pass = 0; pass < dw::NPASS; ++pass) {
+    for (int j = 0; j < my_tiles; ++j)
+      for (int k = 0; k < dw::pass_nops(pass); ++k) {
+        const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
+        const int nb = src.b_rows * 8;                       // 16-byte chunks
         for (int p = 0; p < tq::NPANEL; ++p, ++u) {
           const int r = u % NR, l = u % NL;
           dwq_wait(smem_u32(&s_bars.full[r]), (uint32_t)(u / NR) & 1u, abort_flag);
           TQP(0);
           if (u >= NL) dwq_wait(smem_u32(&s_bars.lo_free[l]), (uint32_t)(u / NL - 1) & 1u, abort_flag);
           TQP(1);
-          float4* a_raw = reinterpret_cast<float4*>(base + r * STAGE);
-          float4* b_raw = reinterpret_cast<float4*>(base + r * STAGE + tq::DW_A_BYTES);
-          float4* a_lo = reinterpret_cast<float4*>(lo_base + l * STAGE);
-          float4* b_lo = reinterpret_cast<float4*>(lo_base + l * STAGE + tq::DW_A_BYTES);
-          {
-            // all loads first (up to 4 + 2 chunks of 16 bytes per thread), then split and store: one exposed
-            // shared-memory latency per unit instead of six
-            float4 va[4], vb[2];
+          const float4* b_raw = reinterpret_cast<const float4*>(base + r * STAGE + tq::DW_A_BYTES);
+          float4* b_lo = reinterpret_cast<float4*>(lo_base + l * tq::DW_B_BYTES);
+          float4 vb[4];
+#ifndef DWQ_PROBE_NO_FEED
 #pragma unroll
-            for (int i = 0; i < 4; ++i) if (ct + i * DWQ_CONV < na) va[i] = a_raw[ct + i * DWQ_CONV];
+          for (int kk = 0; kk < 4; ++kk) if (bt + kk * DWQ_B_THREADS < nb) vb[kk] = b_raw[bt + kk * DWQ_B_THREADS];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) if (ct + i * DWQ_CONV < nb) vb[i] = b_raw[ct + i * DWQ_CONV];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (ct + i * DWQ_CONV < na) a_lo[ct + i * DWQ_CONV] = lo_of(va[i]);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) if (ct + i * DWQ_CONV < nb) b_lo[ct + i * DWQ_CONV] = lo_of(vb[i]);
-          }
-          if (src.ones >= 0 && ct < 64) {                    // 8-row group [ones, ones + 8): row `ones` = 1, rest 0
-            const float v = (ct >> 3) == 0 ? 1.f : 0.f;
-            a_raw[src.ones * 8 + ct] = make_float4(v, v, v, v);
-            a_lo[src.ones * 8 + ct] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int kk = 0; kk < 4; ++kk) if (bt + kk * DWQ_B_THREADS < nb) b_lo[bt + kk * DWQ_B_THREADS] = lo_of(vb[kk]);
+#endif
           tcp::fence_proxy_async_smem();                     // generic writes -> tensor core reads
           tcp::mbar_arrive(smem_u32(&s_bars.lo_ready[l]));
           TQP(2);
         }
       }
-    if (ct == 0) TQP_FLUSH(2, 4, 3);
+    if (my_tiles > 0) flush(pass);
+    TQP(3);
+    }
+    if (bt == 0) TQP_FLUSH(2, 11, 4);
   }
 #ifdef APG_PROFILE
   tqp_k2_ = clock64();
 #endif
 
-  // ===================================================== epilogue: accumulators -> this CTA's gradient partial
-  // unused tensors (ref_in.*) and padding stay zero; every entry of the partial is written exactly once
-  for (int i = tid; i < y.n_params; i += DWQ_THREADS) {
-    const bool conv_w = i >= y.t_wc && i < y.t_wc + tc::NC * tc::RD * 3 + tc::NC;    // conv_ref weight + bias: below
-    if (!conv_w && (my_tiles == 0 || (i >= y.t_wr && i < y.t_br + HID))) P[i] = 0.f;
-  }
-  if (my_tiles > 0 && warp >= 2) {
-    // the eight converter warps: warp w reads TMEM lanes 32 (w & 3) .. +31 (= A rows) and one half of every region's
-    // columns.  The row -> gradient map (base + column * stride) is worked out ONCE per thread and region - measured:
-    // with the index arithmetic (divisions by 20, the switch of grad_index) inside the element loop on four warps this
-    // epilogue took 73 k cycles, a third of the kernel.
-    dwq_wait(smem_u32(&s_bars.done), 0, abort_flag);
-    tcp::fence_after_thread_sync();
-    const int r = (warp & 3) * 32 + lane, half = (warp - 2) >> 2;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* s_T = reinterpret_cast<float*>(base);               // [37][48] conv Toeplitz block (stage memory is free)
-    const int col0[6] = {dw::C_WO, dw::C_W3, dw::C_W2, dw::C_W1A, dw::C_W1B, dw::C_WS};
-    const int ncol[6] = {48, 64, 64, 64, 64, 64};
-#pragma unroll
-    for (int reg = 0; reg < 6; ++reg) {
-      // entry (r, n) -> P[i0 + n * stride]; i0 < 0: this row is padding in this region
-      const int i0 = dw::grad_index(y, reg, r, 0);
-      const int stride = i0 < 0 ? 0 : dw::grad_index(y, reg, r, 1) - i0;
-      const int nvalid = reg == 0 ? tc::MO : ncol[reg];
-      const int c_lo = half * (ncol[reg] / 2), c_hi = c_lo + ncol[reg] / 2;
-      for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-        uint32_t vb[8];
-        tcp::tmem_ld8(lane_addr + col0[reg] + c0, vb);
-        if (i0 >= 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (c0 + q < nvalid) P[i0 + (c0 + q) * stride] = __uint_as_float(vb[q]);
-        }
-      }
-    }
-    for (int c0 = half * 24; c0 < half * 24 + 24; c0 += 8) {
-      uint32_t vb[8];
-      tcp::tmem_ld8(lane_addr + dw::C_WT + c0, vb);
-      if (r <= 4 * tc::RD) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s_T[r * 48 + c0 + q] = __uint_as_float(vb[q]);
-      }
-    }
-  }
+  // ===================================================== tail: fold the conv Toeplitz block
   tcp::fence_before_thread_sync();
   __syncthreads();
   if (my_tiles > 0) {
-    const float* s_T = reinterpret_cast<const float*>(base);
     for (int i = tid; i < tc::NC * tc::RD * 3 + tc::NC; i += DWQ_THREADS) {
       float v;
       if (i < tc::NC * tc::RD * 3) {
@@ -313,6 +425,8 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
     TQ_PROF_ARRAY[2][blockIdx.x][8] = tqp_k1_ - tqp_k0_;
     TQ_PROF_ARRAY[2][blockIdx.x][9] = tqp_k2_ - tqp_k1_;
     TQ_PROF_ARRAY[2][blockIdx.x][10] = clock64() - tqp_k2_;
+    TQ_PROF_ARRAY[2][blockIdx.x][17] = tq_globaltimer();
+    TQ_PROF_ARRAY[2][blockIdx.x][18] = clock64() - tqp_k0_;
   }
 #endif
 }
@@ -321,6 +435,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
 // order -> bitwise reproducible; the partials are already in torch order)
 __global__ void __launch_bounds__(128) apg_reduce4_kernel(const float* __restrict__ partials, int ncta, int n,
                                                           float scale, float* __restrict__ grad) {
+  tcp::griddep_wait();                                        // the partials of the kernel before are complete
   __shared__ float s_part[dw::RED_SLICES][32];
   const int pl = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + pl;
@@ -337,6 +452,7 @@ __global__ void __launch_bounds__(128) apg_reduce4_sgd_kernel(const float* __res
                                                               float scale, float* __restrict__ grad,
                                                               float* __restrict__ param, float* __restrict__ buf,
                                                               float lr, float momentum) {
+  tcp::griddep_wait();                                        // the partials of the kernel before are complete
   __shared__ float s_part[dw::RED_SLICES][32];
   const int pl = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + pl;
@@ -355,12 +471,12 @@ __global__ void __launch_bounds__(128) apg_reduce4_sgd_kernel(const float* __res
 
 cudaError_t launch_reduce_grad4_sgd(const float* partials, int ncta, int n, float scale, float* grad, float* param,
                                     float* buf, float lr, float momentum, cudaStream_t st) {
-  APG_LAUNCH((n + 31) / 32, 128, 0, st, apg_reduce4_sgd_kernel)(partials, ncta, n, scale, grad, param, buf, lr, momentum);
+  APG_LAUNCH_PDL((n + 31) / 32, 128, 0, st, apg_reduce4_sgd_kernel)(partials, ncta, n, scale, grad, param, buf, lr, momentum);
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_grad4(const float* partials, int ncta, int n, float scale, float* grad, cudaStream_t st) {
-  APG_LAUNCH((n + 31) / 32, 128, 0, st, apg_reduce4_kernel)(partials, ncta, n, scale, grad);
+  APG_LAUNCH_PDL((n + 31) / 32, 128, 0, st, apg_reduce4_kernel)(partials, ncta, n, scale, grad);
   return cudaGetLastError();
 }
 
@@ -368,7 +484,7 @@ cudaError_t launch_tq_dw(const HutterLayout& y, const RolloutArgs& a, const unsi
                          const unsigned char* zstash, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tq_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWQ_SMEM);
   if (e != cudaSuccess) return e;
-  APG_LAUNCH(grid, DWQ_THREADS, DWQ_SMEM, st, tq_dw_kernel)(y, a, fstash, zstash);
+  APG_LAUNCH_PDL(grid, DWQ_THREADS, DWQ_SMEM, st, tq_dw_kernel)(y, a, fstash, zstash);
   return cudaGetLastError();
 }
 

@@ -73,11 +73,13 @@ inline float tq_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 #else
 __device__ __forceinline__ float tq_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tq_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// branch-free tanh: 1 - 2 / (exp(2x) + 1) on the SFU (absolute error <= 3e-7, saturates correctly for large |x|) and,
-// below |x| = 0.25, an odd Taylor polynomial (the SFU form loses RELATIVE accuracy near 0: 1 - 2/a cancels).  The
-// relative accuracy matters: the batch gradient is a sum with ~300x cancellation at N = 65536, and with the SFU form
-// alone an ulp-level change of the inputs moved the gradient by 5e-4 of its norm (profiles/r2, bench raw-input check);
-// with the polynomial it is 1e-5.  -DTQ_TANH_SFU_ONLY drops the polynomial (timing experiments only).
+// tanh as ONE rational function x P(x^2) / Q(x^2) on |x| <= 7.905 (degree 13 / 6 minimax, the coefficients of Eigen's
+// generic_fast_tanh_float; relative error <= 4e-7 over the whole range INCLUDING x -> 0, checked against fp64 in
+// tests/test_tanh_rational_host.py): 13 FMA-pipe instructions + one SFU reciprocal per value.
+// Why not the SFU form 1 - 2 / (exp(2x) + 1): its error is ABSOLUTE (3e-7: the result cancels near 0), and the batch
+// gradient is a sum with ~300x cancellation at N = 65536 - with it an ulp-level change of the inputs moved the gradient
+// by 5e-4 of its norm (profiles/r2, bench raw-input check); and it costs two SFU operations per value on an SFU-bound
+// epilogue.  -DTQ_TANH_SFU_ONLY / -DTQ_TANH_SFU_POLY keep the two earlier forms for timing experiments.
 __device__ __forceinline__ float tq_tanh_small(float x) {
   const float x2 = x * x;
   float p = fmaf(x2, 0.0218694885f, -0.0539682540f);
@@ -85,16 +87,27 @@ __device__ __forceinline__ float tq_tanh_small(float x) {
   p = fmaf(x2, p, -0.333333333f);
   return fmaf(x * x2, p, x);
 }
+__device__ __forceinline__ float tq_tanh_rational(float x) {
+  x = fminf(fmaxf(x, -7.90531110763549805f), 7.90531110763549805f);
+  const float x2 = x * x;
+  float p = fmaf(x2, -2.76076847742355e-16f, 2.00018790482477e-13f);
+  p = fmaf(x2, p, -8.60467152213735e-11f);
+  p = fmaf(x2, p, 5.12229709037114e-08f);
+  p = fmaf(x2, p, 1.48572235717979e-05f);
+  p = fmaf(x2, p, 6.37261928875436e-04f);
+  p = fmaf(x2, p, 4.89352455891786e-03f);
+  float q = fmaf(x2, 1.19825839466702e-06f, 1.18534705686654e-04f);
+  q = fmaf(x2, q, 2.26843463243900e-03f);
+  q = fmaf(x2, q, 4.89352518554385e-03f);
+  return (x * p) * tq_rcp(q);
+}
 __device__ __forceinline__ float tq_sigmoid(float x) { return tq_rcp(1.f + tq_ex2(x * -1.442695041f)); }
 #endif
-// tanh of two values with THREE SFU operations instead of four: 1/a and 1/b from one reciprocal of a*b.  The SFU
-// (16 lanes per SM) is what a tanh epilogue of a 128-drone tile waits for (measured, profiles/r2): 1024 cycles per
-// 64-wide layer with two SFU operations per element.  |x| is clamped to 15 (tanh = +-1 in fp32 beyond 9) so that a*b
-// stays finite.
+// tanh of two values (the SFU forms share one reciprocal between the two: 1/a and 1/b from 1/(a*b))
 __device__ __forceinline__ void tq_tanh2(float x0, float x1, float* y0, float* y1) {
 #ifdef APG_TC_SIM
   *y0 = tanhf(x0); *y1 = tanhf(x1);
-#else
+#elif defined(TQ_TANH_SFU_ONLY) || defined(TQ_TANH_SFU_POLY)
   const float c0 = fminf(fmaxf(x0, -15.f), 15.f);
   const float c1 = fminf(fmaxf(x1, -15.f), 15.f);
   const float a0 = tq_ex2(c0 * 2.885390082f) + 1.f, a1 = tq_ex2(c1 * 2.885390082f) + 1.f;
@@ -106,6 +119,9 @@ __device__ __forceinline__ void tq_tanh2(float x0, float x1, float* y0, float* y
   *y0 = fabsf(x0) < 0.25f ? tq_tanh_small(x0) : b0;
   *y1 = fabsf(x1) < 0.25f ? tq_tanh_small(x1) : b1;
 #endif
+#else
+  *y0 = tq_tanh_rational(x0);
+  *y1 = tq_tanh_rational(x1);
 #endif
 }
 
@@ -139,15 +155,24 @@ __device__ __forceinline__ void a_operand_ready(uint32_t bar) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) tcp::mbar_arrive(bar);
 }
-// element e (= row * 9 + c) of the policy's reference input built from the RAW reference rows of one drone
-// (QuadDataset.prepare_data, dataset.py:170-201): [ref_pos - pos | ref_vel | ref_vel - vel] per row
-__device__ __forceinline__ float raw_in_ref(const float* ref_drone, int e, const float* pos, const float* vel, bool live) {
+// element K (compile-time, = row * 9 + c) of a window of the policy's reference input, built from the RAW reference
+// rows of one drone starting at `rows` (QuadDataset.prepare_data, dataset.py:170-201):
+// [ref_pos - pos | ref_vel | ref_vel - vel] per row
+template <int K>
+__device__ __forceinline__ float raw_in_ref(const float* rows, const float (&pos)[3], const float (&vel)[3], bool live) {
+  constexpr int r = K / 9, c = K % 9;
   if (!live) return 0.f;
-  const int r = e / 9, c = e - 9 * r;
-  const float* row = ref_drone + 9 * r;
-  if (c < 3) return row[c] - pos[c];
-  if (c < 6) return row[6 + (c - 3)];
-  return row[6 + (c - 6)] - vel[c - 6];
+  if (c < 3) return rows[9 * r + c] - pos[c];
+  if (c < 6) return rows[9 * r + 6 + (c - 3)];
+  return rows[9 * r + 6 + (c - 6)] - vel[c - 6];
+}
+template <int K0, int N, int I = 0>
+__device__ __forceinline__ void raw_window(float* x, const float* rows, const float (&pos)[3], const float (&vel)[3],
+                                           bool live) {
+  if constexpr (I < N) {
+    x[I] = raw_in_ref<K0 + I>(rows, pos, vel, live);
+    raw_window<K0, N, I + 1>(x, rows, pos, vel, live);
+  }
 }
 // L2 prefetch of the 128-byte lines [first, first + nlines) of a contiguous region, spread over the lanes of a warp
 __device__ __forceinline__ void prefetch_lines(const unsigned char* p, int nlines, int lane) {
@@ -215,8 +240,9 @@ __device__ __forceinline__ void issue_series(const OpRec op, uint32_t slot, uint
 }
 
 // common prologue: barriers, TMEM, bulk copies of the weight images; returns the TMEM base
+// (wait_first: the weight images are written by the kernel just before this one in the stream)
 __device__ __forceinline__ uint32_t tq_setup(TqBars& bars, uint32_t* s_tmem, int* s_abort, unsigned char* base,
-                                             const unsigned char* blob, int blob_bytes) {
+                                             const unsigned char* blob, int blob_bytes, bool wait_first) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -231,6 +257,7 @@ __device__ __forceinline__ uint32_t tq_setup(TqBars& bars, uint32_t* s_tmem, int
   tcp::fence_before_thread_sync();
   __syncthreads();
   tcp::fence_after_thread_sync();
+  if (wait_first) tcp::griddep_wait();
   if (warp == TQ_EPI_WARPS && lane == 0) {
     const uint32_t bar = smem_u32(&bars.w_ready);
     tcp::mbar_expect_tx(bar, (uint32_t)blob_bytes);
@@ -246,10 +273,14 @@ __device__ __forceinline__ uint32_t tq_setup(TqBars& bars, uint32_t* s_tmem, int
 __global__ void tq_pack_kernel(const float* __restrict__ params, const HutterLayout y, unsigned char* __restrict__ blob,
                                unsigned char* __restrict__ tblob) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  tcp::griddep_launch();                                      // the forward chain may set itself up meanwhile
   if (e < PAIRS_TOTAL + B_TOTAL) pack_body(e, params, y, blob);
   else if (e - (PAIRS_TOTAL + B_TOTAL) < tq::TPAIRS_TOTAL) tq::pack_t_body(e - (PAIRS_TOTAL + B_TOTAL), params, y, tblob);
 }
 
+// RAW: `cur` / `ref` are raw samples and prepare_data runs here (two instantiations: no run-time branches, no
+// second copy of the input code in the instruction stream)
+template <bool RAW>
 __global__ void __launch_bounds__(TQ_THREADS, 1)
     tq_fwd_kernel(const unsigned char* __restrict__ blob, const RolloutArgs g, unsigned char* __restrict__ fstash) {
   APG_TC_DYNAMIC_SMEM(smem_raw);
@@ -262,13 +293,16 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef APG_PROFILE
   const long long t_entry_ = clock64();
+  if (threadIdx.x == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][16] = tq_globaltimer();
 #endif
   if (tid < NOPS) {
     const Op op = op_of(tid);
     const uint32_t whi = smem_u32(base + op.img_off);
     s_ops[tid] = make_oprec(whi, whi + img_bytes(op.rows, op.K), op.K, op.K, op.N, op.d_col, op.clear ? 0 : 1);
   }
-  const uint32_t tmem = tq_setup(s_bars, &s_tmem, &s_abort, base, blob, BLOB_BYTES);
+  // launched with programmatic serialization behind the pack kernel: everything up to the weight copy overlaps its tail
+  const uint32_t tmem = tq_setup(s_bars, &s_tmem, &s_abort, base, blob, BLOB_BYTES, true);
+  tcp::griddep_launch();
   const int n = g.N;
   const int ntiles = (n + TMT - 1) / TMT;
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -350,7 +384,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       if (j + 2 < my_tiles && hf == 0) {                       // next tile of this slot: its inputs into L2 now
         const size_t d0n = ((size_t)tile + 2 * (size_t)gridDim.x) * TMT + (size_t)(warp & 3) * 32;
         if (d0n + 32 <= (size_t)n) {
-          if (g.raw_inputs) {
+          if (RAW) {
             prefetch_lines(reinterpret_cast<const unsigned char*>(g.ref + d0n * REFW), 32 * REFW * 4 / 128, lane);
             prefetch_lines(reinterpret_cast<const unsigned char*>(g.cur + d0n * 12), 32 * 12 * 4 / 128, lane);
           } else {
@@ -393,14 +427,14 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       float cpos[3] = {0.f, 0.f, 0.f}, cvel[3] = {0.f, 0.f, 0.f};
       {
         float x0[8];
-        if (g.raw_inputs) {
+        if (RAW) {
           float st12[12], f15[16];
 #pragma unroll
           for (int q = 0; q < 12; ++q) st12[q] = live ? g.cur[drone * 12 + q] : 0.f;
           Quad<float>::features(st12, f15);
           f15[15] = 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) x0[k] = live ? f15[hf * 8 + k] : 0.f;
+          for (int k = 0; k < 8; ++k) x0[k] = live ? (hf ? f15[8 + k] : f15[k]) : 0.f;   // (no dynamic indexing)
 #pragma unroll
           for (int c = 0; c < 3; ++c) { cpos[c] = st12[c]; cvel[c] = st12[6 + c]; }
         } else {
@@ -432,9 +466,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
         const SetPtr sp_w = set_ptr(tb, tq::O_WIN + tq::R_WIN * gq, tq::R_WIN, row);
         if (hf == 0) {
           float x[24];
-          if (g.raw_inputs) {
-#pragma unroll
-            for (int k = 0; k < 24; ++k) x[k] = raw_in_ref(g.ref + drone * REFW, 18 * gq + k, cpos, cvel, live);
+          if (RAW) {
+            raw_window<0, 24>(x, g.ref + drone * REFW + 18 * gq, cpos, cvel, live);
           } else {
 #pragma unroll
             for (int k = 0; k < 24; k += 2) {
@@ -450,9 +483,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           for (int k = 0; k < 24; ++k) set_store(sp_w, k, x[k]);
         } else {
           float x[16];
-          if (g.raw_inputs) {
-#pragma unroll
-            for (int k = 0; k < 12; ++k) x[k] = raw_in_ref(g.ref + drone * REFW, 18 * gq + 24 + k, cpos, cvel, live);
+          if (RAW) {
+            raw_window<24, 12>(x, g.ref + drone * REFW + 18 * gq, cpos, cvel, live);
           } else {
 #pragma unroll
             for (int k = 0; k < 12; k += 2) {
@@ -543,6 +575,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   __syncthreads();
 #ifdef APG_PROFILE
   if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][15] = clock64() - t_entry_;       // all warps done
+  if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[0][blockIdx.x][17] = tq_globaltimer();
 #endif
   if (tid == 0 && s_abort && my_tiles > 0)                     // poison: the dynamics kernel turns it into a NaN loss
     *reinterpret_cast<float*>(fstash + (size_t)blockIdx.x * tq::F_TILE_BYTES + tq::set_base(tq::O_ACT)) =
@@ -570,6 +603,8 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
   const int n = g.N;
   const int nhalf = ((n + TMT - 1) / TMT) * (TMT / TD);       // half tiles (dead drones of a ragged tile included)
   float my_loss = 0.f;
+  tcp::griddep_wait();                                        // the forward chain has completed (actions in the stash)
+  tcp::griddep_launch();                                      // AFTER the wait: whoever starts now knows that too
   // the horizon loops are NOT unrolled (measured: the unrolled body thrashed the instruction cache, 6 of 10 issue
   // slots lost to instruction fetch); actions / logit gradients go straight from / to the stash sets per step
   for (int hb = blockIdx.x; hb < nhalf; hb += gridDim.x) {
@@ -696,6 +731,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef APG_PROFILE
   const long long t_entry_ = clock64();
+  if (threadIdx.x == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[1][blockIdx.x][16] = tq_globaltimer();
 #endif
   if (tid < tq::NXS) {
     const tq::XOp op = tq::xop_of(tid);
@@ -703,7 +739,12 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
     const uint32_t whi = smem_u32(base + im.off) + (uint32_t)(op.row0 >> 3) * (uint32_t)((im.K >> 2) * 128);
     s_ops[tid] = make_oprec(whi, whi + img_bytes(im.rows, im.K), im.K, op.K, op.N, tq::XC_D + op.d_col, 0);
   }
-  const uint32_t tmem = tq_setup(s_bars, &s_tmem, &s_abort, base, tblob, tq::TBLOB_BYTES);
+  // launched with programmatic serialization behind the dynamics kernel.  The transposed weight images were written
+  // by the pack kernel, which had completed before the forward chain (two kernels back) passed its own wait: their
+  // copy starts before this kernel's wait and overlaps the tail of the dynamics kernel.
+  const uint32_t tmem = tq_setup(s_bars, &s_tmem, &s_abort, base, tblob, tq::TBLOB_BYTES, false);
+  tcp::griddep_wait();
+  tcp::griddep_launch();
   const int n = g.N;
   const int ntiles = (n + TMT - 1) / TMT;
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -881,6 +922,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
   __syncthreads();
 #ifdef APG_PROFILE
   if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[1][blockIdx.x][15] = clock64() - t_entry_;       // all warps done
+  if (tid == 0 && blockIdx.x < 148) TQ_PROF_ARRAY[1][blockIdx.x][17] = tq_globaltimer();
 #endif
   // the stash / weight images must come from the forward of THIS path (workspace stamp, capi.cu)
   if (tid == 0 && stamp && (int)stamp[0] != want_stamp) s_abort = 1;
@@ -914,9 +956,12 @@ cudaError_t launch_tq_pack(const HutterLayout& y, const float* params, unsigned 
 
 cudaError_t launch_tq_fwd(const unsigned char* blob, const RolloutArgs& a, unsigned char* fstash, int grid,
                           cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_FWD_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(tq_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_FWD_SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tq_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_FWD_SMEM);
   if (e != cudaSuccess) return e;
-  APG_LAUNCH(grid, TQ_THREADS, TQ_FWD_SMEM, st, tq_fwd_kernel)(blob, a, fstash);
+  if (a.raw_inputs) APG_LAUNCH_PDL(grid, TQ_THREADS, TQ_FWD_SMEM, st, tq_fwd_kernel<true>)(blob, a, fstash);
+  else APG_LAUNCH_PDL(grid, TQ_THREADS, TQ_FWD_SMEM, st, tq_fwd_kernel<false>)(blob, a, fstash);
   return cudaGetLastError();
 }
 
@@ -925,7 +970,7 @@ cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned 
                           unsigned* ticket, unsigned ticket0, int dyn_grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tq_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
   if (e != cudaSuccess) return e;
-  APG_LAUNCH(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel)(a, fstash, zstash, loss_out, ticket, ticket0);
+  APG_LAUNCH_PDL(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel)(a, fstash, zstash, loss_out, ticket, ticket0);
   return cudaGetLastError();
 }
 
@@ -933,7 +978,7 @@ cudaError_t launch_tq_dx(const unsigned char* tblob, const RolloutArgs& a, unsig
                          unsigned char* zstash, const unsigned char* stamp, int want_stamp, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tq_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DX_SMEM);
   if (e != cudaSuccess) return e;
-  APG_LAUNCH(grid, TQ_THREADS, TQ_DX_SMEM, st, tq_dx_kernel)(tblob, a, fstash, zstash, stamp, want_stamp);
+  APG_LAUNCH_PDL(grid, TQ_THREADS, TQ_DX_SMEM, st, tq_dx_kernel)(tblob, a, fstash, zstash, stamp, want_stamp);
   return cudaGetLastError();
 }
 

@@ -24,7 +24,8 @@
 
 // ---- optional per-role cycle accounting (build with -DAPG_PROFILE; tools/tq_profile.py): kernel k, CTA, counter
 #ifdef APG_PROFILE
-#define TQ_NPROF 16
+#define TQ_NPROF 20
+__device__ __forceinline__ long long tq_globaltimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define TQP_DECL long long tqp_t_ = clock64(); long long tqp_a_[6] = {0, 0, 0, 0, 0, 0};
 #define TQP(i) do { const long long t_ = clock64(); tqp_a_[i] += t_ - tqp_t_; tqp_t_ = t_; } while (0)
 #define TQP_FLUSH(k, base, n) do { if (blockIdx.x < 148) for (int i_ = 0; i_ < (n); ++i_) TQ_PROF_ARRAY[k][blockIdx.x][(base) + i_] = tqp_a_[i_]; } while (0)
@@ -154,7 +155,8 @@ APG_HD DwSrc dw_src(int i) {
 }
 constexpr int DW_A_ROWS = 128, DW_B_ROWS = 64;
 constexpr int DW_A_BYTES = DW_A_ROWS * 128, DW_B_BYTES = DW_B_ROWS * 128;          // one panel image (raw or lo)
-constexpr int DW_NRAW = 6, DW_NLO = 3;                                            // stage rings (tq_dw_kernels.cu)
+constexpr int DW_NRAW = 7, DW_NLO = 6;                                            // raw / B-lo stage rings (tq_dw_kernels.cu)
+constexpr int DW_NTMEM = 7;                                                       // A ring in TMEM: stages of 16 drones x (raw, lo)
 
 }  // namespace tq
 }  // namespace apg

@@ -233,6 +233,18 @@ def measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier):
         lb = float(lb.item())
         gerr = float((gb - ga).norm() / (ga.norm() + 1e-30))
         check = {"loss_prepared": la, "loss_raw": lb, "grad_rel_l2": gerr}
+        if w["system"] == "quad" and w.get("mode", "concurrent") == "concurrent":
+            # the prepared tensors of `case` were made on the host; the raw path computes the same features in the
+            # kernel prologue and the two differ by ulps - which the batch gradient (a sum with ~300x cancellation)
+            # amplifies to ~1e-4 of its norm.  Like for like: the prepared-input path on the tensors the DEVICE
+            # prepare kernels make from the same raw samples.
+            from apg_trajectory_tracking_b200 import prepare as PR
+            prep = PR.prepare_quad(kw["cur"].to(dev), kw["ref"].to(dev))
+            lc, gc = stepper.runner.value_and_grad(stepper.flat, prep["in_state"], prep["cur"], prep["in_ref"],
+                                                   prep["ref"])
+            check["grad_rel_l2_vs_host_prepared_inputs"] = gerr
+            la, gerr = float(lc.item()), float((gb - gc).norm() / (gc.norm() + 1e-30))
+            check.update({"loss_prepared": la, "grad_rel_l2": gerr})
         if not (abs(la - lb) <= 1e-5 * abs(la) and gerr <= 1e-4):
             ok = 0.0
     except Exception as ex:                                       # noqa: BLE001

@@ -101,6 +101,8 @@ inline void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_
   st.cv.notify_all();
 }
 inline void prefetch_l2(const void*) {}
+inline void griddep_wait() {}
+inline void griddep_launch() {}
 inline bool elect_one() { return (threadIdx.x & 31) == 0; }
 // true once the phase with the given parity has completed (PTX mbarrier.try_wait.parity)
 inline bool mbar_try_wait(uint32_t bar, uint32_t parity) {

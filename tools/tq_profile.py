@@ -16,8 +16,8 @@ def main():
     for _ in range(3):
         r.value_and_grad(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
     torch.cuda.synchronize()
-    out = np.zeros((3, 148, 16), dtype=np.int64)
-    out_dw = np.zeros((3, 148, 16), dtype=np.int64)
+    out = np.zeros((3, 148, 20), dtype=np.int64)
+    out_dw = np.zeros((3, 148, 20), dtype=np.int64)
     lib = ctypes.CDLL(_capi.LIB_PATH)
     rc = lib.apg_debug_profile_tq_chain(ctypes.c_void_p(out.ctypes.data))
     assert rc == 0, rc
@@ -25,7 +25,10 @@ def main():
     assert rc == 0, rc
     out[2] = out_dw[2]
     names = {0: ["epi wait_d", "epi other work", "dense: tmem ld16+wait", "dense: tanh/stash/split", "dense: tmem st16 x2", "dense: wait::st+fence+arrive"], 1: ["epi wait_d", "epi work"],
-             2: ["prod wait rfree", "prod issue", "mma wait lo_ready", "mma issue", "conv wait full", "conv wait lo_free", "conv work", "-", "setup", "main loop", "epilogue + exit"]}
+             2: ["prod wait rfree", "prod issue", "mma wait lo_ready", "mma issue", "A feeder wait full", "A feeder wait tfree",
+                 "A feeder work", "A feeder flush (wait done + TMEM -> partial)", "setup", "main loop + flushes", "tail",
+                 "B feeder wait full", "B feeder wait lo_free", "B feeder work", "B feeder flush", "-", "-", "-", "-",
+                 "mma wait a_ready"]}
     t = out[0][:, 6:12].astype(np.float64)
     seg = [("H1 epilogue of warp 0 (ld, tanh, stash, st, arrive)", t[:, 1] - t[:, 0]),
            ("warp 0 arrived -> issuer saw all 8 warps", t[:, 2] - t[:, 1]),
@@ -35,6 +38,12 @@ def main():
     print("one hand-off of tq_fwd (tile 0, slot 0, H1 -> fc2), cycles, mean / max over CTAs")
     for nm, v in seg:
         print(f"  {nm:62s} {v.mean():8.0f} {v.max():8.0f}")
+    for k, kn in ((0, "tq_fwd"), (1, "tq_dx"), (2, "tq_dw")):
+        g0, g1 = out[k][:, 16].astype(np.float64), out[k][:, 17].astype(np.float64)
+        cyc = (out[k][:, 15] if k < 2 else out[k][:, 18]).astype(np.float64)
+        print(f"{kn}: %globaltimer span first CTA entry -> last CTA end {(g1.max() - g0.min()) / 1e3:.1f} us; CTA entry spread "
+              f"{(g0.max() - g0.min()) / 1e3:.1f} us; CTA body mean {(g1 - g0).mean() / 1e3:.1f} us max {(g1 - g0).max() / 1e3:.1f} us; "
+              f"SM clock from cycles / ns: {(cyc / np.maximum(g1 - g0, 1)).mean() * 1e3:.0f} MHz")
     for k, kn in ((0, "tq_fwd"), (1, "tq_dx")):
         tl = out[k][:, 12:16].astype(np.float64)
         print(f"{kn} timeline of thread 0, cycles from kernel entry, mean / min / max over CTAs")
@@ -45,6 +54,6 @@ def main():
         m = out[k].mean(0); mx = out[k].max(0)
         print(kn)
         for i, nm in enumerate(names[k]):
-            print(f"  {nm:20s} mean {m[i]:10.0f}  max {mx[i]:10.0f} cycles")
+            print(f"  {nm:44s} mean {m[i]:10.0f}  max {mx[i]:10.0f} cycles")
 
 main()
