@@ -7,20 +7,26 @@
 //
 // Pipeline (unit = one 32-drone panel of one op):
 //   warp 0       producer  : two 1-D bulk copies per unit (A panel, B panel) straight from the stash into a ring of
-//                            7 raw stages - the stash IS the 128B-swizzled K-major image, so there is no loader
-//                            arithmetic and no tensor map; the copies in flight are what hides the HBM latency
-//   warps 2-5    A feeders : thread = A row (= TMEM lane).  Reads its 128-byte row of the raw panel from shared memory
+//                            12 (pass 0) / 7 (pass 1) raw stages - the stash IS the 128B-swizzled K-major image, so there
+//                            is no loader arithmetic and no tensor map; the copies in flight hide the HBM latency
+//   warps 2-13   A feeders : three groups of four warps, one per operand slot; thread = A row (= TMEM lane).  Reads its 128-byte row of the raw panel from shared memory
 //                            ONCE (conflict free: the swizzle spreads 8 rows over the 8 bank groups), splits it into
-//                            (raw, lo = x - tf32(x)) and writes both with tcgen05.st into a 7-stage ring of TMEM columns
-//                            (16 drones each; measured with 3 stages: every role waited on the round trip commit ->
-//                            feeder wake-up -> tcgen05.st -> issuer wake-up, ~1000 cycles per 3 stages).  Rows past the op's A rows are neither read nor written: row m of A
-//                            only ever reaches row m of D, and the epilogue ignores those rows
-//   warps 6-9    B feeders : lo image of the B panel into a ring of 6 shared-memory stages
-//   warp 1       MMA issuer: per unit 2 halves x 2 k-steps x 3 MMAs (3xTF32), A FROM TMEM, B from shared memory
-// Why A from TMEM (measured, profiles/r2): with both operands in shared memory every MMA re-read a full 128-row A panel
-// (16 KiB, three times per unit, also for the 16-row and 37-row ops) and the feeders wrote a second 16 KiB lo image:
-// ~144 KiB of shared-memory traffic per unit at 128 B/clk = the kernel's bound (1660 MMAs per CTA at 54 cycles each vs the
-// 32-cycle tensor floor).  Now shared memory sees the raw panels once each and the B panel three times.
+//                            (raw, lo = x - tf32(x)) and writes both with tcgen05.st into the unit's slot of TMEM columns.
+//                            Rows past the op's A rows are neither read nor written: row m of A only ever reaches row m
+//                            of D, and the flush ignores those rows
+//   warps 14-16  B feeders : one warp per operand slot: lo image of the B panel into the slot's shared memory
+//   warp 1       MMA issuer: per unit ONE wait (slot ready: 5 warp arrivals), 4 k-steps x 3 MMAs (3xTF32) with A FROM
+//                            TMEM and B from shared memory, two commits (slot free, raw stage free)
+// Measured on the way here (profiles/r2):
+//   * both operands from shared memory: every MMA re-read a full 128-row A panel (also for the 16- and 37-row ops) and
+//     the feeders wrote a second lo image - ~144 KiB of shared-memory traffic per unit at 128 B/clk, 48 cycles per MMA
+//     against 32 with A from TMEM (tools/micro/tcgen05_rate.cu);
+//   * an mbarrier wait costs the waiting warp ~150 cycles even when the phase is already complete
+//     (tools/micro/mbar_pingpong.cu: 374 cycles per wait + arrive pair, whatever the ring depth): with separate
+//     barriers for the B lo image and each half of the A columns the issuer spent 1200 cycles per unit, 336 of them on
+//     tensor work.  Hence ONE ready barrier per unit - and, for the same reason, feeder warps that each own WHOLE units
+//     (a feeder's two waits + fence + arrive cost it ~900 cycles per unit, whatever the amount of data): with every
+//     feeder warp taking part in every unit the feeders, not the tensor core or HBM, set the pace.
 // HBM-bound by construction: 4.2 KB per drone.  Op list / accumulator columns / gradient map: adj_dw_layout.cuh.
 #include "tq_layout.cuh"
 #include "tc_prims.cuh"
@@ -42,24 +48,37 @@ namespace apg {
 
 namespace {
 
-constexpr int DWQ_THREADS = 320;                              // warps: producer, MMA issuer, 4 A feeders, 4 B feeders
-constexpr int DWQ_B_THREADS = 128;
-constexpr int NR = tq::DW_NRAW, NL = tq::DW_NLO, NTM = tq::DW_NTMEM;
-constexpr int STAGE = tq::DW_A_BYTES + tq::DW_B_BYTES;        // one raw stage: A panel (128 rows) | B panel (64 rows)
+// warps: producer, MMA issuer, then one TEAM per operand slot - four A feeder warps and one B feeder warp that own
+// every third unit (unit u -> slot u % 3 -> team u % 3).  A team observes every phase of its slot's barriers; that is
+// what makes waiting by parity safe (a waiter that skipped a phase could take the phase before for the one it needs).
+constexpr int DWQ_TEAMS = tq::DW_NSLOT;
+constexpr int DWQ_THREADS = 32 * (2 + 5 * DWQ_TEAMS);         // 544
+constexpr int NRMAX = tq::DW_NRAW_MAX, NS = tq::DW_NSLOT;
 constexpr int DWQ_T_FLOATS = (4 * tc::RD + 1) * 48;           // conv Toeplitz block between its flush and the fold
-constexpr int DWQ_SMEM = 1024 + NR * STAGE + NL * tq::DW_B_BYTES + ((DWQ_T_FLOATS * 4 + 1023) / 1024) * 1024;
+constexpr int DWQ_SMEM = 1024 + tq::DW_RAW_BYTES + NS * tq::DW_B_BYTES;
 static_assert(DWQ_SMEM <= 232448, "stage rings do not fit in shared memory");
-static_assert(dw::C_ARING + NTM * 32 <= 512, "accumulators + A ring do not fit in TMEM");
+static_assert(tq::DW_T_OFFSET + DWQ_T_FLOATS * 4 <= tq::DW_RAW_BYTES, "conv block does not fit behind the pass-1 stages");
+static_assert(dw::C_ARING + NS * 64 <= 512, "accumulators + A slots do not fit in TMEM");
+
+// Cursor of one role over the raw stages of the current pass.  The parity a wait uses is kept per stage in a bit mask
+// (flipped at every use) instead of being derived from a unit counter: the number of stages changes with the pass.
+// Consumers start at 0 (wait for the first completion), the producer at all-ones (a fresh barrier counts as "the phase
+// of parity 1 has completed": the first wait on every stage passes at once).
+struct RawCursor {
+  int r;
+  uint32_t par;
+  __device__ __forceinline__ uint32_t parity() const { return (par >> r) & 1u; }
+  __device__ __forceinline__ void next(int nr) { par ^= 1u << r; r = (r + 1 == nr) ? 0 : r + 1; }
+};
 
 struct DwqBars {
-  unsigned long long full[NR];                   // bulk copies landed (1 arrival + bytes)
-  unsigned long long rfree[NR];                  // MMAs of the unit are complete (tcgen05.commit): raw stage reusable
-  unsigned long long lo_ready[NL];               // B lo image written (128 arrivals)
-  unsigned long long lo_free[NL];                // MMAs that read the lo stage are complete (tcgen05.commit)
-  unsigned long long a_ready[NTM];                // A columns written (4 arrivals: lane 0 of each feeder warp)
-  unsigned long long tfree[NTM];                  // MMAs that read the A columns are complete (tcgen05.commit)
+  unsigned long long full[NRMAX];                   // bulk copies landed (1 arrival + bytes)
+  unsigned long long rfree[NRMAX];                  // MMAs of the unit are complete (tcgen05.commit): raw stage reusable
+  unsigned long long ready[NS];                  // A columns + B lo image of the slot written (5 arrivals: lane 0 of
+                                                 // the four A feeder warps of the unit's group and of its B feeder warp)
+  unsigned long long sfree[NS];                  // MMAs that read the slot are complete (tcgen05.commit)
   unsigned long long done[dw::NPASS];            // accumulators of the pass are final (tcgen05.commit)
-  unsigned long long flushed;                    // pass-0 accumulators are in the partial (8 arrivals): columns reusable
+  unsigned long long flushed;                    // pass-0 accumulators are in the partial (12 arrivals): columns reusable
 };
 
 __device__ __forceinline__ void dwq_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
@@ -113,24 +132,20 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
   volatile int* abort_flag = &s_abort;
-  unsigned char* lo_base = base + NR * STAGE;
-  float* s_T = reinterpret_cast<float*>(lo_base + NL * tq::DW_B_BYTES);     // [37][48] conv Toeplitz block
+  unsigned char* lo_base = base + tq::DW_RAW_BYTES;
+  float* s_T = reinterpret_cast<float*>(base + tq::DW_T_OFFSET);            // [37][48] conv Toeplitz block
 
   if (tid == 0) {
-    for (int s = 0; s < NR; ++s) {
+    for (int s = 0; s < NRMAX; ++s) {
       tcp::mbar_init(smem_u32(&s_bars.full[s]), 1);
       tcp::mbar_init(smem_u32(&s_bars.rfree[s]), 1);
     }
-    for (int s = 0; s < NL; ++s) {
-      tcp::mbar_init(smem_u32(&s_bars.lo_ready[s]), DWQ_B_THREADS);
-      tcp::mbar_init(smem_u32(&s_bars.lo_free[s]), 1);
-    }
-    for (int s = 0; s < NTM; ++s) {
-      tcp::mbar_init(smem_u32(&s_bars.a_ready[s]), 4);
-      tcp::mbar_init(smem_u32(&s_bars.tfree[s]), 1);
+    for (int s = 0; s < NS; ++s) {
+      tcp::mbar_init(smem_u32(&s_bars.ready[s]), 5);
+      tcp::mbar_init(smem_u32(&s_bars.sfree[s]), 1);
     }
     for (int s = 0; s < dw::NPASS; ++s) tcp::mbar_init(smem_u32(&s_bars.done[s]), 1);
-    tcp::mbar_init(smem_u32(&s_bars.flushed), 8);
+    tcp::mbar_init(smem_u32(&s_bars.flushed), 4 * DWQ_TEAMS);
     s_abort = 0;
     tcp::fence_mbar_init();
   }
@@ -154,30 +169,31 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
   auto flush = [&](int pass) {
     dwq_wait(smem_u32(&s_bars.done[pass]), 0, abort_flag);
     tcp::fence_after_thread_sync();
-    const int r = (warp & 3) * 32 + lane, half = (warp - 2) >> 2;
+    const int r = (warp & 3) * 32 + lane, grp = (warp - 2) >> 2;      // the twelve A feeder warps
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int col0[6] = {dw::C_WO, dw::C_W3, dw::C_W2, dw::C_W1A, dw::C_W1B, dw::C_WS};
     const int ncol[6] = {48, 64, 64, 64, 64, 64};
+    if (grp < 2) {                                             // groups 0 and 1: one half of every region's columns
 #pragma unroll
-    for (int reg = 0; reg < 6; ++reg) {
-      if ((reg == 3 || reg == 4) != (pass == 1)) continue;      // fc1 regions belong to pass 1
-      // entry (r, n) -> P[i0 + n * stride]; i0 < 0: this row is padding in this region
-      const int i0 = dw::grad_index(y, reg, r, 0);
-      const int stride = i0 < 0 ? 0 : dw::grad_index(y, reg, r, 1) - i0;
-      const int nvalid = reg == 0 ? tc::MO : ncol[reg];
-      const int c_lo = half * (ncol[reg] / 2), c_hi = c_lo + ncol[reg] / 2;
-      for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-        uint32_t vb[8];
-        tcp::tmem_ld8(lane_addr + col0[reg] + c0, vb);
-        if (i0 >= 0) {
+      for (int reg = 0; reg < 6; ++reg) {
+        if ((reg == 3 || reg == 4) != (pass == 1)) continue;    // fc1 regions belong to pass 1
+        // entry (r, n) -> P[i0 + n * stride]; i0 < 0: this row is padding in this region
+        const int i0 = dw::grad_index(y, reg, r, 0);
+        const int stride = i0 < 0 ? 0 : dw::grad_index(y, reg, r, 1) - i0;
+        const int nvalid = reg == 0 ? tc::MO : ncol[reg];
+        const int c_lo = grp * (ncol[reg] / 2), c_hi = c_lo + ncol[reg] / 2;
+        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+          uint32_t vb[8];
+          tcp::tmem_ld8(lane_addr + col0[reg] + c0, vb);
+          if (i0 >= 0) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (c0 + q < nvalid) P[i0 + (c0 + q) * stride] = __uint_as_float(vb[q]);
+            for (int q = 0; q < 8; ++q)
+              if (c0 + q < nvalid) P[i0 + (c0 + q) * stride] = __uint_as_float(vb[q]);
+          }
         }
       }
-    }
-    if (pass == 0) {
-      for (int c0 = half * 24; c0 < half * 24 + 24; c0 += 8) {
+    } else if (pass == 0) {                                    // group 2: the conv Toeplitz block
+      for (int c0 = 0; c0 < 48; c0 += 8) {
         uint32_t vb[8];
         tcp::tmem_ld8(lane_addr + dw::C_WT + c0, vb);
         if (r <= 4 * tc::RD) {
@@ -185,6 +201,8 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
           for (int q = 0; q < 8; ++q) s_T[r * 48 + c0 + q] = __uint_as_float(vb[q]);   // folded after the last pass
         }
       }
+    }
+    if (pass == 0) {
       // every tcgen05.ld above has completed (tmem_ld8 waits): the issuer may overwrite the columns
       tcp::fence_before_thread_sync();
       __syncwarp();
@@ -201,8 +219,13 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
     {
       const bool leader = tcp::elect_one();
       TQP_DECL
-      int u = 0;
-      for (int pass = 0; pass < dw::NPASS; ++pass)
+      RawCursor rc{0, 0xffffffffu};
+      for (int pass = 0; pass < dw::NPASS; ++pass) {
+      rc.r = 0;
+      const int nr = tq::dw_nraw(pass), sbytes = tq::dw_stage_bytes(pass), boff = tq::dw_b_offset(pass);
+      // the stages of this pass lie across the stages of the one before (different size): every MMA of that pass
+      // must have read its operands before the first copy of this one lands.  (The bubble overlaps the flush.)
+      if (pass > 0 && my_tiles > 0) dwq_wait(smem_u32(&s_bars.done[pass - 1]), 0, abort_flag);
       for (int j = 0; j < my_tiles; ++j) {
         const int tile = (int)blockIdx.x + j * (int)gridDim.x;
         const unsigned char* fb = fstash + (size_t)tile * tq::F_TILE_BYTES;
@@ -210,17 +233,18 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
         for (int k = 0; k < dw::pass_nops(pass); ++k) {
           const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
           const uint32_t a_bytes = (uint32_t)src.a_rows * 128u, b_bytes = (uint32_t)src.b_rows * 128u;
-          for (int p = 0; p < tq::NPANEL; ++p, ++u) {
-            const int r = u % NR;
-            if (u >= NR) dwq_wait(smem_u32(&s_bars.rfree[r]), (uint32_t)(u / NR - 1) & 1u, abort_flag);
+          for (int p = 0; p < tq::NPANEL; ++p) {
+            const int r = rc.r;
+            dwq_wait(smem_u32(&s_bars.rfree[r]), rc.parity(), abort_flag);
+            rc.next(nr);
             TQP(0);
-            unsigned char* st = base + r * STAGE;
+            unsigned char* st = base + r * sbytes;
             const uint32_t bar = smem_u32(&s_bars.full[r]);
             if (leader) {
             tcp::mbar_expect_tx(bar, a_bytes + b_bytes);
             tcp::bulk_g2s(smem_u32(st), fb + tq::set_base(src.a_set) + (size_t)p * (size_t)(src.a_R * 128) +
                                             (size_t)src.a_row0 * 128, a_bytes, bar);
-            tcp::bulk_g2s(smem_u32(st + tq::DW_A_BYTES), zb + tq::set_base(src.b_set) +
+            tcp::bulk_g2s(smem_u32(st + boff), zb + tq::set_base(src.b_set) +
                                                              (size_t)p * (size_t)(src.b_R * 128) +
                                                              (size_t)src.b_row0 * 128, b_bytes, bar);
             }
@@ -228,6 +252,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
             TQP(1);
           }
         }
+      }
       }
       if (leader) TQP_FLUSH(2, 0, 2);
     }
@@ -239,7 +264,10 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       const uint32_t raw0 = smem_u32(base), lo0 = smem_u32(lo_base);
       const uint64_t DESC_HI = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
       int u = 0;
+      RawCursor rc{0, 0u};                                  // (only the stage index: this warp does not wait on `full`)
       for (int pass = 0; pass < dw::NPASS; ++pass) {
+      rc.r = 0;
+      const int nr = tq::dw_nraw(pass), sbytes = tq::dw_stage_bytes(pass), boff = tq::dw_b_offset(pass);
       if (pass > 0 && my_tiles > 0) {                      // the columns of pass 0 must have been flushed
         if (leader) dwq_wait(smem_u32(&s_bars.flushed), 0, abort_flag);
         __syncwarp();
@@ -251,44 +279,36 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
           const uint32_t idesc = tc::idesc_tf32(128, op.N);
           const uint32_t d = tmem + op.d_col;
           for (int p = 0; p < tq::NPANEL; ++p, ++u) {
-            const int r = u % NR, l = u % NL;
+            const int r = rc.r, sl = u % NS;
+            rc.next(nr);
             // only the issuing lane polls: a barrier of a short ring can complete AGAIN as soon as this unit's MMAs
             // are committed, so a lane that looked late would see the parity it is waiting for already gone
-            if (leader) dwq_wait(smem_u32(&s_bars.lo_ready[l]), (uint32_t)(u / NL) & 1u, abort_flag);
+            if (leader) dwq_wait(smem_u32(&s_bars.ready[sl]), (uint32_t)(u / NS) & 1u, abort_flag);
             __syncwarp();
             TQP(0);
+            tcp::fence_after_thread_sync();
             // B descriptors: constant high word (SBO 1024, version, SWIZZLE_128B), low word = address >> 4 | LBO
             // field; k-step ks adds 2 (32 bytes >> 4)
-            uint32_t br = ((raw0 + (uint32_t)r * STAGE + tq::DW_A_BYTES) >> 4) | (1u << 16);
-            uint32_t bl = ((lo0 + (uint32_t)l * tq::DW_B_BYTES) >> 4) | (1u << 16);
+            uint32_t br = ((raw0 + (uint32_t)(r * sbytes + boff)) >> 4) | (1u << 16);
+            uint32_t bl = ((lo0 + (uint32_t)sl * tq::DW_B_BYTES) >> 4) | (1u << 16);
+            const uint32_t a_hi = tmem + dw::C_ARING + sl * 64, a_lo = a_hi + 32;
             const bool clear = (j == 0) && op.first && (p == 0);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int h = 2 * u + hh, ts = h % NTM;
-              TQP(1);
-              if (leader) dwq_wait(smem_u32(&s_bars.a_ready[ts]), (uint32_t)(h / NTM) & 1u, abort_flag);
-              __syncwarp();
-              TQP(2);
-              tcp::fence_after_thread_sync();
-              const uint32_t a_hi = tmem + dw::C_ARING + ts * 32, a_lo = a_hi + 16;
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk, br += 2, bl += 2) {
-                const uint64_t dbh = DESC_HI | br, dbl = DESC_HI | bl;
+            for (int ks = 0; ks < 4; ++ks, br += 2, bl += 2) {
+              const uint64_t dbh = DESC_HI | br, dbl = DESC_HI | bl;
 #ifdef DWQ_PROBE_NO_MMA      // timing experiment: how fast can the operands be delivered at all (wrong results)
-                if (false) {
+              if (false) {
 #else
-                if (leader) {
+              if (leader) {
 #endif
-                  tcp::mma_ts(d, a_lo + kk * 8, dbh, idesc, (hh + kk > 0 || !clear) ? 1u : 0u);
-                  tcp::mma_ts(d, a_hi + kk * 8, dbl, idesc, 1u);
-                  tcp::mma_ts(d, a_hi + kk * 8, dbh, idesc, 1u);
-                }
+                tcp::mma_ts(d, a_lo + ks * 8, dbh, idesc, (ks > 0 || !clear) ? 1u : 0u);
+                tcp::mma_ts(d, a_hi + ks * 8, dbl, idesc, 1u);
+                tcp::mma_ts(d, a_hi + ks * 8, dbh, idesc, 1u);
               }
-              if (leader) tcp::commit(smem_u32(&s_bars.tfree[ts]));
             }
             if (leader) {
-              tcp::commit(smem_u32(&s_bars.rfree[r]));    // both stages are free once these MMAs have read them
-              tcp::commit(smem_u32(&s_bars.lo_free[l]));
+              tcp::commit(smem_u32(&s_bars.sfree[sl]));   // slot and raw stage are free once these MMAs have read them
+              tcp::commit(smem_u32(&s_bars.rfree[r]));
             }
             __syncwarp();          // lanes stay within one unit of each other (parity waits alias with period 2)
             TQP(1);
@@ -298,17 +318,17 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       __syncwarp();
       }
       if (leader) TQP_FLUSH(2, 2, 2);
-#ifdef APG_PROFILE
-      if (leader && blockIdx.x < 148) TQ_PROF_ARRAY[2][blockIdx.x][19] = tqp_a_[2];          // wait a_ready
-#endif
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + 4 * DWQ_TEAMS) {
     // ===================================================== A feeders: raw panel row -> (raw, lo) TMEM columns
-    const int q = warp & 3, row = q * 32 + lane, ph = row & 7;
+    const int q = warp & 3, row = q * 32 + lane, ph = row & 7, grp = (warp - 2) >> 2;
     const uint32_t a_cols = tmem + ((uint32_t)(q * 32) << 16) + dw::C_ARING;
     TQP_DECL
     int u = 0;
+    RawCursor rc{0, 0u};
     for (int pass = 0; pass < dw::NPASS; ++pass) {
+    rc.r = 0;
+    const int nr = tq::dw_nraw(pass), sbytes = tq::dw_stage_bytes(pass);
     for (int j = 0; j < my_tiles; ++j)
       for (int k = 0; k < dw::pass_nops(pass); ++k) {
         const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
@@ -317,28 +337,29 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
         const bool has_row = row < src.a_rows;
         const uint32_t fill = (row == src.ones) ? 0x3f800000u : 0u;       // constant ones row of a bias gradient
         for (int p = 0; p < tq::NPANEL; ++p, ++u) {
-          const int r = u % NR;
+          const int r = rc.r, sl = u % NS;
+          const uint32_t full_parity = rc.parity();
+          rc.next(nr);
+          if (sl != grp) continue;                            // another team's unit
           uint4 v[8];
+#ifndef DWQ_PROBE_NO_FEED
           if (warp_active) {
-            dwq_wait(smem_u32(&s_bars.full[r]), (uint32_t)(u / NR) & 1u, abort_flag);
+            dwq_wait(smem_u32(&s_bars.full[r]), full_parity, abort_flag);
             TQP(0);
             // logical 16-byte chunk c (drones 4c .. 4c+3) of row `row` sits at chunk c ^ (row & 7) of its 128 bytes
-            const unsigned char* a_row = base + r * STAGE + row * 128;
+            const unsigned char* a_row = base + r * sbytes + row * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               v[c] = has_row ? *reinterpret_cast<const uint4*>(a_row + ((c ^ ph) << 4)) : make_uint4(fill, fill, fill, fill);
           }
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int h = 2 * u + hh, ts = h % NTM;
-            if (h >= NTM) dwq_wait(smem_u32(&s_bars.tfree[ts]), (uint32_t)(h / NTM - 1) & 1u, abort_flag);
-            TQP(1);
-            tcp::fence_after_thread_sync();
-#ifdef DWQ_PROBE_NO_FEED
-            if (false) {
-#else
-            if (warp_active) {
 #endif
+          if (u >= NS) dwq_wait(smem_u32(&s_bars.sfree[sl]), (uint32_t)(u / NS - 1) & 1u, abort_flag);
+          TQP(1);
+          tcp::fence_after_thread_sync();
+#ifndef DWQ_PROBE_NO_FEED
+          if (warp_active) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -347,15 +368,16 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
                 lo[4 * c + 0] = has_row ? lo_bits(x.x) : 0u; lo[4 * c + 1] = has_row ? lo_bits(x.y) : 0u;
                 lo[4 * c + 2] = has_row ? lo_bits(x.z) : 0u; lo[4 * c + 3] = has_row ? lo_bits(x.w) : 0u;
               }
-              tcp::tmem_st16(a_cols + ts * 32, hi);          // the tensor core truncates the raw image: the hi part
-              tcp::tmem_st16(a_cols + ts * 32 + 16, lo);
-              tcp::wait_st();
+              tcp::tmem_st16(a_cols + sl * 64 + hh * 16, hi);        // the tensor core truncates the raw image: the hi part
+              tcp::tmem_st16(a_cols + sl * 64 + 32 + hh * 16, lo);
             }
-            tcp::fence_before_thread_sync();
-            __syncwarp();
-            if (lane == 0) tcp::mbar_arrive(smem_u32(&s_bars.a_ready[ts]));
-            TQP(2);
+            tcp::wait_st();
           }
+#endif
+          tcp::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) tcp::mbar_arrive(smem_u32(&s_bars.ready[sl]));
+          TQP(2);
         }
       }
     if (my_tiles > 0) flush(pass);
@@ -363,39 +385,46 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
     }
     if (tid == 64) TQP_FLUSH(2, 4, 4);
   } else {
-    // ===================================================== B feeders: lo image of the B panel
-    const int bt = tid - 192;
+    // ===================================================== B feeders: lo image of the B panel, one warp per unit
+    const int bw = warp - (2 + 4 * DWQ_TEAMS);
     TQP_DECL
     int u = 0;
+    RawCursor rc{0, 0u};
     for (int pass = 0; pass < dw::NPASS; ++pass) {
+    rc.r = 0;
+    const int nr = tq::dw_nraw(pass), sbytes = tq::dw_stage_bytes(pass), boff = tq::dw_b_offset(pass);
     for (int j = 0; j < my_tiles; ++j)
       for (int k = 0; k < dw::pass_nops(pass); ++k) {
         const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
-        const int nb = src.b_rows * 8;                       // 16-byte chunks
+        const int nb = src.b_rows * 8;                       // 16-byte chunks (320 or 512: a multiple of 32)
         for (int p = 0; p < tq::NPANEL; ++p, ++u) {
-          const int r = u % NR, l = u % NL;
-          dwq_wait(smem_u32(&s_bars.full[r]), (uint32_t)(u / NR) & 1u, abort_flag);
+          const int r = rc.r, sl = u % NS;
+          const uint32_t full_parity = rc.parity();
+          rc.next(nr);
+          if (sl != bw) continue;                             // another team's unit
+          dwq_wait(smem_u32(&s_bars.full[r]), full_parity, abort_flag);
           TQP(0);
-          if (u >= NL) dwq_wait(smem_u32(&s_bars.lo_free[l]), (uint32_t)(u / NL - 1) & 1u, abort_flag);
-          TQP(1);
-          const float4* b_raw = reinterpret_cast<const float4*>(base + r * STAGE + tq::DW_A_BYTES);
-          float4* b_lo = reinterpret_cast<float4*>(lo_base + l * tq::DW_B_BYTES);
-          float4 vb[4];
+          const float4* b_raw = reinterpret_cast<const float4*>(base + r * sbytes + boff);
+          float4* b_lo = reinterpret_cast<float4*>(lo_base + sl * tq::DW_B_BYTES);
+          float4 vb[16];
 #ifndef DWQ_PROBE_NO_FEED
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) if (bt + kk * DWQ_B_THREADS < nb) vb[kk] = b_raw[bt + kk * DWQ_B_THREADS];
+          for (int kk = 0; kk < 16; ++kk) if (lane + kk * 32 < nb) vb[kk] = b_raw[lane + kk * 32];
+#endif
+          if (u >= NS) dwq_wait(smem_u32(&s_bars.sfree[sl]), (uint32_t)(u / NS - 1) & 1u, abort_flag);
+          TQP(1);
+#ifndef DWQ_PROBE_NO_FEED
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) if (bt + kk * DWQ_B_THREADS < nb) b_lo[bt + kk * DWQ_B_THREADS] = lo_of(vb[kk]);
+          for (int kk = 0; kk < 16; ++kk) if (lane + kk * 32 < nb) b_lo[lane + kk * 32] = lo_of(vb[kk]);
 #endif
           tcp::fence_proxy_async_smem();                     // generic writes -> tensor core reads
-          tcp::mbar_arrive(smem_u32(&s_bars.lo_ready[l]));
+          __syncwarp();
+          if (lane == 0) tcp::mbar_arrive(smem_u32(&s_bars.ready[sl]));
           TQP(2);
         }
       }
-    if (my_tiles > 0) flush(pass);
-    TQP(3);
     }
-    if (bt == 0) TQP_FLUSH(2, 11, 4);
+    if (lane == 0 && bw == 0) TQP_FLUSH(2, 11, 3);
   }
 #ifdef APG_PROFILE
   tqp_k2_ = clock64();

@@ -73,13 +73,13 @@ inline float tq_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 #else
 __device__ __forceinline__ float tq_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tq_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// tanh as ONE rational function x P(x^2) / Q(x^2) on |x| <= 7.905 (degree 13 / 6 minimax, the coefficients of Eigen's
-// generic_fast_tanh_float; relative error <= 4e-7 over the whole range INCLUDING x -> 0, checked against fp64 in
-// tests/test_tanh_rational_host.py): 13 FMA-pipe instructions + one SFU reciprocal per value.
-// Why not the SFU form 1 - 2 / (exp(2x) + 1): its error is ABSOLUTE (3e-7: the result cancels near 0), and the batch
-// gradient is a sum with ~300x cancellation at N = 65536 - with it an ulp-level change of the inputs moved the gradient
-// by 5e-4 of its norm (profiles/r2, bench raw-input check); and it costs two SFU operations per value on an SFU-bound
-// epilogue.  -DTQ_TANH_SFU_ONLY / -DTQ_TANH_SFU_POLY keep the two earlier forms for timing experiments.
+// tanh of the forward epilogues.  Default: 1 - 2 / (exp(2x) + 1) on the SFU for |x| >= 0.25 (absolute error 3e-7) and an
+// odd Taylor polynomial below (the SFU form cancels near 0).  What decides between the candidates is not the worst-case
+// error but how NOISY the function is: the batch gradient is a sum with ~300x cancellation at N = 65536, and an
+// ulp-level change of the inputs moved it (bench raw-input check, profiles/r2) by
+//     1.2e-5 of its norm with this form,   4e-4 with the rational x P(x^2) / Q(x^2) below (3 ulp of rounding noise
+//     everywhere, relative error 4e-7, tests/test_tanh_rational_host.py),   5e-4 with the SFU form alone,
+// at 83.8 / 83.1 / 77.3 us for the forward chain.  -DTQ_TANH_RATIONAL / -DTQ_TANH_SFU_ONLY select the other two.
 __device__ __forceinline__ float tq_tanh_small(float x) {
   const float x2 = x * x;
   float p = fmaf(x2, 0.0218694885f, -0.0539682540f);
@@ -107,7 +107,7 @@ __device__ __forceinline__ float tq_sigmoid(float x) { return tq_rcp(1.f + tq_ex
 __device__ __forceinline__ void tq_tanh2(float x0, float x1, float* y0, float* y1) {
 #ifdef APG_TC_SIM
   *y0 = tanhf(x0); *y1 = tanhf(x1);
-#elif defined(TQ_TANH_SFU_ONLY) || defined(TQ_TANH_SFU_POLY)
+#elif !defined(TQ_TANH_RATIONAL)
   const float c0 = fminf(fmaxf(x0, -15.f), 15.f);
   const float c1 = fminf(fmaxf(x1, -15.f), 15.f);
   const float a0 = tq_ex2(c0 * 2.885390082f) + 1.f, a1 = tq_ex2(c1 * 2.885390082f) + 1.f;

@@ -153,10 +153,18 @@ APG_HD DwSrc dw_src(int i) {
   const int g = i - 6;
   return {O_WIN + R_WIN * g, 0, R_WIN, R_WIN, -1, O_ZX, HID + 2 * NC * g, 2 * NC, K1};
 }
-constexpr int DW_A_ROWS = 128, DW_B_ROWS = 64;
-constexpr int DW_A_BYTES = DW_A_ROWS * 128, DW_B_BYTES = DW_B_ROWS * 128;          // one panel image (raw or lo)
-constexpr int DW_NRAW = 7, DW_NLO = 6;                                            // raw / B-lo stage rings (tq_dw_kernels.cu)
-constexpr int DW_NTMEM = 7;                                                       // A ring in TMEM: stages of 16 drones x (raw, lo)
+// raw operand ring of the dW kernel: the stage geometry follows the pass (adj_dw_layout.cuh) - pass 0 (every op but
+// fc1): A <= 64 rows, B <= 64 rows -> 16 KiB stages, 12 of them; pass 1 (fc1): A <= 128 rows -> 24 KiB stages, 7.
+// Operand SLOTS (3): what a unit needs besides its raw stage - 8 KiB of shared memory for the B lo image and 64 TMEM
+// columns for the A panel (32 drones x (raw, lo)).
+constexpr int DW_B_BYTES = 64 * 128;
+APG_HD constexpr int dw_stage_bytes(int pass) { return pass == 0 ? 16384 : 24576; }
+APG_HD constexpr int dw_b_offset(int pass) { return pass == 0 ? 8192 : 16384; }
+APG_HD constexpr int dw_nraw(int pass) { return pass == 0 ? 12 : 7; }
+constexpr int DW_NRAW_MAX = 12, DW_RAW_BYTES = 12 * 16384;
+constexpr int DW_T_OFFSET = 7 * 24576;            // conv Toeplitz block: raw-ring bytes that pass 1 never touches
+constexpr int DW_NSLOT = 3;
+static_assert(dw_nraw(0) * dw_stage_bytes(0) <= DW_RAW_BYTES && dw_nraw(1) * dw_stage_bytes(1) <= DW_T_OFFSET, "raw ring");
 
 }  // namespace tq
 }  // namespace apg

@@ -2,7 +2,7 @@
 # dW kernel: where does the time go (probes without MMAs / without feeders), PDL launches
 set -u
 cd "$(dirname "$0")/.."
-out=gpurun_out/r2_dw4
+out=gpurun_out/r2_dw8
 mkdir -p "$out"
 timeout 600 python -m pytest tests/test_zz_new_paths_gpu.py -q -m gpu -x -k "tc1 or tc2 or tc3" > "$out/pytest_tc.log" 2>&1
 echo "exit=$?" >> "$out/pytest_tc.log"

@@ -25,9 +25,9 @@ def main():
     assert rc == 0, rc
     out[2] = out_dw[2]
     names = {0: ["epi wait_d", "epi other work", "dense: tmem ld16+wait", "dense: tanh/stash/split", "dense: tmem st16 x2", "dense: wait::st+fence+arrive"], 1: ["epi wait_d", "epi work"],
-             2: ["prod wait rfree", "prod issue", "mma wait lo_ready", "mma issue", "A feeder wait full", "A feeder wait tfree",
+             2: ["prod wait rfree", "prod issue", "mma wait slot ready", "mma issue", "A feeder wait full", "A feeder wait slot free",
                  "A feeder work", "A feeder flush (wait done + TMEM -> partial)", "setup", "main loop + flushes", "tail",
-                 "B feeder wait full", "B feeder wait lo_free", "B feeder work", "B feeder flush", "-", "-", "-", "-",
+                 "B feeder wait full", "B feeder wait slot free", "B feeder work", "B feeder flush", "-", "-", "-", "-",
                  "mma wait a_ready"]}
     t = out[0][:, 6:12].astype(np.float64)
     seg = [("H1 epilogue of warp 0 (ld, tanh, stash, st, arrive)", t[:, 1] - t[:, 0]),
