@@ -6,21 +6,36 @@
 #include "../../include/apg_b200.h"
 #include "kernels.h"
 #include "pack_tables.h"
+#include <mutex>
 
 using namespace apg;
 
 namespace {
 
-int g_sm_count = -1;
+// Per-device state, keyed by cudaGetDevice() under one mutex: the SM count (grid and workspace sizes follow it) and
+// the cached buffer / stream of the host-buffer entry point.  A process may use several devices from several threads.
+constexpr int APG_MAX_DEVICES = 64;
+std::mutex g_dev_mutex;
+int g_sm_counts[APG_MAX_DEVICES];
+bool g_sm_known[APG_MAX_DEVICES];
+
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= APG_MAX_DEVICES) return -1;
+  return dev;
+}
 
 int sm_count() {
-  if (g_sm_count < 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  const int dev = current_device();
+  if (dev < 0) return -1;
+  std::lock_guard<std::mutex> lk(g_dev_mutex);
+  if (!g_sm_known[dev]) {
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    g_sm_count = n;
+    g_sm_counts[dev] = n;
+    g_sm_known[dev] = true;
   }
-  return g_sm_count;
+  return g_sm_counts[dev];
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -171,8 +186,11 @@ bool env_flag(const char* name);
 bool use_tq(const apg_config* c, const HutterLayout& y);
 
 int check_ptrs(const apg_config* c, const float* params, const float* in_state, const float* cur, const float* in_ref,
-               const float* ref, void* workspace) {
+               const float* ref, const float* h0c0, void* workspace) {
   if (!params || !cur || !workspace) return APG_ERR_BAD_CONFIG;
+  // the LSTM policy starts from the caller's (h0, c0) in the forward AND in the adjoint
+  if (c->net == NET_LSTM && !h0c0) return APG_ERR_BAD_CONFIG;
+  if (!aligned16(h0c0)) return APG_ERR_ALIGNMENT;
   // recurrent modes featurise `cur` in-kernel; the tcgen05 path takes RAW samples when in_state and in_ref are both
   // NULL (cur = raw states, ref = raw reference rows: QuadDataset.prepare_data runs in the kernels' prologue)
   const bool raw_ok = is_hutter(c) && !is_recurrent(c) && use_tq(c, hutter_layout(c)) && !in_state && !in_ref && ref;
@@ -217,12 +235,14 @@ void tmark(int i, cudaStream_t st) {
 void tmark(int, cudaStream_t) {}
 #endif
 
-// cached device buffers of the host-buffer entry point
+// cached device buffer and stream of the host-buffer entry point, one per device; a call holds its device's entry
+// locked from the first copy to the final synchronize (the entry point is synchronous anyway)
 struct HostCache {
   void* buf = nullptr;
   size_t cap = 0;
   cudaStream_t stream = nullptr;
-} g_cache;
+  std::mutex busy;
+} g_caches[APG_MAX_DEVICES];
 
 }  // namespace
 
@@ -287,7 +307,7 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
                         float* states_out, float* actions_out, void* stream) {
   int e = check_config(cfg);
   if (e) return e;
-  if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, workspace))) return e;
+  if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, h0c0, workspace))) return e;
   if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const Plan p = make_plan(cfg, net_info(cfg));
@@ -367,7 +387,7 @@ int rollout_backward_impl(const apg_config* cfg, const float* params, const floa
                           float* grad_params, const apg_grad_comm* comm, void* stream, const SgdFuse* sgd = nullptr) {
   int e = check_config(cfg);
   if (e) return e;
-  if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, workspace))) return e;
+  if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, h0c0, workspace))) return e;
   if (!grad_params && !comm && !sgd) return APG_ERR_BAD_CONFIG;
   if (comm && (!comm->slot_ptrs || !comm->flag_ptrs || !comm->ticket || comm->world < 1 || comm->rank < 0 ||
                comm->rank >= comm->world))
@@ -503,6 +523,10 @@ __attribute__((visibility("default"))) int apg_rollout_value_and_grad_host(const
   const size_t b_ws = apg_workspace_bytes(cfg);
   const size_t need = 2 * b_params + b_ins + b_cur + b_inr + b_ref + b_hc + 256 + b_ws;
   cudaError_t ce;
+  const int dev = current_device();
+  if (dev < 0) return APG_ERR_BAD_CONFIG;
+  HostCache& g_cache = g_caches[dev];
+  std::lock_guard<std::mutex> cache_lock(g_cache.busy);
   if (!g_cache.stream && (ce = cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking))) return (int)ce;
   if (g_cache.cap < need) {
     if (g_cache.buf) cudaFree(g_cache.buf);

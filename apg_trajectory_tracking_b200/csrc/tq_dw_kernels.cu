@@ -393,6 +393,11 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
     for (int pass = 0; pass < dw::NPASS; ++pass) {
     rc.r = 0;
     const int nr = tq::dw_nraw(pass), sbytes = tq::dw_stage_bytes(pass), boff = tq::dw_b_offset(pass);
+    // A wait by parity is only safe if the phase BEFORE the awaited one is known to be complete.  Within a pass that
+    // follows from the order of the MMAs (see DWQ_TEAMS); across the pass boundary this warp - unlike the A feeders,
+    // which flush - would otherwise reach the first `full` barrier of the new pass while the last copies of the old
+    // pass, made by other teams into other stages that share these barriers, may still be in flight.
+    if (pass > 0 && my_tiles > 0) dwq_wait(smem_u32(&s_bars.done[pass - 1]), 0, abort_flag);
     for (int j = 0; j < my_tiles; ++j)
       for (int k = 0; k < dw::pass_nops(pass); ++k) {
         const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));

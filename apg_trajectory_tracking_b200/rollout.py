@@ -112,14 +112,26 @@ class Rollout:
             self.workspace = torch.empty(ws + 256, dtype=torch.uint8, device=self.device)
             off = (-self.workspace.data_ptr()) % 256
             self._ws_ptr = ctypes.c_void_p(self.workspace.data_ptr() + off)
-            self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+            # the loss of forward number k lands in element k % LOSS_RING of this buffer, and forward() returns that
+            # 1-element view: losses collected over up to LOSS_RING steps stay what they were (the reference returns a
+            # fresh tensor per step) without an extra clone launch per step
+            self._loss_ring = torch.zeros(self.LOSS_RING, dtype=torch.float32, device=self.device)
+            self.loss = self._loss_ring[0:1]
+            self.forward_count = 0
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    LOSS_RING = 1024
+
     def forward(self, params_flat, in_state, cur, in_ref=None, ref=None, h0c0=None, want_states=False,
                 want_actions=False):
+        """One fused rollout; returns (loss, states or None, actions or None).  ``loss`` is a 1-element view into a ring
+        of ``LOSS_RING`` device floats: it keeps its value until ``LOSS_RING`` further forwards have run (clone it to
+        keep it longer).  ``backward`` differentiates the LAST forward of this runner."""
         s = self.spec
+        self.loss = self._loss_ring[self.forward_count % self.LOSS_RING:self.forward_count % self.LOSS_RING + 1]
+        self.forward_count += 1
         self._inputs = [_dev_f32(x, n) for x, n in ((params_flat, "params"), (in_state, "in_state"), (cur, "cur"),
                                                      (in_ref, "in_ref"), (ref, "ref"), (h0c0, "h0c0"))]
         states = torch.empty(self.n, s.horizon, s.state_dim, device=self.device) if want_states else None
@@ -198,10 +210,15 @@ class _FusedRolloutFn(torch.autograd.Function):
     def forward(ctx, params_flat, runner, in_state, cur, in_ref, ref, h0c0):
         loss, _, _ = runner.forward(params_flat, in_state, cur, in_ref, ref, h0c0)
         ctx.runner = runner
+        ctx.forward_count = runner.forward_count
         return loss.clone().reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.runner.forward_count != ctx.forward_count:
+            raise RuntimeError("fused_rollout_loss: the runner has run another forward since this loss was computed; its "
+                               "adjoint would differentiate that one (use one Rollout per live loss, or call backward "
+                               "before the next forward)")
         g = ctx.runner.backward(1.0)
         return g * grad_out, None, None, None, None, None, None
 

@@ -181,7 +181,7 @@ class FusedTrainStep:
         # theirs (step_host_async); the loss of a step is copied into one of two pinned scalars
         st = {"n": n, "copy_stream": torch.cuda.Stream(device=dev), "runners": {}, "sets": [self._staging(n),
               self._staging(n)], "turn": 0, "grad_tmp": torch.zeros_like(self.grad),
-              "loss": torch.zeros(1, device=dev),
+              "loss_ring": torch.zeros(1024, device=dev), "calls": 0,
               "loss_host": [torch.empty(1, pin_memory=torch.cuda.is_available()) for _ in range(2)]}
         self._hs = st
         return st
@@ -240,6 +240,11 @@ class FusedTrainStep:
         if spec.system == "wing":
             mean, std = norm if norm is not None else (_syn.WING_MEAN, _syn.WING_STD)
         first = True
+        # the summed loss of this call: one element of a ring (like Rollout.forward), so that losses returned by
+        # earlier calls keep their values
+        k = st["calls"] % st["loss_ring"].numel()
+        st["calls"] += 1
+        st["loss"] = st["loss_ring"][k:k + 1]
         for a, b in bounds:
             with torch.cuda.stream(copy):
                 sg["cur"][a:b].copy_(cur[a:b], non_blocking=True)

@@ -229,11 +229,17 @@ def measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier):
         la, ga = stepper.runner.value_and_grad(stepper.flat, case["in_state"], case["cur"], case.get("in_ref"),
                                                case.get("ref"), case.get("h0c0"))
         la, ga = float(la.item()), ga.clone()
-        lb, gb = stepper.value_and_grad_host(allreduce=False, **kw)
-        lb = float(lb.item())
+        # whole batch in one chunk: same kernels, same reduction order as the prepared-input call.  (Cutting the batch
+        # into chunks changes the order of an fp32 sum whose terms cancel ~300-fold at this size; that alone moves the
+        # gradient by 1e-5 .. 1e-3 of its norm - reported as grad_rel_l2_default_chunks, not judged here; the chunked
+        # path is checked against the oracle at sizes where the oracle is exact enough, tests/test_step_host_*.)
+        lb, gb = stepper.value_and_grad_host(allreduce=False, chunk=0, **kw)
+        lb, gb = float(lb.item()), gb.clone()
         gerr = float((gb - ga).norm() / (ga.norm() + 1e-30))
         check = {"loss_prepared": la, "loss_raw": lb, "grad_rel_l2": gerr}
-        if w["system"] == "quad" and w.get("mode", "concurrent") == "concurrent":
+        _, gchunks = stepper.value_and_grad_host(allreduce=False, **kw)
+        check["grad_rel_l2_default_chunks"] = float((gchunks - ga).norm() / (ga.norm() + 1e-30))
+        if w["system"] == "quad" and w.get("mode", "concurrent") == "concurrent" and torch.device(dev).type == "cuda":
             # the prepared tensors of `case` were made on the host; the raw path computes the same features in the
             # kernel prologue and the two differ by ulps - which the batch gradient (a sum with ~300x cancellation)
             # amplifies to ~1e-4 of its norm.  Like for like: the prepared-input path on the tensors the DEVICE

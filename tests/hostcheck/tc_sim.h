@@ -86,11 +86,60 @@ inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   if (bad) sim::fail("expect_tx on an uninitialised mbarrier");
   st.cv.notify_all();
 }
-// cp.async.bulk global -> shared: copied at issue, then complete_tx on the barrier
+// cp.async.bulk global -> shared.  Default: copied at issue, then complete_tx on the barrier.
+// APG_SIM_BULK_DELAY_US=<max>: the copy LANDS LATER - after a pseudo-random delay of up to <max> microseconds, different
+// for every copy, so that copies complete out of order like on hardware - and until then its destination holds NaN
+// patterns.  A thread that passes a wait it should not have passed (a parity wait that took the phase before for the
+// one it needs, a stage handed on too early) then reads NaNs, and the result shows it.  Pending copies are completed
+// by whichever thread next polls or signals a barrier.
+struct PendingBulk { uint32_t dst; const void* src; uint32_t bytes, bar; long long due_ns; };
+inline std::vector<PendingBulk>& pending_bulk() { static std::vector<PendingBulk> v; return v; }
+inline long long sim_now_ns() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline long long bulk_delay_max_ns() {
+  static const long long v = getenv("APG_SIM_BULK_DELAY_US") ? atoll(getenv("APG_SIM_BULK_DELAY_US")) * 1000LL : 0LL;
+  return v;
+}
+// (st.m held)
+inline void land_due_copies_locked(sim::State& st, bool all) {
+  std::vector<PendingBulk>& v = pending_bulk();
+  if (v.empty()) return;
+  const long long now = sim_now_ns();
+  bool any = false;
+  for (size_t i = 0; i < v.size();) {
+    if (all || v[i].due_ns <= now) {
+      memcpy(st.smem + v[i].dst, v[i].src, v[i].bytes);
+      sim::Mbar& b = st.bars[v[i].bar];
+      b.tx -= v[i].bytes;
+      settle(b);
+      v[i] = v.back();
+      v.pop_back();
+      any = true;
+    } else {
+      ++i;
+    }
+  }
+  if (any) st.cv.notify_all();
+}
+inline void land_due_copies() {
+  if (!bulk_delay_max_ns()) return;
+  sim::State& st = sim::S();
+  std::lock_guard<std::mutex> lk(st.m);
+  land_due_copies_locked(st, false);
+}
 inline void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   sim::State& st = sim::S();
   if ((bytes & 15u) || (dst_smem & 15u) || ((uintptr_t)src & 15u)) sim::fail("cp.async.bulk: size / address not 16-byte aligned");
   if ((dst_smem >> 30) != 0 || (size_t)dst_smem + bytes > sim::DYN_SMEM) { sim::fail("cp.async.bulk: destination outside the dynamic shared memory"); return; }
+  if (bulk_delay_max_ns()) {
+    static std::atomic<uint64_t> lcg{0x9e3779b97f4a7c15ull};
+    const uint64_t x = lcg.fetch_add(0x9e3779b97f4a7c15ull) * 0xbf58476d1ce4e5b9ull;
+    std::lock_guard<std::mutex> lk(st.m);
+    memset(st.smem + dst_smem, 0xff, bytes);            // in flight: the destination is garbage
+    pending_bulk().push_back({dst_smem, src, bytes, bar, sim_now_ns() + (long long)((x >> 20) % (uint64_t)bulk_delay_max_ns())});
+    return;
+  }
   memcpy(st.smem + dst_smem, src, bytes);
   {
     std::lock_guard<std::mutex> lk(st.m);
@@ -108,6 +157,7 @@ inline bool elect_one() { return (threadIdx.x & 31) == 0; }
 inline bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   sim::State& st = sim::S();
   std::unique_lock<std::mutex> lk(st.m);
+  if (bulk_delay_max_ns()) land_due_copies_locked(st, false);
   sim::Mbar& b = st.bars[bar];
   return st.cv.wait_for(lk, std::chrono::microseconds(500), [&] { return b.init && b.phase != (parity & 1u); });
 }
@@ -115,6 +165,7 @@ inline bool mbar_test_wait(uint32_t bar, uint32_t parity) {
   bool ok;
   {
     std::lock_guard<std::mutex> lk(sim::S().m);
+    if (bulk_delay_max_ns()) land_due_copies_locked(sim::S(), false);
     sim::Mbar& b = sim::S().bars[bar];
     ok = b.init && b.phase != (parity & 1u);
   }

@@ -817,6 +817,31 @@ def test_tc3_raw_samples_in_the_kernel_prologue_equal_prepared_inputs(n):
     assert rel_err(g1, g0) <= 1e-4
 
 
+@pytest.mark.parametrize("n", [1000, 65536])
+def test_tc4_tcgen05_gradient_is_bitwise_reproducible(n):
+    """every kernel of the tcgen05 path reduces in a fixed order: the same inputs give the same bits, launch after
+    launch (a protocol race - an operand read before it was complete, a stage overwritten early - shows up here as
+    run-to-run noise long before it is large enough to fail a tolerance)"""
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    h, dt = 10, 0.1
+    params = B.default_init("quad", h, seed=3)
+    case = {k: v.cuda() for k, v in SY.quad_case(n, h, dt, seed=5).items()}
+    flat = R.flatten_params(params).cuda()
+    r = R.Rollout(R.RolloutSpec.quad_concurrent(h, dt), n, "cuda:0")
+    assert r.tcgen05
+    grads, losses = [], []
+    for rep in range(6):
+        loss, _, _ = r.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
+        losses.append(float(loss.item()))
+        grads.append(r.backward(1.0).clone())
+    torch.cuda.synchronize()
+    assert len(set(losses)) == 1, losses
+    worst = max(float((g - grads[0]).abs().max()) for g in grads[1:])
+    rel = max(rel_err(g, grads[0]) for g in grads[1:])
+    assert worst == 0.0, f"gradient differs between identical launches: max abs {worst}, rel l2 {rel}"
+
+
 def test_tc2_backward_after_a_forward_of_the_other_path_poisons_the_gradient():
     """the workspace is stamped by the forward that filled its stash; an adjoint of the tcgen05 path run on a
     workspace whose last forward was the legacy one must not return a silently wrong gradient"""
