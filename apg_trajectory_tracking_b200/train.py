@@ -362,7 +362,9 @@ class ModuleRollout:
         cur = self._dev(cur)
         runner = self.runner(cur.shape[0])
         in_state, in_ref, ref = self._dev(in_state), self._dev(in_ref), self._dev(ref)
-        if self.spec.system == "quad" and in_ref is None and ref is not None:
+        if self.spec.system == "quad" and in_ref is None and ref is not None and not (
+                self.spec.mode == "concurrent" and getattr(runner, "tcgen05", False)):
+            # (the tcgen05 kernels take the raw samples as they are: prepare_data runs in their prologue)
             want = ("in_state", "cur", "in_ref", "ref") if self.spec.mode == "concurrent" else ("cur", "in_ref", "ref")
             d = PR.prepare_quad(cur, ref, want=want)
             in_state, cur, in_ref, ref = d.get("in_state"), d["cur"], d["in_ref"], d["ref"]

@@ -376,3 +376,52 @@ def test_device_dataset_epoch_on_the_model_library(simlib):
     assert rel_err(mb.flat, ma.flat) <= 1e-6
     d3 = DD.DeviceQuadDataset.from_trajectory(torch.randn(301, 9), h, device="cpu")
     assert len(d3) == len(range(0, 301 - (h + 1), 2 * h))
+
+
+def test_trainer_rollout_uses_the_physics_of_the_train_dynamics_it_was_given(simlib, monkeypatch):
+    """the reference differentiates through ``self.train_dynamics`` (train_drone.py:186-190).  A trainer
+    built on ``FlightmareDynamics(modified_params=...)`` - with NO ``modified_params`` entry in its config, or with an
+    entry that describes the evaluation dynamics instead - must roll out the MODIFIED model: its fused loss equals the
+    oracle's with the same constants and differs from the default-physics loss; learnt dynamics with a recurrent
+    train mode are refused instead of silently integrating the analytic model."""
+    from apg_trajectory_tracking_b200.scripts import train_drone as TD
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_trained import LearntDynamics
+    from apg_trajectory_tracking_b200.neural_control import environments as ENV
+    import importlib
+    monkeypatch.setattr(ENV, "compute_device", lambda: torch.device("cpu"), raising=False)
+    for name in ("models.hutter_model", "dynamics.quad_dynamics_flightmare", "dynamics.quad_dynamics_trained", "dataset"):
+        mod = importlib.import_module("apg_trajectory_tracking_b200.neural_control." + name)
+        monkeypatch.setattr(mod, "_require_cuda", lambda *a, **k: None, raising=False)
+    monkeypatch.setenv("APG_LEGACY_MMA", "1")             # (the smaller CPU-model run; the constants reach both paths)
+    mp = {"translational_drag": [0.3, 0.3, 0.3], "kinv_ang_vel_tau": [20.0, 20.0, 6.0]}   # (the mass cancels in this model)
+    # the reference's configs/quad_config.json, minus its modified_params entry
+    config = dict(nr_epochs=1, delta_t=0.1, delta_t_train=0.1, epoch_size=64, self_play=0, self_play_every_x=2,
+                  batch_size=64, reset_strength=1.2, max_drone_dist=0.25, max_steps=1000, thresh_div_start=0.1,
+                  thresh_div_end=2, thresh_stable_start=1, thresh_stable_end=2, state_size=12, horizon=10,
+                  train_mode="concurrent", ref_dim=9, action_dim=4, l2_lambda=0.01, learning_rate_controller=1e-5,
+                  learning_rate_dynamics=0.001, resample_every=3, suc_up_down=1, speed_factor=0.5, system="quad",
+                  sample_in="train_env", device="cpu")  # the "device" memory of the CPU-model library
+    n, h, dt = 64, 10, 0.1
+    case = SY.quad_case(n, h, dt, seed=11)
+    losses = {}
+    for key, dyn, cfg_extra in (("default", FlightmareDynamics(), {}),
+                                ("modified", FlightmareDynamics(modified_params=mp), {}),
+                                ("modified_cfg_is_eval", FlightmareDynamics(modified_params=mp),
+                                 {"modified_params": {"translational_drag": [0.9, 0.9, 0.9]}})):
+        tr = TD.TrainDrone(dyn, FlightmareDynamics(), dict(config, **cfg_extra))
+        torch.manual_seed(5)
+        tr.initialize_model()
+        assert (tr.modified_params()["translational_drag"] == [0.3, 0.3, 0.3]) == (key != "default")
+        params = [p.detach().clone() for p in tr.net.parameters()]
+        loss = tr.fused.loss_and_grad(case["in_state"], case["cur"], case["in_ref"], case["ref"])
+        losses[key] = (float(loss), params)
+    assert abs(losses["modified"][0] - losses["default"][0]) > 1e-3 * abs(losses["default"][0])
+    assert losses["modified_cfg_is_eval"][0] == losses["modified"][0]
+    cfg_mod = dict(O.QUAD_CFG, **mp)
+    monkeypatch.setitem(O.STEP_FN, "quad", lambda s, a, d: O.quad_step(s, a, d, cfg=cfg_mod))
+    want, _, _, _ = O.concurrent_value_and_grad("quad", losses["modified"][1], case["in_state"], case["cur"],
+                                                case["in_ref"], case["ref"], h, dt)
+    assert abs(losses["modified"][0] - float(want)) <= 2e-5 * abs(float(want))
+    with pytest.raises(ValueError):
+        TD.TrainDrone(LearntDynamics(), FlightmareDynamics(), dict(config, train_mode="autoregressive")).modified_params()
