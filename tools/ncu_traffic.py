@@ -21,7 +21,7 @@ def main():
                                     "gpu__time_duration.sum")}
     out = {}
     for r in rows[2:]:
-        name = r[ix["Kernel Name"]].split("(")[0].split("::")[-1]
+        name = r[ix["Kernel Name"]].split("(")[0].split("::")[-1].split("<")[0].replace("void ", "").strip()
         rd = float(r[ix["dram__bytes_read.sum"]]) * SCALE[units[ix["dram__bytes_read.sum"]]]
         wr = float(r[ix["dram__bytes_write.sum"]]) * SCALE[units[ix["dram__bytes_write.sum"]]]
         out[name] = rd + wr
