@@ -22,6 +22,8 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) { return *p; }
 __device__ __forceinline__ unsigned ticket_add(unsigned* p) { return simte::atomic_inc(p); }
 __device__ __forceinline__ void fence_system() {}
 __device__ __forceinline__ long long p2p_clock() { return simte::slow_clock(); }
+__device__ __forceinline__ void p2p_griddep_wait() {}
+__device__ __forceinline__ void p2p_griddep_launch() {}
 #else
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
@@ -41,6 +43,10 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 __device__ __forceinline__ unsigned ticket_add(unsigned* p) { return atomicAdd(p, 1u); }
 __device__ __forceinline__ void fence_system() { __threadfence_system(); }
 __device__ __forceinline__ long long p2p_clock() { return clock64(); }
+// programmatic dependent launch (layouts.h APG_LAUNCH_PDL): the kernel before in the stream has completed / the kernel
+// after may start
+__device__ __forceinline__ void p2p_griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void p2p_griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 #endif
 }  // namespace
 
@@ -52,6 +58,8 @@ __global__ void __launch_bounds__(128)
                                   unsigned* const* __restrict__ flags, int rank, int world, unsigned epoch,
                                   unsigned* __restrict__ ticket) {
   __shared__ float s_part[4][32];
+  p2p_griddep_wait();                          // the partials of the adjoint kernel before are complete
+  p2p_griddep_launch();                        // the gather kernel may start polling its flags
   const int pl = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int p = blockIdx.x * 32 + pl;
   const int per = (ncta + 3) / 4;
@@ -79,6 +87,9 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
                                           float* __restrict__ param, float* __restrict__ momentum_buf, float lr,
                                           float momentum) {
   __shared__ int s_ok;
+  // Launched with programmatic serialization and WITHOUT a griddepcontrol.wait: what it consumes arrives through the
+  // flags (this rank's own contribution included), and nothing earlier in the stream still touches what it writes
+  // (parameters, momentum buffer, gradient); the next kernel of the stream is launched normally and waits for it.
   if (threadIdx.x == 0) {
     int ok = 1;
     const long long t0 = p2p_clock();
@@ -106,7 +117,7 @@ __global__ void apg_gather_sgd_p2p_kernel(const float* __restrict__ slots_local,
 cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, float scale, int pm_off, int pm_k1,
                                       int pm_npos, float* const* slots, unsigned* const* flags, int rank, int world,
                                       unsigned epoch, unsigned* ticket, cudaStream_t st) {
-  APG_LAUNCH((n + 31) / 32, 128, 0, st, apg_reduce_scatter_p2p_kernel)(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
+  APG_LAUNCH_PDL((n + 31) / 32, 128, 0, st, apg_reduce_scatter_p2p_kernel)(partials, ncta, n, scale, pm_off, pm_k1, pm_npos,
                                                                  slots, flags, rank, world, epoch, ticket);
   return cudaGetLastError();
 }
@@ -114,7 +125,7 @@ cudaError_t launch_reduce_scatter_p2p(const float* partials, int ncta, int n, fl
 cudaError_t launch_gather_sgd_p2p(const float* slots_local, const unsigned* flags_local, int world, int n,
                                   unsigned epoch, float* grad_out, float* param, float* momentum_buf, float lr,
                                   float momentum, cudaStream_t st) {
-  APG_LAUNCH((n + 127) / 128, 128, 0, st, apg_gather_sgd_p2p_kernel)(slots_local, flags_local, world, n, epoch, grad_out, param,
+  APG_LAUNCH_PDL((n + 127) / 128, 128, 0, st, apg_gather_sgd_p2p_kernel)(slots_local, flags_local, world, n, epoch, grad_out, param,
                                                              momentum_buf, lr, momentum);
   return cudaGetLastError();
 }

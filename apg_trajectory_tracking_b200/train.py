@@ -67,13 +67,34 @@ class FusedTrainStep:
         # forward chain, dynamics (+ loss sum), dX chain, dW GEMM, grad-reduce (+ SGD on one device) on the tcgen05 path;
         # elsewhere the SGD update adds two torch element-wise launches, N > 1 one NCCL all-reduce kernel
         self.kernel_launches_per_step = 6 if getattr(self.runner, "tcgen05", False) else 5
+        # Gradient exchange with more than one rank.  Measured on 2 / 4 / 8 B200 (profiles/r2_multi_gpu.md): the package's
+        # own peer-memory kernels beat NCCL all-reduce + two optimizer launches at every size (8 GPUs: 0.324 vs 0.336 ms
+        # per iteration) and keep the replicas bitwise identical, so they are the DEFAULT for the configuration they
+        # were measured on (the tcgen05 path, NCCL backend); APG_P2P_GRAD=0 / =1 forces NCCL / the peer kernels
+        # everywhere.  If the peer mappings cannot be set up on some rank, all ranks fall back to NCCL together.
         if peer_exchange is None:
-            peer_exchange = os.environ.get("APG_P2P_GRAD") == "1"
+            env = os.environ.get("APG_P2P_GRAD")
+            if env is not None:
+                peer_exchange = env == "1"
+            else:
+                peer_exchange = bool(getattr(self.runner, "tcgen05", False)) and self.distributed and \
+                    torch.distributed.get_backend(process_group) == "nccl"
         self.peer = None
         if peer_exchange and self.distributed:
             from . import dist as D
-            self.peer = D.PeerGradExchange(self.runner.n_params, self.device, process_group)
-            self.kernel_launches_per_step += 1  # + the gather / SGD kernel (the exchange rides on the grad-reduce)
+            try:
+                self.peer = D.PeerGradExchange(self.runner.n_params, self.device, process_group)
+                ok = 1.0
+            except Exception as ex:                                   # noqa: BLE001
+                if os.environ.get("APG_P2P_GRAD") == "1":
+                    raise
+                self.peer, ok, self.peer_error = None, 0.0, f"{type(ex).__name__}: {ex}"[:200]
+            flag = torch.tensor([ok], device=self.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=process_group)
+            if float(flag.item()) < 1.0:
+                self.peer = None
+            if self.peer is not None:
+                self.kernel_launches_per_step += 1  # + the gather / SGD kernel (the exchange rides on the grad-reduce)
 
     def _dev(self, x):
         if x is None:

@@ -366,13 +366,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="quad_concurrent", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override drones per GPU")
+    ap.add_argument("--drones-per-gpu", "--n", dest="n", type=int, default=0, help="override drones per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-raw-e2e", action="store_true", help="skip the raw-sample (step_host) end-to-end arm")
     ap.add_argument("--p2p-grad", action="store_true",
                     help="N>1: exchange the gradient with the package's own kernels over NVLink peer memory "
                          "(APG_P2P_GRAD=1) instead of the NCCL all-reduce")
+    ap.add_argument("--nccl-grad", action="store_true",
+                    help="N>1: force the NCCL all-reduce + torch optimizer ops (APG_P2P_GRAD=0); default on the tcgen05 "
+                         "path: the peer-memory kernels")
     ap.add_argument("--legacy-mma", action="store_true",
                     help="quad_concurrent: run the mma.sync kernels (APG_LEGACY_MMA=1) instead of the tcgen05 path")
     args = ap.parse_args()
@@ -390,6 +393,8 @@ def main():
         return
     if args.p2p_grad:
         os.environ["APG_P2P_GRAD"] = "1"
+    if args.nccl_grad:
+        os.environ["APG_P2P_GRAD"] = "0"
     if args.legacy_mma:
         os.environ["APG_LEGACY_MMA"] = "1"
 

@@ -23,7 +23,7 @@ for np in 1 2 4 8; do
   run bench_quad_concurrent_g${np}_nccl $np --steps 50 --warmup 5 --no-cpu-baseline
   [ "$np" = 1 ] || run bench_quad_concurrent_g${np}_p2p $np --steps 50 --warmup 5 --no-cpu-baseline --p2p-grad
 done
-run bench_wing_concurrent_g4 4 --workload wing_concurrent --n 32768 --steps 20 --warmup 5 --no-cpu-baseline
+run bench_wing_concurrent_g4 4 --workload wing_concurrent --drones-per-gpu 32768 --steps 20 --warmup 5 --no-cpu-baseline
 run bench_wing_concurrent_g4_weak 4 --workload wing_concurrent --steps 20 --warmup 5 --no-cpu-baseline
 run bench_quad_lstm_g8 8 --workload quad_lstm --steps 20 --warmup 5 --no-cpu-baseline
 run bench_quad_autoregressive_g8 8 --workload quad_autoregressive --steps 20 --warmup 5 --no-cpu-baseline
