@@ -294,3 +294,53 @@ def test_full_size_properties():
                                                  sub["ref"], h, dt)
     assert abs(ls - float(ol)) <= LOSS_TOL * abs(float(ol))
     assert max_rel_to_scale(acts, oact) <= ACT_TOL
+
+
+@pytest.mark.parametrize("config", ["wing_131072", "autoregressive_65536", "lstm_32768"])
+def test_full_size_properties_of_the_other_baseline_configurations(config):
+    """BASELINE.json configs 3-5 at their per-GPU sizes (fixed wing h = 20 N = 131072; quad autoregressive h = 10
+    N = 65536; quad LSTM h = 10, 32768 of the 262144 drones per GPU): run-to-run bitwise determinism, additivity of loss
+    and gradient over a partition of the drones, and a 256-drone sample of the SAME batch against the oracle - loss,
+    actions, states AND the parameter gradient."""
+    R, SY, P, _capi, O = _imports()
+    import bench as B
+    kind, n = config.split("_")[0], int(config.split("_")[1])
+    if kind == "wing":
+        h, dt = 20, 0.05
+        case = SY.wing_case(n, h, dt, seed=3)
+        params = B.default_init("wing", h, seed=3)
+        spec = R.RolloutSpec.wing_concurrent(h, dt)
+        args = lambda sl: (case["in_state"][sl], case["cur"][sl], case["in_ref"][sl], case["ref"][sl], None)   # noqa: E731
+        oracle = lambda a: O.concurrent_value_and_grad("wing", params, a[0], a[1], a[2], a[3], h, dt)          # noqa: E731
+    else:
+        h, dt = 10, 0.1
+        mode = "autoregressive" if kind == "autoregressive" else "lstm"
+        case = SY.quad_case(n, 2 * h, dt, seed=4)
+        params = B.default_init("quad", h, seed=4, mode=mode)
+        spec = R.RolloutSpec.quad_recurrent(mode, h, dt, "cumulative")
+        gen = torch.Generator().manual_seed(9)
+        hc = torch.stack((torch.randn(n, 8, generator=gen), torch.randn(n, 8, generator=gen)), 0) if mode == "lstm" else None
+        args = lambda sl: (None, case["cur"][sl], case["in_ref"][sl], case["ref"][sl],                          # noqa: E731
+                           None if hc is None else hc[:, sl].contiguous())
+        oracle = lambda a: O.recurrent_value_and_grad(mode, params, a[1], a[2], a[3], h, dt, window="cumulative",  # noqa: E731
+                                                      hc0=None if a[4] is None else (a[4][0], a[4][1]))
+    full = slice(0, n)
+    loss, _, _, grads, _ = _run_gpu(R, spec, params, *args(full))
+    loss2, _, _, grads2, _ = _run_gpu(R, spec, params, *args(full))
+    assert loss == loss2 and all(torch.equal(a, b) for a, b in zip(grads, grads2))
+    cut = (n * 5 // 8) // 64 * 64
+    parts = [_run_gpu(R, spec, params, *args(sl)) for sl in (slice(0, cut), slice(cut, n))]
+    assert abs(parts[0][0] + parts[1][0] - loss) <= 2e-5 * abs(loss)
+    for gfull, ga, gb in zip(grads, parts[0][3], parts[1][3]):
+        if float(gfull.abs().max()) > 0:
+            # the gradient is a sum over drones whose terms cancel: the bar is relative to the size of the two partial
+            # sums (what fp32 reassociation can move), not to the norm of their sum
+            bar = 2e-5 * float(gfull.norm()) + 2e-6 * float((ga.abs() + gb.abs()).norm())
+            assert float((ga + gb - gfull).norm()) <= bar
+    idx = torch.arange(0, n, n // 256)
+    sub = args(idx)
+    ls, sts, acts, gs, _ = _run_gpu(R, spec, params, *sub)
+    ol, og, ost, oact = oracle(sub)
+    assert abs(ls - float(ol)) <= LOSS_TOL * abs(float(ol)), (ls, float(ol))
+    assert max_rel_to_scale(acts, oact) <= 2e-5 and max_rel_to_scale(sts, ost) <= 2e-5
+    _check_grads(gs, og, tol=2e-4)
