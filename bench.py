@@ -208,6 +208,33 @@ def raw_host_inputs(w, host):
     return kw
 
 
+def live_dram_traffic(workload, n, kernel):
+    """dram bytes (read + write) of one launch of `kernel` in workload `workload` at n drones, from a short ncu run of
+    tools/one_step.py in a child process; None if ncu is missing / fails / finds no such launch"""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+           "-k", "regex:" + kernel, "-s", "2", "-c", "1", sys.executable, os.path.join(ROOT, "tools", "one_step.py"),
+           workload, str(n), "4"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+        rows = list(csv.reader(io.StringIO(out[out.index('"ID"'):])))
+        hdr = rows[0]
+        total = 0.0
+        for r in rows[1:]:
+            if len(r) != len(hdr):
+                continue
+            unit, val = r[hdr.index("Metric Unit")], float(r[hdr.index("Metric Value")].replace(",", ""))
+            total += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        return total if total > 0 else None
+    except Exception:                                               # noqa: BLE001
+        return None
+
+
 def measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier):
     """e2e through FusedTrainStep.step_host: per step H2D of the raw samples (chunked, copy stream), device-side
     prepare, forward, adjoint, [allreduce], SGD, D2H of the loss.  Before timing, loss and gradient of this path are
@@ -370,6 +397,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-raw-e2e", action="store_true", help="skip the raw-sample (step_host) end-to-end arm")
+    ap.add_argument("--no-live-traffic", action="store_true",
+                    help="do not measure roofline.traffic with an ncu child process (use profiles/ncu_traffic.json)")
     ap.add_argument("--p2p-grad", action="store_true",
                     help="N>1: exchange the gradient with the package's own kernels over NVLink peer memory "
                          "(APG_P2P_GRAD=1) instead of the NCCL all-reduce")
@@ -587,13 +616,21 @@ def main():
             dom_ms, model = ms_adj, {}
         alg_bytes = 0.5 * w["bytes_per_step"] * n * h
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
-            except Exception:
-                traffic = None
+        # DRAM bytes of ONE launch of the dominant kernel: measured now, by a short ncu capture of the same workload in
+        # a child process (two metrics, one kernel launch, outside every timed region); if ncu is not there or fails,
+        # the figure of the committed `--set full` capture (profiles/ncu_traffic.json), and the line says which
+        traffic, traffic_src = None, None
+        if world == 1 and not args.no_live_traffic:
+            traffic = live_dram_traffic(args.workload, n, dom.split(" ")[0])
+            traffic_src = "ncu child process of this run (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        if traffic is None:
+            tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+                    traffic_src = "profiles/ncu_traffic.json (committed ncu --set full capture)"
+                except Exception:
+                    traffic = None
         flops = w["flops_per_step"] * n * h
         if tq:
             tf32_peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1650.0))) / 2.0
@@ -628,11 +665,11 @@ def main():
             "ms_forward_kernel": ms_fwd, "ms_adjoint_kernel": ms_adj, "wall_s_timed_region": t_wall,
             "final_loss": final_loss,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "ms_kernel": dom_ms,
                          "note": "algorithmic bytes = the per-drone inputs read once by the adjoint pass (SURVEY 8d: "
                                  "828 B per drone for this workload) over the duration of the dominant launch; "
-                                 "traffic = ncu dram bytes of one launch of that kernel (profiles/ncu_traffic.json); "
+                                 "traffic = ncu dram bytes of one launch of that kernel (traffic_source); "
                                  "the kernels move more than the algorithmic bytes by design (operand-image stash, "
                                  "see roofline_stash); the path as a whole is compute / latency bound, see "
                                  "roofline_compute"},

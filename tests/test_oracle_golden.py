@@ -125,6 +125,47 @@ def test_recurrent_gradients_exist_and_match_fp64():
             assert rel_err(a, b) <= 5e-5
 
 
+@pytest.mark.parametrize("mode,fname,window", [("autoregressive", "rec_ar_rand.npz", "cumulative"),
+                                               ("autoregressive", "rec_ar_rand.npz", "relative"),
+                                               ("lstm", "rec_lstm_rand.npz", "cumulative")])
+def test_recurrent_gradient_oracle_against_fp64_finite_differences(mode, fname, window):
+    """The reference's own backward() raises in the recurrent modes (in-place write into the shared reference buffer,
+    train_drone.py:138-142), so no reference gradient exists to pin the oracle's on.  What CAN be pinned: the oracle's
+    forward on the reference's forward (the goldens above), and its gradient on that forward - autograd of the
+    restatement against CENTRAL FINITE DIFFERENCES of the same fp64 loss, for a random sample of entries of every
+    parameter tensor.  A gradient that matches finite differences of a forward that matches the reference is the
+    gradient the reference would compute if its backward ran."""
+    g = load_golden(fname)
+    h, dt = int(g["h"]), float(g["dt"])
+    d = torch.float64
+    n = 6                                                  # a few drones: the loss is a sum over drones
+    params = golden_params(g, d)
+    cur, in_ref, ref = t(g["cur"], d)[:n], t(g["in_ref"], d)[:n], t(g["ref"], d)[:n]
+    hc0 = (t(g["h0"], d)[:n], t(g["c0"], d)[:n]) if mode == "lstm" else None
+
+    def loss_of(ps):
+        return float(O.rollout_recurrent(mode, ps, cur, in_ref, ref, h, dt, window=window, hc0=hc0)[0])
+
+    _, grads, _, _ = O.recurrent_value_and_grad(mode, params, cur, in_ref, ref, h, dt, window=window, hc0=hc0)
+    gen = torch.Generator().manual_seed(7)
+    checked = 0
+    for i, (p, gp) in enumerate(zip(params, grads)):
+        if gp is None:
+            continue
+        flat = p.reshape(-1)
+        for j in torch.randperm(flat.numel(), generator=gen)[:4].tolist():
+            eps = 1e-6 * max(1.0, abs(float(flat[j])))
+            plus = [q.clone() for q in params]
+            minus = [q.clone() for q in params]
+            plus[i].reshape(-1)[j] += eps
+            minus[i].reshape(-1)[j] -= eps
+            fd = (loss_of(plus) - loss_of(minus)) / (2 * eps)
+            an = float(gp.reshape(-1)[j])
+            assert abs(fd - an) <= 1e-6 * max(1.0, abs(an), float(gp.abs().max())), (mode, window, i, j, fd, an)
+            checked += 1
+    assert checked >= 20
+
+
 def test_sgd_momentum_matches_torch():
     torch.manual_seed(0)
     p = [torch.randn(5, 3), torch.randn(7)]

@@ -16,7 +16,7 @@ timeout 300 python tools/tq_kernel_times.py 65536 > "$out/kernel_times.log" 2>&1
 APG_B200_LIB=$PWD/apg_trajectory_tracking_b200/libapg_b200_prof.so timeout 300 python tools/tq_profile.py > "$out/tq_profile.log" 2>&1
 timeout 300 python tools/raw_vs_prepared.py 65536 > "$out/raw_vs_prepared.log" 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_bench.csv" \
-  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-raw-e2e > "$out/bench_under_ncu.log" 2>&1
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-raw-e2e --no-live-traffic > "$out/bench_under_ncu.log" 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on \
   -k regex:'tq_fwd_kernel|tq_dx_kernel|tq_dw_kernel|tq_dyn_kernel|apg_reduce4' -s 14 -c 5 -o "$out/tq_kernels" \
   python tools/quick_bench.py 65536 > "$out/ncu_tq.log" 2>&1
