@@ -617,6 +617,20 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
     unsigned char* zo_b = zstash + (size_t)tile * tq::Z_TILE_BYTES + tq::set_base(tq::O_ZO) +
                           (size_t)(row >> 5) * (MO * 128) + (row & 3) * 4;
     auto elem = [&](int r) { return (uint32_t)r * 128u + (c4 ^ ((uint32_t)(r & 7) << 4)); };
+#ifndef TQ_DYN_NO_PREFETCH
+    {
+      // Everything this warp will read over the 2 x h dependent steps, into L2 now: the 40 action rows of its panel
+      // (one 128-byte line each) and its 32 drones' reference rows (contiguous) - the per-step loads below then cost an
+      // L2 hit instead of an HBM round trip each (the kernel is one wave of 14 warps per SM: latency is all it has).
+      const unsigned char* act_panel = fstash + (size_t)tile * tq::F_TILE_BYTES + tq::set_base(tq::O_ACT) +
+                                       (size_t)(row >> 5) * (tq::R_ACT * 128);
+      prefetch_lines(act_panel, tq::R_ACT, lane);
+      const size_t d0 = (size_t)tile * TMT + (size_t)(row & ~31);
+      if (d0 + 32 <= (size_t)n)
+        prefetch_lines(reinterpret_cast<const unsigned char*>(g.ref + d0 * g.ref_rows * R), 32 * g.ref_rows * R * 4 / 128,
+                       lane);
+    }
+#endif
     if (live) {
       float sc[S], s0[S], sn[S], rf[R], a[A];
       const float* cur_g = g.cur + drone * S;
