@@ -33,6 +33,8 @@ EXPORTS = {
     "apg_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ApgConfig)]),
     "apg_rollout_forward": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p] +
                             [c_float_p] * 3 + [ctypes.c_void_p]),
+    "apg_rollout_forward_learnt": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p] +
+                                   [c_float_p] * 3 + [ctypes.c_void_p]),
     "apg_rollout_backward": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p,
                              ctypes.c_float, c_float_p, ctypes.c_void_p]),
     "apg_rollout_backward_sgd": (ctypes.c_int, [ctypes.POINTER(ApgConfig)] + [c_float_p] * 6 + [ctypes.c_void_p,

@@ -302,18 +302,25 @@ __attribute__((visibility("default"))) size_t apg_workspace_bytes(const apg_conf
   return make_plan(cfg, net_info(cfg)).total;
 }
 
-__attribute__((visibility("default"))) int apg_rollout_forward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
-                        const float* in_ref, const float* ref, const float* h0c0, void* workspace, float* loss,
-                        float* states_out, float* actions_out, void* stream) {
+}  // extern "C"
+
+namespace {
+int rollout_forward_impl(const apg_config* cfg, const float* params, const float* learnt, const float* in_state,
+                         const float* cur, const float* in_ref, const float* ref, const float* h0c0, void* workspace,
+                         float* loss, float* states_out, float* actions_out, void* stream) {
   int e = check_config(cfg);
   if (e) return e;
   if ((e = check_ptrs(cfg, params, in_state, cur, in_ref, ref, h0c0, workspace))) return e;
   if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  // learnt dynamics inside the horizon: the dynamics kernel of the tcgen05 path has the variant, nothing else does
+  if (learnt && !(is_hutter(cfg) && !is_recurrent(cfg) && use_tq(cfg, hutter_layout(cfg)))) return APG_ERR_UNSUPPORTED;
+  if (!aligned16(learnt)) return APG_ERR_ALIGNMENT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const Plan p = make_plan(cfg, net_info(cfg));
   RolloutArgs a = make_args(cfg, p, in_state, cur, in_ref, ref, h0c0, workspace);
   a.states_out = states_out;
   a.actions_out = actions_out;
+  a.learnt = learnt;
   cudaError_t ce;
   if (is_hutter(cfg)) {
     const HutterLayout y = hutter_layout(cfg);
@@ -360,6 +367,32 @@ __attribute__((visibility("default"))) int apg_rollout_forward(const apg_config*
   }
   if (loss && (ce = launch_sum_loss(a.loss_partials, p.grid, loss, st))) return (int)ce;
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) int apg_rollout_forward(const apg_config* cfg, const float* params, const float* in_state, const float* cur,
+                        const float* in_ref, const float* ref, const float* h0c0, void* workspace, float* loss,
+                        float* states_out, float* actions_out, void* stream) {
+  return rollout_forward_impl(cfg, params, nullptr, in_state, cur, in_ref, ref, h0c0, workspace, loss, states_out,
+                              actions_out, stream);
+}
+
+// apg_rollout_forward with the h dynamics steps taken by the LEARNT residual model (LearntDynamics.forward,
+// neural_control/dynamics/quad_dynamics_trained.py:58-69) instead of the analytic one: the controller-training phase of
+// run_dynamics (scripts/train_base.py:334-375 -> train_drone.py:175-199 with train_dynamics = LearntDynamics) as one
+// fused rollout.  `learnt_params`: the 1891 floats of apg_learnt_num_params(APG_SYS_QUAD), named_parameters() order;
+// cfg->phys carries the construction-time constants of the learnt object.  The reverse sweep (d loss / d logits through
+// the learnt steps) is part of this call, so the adjoint of it is the ordinary apg_rollout_backward / _sgd / _p2p.
+// Configurations served by the tcgen05 path only (apg_rollout_kernel_path(cfg) == 1), APG_ERR_UNSUPPORTED otherwise.
+__attribute__((visibility("default"))) int apg_rollout_forward_learnt(const apg_config* cfg, const float* params,
+                        const float* learnt_params, const float* in_state, const float* cur, const float* in_ref,
+                        const float* ref, void* workspace, float* loss, float* states_out, float* actions_out,
+                        void* stream) {
+  if (!learnt_params) return APG_ERR_BAD_CONFIG;
+  return rollout_forward_impl(cfg, params, learnt_params, in_state, cur, in_ref, ref, nullptr, workspace, loss,
+                              states_out, actions_out, stream);
 }
 
 }  // extern "C"

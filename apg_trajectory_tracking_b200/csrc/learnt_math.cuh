@@ -115,6 +115,54 @@ struct LearntQuad {
     }
   }
 
+  // ---- streaming forms for the fused horizon kernels (controller trained THROUGH the learnt dynamics,
+  //      scripts/train_drone.py:175-199 with train_dynamics = LearntDynamics): state / action cotangents only, hidden
+  //      units produced and consumed one at a time (nothing but registers), same summation order as forward / adjoint
+  //      above.  `pc` holds the analytic constants, P the flat parameter vector (shared memory in the kernels).
+  APG_HD static void step_sa(const T* P, const float* pc, const T* s, const T* a, T dt, T* out) {
+    T at[4], v[Y::SD];
+    transform_action(P, a, at);
+    Quad<T>::step(s, at, dt, pc, out);
+#pragma unroll
+    for (int i = 0; i < Y::SD; ++i) v[i] = P[Y::O_B2 + i];
+#pragma unroll 4
+    for (int j = 0; j < Y::HD; ++j) {
+      const T hj = hidden(P, s, at, j);
+#pragma unroll
+      for (int i = 0; i < Y::SD; ++i) v[i] += P[Y::O_W2 + i * Y::HD + j] * hj;
+    }
+#pragma unroll
+    for (int i = 0; i < Y::SD; ++i) out[i] += v[i];
+  }
+  APG_HD static void step_adj_sa(const T* P, const float* pc, const T* s, const T* a, T dt, const T* g, T* gs, T* ga) {
+    T at[4], gat[4], acc[Y::XD];
+    transform_action(P, a, at);
+    Quad<T>::step_adj(s, at, dt, pc, g, gs, gat);
+#pragma unroll
+    for (int k = 0; k < Y::XD; ++k) acc[k] = T(0);
+#pragma unroll 4
+    for (int j = 0; j < Y::HD; ++j) {
+      T dh = T(0);
+      if (hidden(P, s, at, j) > T(0)) {
+#pragma unroll
+        for (int i = 0; i < Y::SD; ++i) dh += P[Y::O_W2 + i * Y::HD + j] * g[i];
+      }
+#pragma unroll
+      for (int k = 0; k < Y::XD; ++k) acc[k] += P[Y::O_W1 + j * Y::XD + k] * dh;
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) gs[k] += acc[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gat[k] += acc[12 + k];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      T v = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v += P[Y::O_LAT + r * 4 + c] * gat[r];
+      ga[c] = v;
+    }
+  }
+
   // ---- the interface the kernels use (same for the fixed wing): x = the 16 inputs of the residual MLP,
   //      dph = per-drone cotangents of the NPH = 23 parameters that precede the MLP in the flat vector
   static constexpr int NPH = Y::O_W1;

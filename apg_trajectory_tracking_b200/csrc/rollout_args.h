@@ -34,6 +34,9 @@ struct RolloutArgs {
   float* grad_partials;    // [gridDim.x][n_params]   (adjoint kernel)
   float* states_out;       // optional [N][h][S]
   float* actions_out;      // optional [N][h][A]
+  // learnt residual dynamics (quad_dynamics_trained.py:10-69) in place of the analytic step: flat parameter vector of
+  // LearntDynamics (learnt_math.cuh layout, 1891 floats) or NULL.  tcgen05 path only (tq_dyn_kernel<true>).
+  const float* learnt;
 };
 
 }  // namespace apg

@@ -19,6 +19,7 @@
 #include "tq_layout.cuh"
 #include "tc_prims.cuh"
 #include "rollout_args.h"
+#include "learnt_math.cuh"
 #ifndef APG_TC_SIM
 #include "tile_engine.cuh"
 #endif
@@ -588,12 +589,18 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
 // once the reverse sweep (hand-written adjoints, apg_math.cuh) -> d loss / d logits into set ZO of the dZ stash.
 // States of the horizon live in shared memory ([k*12 + q][thread], conflict free); nothing but the actions is read
 // from the stash and nothing but ZO is written.  Dead drones of a ragged tile write zeros.
+// LEARNT: the step is LearntDynamics.forward (quad_dynamics_trained.py:58-69: analytic step on the transformed action +
+// residual MLP 16 -> 64 -> 12, parameters g.learnt staged in shared memory) and the reverse sweep goes through its
+// state / action adjoint - the controller-through-learnt-dynamics epoch of train_drone.py:260-278 as ONE fused rollout.
 // =========================================================================================================
-__global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
+template <bool LEARNT>
+__global__ void __launch_bounds__(TQ_DYN_THREADS, LEARNT ? 4 : 7)
     tq_dyn_kernel(const RolloutArgs g, unsigned char* __restrict__ fstash, unsigned char* __restrict__ zstash,
                   float* __restrict__ loss_out, unsigned* __restrict__ ticket, unsigned ticket0) {
   APG_TC_DYNAMIC_SMEM(smem_raw);
   float* s_st = reinterpret_cast<float*>(smem_raw);           // [H*12][TQ_DYN_THREADS]
+  __shared__ float s_lp[LEARNT ? LearntLayout::NP + 1 : 1];   // LearntDynamics parameters (inputs, not forward results)
+  using LQ = LearntQuad<float>;
   __shared__ float s_red[TQ_DYN_THREADS / 32];
   __shared__ double s_dsum[TQ_DYN_THREADS];
   __shared__ int s_last;
@@ -605,6 +612,10 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
   float my_loss = 0.f;
   tcp::griddep_wait();                                        // the forward chain has completed (actions in the stash)
   tcp::griddep_launch();                                      // AFTER the wait: whoever starts now knows that too
+  if (LEARNT) {
+    for (int i = threadIdx.x; i < LearntLayout::NP; i += TQ_DYN_THREADS) s_lp[i] = g.learnt[i];
+    __syncthreads();
+  }
   // the horizon loops are NOT unrolled (measured: the unrolled body thrashed the instruction cache, 6 of 10 issue
   // slots lost to instruction fetch); actions / logit gradients go straight from / to the stash sets per step
   for (int hb = blockIdx.x; hb < nhalf; hb += gridDim.x) {
@@ -648,7 +659,8 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
         for (int c = 0; c < A; ++c) a[c] = *reinterpret_cast<const float*>(act_b + elem(k * A + c));
 #pragma unroll
         for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c] - (c < 3 ? p0[c] : 0.f);
-        Sys::step(sc, a, g.dt, g.pc.v, sn);
+        if (LEARNT) LQ::step_sa(s_lp, g.pc.v, sc, a, g.dt, sn);
+        else Sys::step(sc, a, g.dt, g.pc.v, sn);
         my_loss += Sys::loss(sn, rf, a, s0, k, H);
 #pragma unroll
         for (int q = 0; q < S; ++q) {
@@ -682,7 +694,8 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, 7)
           for (int q = 0; q < S; ++q) sk[q] = s0[q];
         }
         Sys::loss_grad(sn, rf, a, s0, k, H, gq, ga);
-        Sys::step_adj(sk, a, g.dt, g.pc.v, gq, gs, ga2);
+        if (LEARNT) LQ::step_adj_sa(s_lp, g.pc.v, sk, a, g.dt, gq, gs, ga2);
+        else Sys::step_adj(sk, a, g.dt, g.pc.v, gq, gs, ga2);
 #pragma unroll
         for (int c = 0; c < A; ++c)
           *reinterpret_cast<float*>(zo_b + elem(k * A + c)) = (ga[c] + ga2[c]) * a[c] * (1.f - a[c]);      // sigmoid'
@@ -982,9 +995,14 @@ cudaError_t launch_tq_fwd(const unsigned char* blob, const RolloutArgs& a, unsig
 // dynamics / loss / reverse sweep: writes tq_dyn_grid(n, sms) loss partials and (loss_out != NULL) their sum
 cudaError_t launch_tq_dyn(const RolloutArgs& a, unsigned char* fstash, unsigned char* zstash, float* loss_out,
                           unsigned* ticket, unsigned ticket0, int dyn_grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tq_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(tq_dyn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tq_dyn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TQ_DYN_SMEM);
   if (e != cudaSuccess) return e;
-  APG_LAUNCH_PDL(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel)(a, fstash, zstash, loss_out, ticket, ticket0);
+  if (a.learnt)
+    APG_LAUNCH_PDL(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel<true>)(a, fstash, zstash, loss_out, ticket, ticket0);
+  else
+    APG_LAUNCH_PDL(dyn_grid, TQ_DYN_THREADS, TQ_DYN_SMEM, st, tq_dyn_kernel<false>)(a, fstash, zstash, loss_out, ticket, ticket0);
   return cudaGetLastError();
 }
 

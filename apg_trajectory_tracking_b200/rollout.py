@@ -125,10 +125,14 @@ class Rollout:
     LOSS_RING = 1024
 
     def forward(self, params_flat, in_state, cur, in_ref=None, ref=None, h0c0=None, want_states=False,
-                want_actions=False):
+                want_actions=False, learnt_params=None):
         """One fused rollout; returns (loss, states or None, actions or None).  ``loss`` is a 1-element view into a ring
         of ``LOSS_RING`` device floats: it keeps its value until ``LOSS_RING`` further forwards have run (clone it to
-        keep it longer).  ``backward`` differentiates the LAST forward of this runner."""
+        keep it longer).  ``backward`` differentiates the LAST forward of this runner.
+
+        ``learnt_params`` (flat vector of ``LearntDynamics``, 1891 floats): the h steps are taken by the learnt residual
+        model instead of the analytic one (``apg_rollout_forward_learnt``; tcgen05 configurations only) - the
+        controller-through-learnt-dynamics phase of the reference (train_drone.py:175-199, 260-278)."""
         s = self.spec
         self.loss = self._loss_ring[self.forward_count % self.LOSS_RING:self.forward_count % self.LOSS_RING + 1]
         self.forward_count += 1
@@ -137,9 +141,22 @@ class Rollout:
         states = torch.empty(self.n, s.horizon, s.state_dim, device=self.device) if want_states else None
         actions = torch.empty(self.n, s.horizon, s.action_dim, device=self.device) if want_actions else None
         with torch.cuda.device(self.device):
-            _capi.check(self.lib.apg_rollout_forward(ctypes.byref(self.cfg), *[_ptr(x) for x in self._inputs],
-                                                     self._ws_ptr, _ptr(self.loss), _ptr(states), _ptr(actions),
-                                                     self._stream()))
+            if learnt_params is not None:
+                lp = _dev_f32(learnt_params, "learnt_params")
+                if lp.numel() != self.lib.apg_learnt_num_params(self.cfg.system):
+                    raise _capi.ApgError("learnt_params: wrong length for this system's learnt dynamics")
+                if h0c0 is not None:
+                    raise _capi.ApgError("learnt dynamics inside the rollout: concurrent mode only")
+                self._learnt = lp                  # keeps the vector alive until the launch has run
+                i = self._inputs
+                _capi.check(self.lib.apg_rollout_forward_learnt(ctypes.byref(self.cfg), _ptr(i[0]), _ptr(lp),
+                                                                _ptr(i[1]), _ptr(i[2]), _ptr(i[3]), _ptr(i[4]),
+                                                                self._ws_ptr, _ptr(self.loss), _ptr(states),
+                                                                _ptr(actions), self._stream()))
+            else:
+                _capi.check(self.lib.apg_rollout_forward(ctypes.byref(self.cfg), *[_ptr(x) for x in self._inputs],
+                                                         self._ws_ptr, _ptr(self.loss), _ptr(states), _ptr(actions),
+                                                         self._stream()))
         return self.loss, states, actions
 
     def backward(self, grad_loss=1.0, out=None):
@@ -173,8 +190,9 @@ class Rollout:
                                                           self._ws_ptr, ctypes.c_float(float(grad_loss)),
                                                           ctypes.byref(comm), self._stream()))
 
-    def value_and_grad(self, params_flat, in_state, cur, in_ref=None, ref=None, h0c0=None, out=None):
-        loss, _, _ = self.forward(params_flat, in_state, cur, in_ref, ref, h0c0)
+    def value_and_grad(self, params_flat, in_state, cur, in_ref=None, ref=None, h0c0=None, out=None,
+                       learnt_params=None):
+        loss, _, _ = self.forward(params_flat, in_state, cur, in_ref, ref, h0c0, learnt_params=learnt_params)
         return loss, self.backward(1.0, out=out)
 
 

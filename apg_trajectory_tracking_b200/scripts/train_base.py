@@ -55,7 +55,10 @@ class TrainBase:
             if self.train_mode != "concurrent":
                 raise ValueError("learnt dynamics are only supported with train_mode='concurrent' (the recurrent "
                                  "kernels integrate the analytic model)")
-            return {}
+            # quadrotor: the fused learnt rollout integrates with the construction-time constants of the learnt object
+            # (what its simulator keeps using, quad_dynamics_trained.py:47-48); fixed wing: per-step ops, spec unused
+            cfg = getattr(self.train_dynamics, "cfg", None) if self.system == "quad" else None
+            return dict(cfg) if isinstance(cfg, dict) else {}
         cfg = getattr(self.train_dynamics, "cfg", None)
         if cfg is not None:
             return dict(cfg)
@@ -102,15 +105,16 @@ class TrainBase:
         """implemented in the sub classes (un-fused path: the caller already evaluated the policy)"""
         raise NotImplementedError
 
-    def fused_train_step(self, in_state, current_state, in_ref_state, ref_states):
-        """zero_grad -> rollout loss + analytic gradient (two launches) -> optimizer step"""
+    def fused_train_step(self, in_state, current_state, in_ref_state, ref_states, learnt_params=None):
+        """zero_grad -> rollout loss + analytic gradient (two launches) -> optimizer step.  ``learnt_params``: the
+        horizon is rolled through the learnt dynamics with these (frozen) parameters."""
         self.optimizer_controller.zero_grad()
         h0c0 = None
         if self.train_mode == "LSTM":
             self.net.reset_hidden_state(current_state.size()[0])
             h0c0 = torch.stack((self.net.hidden_state, self.net.cell_state), 0)
         loss = self.fused.loss_and_grad(None if self.train_mode != "concurrent" else in_state, current_state,
-                                        in_ref_state, ref_states, h0c0)
+                                        in_ref_state, ref_states, h0c0, learnt_params=learnt_params)
         self.writer.add_scalar("loss/training", loss)
         self.optimizer_controller.step()
         return loss
@@ -120,9 +124,18 @@ class TrainBase:
         learnt = isinstance(self.train_dynamics, torch.nn.Module)      # LearntDynamics / LearntFixedWingDynamics
         for i, data in enumerate(self.trainloader, 0):
             in_state, current_state, in_ref_state, ref_states = data
-            if learnt and self.train_mode == "concurrent":
-                # the controller is trained THROUGH the learnt dynamics (train_drone.py:262-279): the reference's
-                # own loop, autograd over the per-step CUDA ops (policy forward, learnt step + its adjoint kernel)
+            fused_learnt = (learnt and self.train_mode == "concurrent" and self.system == "quad" and
+                            not self.config.get("unfused_learnt_rollout", False) and
+                            self.fused.supports_learnt_dynamics(current_state.shape[0]))
+            if fused_learnt:
+                # the controller is trained THROUGH the learnt dynamics (train_drone.py:262-279) in the fused rollout:
+                # the dynamics kernel of the tcgen05 path steps LearntDynamics.forward and its state / action adjoint
+                with torch.no_grad():
+                    lp = self.train_dynamics._flat().to(self.fused.device)
+                loss = self.fused_train_step(in_state, current_state, in_ref_state, ref_states, learnt_params=lp)
+            elif learnt and self.train_mode == "concurrent":
+                # configurations without the fused variant (fixed wing, other horizons): the reference's own loop,
+                # autograd over the per-step CUDA ops (policy forward, learnt step + its adjoint kernel)
                 dev = self.fused.device
                 in_state, current_state, in_ref_state, ref_states = (x.to(dev) for x in (in_state, current_state,
                                                                                           in_ref_state, ref_states))

@@ -377,9 +377,14 @@ class ModuleRollout:
     def _dev(self, x):
         return None if x is None else x.to(self.device, non_blocking=True)
 
-    def loss_and_grad(self, in_state, cur, in_ref=None, ref=None, h0c0=None):
+    def supports_learnt_dynamics(self, n):
+        """True if the rollout of n drones can take its steps through a learnt dynamics model (tcgen05 path)"""
+        return self.spec.system == "quad" and self.spec.mode == "concurrent" and getattr(self.runner(n), "tcgen05", False)
+
+    def loss_and_grad(self, in_state, cur, in_ref=None, ref=None, h0c0=None, learnt_params=None):
         """``in_ref=None`` for a quadrotor batch: the policy inputs are derived from the raw ``(cur, ref)`` samples on
-        the device (QuadDataset.prepare_data as a kernel, prepare.py) -- only those two tensors cross PCIe."""
+        the device (QuadDataset.prepare_data as a kernel, prepare.py) -- only those two tensors cross PCIe.
+        ``learnt_params``: flat parameters of a ``LearntDynamics`` the horizon is rolled through (see Rollout.forward)."""
         cur = self._dev(cur)
         runner = self.runner(cur.shape[0])
         in_state, in_ref, ref = self._dev(in_state), self._dev(in_ref), self._dev(ref)
@@ -389,7 +394,8 @@ class ModuleRollout:
             want = ("in_state", "cur", "in_ref", "ref") if self.spec.mode == "concurrent" else ("cur", "in_ref", "ref")
             d = PR.prepare_quad(cur, ref, want=want)
             in_state, cur, in_ref, ref = d.get("in_state"), d["cur"], d["in_ref"], d["ref"]
-        loss, _ = runner.value_and_grad(self.flat, in_state, cur, in_ref, ref, self._dev(h0c0), out=self.flat_grad)
+        loss, _ = runner.value_and_grad(self.flat, in_state, cur, in_ref, ref, self._dev(h0c0), out=self.flat_grad,
+                                        learnt_params=learnt_params)
         if torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size(self.pg) > 1:
             torch.distributed.all_reduce(self.flat_grad, group=self.pg)

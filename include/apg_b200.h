@@ -204,6 +204,18 @@ int apg_learnt_step_adjoint(int system, const float* params, const float* phys, 
                             float dt, int n, const float* grad_out, float* grad_state, float* grad_action,
                             float* grad_params, void* workspace, void* stream);
 
+/* The learnt quadrotor step INSIDE the fused rollout: apg_rollout_forward with every one of the h dynamics steps taken
+ * by LearntDynamics.forward instead of the analytic model - the controller-training phase of run_dynamics
+ * (scripts/train_base.py:334-375; scripts/train_drone.py:175-199 with self.train_dynamics = LearntDynamics, :260-278).
+ * `learnt_params`: the 1891 floats above (device); cfg->phys: the construction-time constants of the learnt object.
+ * Same inputs / outputs / raw-sample form as apg_rollout_forward; its adjoint is the ordinary apg_rollout_backward
+ * (or _sgd / _p2p) on the same workspace: d loss / d logits through the learnt steps is produced by this call, the
+ * gradient w.r.t. the LEARNT parameters is not (the reference's controller optimizer does not use it).
+ * Configurations with apg_rollout_kernel_path(cfg) == 1 only; APG_ERR_UNSUPPORTED otherwise. */
+int apg_rollout_forward_learnt(const apg_config* cfg, const float* params, const float* learnt_params,
+                               const float* in_state, const float* cur, const float* in_ref, const float* ref,
+                               void* workspace, float* loss, float* states_out, float* actions_out, void* stream);
+
 /* ---- the path's one collective (sum of the flat weight gradient over the drone-axis shards) as this
  * library's own kernels over NVLink peer memory, instead of a library all-reduce after the adjoint pass:
  *   apg_rollout_backward_p2p   = apg_rollout_backward whose final gradient reduction stores its result straight into

@@ -564,6 +564,19 @@ def learnt_quad_step(lparams, state, action, dt, cfg=QUAD_CFG):
     return new_state + added                                              # :65-66
 
 
+def rollout_concurrent_learnt(params, lparams, in_state, cur, in_ref, ref, h, dt, cfg=QUAD_CFG):
+    """The controller-training phase of run_dynamics (scripts/train_base.py:334-375): TrainDrone.train_controller_model
+    (scripts/train_drone.py:175-199) with self.train_dynamics = LearntDynamics - the concurrent quadrotor rollout whose
+    h steps are taken by the learnt model.  Returns (loss, states (N,h,12), actions (N,h,4))."""
+    act = torch.sigmoid(hutter_forward(params, in_state, in_ref, conv=True)).reshape(-1, h, 4)   # train_base.py:202-206
+    states, s = [], cur
+    for k in range(h):
+        s = learnt_quad_step(lparams, s, act[:, k], dt, cfg)                                      # train_drone.py:186-190
+        states.append(s)
+    states = torch.stack(states, dim=1)
+    return quad_mpc_loss(states, ref, act), states, act
+
+
 def learnt_dynamics_loss(lparams, state, action, target_next, dt, l2_lambda=0.0, cfg=QUAD_CFG):
     """TrainBase.train_dynamics_model (scripts/train_base.py:160-186): sum of squared differences between the learnt
     step and the target dynamics' step on the first action, + l2_lambda * (norms of the residual MLP tensors)."""

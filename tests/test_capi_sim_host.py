@@ -114,6 +114,52 @@ def test_rollout_forward_backward_through_the_c_abi_all_kernel_selections(simlib
     _check(loss, grad, params, want)
 
 
+def _learnt_case(n, seed):
+    """random policy + the reference-pinned learnt dynamics of tests/golden/learnt_dyn.npz (variant b: non-trivial
+    action transform and residual MLP), quadrotor concurrent case"""
+    g = load_golden("learnt_dyn.npz")
+    params = B.default_init("quad", 10, seed=seed)
+    case = SY.quad_case(n, 10, 0.1, seed=seed)
+    d = QT.LearntDynamics({"rotational_drag": [float(x) for x in g["b_rot_drag"]]})
+    with torch.no_grad():
+        for i, (_, p) in enumerate(d.named_parameters()):
+            if i not in (1, 2, 3):
+                p.copy_(torch.tensor(g[f"b_param_{i}"]))
+    lparams = [p.detach().clone() for _, p in d.named_parameters()]
+    cfg = dict(O.QUAD_CFG, rotational_drag=tuple(float(x) for x in g["b_rot_drag"]))
+    return params, case, d, lparams, cfg
+
+
+def test_rollout_through_learnt_dynamics_fused(simlib):
+    """apg_rollout_forward_learnt + apg_rollout_backward: the quadrotor concurrent rollout with every step taken by
+    LearntDynamics (tq_dyn_kernel<true>) gives the oracle's loss, states and policy gradient; and it differs from the
+    analytic rollout (the learnt parameters are live)"""
+    n = 100
+    params, case, d, lparams, cfg = _learnt_case(n, 23)
+    want = O.value_and_grad(lambda ps: O.rollout_concurrent_learnt(ps, lparams, case["in_state"], case["cur"],
+                                                                   case["in_ref"], case["ref"], 10, 0.1, cfg), params)
+    spec = R.RolloutSpec.quad_concurrent(10, 0.1, modified_params=dict(d.cfg))
+    runner = R.Rollout(spec, n, "cpu")
+    flat = R.flatten_params(params)
+    lflat = d._flat().detach()
+    loss, states, _ = runner.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"],
+                                     want_states=True, learnt_params=lflat)
+    loss = loss.clone()
+    grad = runner.backward(1.0)
+    _check(loss, grad, params, want)
+    assert float((states - want[2]).abs().max()) <= 2e-5 * float(want[2].abs().max())
+    plain, _, _ = runner.forward(flat, case["in_state"], case["cur"], case["in_ref"], case["ref"])
+    assert abs(float(plain) - float(loss)) > 1e-3 * abs(float(loss))
+    # configurations without the variant refuse instead of silently integrating the analytic model
+    wing = R.Rollout(R.RolloutSpec.wing_concurrent(10, 0.05), 8, "cpu")
+    wcase = SY.wing_case(8, 10, 0.05, seed=1) if hasattr(SY, "wing_case") else None
+    if wcase is not None:
+        wp = R.flatten_params(B.default_init("wing", 10, seed=1))
+        with pytest.raises(_capi.ApgError):
+            wing.forward(wp, wcase["in_state"], wcase["cur"], wcase["in_ref"], wcase["ref"],
+                         learnt_params=torch.zeros(1914))
+
+
 def test_peer_exchange_entry_points_single_rank(simlib):
     """apg_rollout_backward_p2p + apg_grad_gather_sgd_p2p with world = 1 on a host buffer: the gradient that comes
     out of the slot equals the plain backward's, and the fused SGD update equals the torch ops"""
@@ -425,3 +471,56 @@ def test_trainer_rollout_uses_the_physics_of_the_train_dynamics_it_was_given(sim
     assert abs(losses["modified"][0] - float(want)) <= 2e-5 * abs(float(want))
     with pytest.raises(ValueError):
         TD.TrainDrone(LearntDynamics(), FlightmareDynamics(), dict(config, train_mode="autoregressive")).modified_params()
+
+
+def test_trainer_epoch_through_learnt_dynamics_is_the_fused_rollout(simlib, monkeypatch):
+    """``TrainDrone.run_epoch`` with ``train_dynamics = LearntDynamics`` (the controller phase of the
+    reference's run_dynamics, train_drone.py:260-278) takes the FUSED rollout through the learnt steps
+    (apg_rollout_forward_learnt), follows the oracle's training on the same batches, and the un-fused per-step loop
+    (config ``unfused_learnt_rollout``) gives the same epoch loss"""
+    from apg_trajectory_tracking_b200.scripts import train_drone as TD
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from apg_trajectory_tracking_b200.neural_control import environments as ENV, dataset as DS
+    import importlib
+    monkeypatch.setattr(ENV, "compute_device", lambda: torch.device("cpu"), raising=False)
+    for name in ("models.hutter_model", "dynamics.quad_dynamics_flightmare", "dynamics.quad_dynamics_trained", "dataset",
+                 "drone_loss"):
+        mod = importlib.import_module("apg_trajectory_tracking_b200.neural_control." + name)
+        monkeypatch.setattr(mod, "_require_cuda", lambda *a, **k: None, raising=False)
+    g = load_golden("learnt_dyn.npz")
+    n, h, dt, bs, lr = 128, 10, 0.1, 64, 1e-5
+    raw = SY.quad_case(n, h, dt, seed=4)
+    config = dict(delta_t=dt, horizon=h, ref_dim=9, action_dim=4, state_size=12, batch_size=bs, system="quad",
+                  learning_rate_controller=lr, train_mode="concurrent", device="cpu")
+    curves, calls = [], []
+    real = simlib.apg_rollout_forward_learnt
+
+    def counted(*a):
+        calls.append(1)
+        return real(*a)
+    monkeypatch.setattr(simlib, "apg_rollout_forward_learnt", counted, raising=False)
+    for unfused in (False, True):
+        _, _, d, lparams, ocfg = _learnt_case(1, 0)
+        tr = TD.TrainDrone(d, FlightmareDynamics(), dict(config, unfused_learnt_rollout=unfused))
+        torch.manual_seed(0)
+        tr.initialize_model(state_data=DS.QuadDataset(raw["cur"].numpy(), raw["ref"].numpy()))
+        tr.trainloader = torch.utils.data.DataLoader(tr.state_data, batch_size=bs, shuffle=False)
+        if not unfused:
+            p0 = [p.detach().clone() for p in tr.net.parameters()]
+        before = len(calls)
+        curves.append(tr.run_epoch(epoch=0))
+        assert (len(calls) - before) == (0 if unfused else n // bs)
+        if not unfused:
+            trained = [p.detach().clone() for p in tr.net.parameters()]
+    ds = DS.QuadDataset(raw["cur"].numpy(), raw["ref"].numpy())
+    ps, bufs, run = [p.clone() for p in p0], [None] * len(p0), 0.0
+    for b in range(n // bs):
+        ins, cur, inr, ref = (torch.stack(x) for x in zip(*[ds[i] for i in range(b * bs, (b + 1) * bs)]))
+        loss, grads, _, _ = O.value_and_grad(
+            lambda q: O.rollout_concurrent_learnt(q, lparams, ins, cur, inr, ref, h, dt, ocfg), ps)
+        ps, bufs = O.sgd_momentum_step(ps, grads, bufs, lr)
+        run += float(loss)
+    want = run / (n // bs - 1)
+    assert abs(curves[0] - want) <= 2e-5 * abs(want) and abs(curves[1] - want) <= 2e-5 * abs(want), (curves, want)
+    for a, w in zip(trained, ps):
+        assert rel_err(a, w) <= 1e-4

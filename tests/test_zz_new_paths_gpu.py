@@ -442,6 +442,112 @@ def test_learnt_controller_epoch_through_identity_learnt_dynamics_equals_fused_e
         assert abs(a - b) <= 1e-4 * abs(a), losses
 
 
+@pytest.mark.parametrize("n", [100, 1337])
+def test_rollout_through_learnt_dynamics_fused_vs_oracle(n):
+    """apg_rollout_forward_learnt (tq_dyn_kernel<true>: every step = LearntDynamics.forward, reverse sweep through its
+    state / action adjoint) + the ordinary backward: loss, states and policy gradient of the oracle's rollout through
+    the learnt model (reference-pinned parameters, golden variant b), prepared AND raw inputs; the per-step loop of
+    CUDA ops (learnt step kernel under autograd) gives the same loss"""
+    import bench as B
+    from oracle import apg_oracle as O
+    PR, R, SY, T, DS = _mods()
+    g = load_golden("learnt_dyn.npz")
+    d = _learnt_module(g, "b")
+    lparams = [p.detach().cpu().clone() for _, p in d.named_parameters()]
+    cfg = dict(O.QUAD_CFG, rotational_drag=tuple(float(x) for x in g["b_rot_drag"]))
+    h, dt = 10, 0.1
+    params = B.default_init("quad", h, seed=n)
+    case = SY.quad_case(n, h, dt, seed=n)
+    want = O.value_and_grad(lambda ps: O.rollout_concurrent_learnt(ps, lparams, case["in_state"], case["cur"],
+                                                                   case["in_ref"], case["ref"], h, dt, cfg), params)
+    runner = R.Rollout(R.RolloutSpec.quad_concurrent(h, dt, modified_params=dict(d.cfg)), n, "cuda:0")
+    assert runner.tcgen05
+    flat, lflat = R.flatten_params(params).cuda(), d._flat().detach()
+    cu = {k: v.cuda() for k, v in case.items()}
+    loss, states, actions = runner.forward(flat, cu["in_state"], cu["cur"], cu["in_ref"], cu["ref"], want_states=True,
+                                           want_actions=True, learnt_params=lflat)
+    loss = loss.clone()
+    grad = runner.backward(1.0).cpu()
+    assert abs(float(loss) - float(want[0])) <= 2e-5 * abs(float(want[0]))
+    assert _close(states, want[2], 2e-5) and _close(actions, want[3], 2e-5)
+    for got, w in zip(R.split_flat(grad, params), want[1]):
+        if w is None:
+            assert float(got.abs().max()) == 0
+        else:
+            assert rel_err(got, w) <= 1e-4
+    # the un-fused form of the same rollout: h launches of the learnt step under autograd on the kernel's actions
+    s = cu["cur"]
+    sts = []
+    for k in range(h):
+        s = d(s, actions[:, k].contiguous(), dt)
+        sts.append(s)
+    from apg_trajectory_tracking_b200.neural_control.drone_loss import quad_mpc_loss
+    l2 = quad_mpc_loss(torch.stack(sts, 1), cu["ref"], actions)
+    assert abs(float(l2) - float(loss)) <= 2e-5 * abs(float(loss))
+    # raw samples (prepare_data in the kernels' prologue) through the learnt steps
+    raw = SY.quad_case(n, h, dt, seed=n + 1)
+    gen = torch.Generator().manual_seed(n)
+    raw_cur = raw["cur"].clone()
+    raw_cur[:, :3] = torch.randn(n, 3, generator=gen)
+    raw_ref = raw["ref"].clone()
+    raw_ref[:, :, :3] += raw_cur[:, None, :3]
+    prep = PR.prepare_quad(raw_cur.cuda(), raw_ref.cuda())
+    l_prep, _, _ = runner.forward(flat, prep["in_state"], prep["cur"], prep["in_ref"], prep["ref"], learnt_params=lflat)
+    l_prep = l_prep.clone()
+    g_prep = runner.backward(1.0).clone()
+    l_raw, _, _ = runner.forward(flat, None, raw_cur.cuda(), None, raw_ref.cuda(), learnt_params=lflat)
+    g_raw = runner.backward(1.0)
+    assert abs(float(l_raw) - float(l_prep)) <= 1e-5 * abs(float(l_prep))
+    assert rel_err(g_raw, g_prep) <= 1e-4
+
+
+def test_learnt_controller_epoch_fused_vs_oracle_training():
+    """TrainDrone.run_epoch with train_dynamics = LearntDynamics (golden variant b): the FUSED rollout through the learnt
+    steps + SGD, two epochs of four mini-batches, against the same training on the oracle; the un-fused per-step loop
+    (config unfused_learnt_rollout) follows the same curve"""
+    import bench as B
+    from oracle import apg_oracle as O
+    from apg_trajectory_tracking_b200.scripts.train_drone import TrainDrone
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    PR, R, SY, T, DS = _mods()
+    g = load_golden("learnt_dyn.npz")
+    n, h, dt, bs, lr = 512, 10, 0.1, 128, 1e-5
+    raw = SY.quad_case(n, h, dt, seed=4)
+    cfg = dict(delta_t=dt, horizon=h, ref_dim=9, action_dim=4, state_size=12, batch_size=bs, system="quad",
+               learning_rate_controller=lr, train_mode="concurrent", device="cuda:0")
+    curves, nets = [], []
+    for unfused in (False, True):
+        torch.manual_seed(0)
+        d = _learnt_module(g, "b")
+        tr = TrainDrone(d, FlightmareDynamics(), dict(cfg, unfused_learnt_rollout=unfused))
+        tr.initialize_model(state_data=DS.QuadDataset(raw["cur"].numpy(), raw["ref"].numpy()))
+        tr.trainloader = torch.utils.data.DataLoader(tr.state_data, batch_size=bs, shuffle=False)
+        if not unfused:
+            p0 = [p.detach().cpu().clone() for p in tr.net.parameters()]
+            assert tr.fused.supports_learnt_dynamics(bs)
+        curves.append([tr.run_epoch(epoch=e) for e in range(2)])
+        nets.append([p.detach().cpu().clone() for p in tr.net.parameters()])
+    # the oracle's training: same batches in the same order, SGD momentum 0.9 (train_base.py:139-143)
+    lparams = [p.detach().cpu().clone() for _, p in d.named_parameters()]
+    ocfg = dict(O.QUAD_CFG, rotational_drag=tuple(float(x) for x in g["b_rot_drag"]))
+    ds = DS.QuadDataset(raw["cur"].numpy(), raw["ref"].numpy())
+    ps, bufs, want_curve = [p.clone() for p in p0], [None] * len(p0), []
+    for e in range(2):
+        run = 0.0
+        for b in range(n // bs):
+            ins, cur, inr, ref = (torch.stack(x) for x in zip(*[ds[i] for i in range(b * bs, (b + 1) * bs)]))
+            loss, grads, _, _ = O.value_and_grad(
+                lambda q: O.rollout_concurrent_learnt(q, lparams, ins, cur, inr, ref, h, dt, ocfg), ps)
+            ps, bufs = O.sgd_momentum_step(ps, grads, bufs, lr)
+            run += float(loss)
+        want_curve.append(run / (n // bs - 1))                    # the reference divides by the last batch index
+    for got in curves:
+        for a, w in zip(got, want_curve):
+            assert abs(a - w) <= 1e-4 * abs(w), (curves, want_curve)
+    for a, w in zip(nets[0], ps):
+        assert rel_err(a, w) <= 1e-4
+
+
 def test_learnt_dynamics_many_tiles_vs_oracle_and_training_step():
     """N = 5000 (several 128-drone tiles per block, ragged tail) against fp32 autograd of the oracle; then three
     train_dynamics_model steps of the trainer against the same steps on the oracle"""
