@@ -58,6 +58,10 @@ EXPORTS = {
                                         ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p, c_float_p,
                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "apg_eval_rollout_lstm": (ctypes.c_int, [ctypes.POINTER(ApgConfig), c_float_p, c_float_p, c_float_p,
+                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int,
+                                             ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, c_float_p,
+                                             c_float_p, c_float_p, ctypes.c_void_p, c_float_p, ctypes.c_void_p]),
     "apg_eval_fly_to_points": (ctypes.c_int, [ctypes.POINTER(ApgConfig), c_float_p, c_float_p, ctypes.c_int, c_float_p,
                                               c_float_p, c_float_p, ctypes.c_float, ctypes.c_int, ctypes.c_float,
                                               ctypes.c_float, ctypes.c_int, ctypes.c_void_p, c_float_p, c_float_p,

@@ -663,6 +663,40 @@ __attribute__((visibility("default"))) int apg_eval_rollout(const apg_config* cf
   return 0;
 }
 
+// apg_eval_rollout for the LSTM policy (train_mode "LSTM", models/rnn.py LSTM_NEW): h0c0 [2][N][8] is every drone's
+// hidden / cell state before its first policy call, hc_out (optional) the state after its last one.
+__attribute__((visibility("default"))) int apg_eval_rollout_lstm(const apg_config* cfg, const float* params, const float* h0c0, const float* tables,
+                          const int* table_index, int n_tables, int table_rows, const float* init_states, int steps,
+                          float thresh_div, float thresh_stable, int test_time, void* workspace, float* states_out,
+                          float* div_out, float* actions_out, int* n_steps_out, float* hc_out, void* stream) {
+  int e = check_config(cfg);
+  if (e) return e;
+  if (cfg->net != NET_LSTM || cfg->system != SYS_QUAD) return APG_ERR_UNSUPPORTED;
+  if (cfg->state_feat != 15 || cfg->ref_dim != 9 || cfg->ref_len != cfg->horizon || cfg->out_dim != 4) return APG_ERR_BAD_CONFIG;
+  if (!params || !h0c0 || !tables || !init_states || !workspace) return APG_ERR_BAD_CONFIG;
+  if (n_tables < 1 || table_rows < 1 || steps < 1) return APG_ERR_BAD_CONFIG;
+  if (!table_index && n_tables < cfg->n_drones) return APG_ERR_BAD_CONFIG;
+  if (!aligned16(params) || !aligned16(h0c0) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return APG_ERR_ALIGNMENT;
+  if (sm_count() <= 0) return APG_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Plan p = make_plan(cfg, net_info(cfg));
+  char* w = static_cast<char*>(workspace);
+  float* wf = reinterpret_cast<float*>(w + p.o_wf);
+  float* wb = reinterpret_cast<float*>(w + p.o_wb);
+  const LstmLayout y = lstm_layout(cfg);
+  cudaError_t ce;
+  if ((ce = launch_pack(lstm_pack_table(y), params, wf, wb, st))) return (int)ce;
+  PhysConsts pc;
+  memcpy(pc.v, cfg->phys, sizeof(float) * MAX_PHYS);
+  EvalParams ev;
+  ev.steps = steps; ev.table_rows = table_rows; ev.test_time = test_time ? 1 : 0;
+  ev.thresh_div = thresh_div; ev.thresh_stable = thresh_stable;
+  if ((ce = launch_eval_rollout_lstm(y, wf, h0c0, tables, table_index, init_states, cfg->n_drones, cfg->dt, pc, ev,
+                                     states_out, div_out, actions_out, n_steps_out, hc_out, p.grid, st)))
+    return (int)ce;
+  return 0;
+}
+
 // Closed-loop evaluation of the fixed wing towards target points (eval_kernels.cu).
 __attribute__((visibility("default"))) int apg_eval_fly_to_points(const apg_config* cfg, const float* params, const float* targets, int n_targets,
                            const float* init_states, const float* mean_host, const float* std_host, float dt_data,

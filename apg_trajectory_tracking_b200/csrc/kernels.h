@@ -71,6 +71,10 @@ cudaError_t launch_eval_rollout(const HutterLayout& y, const float* wf, const fl
                                 float* states_out, float* div_out, float* actions_out, int* n_steps_out, int grid,
                                 cudaStream_t st);
 
+cudaError_t launch_eval_rollout_lstm(const LstmLayout& y, const float* wf, const float* h0c0, const float* tables,
+                                     const int* table_index, const float* init_states, int n, float dt,
+                                     const PhysConsts& pc, const EvalParams& ev, float* states_out, float* div_out,
+                                     float* actions_out, int* n_steps_out, float* hc_out, int grid, cudaStream_t st);
 cudaError_t launch_eval_wing(const HutterLayout& y, const float* wf, const float* targets, const float* init_states,
                              int n, float dt_env, const PhysConsts& pc, const float* mean_host, const float* std_host,
                              const WingEvalParams& ev, float* states_out, float* div_out, float* actions_out,

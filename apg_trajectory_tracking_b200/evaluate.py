@@ -20,8 +20,8 @@ class TableEvaluator:
     def __init__(self, spec: R.RolloutSpec, n_drones: int, device=None):
         if not torch.cuda.is_available():
             raise _capi.ApgError("no CUDA device: the evaluation rollout only runs on the GPU")
-        if spec.system != "quad" or spec.net != "hutter_conv":
-            raise _capi.ApgError("table evaluation is implemented for the quadrotor hutter conv nets")
+        if spec.system != "quad" or spec.net not in ("hutter_conv", "lstm"):
+            raise _capi.ApgError("table evaluation is implemented for the quadrotor hutter conv and LSTM policies")
         self.spec, self.n = spec, int(n_drones)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.lib = _capi.lib()
@@ -35,11 +35,12 @@ class TableEvaluator:
             self._ws_ptr = ctypes.c_void_p(self.workspace.data_ptr() + off)
 
     def follow(self, params_flat, tables, init_states=None, table_index=None, steps=251, thresh_div=1.0,
-               thresh_stable=1.0, test_time=0, want=("states", "div", "actions")):
+               thresh_stable=1.0, test_time=0, want=("states", "div", "actions"), h0c0=None):
         """tables (T,RL,9) rows [pos, euler, vel]; table_index (N,) int32 or None (drone i walks table i);
         init_states (N,12) or None (at rest on the first table point, like ``zero_reset(*initial_pos)``).
         Returns dict(states (N,steps+1,12), div (N,steps), actions (N,steps,4), n_steps (N,) int32); entries after a
-        drone stopped are zero."""
+        drone stopped are zero.  LSTM policy: ``h0c0`` (2,N,8) = every drone's hidden / cell state before its first
+        policy call (required), and the dict also holds ``hc`` (2,N,8), the state after its last one."""
         _require_cuda(params_flat, tables, init_states, table_index)
         tables = tables if (tables.dtype == torch.float32 and tables.is_contiguous()) else tables.contiguous().float()
         n, dev = self.n, self.device
@@ -62,6 +63,20 @@ class TableEvaluator:
         if "actions" in want:
             out["actions"] = torch.zeros(n, steps, 4, device=dev)
         opt = lambda k: None if k not in out else _p(out[k])          # noqa: E731
+        if self.spec.net == "lstm":
+            if h0c0 is None or tuple(h0c0.shape) != (2, n, 8):
+                raise ValueError("LSTM policy: h0c0 of shape (2, N, 8) is required")
+            _require_cuda(h0c0)
+            h0c0 = h0c0.contiguous().float()
+            out["hc"] = torch.zeros(2, n, 8, device=dev)
+            with torch.cuda.device(dev):
+                _capi.check(self.lib.apg_eval_rollout_lstm(
+                    ctypes.byref(self.cfg), _p(params_flat), _p(h0c0), _p(tables),
+                    None if table_index is None else _p(table_index), int(tables.shape[0]), int(tables.shape[1]),
+                    _p(init_states), int(steps), ctypes.c_float(thresh_div), ctypes.c_float(thresh_stable),
+                    int(test_time), self._ws_ptr, opt("states"), opt("div"), opt("actions"), _p(out["n_steps"]),
+                    _p(out["hc"]), _stream(tables)))
+            return out
         with torch.cuda.device(dev):
             _capi.check(self.lib.apg_eval_rollout(
                 ctypes.byref(self.cfg), _p(params_flat), _p(tables), None if table_index is None else _p(table_index),

@@ -48,8 +48,16 @@ class QuadEvaluator:
         tables = tables.to(dev, torch.float32)
         ev = EV.TableEvaluator(spec, tables.shape[0], dev)
         flat = R.flatten_params([p.detach() for p in net.parameters()]).to(dev).float().contiguous()
+        h0c0 = None
+        if spec.net == "lstm":
+            # the reference carries ONE hidden / cell state through its consecutive runs (rnn.py:45-48); here the T runs
+            # are simultaneous: each starts from the net's current state, the net keeps the last run's final state
+            hs, cs = net.hidden_state.detach().to(dev).float(), net.cell_state.detach().to(dev).float()
+            h0c0 = torch.stack((hs[:1].expand(tables.shape[0], -1), cs[:1].expand(tables.shape[0], -1))).contiguous()
         out = ev.follow(flat, tables, init_states=init_states, steps=max_nr_steps, thresh_div=thresh_div,
-                        thresh_stable=thresh_stable, test_time=self.test_time)
+                        thresh_stable=thresh_stable, test_time=self.test_time, h0c0=h0c0)
+        if h0c0 is not None:
+            net.hidden_state, net.cell_state = out["hc"][0, -1:].clone(), out["hc"][1, -1:].clone()
         self._feed_self_play(out, tables, thresh_div, thresh_stable)
         return out
 

@@ -153,6 +153,16 @@ int apg_eval_rollout(const apg_config* cfg, const float* params, const float* ta
                      float thresh_stable, int test_time, void* workspace, float* states_out, float* div_out,
                      float* actions_out, int* n_steps_out, void* stream);
 
+/* The same closed loop with the LSTM policy (train_mode "LSTM": neural_control/models/rnn.py:8-50 LSTM_NEW; the applied
+ * action is the net's 4 outputs, scripts/evaluate_drone.py:156-157).  cfg: quadrotor, APG_NET_LSTM, out_dim 4.
+ * h0c0 [2][N][8] (device): hidden / cell state of every drone before its first policy call (the reference draws one
+ * with torch.randn when the evaluator is constructed, evaluate_drone.py:55-57, and carries it through runs and drone
+ * resets); hc_out [2][N][8] (optional): the state after the drone's last policy call. */
+int apg_eval_rollout_lstm(const apg_config* cfg, const float* params, const float* h0c0, const float* tables,
+                          const int* table_index, int n_tables, int table_rows, const float* init_states, int steps,
+                          float thresh_div, float thresh_stable, int test_time, void* workspace, float* states_out,
+                          float* div_out, float* actions_out, int* n_steps_out, float* hc_out, void* stream);
+
 /* Fixed wing: FixedWingEvaluator.fly_to_point (scripts/evaluate_fixed_wing.py:46-130) with
  * FixedWingNetWrapper.predict_actions (controllers/network_wrapper.py:81-98), WingDataset.prepare_data,
  * SimpleWingEnv.step (environments/wing_env.py:44-58) and project_to_line (trajectory/q_funcs.py:6-18) for

@@ -454,8 +454,13 @@ def eval_window(tables, ci, h):
 
 
 def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0, thresh_stable=1.0, test_time=0,
-                       cfg=QUAD_CFG, record_policy_inputs=False):
+                       cfg=QUAD_CFG, record_policy_inputs=False, hc0=None):
     """Batched restatement of QuadEvaluator.follow_trajectory("rand").
+
+    hc0 = (h0 (N,8), c0 (N,8)): `params` are those of the LSTM policy (models/rnn.py LSTM_NEW, 10 tensors); every
+    policy call advances the drone's hidden / cell state (rnn.py:45-48) - resets of the drone do not touch it, the
+    reference only re-draws it when an evaluator is constructed (evaluate_drone.py:55-57).  The final state is
+    returned as out["hc"].
 
     params: hutter Net(15,h,9,4h) (concurrent: the first of the h predicted actions is applied,
     evaluate_drone.py:154-155) or Net(15,h,9,4); tables (N,RL,9) reference rows [pos, euler, vel] as
@@ -475,7 +480,8 @@ def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0
     states[:, 0] = s
     divs, actions = torch.zeros(n, steps), torch.zeros(n, steps, 4)
     n_steps = torch.zeros(n, dtype=torch.long)
-    out_dim = params[-1].shape[0]
+    out_dim = params[-1].shape[0] if hc0 is None else 4
+    hc = None if hc0 is None else (hc0[0].float().clone(), hc0[1].float().clone())
     pol_states, windows = torch.zeros(n, steps, 12), torch.zeros(n, steps, h, 9)
     for i in range(steps):
         if not bool(alive.any()):
@@ -490,7 +496,12 @@ def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0
         cur[:, :3] = 0
         in_ref = torch.cat((rel[:, :, :3], rel[:, :, 6:9], rel[:, :, 6:9] - cur[:, None, 6:9]), dim=2)
         with torch.no_grad():
-            act = torch.sigmoid(hutter_forward(params, state_preprocessing(cur), in_ref))
+            if hc0 is None:
+                act = torch.sigmoid(hutter_forward(params, state_preprocessing(cur), in_ref))
+            else:
+                logits, (h_new, c_new) = lstm_forward(params, state_preprocessing(cur), in_ref, hc)
+                hc = (torch.where(alive[:, None], h_new, hc[0]), torch.where(alive[:, None], c_new, hc[1]))
+                act = torch.sigmoid(logits)
         a0 = (act.reshape(n, h, 4)[:, 0] if out_dim == 4 * h else act).clamp(0.0, 1.0)
         nxt = quad_step(s.double(), a0.double(), dt, cfg).float()
         stable = (nxt[:, 3:5].abs() < thresh_stable).all(dim=1)           # drone_env.py:66-74
@@ -509,6 +520,8 @@ def eval_follow_tables(params, tables, init_states, steps, h, dt, thresh_div=1.0
             s = torch.where((alive & bad)[:, None], reset_state, torch.where(alive[:, None], nxt, s))
         alive = alive & (i < rl)                                          # evaluate_drone.py:187-188
     out = dict(states=states, div=divs, actions=actions, n_steps=n_steps)
+    if hc is not None:
+        out["hc"] = hc
     if record_policy_inputs:
         out.update(policy_states=pol_states, windows=windows)
     return out

@@ -112,6 +112,66 @@ def make_eval_golden(args):
     np.savez_compressed(os.path.join(args.out, "eval_rand.npz"), **out)
 
 
+def make_eval_lstm_golden(args):
+    """eval_rand_lstm.npz: QuadEvaluator.follow_trajectory("rand") of the unmodified reference with an LSTM_NEW policy
+    (models/rnn.py; seeded default init - the reference ships no trained LSTM), train_mode="LSTM": the applied action is
+    the net's 4 outputs, the hidden / cell state drawn at evaluator construction (evaluate_drone.py:55-57) is carried
+    through the run.  Same trajectory-file substitution as make_eval_golden."""
+    import torch
+    cwd = os.getcwd()
+    os.chdir(args.ref)
+    _np_random = lambda seed=None: (np.random.RandomState(0), 0)
+    sys.modules['gym.utils'].seeding.np_random = _np_random
+    sys.modules['gym'].utils.seeding.np_random = _np_random
+    import neural_control.trajectory.random_traj as RT
+    import evaluate_drone as ED
+    from neural_control.environments.drone_env import QuadRotorEnvBase
+    from neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    from neural_control.controllers.network_wrapper import NetworkWrapper
+    from neural_control.dataset import QuadDataset
+    from neural_control.models.rnn import LSTM_NEW
+    h, dt = 10, 0.1
+    torch.manual_seed(7)
+    net = LSTM_NEW(15, h, 9, 4)
+    with torch.no_grad():
+        net.fc_out.bias += torch.tensor([0.3, 0.0, 0.0, 0.0])   # hover-ish thrust so that runs last a few steps
+    net.eval()
+    ds = QuadDataset.__new__(QuadDataset)
+    ds.get_and_add_eval_data = lambda st, rf, add_to_dataset=False: QuadDataset.prepare_data(ds, st, rf)
+    out = {}
+    for i, (_, p) in enumerate(net.named_parameters()):
+        out[f"param_{i}"] = p.detach().numpy().copy()
+    out["param_names"] = np.array([n for n, _ in net.named_parameters()])
+    runs = [("gentle", 1, 120, 0.25, 60, 0, 1.0, 1.0), ("fast_stop", 2, 120, 1.0, 60, 1, 1.0, 1.0),
+            ("loose", 4, 100, 0.6, 50, 0, 3.0, 0.4)]
+    for name, seed, rows, speed, steps, test_time, tdiv, tstab in runs:
+        table = eval_table(seed, rows, dt, speed)
+        RT.load_prepare_trajectory = lambda base_dir, dt_, speed_factor, test=False, _t=table: _t.copy()
+        env = QuadRotorEnvBase(FlightmareDynamics(), dt)
+        ctrl = NetworkWrapper(net, ds, horizon=h, dt=dt)
+        torch.manual_seed(100 + seed)
+        ev = ED.QuadEvaluator(ctrl, env, ref_length=h, dt=dt, test_time=test_time, speed_factor=0.4,
+                              train_mode="LSTM")
+        out[f"{name}_h0"] = net.hidden_state.detach().numpy().copy()
+        out[f"{name}_c0"] = net.cell_state.detach().numpy().copy()
+        ref_traj, drone_traj, div, acts = ev.follow_trajectory("rand", max_nr_steps=steps, thresh_stable=tstab,
+                                                               thresh_div=tdiv)
+        tab = table.copy()
+        tab[:, 2] += 3
+        out[f"{name}_table"] = tab
+        out[f"{name}_cfg"] = np.array([steps, test_time, tdiv, tstab, h, dt], dtype=np.float64)
+        out[f"{name}_states"] = np.asarray(drone_traj)
+        out[f"{name}_div"] = np.asarray(div)
+        out[f"{name}_actions"] = np.asarray(acts)                # train_mode LSTM: the action IS the output (:156-157)
+        out[f"{name}_h1"] = net.hidden_state.detach().numpy().copy()
+        out[f"{name}_c1"] = net.cell_state.detach().numpy().copy()
+        print("eval lstm", name, "steps taken", len(div), "mean div %.4f" % np.mean(div), "resets/stops",
+              int(np.sum(np.asarray(div) > tdiv)))
+    out["run_names"] = np.array([r[0] for r in runs])
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(args.out, "eval_rand_lstm.npz"), **out)
+
+
 def make_selfplay_golden(args):
     """eval_selfplay.npz: the self-play feed of the evaluation (NetworkWrapper.predict_actions,
     controllers/network_wrapper.py:42-52 -> DroneDataset.get_and_add_eval_data, dataset.py:98-119).  ONE controller
@@ -521,6 +581,7 @@ def main():
     ap.add_argument("--only-wing-eval", action="store_true", help="only (re)generate eval_wing.npz")
     ap.add_argument("--only-cartpole-eval", action="store_true", help="only (re)generate eval_cartpole.npz")
     ap.add_argument("--only-selfplay", action="store_true", help="only (re)generate eval_selfplay.npz")
+    ap.add_argument("--only-eval-lstm", action="store_true", help="only (re)generate eval_rand_lstm.npz")
     ap.add_argument("--only-wing-selfplay", action="store_true", help="only (re)generate eval_wing_selfplay.npz")
     ap.add_argument("--only-ref-table", action="store_true", help="only (re)generate ref_table.npz")
     ap.add_argument("--only-poly-traj", action="store_true", help="only (re)generate poly_traj.npz")
@@ -533,6 +594,9 @@ def main():
         return
     if args.only_learnt:
         make_learnt_golden(args)
+        return
+    if args.only_eval_lstm:
+        make_eval_lstm_golden(args)
         return
     if args.only_wing_eval:
         make_wing_eval_golden(args)

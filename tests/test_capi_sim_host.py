@@ -243,6 +243,66 @@ def test_evaluation_entry_points_through_the_c_abi(simlib):
     assert np.abs(cout["states"][0, :7].numpy() - gc["falls_states"]).max() <= 2e-5
 
 
+def test_evaluation_with_the_lstm_policy_through_the_c_abi(simlib):
+    """apg_eval_rollout_lstm (eval_rollout_lstm_kernel): the reference evaluator's runs with an LSTM_NEW policy
+    (tests/golden/eval_rand_lstm.npz: states, divergences, actions, final hidden / cell state), one drone per run in
+    ONE launch where the tables have one length; then a ragged batch against the oracle"""
+    g = load_golden("eval_rand_lstm.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    flat = R.flatten_params(params)
+    spec = R.RolloutSpec.quad_recurrent("lstm", 10, 0.1)
+    for name in ("gentle", "fast_stop", "loose"):
+        steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
+        steps = min(int(steps), 25)                      # (the CPU model runs one OS thread per GPU thread)
+        taken = min(len(g[f"{name}_div"]), steps)
+        ev = EV.TableEvaluator(spec, 1, "cpu")
+        h0c0 = torch.tensor(np.stack([g[f"{name}_h0"], g[f"{name}_c0"]]))
+        out = ev.follow(flat, torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None],
+                        init_states=torch.tensor(g[f"{name}_states"][:1], dtype=torch.float32), steps=steps,
+                        thresh_div=tdiv, thresh_stable=tstab, test_time=int(test_time), h0c0=h0c0)
+        assert int(out["n_steps"][0]) == taken
+        assert np.abs(out["states"][0, :taken + 1].numpy() - g[f"{name}_states"][:taken + 1]).max() <= 1e-4
+        assert np.abs(out["div"][0, :taken].numpy() - g[f"{name}_div"][:taken]).max() <= 1e-4
+        assert np.abs(out["actions"][0, :taken].numpy() - g[f"{name}_actions"][:taken]).max() <= 1e-4
+        if taken == len(g[f"{name}_div"]):
+            assert np.abs(out["hc"][0, 0].numpy() - g[f"{name}_h1"][0]).max() <= 1e-4
+            assert np.abs(out["hc"][1, 0].numpy() - g[f"{name}_c1"][0]).max() <= 1e-4
+    n, steps = 70, 8                                     # two tiles, the second ragged; shared tables through the index
+    tabs = torch.tensor(np.stack([g["gentle_table"][:100], g["loose_table"][:100]]), dtype=torch.float32)
+    gen = torch.Generator().manual_seed(5)
+    index = torch.randint(0, 2, (n,), generator=gen, dtype=torch.int32)
+    init = torch.zeros(n, 12)
+    init[:, :3] = tabs[index.long(), 0, :3] + 0.05 * torch.randn(n, 3, generator=gen)
+    hc0 = torch.randn(2, n, 8, generator=gen)
+    want = O.eval_follow_tables(params, tabs[index.long()], init, steps, 10, 0.1, 0.5, 0.4, 1, hc0=(hc0[0], hc0[1]))
+    out = EV.TableEvaluator(spec, n, "cpu").follow(flat, tabs, init_states=init, table_index=index, steps=steps,
+                                                   thresh_div=0.5, thresh_stable=0.4, test_time=1, h0c0=hc0)
+    assert torch.equal(out["n_steps"], want["n_steps"].to(torch.int32))
+    assert float((out["states"] - want["states"]).abs().max()) <= 1e-4
+    assert float((out["hc"][0] - want["hc"][0]).abs().max()) <= 1e-4
+    assert float((out["hc"][1] - want["hc"][1]).abs().max()) <= 1e-4
+    with pytest.raises(ValueError):
+        EV.TableEvaluator(spec, n, "cpu").follow(flat, tabs, init_states=init, table_index=index, steps=steps)
+    # the evaluator mirror with an LSTM net: starts every run from the net's state, leaves the last run's state in it
+    import types
+    from apg_trajectory_tracking_b200.scripts import evaluate_drone as ED
+    from apg_trajectory_tracking_b200.neural_control.dynamics.quad_dynamics_flightmare import FlightmareDynamics
+    net = rnn.LSTM_NEW(15, 10, 9, 4)
+    with torch.no_grad():
+        for p_, q in zip(net.parameters(), params):
+            p_.copy_(q)
+    ctrl = types.SimpleNamespace(net=net, action_counter=0)
+    env = types.SimpleNamespace(dynamics=FlightmareDynamics(), dt=0.1)
+    qe = ED.QuadEvaluator(ctrl, env, ref_length=10, dt=0.1, speed_factor=0.4, train_mode="LSTM")
+    net.hidden_state, net.cell_state = torch.tensor(g["gentle_h0"]), torch.tensor(g["gentle_c0"])
+    two = torch.tensor(np.stack([g["gentle_table"][:100], g["gentle_table"][:100]]), dtype=torch.float32)
+    res = qe.follow_tables(two, max_nr_steps=6, thresh_stable=1.0, thresh_div=1.0,
+                           init_states=torch.tensor(np.repeat(g["gentle_states"][:1], 2, 0), dtype=torch.float32))
+    assert np.abs(res["states"][1, :7].numpy() - g["gentle_states"][:7]).max() <= 1e-4
+    assert torch.equal(res["states"][0], res["states"][1]) and ctrl.action_counter == 12
+    assert torch.equal(net.hidden_state, res["hc"][0, -1:]) and tuple(net.cell_state.shape) == (1, 8)
+
+
 def test_input_side_and_learnt_entry_points_through_the_c_abi(simlib):
     g = load_golden("prep_data.npz")
     out = PR.prepare_quad(torch.tensor(g["quad_raw_states"]), torch.tensor(g["quad_raw_refs"]))

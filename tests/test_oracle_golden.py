@@ -211,6 +211,27 @@ def test_eval_follow_tables_matches_reference_evaluator(name):
     assert float(out["states"][0, taken + 1:].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("name", ["gentle", "fast_stop", "loose"])
+def test_eval_follow_tables_lstm_policy_matches_reference_evaluator(name):
+    """train_mode "LSTM": LSTM_NEW policy whose hidden / cell state is carried through the run (and through resets)"""
+    g = load_golden("eval_rand_lstm.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
+    steps, test_time, h = int(steps), int(test_time), int(h)
+    table = torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None]
+    ref_states = g[f"{name}_states"]
+    init = torch.tensor(ref_states[0], dtype=torch.float32)[None]
+    hc0 = (torch.tensor(g[f"{name}_h0"]), torch.tensor(g[f"{name}_c0"]))
+    out = O.eval_follow_tables(params, table, init, steps, h, dt, tdiv, tstab, test_time, hc0=hc0)
+    taken = len(g[f"{name}_div"])
+    assert int(out["n_steps"][0]) == taken
+    assert np.abs(out["states"][0, :taken + 1].numpy() - ref_states).max() <= 2e-5
+    assert np.abs(out["div"][0, :taken].numpy() - g[f"{name}_div"]).max() <= 2e-5
+    assert np.abs(out["actions"][0, :taken].numpy() - g[f"{name}_actions"]).max() <= 2e-5
+    assert np.abs(out["hc"][0].numpy() - g[f"{name}_h1"]).max() <= 2e-5
+    assert np.abs(out["hc"][1].numpy() - g[f"{name}_c1"]).max() <= 2e-5
+
+
 def test_eval_follow_tables_is_batched_consistently():
     """N drones at once == the same drones one by one (different tables, thresholds hit at different steps)"""
     g, names = _eval_runs()

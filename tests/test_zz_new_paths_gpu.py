@@ -333,6 +333,61 @@ def test_eval_rollout_batched_vs_oracle(mode, n):
         assert len(stats) == 6 and np.isfinite(stats[4])
 
 
+@pytest.mark.parametrize("name", ["gentle", "fast_stop", "loose"])
+def test_eval_rollout_lstm_policy_matches_reference_evaluator(name):
+    """apg_eval_rollout_lstm against QuadEvaluator.follow_trajectory("rand") of the reference with an LSTM_NEW policy
+    (train_mode "LSTM"): states, divergences, applied actions and the hidden / cell state the net is left with"""
+    EV, R, O, golden_params = _eval_mods()
+    g = load_golden("eval_rand_lstm.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
+    steps, test_time, h = int(steps), int(test_time), int(h)
+    ev = EV.TableEvaluator(R.RolloutSpec.quad_recurrent("lstm", h, dt), 1, "cuda:0")
+    h0c0 = torch.tensor(np.stack([g[f"{name}_h0"], g[f"{name}_c0"]])).cuda()
+    out = ev.follow(R.flatten_params(params).cuda(), torch.tensor(g[f"{name}_table"], dtype=torch.float32)[None].cuda(),
+                    init_states=torch.tensor(g[f"{name}_states"][:1], dtype=torch.float32).cuda(), steps=steps,
+                    thresh_div=tdiv, thresh_stable=tstab, test_time=test_time, h0c0=h0c0)
+    taken = len(g[f"{name}_div"])
+    assert int(out["n_steps"][0]) == taken
+    assert np.abs(out["states"][0, :taken + 1].cpu().numpy() - g[f"{name}_states"]).max() <= 1e-4
+    assert np.abs(out["div"][0, :taken].cpu().numpy() - g[f"{name}_div"]).max() <= 1e-4
+    assert np.abs(out["actions"][0, :taken].cpu().numpy() - g[f"{name}_actions"]).max() <= 1e-4
+    assert np.abs(out["hc"][0, 0].cpu().numpy() - g[f"{name}_h1"][0]).max() <= 1e-4
+    assert np.abs(out["hc"][1, 0].cpu().numpy() - g[f"{name}_c1"][0]).max() <= 1e-4
+    assert float(out["states"][0, taken + 1:].abs().sum()) == 0.0
+
+
+def test_eval_rollout_lstm_policy_batched_vs_oracle():
+    """many drones with their own hidden states (partial tiles, several tiles per CTA), shared tables"""
+    EV, R, O, golden_params = _eval_mods()
+    g = load_golden("eval_rand_lstm.npz")
+    params = [torch.tensor(g[f"param_{i}"]) for i in range(10)]
+    h, dt, steps, n = 10, 0.1, 40, 333
+    spec = R.RolloutSpec.quad_recurrent("lstm", h, dt)
+    tabs = torch.tensor(np.stack([g["gentle_table"][:100], g["loose_table"][:100], g["fast_stop_table"][:100]]),
+                        dtype=torch.float32)
+    gen = torch.Generator().manual_seed(n)
+    index = torch.randint(0, 3, (n,), generator=gen, dtype=torch.int32)
+    init = torch.zeros(n, 12)
+    init[:, :3] = tabs[index.long(), 0, :3] + 0.05 * torch.randn(n, 3, generator=gen)
+    init[:, 6:9] = 0.1 * torch.randn(n, 3, generator=gen)
+    hc0 = torch.randn(2, n, 8, generator=gen)
+    for test_time in (0, 1):
+        want = O.eval_follow_tables(params, tabs[index.long()], init, steps, h, dt, 0.5, 0.4, test_time,
+                                    hc0=(hc0[0], hc0[1]))
+        out = EV.TableEvaluator(spec, n, "cuda:0").follow(
+            R.flatten_params(params).cuda(), tabs.cuda(), init_states=init.cuda(), table_index=index.cuda(), steps=steps,
+            thresh_div=0.5, thresh_stable=0.4, test_time=test_time, h0c0=hc0.cuda())
+        same = (out["n_steps"].cpu() == want["n_steps"].to(torch.int32))
+        assert float(same.float().mean()) >= 0.98
+        d = (out["states"].cpu() - want["states"]).abs().amax(dim=(1, 2))
+        assert float((d[same] <= 2e-3).float().mean()) >= 0.98
+        k = int(want["n_steps"].min().clamp(max=5))
+        assert float((out["states"].cpu()[:, :k + 1] - want["states"][:, :k + 1]).abs().max()) <= 1e-4
+        dh = (out["hc"][0].cpu() - want["hc"][0]).abs().amax(dim=1)
+        assert float((dh[same] <= 2e-3).float().mean()) >= 0.98
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # N3: learnt residual quadrotor dynamics (csrc/learnt_kernels.cu) vs the reference's LearntDynamics and the oracle
 # ---------------------------------------------------------------------------------------------------------------
