@@ -236,7 +236,58 @@ class FusedTrainStep:
         ev.record(torch.cuda.current_stream(self.device))
         return HostLoss(host, ev)
 
-    def value_and_grad_host(self, cur, ref=None, h0c0=None, target=None, norm=None, chunk=None, allreduce=True):
+    def capture_host(self, cur, ref=None, h0c0=None, target=None, norm=None, chunk=None, warmup=2):
+        """Capture ``step_host`` on the given PINNED host tensors into ONE CUDA graph: the chunked H2D copies (a parallel
+        branch of the graph that runs ahead of the kernels), prepare / forward / adjoint of every chunk, the SGD update
+        and the D2H copy of the loss into a pinned scalar.  Eagerly, every chunk costs ~15 CUDA calls issued from
+        Python; beyond two chunks that CPU time, not PCIe or the kernels, sets the step time - captured, a step is one
+        launch and the batch can be cut finely enough that little is left to compute once the last copy has landed.
+        ``replay_host()`` reruns it on whatever the host tensors hold THEN and returns a ``HostLoss``."""
+        if self.distributed:
+            raise _capi.ApgError("capture_host() is single-process (the gradient all-reduce is not captured)")
+        host = [x for x in (cur, ref, h0c0, target) if x is not None]
+        if not all(x.is_pinned() for x in host):
+            raise _capi.ApgError("capture_host(): the host tensors must be pinned (asynchronous copies inside a graph)")
+        kw = dict(cur=cur, ref=ref, h0c0=h0c0, target=target, norm=norm, chunk=chunk)
+        self._graph_state(int(cur.shape[0]))
+        main = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # per-chunk runners / workspaces are created here, not in capture
+                self._host_step_body(kw, graph=True)
+        main.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._host_step_body(kw, graph=True)
+        self._hgraph, self._hgraph_keep = g, kw
+        return self
+
+    def _graph_state(self, n):
+        st = self._host_state(n)
+        if "graph_set" not in st:
+            st["graph_set"] = self._staging(n)
+            st["graph_loss_host"] = torch.empty(1, pin_memory=torch.cuda.is_available())
+        return st
+
+    def _host_step_body(self, kw, graph):
+        st = self._hs
+        loss, grad = self.value_and_grad_host(kw["cur"], kw["ref"], kw["h0c0"], kw["target"], kw["norm"], kw["chunk"],
+                                              _graph=graph)
+        self.buf.mul_(self.momentum).add_(grad)
+        self.flat.add_(self.buf, alpha=-self.lr)
+        st["graph_loss_host"].copy_(loss, non_blocking=True)
+
+    def replay_host(self):
+        """one captured ``step_host`` (see ``capture_host``); returns a ``HostLoss`` (``item()`` waits for the step)"""
+        self._hgraph.replay()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return HostLoss(self._hs["graph_loss_host"], ev)
+
+    def value_and_grad_host(self, cur, ref=None, h0c0=None, target=None, norm=None, chunk=None, allreduce=True,
+                            _graph=False):
         """Loss and flat gradient from RAW host samples (pinned memory for asynchronous copies).
 
         quad: ``cur`` (N,12), ``ref`` (N,L,9) raw reference rows (L = h concurrent, 2h recurrent) [+ ``h0c0`` (2,N,8)];
@@ -248,15 +299,21 @@ class FusedTrainStep:
         spec = self.runner.spec
         n = int(cur.shape[0])
         st = self._host_state(n)
-        sg = st["sets"][st["turn"]]
-        st["turn"] ^= 1
         compute = torch.cuda.current_stream(self.device)
         copy = st["copy_stream"]
-        if sg["done"] is None:
-            # first use: freshly allocated staging memory may be a recycled block with compute-stream work in flight
+        if _graph:
+            # inside (or warming up for) a stream capture: a staging set of its own, the copy stream forks off the
+            # capturing stream here and joins it again below; consecutive replays are ordered by the launching stream
+            sg = st["graph_set"]
             copy.wait_stream(compute)
         else:
-            copy.wait_event(sg["done"])          # the step that last used this set (two calls ago) has finished
+            sg = st["sets"][st["turn"]]
+            st["turn"] ^= 1
+            if sg["done"] is None:
+                # first use: freshly allocated staging memory may be a recycled block with compute-stream work in flight
+                copy.wait_stream(compute)
+            else:
+                copy.wait_event(sg["done"])          # the step that last used this set (two calls ago) has finished
         bounds = chunk_bounds(n, chunk if chunk is not None else self.default_chunk())
         if spec.system == "wing":
             mean, std = norm if norm is not None else (_syn.WING_MEAN, _syn.WING_STD)
@@ -311,8 +368,11 @@ class FusedTrainStep:
                 st["loss"].add_(loss)
         if self.distributed and allreduce:
             torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-        sg["done"] = torch.cuda.Event()
-        sg["done"].record(compute)
+        if _graph:
+            compute.wait_stream(copy)            # join (every copy is already ordered before its chunk's kernels)
+        else:
+            sg["done"] = torch.cuda.Event()
+            sg["done"].record(compute)
         # launches of this package's kernels: per chunk the rollout's 5 + the prepare kernels (quad / wing: 2)
         raw_mode = spec.system == "quad" and spec.mode == "concurrent" and getattr(self.runner, "tcgen05", False)
         self.host_launches_per_step = len(bounds) * (self.kernel_launches_per_step +

@@ -320,15 +320,53 @@ def measure_e2e_raw(stepper, w, host, case, e2e_steps, world, dev, barrier):
     barrier()
     t_async = agree((time.perf_counter() - t0) / e2e_steps, "MAX")
     t = t_sync                          # headline: every step's loss is read before the next step is issued
-    return {"ok": True, "value": world * n * h / t, "unit": "drone-steps/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": 4, "steps": e2e_steps, "chunk": chunk if chunk else n,
-            "chunk_candidates_ms": {str(c if c else n): round(v * 1e3, 4) for c, v in times.items()}, "check": check,
-            "value_loss_read_every_step": world * n * h / t_sync,
-            "value_loss_read_one_step_late": world * n * h / t_async,
-            "api": "apg_trajectory_tracking_b200.train.FusedTrainStep.step_host / step_host_async(raw host samples): "
-                   "chunked H2D on a copy stream overlapped with prepare + forward + adjoint of the previous chunk; "
-                   "value = loss read on the host after EVERY step (value_loss_read_one_step_late: the pipelined "
-                   "variant, reported next to it)"}
+    api = ("apg_trajectory_tracking_b200.train.FusedTrainStep.step_host / step_host_async(raw host samples): "
+           "chunked H2D on a copy stream overlapped with prepare + forward + adjoint of the previous chunk; "
+           "value = loss read on the host after EVERY step (value_loss_read_one_step_late: the pipelined "
+           "variant, reported next to it)")
+    extra = {}
+    if world == 1 and torch.device(dev).type == "cuda":
+        # The same step as ONE CUDA-graph launch (FusedTrainStep.capture_host / replay_host): eagerly every chunk costs
+        # ~15 CUDA calls issued from Python and beyond two chunks that CPU time sets the step time; captured, the batch
+        # can be cut finely and little is left to compute after the last copy has landed.  Every replay still copies the
+        # step's inputs from the pinned host tensors and the loss is read on the host before the next replay.
+        try:
+            gtimes = {}
+            for c in [c for c in (2 * wave, wave, wave // 2, wave // 4) if 0 < c < n]:
+                stepper.capture_host(chunk=c, warmup=1, **kw)
+                for _ in range(2):
+                    stepper.replay_host().item()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    stepper.replay_host().item()
+                gtimes[c] = (time.perf_counter() - t0) / 3
+            if gtimes:
+                gchunk = min(gtimes, key=gtimes.get)
+                stepper.capture_host(chunk=gchunk, warmup=1, **kw)
+                stepper.replay_host().item()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    stepper.replay_host().item()
+                t_graph = (time.perf_counter() - t0) / e2e_steps
+                extra = {"value_eager_step_host": world * n * h / t_sync, "value_graph_replay_host": world * n * h / t_graph,
+                         "graph_chunk": gchunk,
+                         "graph_chunk_candidates_ms": {str(c): round(v * 1e3, 4) for c, v in gtimes.items()}}
+                if t_graph < t:
+                    t = t_graph
+                    api = ("apg_trajectory_tracking_b200.train.FusedTrainStep.capture_host / replay_host(raw pinned host "
+                           "samples): one CUDA-graph launch per step = chunked H2D (parallel branch) + forward + adjoint "
+                           "per chunk + SGD + D2H of the loss; value = loss read on the host after EVERY step "
+                           "(value_eager_step_host: the same step issued call by call)")
+        except Exception as ex:                                   # noqa: BLE001
+            extra = {"graph_error": f"{type(ex).__name__}: {ex}"[:300]}
+    out = {"ok": True, "value": world * n * h / t, "unit": "drone-steps/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "steps": e2e_steps, "chunk": chunk if chunk else n,
+           "chunk_candidates_ms": {str(c if c else n): round(v * 1e3, 4) for c, v in times.items()}, "check": check,
+           "value_loss_read_every_step": world * n * h / t,
+           "value_loss_read_one_step_late": world * n * h / t_async,
+           "api": api}
+    out.update(extra)
+    return out
 
 
 def physical_cores():
@@ -697,7 +735,9 @@ def main():
                 line["e2e"] = {k: e2e_raw[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step",
                                                         "steps", "api", "chunk", "chunk_candidates_ms", "check",
                                                         "value_loss_read_every_step",
-                                                        "value_loss_read_one_step_late")}
+                                                        "value_loss_read_one_step_late", "value_eager_step_host",
+                                                        "value_graph_replay_host", "graph_chunk",
+                                                        "graph_chunk_candidates_ms", "graph_error") if k in e2e_raw}
             else:
                 line["e2e_raw_samples"] = e2e_raw
         if cpu_baseline is not None:

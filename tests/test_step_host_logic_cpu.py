@@ -186,3 +186,23 @@ def test_step_host_async_equals_step_host(cpu_doubles):
     lb.append(prev.item())
     assert la == lb and torch.equal(a.flat, b.flat)
     assert b._hs["sets"][0]["done"].recorded and b._hs["sets"][1]["done"].recorded
+
+
+def test_captured_host_step_body_equals_step_host(cpu_doubles):
+    """the body capture_host records (graph mode of value_and_grad_host: its own staging set, copy stream forked off and
+    joined to the capturing stream, SGD update, loss into the pinned scalar) trains exactly like step_host"""
+    n, h = 200, 10
+    w = dict(B.WORKLOADS["quad_concurrent"], n=n)
+    case = B.make_case(w, n, 9, "cpu")
+    params = B.default_init("quad", h, seed=2)
+    a = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cpu", distributed=False)
+    b = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cpu", distributed=False)
+    kw = dict(cur=case["cur"], ref=case["ref"], h0c0=None, target=None, norm=None, chunk=64)
+    st = b._graph_state(n)
+    la, lb = [], []
+    for _ in range(3):
+        la.append(float(a.step_host(case["cur"], ref=case["ref"], chunk=64)))
+        b._host_step_body(kw, graph=True)
+        lb.append(float(st["graph_loss_host"][0]))
+    assert la == lb and torch.equal(a.flat, b.flat)
+    assert st["sets"][0]["done"] is None and st["sets"][1]["done"] is None     # the eager staging sets stay untouched

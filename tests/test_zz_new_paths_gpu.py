@@ -179,6 +179,36 @@ def test_step_host_async_overlapped_steps_equal_step_host():
     assert torch.equal(a.flat, b.flat)
 
 
+@pytest.mark.parametrize("name", ["quad", "wing"])
+def test_step_host_captured_graph_equals_eager_step_host(name):
+    """capture_host / replay_host: one CUDA-graph launch per step (chunked H2D branch + kernels + SGD + loss D2H) ==
+    the eager step_host on the same chunk schedule, with NEW data written into the same pinned tensors every step"""
+    import bench as B
+    PR, R, SY, T, DS = _mods()
+    c = CASES[name]
+    h, dt, n = c["h"], c["dt"], 1000
+    w = dict(system=name, mode="concurrent", h=h, dt=dt)
+    params = B.default_init(name, h, seed=3)
+    a = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cuda:0", distributed=False)
+    b = T.FusedTrainStep(params, B.make_spec(w), n, lr=1e-4, device="cuda:0", distributed=False)
+    batches = [B.make_case(w, n, 60 + i, "cpu") for i in range(5)]
+    pin = {k: v.clone().pin_memory() for k, v in batches[0].items() if k in ("cur", "ref", "target")}
+    kw = dict(ref=pin.get("ref") if name == "quad" else None, target=pin.get("target"), chunk=192)
+    b.capture_host(pin["cur"], warmup=2, **kw)          # 2 warm-up steps + the captured one do not count: replays do
+    for _ in range(2):
+        a.step_host(pin["cur"], **kw)
+    la, lb = [], []
+    for case in batches:
+        for k in pin:
+            pin[k].copy_(case[k])
+        la.append(float(a.step_host(pin["cur"], **kw).item()))
+        lb.append(b.replay_host().item())
+    assert la == lb, (la, lb)
+    assert torch.equal(a.flat, b.flat)
+    with pytest.raises(Exception):
+        b.capture_host(batches[0]["cur"], ref=batches[0].get("ref"), target=batches[0].get("target"))   # not pinned
+
+
 def test_step_host_accepts_absolute_positions():
     """truly raw quad samples (drone not at the origin): the device prepare makes them relative like the dataset"""
     import bench as B
