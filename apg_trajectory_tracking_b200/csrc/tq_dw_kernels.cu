@@ -129,7 +129,19 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
 #endif
   const int n = g.N;
   const int ntiles = (n + tc::TMT - 1) / tc::TMT;
-  const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // The drone axis is the K dimension of this GEMM, so the work splits at PANEL granularity (32 drones), not by tile:
+  // CTA b takes the contiguous items [i0, i1) of the ntiles * NPANEL (tile, panel) pairs - 2048 panels over 148 CTAs
+  // are 13 or 14 each (99 % balanced) where 512 whole tiles were 3 or 4 (86 %).  Its first and last tile may be partial:
+  // tile t0 + j contributes the panels [p_lo(j), p_hi(j)).  Every role below walks (tile, op, panel) in this order.
+  const int n_items = ntiles * tq::NPANEL;
+  const int i0 = (int)(((long long)blockIdx.x * n_items) / (int)gridDim.x);
+  const int i1 = (int)(((long long)(blockIdx.x + 1) * n_items) / (int)gridDim.x);
+  const int t0 = i0 / tq::NPANEL;
+  const int my_tiles = i1 > i0 ? (i1 - 1) / tq::NPANEL - t0 + 1 : 0;
+  // first panel of the first tile | (end panel of the last tile) << 4, in one register (the feeder warps are at 96)
+  const int p_ends = (i0 - t0 * tq::NPANEL) | ((i1 - (t0 + my_tiles - 1) * tq::NPANEL) << 4);
+  auto p_lo = [&](int j) { return j == 0 ? (p_ends & 15) : 0; };
+  auto p_hi = [&](int j) { return j == my_tiles - 1 ? (p_ends >> 4) : tq::NPANEL; };
   float* P = g.grad_partials + (size_t)blockIdx.x * y.n_params;
   volatile int* abort_flag = &s_abort;
   unsigned char* lo_base = base + tq::DW_RAW_BYTES;
@@ -227,13 +239,13 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       // must have read its operands before the first copy of this one lands.  (The bubble overlaps the flush.)
       if (pass > 0 && my_tiles > 0) dwq_wait(smem_u32(&s_bars.done[pass - 1]), 0, abort_flag);
       for (int j = 0; j < my_tiles; ++j) {
-        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+        const int tile = t0 + j;
         const unsigned char* fb = fstash + (size_t)tile * tq::F_TILE_BYTES;
         const unsigned char* zb = zstash + (size_t)tile * tq::Z_TILE_BYTES;
         for (int k = 0; k < dw::pass_nops(pass); ++k) {
           const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
           const uint32_t a_bytes = (uint32_t)src.a_rows * 128u, b_bytes = (uint32_t)src.b_rows * 128u;
-          for (int p = 0; p < tq::NPANEL; ++p) {
+          for (int p = p_lo(j); p < p_hi(j); ++p) {
             const int r = rc.r;
             dwq_wait(smem_u32(&s_bars.rfree[r]), rc.parity(), abort_flag);
             rc.next(nr);
@@ -278,7 +290,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
           const dw::Op op = dw::op_of(dw::pass_op(pass, k));
           const uint32_t idesc = tc::idesc_tf32(128, op.N);
           const uint32_t d = tmem + op.d_col;
-          for (int p = 0; p < tq::NPANEL; ++p, ++u) {
+          for (int p = p_lo(j); p < p_hi(j); ++p, ++u) {
             const int r = rc.r, sl = u % NS;
             rc.next(nr);
             // only the issuing lane polls: a barrier of a short ring can complete AGAIN as soon as this unit's MMAs
@@ -292,7 +304,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
             uint32_t br = ((raw0 + (uint32_t)(r * sbytes + boff)) >> 4) | (1u << 16);
             uint32_t bl = ((lo0 + (uint32_t)sl * tq::DW_B_BYTES) >> 4) | (1u << 16);
             const uint32_t a_hi = tmem + dw::C_ARING + sl * 64, a_lo = a_hi + 32;
-            const bool clear = (j == 0) && op.first && (p == 0);
+            const bool clear = (j == 0) && op.first && (p == p_lo(0));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks, br += 2, bl += 2) {
               const uint64_t dbh = DESC_HI | br, dbl = DESC_HI | bl;
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
         const bool warp_active = q * 32 < src.a_rows + (src.ones >= 0 ? 1 : 0);
         const bool has_row = row < src.a_rows;
         const uint32_t fill = (row == src.ones) ? 0x3f800000u : 0u;       // constant ones row of a bias gradient
-        for (int p = 0; p < tq::NPANEL; ++p, ++u) {
+        for (int p = p_lo(j); p < p_hi(j); ++p, ++u) {
           const int r = rc.r, sl = u % NS;
           const uint32_t full_parity = rc.parity();
           rc.next(nr);
@@ -402,7 +414,7 @@ __global__ void __launch_bounds__(DWQ_THREADS, 1)
       for (int k = 0; k < dw::pass_nops(pass); ++k) {
         const tq::DwSrc src = tq::dw_src(dw::pass_op(pass, k));
         const int nb = src.b_rows * 8;                       // 16-byte chunks (320 or 512: a multiple of 32)
-        for (int p = 0; p < tq::NPANEL; ++p, ++u) {
+        for (int p = p_lo(j); p < p_hi(j); ++p, ++u) {
           const int r = rc.r, sl = u % NS;
           const uint32_t full_parity = rc.parity();
           rc.next(nr);
