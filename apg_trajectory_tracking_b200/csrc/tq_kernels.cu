@@ -138,6 +138,9 @@ __device__ __forceinline__ SetPtr set_ptr(unsigned char* tile_block, int o_rows,
   return sp;
 }
 __device__ __forceinline__ void set_store(const SetPtr& sp, int r, float v) {
+#ifdef TQ_PROBE_NO_STASH      // timing experiment: what do the stash stores of the chain epilogues cost (wrong results)
+  if (v == 1.2345e-33f)
+#endif
   *reinterpret_cast<float*>(sp.p[r & 7] + r * 128) = v;
 }
 __device__ __forceinline__ float set_load(const SetPtr& sp, int r) {
@@ -156,23 +159,57 @@ __device__ __forceinline__ void a_operand_ready(uint32_t bar) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) tcp::mbar_arrive(bar);
 }
+// NF consecutive floats of ONE drone's row (p: 8-byte aligned, no more) into registers with as few load instructions
+// as alignment allows.  The rows of the per-drone tensors are 360 bytes apart, so the 32 lanes of a warp touch 32
+// different cache lines with EVERY load instruction, and at one tag look-up per line and cycle it is the NUMBER of load
+// instructions that costs (measured, profiles/r2: with the window loads replaced by constants the forward chain takes
+// 65.7 instead of 83.4 us).  Lanes whose address is 16-byte aligned read float4s from p; the others a float2 head, float4s
+// from p + 8 and a float2 tail: NF / 4 + 3 instructions per warp (two of them for half the lanes) instead of NF / 2.
+// NF is a multiple of 4; exactly the bytes [p, p + 4 NF) are read.
+template <int NF>
+__device__ __forceinline__ void load_segment(float* out, const float* p, bool live) {
+  static_assert(NF % 4 == 0 && NF >= 8, "segment length");
+  constexpr int M = NF / 4 - 1;                               // float4 loads every lane makes
+  const bool odd = (reinterpret_cast<uintptr_t>(p) & 8u) != 0;
+  const float4* q = reinterpret_cast<const float4*>(p + (odd ? 2 : 0));
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float2 z2 = make_float2(0.f, 0.f);
+  const float2 head = (live && odd) ? *reinterpret_cast<const float2*>(p) : z2;
+  float4 v[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) v[i] = live ? q[i] : z4;
+  const float4 t4 = (live && !odd) ? q[M] : z4;
+  const float2 t2 = (live && odd) ? *reinterpret_cast<const float2*>(p + NF - 2) : z2;
+  float e[NF], o[NF];                                         // the stream as an aligned / a shifted lane sees it
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    e[4 * i] = v[i].x; e[4 * i + 1] = v[i].y; e[4 * i + 2] = v[i].z; e[4 * i + 3] = v[i].w;
+    o[4 * i + 2] = v[i].x; o[4 * i + 3] = v[i].y; o[4 * i + 4] = v[i].z; o[4 * i + 5] = v[i].w;
+  }
+  e[4 * M] = t4.x; e[4 * M + 1] = t4.y; e[4 * M + 2] = t4.z; e[4 * M + 3] = t4.w;
+  o[0] = head.x; o[1] = head.y; o[NF - 2] = t2.x; o[NF - 1] = t2.y;
+#pragma unroll
+  for (int k = 0; k < NF; ++k) out[k] = odd ? o[k] : e[k];
+}
+
 // element K (compile-time, = row * 9 + c) of a window of the policy's reference input, built from the RAW reference
 // rows of one drone starting at `rows` (QuadDataset.prepare_data, dataset.py:170-201):
 // [ref_pos - pos | ref_vel | ref_vel - vel] per row
-template <int K>
-__device__ __forceinline__ float raw_in_ref(const float* rows, const float (&pos)[3], const float (&vel)[3], bool live) {
+// `seg` holds the raw floats [S0, ...) of the window's rows in registers (load_segment)
+template <int K, int S0>
+__device__ __forceinline__ float raw_in_ref(const float* seg, const float (&pos)[3], const float (&vel)[3], bool live) {
   constexpr int r = K / 9, c = K % 9;
   if (!live) return 0.f;
-  if (c < 3) return rows[9 * r + c] - pos[c];
-  if (c < 6) return rows[9 * r + 6 + (c - 3)];
-  return rows[9 * r + 6 + (c - 6)] - vel[c - 6];
+  if (c < 3) return seg[9 * r + c - S0] - pos[c];
+  if (c < 6) return seg[9 * r + 6 + (c - 3) - S0];
+  return seg[9 * r + 6 + (c - 6) - S0] - vel[c - 6];
 }
-template <int K0, int N, int I = 0>
-__device__ __forceinline__ void raw_window(float* x, const float* rows, const float (&pos)[3], const float (&vel)[3],
+template <int K0, int N, int S0, int I = 0>
+__device__ __forceinline__ void raw_window(float* x, const float* seg, const float (&pos)[3], const float (&vel)[3],
                                            bool live) {
   if constexpr (I < N) {
-    x[I] = raw_in_ref<K0 + I>(rows, pos, vel, live);
-    raw_window<K0, N, I + 1>(x, rows, pos, vel, live);
+    x[I] = raw_in_ref<K0 + I, S0>(seg, pos, vel, live);
+    raw_window<K0, N, S0, I + 1>(x, seg, pos, vel, live);
   }
 }
 // L2 prefetch of the 128-byte lines [first, first + nlines) of a contiguous region, spread over the lanes of a warp
@@ -467,16 +504,19 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
         const SetPtr sp_w = set_ptr(tb, tq::O_WIN + tq::R_WIN * gq, tq::R_WIN, row);
         if (hf == 0) {
           float x[24];
-          if (RAW) {
-            raw_window<0, 24>(x, g.ref + drone * REFW + 18 * gq, cpos, cvel, live);
-          } else {
+#ifdef TQ_PROBE_NO_WINLOAD    // timing experiment: what do the per-drone strided window loads cost (wrong results)
 #pragma unroll
-            for (int k = 0; k < 24; k += 2) {
-              const float2 tt = live ? *(const float2*)(rr + 18 * gq + k) : make_float2(0.f, 0.f);
-              x[k] = tt.x;
-              x[k + 1] = tt.y;
-            }
+          for (int k = 0; k < 24; ++k) x[k] = 0.01f * k;
+#else
+          if (RAW) {
+            // window elements [0, 24) = rows 2gq, 2gq + 1 and (pos, vel) of row 2gq + 2: raw floats [0, 27) of the window
+            float seg[28];
+            load_segment<28>(seg, g.ref + drone * REFW + 18 * gq, live);
+            raw_window<0, 24, 0>(x, seg, cpos, cvel, live);
+          } else {
+            load_segment<24>(x, rr + 18 * gq, live);
           }
+#endif
           wait_d();      // op 1 (gq = 0) or the fc1 piece of the previous pair: the A columns are free again
           a_store<24>(ahi, alo, x);
           a_operand_ready(bar_a);
@@ -484,16 +524,19 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
           for (int k = 0; k < 24; ++k) set_store(sp_w, k, x[k]);
         } else {
           float x[16];
-          if (RAW) {
-            raw_window<24, 12>(x, g.ref + drone * REFW + 18 * gq, cpos, cvel, live);
-          } else {
+#ifdef TQ_PROBE_NO_WINLOAD
 #pragma unroll
-            for (int k = 0; k < 12; k += 2) {
-              const float2 tt = live ? *(const float2*)(rr + 18 * gq + 24 + k) : make_float2(0.f, 0.f);
-              x[k] = tt.x;
-              x[k + 1] = tt.y;
-            }
+          for (int k = 0; k < 12; ++k) x[k] = 0.01f * k;
+#else
+          if (RAW) {
+            // window elements [24, 36) = the velocity differences of row 2gq + 2 and row 2gq + 3: raw floats [24, 36)
+            float seg[12];
+            load_segment<12>(seg, g.ref + drone * REFW + 18 * gq + 24, live);
+            raw_window<24, 12, 24>(x, seg, cpos, cvel, live);
+          } else {
+            load_segment<12>(x, rr + 18 * gq + 24, live);
           }
+#endif
           x[12] = live ? 1.f : 0.f;
           x[13] = x[14] = x[15] = 0.f;
           wait_d();
