@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
       for (int gq = 0; gq < 4; ++gq) {
         // window of position pair gq: in_ref rows 2gq .. 2gq+3 (36 values) | 1 (ones row of the conv weight
         // gradient; its image column is 0) | 0 0 0; this thread's columns [0,24) or [24,40)
-        // (measured: issuing the loads of window gq + 1 one hand-off early costs more in spills than it hides)
+        // (measured twice: issuing the loads of window gq + 1 one hand-off early - even with the conv epilogue cut into
+        // 8-column pieces to make room for them - is slower, 86.9 against 81.8 us: profiles/r2/window_prefetch_variant.log)
         const SetPtr sp_w = set_ptr(tb, tq::O_WIN + tq::R_WIN * gq, tq::R_WIN, row);
         if (hf == 0) {
           float x[24];

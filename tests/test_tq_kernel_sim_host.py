@@ -26,7 +26,9 @@ H = 10
 def sim(tmp_path_factory):
     tmp = tmp_path_factory.mktemp("hostcheck_tqsim")
     out = tmp / "libhostcheck_tqsim.so"
-    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++",
+    # APG_SIM_DEFINES="-DX -DY": build variants of the kernels (e.g. -DTQ_WIN_PREFETCH) on the model
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++20", "-pthread", "-ffp-contract=off", "-x", "c++"] +
+                          os.environ.get("APG_SIM_DEFINES", "").split() + [
                            "-I", os.path.join(ROOT, "apg_trajectory_tracking_b200", "csrc"),
                            os.path.join(ROOT, "tests", "hostcheck", "hostcheck_tqsim.cpp"), "-o", str(out)])
     return ctypes.CDLL(str(out))
