@@ -3,7 +3,7 @@
 # the other workloads
 set -u
 cd "$(dirname "$0")/.."
-out=gpurun_out/r2_final4
+out=gpurun_out/r2_final5
 mkdir -p "$out"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > "$out/smoke.log" 2>&1
 echo "exit=$?" >> "$out/smoke.log"
