@@ -586,6 +586,55 @@ def test_rollout_through_learnt_dynamics_fused_vs_oracle(n):
     assert rel_err(g_raw, g_prep) <= 1e-4
 
 
+def test_rollout_through_learnt_dynamics_full_size_properties():
+    """BASELINE size (N = 65536, h = 10) through the learnt steps: run-to-run bitwise determinism, additivity of loss and
+    gradient over a partition of the drones, and a 256-drone sample of the SAME batch against the oracle (loss, states,
+    actions, policy gradient)"""
+    import bench as B
+    from oracle import apg_oracle as O
+    PR, R, SY, T, DS = _mods()
+    g = load_golden("learnt_dyn.npz")
+    d = _learnt_module(g, "b")
+    lparams = [p.detach().cpu().clone() for _, p in d.named_parameters()]
+    cfg = dict(O.QUAD_CFG, rotational_drag=tuple(float(x) for x in g["b_rot_drag"]))
+    n, h, dt = 65536, 10, 0.1
+    params = B.default_init("quad", h, seed=6)
+    case = {k: v.cuda() for k, v in SY.quad_case(n, h, dt, seed=6).items()}
+    flat, lflat = R.flatten_params(params).cuda(), d._flat().detach()
+    spec = R.RolloutSpec.quad_concurrent(h, dt, modified_params=dict(d.cfg))
+
+    def run(sl):
+        r = R.Rollout(spec, case["cur"][sl].shape[0], "cuda:0")
+        loss, st, ac = r.forward(flat, case["in_state"][sl].contiguous(), case["cur"][sl].contiguous(),
+                                 case["in_ref"][sl].contiguous(), case["ref"][sl].contiguous(), want_states=True,
+                                 want_actions=True, learnt_params=lflat)
+        loss = float(loss.item())
+        return loss, st.cpu(), ac.cpu(), r.backward(1.0).cpu()
+    full = run(slice(0, n))
+    again = run(slice(0, n))
+    assert full[0] == again[0] and torch.equal(full[3], again[3])
+    cut = 40000
+    a, b = run(slice(0, cut)), run(slice(cut, n))
+    assert abs(a[0] + b[0] - full[0]) <= 2e-5 * abs(full[0])
+    assert rel_err(a[3] + b[3], full[3]) <= 2e-5
+    idx = torch.arange(0, n, n // 256)
+    sub = {k: v[idx.cuda()].contiguous() for k, v in case.items()}
+    r = R.Rollout(spec, len(idx), "cuda:0")
+    ls, st, ac = r.forward(flat, sub["in_state"], sub["cur"], sub["in_ref"], sub["ref"], want_states=True,
+                           want_actions=True, learnt_params=lflat)
+    ls = float(ls.item())
+    gs = r.backward(1.0).cpu()
+    want = O.value_and_grad(lambda ps: O.rollout_concurrent_learnt(ps, lparams, sub["in_state"].cpu(), sub["cur"].cpu(),
+                                                                   sub["in_ref"].cpu(), sub["ref"].cpu(), h, dt, cfg),
+                            params)
+    assert abs(ls - float(want[0])) <= 2e-5 * abs(float(want[0]))
+    assert _close(st, want[2], 2e-5) and _close(ac, want[3], 2e-5)
+    assert torch.equal(st.cpu(), full[1][idx]) and torch.equal(ac.cpu(), full[2][idx])     # same drones, same bits
+    for got, w in zip(R.split_flat(gs, params), want[1]):
+        if w is not None:
+            assert rel_err(got, w) <= 1e-4
+
+
 def test_learnt_controller_epoch_fused_vs_oracle_training():
     """TrainDrone.run_epoch with train_dynamics = LearntDynamics (golden variant b): the FUSED rollout through the learnt
     steps + SGD, two epochs of four mini-batches, against the same training on the oracle; the un-fused per-step loop
