@@ -22,15 +22,23 @@ __device__ __forceinline__ float dyn_forward_conc(const float* __restrict__ act,
                                                   float* __restrict__ actions_out) {
   using Sys = SysT<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
-  float s[S], s0[S], sn[S], a[A], rf[R > 0 ? R : 1];
+  float s[S], s0[S], sn[S], a[A], rf[R > 0 ? R : 1], rf_next[R > 0 ? R : 1];
 #pragma unroll
   for (int i = 0; i < S; ++i) s0[i] = s[i] = cur_g[i];
+#pragma unroll
+  for (int c = 0; c < R; ++c) rf_next[c] = ref_g[c];
   float loss = 0.f;
   for (int k = 0; k < h; ++k) {
 #pragma unroll
     for (int c = 0; c < A; ++c) a[c] = act[(k * A + c) * TMP + d];
+    // the reference row of step k + 1 is requested now: the h steps of a drone are one dependent chain on two warps per
+    // CTA, and a global load issued where it is needed adds its whole latency to every link of that chain
 #pragma unroll
-    for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
+    for (int c = 0; c < R; ++c) rf[c] = rf_next[c];
+    if (k + 1 < h) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) rf_next[c] = ref_g[(k + 1) * R + c];
+    }
     Sys::step(s, a, dt, pc, sn);
     loss += Sys::loss(sn, rf, a, s0, k, h);
 #pragma unroll
@@ -59,22 +67,35 @@ __device__ __forceinline__ void dyn_adjoint_conc(const float* __restrict__ st_ac
   using Sys = SysT<float>;
   constexpr int S = Sys::S, A = Sys::A, R = Sys::REFW;
   float s0[S], sk[S], sn[S], a[A], rf[R > 0 ? R : 1], g[S], gs[S], ga[A], ga2[A];
+  float a_nx[A], rf_nx[R > 0 ? R : 1], sk_nx[S];         // operands of the NEXT (earlier) step, requested one step ahead
 #pragma unroll
   for (int i = 0; i < S; ++i) { s0[i] = cur_g[i]; g[i] = 0.f; }
 #pragma unroll
   for (int i = 0; i < S; ++i) sn[i] = st_states[((h - 1) * S + i) * TMP + d];
-  for (int k = h - 1; k >= 0; --k) {
+  auto request = [&](int k) {                             // stashed action, reference row and state BEFORE step k
 #pragma unroll
-    for (int c = 0; c < A; ++c) { a[c] = st_act[(k * A + c) * TMP + d]; ga[c] = 0.f; }
+    for (int c = 0; c < A; ++c) a_nx[c] = st_act[(k * A + c) * TMP + d];
 #pragma unroll
-    for (int c = 0; c < R; ++c) rf[c] = ref_g[k * R + c];
+    for (int c = 0; c < R; ++c) rf_nx[c] = ref_g[k * R + c];
     if (k > 0) {
 #pragma unroll
-      for (int i = 0; i < S; ++i) sk[i] = st_states[((k - 1) * S + i) * TMP + d];
+      for (int i = 0; i < S; ++i) sk_nx[i] = st_states[((k - 1) * S + i) * TMP + d];
     } else {
 #pragma unroll
-      for (int i = 0; i < S; ++i) sk[i] = s0[i];
+      for (int i = 0; i < S; ++i) sk_nx[i] = s0[i];
     }
+  };
+  request(h - 1);
+  for (int k = h - 1; k >= 0; --k) {
+#pragma unroll
+    for (int c = 0; c < A; ++c) { a[c] = a_nx[c]; ga[c] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < R; ++c) rf[c] = rf_nx[c];
+#pragma unroll
+    for (int i = 0; i < S; ++i) sk[i] = sk_nx[i];
+    // (the reverse sweep of a drone is one dependent chain on two warps per CTA: loads issued where they are needed
+    // add their whole latency to every link of it)
+    if (k > 0) request(k - 1);
     Sys::loss_grad(sn, rf, a, s0, k, h, g, ga);          // g += dl_k/ds_{k+1}, ga += dl_k/da_k
     Sys::step_adj(sk, a, dt, pc, g, gs, ga2);             // through the step
 #pragma unroll
