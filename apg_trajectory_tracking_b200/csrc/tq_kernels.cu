@@ -661,7 +661,10 @@ __global__ void __launch_bounds__(TQ_DYN_THREADS, LEARNT ? 4 : 7)
     __syncthreads();
   }
   // the horizon loops are NOT unrolled (measured: the unrolled body thrashed the instruction cache, 6 of 10 issue
-  // slots lost to instruction fetch); actions / logit gradients go straight from / to the stash sets per step
+  // slots lost to instruction fetch); actions / logit gradients go straight from / to the stash sets per step.
+  // (Requesting the next step's action / reference row one step ahead in registers - what pays in the two-warp dynamics
+  // groups of the tile-engine kernels, dyn_phase.cuh - is slower here, 52.3 against 50.1 us: this kernel runs 14 warps
+  // per SM and is bound by issue slots, not by the latency of its L2 hits; profiles/r2/tq_dyn_prefetch_variant.log)
   for (int hb = blockIdx.x; hb < nhalf; hb += gridDim.x) {
     const int tile = hb / (TMT / TD), row = (hb % (TMT / TD)) * TD + tx;
     const uint32_t c4 = ((uint32_t)(row & 31) >> 2) << 4;     // this thread's 16-byte chunk, before the row XOR
