@@ -253,7 +253,7 @@ def test_evaluation_with_the_lstm_policy_through_the_c_abi(simlib):
     spec = R.RolloutSpec.quad_recurrent("lstm", 10, 0.1)
     for name in ("gentle", "fast_stop", "loose"):
         steps, test_time, tdiv, tstab, h, dt = [float(x) for x in g[f"{name}_cfg"]]
-        steps = min(int(steps), 25)                      # (the CPU model runs one OS thread per GPU thread)
+        steps = min(int(steps), 14)                      # (the CPU model runs one OS thread per GPU thread)
         taken = min(len(g[f"{name}_div"]), steps)
         ev = EV.TableEvaluator(spec, 1, "cpu")
         h0c0 = torch.tensor(np.stack([g[f"{name}_h0"], g[f"{name}_c0"]]))
@@ -267,7 +267,7 @@ def test_evaluation_with_the_lstm_policy_through_the_c_abi(simlib):
         if taken == len(g[f"{name}_div"]):
             assert np.abs(out["hc"][0, 0].numpy() - g[f"{name}_h1"][0]).max() <= 1e-4
             assert np.abs(out["hc"][1, 0].numpy() - g[f"{name}_c1"][0]).max() <= 1e-4
-    n, steps = 70, 8                                     # two tiles, the second ragged; shared tables through the index
+    n, steps = 70, 5                                     # two tiles, the second ragged; shared tables through the index
     tabs = torch.tensor(np.stack([g["gentle_table"][:100], g["loose_table"][:100]]), dtype=torch.float32)
     gen = torch.Generator().manual_seed(5)
     index = torch.randint(0, 2, (n,), generator=gen, dtype=torch.int32)
