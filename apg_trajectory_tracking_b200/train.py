@@ -280,7 +280,8 @@ class FusedTrainStep:
         st["graph_loss_host"].copy_(loss, non_blocking=True)
 
     def replay_host(self):
-        """one captured ``step_host`` (see ``capture_host``); returns a ``HostLoss`` (``item()`` waits for the step)"""
+        """one captured ``step_host`` (see ``capture_host``); returns a ``HostLoss`` (``item()`` waits for the step).
+        Every replay writes its loss into the same pinned scalar: read a handle before the next replay."""
         self._hgraph.replay()
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
